@@ -1,0 +1,146 @@
+/*
+ * bg_b200.h -- C ABI of libbg_b200.so: the B200 (sm_100a) batched backgammon engine.
+ *
+ * Drop-in boundary for ONE hot path of Nick-qsv/MLP-PPO-2PLY-P3 (all-Python reference, no FFI of
+ * its own): the functions below are what a ctypes/cffi binding on the reference side calls in place
+ * of its per-game Python objects (INTEGRATION.md shows the stub).  Paths cite /root/reference/src.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch allocates), unless named host_*;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream), allocates nothing and never synchronises the host;
+ *   - return value: BG_OK (0) or a negative BG_ERR_* code; bg_last_error() gives the message of the
+ *     calling thread's last failure.  Data-dependent conditions (bad board, scratch/output overflow)
+ *     cannot be returned synchronously: kernels OR them into the caller's device `status` word
+ *     (BG_STATUS_*), which the caller reads when it next synchronises.  Nothing is dropped silently.
+ *   - position layout "board52": int8[52] = [P1 points 0..23][P2 points 0..23][bar1 bar2 off1 off2],
+ *     i.e. rows 0,1 and the used cells of rows 2,3 of the reference's (4,24) int8 tensor
+ *     (board/immutable_board.py:20-27).  Counts must be 0..15.
+ *   - players: int8, 0 = PLAYER1 (moves 0->23), 1 = PLAYER2 (moves 23->0)  (players/player.py:6-12).
+ *   - dice: int8[2] per position, 1..6, any order (moves/get_all_moves.py:28-30 sorts internally).
+ */
+#ifndef BG_B200_H
+#define BG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BG_OK 0
+#define BG_ERR_INVALID (-1)   /* bad argument (null pointer, negative size, workspace too small) */
+#define BG_ERR_CUDA (-2)      /* CUDA runtime error at launch; see bg_last_error() */
+
+#define BG_STATUS_BAD_INPUT 1         /* a board had a count outside 0..15 or dice outside 1..6 */
+#define BG_STATUS_SCRATCH_OVERFLOW 2  /* a position produced more boards per level than BG_MOVEGEN_CAP_BIG */
+#define BG_STATUS_OUTPUT_OVERFLOW 4   /* the afterstate buffer was too small; affected counts are 0 */
+#define BG_STATUS_DICE_EXHAUSTED 8    /* an external dice stream ran out */
+
+#define BG_FEATURES 198               /* board/immutable_board.py:171-212 */
+#define BG_BOARD_BYTES 52
+#define BG_HIDDEN 128                 /* agent/config.py HIDDEN_SIZE, agent/policy_network.py:44 */
+#define BG_FEAT_LD_BF16 208           /* 198 padded to a multiple of 16 (one tcgen05 K step) */
+
+const char* bg_last_error(void);
+int bg_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  legal-move generation.  Replaces get_all_possible_moves (moves/get_all_moves.py:9-94) and
+ * everything below it (moves/handle_moves.py:109-341, moves/move_logic.py:20-275,
+ * moves/conditions.py:7-147, board/immutable_board.py:42-89,236-246) for B positions at once.
+ * Afterstates of a position are emitted in the reference's legal_moves order, so index k here is
+ * action k of the reference env (environment/backgammon_env.py:152).
+ *
+ * workspace: bg_movegen_workspace_bytes(B) bytes of device scratch (contents undefined).
+ * counts_true[b] = number of legal plays (never truncated; -1 if the position was rejected).
+ */
+size_t bg_movegen_workspace_bytes(long long B);
+
+/* pass 1 of the deterministic two-pass form: counts only */
+int bg_movegen_count(const int8_t* boards52, const int8_t* players, const int8_t* dice, long long B,
+                     int32_t* counts_true, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* pass 2: rows of position b are written at afterstates52 + 52*offsets[b] (offsets = exclusive scan
+ * of min(counts_true, max_rows_per_board) computed by the caller; max_rows_per_board 0 = uncapped). */
+int bg_movegen_write(const int8_t* boards52, const int8_t* players, const int8_t* dice, long long B,
+                     const long long* offsets, int max_rows_per_board, int8_t* afterstates52,
+                     long long afterstate_capacity_rows, int32_t* counts_true /*nullable*/, int32_t* counts /*nullable*/,
+                     int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* single-pass form used by the env: every warp reserves its rows with one atomicAdd on *alloc_rows
+ * (caller zeroes it); starts[b] receives the first row.  Row blocks of different positions are in
+ * arbitrary order, rows inside a block are in reference order.  counts[b] = min(true, max_rows). */
+int bg_movegen_slab(const int8_t* boards52, const int8_t* players, const int8_t* dice, long long B,
+                    int max_rows_per_board, int8_t* afterstates52, long long afterstate_capacity_rows,
+                    int32_t* counts_true /*nullable*/, int32_t* counts, long long* starts,
+                    unsigned long long* alloc_rows, int32_t* status, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  feature encoding.  Replaces get_board_features_batch_from_tensors (ai/batching.py:78-147) ==
+ * ImmutableBoard.get_board_features (board/immutable_board.py:171-212).  flags[b] = player whose
+ * turn flag is set (features 196/197); for afterstates that is the MOVER (ai/batching.py:72-74).
+ * If flags == NULL, `seg_flags`/`seg_of_row` are not used and flag_all (0/1) applies to every row.
+ */
+int bg_encode_f32(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
+                  float* out, long long ld /* >= 198, in floats */, void* stream);
+/* bf16 rows, ld >= 198 elements and a multiple of 8; columns 198..ld-1 are written as zeros. */
+int bg_encode_bf16(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
+                   uint16_t* out, long long ld, void* stream);
+/* ragged form for afterstate blocks: row r of block b (rows starts[b] .. starts[b]+counts[b]) gets
+ * flag players[b].  row_owner is device scratch of `rows_capacity` int32 filled by the call. */
+int bg_fill_row_flags(const long long* starts, const int32_t* counts, const int8_t* players, long long B,
+                      int8_t* row_flags, long long rows_capacity, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  fused step / reward / terminal / auto-reset / dice.  Replaces BackgammonEnv.step/reset/
+ * roll_dice/pass_turn/check_for_gammon/check_for_backgammon (environment/backgammon_env.py:78-191,
+ * 245-251,365-405) and the auto-reset of VectorizedBackgammonEnv.step (environment/vec_bg_env.py:28-49)
+ * for N games.  Legal-move lists are NOT produced here: call bg_movegen_slab on (boards, players,
+ * dice) afterwards (that is update_legal_moves, backgammon_env.py:198-243).
+ */
+typedef struct bg_env_state {
+    long long n_games;
+    int8_t* boards52;        /* [N][52]  current positions */
+    int8_t* players;         /* [N]      player to move */
+    int8_t* dice;            /* [N][2]   current roll, as rolled */
+    int32_t* scores;         /* [N][2]   match points of PLAYER1/PLAYER2 (backgammon_env.py:42-45) */
+    uint32_t* draws;         /* [N]      dice draws consumed by the game slot's stream */
+    int8_t* match_over;      /* [N]      set when a match ended; cleared (with scores) by the next reset */
+    /* legal plays of the current positions (output of bg_movegen_slab) */
+    const int8_t* afterstates52;
+    const long long* starts; /* [N] */
+    const int32_t* counts;   /* [N] min(true count, max_legal_moves) */
+    /* dice source: Philox4x32-10 keyed by seed, counter (stream_base + game index, draw); or, if
+     * ext_dice != NULL, ext_dice[g][draw][2] with ext_len draws per game. */
+    unsigned long long seed;
+    unsigned long long stream_base;
+    const int8_t* ext_dice;
+    long long ext_len;
+    int32_t match_length;
+} bg_env_state;
+
+typedef struct bg_step_out {
+    float* rewards;          /* [N]  -1 invalid, 0, 1 / 1.5 / 2 (backgammon_env.py:23-28) */
+    uint8_t* dones;          /* [N] */
+    int8_t* info_player;     /* [N] player to move at entry (info["current_player"], :117) */
+    int8_t* winner;          /* [N] -1 = none */
+    int8_t* game_score;      /* [N] 0, 1, 2, 3 */
+    uint8_t* flags;          /* [N] bit0 passed, bit1 invalid action */
+} bg_step_out;
+
+/* reset all games (mask == NULL) or those with mask[g] != 0: initial position + opening protocol
+ * (backgammon_env.py:78-113). */
+int bg_env_reset(const bg_env_state* st, const uint8_t* mask, int32_t* status, void* stream);
+/* one step of every game with actions[g] (int32 index into its legal plays; ignored on a pass). */
+int bg_env_step(const bg_env_state* st, const int32_t* actions, const bg_step_out* out, int32_t* status, void* stream);
+/* uniform random policy: actions[g] = mulhi(Philox(seed, stream_base+g, t; "ACT1"), counts[g]) (0 if none). */
+int bg_random_actions(const int32_t* counts, long long N, unsigned long long seed, unsigned long long stream_base,
+                      uint32_t t, int32_t* actions, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BG_B200_H */
