@@ -66,15 +66,16 @@ int bg_movegen_count(const int8_t* boards52, const int8_t* players, const int8_t
  * of min(counts_true, max_rows_per_board) computed by the caller; max_rows_per_board 0 = uncapped). */
 int bg_movegen_write(const int8_t* boards52, const int8_t* players, const int8_t* dice, long long B,
                      const long long* offsets, int max_rows_per_board, int8_t* afterstates52,
-                     long long afterstate_capacity_rows, int32_t* counts_true /*nullable*/, int32_t* counts /*nullable*/,
-                     int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+                     long long afterstate_capacity_rows, int8_t* row_players /*nullable: mover of each row*/,
+                     int32_t* counts_true /*nullable*/, int32_t* counts /*nullable*/, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
 /* single-pass form used by the env: every warp reserves its rows with one atomicAdd on *alloc_rows
  * (caller zeroes it); starts[b] receives the first row.  Row blocks of different positions are in
  * arbitrary order, rows inside a block are in reference order.  counts[b] = min(true, max_rows). */
 int bg_movegen_slab(const int8_t* boards52, const int8_t* players, const int8_t* dice, long long B,
                     int max_rows_per_board, int8_t* afterstates52, long long afterstate_capacity_rows,
-                    int32_t* counts_true /*nullable*/, int32_t* counts, long long* starts,
+                    int8_t* row_players /*nullable*/, int32_t* counts_true /*nullable*/, int32_t* counts,
+                    long long* starts,
                     unsigned long long* alloc_rows, int32_t* status, void* workspace, size_t workspace_bytes,
                     void* stream);
 
@@ -82,17 +83,14 @@ int bg_movegen_slab(const int8_t* boards52, const int8_t* players, const int8_t*
  * K3  feature encoding.  Replaces get_board_features_batch_from_tensors (ai/batching.py:78-147) ==
  * ImmutableBoard.get_board_features (board/immutable_board.py:171-212).  flags[b] = player whose
  * turn flag is set (features 196/197); for afterstates that is the MOVER (ai/batching.py:72-74).
- * If flags == NULL, `seg_flags`/`seg_of_row` are not used and flag_all (0/1) applies to every row.
+ * If flags == NULL, flag_all (0/1) applies to every row.  (K1's row_players output is the flags
+ * array of a ragged afterstate buffer.)
  */
 int bg_encode_f32(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
                   float* out, long long ld /* >= 198, in floats */, void* stream);
 /* bf16 rows, ld >= 198 elements and a multiple of 8; columns 198..ld-1 are written as zeros. */
 int bg_encode_bf16(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
                    uint16_t* out, long long ld, void* stream);
-/* ragged form for afterstate blocks: row r of block b (rows starts[b] .. starts[b]+counts[b]) gets
- * flag players[b].  row_owner is device scratch of `rows_capacity` int32 filled by the call. */
-int bg_fill_row_flags(const long long* starts, const int32_t* counts, const int8_t* players, long long B,
-                      int8_t* row_flags, long long rows_capacity, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2  fused step / reward / terminal / auto-reset / dice.  Replaces BackgammonEnv.step/reset/

@@ -15,6 +15,18 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+// The rule functions are __host__ __device__ so that tests/host_emul can run the very same code on the CPU.
+#define BG_HD __host__ __device__ __forceinline__
+#ifdef __CUDA_ARCH__
+#define BG_FFS(x) __ffs((int)(x))
+#define BG_CLZ(x) __clz((int)(x))
+#define BG_POPC(x) __popc(x)
+#else
+#define BG_FFS(x) __builtin_ffs((int)(x))
+#define BG_CLZ(x) ((x) ? __builtin_clz((unsigned)(x)) : 32)
+#define BG_POPC(x) __builtin_popcount((unsigned)(x))
+#endif
+
 namespace bg {
 
 constexpr int kBoardBytes = 52;
@@ -38,9 +50,9 @@ struct Root {
     int tot15;        // own points + bar + off == 15 (needed by all_checkers_home, conditions.py:147)
 };
 
-__device__ __forceinline__ int node_bar(const Node& n) { return (int)((n.hi >> 32) & 15ull); }
-__device__ __forceinline__ int node_off(const Node& n) { return (int)((n.hi >> 36) & 15ull); }
-__device__ __forceinline__ int node_count(const Node& n, int p) {
+BG_HD int node_bar(const Node& n) { return (int)((n.hi >> 32) & 15ull); }
+BG_HD int node_off(const Node& n) { return (int)((n.hi >> 36) & 15ull); }
+BG_HD int node_count(const Node& n, int p) {
     return p < 16 ? (int)((n.lo >> (4 * p)) & 15ull) : (int)((n.hi >> (4 * (p - 16))) & 15ull);
 }
 
@@ -49,7 +61,7 @@ __device__ __forceinline__ int node_count(const Node& n, int p) {
 // List order of the reference = ascending source point, then the bear-off move
 // (get_moves_normal move_logic.py:47-92, get_moves_bar :95-137, get_moves_bear_off :140-255,
 //  compute_board_state :258-275).
-__device__ __forceinline__ void one_die(const Node& n, const Root& R, int d, uint32_t& mask, int& special) {
+BG_HD void one_die(const Node& n, const Root& R, int d, uint32_t& mask, int& special) {
     mask = 0; special = -1;
     if (node_off(n) == 15) return;                                   // GAME_OVER (conditions.py:96-108)
     if (node_bar(n) > 0) {                                           // ON_BAR
@@ -62,26 +74,26 @@ __device__ __forceinline__ void one_die(const Node& n, const Root& R, int d, uin
     const uint32_t home = R.player == 0 ? 0xFC0000u : 0x00003Fu;     // conditions.py:123-126
     if (R.tot15 && (n.occ & ~home) == 0 && n.occ != 0) {             // BEAR_OFF (all_checkers_home)
         if (R.player == 0) {
-            int last = __ffs(n.occ) - 1;                             // farthest from exit, move_logic.py:196-201
+            int last = BG_FFS(n.occ) - 1;                             // farthest from exit, move_logic.py:196-201
             if (last + d >= 24) special = last;                      // :212-218
             else if ((n.occ >> (24 - d)) & 1u) special = 24 - d;     // :221-231
         } else {
-            int last = 31 - __clz(n.occ);                            // :202-207
+            int last = 31 - BG_CLZ(n.occ);                            // :202-207
             if (last - d < 0) special = last;                        // :234-240
             else if ((n.occ >> (d - 1)) & 1u) special = d - 1;       // :243-253
         }
     }
 }
 
-__device__ __forceinline__ int nth_set_bit(uint32_t m, int j) {
+BG_HD int nth_set_bit(uint32_t m, int j) {
     for (int k = 0; k < j; ++k) m &= m - 1u;
-    return __ffs(m) - 1;
+    return BG_FFS(m) - 1;
 }
 
 // Apply move number j of the (mask, special) list with die d  (move_checker, immutable_board.py:42-89).
-__device__ __forceinline__ Node apply_move(const Node& n, const Root& R, int d, uint32_t mask, int special, int j) {
+BG_HD Node apply_move(const Node& n, const Root& R, int d, uint32_t mask, int special, int j) {
     Node c = n;
-    int nm = __popc(mask);
+    int nm = BG_POPC(mask);
     int s, t;
     if (j < nm) { s = nth_set_bit(mask, j); t = R.player == 0 ? s + d : s - d; }
     else if (special == kBar) { s = kBar; t = R.player == 0 ? d - 1 : 24 - d; }
@@ -101,22 +113,22 @@ __device__ __forceinline__ Node apply_move(const Node& n, const Root& R, int d, 
 }
 
 // 4 nibbles (16 bits) -> 4 bytes
-__device__ __forceinline__ uint32_t spread_nibbles(uint32_t x) {
+BG_HD uint32_t spread_nibbles(uint32_t x) {
     x &= 0xFFFFu;
     x = (x | (x << 8)) & 0x00FF00FFu;
     x = (x | (x << 4)) & 0x0F0F0F0Fu;
     return x;
 }
 // 4 bits -> 4 bytes of 0/1
-__device__ __forceinline__ uint32_t spread_bits(uint32_t x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
+BG_HD uint32_t spread_bits(uint32_t x) { return ((x & 0xFu) * 0x00204081u) & 0x01010101u; }
 
 // Word k (0..12) of the board52 row of node n; rootw = the root's 13 words.
-__device__ __forceinline__ uint32_t node_row_word(const Node& n, int player, const uint32_t* rootw, int k) {
+BG_HD uint32_t node_row_word(const Node& n, int player, const uint32_t* rootw, int k) {
     const int own0 = player == 0 ? 0 : 6, opp0 = player == 0 ? 6 : 0;
     if (k == 12) {
         uint32_t ob = (uint32_t)node_bar(n), oo = (uint32_t)node_off(n);
         uint32_t m = rootw[12];
-        uint32_t pb = ((m >> (player == 0 ? 8 : 0)) & 0xFFu) + (uint32_t)__popc(n.hit);   // opponent bar
+        uint32_t pb = ((m >> (player == 0 ? 8 : 0)) & 0xFFu) + (uint32_t)BG_POPC(n.hit);   // opponent bar
         uint32_t po = (m >> (player == 0 ? 24 : 16)) & 0xFFu;                              // opponent off
         return player == 0 ? (ob | (pb << 8) | (oo << 16) | (po << 24))
                            : (pb | (ob << 8) | (po << 16) | (oo << 24));
@@ -130,7 +142,7 @@ __device__ __forceinline__ uint32_t node_row_word(const Node& n, int player, con
     return rootw[k] - spread_bits(n.hit >> (4 * q));
 }
 
-__device__ __forceinline__ uint32_t hash_node(const Node& n) {
+BG_HD uint32_t hash_node(const Node& n) {
     uint32_t h = (uint32_t)n.lo * 0x9E3779B1u;
     h ^= (uint32_t)(n.lo >> 32) * 0x85EBCA77u;
     h ^= (uint32_t)n.hi * 0xC2B2AE3Du;

@@ -18,6 +18,6 @@ int bg_sm_count();
 namespace bg {
 int movegen_run(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B, int mode,
                 const long long* offsets, int max_rows, int8_t* after, long long after_cap_rows,
-                int32_t* counts_true, int32_t* counts, long long* starts, unsigned long long* alloc,
+                int8_t* row_players, int32_t* counts_true, int32_t* counts, long long* starts, unsigned long long* alloc,
                 int32_t* status, void* workspace, size_t ws_bytes, cudaStream_t stream);
 }

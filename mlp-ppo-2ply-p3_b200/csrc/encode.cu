@@ -1,0 +1,140 @@
+// encode.cu -- K3: the reference's 198-feature board encoding, written as f32 rows (API parity) or
+// as bf16 rows padded to a multiple of 8 columns (the MLP's tensor-core input).
+//
+// Replaces get_board_features_batch_from_tensors (src/ai/batching.py:78-147) and
+// ImmutableBoard.get_board_features (src/board/immutable_board.py:171-212):
+//   [0,96)   PLAYER1 points 0..23, 4 units each: c==1 -> 1,0,0,0; c==2 -> 1,1,0,0; c>=3 -> 1,1,1,(c-3)/2
+//   [96] bar1/2   [97] off1/15   [98,194) PLAYER2 points   [194] bar2/2   [195] off2/15
+//   [196] 1 if flag==PLAYER1     [197] 1 if flag==PLAYER2
+// HBM-bound: 52 B read, 792 B (f32) or 2*ld B (bf16) written per row.  A CTA stages ROWS boards in
+// shared memory with coalesced loads, then every thread produces 16-byte (bf16) / 8-byte (f32) output
+// vectors so that a warp's stores cover contiguous 512 / 256 bytes.
+#include <cuda_bf16.h>
+#include "bg_device.cuh"
+#include "bg_internal.h"
+
+namespace bg {
+
+constexpr int kEncRows = 128;     // boards per CTA tile
+constexpr int kEncThreads = 256;
+
+__device__ __forceinline__ uint32_t bf16_bits(float f) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f)); }
+
+// 4 bf16 units of one point with c men, packed little-endian into (x = units 0,1; y = units 2,3)
+__device__ __forceinline__ uint2 point_units_bf16(int c) {
+    uint2 r;
+    r.x = (c >= 1 ? 0x3F80u : 0u) | (c >= 2 ? 0x3F800000u : 0u);
+    r.y = (c >= 3 ? 0x3F80u : 0u) | (c >= 4 ? (bf16_bits((float)(c - 3) * 0.5f) << 16) : 0u);
+    return r;
+}
+__device__ __forceinline__ float4 point_units_f32(int c) {
+    float4 r;
+    r.x = c >= 1 ? 1.0f : 0.0f; r.y = c >= 2 ? 1.0f : 0.0f; r.z = c >= 3 ? 1.0f : 0.0f;
+    r.w = c >= 3 ? ((float)c - 3.0f) / 2.0f : 0.0f;                       // batching.py:117-119
+    return r;
+}
+
+// 16-byte chunk k (features 8k .. 8k+7) of the bf16 row of board b (52 bytes in shared memory).
+__device__ __forceinline__ uint4 bf16_chunk(const int8_t* b, int flag, int k) {
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (k < 12) {                                    // PLAYER1 points 2k, 2k+1
+        uint2 a = point_units_bf16(b[2 * k]), c = point_units_bf16(b[2 * k + 1]);
+        o = make_uint4(a.x, a.y, c.x, c.y);
+    } else if (k == 12) {                            // bar1/2, off1/15, P2 point 0, first half of P2 point 1
+        uint2 a = point_units_bf16(b[24]), c = point_units_bf16(b[25]);
+        o.x = bf16_bits((float)b[48] / 2.0f) | (bf16_bits((float)b[50] / 15.0f) << 16);
+        o.y = a.x; o.z = a.y; o.w = c.x;
+    } else if (k < 24) {                             // second half of P2 point q, P2 point q+1, first half of q+2
+        int q = 2 * (k - 12) - 1;
+        uint2 a = point_units_bf16(b[24 + q]), c = point_units_bf16(b[24 + q + 1]), e = point_units_bf16(b[24 + q + 2]);
+        o = make_uint4(a.y, c.x, c.y, e.x);
+    } else if (k == 24) {                            // second half of P2 point 23, bar2/2, off2/15, flags, pad
+        uint2 a = point_units_bf16(b[47]);
+        o.x = a.y;
+        o.y = bf16_bits((float)b[49] / 2.0f) | (bf16_bits((float)b[51] / 15.0f) << 16);
+        o.z = flag == 0 ? 0x00003F80u : 0x3F800000u;
+    }
+    return o;
+}
+
+// float2 pair j (features 2j, 2j+1) of the f32 row
+__device__ __forceinline__ float2 f32_pair(const int8_t* b, int flag, int j) {
+    if (j < 48) { float4 u = point_units_f32(b[j >> 1]); return (j & 1) ? make_float2(u.z, u.w) : make_float2(u.x, u.y); }
+    if (j == 48) return make_float2((float)b[48] / 2.0f, (float)b[50] / 15.0f);
+    if (j < 97) { int r = j - 49; float4 u = point_units_f32(b[24 + (r >> 1)]); return (r & 1) ? make_float2(u.z, u.w) : make_float2(u.x, u.y); }
+    if (j == 97) return make_float2((float)b[49] / 2.0f, (float)b[51] / 15.0f);
+    return flag == 0 ? make_float2(1.0f, 0.0f) : make_float2(0.0f, 1.0f);
+}
+
+__device__ __forceinline__ void stage_boards(const int8_t* __restrict__ boards, long long row0, int rows, uint32_t* sm) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
+    for (int i = threadIdx.x; i < rows * kBoardWords; i += kEncThreads) sm[i] = __ldg(src + i);
+}
+
+__global__ void __launch_bounds__(kEncThreads) encode_bf16_kernel(const int8_t* __restrict__ boards,
+                                                                  const int8_t* __restrict__ flags, int flag_all,
+                                                                  long long B, uint16_t* __restrict__ out, int cpr /* ld/8 */) {
+    __shared__ __align__(16) uint32_t sm[kEncRows * kBoardWords];
+    __shared__ int8_t sflag[kEncRows];
+    for (long long row0 = (long long)blockIdx.x * kEncRows; row0 < B; row0 += (long long)gridDim.x * kEncRows) {
+        int rows = (int)min((long long)kEncRows, B - row0);
+        stage_boards(boards, row0, rows, sm);
+        for (int i = threadIdx.x; i < rows; i += kEncThreads) sflag[i] = flags ? (flags[row0 + i] & 1) : (int8_t)flag_all;
+        __syncthreads();
+        uint4* dst = reinterpret_cast<uint4*>(out + row0 * (long long)cpr * 8);
+        const int total = rows * cpr;
+        for (int c = threadIdx.x; c < total; c += kEncThreads) {
+            int r = c / cpr, k = c - r * cpr;
+            dst[c] = bf16_chunk(reinterpret_cast<const int8_t*>(sm) + r * kBoardBytes, sflag[r], k);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kEncThreads) encode_f32_kernel(const int8_t* __restrict__ boards,
+                                                                 const int8_t* __restrict__ flags, int flag_all,
+                                                                 long long B, float* __restrict__ out, long long ld) {
+    __shared__ __align__(16) uint32_t sm[kEncRows * kBoardWords];
+    __shared__ int8_t sflag[kEncRows];
+    for (long long row0 = (long long)blockIdx.x * kEncRows; row0 < B; row0 += (long long)gridDim.x * kEncRows) {
+        int rows = (int)min((long long)kEncRows, B - row0);
+        stage_boards(boards, row0, rows, sm);
+        for (int i = threadIdx.x; i < rows; i += kEncThreads) sflag[i] = flags ? (flags[row0 + i] & 1) : (int8_t)flag_all;
+        __syncthreads();
+        const int total = rows * 99;
+        for (int c = threadIdx.x; c < total; c += kEncThreads) {
+            int r = c / 99, j = c - r * 99;
+            float2 v = f32_pair(reinterpret_cast<const int8_t*>(sm) + r * kBoardBytes, sflag[r], j);
+            *reinterpret_cast<float2*>(out + (row0 + r) * ld + 2 * j) = v;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace bg
+
+using namespace bg;
+
+static unsigned enc_grid(long long B) {
+    long long tiles = (B + kEncRows - 1) / kEncRows;
+    long long g = (long long)bg_sm_count() * 8;
+    return (unsigned)(tiles < g ? tiles : g);
+}
+
+extern "C" int bg_encode_f32(const int8_t* boards52, const int8_t* flags, int flag_all, long long B, float* out,
+                             long long ld, void* stream) {
+    if (B < 0 || ld < BG_FEATURES || (ld & 1)) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_f32: bad B or ld (need even ld >= 198)");
+    if (B == 0) return BG_OK;
+    if (!boards52 || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_f32: null pointer");
+    encode_f32_kernel<<<enc_grid(B), kEncThreads, 0, (cudaStream_t)stream>>>(boards52, flags, flag_all & 1, B, out, ld);
+    return bg_set_error(cudaGetLastError(), "bg_encode_f32: launch");
+}
+
+extern "C" int bg_encode_bf16(const int8_t* boards52, const int8_t* flags, int flag_all, long long B, uint16_t* out,
+                              long long ld, void* stream) {
+    if (B < 0 || ld < 200 || (ld & 7) || ld > 4096) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: bad B or ld (need ld >= 200, multiple of 8)");
+    if (B == 0) return BG_OK;
+    if (!boards52 || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: null pointer");
+    encode_bf16_kernel<<<enc_grid(B), kEncThreads, 0, (cudaStream_t)stream>>>(boards52, flags, flag_all & 1, B, out, (int)(ld / 8));
+    return bg_set_error(cudaGetLastError(), "bg_encode_bf16: launch");
+}

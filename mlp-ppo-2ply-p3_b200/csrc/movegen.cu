@@ -229,8 +229,8 @@ __global__ void __launch_bounds__(256) movegen_kernel(
     const int8_t* __restrict__ boards, const int8_t* __restrict__ players, const int8_t* __restrict__ dice,
     long long B, const unsigned int* __restrict__ nwork_dev, const int32_t* __restrict__ worklist,
     int mode, const long long* __restrict__ offsets, int max_rows,
-    int8_t* __restrict__ after, long long after_cap_rows, int32_t* __restrict__ counts_true,
-    int32_t* __restrict__ counts, long long* __restrict__ starts,
+    int8_t* __restrict__ after, long long after_cap_rows, int8_t* __restrict__ row_players,
+    int32_t* __restrict__ counts_true, int32_t* __restrict__ counts, long long* __restrict__ starts,
     unsigned long long* __restrict__ alloc, int32_t* __restrict__ status,
     unsigned int* __restrict__ work_ctr, int32_t* __restrict__ overflow_list, unsigned int* __restrict__ overflow_ctr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(256) movegen_kernel(
                     __syncwarp();
                     int rows = min(32, nw - r0);
                     for (int k = lane; k < rows * kBoardWords; k += 32) gout[(long long)r0 * kBoardWords + k] = stage[k];
+                    if (row_players && lane < rows) row_players[start + r0 + lane] = (int8_t)player;
                     __syncwarp();
                 }
             }
@@ -345,7 +346,7 @@ template <int CAP, int HS, int WARPS>
 static int launch_movegen(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B,
                           const unsigned int* nwork_dev, const int32_t* worklist, int mode,
                           const long long* offsets, int max_rows, int8_t* after, long long after_cap_rows,
-                          int32_t* counts_true, int32_t* counts, long long* starts, unsigned long long* alloc,
+                          int8_t* row_players, int32_t* counts_true, int32_t* counts, long long* starts, unsigned long long* alloc,
                           int32_t* status, unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr,
                           long long grid_hint, cudaStream_t stream) {
     size_t smem = sizeof(WarpScratch<CAP, HS>) * WARPS;
@@ -359,8 +360,8 @@ static int launch_movegen(const int8_t* boards, const int8_t* players, const int
     if (grid_hint > 0 && grid > grid_hint) grid = grid_hint;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(boards, players, dice, B, nwork_dev, worklist, mode, offsets,
-                                                       max_rows, after, after_cap_rows, counts_true, counts, starts,
-                                                       alloc, status, work_ctr, overflow_list, overflow_ctr);
+                                                       max_rows, after, after_cap_rows, row_players, counts_true, counts,
+                                                       starts, alloc, status, work_ctr, overflow_list, overflow_ctr);
     return bg_set_error(cudaGetLastError(), "movegen: launch");
 }
 
@@ -373,8 +374,8 @@ extern "C" size_t bg_movegen_workspace_bytes(long long B) { return 64 + sizeof(i
 
 int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B, int mode,
                     const long long* offsets, int max_rows, int8_t* after, long long after_cap_rows,
-                    int32_t* counts_true, int32_t* counts, long long* starts, unsigned long long* alloc,
-                    int32_t* status, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+                    int8_t* row_players, int32_t* counts_true, int32_t* counts, long long* starts,
+                    unsigned long long* alloc, int32_t* status, void* workspace, size_t ws_bytes, cudaStream_t stream) {
     if (B < 0) return bg_set_error_msg(BG_ERR_INVALID, "movegen: negative batch");
     if (B == 0) return BG_OK;
     if (!boards || !players || !dice || !status || !workspace)
@@ -392,13 +393,13 @@ int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* d
     cudaError_t e = cudaMemsetAsync(ws, 0, 64, stream);
     if (e != cudaSuccess) return bg_set_error(e, "movegen: memset");
     int rc = launch_movegen<BG_MOVEGEN_CAP_SMALL, 2 * BG_MOVEGEN_CAP_SMALL, 8>(
-        boards, players, dice, B, nullptr, nullptr, mode, offsets, max_rows, after, after_cap_rows, counts_true,
-        counts, starts, alloc, status, work_ctr, overflow_list, overflow_ctr, (B + 7) / 8, stream);
+        boards, players, dice, B, nullptr, nullptr, mode, offsets, max_rows, after, after_cap_rows, row_players,
+        counts_true, counts, starts, alloc, status, work_ctr, overflow_list, overflow_ctr, (B + 7) / 8, stream);
     if (rc != BG_OK) return rc;
     // Large-scratch pass over the (rare) positions whose levels did not fit: one warp per CTA, work count read
     // from device memory so no host synchronisation is needed.  Positions that do not fit even this scratch
     // raise BG_STATUS_SCRATCH_OVERFLOW (never dropped silently).
     return launch_movegen<BG_MOVEGEN_CAP_BIG, BG_MOVEGEN_HASH_BIG, 1>(
         boards, players, dice, B, overflow_ctr, overflow_list, mode, offsets, max_rows, after, after_cap_rows,
-        counts_true, counts, starts, alloc, status, work_ctr2, nullptr, nullptr, 0, stream);
+        row_players, counts_true, counts, starts, alloc, status, work_ctr2, nullptr, nullptr, 0, stream);
 }

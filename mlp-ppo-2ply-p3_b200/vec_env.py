@@ -1,0 +1,251 @@
+"""B200BackgammonVecEnv -- drop-in for the reference's VectorizedBackgammonEnv
+(src/environment/vec_bg_env.py:7-71) with every game resident in HBM.
+
+Same constructor arguments and method set (reset / step / get_action_masks /
+get_legal_board_features / close), same return shapes and dtypes, same per-game semantics as
+BackgammonEnv (src/environment/backgammon_env.py:38-251, 357-405) including auto-reset on done,
+pass turns, invalid-action reward -1 and the first-`max_legal_moves` truncation.  Differences, all
+additive: `infos` is a lazy list view over device tensors; legal plays are also available ragged
+(`legal_counts`, `legal_starts`, `afterstates`, `afterstate_features`); dice come from a counter-based
+Philox stream (or an injected per-game dice list for parity runs) instead of numpy's global MT19937.
+
+All compute is in libbg_b200.so (hand-written sm_100a kernels); torch only owns the memory.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BgError, EnvState, StepOut, check, lib
+from .engine import FEATURES, LD_BF16, from_board52, to_board52, _stream
+
+
+class StepInfos:
+    """Lazy list-of-dicts view of the per-game info tensors (reference: list of dicts, vec_bg_env.py:40).
+
+    Keys as in backgammon_env.py:117,139,149,172: "current_player", "info" (on pass / invalid action),
+    "winner" and "game_score" (on a win).  The tensors themselves are the cheap way to read them.
+    """
+
+    def __init__(self, current_player, winner, game_score, flags):
+        self.current_player, self.winner, self.game_score, self.flags = current_player, winner, game_score, flags
+        self._host = None
+
+    def __len__(self):
+        return self.current_player.shape[0]
+
+    def _h(self):
+        if self._host is None:
+            self._host = (self.current_player.cpu().tolist(), self.winner.cpu().tolist(),
+                          self.game_score.cpu().tolist(), self.flags.cpu().tolist())
+        return self._host
+
+    def __getitem__(self, i):
+        cp, w, gs, fl = self._h()
+        d = {"current_player": cp[i]}
+        if fl[i] & 1:
+            d["info"] = "No legal actions, turn passed"
+        if fl[i] & 2:
+            d["info"] = "Invalid action"
+        if w[i] >= 0:
+            d["winner"], d["game_score"] = w[i], gs[i]
+        return d
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class B200BackgammonVecEnv:
+    def __init__(self, num_envs=1, match_length=15, max_legal_moves=500, device=None, seed=0x5EED,
+                 stream_base=0, rows_per_game=64, dense_budget_bytes=4 << 30, check_every=16):
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+        device = torch.device(device) if device is not None else None
+        if device is None or device.type != "cuda":
+            raise BgError("B200BackgammonVecEnv needs a CUDA device (there is no CPU fallback)")
+        lib()   # fail loudly now if the extension is missing
+        self.num_envs, self.match_length, self.max_legal_moves = int(num_envs), int(match_length), int(max_legal_moves)
+        self.device, self.seed, self.stream_base = device, int(seed), int(stream_base)
+        self.dense_budget_bytes, self.check_every = int(dense_budget_bytes), int(check_every)
+        N = self.num_envs
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
+        self.boards52, self.players, self.dice = z((N, 52), torch.int8), z((N,), torch.int8), z((N, 2), torch.int8)
+        self.scores, self.draws, self.match_over = z((N, 2), torch.int32), z((N,), torch.int32), z((N,), torch.int8)
+        self.cap_rows = max(N * int(rows_per_game), 4096)
+        self.after52 = z((self.cap_rows, 52), torch.int8)
+        self.row_players = z((self.cap_rows,), torch.int8)
+        self.legal_starts, self.legal_counts = z((N,), torch.int64), z((N,), torch.int32)
+        self.legal_counts_true = z((N,), torch.int32)
+        self.alloc_rows = z((1,), torch.int64)
+        self.status = z((1,), torch.int32)
+        self.rewards, self.dones_u8 = z((N,), torch.float32), z((N,), torch.uint8)
+        self.info_player, self.winner, self.game_score = z((N,), torch.int8), z((N,), torch.int8), z((N,), torch.int8)
+        self.flags = z((N,), torch.uint8)
+        self._ws_bytes = int(lib().bg_movegen_workspace_bytes(max(N, 1)))
+        self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=device)
+        self._ext_dice = None
+        self._steps = 0
+        # reference attributes (vec_bg_env.py:16-18); gym is not a dependency, so plain descriptors
+        self.observation_space = {"shape": (FEATURES,), "low": -1.0, "high": 1.0, "dtype": "float32"}
+        self.action_space = {"n": self.max_legal_moves}
+
+    # ------------------------------------------------------------------ plumbing
+    def _state(self) -> EnvState:
+        e = self._ext_dice
+        return EnvState(self.num_envs, self.boards52.data_ptr(), self.players.data_ptr(), self.dice.data_ptr(),
+                        self.scores.data_ptr(), self.draws.data_ptr(), self.match_over.data_ptr(),
+                        self.after52.data_ptr(), self.legal_starts.data_ptr(), self.legal_counts.data_ptr(),
+                        self.seed, self.stream_base, e.data_ptr() if e is not None else None,
+                        e.shape[1] if e is not None else 0, self.match_length)
+
+    def _refresh_legal_moves(self):
+        """update_legal_moves (backgammon_env.py:198-243) for every game: K1 in slab mode."""
+        self.alloc_rows.zero_()
+        check(lib().bg_movegen_slab(self.boards52.data_ptr(), self.players.data_ptr(), self.dice.data_ptr(),
+                                    self.num_envs, self.max_legal_moves, self.after52.data_ptr(), self.cap_rows,
+                                    self.row_players.data_ptr(), self.legal_counts_true.data_ptr(),
+                                    self.legal_counts.data_ptr(), self.legal_starts.data_ptr(),
+                                    self.alloc_rows.data_ptr(), self.status.data_ptr(), self._ws.data_ptr(),
+                                    self._ws_bytes, _stream()), "bg_movegen_slab")
+
+    def check_status(self):
+        s = int(self.status.item())
+        if s:
+            raise BgError(f"device status {s}: {_lib.status_message(s)}"
+                          + (" -- construct the env with a larger rows_per_game" if s & 4 else ""))
+
+    def observations(self, dtype=torch.float32) -> torch.Tensor:
+        """get_observation (backgammon_env.py:193-196) of every game: (N,198) f32 (or (N,208) bf16)."""
+        from .engine import encode
+        return encode(self.boards52, self.players, dtype=dtype)
+
+    # ------------------------------------------------------------------ reference API
+    def reset(self):
+        """vec_bg_env.py:20-26 -> (N,198) f32"""
+        with torch.cuda.device(self.device):
+            st = self._state()
+            check(lib().bg_env_reset(C.byref(st), None, self.status.data_ptr(), _stream()), "bg_env_reset")
+            self._refresh_legal_moves()
+            obs = self.observations()
+        self.check_status()
+        return obs
+
+    def step(self, actions, return_obs=True):
+        """vec_bg_env.py:28-49 -> (obs (N,198) f32, rewards (N,) f32, dones (N,) bool, infos)"""
+        if not isinstance(actions, torch.Tensor):
+            import numpy as np
+            acts = [0 if a is None else int(a) for a in actions] if not isinstance(actions, np.ndarray) else actions
+            actions = torch.as_tensor(acts)
+        actions = actions.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
+        if actions.shape[0] != self.num_envs:
+            raise BgError("step: need one action per env")
+        with torch.cuda.device(self.device):
+            self.step_device(actions)
+            obs = self.observations() if return_obs else None
+        self._steps += 1
+        if self.check_every and self._steps % self.check_every == 0:
+            self.check_status()
+        infos = StepInfos(self.info_player.clone(), self.winner.clone(), self.game_score.clone(), self.flags.clone())
+        return obs, self.rewards.clone(), self.dones_u8.to(torch.bool), infos
+
+    def step_device(self, actions_i32: torch.Tensor):
+        """The hot path only: K2 (step/reward/terminal/reset/dice) + K1 (legal plays of the new positions).
+        Results land in self.rewards / dones_u8 / info_* / legal_* without any host synchronisation."""
+        st = self._state()
+        out = StepOut(self.rewards.data_ptr(), self.dones_u8.data_ptr(), self.info_player.data_ptr(),
+                      self.winner.data_ptr(), self.game_score.data_ptr(), self.flags.data_ptr())
+        check(lib().bg_env_step(C.byref(st), actions_i32.data_ptr(), C.byref(out), self.status.data_ptr(), _stream()),
+              "bg_env_step")
+        self._refresh_legal_moves()
+
+    def random_actions(self, seed: int, t: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Uniform random policy on the device (Philox, domain "ACT1")."""
+        if out is None:
+            out = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        check(lib().bg_random_actions(self.legal_counts.data_ptr(), self.num_envs, int(seed), self.stream_base, int(t),
+                                      out.data_ptr(), _stream()), "bg_random_actions")
+        return out
+
+    def get_action_masks(self):
+        """vec_bg_env.py:51-56 -> (N, max_legal_moves) f32"""
+        ar = torch.arange(self.max_legal_moves, device=self.device, dtype=torch.int32)
+        return (ar[None, :] < self.legal_counts[:, None]).to(torch.float32)
+
+    def get_legal_board_features(self):
+        """vec_bg_env.py:58-63 -> dense (N, max_legal_moves, 198) f32, zero padded (backgammon_env.py:233-243).
+        Guarded: the dense tensor is 396 KB per game; use afterstate_features() at scale."""
+        need = self.num_envs * self.max_legal_moves * FEATURES * 4
+        if need > self.dense_budget_bytes:
+            raise BgError(f"dense legal_board_features would take {need / 2**30:.1f} GiB; use the ragged "
+                          "afterstate_features() / legal_starts / legal_counts accessors instead")
+        feats, rows_game, rows_idx = self._ragged_features(torch.float32)
+        dense = torch.zeros((self.num_envs, self.max_legal_moves, FEATURES), dtype=torch.float32, device=self.device)
+        dense[rows_game, rows_idx] = feats
+        return dense
+
+    def close(self):
+        self.check_status()
+
+    def render(self):
+        raise NotImplementedError("render is out of scope (the reference's own render is broken, SURVEY.md section 2)")
+
+    # ------------------------------------------------------------------ ragged extras
+    def total_rows(self) -> int:
+        return int(self.alloc_rows.item())
+
+    def afterstates(self):
+        """(rows,52) int8 view of the current legal-play buffer; game g owns rows
+        legal_starts[g] .. legal_starts[g]+legal_counts[g], in the reference's legal_moves order."""
+        return self.after52[: self.total_rows()]
+
+    def afterstate_features(self, dtype=torch.bfloat16):
+        """generate_all_board_features (ai/batching.py:10-75) for every game, ragged: (rows, 208) bf16 or
+        (rows,198) f32, row r encoded with its mover's turn flag (batching.py:72-74)."""
+        from .engine import encode
+        n = self.total_rows()
+        return encode(self.after52[:n], self.row_players[:n], dtype=dtype)
+
+    def _ragged_features(self, dtype):
+        from .engine import encode
+        counts = self.legal_counts.to(torch.int64)
+        total = int(counts.sum().item())
+        games = torch.repeat_interleave(torch.arange(self.num_envs, device=self.device), counts)
+        offs = torch.cumsum(counts, 0) - counts
+        idx = torch.arange(total, device=self.device) - offs[games]
+        rows = self.legal_starts[games] + idx
+        feats = encode(self.after52[rows], self.players[games], dtype=dtype)
+        return feats, games, idx
+
+    # ------------------------------------------------------------------ parity / injection hooks
+    def boards(self) -> torch.Tensor:
+        """(N,4,24) int8 in the reference layout."""
+        return from_board52(self.boards52)
+
+    def set_dice_stream(self, dice: torch.Tensor | None):
+        """Inject dice: (N, L, 2) int8, game g consumes dice[g, draw] in order (replaces np.random.randint of
+        backgammon_env.py:245-246).  None returns to Philox."""
+        if dice is None:
+            self._ext_dice = None
+        else:
+            d = torch.as_tensor(dice).to(device=self.device, dtype=torch.int8).contiguous()
+            if d.dim() != 3 or d.shape[0] != self.num_envs or d.shape[2] != 2:
+                raise BgError("set_dice_stream: need (N, L, 2)")
+            self._ext_dice = d
+        self.draws.zero_()
+
+    def load_positions(self, boards, players, dice):
+        """Overwrite every game's position (reference-layout (N,4,24) or packed (N,52)), mover and roll, then
+        refresh the legal plays."""
+        b = torch.as_tensor(boards).to(self.device)
+        self.boards52.copy_(b if b.shape[-1] == 52 and b.dim() == 2 else to_board52(b))
+        self.players.copy_(torch.as_tensor(players).to(self.device, torch.int8))
+        self.dice.copy_(torch.as_tensor(dice).to(self.device, torch.int8).reshape(-1, 2))
+        with torch.cuda.device(self.device):
+            self._refresh_legal_moves()
+        self.check_status()
+
+
+# The reference's class name, for callers that do `VectorizedBackgammonEnv(num_envs, ...)` (train.py:128-133)
+VectorizedBackgammonEnv = B200BackgammonVecEnv
