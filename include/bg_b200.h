@@ -84,13 +84,15 @@ int bg_movegen_slab(const int8_t* boards52, const int8_t* players, const int8_t*
  * ImmutableBoard.get_board_features (board/immutable_board.py:171-212).  flags[b] = player whose
  * turn flag is set (features 196/197); for afterstates that is the MOVER (ai/batching.py:72-74).
  * If flags == NULL, flag_all (0/1) applies to every row.  (K1's row_players output is the flags
- * array of a ragged afterstate buffer.)
+ * array of a ragged afterstate buffer.)  If n_rows_dev != NULL the number of rows encoded is
+ * min(B, *n_rows_dev), read on the device (K1's alloc_rows counter), so no host sync is needed.
  */
 int bg_encode_f32(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
-                  float* out, long long ld /* >= 198, in floats */, void* stream);
+                  const unsigned long long* n_rows_dev /*nullable*/, float* out, long long ld /* even, >= 198 */,
+                  void* stream);
 /* bf16 rows, ld >= 198 elements and a multiple of 8; columns 198..ld-1 are written as zeros. */
 int bg_encode_bf16(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
-                   uint16_t* out, long long ld, void* stream);
+                   const unsigned long long* n_rows_dev /*nullable*/, uint16_t* out, long long ld, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K2  fused step / reward / terminal / auto-reset / dice.  Replaces BackgammonEnv.step/reset/

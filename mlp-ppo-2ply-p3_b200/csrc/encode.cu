@@ -73,9 +73,11 @@ __device__ __forceinline__ void stage_boards(const int8_t* __restrict__ boards, 
 
 __global__ void __launch_bounds__(kEncThreads) encode_bf16_kernel(const int8_t* __restrict__ boards,
                                                                   const int8_t* __restrict__ flags, int flag_all,
-                                                                  long long B, uint16_t* __restrict__ out, int cpr /* ld/8 */) {
+                                                                  long long B, const unsigned long long* __restrict__ n_rows_dev,
+                                                                  uint16_t* __restrict__ out, int cpr /* ld/8 */) {
     __shared__ __align__(16) uint32_t sm[kEncRows * kBoardWords];
     __shared__ int8_t sflag[kEncRows];
+    if (n_rows_dev) B = min(B, (long long)*n_rows_dev);
     for (long long row0 = (long long)blockIdx.x * kEncRows; row0 < B; row0 += (long long)gridDim.x * kEncRows) {
         int rows = (int)min((long long)kEncRows, B - row0);
         stage_boards(boards, row0, rows, sm);
@@ -93,9 +95,11 @@ __global__ void __launch_bounds__(kEncThreads) encode_bf16_kernel(const int8_t* 
 
 __global__ void __launch_bounds__(kEncThreads) encode_f32_kernel(const int8_t* __restrict__ boards,
                                                                  const int8_t* __restrict__ flags, int flag_all,
-                                                                 long long B, float* __restrict__ out, long long ld) {
+                                                                 long long B, const unsigned long long* __restrict__ n_rows_dev,
+                                                                 float* __restrict__ out, long long ld) {
     __shared__ __align__(16) uint32_t sm[kEncRows * kBoardWords];
     __shared__ int8_t sflag[kEncRows];
+    if (n_rows_dev) B = min(B, (long long)*n_rows_dev);
     for (long long row0 = (long long)blockIdx.x * kEncRows; row0 < B; row0 += (long long)gridDim.x * kEncRows) {
         int rows = (int)min((long long)kEncRows, B - row0);
         stage_boards(boards, row0, rows, sm);
@@ -121,20 +125,20 @@ static unsigned enc_grid(long long B) {
     return (unsigned)(tiles < g ? tiles : g);
 }
 
-extern "C" int bg_encode_f32(const int8_t* boards52, const int8_t* flags, int flag_all, long long B, float* out,
-                             long long ld, void* stream) {
+extern "C" int bg_encode_f32(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
+                             const unsigned long long* n_rows_dev, float* out, long long ld, void* stream) {
     if (B < 0 || ld < BG_FEATURES || (ld & 1)) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_f32: bad B or ld (need even ld >= 198)");
     if (B == 0) return BG_OK;
     if (!boards52 || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_f32: null pointer");
-    encode_f32_kernel<<<enc_grid(B), kEncThreads, 0, (cudaStream_t)stream>>>(boards52, flags, flag_all & 1, B, out, ld);
+    encode_f32_kernel<<<enc_grid(B), kEncThreads, 0, (cudaStream_t)stream>>>(boards52, flags, flag_all & 1, B, n_rows_dev, out, ld);
     return bg_set_error(cudaGetLastError(), "bg_encode_f32: launch");
 }
 
-extern "C" int bg_encode_bf16(const int8_t* boards52, const int8_t* flags, int flag_all, long long B, uint16_t* out,
-                              long long ld, void* stream) {
+extern "C" int bg_encode_bf16(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
+                              const unsigned long long* n_rows_dev, uint16_t* out, long long ld, void* stream) {
     if (B < 0 || ld < 200 || (ld & 7) || ld > 4096) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: bad B or ld (need ld >= 200, multiple of 8)");
     if (B == 0) return BG_OK;
     if (!boards52 || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: null pointer");
-    encode_bf16_kernel<<<enc_grid(B), kEncThreads, 0, (cudaStream_t)stream>>>(boards52, flags, flag_all & 1, B, out, (int)(ld / 8));
+    encode_bf16_kernel<<<enc_grid(B), kEncThreads, 0, (cudaStream_t)stream>>>(boards52, flags, flag_all & 1, B, n_rows_dev, out, (int)(ld / 8));
     return bg_set_error(cudaGetLastError(), "bg_encode_bf16: launch");
 }

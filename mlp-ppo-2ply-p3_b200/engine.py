@@ -110,10 +110,12 @@ def legal_moves(boards52: torch.Tensor, players: torch.Tensor, dice: torch.Tenso
     return counts_true, offsets, after
 
 
-def encode(boards52: torch.Tensor, flags, dtype=torch.float32, ld: int | None = None) -> torch.Tensor:
+def encode(boards52: torch.Tensor, flags, dtype=torch.float32, ld: int | None = None, out: torch.Tensor | None = None,
+           n_rows_dev: torch.Tensor | None = None) -> torch.Tensor:
     """198-feature encoding of B positions.  flags: int (0/1 for all rows) or (B,) int8 tensor = the player
     whose turn flag is set.  f32 -> (B,198) exactly the reference's tensor; bf16 -> (B, ld) with ld=208 by
-    default, columns 198.. zero (the MLP's K padding)."""
+    default, columns 198.. zero (the MLP's K padding).  `out` reuses a buffer; `n_rows_dev` (1-element int64
+    CUDA tensor) bounds the rows on the device, e.g. the env's alloc_rows counter."""
     _require_cuda(boards52)
     boards52 = boards52.reshape(-1, 52).contiguous()
     B = boards52.shape[0]
@@ -124,15 +126,22 @@ def encode(boards52: torch.Tensor, flags, dtype=torch.float32, ld: int | None = 
     else:
         fl, fptr, fall = None, None, int(flags)
     L = lib()
+    nptr = n_rows_dev.data_ptr() if n_rows_dev is not None else None
+    if out is not None and (not out.is_contiguous() or out.shape[0] < B):
+        raise BgError("encode: `out` must be contiguous with at least B rows")
+    if out is not None:
+        ld = out.shape[1]
     with torch.cuda.device(dev):
         if dtype == torch.float32:
             ld = ld or FEATURES
-            out = torch.empty((B, ld), dtype=torch.float32, device=dev)
-            check(L.bg_encode_f32(boards52.data_ptr(), fptr, fall, B, out.data_ptr(), ld, _stream()), "bg_encode_f32")
+            if out is None:
+                out = torch.empty((B, ld), dtype=torch.float32, device=dev)
+            check(L.bg_encode_f32(boards52.data_ptr(), fptr, fall, B, nptr, out.data_ptr(), ld, _stream()), "bg_encode_f32")
         elif dtype == torch.bfloat16:
             ld = ld or LD_BF16
-            out = torch.empty((B, ld), dtype=torch.bfloat16, device=dev)
-            check(L.bg_encode_bf16(boards52.data_ptr(), fptr, fall, B, out.data_ptr(), ld, _stream()), "bg_encode_bf16")
+            if out is None:
+                out = torch.empty((B, ld), dtype=torch.bfloat16, device=dev)
+            check(L.bg_encode_bf16(boards52.data_ptr(), fptr, fall, B, nptr, out.data_ptr(), ld, _stream()), "bg_encode_bf16")
         else:
             raise BgError("encode: dtype must be float32 or bfloat16")
     return out

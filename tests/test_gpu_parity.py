@@ -261,8 +261,8 @@ def test_c_abi_rejects_bad_arguments(bg):
     L = bg.lib()
     assert L.bg_movegen_count(None, None, None, 4, None, None, None, 0, None) == -1
     assert b"null" in L.bg_last_error()
-    assert L.bg_encode_f32(None, None, 0, 4, None, 198, None) == -1
-    assert L.bg_encode_bf16(None, None, 0, 0, None, 100, None) == -1
+    assert L.bg_encode_f32(None, None, 0, 4, None, None, 198, None) == -1
+    assert L.bg_encode_bf16(None, None, 0, 0, None, None, 100, None) == -1
     assert L.bg_movegen_count(None, None, None, 0, None, None, None, 0, None) == 0      # empty batch is fine
 
 

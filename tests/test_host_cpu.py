@@ -36,7 +36,7 @@ def test_argument_validation_without_gpu():
     L = bg_b200.lib()
     assert L.bg_movegen_count(None, None, None, -1, None, None, None, 0, None) == -1
     assert b"negative" in L.bg_last_error()
-    assert L.bg_encode_f32(None, None, 0, 1, None, 197, None) == -1
+    assert L.bg_encode_f32(None, None, 0, 1, None, None, 197, None) == -1
 
 
 def test_no_cpu_fallback():
