@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- env steps/sec with legal-move generation (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): batched legal-move generation + step on 65,536 parallel games per GPU,
+uniform-random policy, positions from the engine's own random self-play (Philox seed 0x5EED, 128 untimed
+de-phasing turns).  One "step" = one turn of every game:
+    bg_random_actions -> K2 bg_env_step (apply play, reward/terminal, auto-reset, Philox dice)
+    -> K1 bg_movegen_slab (all legal afterstates of the new positions, reference order)
+    -> K3 bg_encode_f32 (observations) + bg_encode_bf16 (ragged afterstate features)
+i.e. everything BackgammonEnv.step + update_legal_moves + get_observation do, minus the dense
+(500,198) zero padding.  Games shard across GPUs by game id with no collective ("scaling": "weak").
+
+Prints ONE JSON line (see the keys below).  `--impl reference` times the CPU port of the reference's
+path (oracle/, kind "port": the reference itself is Python and cannot travel to the GPU box) on all
+host cores for the same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 0x5EED
+ACT_SEED = 0xAC7
+METRIC = "env steps/sec w/ legal-move gen"
+UNIT = "env_steps/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+
+def cpu_rollout(seconds: float, threads: int, chunk: int = 2000, encode: bool = True):
+    """Uniform-random self-play through the oracle's restatement of BackgammonEnv (same Philox dice / action
+    conventions as the engine), `threads` envs in parallel (ctypes releases the GIL).  -> (steps, elapsed s)"""
+    from oracle import bg_oracle as O
+    O.lib()
+    done_steps = [0] * threads
+    t_end = [0.0] * threads
+    start = time.perf_counter()
+
+    def work(i):
+        e = O.Env()
+        e.set_philox(SEED, i)
+        e.reset()
+        n = 0
+        while time.perf_counter() - start < seconds:
+            e.random_rollout(chunk, ACT_SEED, encode)
+            n += chunk
+        done_steps[i] = n
+        t_end[i] = time.perf_counter()
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return sum(done_steps), max(t_end) - start
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step_s = max(0.5, min(8.0, 90.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_rollout(per_step_s, threads)
+    total, el = 0, 0.0
+    for _ in range(args.steps):
+        n, e = cpu_rollout(per_step_s, threads)
+        total += n; el += e
+    v = total / el
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * el / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": "uniform-random self-play, BackgammonEnv.step + update_legal_moves + encoders, CPU port of "
+                                   "the reference path (oracle/bg_oracle.c); the Python reference itself (~50 steps/s/core, "
+                                   "BASELINE.md) cannot travel to the GPU box",
+                       "games": threads, "policy": "uniform random (Philox)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{total} env steps in {el:.1f} s over {threads} threads, each step of this arm = "
+                                       f"{per_step_s:.1f} s of rollout per thread"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    import bg_b200
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N = args.games
+    env = bg_b200.B200BackgammonVecEnv(num_envs=N, device=dev, seed=SEED, stream_base=rank * N,
+                                       rows_per_game=args.rows_per_game, check_every=0)
+    env.reset()
+    acts = torch.empty(N, dtype=torch.int32, device=dev)
+    rows_acc = torch.zeros(1, dtype=torch.int64, device=dev)
+    launches = [0]
+    feats = not args.no_afterstate_features
+
+    def one_step(t, ev=None):
+        env.random_actions(ACT_SEED, t, out=acts); launches[0] += 1
+        env._apply_actions(acts); launches[0] += 1
+        if ev is not None:
+            ev[0].record()
+        env._refresh_legal_moves(); launches[0] += 2          # small-scratch pass + large-scratch pass
+        if ev is not None:
+            ev[1].record()
+        env.encode_resident(obs=True, afterstates=feats); launches[0] += 1 + int(feats)
+        rows_acc.add_(env.alloc_rows)
+
+    t = 0
+    for _ in range(args.dephase + args.warmup):               # de-phase the games, then W warm-up steps (untimed)
+        one_step(t); t += 1
+    env.check_status()
+    rows_acc.zero_()
+    launches[0] = 0
+    K = args.steps
+    k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(K):
+        one_step(t, k1_events[k]); t += 1
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    env.check_status()
+    k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / K
+    rows_per_step = float(rows_acc.item()) / K
+    n_launch = launches[0]
+
+    # ---- end to end through the public API with host buffers: actions from pinned host memory every step,
+    # rewards / dones / legal-play counts read back to the host every step (what a host-side policy needs).
+    E = max(1, min(args.e2e_steps, K))
+    import numpy as np
+    h_counts = torch.empty(N, dtype=torch.int32).pin_memory()
+    h_acts = torch.empty(N, dtype=torch.int32).pin_memory()
+    h_rew = torch.empty(N, dtype=torch.float32).pin_memory()
+    h_done = torch.empty(N, dtype=torch.bool).pin_memory()
+    rng = np.random.default_rng(1)
+    u = rng.random((E, N), dtype=np.float32)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(E):
+        h_counts.copy_(env.legal_counts)                                        # D2H (synchronous: pinned target)
+        np.multiply(u[k], h_counts.numpy(), out=u[k])
+        h_acts.numpy()[:] = u[k].astype(np.int32)
+        obs, rew, done, infos = env.step(h_acts)                                # H2D inside; obs stays on the device
+        if feats:
+            env.encode_resident(obs=False, afterstates=True)
+        h_rew.copy_(rew); h_done.copy_(done)                                    # D2H
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    env.check_status()
+
+    tm = torch.tensor([ms, e2e_s * 1e3, k1_ms], dtype=torch.float64, device=dev)
+    rw = torch.tensor([rows_per_step], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rw, op=dist.ReduceOp.SUM)
+        rw /= world
+    ms, e2e_ms, k1_ms = [float(x) for x in tm.tolist()]
+    rows_per_step = float(rw.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * N * K / (ms * 1e-3)
+    e2e_value = world * N * E / (e2e_ms * 1e-3)
+    peak, peak_src = load_peaks()
+    # K1 algorithmic bytes per launch (DESIGN.md "K1"): per game 52 board + 1 player + 2 dice read; 4 count +
+    # 4 true count + 8 start written; per legal play 52 afterstate + 1 mover flag written.
+    k1_bytes = N * 71.0 + rows_per_step * 53.0
+    achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int8", "data": "synthetic",
+        "config": {"workload": "configs[1]: batched legal-move generation + step, uniform-random policy",
+                   "games_per_gpu": N, "max_legal_moves": 500, "dephase_steps": args.dephase,
+                   "afterstate_features": "bf16 ragged (ld 208)" if feats else "off", "observations": "f32 (N,198)",
+                   "legal_plays_per_step_mean": rows_per_step / N, "parallelism": f"games sharded x{world}, no collective",
+                   "l2": "per-step working set (afterstates + features + observations) exceeds the 126 MB L2; no flush"},
+        "roofline": {"kernel": "movegen_kernel (K1, small + large scratch passes)", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / (ms / K),
+                     "algorithmic_bytes_per_launch": k1_bytes,
+                     "note": "K1 is integer/latency-bound (SURVEY 8(d)); the HBM fraction is reported as required"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * N * 4, "d2h_bytes_per_step": world * N * 9,
+                "steps": E, "what": "B200BackgammonVecEnv.step(actions from pinned host memory); rewards, dones and "
+                                    "legal-play counts copied to the host every step; observations stay on the device "
+                                    "as the reference API returns them"},
+        "gpu_launches": n_launch, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n, el = cpu_rollout(args.cpu_seconds, threads)
+        line["cpu_baseline"] = {"value": n / el, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{n} env steps of the same uniform-random workload in {el:.1f} s over {threads} "
+                                          "threads (oracle/bg_oracle.c; the Python reference measures ~50 steps/s/core, BASELINE.md)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games", type=int, default=65536, help="games per GPU")
+    ap.add_argument("--dephase", type=int, default=128)
+    ap.add_argument("--rows-per-game", type=int, default=64)
+    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-afterstate-features", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

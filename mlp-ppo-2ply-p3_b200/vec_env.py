@@ -150,15 +150,33 @@ class B200BackgammonVecEnv:
         infos = StepInfos(self.info_player.clone(), self.winner.clone(), self.game_score.clone(), self.flags.clone())
         return obs, self.rewards.clone(), self.dones_u8.to(torch.bool), infos
 
-    def step_device(self, actions_i32: torch.Tensor):
-        """The hot path only: K2 (step/reward/terminal/reset/dice) + K1 (legal plays of the new positions).
-        Results land in self.rewards / dones_u8 / info_* / legal_* without any host synchronisation."""
+    def _apply_actions(self, actions_i32: torch.Tensor):
+        """K2: step / reward / terminal / auto-reset / dice for every game."""
         st = self._state()
         out = StepOut(self.rewards.data_ptr(), self.dones_u8.data_ptr(), self.info_player.data_ptr(),
                       self.winner.data_ptr(), self.game_score.data_ptr(), self.flags.data_ptr())
         check(lib().bg_env_step(C.byref(st), actions_i32.data_ptr(), C.byref(out), self.status.data_ptr(), _stream()),
               "bg_env_step")
+
+    def step_device(self, actions_i32: torch.Tensor):
+        """The hot path only: K2 (step/reward/terminal/reset/dice) + K1 (legal plays of the new positions).
+        Results land in self.rewards / dones_u8 / info_* / legal_* without any host synchronisation."""
+        self._apply_actions(actions_i32)
         self._refresh_legal_moves()
+
+    def encode_resident(self, obs=True, afterstates=True):
+        """K3 into persistent buffers, no host sync: self.obs_f32 (N,198) f32 = get_observation of every game,
+        self.after_feats (cap_rows,208) bf16 = generate_all_board_features of every game (ragged, rows
+        [0, alloc_rows) valid).  What the reference computes eagerly in update_legal_moves/get_observation."""
+        from .engine import encode
+        if obs:
+            if not hasattr(self, "obs_f32"):
+                self.obs_f32 = torch.empty((self.num_envs, FEATURES), dtype=torch.float32, device=self.device)
+            encode(self.boards52, self.players, dtype=torch.float32, out=self.obs_f32)
+        if afterstates:
+            if not hasattr(self, "after_feats"):
+                self.after_feats = torch.empty((self.cap_rows, LD_BF16), dtype=torch.bfloat16, device=self.device)
+            encode(self.after52, self.row_players, dtype=torch.bfloat16, out=self.after_feats, n_rows_dev=self.alloc_rows)
 
     def random_actions(self, seed: int, t: int, out: torch.Tensor | None = None) -> torch.Tensor:
         """Uniform random policy on the device (Philox, domain "ACT1")."""
