@@ -140,6 +140,47 @@ int bg_env_step(const bg_env_state* st, const int32_t* actions, const bg_step_ou
 int bg_random_actions(const int32_t* counts, long long N, unsigned long long seed, unsigned long long stream_base,
                       uint32_t t, int32_t* actions, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K4  MLP leaf evaluator: value head of BackgammonPolicyNetwork.forward (agent/policy_network.py:58-75)
+ * v = w_v . relu(W1 x + b1) + b_v, fused with the feature encoding: input is board52 + flag, the
+ * 198-wide bf16 rows are built in shared memory and multiplied on the tcgen05 tensor cores
+ * (bf16 x bf16 -> f32 in TMEM); the hidden layer is reduced in the epilogue straight out of TMEM.
+ *   w1_bf16: [128][208] bf16, row h = fc1.weight[h, :198] then zeros (bg_pack_w1 does it on device)
+ *   flags / flag_all as in K3; flip_flags = 1 evaluates every row with the OTHER player's flag.
+ *   terminal_aware = 1: a row whose flag player has borne off 15 men gets the win reward 1 / 1.5 / 2
+ *   (environment/backgammon_env.py:156-171) instead of the network value (2-ply leaf rule).
+ *   n_rows_dev as in K3.
+ */
+int bg_pack_w1(const float* fc1_weight /*[128][198] f32*/, uint16_t* w1_bf16 /*[128][208]*/, void* stream);
+int bg_mlp_value(const int8_t* boards52, const int8_t* flags, int flag_all, int flip_flags, long long B,
+                 const unsigned long long* n_rows_dev /*nullable*/, const uint16_t* w1_bf16,
+                 const float* b1 /*[128]*/, const float* wv /*[128]*/, float bv, int terminal_aware,
+                 float* values, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5  2-ply search (the reference's own 2-ply, moves/expect_minmax.py:1-206, is
+ * commented-out code, so the definition is the build's, on the reference's live primitives).
+ * Pipeline (mlp-ppo-2ply-p3_b200/twoply.py): K1 on the roots -> bg_movegen_replies_slab on the root
+ * afterstates -> bg_mlp_value on the replies (terminal_aware) and on the afterstates (pass value)
+ * -> bg_twoply_scores -> bg_segment_argmax.
+ */
+/* replies of the OPPONENT of movers[i] to each of M positions for each of the 21 sorted rolls
+ * (moves/get_all_dice_rolls.py:5-34 order): work item i*21+r; counts/starts/counts_true have M*21
+ * entries; workspace must hold bg_movegen_workspace_bytes(M*21). Otherwise as bg_movegen_slab. */
+int bg_movegen_replies_slab(const int8_t* positions52, const int8_t* movers, long long M,
+                            int max_rows_per_board, int8_t* replies52, long long reply_capacity_rows,
+                            int8_t* row_players /*nullable*/, int32_t* counts_true /*nullable*/, int32_t* counts,
+                            long long* starts, unsigned long long* alloc_rows, int32_t* status, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* scores[i] = +win reward if movers[i] has borne off 15 in after52[i], else
+ * -sum_r p_r * (max over the replies of (i,r) of leaf_values, or pass_values[i] when there is no reply) */
+int bg_twoply_scores(const float* leaf_values, const long long* reply_starts, const int32_t* reply_counts,
+                     const float* pass_values, const int8_t* after52, const int8_t* movers, long long M,
+                     float* scores, void* stream);
+/* best[b] = lowest index (within block b) of the maximum of scores[starts[b] .. +counts[b]), -1 if empty */
+int bg_segment_argmax(const float* scores, const long long* starts, const int32_t* counts, long long B,
+                      int32_t* best, float* best_score /*nullable*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

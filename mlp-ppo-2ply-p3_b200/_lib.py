@@ -46,6 +46,11 @@ SIGNATURES = {
     "bg_env_reset": (_I, [C.POINTER(EnvState), _V, _V, _V]),
     "bg_env_step": (_I, [C.POINTER(EnvState), _V, C.POINTER(StepOut), _V, _V]),
     "bg_random_actions": (_I, [_V, _LL, _U64, _U64, _U32, _V, _V]),
+    "bg_movegen_replies_slab": (_I, [_V, _V, _LL, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
+    "bg_twoply_scores": (_I, [_V, _V, _V, _V, _V, _V, _LL, _V, _V]),
+    "bg_segment_argmax": (_I, [_V, _V, _V, _LL, _V, _V, _V]),
+    "bg_pack_w1": (_I, [_V, _V, _V]),
+    "bg_mlp_value": (_I, [_V, _V, _I, _I, _LL, _V, _V, _V, _V, _F, _I, _V, _V]),
 }
 
 _lib = None

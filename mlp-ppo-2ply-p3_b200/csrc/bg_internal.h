@@ -16,7 +16,9 @@ int bg_set_error_msg(int code, const char* msg);
 int bg_sm_count();
 
 namespace bg {
-int movegen_run(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B, int mode,
+// B work items; replicate == 21: item g = (position g/21, sorted roll g%21), player = players[g/21] ^ flip_player
+int movegen_run(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B, int replicate,
+                int flip_player, int mode,
                 const long long* offsets, int max_rows, int8_t* after, long long after_cap_rows,
                 int8_t* row_players, int32_t* counts_true, int32_t* counts, long long* starts, unsigned long long* alloc,
                 int32_t* status, void* workspace, size_t ws_bytes, cudaStream_t stream);

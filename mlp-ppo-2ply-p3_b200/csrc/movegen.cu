@@ -28,6 +28,9 @@ namespace bg {
 
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 
+__device__ __constant__ int8_t kRoll21[21][2] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {2, 2}, {2, 3}, {2, 4}, {2, 5}, {2, 6},
+                                                {3, 3}, {3, 4}, {3, 5}, {3, 6}, {4, 4}, {4, 5}, {4, 6}, {5, 5}, {5, 6}, {6, 6}};
+
 template <int CAP, int HS>
 struct WarpScratch {
     uint32_t list[2][6][CAP];   // two level lists, SoA: lo.lo lo.hi hi.lo hi.hi hit occ
@@ -228,7 +231,7 @@ template <int CAP, int HS>
 __global__ void __launch_bounds__(256) movegen_kernel(
     const int8_t* __restrict__ boards, const int8_t* __restrict__ players, const int8_t* __restrict__ dice,
     long long B, const unsigned int* __restrict__ nwork_dev, const int32_t* __restrict__ worklist,
-    int mode, const long long* __restrict__ offsets, int max_rows,
+    int replicate, int flip_player, int mode, const long long* __restrict__ offsets, int max_rows,
     int8_t* __restrict__ after, long long after_cap_rows, int8_t* __restrict__ row_players,
     int32_t* __restrict__ counts_true, int32_t* __restrict__ counts, long long* __restrict__ starts,
     unsigned long long* __restrict__ alloc, int32_t* __restrict__ status,
@@ -246,11 +249,16 @@ __global__ void __launch_bounds__(256) movegen_kernel(
         const long long g = worklist ? (long long)worklist[wi] : (long long)wi;
 
         // ---- load the root (13 words, coalesced) and build the mover-relative view
-        const uint32_t* bw = reinterpret_cast<const uint32_t*>(boards + g * kBoardBytes);
+        // replicate == 21: work item g is (position g / 21, sorted roll g % 21) -- the 2-ply opponent expansion
+        // in the roll order of get_all_dice_rolls_tensor (moves/get_all_dice_rolls.py:19-32)
+        const long long src = replicate > 1 ? g / replicate : g;
+        const uint32_t* bw = reinterpret_cast<const uint32_t*>(boards + src * kBoardBytes);
         uint32_t w = lane < kBoardWords ? bw[lane] : 0u;
         if (lane < kBoardWords) S.rootw[lane] = w;
-        const int player = players[g] & 1;
-        const int d0 = dice[2 * g], d1 = dice[2 * g + 1];
+        const int player = (players[src] ^ flip_player) & 1;
+        int d0, d1;
+        if (replicate > 1) { const int r = (int)(g - src * replicate); d0 = kRoll21[r][0]; d1 = kRoll21[r][1]; }
+        else { d0 = dice[2 * g]; d1 = dice[2 * g + 1]; }
         const int p = lane < 24 ? lane : 0;
         uint32_t ownw = __shfl_sync(kFull, w, (player ? 6 : 0) + (p >> 2));
         uint32_t oppw = __shfl_sync(kFull, w, (player ? 0 : 6) + (p >> 2));
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(256) movegen_kernel(
 
 template <int CAP, int HS, int WARPS>
 static int launch_movegen(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B,
-                          const unsigned int* nwork_dev, const int32_t* worklist, int mode,
+                          const unsigned int* nwork_dev, const int32_t* worklist, int replicate, int flip_player, int mode,
                           const long long* offsets, int max_rows, int8_t* after, long long after_cap_rows,
                           int8_t* row_players, int32_t* counts_true, int32_t* counts, long long* starts, unsigned long long* alloc,
                           int32_t* status, unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr,
@@ -359,7 +367,7 @@ static int launch_movegen(const int8_t* boards, const int8_t* players, const int
     long long grid = (long long)bg_sm_count() * occ;
     if (grid_hint > 0 && grid > grid_hint) grid = grid_hint;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(boards, players, dice, B, nwork_dev, worklist, mode, offsets,
+    kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(boards, players, dice, B, nwork_dev, worklist, replicate, flip_player, mode, offsets,
                                                        max_rows, after, after_cap_rows, row_players, counts_true, counts,
                                                        starts, alloc, status, work_ctr, overflow_list, overflow_ctr);
     return bg_set_error(cudaGetLastError(), "movegen: launch");
@@ -372,13 +380,15 @@ using namespace bg;
 // Workspace layout (bytes): [0] work_ctr u32, [4] overflow_ctr u32, [8] work_ctr2 u32, [64..] overflow_list int32[B]
 extern "C" size_t bg_movegen_workspace_bytes(long long B) { return 64 + sizeof(int32_t) * (size_t)(B > 0 ? B : 1); }
 
-int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B, int mode,
+int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B, int replicate,
+                    int flip_player, int mode,
                     const long long* offsets, int max_rows, int8_t* after, long long after_cap_rows,
                     int8_t* row_players, int32_t* counts_true, int32_t* counts, long long* starts,
                     unsigned long long* alloc, int32_t* status, void* workspace, size_t ws_bytes, cudaStream_t stream) {
     if (B < 0) return bg_set_error_msg(BG_ERR_INVALID, "movegen: negative batch");
     if (B == 0) return BG_OK;
-    if (!boards || !players || !dice || !status || !workspace)
+    if (replicate < 1) replicate = 1;
+    if (!boards || !players || (!dice && replicate == 1) || !status || !workspace)
         return bg_set_error_msg(BG_ERR_INVALID, "movegen: null pointer");
     if (mode != 0 && !after) return bg_set_error_msg(BG_ERR_INVALID, "movegen: null output");
     if (mode == 1 && !offsets) return bg_set_error_msg(BG_ERR_INVALID, "movegen: null offsets");
@@ -393,13 +403,15 @@ int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* d
     cudaError_t e = cudaMemsetAsync(ws, 0, 64, stream);
     if (e != cudaSuccess) return bg_set_error(e, "movegen: memset");
     int rc = launch_movegen<BG_MOVEGEN_CAP_SMALL, 2 * BG_MOVEGEN_CAP_SMALL, 8>(
-        boards, players, dice, B, nullptr, nullptr, mode, offsets, max_rows, after, after_cap_rows, row_players,
+        boards, players, dice, B, nullptr, nullptr, replicate, flip_player, mode, offsets, max_rows, after,
+        after_cap_rows, row_players,
         counts_true, counts, starts, alloc, status, work_ctr, overflow_list, overflow_ctr, (B + 7) / 8, stream);
     if (rc != BG_OK) return rc;
     // Large-scratch pass over the (rare) positions whose levels did not fit: one warp per CTA, work count read
     // from device memory so no host synchronisation is needed.  Positions that do not fit even this scratch
     // raise BG_STATUS_SCRATCH_OVERFLOW (never dropped silently).
     return launch_movegen<BG_MOVEGEN_CAP_BIG, BG_MOVEGEN_HASH_BIG, 1>(
-        boards, players, dice, B, overflow_ctr, overflow_list, mode, offsets, max_rows, after, after_cap_rows,
+        boards, players, dice, B, overflow_ctr, overflow_list, replicate, flip_player, mode, offsets, max_rows, after,
+        after_cap_rows,
         row_players, counts_true, counts, starts, alloc, status, work_ctr2, nullptr, nullptr, 0, stream);
 }

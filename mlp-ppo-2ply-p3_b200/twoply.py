@@ -1,0 +1,100 @@
+"""2-ply lookahead and 1-ply greedy on the device (K5), built from K1 (legal plays), K4 (tensor-core MLP
+leaf evaluation fused with the encoder) and two segmented reductions.
+
+The reference's own 2-ply (src/moves/expect_minmax.py:1-206) is commented-out code; this implements the
+definition of SURVEY.md 8(c) on the reference's live primitives:
+
+    A      = get_all_possible_moves(me, board, roll)                       (afterstates, reference order)
+    score_i = +win_reward(A_i)                      if me has borne off 15 in A_i
+            = - sum_{r in 21 rolls} p_r * v_r       otherwise, with
+    v_r    = max_j leaf(B_ij),  B_i. = get_all_possible_moves(opp, A_i, r);  V(encode(A_i, opp)) if no reply
+    leaf(B) = win_reward(B) if opp has borne off 15 else V(encode(B, flag=opp))
+    choice = argmax_i score_i (lowest index on ties)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import BgError, check, lib
+from .engine import MovegenWorkspace, _stream, legal_moves
+from .value_net import ValueNet
+
+
+def segment_argmax(scores: torch.Tensor, starts: torch.Tensor, counts: torch.Tensor):
+    B = counts.shape[0]
+    best = torch.empty(B, dtype=torch.int32, device=scores.device)
+    best_score = torch.empty(B, dtype=torch.float32, device=scores.device)
+    with torch.cuda.device(scores.device):
+        check(lib().bg_segment_argmax(scores.data_ptr(), starts.data_ptr(), counts.data_ptr(), B, best.data_ptr(),
+                                      best_score.data_ptr(), _stream()), "bg_segment_argmax")
+    return best, best_score
+
+
+def greedy_actions(env, net: ValueNet):
+    """1-ply greedy (BASELINE config 3): argmax_i V(encode(A_i, flag=mover)) over each game's legal plays,
+    straight from the env's ragged afterstate buffer.  -> (actions (N,) i32 (-1 where no legal play), values)"""
+    vals = net.values(env.after52, env.row_players, n_rows_dev=env.alloc_rows)
+    return segment_argmax(vals, env.legal_starts, env.legal_counts)
+
+
+class TwoPlySearch:
+    def __init__(self, net: ValueNet, max_afterstates_per_chunk: int = 65536, replies_per_position: int = 40):
+        self.net = net
+        self.chunk = int(max_afterstates_per_chunk)
+        self.rpp = int(replies_per_position)
+        self.leaves_evaluated = 0
+
+    def _score_chunk(self, A: torch.Tensor, movers: torch.Tensor) -> torch.Tensor:
+        dev = A.device
+        M = A.shape[0]
+        W = M * 21
+        ws = MovegenWorkspace(W, dev)
+        counts = torch.empty(W, dtype=torch.int32, device=dev)
+        starts = torch.empty(W, dtype=torch.int64, device=dev)
+        alloc = torch.zeros(1, dtype=torch.int64, device=dev)
+        cap = max(W * self.rpp, 4096)
+        L = lib()
+        while True:
+            replies = torch.empty((cap, 52), dtype=torch.int8, device=dev)
+            rowp = torch.empty(cap, dtype=torch.int8, device=dev)
+            alloc.zero_()
+            ws.status.zero_()
+            with torch.cuda.device(dev):
+                check(L.bg_movegen_replies_slab(A.data_ptr(), movers.data_ptr(), M, 0, replies.data_ptr(), cap,
+                                                rowp.data_ptr(), None, counts.data_ptr(), starts.data_ptr(),
+                                                alloc.data_ptr(), ws.status.data_ptr(), ws.buf.data_ptr(), ws.nbytes,
+                                                _stream()), "bg_movegen_replies_slab")
+            st = int(ws.status.item())
+            if st & 4:                      # output overflow: grow and redo (never dropped silently)
+                cap *= 2
+                continue
+            if st:
+                raise BgError(f"2-ply reply generation: device status {st}: {_lib.status_message(st)}")
+            break
+        n_leaves = int(alloc.item())
+        self.leaves_evaluated += n_leaves
+        leaf_v = self.net.values(replies, rowp, terminal_aware=True, n_rows_dev=alloc)
+        pass_v = self.net.values(A, movers, flip_flags=True)
+        scores = torch.empty(M, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(L.bg_twoply_scores(leaf_v.data_ptr(), starts.data_ptr(), counts.data_ptr(), pass_v.data_ptr(),
+                                     A.data_ptr(), movers.data_ptr(), M, scores.data_ptr(), _stream()), "bg_twoply_scores")
+        return scores
+
+    def score_afterstates(self, after52: torch.Tensor, movers: torch.Tensor) -> torch.Tensor:
+        """2-ply score of every root afterstate (movers[i] = the player who made play i)."""
+        M = after52.shape[0]
+        out = torch.empty(M, dtype=torch.float32, device=after52.device)
+        for m0 in range(0, M, self.chunk):
+            m1 = min(M, m0 + self.chunk)
+            out[m0:m1] = self._score_chunk(after52[m0:m1].contiguous(), movers[m0:m1].contiguous())
+        return out
+
+    def search(self, boards52: torch.Tensor, players: torch.Tensor, dice: torch.Tensor):
+        """-> best (B,) i32 index into each root's legal plays (-1 if none), scores (total,) f32,
+        offsets (B+1,) i64, afterstates (total,52) i8 (reference legal_moves order)."""
+        counts, offsets, A, rowp = legal_moves(boards52, players, dice, with_row_players=True)
+        scores = self.score_afterstates(A, rowp) if A.shape[0] else torch.empty(0, dtype=torch.float32, device=A.device)
+        best, _ = segment_argmax(scores, offsets[:-1].contiguous(), counts.clamp(min=0).contiguous())
+        return best, scores, offsets, A

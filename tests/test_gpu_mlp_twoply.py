@@ -1,0 +1,154 @@
+"""GPU tests of K4 (tcgen05 MLP leaf evaluator fused with the encoder) and K5 (2-ply / 1-ply greedy).
+
+Floating point: the GPU evaluates with bf16 inputs/weights and f32 accumulation (TMEM).  Tolerances:
+  * against the oracle evaluated on bf16-ROUNDED operands (exact products, double accumulate): 2e-4 abs
+    (accumulation-order noise only);
+  * against the f32 reference network: 2e-2 abs for |V| <~ 2 (SURVEY.md 8(c) stated tolerance);
+  * 2-ply scores: same bounds; move choices compared when the oracle's top-2 gap exceeds the tolerance.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+TOL_BF16, TOL_F32 = 2e-4, 2e-2
+
+
+@pytest.fixture(scope="module")
+def bg():
+    import bg_b200
+    return bg_b200
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import bg_oracle
+    return bg_oracle
+
+
+@pytest.fixture(scope="module")
+def weights():
+    d = np.load(os.path.join(G, "mlp.npz"))
+    return d["fc1_weight"], d["fc1_bias"], d["value_weight"], float(d["value_bias"][0])
+
+
+@pytest.fixture(scope="module")
+def net(bg, weights):
+    return bg.ValueNet(weights[0], weights[1], weights[2], weights[3], "cuda:0")
+
+
+def test_mlp_value_golden_torch_forward(bg, net, O):
+    """positions of the encoder golden -> values of the reference's torch network (mlp.npz was produced by
+    BackgammonPolicyNetwork.forward on these features)."""
+    e = np.load(os.path.join(G, "encode.npz"))
+    m = np.load(os.path.join(G, "mlp.npz"))
+    b = torch.as_tensor(e["boards"]).cuda()
+    v0 = net.values(b[:200], 0).cpu().numpy()
+    v1 = net.values(b[200:400], 1).cpu().numpy()
+    got = np.concatenate([v0, v1])
+    assert np.max(np.abs(got - m["values"])) < TOL_F32
+    x = m["x"]
+    tight = O.mlp_value_bf16(x, m["fc1_weight"], m["fc1_bias"], m["value_weight"], float(m["value_bias"][0]))
+    assert np.max(np.abs(got - tight)) < TOL_BF16
+
+
+@pytest.mark.parametrize("B", [1, 127, 128, 129, 1000, 40000])
+def test_mlp_value_vs_oracle_sizes(bg, net, O, weights, B):
+    d = np.load(os.path.join(G, "allrolls.npz"))
+    rng = np.random.RandomState(B)
+    rows = d["after"][rng.randint(0, len(d["after"]), B)]
+    flags = rng.randint(0, 2, B).astype(np.int8)
+    got = net.values(torch.as_tensor(rows).cuda(), torch.as_tensor(flags).cuda()).cpu().numpy()
+    x = O.encode(O.unpack52(rows), flags)
+    ref = O.mlp_value(x, *weights)
+    assert np.max(np.abs(got - ref)) < TOL_F32
+    n = min(B, 600)
+    tight = O.mlp_value_bf16(x[:n], *weights)
+    assert np.max(np.abs(got[:n] - tight)) < TOL_BF16
+    # flip_flags evaluates with the other player's flag
+    got_f = net.values(torch.as_tensor(rows).cuda(), torch.as_tensor(flags).cuda(), flip_flags=True).cpu().numpy()
+    ref_f = O.mlp_value(O.encode(O.unpack52(rows), 1 - flags), *weights)
+    assert np.max(np.abs(got_f - ref_f)) < TOL_F32
+
+
+def test_mlp_terminal_aware(bg, net, O, weights):
+    d = np.load(os.path.join(G, "env_end.npz"))
+    after = O.pack52(d["after"])
+    pl = d["player"].astype(np.int8)
+    got = net.values(torch.as_tensor(after).cuda(), torch.as_tensor(pl).cuda(), terminal_aware=True).cpu().numpy()
+    assert got.tolist() == d["reward"].tolist()
+
+
+def test_mlp_reference_state_dict_keys(bg, weights):
+    sd = {"fc1.weight": torch.tensor(weights[0]), "fc1.bias": torch.tensor(weights[1]),
+          "action_head.weight": torch.zeros(500, 128), "action_head.bias": torch.zeros(500),
+          "value_head.weight": torch.tensor(weights[2]), "value_head.bias": torch.tensor([weights[3]])}
+    n = bg.ValueNet.from_state_dict(sd, "cuda:0")
+    v = n.values(bg.initial_board52(1, "cuda:0"), 0)
+    assert torch.isfinite(v).all()
+
+
+def _check_twoply(bg, O, net, weights, boards52, players, dice):
+    s = bg.TwoPlySearch(net, max_afterstates_per_chunk=64)
+    best, scores, offsets, A = s.search(torch.as_tensor(boards52).cuda(), torch.as_tensor(players).cuda(),
+                                        torch.as_tensor(dice).cuda())
+    best, scores, offsets = best.cpu().numpy(), scores.cpu().numpy(), offsets.cpu().numpy()
+    leaves = 0
+    for i in range(len(players)):
+        b96 = O.unpack52(boards52[i])[0]
+        ref, rbest, nl = O.twoply(b96, int(players[i]), int(dice[i, 0]), int(dice[i, 1]), *weights)
+        tight, tbest, _ = O.twoply(b96, int(players[i]), int(dice[i, 0]), int(dice[i, 1]), *weights, use_bf16=True)
+        leaves += nl
+        got = scores[offsets[i]:offsets[i + 1]]
+        assert len(got) == len(ref)
+        if len(ref) == 0:
+            assert best[i] == -1
+            continue
+        assert np.max(np.abs(got - ref)) < TOL_F32, i
+        assert np.max(np.abs(got - tight)) < TOL_BF16, i
+        srt = np.sort(ref)[::-1]
+        if len(srt) == 1 or srt[0] - srt[1] > 2 * TOL_F32:
+            assert best[i] == rbest, i
+        assert got[best[i]] == got.max() and best[i] == int(np.argmax(got))
+    return leaves
+
+
+def test_twoply_vs_oracle_random_play(bg, O, net, weights):
+    d = np.load(os.path.join(G, "allrolls.npz"))
+    rng = np.random.RandomState(0)
+    idx = rng.choice(len(d["counts"]), 40, replace=False)
+    leaves = _check_twoply(bg, O, net, weights, d["boards"][idx], d["players"][idx], d["dice"][idx])
+    assert leaves > 10000
+
+
+def test_twoply_endgames_and_golden(bg, O, net, weights):
+    g = np.load(os.path.join(G, "twoply.npz"))
+    _check_twoply(bg, O, net, weights, g["boards"], g["players"], g["dice"])
+    s = bg.TwoPlySearch(net)
+    best, scores, offsets, A = s.search(torch.as_tensor(g["boards"]).cuda(), torch.as_tensor(g["players"]).cuda(),
+                                        torch.as_tensor(g["dice"]).cuda())
+    assert np.max(np.abs(scores.cpu().numpy() - g["scores"])) < TOL_F32       # restatement on reference primitives
+
+
+def test_greedy_one_ply_vs_oracle(bg, O, net, weights):
+    env = bg.B200BackgammonVecEnv(num_envs=512, device="cuda:0", seed=77, check_every=0)
+    env.reset()
+    for t in range(30):
+        env.step(env.random_actions(5, t), return_obs=False)
+    acts, vals = bg.greedy_actions(env, net)
+    acts, vals = acts.cpu().numpy(), vals.cpu().numpy()
+    rows, st, cn, pl = env.after52.cpu().numpy(), env.legal_starts.cpu().numpy(), env.legal_counts.cpu().numpy(), env.players.cpu().numpy()
+    for g in range(0, 512, 7):
+        n = int(cn[g])
+        if n == 0:
+            assert acts[g] == -1
+            continue
+        x = O.encode(O.unpack52(rows[st[g]:st[g] + n]), int(pl[g]))
+        ref = O.mlp_value(x, *weights)
+        assert abs(vals[g] - ref.max()) < TOL_F32
+        srt = np.sort(ref)[::-1]
+        if n == 1 or srt[0] - srt[1] > 2 * TOL_F32:
+            assert acts[g] == int(np.argmax(ref))

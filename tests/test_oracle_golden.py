@@ -121,3 +121,22 @@ def test_mlp_value_matches_torch_reference():
 def test_pack_roundtrip():
     d = np.load(os.path.join(G, "allrolls.npz"))
     assert np.array_equal(O.pack52(O.unpack52(d["boards"])), d["boards"])
+
+
+def test_twoply_matches_restatement_on_reference_primitives():
+    """bg_twoply (SURVEY 8(c) definition) vs the Python restatement built from the reference's own
+    get_all_possible_moves / generate_all_board_features / BackgammonPolicyNetwork (make_golden_twoply.py)."""
+    p = os.path.join(G, "twoply.npz")
+    if not os.path.exists(p):
+        pytest.skip("twoply golden not generated")
+    g = np.load(p)
+    m = np.load(os.path.join(G, "mlp.npz"))
+    w = (m["fc1_weight"], m["fc1_bias"], m["value_weight"], float(m["value_bias"][0]))
+    off = 0
+    for i in range(len(g["counts"])):
+        sc, best, leaves = O.twoply(O.unpack52(g["boards"][i])[0], int(g["players"][i]), int(g["dice"][i, 0]),
+                                    int(g["dice"][i, 1]), *w)
+        n = int(g["counts"][i])
+        assert len(sc) == n and leaves == g["leaves"][i]
+        assert np.max(np.abs(sc - g["scores"][off:off + n])) < 5e-6
+        off += n
