@@ -8,6 +8,7 @@
 // Per-warp shared-memory scratch of K1: boards per level (lists) before a position is handed to the
 // large-scratch pass, and the size of that pass (DESIGN.md "K1 capacity").
 #define BG_MOVEGEN_CAP_SMALL 128
+#define BG_MOVEGEN_CAP_MID 512
 #define BG_MOVEGEN_CAP_BIG 3072
 #define BG_MOVEGEN_HASH_BIG 4096
 

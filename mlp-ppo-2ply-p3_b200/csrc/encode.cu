@@ -71,24 +71,54 @@ __device__ __forceinline__ void stage_boards(const int8_t* __restrict__ boards, 
     for (int i = threadIdx.x; i < rows * kBoardWords; i += kEncThreads) sm[i] = __ldg(src + i);
 }
 
+// bf16 rows.  Phase 1 (uniform, no divergence on the common path): item (row, j<48) expands point j of the row
+// (j = side*24 + point = byte j of board52) into its 4 units at element 4j (+2 for PLAYER2: the bar/off pair of
+// PLAYER1 sits at 96,97), items j>=48 write the bar/off pairs, the flag pair and the zero padding.  Phase 2: the
+// finished tile (kBfRows x ld bf16, contiguous in global memory as well) is copied out with 16-byte stores.
+constexpr int kBfRows = 64;
+
 __global__ void __launch_bounds__(kEncThreads) encode_bf16_kernel(const int8_t* __restrict__ boards,
                                                                   const int8_t* __restrict__ flags, int flag_all,
                                                                   long long B, const unsigned long long* __restrict__ n_rows_dev,
                                                                   uint16_t* __restrict__ out, int cpr /* ld/8 */) {
-    __shared__ __align__(16) uint32_t sm[kEncRows * kBoardWords];
-    __shared__ int8_t sflag[kEncRows];
+    extern __shared__ __align__(16) uint32_t enc_smem[];
+    uint32_t* tile = enc_smem;                                   // kBfRows x (cpr*4) words
+    uint32_t* sm = tile + kBfRows * cpr * 4;                     // kBfRows x 13 words of boards
+    int8_t* sflag = reinterpret_cast<int8_t*>(sm + kBfRows * kBoardWords);
     if (n_rows_dev) B = min(B, (long long)*n_rows_dev);
-    for (long long row0 = (long long)blockIdx.x * kEncRows; row0 < B; row0 += (long long)gridDim.x * kEncRows) {
-        int rows = (int)min((long long)kEncRows, B - row0);
-        stage_boards(boards, row0, rows, sm);
+    const int wpr = cpr * 4;                                     // words per output row
+    const int items = 48 + 3 + (wpr - 99);                       // points, bar/off x2, flags, zero words
+    for (long long row0 = (long long)blockIdx.x * kBfRows; row0 < B; row0 += (long long)gridDim.x * kBfRows) {
+        const int rows = (int)min((long long)kBfRows, B - row0);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
+        for (int i = threadIdx.x; i < rows * kBoardWords; i += kEncThreads) sm[i] = __ldg(src + i);
         for (int i = threadIdx.x; i < rows; i += kEncThreads) sflag[i] = flags ? (flags[row0 + i] & 1) : (int8_t)flag_all;
         __syncthreads();
-        uint4* dst = reinterpret_cast<uint4*>(out + row0 * (long long)cpr * 8);
-        const int total = rows * cpr;
-        for (int c = threadIdx.x; c < total; c += kEncThreads) {
-            int r = c / cpr, k = c - r * cpr;
-            dst[c] = bf16_chunk(reinterpret_cast<const int8_t*>(sm) + r * kBoardBytes, sflag[r], k);
+        // warp w takes rows w, w+8, ...; lanes sweep the row's items (no integer division, near-uniform control flow)
+        for (int r = threadIdx.x >> 5; r < rows; r += kEncThreads / 32) {
+            const int8_t* b = reinterpret_cast<const int8_t*>(sm) + r * kBoardBytes;
+            uint32_t* orow = tile + r * wpr;
+            for (int j = threadIdx.x & 31; j < items; j += 32) {
+                if (j < 48) {
+                    const uint2 u = point_units_bf16(b[j]);
+                    const int w = 2 * j + (j >= 24 ? 1 : 0);     // word index of element 4j (+2)
+                    orow[w] = u.x; orow[w + 1] = u.y;
+                } else if (j == 48) {
+                    orow[48] = bf16_bits((float)b[48] / 2.0f) | (bf16_bits((float)b[50] / 15.0f) << 16);   // elements 96,97
+                } else if (j == 49) {
+                    orow[97] = bf16_bits((float)b[49] / 2.0f) | (bf16_bits((float)b[51] / 15.0f) << 16);   // elements 194,195
+                } else if (j == 50) {
+                    orow[98] = sflag[r] == 0 ? 0x00003F80u : 0x3F800000u;                                   // elements 196,197
+                } else {
+                    orow[99 + (j - 51)] = 0u;                                                               // padding
+                }
+            }
         }
+        __syncthreads();
+        const uint4* t4 = reinterpret_cast<const uint4*>(tile);
+        uint4* dst = reinterpret_cast<uint4*>(out + row0 * (long long)cpr * 8);
+        const int nvec = rows * cpr;
+        for (int c = threadIdx.x; c < nvec; c += kEncThreads) dst[c] = t4[c];
         __syncthreads();
     }
 }
@@ -136,9 +166,18 @@ extern "C" int bg_encode_f32(const int8_t* boards52, const int8_t* flags, int fl
 
 extern "C" int bg_encode_bf16(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
                               const unsigned long long* n_rows_dev, uint16_t* out, long long ld, void* stream) {
-    if (B < 0 || ld < 200 || (ld & 7) || ld > 4096) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: bad B or ld (need ld >= 200, multiple of 8)");
+    if (B < 0 || ld < 200 || (ld & 7) || ld > 1024) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: bad B or ld (need ld >= 200, multiple of 8)");
     if (B == 0) return BG_OK;
     if (!boards52 || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: null pointer");
-    encode_bf16_kernel<<<enc_grid(B), kEncThreads, 0, (cudaStream_t)stream>>>(boards52, flags, flag_all & 1, B, n_rows_dev, out, (int)(ld / 8));
+    const int cpr = (int)(ld / 8);
+    const size_t smem = (size_t)kBfRows * cpr * 16 + (size_t)kBfRows * kBoardBytes + kBfRows;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(encode_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return bg_set_error(e, "bg_encode_bf16: cudaFuncSetAttribute");
+    }
+    long long tiles = (B + kBfRows - 1) / kBfRows;
+    long long grid = (long long)bg_sm_count() * 7;
+    if (grid > tiles) grid = tiles;
+    encode_bf16_kernel<<<(unsigned)grid, kEncThreads, smem, (cudaStream_t)stream>>>(boards52, flags, flag_all & 1, B, n_rows_dev, out, cpr);
     return bg_set_error(cudaGetLastError(), "bg_encode_bf16: launch");
 }

@@ -31,18 +31,25 @@ constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 __device__ __constant__ int8_t kRoll21[21][2] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {2, 2}, {2, 3}, {2, 4}, {2, 5}, {2, 6},
                                                 {3, 3}, {3, 4}, {3, 5}, {3, 6}, {4, 4}, {4, 5}, {4, 6}, {5, 5}, {5, 6}, {6, 6}};
 
+// Per-warp scratch.  Two level lists ("regions") of CAP boards each plus one slot for the root:
+// node i of region r lives at index r*CAP + i, the root at 2*CAP.  A board is a 16-byte key
+// (x = points 0..7, y = points 8..15, z = points 16..23 as nibbles, w = hit mask | bar << 24 | off << 28)
+// plus its occupancy mask, so loads/stores are one LDS.128/STS.128 + one 32-bit access per lane.
 template <int CAP, int HS>
 struct WarpScratch {
-    uint32_t list[2][6][CAP];   // two level lists, SoA: lo.lo lo.hi hi.lo hi.hi hit occ
+    uint4 key[2 * CAP + 1];
+    uint32_t occ[2 * CAP + 1];
     uint32_t pm[CAP];           // per parent: move mask | (special+1) << 24
-    uint32_t hash[HS];          // open-addressing set of indices into the destination list
+    uint32_t hash[HS];          // open-addressing set of node indices of the destination region
     uint16_t off[CAP + 2];      // exclusive prefix of per-parent move counts
     uint32_t rootw[kBoardWords];
-    uint32_t pad;
+    uint32_t pad[2];
 };
 
 template <int CAP, int HS>
 struct Warp {
+    static_assert(CAP * 16 >= 32 * kBoardWords * 4, "a region must be able to stage 32 output rows");
+    static constexpr int kRoot = 2 * CAP;
     WarpScratch<CAP, HS>& S;
     Root R;
     int lane;
@@ -50,51 +57,53 @@ struct Warp {
 
     __device__ Warp(WarpScratch<CAP, HS>& s, int l) : S(s), lane(l), overflow(false) {}
 
-    __device__ __forceinline__ Node load(int b, int i) const {
+    __device__ __forceinline__ Node load(int i) const {
+        uint4 k = S.key[i];
         Node n;
-        n.lo = (unsigned long long)S.list[b][0][i] | ((unsigned long long)S.list[b][1][i] << 32);
-        n.hi = (unsigned long long)S.list[b][2][i] | ((unsigned long long)S.list[b][3][i] << 32);
-        n.hit = S.list[b][4][i];
-        n.occ = S.list[b][5][i];
+        n.lo = (unsigned long long)k.x | ((unsigned long long)k.y << 32);
+        n.hi = (unsigned long long)k.z | ((unsigned long long)(k.w >> 24) << 32);
+        n.hit = k.w & 0xFFFFFFu;
+        n.occ = S.occ[i];
         return n;
     }
-    __device__ __forceinline__ void store(int b, int i, const Node& n) {
-        S.list[b][0][i] = (uint32_t)n.lo; S.list[b][1][i] = (uint32_t)(n.lo >> 32);
-        S.list[b][2][i] = (uint32_t)n.hi; S.list[b][3][i] = (uint32_t)(n.hi >> 32);
-        S.list[b][4][i] = n.hit; S.list[b][5][i] = n.occ;
+    static __device__ __forceinline__ uint4 key_of(const Node& n) {
+        return make_uint4((uint32_t)n.lo, (uint32_t)(n.lo >> 32), (uint32_t)n.hi, n.hit | ((uint32_t)(n.hi >> 32) << 24));
     }
-    __device__ __forceinline__ bool same(int b, int i, const Node& n) const {
-        return S.list[b][0][i] == (uint32_t)n.lo && S.list[b][1][i] == (uint32_t)(n.lo >> 32) &&
-               S.list[b][2][i] == (uint32_t)n.hi && S.list[b][3][i] == (uint32_t)(n.hi >> 32) &&
-               S.list[b][4][i] == n.hit;
+    __device__ __forceinline__ void store(int i, const Node& n) { S.key[i] = key_of(n); S.occ[i] = n.occ; }
+    __device__ __forceinline__ bool same(int i, const uint4& k) const {
+        uint4 e = S.key[i];
+        return e.x == k.x && e.y == k.y && e.z == k.z && e.w == k.w;
+    }
+    static __device__ __forceinline__ uint32_t hash_key(const uint4& k) {
+        uint32_t h = k.x * 0x9E3779B1u ^ k.y * 0x85EBCA77u ^ k.z * 0xC2B2AE3Du ^ k.w * 0x27D4EB2Fu;
+        return h ^ (h >> 15);
     }
     __device__ void clear_hash() {
         for (int i = lane; i < HS; i += 32) S.hash[i] = kEmpty;
         __syncwarp();
     }
-    // true if a board equal to n is already in destination list b (via the hash set)
-    __device__ __forceinline__ bool in_set(int b, const Node& n) const {
-        uint32_t s = hash_node(n) & (HS - 1);
+    __device__ __forceinline__ bool in_set(const uint4& k) const {
+        uint32_t s = hash_key(k) & (HS - 1);
         for (;;) {
             uint32_t e = S.hash[s];
             if (e == kEmpty) return false;
-            if (same(b, (int)e, n)) return true;
+            if (same((int)e, k)) return true;
             s = (s + 1) & (HS - 1);
         }
     }
-    __device__ __forceinline__ void set_insert(const Node& n, int pos) {
-        uint32_t s = hash_node(n) & (HS - 1);
-        while (atomicCAS(&S.hash[s], kEmpty, (uint32_t)pos) != kEmpty) s = (s + 1) & (HS - 1);
+    __device__ __forceinline__ void set_insert(const uint4& k, int idx) {
+        uint32_t s = hash_key(k) & (HS - 1);
+        while (atomicCAS(&S.hash[s], kEmpty, (uint32_t)idx) != kEmpty) s = (s + 1) & (HS - 1);
     }
 
-    // Count the one-die moves of every parent in list pb[0..np); fills S.pm / S.off. Returns the total.
-    __device__ int count_moves(int pb, int np, int d) {
+    // Count the one-die moves of the parents at [pbase, pbase+np); fills S.pm / S.off. Returns the total.
+    __device__ __forceinline__ int count_moves(int pbase, int np, int d) {
         int base = 0;
         for (int i0 = 0; i0 < np; i0 += 32) {
             int i = i0 + lane;
             int cnt = 0;
             if (i < np) {
-                Node n = load(pb, i);
+                Node n = load(pbase + i);
                 uint32_t mask; int special;
                 one_die(n, R, d, mask, special);
                 cnt = __popc(mask) + (special >= 0);
@@ -114,25 +123,23 @@ struct Warp {
         return base;
     }
 
-    // Append `keep` lanes' nodes to list cb at nc in lane order; returns the new nc (or sets overflow).
-    template <bool INSERT>
-    __device__ __forceinline__ int append(int cb, int nc, bool keep, const Node& ch) {
+    // Append `keep` lanes' nodes to the region at cbase (currently nc entries) in lane order.
+    __device__ __forceinline__ int append(int cbase, int nc, bool keep, const Node& ch, bool insert) {
         unsigned surv = __ballot_sync(kFull, keep);
         int nsurv = __popc(surv);
         if (nc + nsurv > CAP) { overflow = true; return nc; }
         if (keep) {
-            int pos = nc + __popc(surv & ((1u << lane) - 1u));
-            store(cb, pos, ch);
-            if (INSERT) set_insert(ch, pos);
+            int idx = cbase + nc + __popc(surv & ((1u << lane) - 1u));
+            store(idx, ch);
+            if (insert) set_insert(key_of(ch), idx);
         }
         __syncwarp();
         return nc + nsurv;
     }
 
-    // Append the children (die d) of parents pb[0..np) to list cb starting at nc, in reference
-    // order; children equal to an entry already in the set of cb or to an earlier child are
-    // dropped.  count_moves(pb, np, d) must have been called (total = its result).
-    __device__ int expand(int pb, int np, int d, int total, int cb, int nc) {
+    // Children (die d) of the parents at [pbase, pbase+np), in the reference's order, appended to the region at
+    // cbase (nc entries so far).  use_set: drop children equal to an entry of the set or to an earlier child.
+    __device__ __forceinline__ int expand(int pbase, int np, int d, int total, int cbase, int nc, bool use_set) {
         for (int c0 = 0; c0 < total && !overflow; c0 += 32) {
             int idx = c0 + lane;
             bool valid = idx < total;
@@ -146,82 +153,76 @@ struct Warp {
                 }
                 int j = idx - (int)S.off[lo];
                 uint32_t pmv = S.pm[lo];
-                Node p = load(pb, lo);
+                Node p = load(pbase + lo);
                 ch = apply_move(p, R, d, pmv & 0xFFFFFFu, (int)(pmv >> 24) - 1, j);
             }
-            unsigned m = __match_any_sync(kFull, ch.lo) & __match_any_sync(kFull, ch.hi) &
-                         __match_any_sync(kFull, ch.hit);
-            bool keep = valid && (__ffs(m) - 1 == lane);
-            if (keep && in_set(cb, ch)) keep = false;
-            nc = append<true>(cb, nc, keep, ch);
+            bool keep = valid;
+            if (use_set) {
+                uint4 k = key_of(ch);
+                unsigned m = __match_any_sync(kFull, ch.lo) &
+                             __match_any_sync(kFull, (unsigned long long)k.z | ((unsigned long long)k.w << 32));
+                keep = valid && (__ffs(m) - 1 == lane);
+                if (keep && in_set(k)) keep = false;
+            }
+            nc = append(cbase, nc, keep, ch, use_set);
         }
         return nc;
     }
 
-    // Level-1 boards of `root` for die d -> list b[0..n) (distinct sources => distinct boards). Returns n <= 16.
-    __device__ int first_level(const Node& root, int d, int b) {
-        uint32_t mask; int special;
-        one_die(root, R, d, mask, special);
-        int n = __popc(mask) + (special >= 0);
-        if (lane < n) store(b, lane, apply_move(root, R, d, mask, special, lane));
-        __syncwarp();
-        return n;
-    }
-
-    // Full generator.  On return the legal afterstates are list `ob`[from, from+n), reference order.
-    __device__ void generate(const Node& root, int d0, int d1, int& ob, int& from, int& n) {
-        ob = 0; from = 0; n = 0;
-        if (d0 != d1) {
-            const int hi = max(d0, d1), lo = min(d0, d1);          // get_all_moves.py:30
-            clear_hash();
-            int nF = 0;      // plays collected in list 0 (full_moves)
-            int nA1 = 0;     // leading plays of length 1 contributed by pass A
-            bool lenA2 = false, lenB2 = false;
-            // ---- pass A: larger die first (handle_moves.py:109-200, reverse=False)
-            int nA = first_level(root, hi, 1);
-            if (nA) {
-                int t2 = count_moves(1, nA, lo);                   // two_move_sequences_exist, :145-155
-                if (t2) { nF = expand(1, nA, lo, t2, 0, 0); lenA2 = true; }
-                else {                                             // singles are the plays, :192-200
-                    Node c = load(1, lane < nA ? lane : 0);
-                    nF = append<true>(0, 0, lane < nA, c);
-                    nA1 = nA;
-                    if (nA == 1) { n = 1; return; }                // skip-reverse shortcut, get_all_moves.py:43-45
-                }
-                if (overflow) return;
-            }
-            // ---- pass B: smaller die first (reverse=True), sharing full_moves / unique_boards
-            int nB = first_level(root, lo, 1);
-            if (nB) {
-                int t2 = count_moves(1, nB, hi);
-                if (t2) { nF = expand(1, nB, hi, t2, 0, nF); lenB2 = true; }
-                else if (!lenA2) {                                 // only singles anywhere: union (add_unique_board)
-                    Node c = load(1, lane < nB ? lane : 0);
-                    bool keep = lane < nB && !in_set(0, c);
-                    nF = append<true>(0, nF, keep, c);
-                }
-                // (singles of pass B next to length-2 plays of pass A are removed by the max filter
-                //  and, being last, influence nobody's dedupe: not materialised.)
-                if (overflow) return;
-            }
-            // ---- filter_full_moves_by_max_submoves (get_all_moves.py:73-94), applied AFTER dedupe
-            if (lenB2 && !lenA2) { from = nA1; n = nF - nA1; }     // length-1 plays of pass A are dropped
-            else { from = 0; n = nF; }
-        } else {
-            // ---- doubles (handle_moves.py:203-310): levels 1..4, output = deepest non-empty level
-            const int d = d0;
-            if (lane == 0) store(0, 0, root);
-            __syncwarp();
-            int pb = 0, np = 1;
-            for (int depth = 1; depth <= 4; ++depth) {
-                int t = count_moves(pb, np, d);
-                if (t == 0) break;
+    // Full generator.  On return the legal afterstates are nodes [obase, obase+n), reference order.
+    // One stage loop serves both roll kinds so that count_moves/expand are instantiated once (code size).
+    __device__ void generate(const Node& root, int d0, int d1, int& obase, int& n) {
+        obase = 0; n = 0;
+        if (lane == 0) store(kRoot, root);
+        const bool dbl = d0 == d1;
+        const int dhi = max(d0, d1), dlo = min(d0, d1);            // get_all_moves.py:30
+        if (!dbl) clear_hash(); else __syncwarp();                 // non-doubles: one set for full_moves of both passes
+        int pbase = kRoot, np = 1;
+        int nF = 0, nA1 = 0;                                       // non-doubles: plays collected in region 0
+        bool lenA2 = false, lenB2 = false;
+        for (int stage = 0; stage < 4; ++stage) {
+            // doubles (handle_moves.py:203-310): stage k expands level k -> k+1, regions alternate.
+            // non-doubles (handle_moves.py:109-200): stages 0,1 = larger die first; 2,3 = smaller die first.
+            const int d = dbl ? d0 : ((stage == 0 || stage == 3) ? dhi : dlo);
+            const int total = count_moves(pbase, np, d);
+            const bool first = !dbl && (stage & 1) == 0;           // first sub-move of a non-doubles pass
+            int cbase = 0, nc0 = 0;
+            bool use_set = true, do_expand = true;
+            if (dbl) {
+                if (total == 0) break;                             // dead end: the previous level is the answer
+                cbase = (stage & 1) ? CAP : 0;
                 clear_hash();
-                int nc = expand(pb, np, d, t, pb ^ 1, 0);
-                if (overflow) return;
-                pb ^= 1; np = nc;
-                ob = pb; n = np;
+            } else if (first) {
+                if (total == 0) { ++stage; continue; }             // no first move in this order: pass adds nothing
+                cbase = CAP; use_set = false;                      // distinct sources => distinct boards, no set
+            } else if (total > 0) {                                // two_move_sequences_exist, :145-155
+                nc0 = nF;
+                if (stage == 1) lenA2 = true; else lenB2 = true;
+            } else {
+                do_expand = false;
+                if (stage == 1 || !lenA2) {                        // singles are the plays, :192-200
+                    Node c = load(CAP + (lane < np ? lane : 0));
+                    bool keep = lane < np && !in_set(key_of(c));
+                    nF = append(0, nF, keep, c, true);
+                    if (stage == 1) {
+                        nA1 = np;
+                        if (np == 1) { n = 1; return; }            // skip-reverse shortcut, get_all_moves.py:43-45
+                    }
+                }
+                // (singles of the smaller-die-first pass next to length-2 plays of the first pass are removed by the
+                //  max filter and, being last, influence nobody's dedupe: not materialised.)
             }
+            int nc = nc0;
+            if (do_expand) nc = expand(pbase, np, d, total, cbase, nc0, use_set);      // the only call site
+            if (overflow) return;
+            if (dbl) { pbase = cbase; np = nc; obase = cbase; n = nc; }
+            else if (first) { pbase = CAP; np = nc; }
+            else { if (do_expand) nF = nc; pbase = kRoot; np = 1; }
+        }
+        if (!dbl) {
+            // filter_full_moves_by_max_submoves (get_all_moves.py:73-94), applied AFTER dedupe
+            if (lenB2 && !lenA2) { obase = nA1; n = nF - nA1; }    // length-1 plays of the first pass are dropped
+            else { obase = 0; n = nF; }
         }
     }
 };
@@ -285,8 +286,8 @@ __global__ void __launch_bounds__(256) movegen_kernel(
                    d0 < 1 || d0 > 6 || d1 < 1 || d1 > 6;
         __syncwarp();
 
-        int ob = 0, from = 0, n = 0;
-        if (!bad) W.generate(root, d0, d1, ob, from, n);
+        int obase = 0, n = 0;
+        if (!bad) W.generate(root, d0, d1, obase, n);
 
         if (bad) {
             if (lane == 0) {
@@ -327,20 +328,30 @@ __global__ void __launch_bounds__(256) movegen_kernel(
             if (start + nw > after_cap_rows) {
                 if (lane == 0) { atomicOr(status, BG_STATUS_OUTPUT_OVERFLOW); if (counts) counts[g] = 0; }
             } else {
-                // stage 32 rows x 13 words in the unused list, then copy out fully coalesced
-                uint32_t* stage = &S.list[ob ^ 1][0][0];
+                // stage 32 rows x 13 words in the region that does not hold the result, then copy out coalesced
+                uint32_t* stage = reinterpret_cast<uint32_t*>(&S.key[obase < CAP ? CAP : 0]);
                 uint32_t* gout = reinterpret_cast<uint32_t*>(after) + start * kBoardWords;
+                const int own0 = player ? 6 : 0, opp0 = player ? 0 : 6;
+                const uint32_t misc0 = S.rootw[12];
+                const uint32_t opp_bar0 = (misc0 >> (player ? 0 : 8)) & 0xFFu, opp_off0 = (misc0 >> (player ? 16 : 24)) & 0xFFu;
                 for (int r0 = 0; r0 < nw; r0 += 32) {
                     int r = r0 + lane;
                     if (r < nw) {
-                        Node nd = W.load(ob, from + r);
+                        const uint4 k = S.key[obase + r];
+                        uint32_t* row = stage + lane * kBoardWords;
+                        row[own0 + 0] = spread_nibbles(k.x);       row[own0 + 1] = spread_nibbles(k.x >> 16);
+                        row[own0 + 2] = spread_nibbles(k.y);       row[own0 + 3] = spread_nibbles(k.y >> 16);
+                        row[own0 + 4] = spread_nibbles(k.z);       row[own0 + 5] = spread_nibbles(k.z >> 16);
 #pragma unroll
-                        for (int k = 0; k < kBoardWords; ++k)
-                            stage[lane * kBoardWords + k] = node_row_word(nd, player, S.rootw, k);
+                        for (int q = 0; q < 6; ++q) row[opp0 + q] = S.rootw[opp0 + q] - spread_bits(k.w >> (4 * q));
+                        const uint32_t ob = (k.w >> 24) & 15u, oo = k.w >> 28;
+                        const uint32_t pb = opp_bar0 + (uint32_t)__popc(k.w & 0xFFFFFFu);
+                        row[12] = player == 0 ? (ob | (pb << 8) | (oo << 16) | (opp_off0 << 24))
+                                              : (pb | (ob << 8) | (opp_off0 << 16) | (oo << 24));
                     }
                     __syncwarp();
                     int rows = min(32, nw - r0);
-                    for (int k = lane; k < rows * kBoardWords; k += 32) gout[(long long)r0 * kBoardWords + k] = stage[k];
+                    for (int k2 = lane; k2 < rows * kBoardWords; k2 += 32) gout[(long long)r0 * kBoardWords + k2] = stage[k2];
                     if (row_players && lane < rows) row_players[start + r0 + lane] = (int8_t)player;
                     __syncwarp();
                 }
@@ -377,8 +388,9 @@ static int launch_movegen(const int8_t* boards, const int8_t* players, const int
 
 using namespace bg;
 
-// Workspace layout (bytes): [0] work_ctr u32, [4] overflow_ctr u32, [8] work_ctr2 u32, [64..] overflow_list int32[B]
-extern "C" size_t bg_movegen_workspace_bytes(long long B) { return 64 + sizeof(int32_t) * (size_t)(B > 0 ? B : 1); }
+// Workspace layout (bytes): [0] work_ctr0, [4] overflow_ctr A, [8] work_ctr1, [12] overflow_ctr B, [16] work_ctr2,
+// [64 ..] overflow list A int32[B], then overflow list B int32[B]
+extern "C" size_t bg_movegen_workspace_bytes(long long B) { return 64 + 2 * sizeof(int32_t) * (size_t)(B > 0 ? B : 1); }
 
 int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B, int replicate,
                     int flip_player, int mode,
@@ -396,22 +408,26 @@ int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* d
     if (ws_bytes < bg_movegen_workspace_bytes(B)) return bg_set_error_msg(BG_ERR_INVALID, "movegen: workspace too small");
     if (B > 0x7FFFFFF0LL) return bg_set_error_msg(BG_ERR_INVALID, "movegen: batch too large");
     unsigned char* ws = static_cast<unsigned char*>(workspace);
-    unsigned int* work_ctr = reinterpret_cast<unsigned int*>(ws);
-    unsigned int* overflow_ctr = reinterpret_cast<unsigned int*>(ws + 4);
-    unsigned int* work_ctr2 = reinterpret_cast<unsigned int*>(ws + 8);
-    int32_t* overflow_list = reinterpret_cast<int32_t*>(ws + 64);
+    unsigned int* ctr = reinterpret_cast<unsigned int*>(ws);
+    int32_t* list_a = reinterpret_cast<int32_t*>(ws + 64);
+    int32_t* list_b = list_a + B;
     cudaError_t e = cudaMemsetAsync(ws, 0, 64, stream);
     if (e != cudaSuccess) return bg_set_error(e, "movegen: memset");
+    // Tier 0: every position, BG_MOVEGEN_CAP_SMALL boards per level, 8 warps per CTA.
     int rc = launch_movegen<BG_MOVEGEN_CAP_SMALL, 2 * BG_MOVEGEN_CAP_SMALL, 8>(
         boards, players, dice, B, nullptr, nullptr, replicate, flip_player, mode, offsets, max_rows, after,
-        after_cap_rows, row_players,
-        counts_true, counts, starts, alloc, status, work_ctr, overflow_list, overflow_ctr, (B + 7) / 8, stream);
+        after_cap_rows, row_players, counts_true, counts, starts, alloc, status, ctr + 0, list_a, ctr + 1,
+        (B + 7) / 8, stream);
     if (rc != BG_OK) return rc;
-    // Large-scratch pass over the (rare) positions whose levels did not fit: one warp per CTA, work count read
-    // from device memory so no host synchronisation is needed.  Positions that do not fit even this scratch
-    // raise BG_STATUS_SCRATCH_OVERFLOW (never dropped silently).
+    // Tier 1: the (~1 %) positions whose levels did not fit, BG_MOVEGEN_CAP_MID boards per level, 2 warps per CTA.
+    // Work counts of tiers 1 and 2 are read from device memory, so no host synchronisation is needed.
+    rc = launch_movegen<BG_MOVEGEN_CAP_MID, 2 * BG_MOVEGEN_CAP_MID, 2>(
+        boards, players, dice, B, ctr + 1, list_a, replicate, flip_player, mode, offsets, max_rows, after,
+        after_cap_rows, row_players, counts_true, counts, starts, alloc, status, ctr + 2, list_b, ctr + 3, 0, stream);
+    if (rc != BG_OK) return rc;
+    // Tier 2: the rest (> BG_MOVEGEN_CAP_MID boards in a level), one warp per CTA.  Positions that do not fit even
+    // this scratch raise BG_STATUS_SCRATCH_OVERFLOW (never dropped silently).
     return launch_movegen<BG_MOVEGEN_CAP_BIG, BG_MOVEGEN_HASH_BIG, 1>(
-        boards, players, dice, B, overflow_ctr, overflow_list, replicate, flip_player, mode, offsets, max_rows, after,
-        after_cap_rows,
-        row_players, counts_true, counts, starts, alloc, status, work_ctr2, nullptr, nullptr, 0, stream);
+        boards, players, dice, B, ctr + 3, list_b, replicate, flip_player, mode, offsets, max_rows, after,
+        after_cap_rows, row_players, counts_true, counts, starts, alloc, status, ctr + 4, nullptr, nullptr, 0, stream);
 }
