@@ -235,6 +235,8 @@ def run_engine(args):
     e2e_s = time.perf_counter() - t0
     env.check_status()
 
+    extra = run_extras(bg_b200, env, torch, dev, args) if (world == 1 and not args.no_extras) else None
+
     tm = torch.tensor([ms, e2e_s * 1e3, k1_ms], dtype=torch.float64, device=dev)
     rw = torch.tensor([rows_per_step], dtype=torch.float64, device=dev)
     if world > 1:
@@ -282,6 +284,8 @@ def run_engine(args):
                                     "as the reference API returns them"},
         "gpu_launches": n_launch, "clocks": clocks,
     }
+    if extra is not None:
+        line["extra"] = extra
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n, el = cpu_rollout(args.cpu_seconds, threads)
@@ -291,6 +295,56 @@ def run_engine(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extras(bg_b200, env, torch, dev, args):
+    """Secondary figures of the same path (BASELINE.json: "2-ply positions evaluated/sec"; configs[2], configs[3]):
+    K4 leaf evaluator alone, 1-ply greedy self-play steps, 2-ply search.  Random-init weights of the reference
+    architecture (198-128-1 value path), positions = the de-phased random-play games of the main run."""
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps * 1e-3
+    net = bg_b200.ValueNet.random_init(dev, seed=0)
+    out = {}
+    # K4: value of every current afterstate (ragged buffer, ~1.2 M rows), fused encode + tcgen05 GEMM + value head
+    rows = env.total_rows()
+    vbuf = torch.empty(rows, dtype=torch.float32, device=dev)
+    t = timed(lambda: net.values(env.after52[:rows], env.row_players[:rows], out=vbuf), 20)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tf = rows * 53504.0 / t / 1e12
+    out["mlp_value"] = {"positions_per_s": rows / t, "rows": rows, "ms": t * 1e3, "tflops_bf16": tf,
+                        "tensor_peak_tflops": peaks.get("bf16_tflops"), "frac_of_tensor_peak": (tf / peaks["bf16_tflops"]) if peaks.get("bf16_tflops") else None,
+                        "hbm_gbs": rows * 57.0 / t / 1e9}
+    # 1-ply greedy self-play (configs[2] per GPU): K4 on the afterstates + segment argmax + K2 + K1
+    def greedy_step():
+        acts, _ = bg_b200.greedy_actions(env, net)
+        env.step_device(acts.clamp_(min=0))
+    t = timed(greedy_step, 30)
+    out["greedy_1ply"] = {"env_steps_per_s": env.num_envs / t, "ms_per_step": t * 1e3, "games": env.num_envs}
+    # 2-ply (configs[3]): roots = the first R games' positions with their actual dice
+    R = min(args.twoply_roots, env.num_envs)
+    search = bg_b200.TwoPlySearch(net, max_afterstates_per_chunk=args.twoply_chunk)
+    b, p, d = env.boards52[:R].clone(), env.players[:R].clone(), env.dice[:R].clone()
+    search.search(b[:64], p[:64], d[:64])
+    torch.cuda.synchronize()
+    search.leaves_evaluated = 0
+    t0 = time.perf_counter()
+    best, scores, offsets, A = search.search(b, p, d)
+    torch.cuda.synchronize()
+    t = time.perf_counter() - t0
+    out["twoply"] = {"roots": R, "root_afterstates": int(A.shape[0]), "leaves": int(search.leaves_evaluated), "seconds": t,
+                     "root_positions_per_s": R / t, "root_afterstates_per_s": A.shape[0] / t,
+                     "leaves_per_s": search.leaves_evaluated / t,
+                     "note": "wall clock incl. host orchestration; a 2-ply position = one root afterstate fully expanded "
+                             "(21 opponent rolls x replies, leaves MLP-evaluated)"}
+    return out
 
 
 def main():
@@ -306,6 +360,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-afterstate-features", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--twoply-roots", type=int, default=4096)
+    ap.add_argument("--twoply-chunk", type=int, default=32768)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -11,6 +11,7 @@
 // vectors so that a warp's stores cover contiguous 512 / 256 bytes.
 #include <cuda_bf16.h>
 #include "bg_device.cuh"
+#include "bg_features.cuh"
 #include "bg_internal.h"
 
 namespace bg {
@@ -18,51 +19,19 @@ namespace bg {
 constexpr int kEncRows = 128;     // boards per CTA tile
 constexpr int kEncThreads = 256;
 
-__device__ __forceinline__ uint32_t bf16_bits(float f) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f)); }
-
-// 4 bf16 units of one point with c men, packed little-endian into (x = units 0,1; y = units 2,3)
-__device__ __forceinline__ uint2 point_units_bf16(int c) {
-    uint2 r;
-    r.x = (c >= 1 ? 0x3F80u : 0u) | (c >= 2 ? 0x3F800000u : 0u);
-    r.y = (c >= 3 ? 0x3F80u : 0u) | (c >= 4 ? (bf16_bits((float)(c - 3) * 0.5f) << 16) : 0u);
-    return r;
-}
 __device__ __forceinline__ float4 point_units_f32(int c) {
     float4 r;
     r.x = c >= 1 ? 1.0f : 0.0f; r.y = c >= 2 ? 1.0f : 0.0f; r.z = c >= 3 ? 1.0f : 0.0f;
-    r.w = c >= 3 ? ((float)c - 3.0f) / 2.0f : 0.0f;                       // batching.py:117-119
+    r.w = c >= 3 ? ((float)c - 3.0f) * 0.5f : 0.0f;                       // batching.py:117-119 (/2 is exact)
     return r;
-}
-
-// 16-byte chunk k (features 8k .. 8k+7) of the bf16 row of board b (52 bytes in shared memory).
-__device__ __forceinline__ uint4 bf16_chunk(const int8_t* b, int flag, int k) {
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (k < 12) {                                    // PLAYER1 points 2k, 2k+1
-        uint2 a = point_units_bf16(b[2 * k]), c = point_units_bf16(b[2 * k + 1]);
-        o = make_uint4(a.x, a.y, c.x, c.y);
-    } else if (k == 12) {                            // bar1/2, off1/15, P2 point 0, first half of P2 point 1
-        uint2 a = point_units_bf16(b[24]), c = point_units_bf16(b[25]);
-        o.x = bf16_bits((float)b[48] / 2.0f) | (bf16_bits((float)b[50] / 15.0f) << 16);
-        o.y = a.x; o.z = a.y; o.w = c.x;
-    } else if (k < 24) {                             // second half of P2 point q, P2 point q+1, first half of q+2
-        int q = 2 * (k - 12) - 1;
-        uint2 a = point_units_bf16(b[24 + q]), c = point_units_bf16(b[24 + q + 1]), e = point_units_bf16(b[24 + q + 2]);
-        o = make_uint4(a.y, c.x, c.y, e.x);
-    } else if (k == 24) {                            // second half of P2 point 23, bar2/2, off2/15, flags, pad
-        uint2 a = point_units_bf16(b[47]);
-        o.x = a.y;
-        o.y = bf16_bits((float)b[49] / 2.0f) | (bf16_bits((float)b[51] / 15.0f) << 16);
-        o.z = flag == 0 ? 0x00003F80u : 0x3F800000u;
-    }
-    return o;
 }
 
 // float2 pair j (features 2j, 2j+1) of the f32 row
 __device__ __forceinline__ float2 f32_pair(const int8_t* b, int flag, int j) {
     if (j < 48) { float4 u = point_units_f32(b[j >> 1]); return (j & 1) ? make_float2(u.z, u.w) : make_float2(u.x, u.y); }
-    if (j == 48) return make_float2((float)b[48] / 2.0f, (float)b[50] / 15.0f);
+    if (j == 48) return make_float2((float)b[48] * 0.5f, __uint_as_float(kOff15F32[b[50] & 15]));
     if (j < 97) { int r = j - 49; float4 u = point_units_f32(b[24 + (r >> 1)]); return (r & 1) ? make_float2(u.z, u.w) : make_float2(u.x, u.y); }
-    if (j == 97) return make_float2((float)b[49] / 2.0f, (float)b[51] / 15.0f);
+    if (j == 97) return make_float2((float)b[49] * 0.5f, __uint_as_float(kOff15F32[b[51] & 15]));
     return flag == 0 ? make_float2(1.0f, 0.0f) : make_float2(0.0f, 1.0f);
 }
 
@@ -85,6 +54,8 @@ __global__ void __launch_bounds__(kEncThreads) encode_bf16_kernel(const int8_t* 
     uint32_t* tile = enc_smem;                                   // kBfRows x (cpr*4) words
     uint32_t* sm = tile + kBfRows * cpr * 4;                     // kBfRows x 13 words of boards
     int8_t* sflag = reinterpret_cast<int8_t*>(sm + kBfRows * kBoardWords);
+    __shared__ uint2 s_units[16];
+    load_units_lut(s_units);
     if (n_rows_dev) B = min(B, (long long)*n_rows_dev);
     const int wpr = cpr * 4;                                     // words per output row
     const int items = 48 + 3 + (wpr - 99);                       // points, bar/off x2, flags, zero words
@@ -100,13 +71,13 @@ __global__ void __launch_bounds__(kEncThreads) encode_bf16_kernel(const int8_t* 
             uint32_t* orow = tile + r * wpr;
             for (int j = threadIdx.x & 31; j < items; j += 32) {
                 if (j < 48) {
-                    const uint2 u = point_units_bf16(b[j]);
+                    const uint2 u = s_units[b[j] & 15];
                     const int w = 2 * j + (j >= 24 ? 1 : 0);     // word index of element 4j (+2)
                     orow[w] = u.x; orow[w + 1] = u.y;
                 } else if (j == 48) {
-                    orow[48] = bf16_bits((float)b[48] / 2.0f) | (bf16_bits((float)b[50] / 15.0f) << 16);   // elements 96,97
+                    orow[48] = bar_off_pair_bf16(b[48], b[50]);                                            // elements 96,97
                 } else if (j == 49) {
-                    orow[97] = bf16_bits((float)b[49] / 2.0f) | (bf16_bits((float)b[51] / 15.0f) << 16);   // elements 194,195
+                    orow[97] = bar_off_pair_bf16(b[49], b[51]);                                            // elements 194,195
                 } else if (j == 50) {
                     orow[98] = sflag[r] == 0 ? 0x00003F80u : 0x3F800000u;                                   // elements 196,197
                 } else {

@@ -13,40 +13,10 @@
 // are contiguous (128 B), 8-row groups advance by SBO = 128 B, 8-column chunks by LBO = 2048 B.
 #include <cuda_bf16.h>
 #include "bg_device.cuh"
+#include "bg_features.cuh"
 #include "bg_internal.h"
 
 namespace bg {
-
-// from encode.cu (same translation rules; duplicated declaration-free by including the chunk builder here)
-__device__ __forceinline__ uint32_t bf16_bits_m(float f) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f)); }
-__device__ __forceinline__ uint2 point_units_bf16_m(int c) {
-    uint2 r;
-    r.x = (c >= 1 ? 0x3F80u : 0u) | (c >= 2 ? 0x3F800000u : 0u);
-    r.y = (c >= 3 ? 0x3F80u : 0u) | (c >= 4 ? (bf16_bits_m((float)(c - 3) * 0.5f) << 16) : 0u);
-    return r;
-}
-// 16-byte chunk k (features 8k..8k+7) of the bf16 feature row (board/immutable_board.py:171-212)
-__device__ __forceinline__ uint4 feature_chunk(const int8_t* b, int flag, int k) {
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (k < 12) {
-        uint2 a = point_units_bf16_m(b[2 * k]), c = point_units_bf16_m(b[2 * k + 1]);
-        o = make_uint4(a.x, a.y, c.x, c.y);
-    } else if (k == 12) {
-        uint2 a = point_units_bf16_m(b[24]), c = point_units_bf16_m(b[25]);
-        o.x = bf16_bits_m((float)b[48] / 2.0f) | (bf16_bits_m((float)b[50] / 15.0f) << 16);
-        o.y = a.x; o.z = a.y; o.w = c.x;
-    } else if (k < 24) {
-        int q = 2 * (k - 12) - 1;
-        uint2 a = point_units_bf16_m(b[24 + q]), c = point_units_bf16_m(b[24 + q + 1]), e = point_units_bf16_m(b[24 + q + 2]);
-        o = make_uint4(a.y, c.x, c.y, e.x);
-    } else if (k == 24) {
-        uint2 a = point_units_bf16_m(b[47]);
-        o.x = a.y;
-        o.y = bf16_bits_m((float)b[49] / 2.0f) | (bf16_bits_m((float)b[51] / 15.0f) << 16);
-        o.z = flag == 0 ? 0x00003F80u : 0x3F800000u;
-    }
-    return o;
-}
 
 constexpr int kTileM = 128;            // positions per tile = UMMA M
 constexpr int kHidden = BG_HIDDEN;     // UMMA N
@@ -62,6 +32,7 @@ struct MlpSmem {
     float b1[kHidden];
     float wv[kHidden];
     int8_t flag[kTileM];
+    uint2 units[16];
     unsigned long long mbar;
     uint32_t tmem_base;
 };
@@ -127,6 +98,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
         uint4 v = *reinterpret_cast<const uint4*>(w1 + (size_t)n * kKPad + kc * 8);
         *reinterpret_cast<uint4*>(S.W + kc * 2048 + n * 16) = v;
     }
+    load_units_lut(S.units);
     S.b1[tid] = b1[tid];
     S.wv[tid] = wv[tid];
     if (tid == 0) {
@@ -161,7 +133,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
             const int fl = S.flag[tid];
 #pragma unroll 2
             for (int kc = 0; kc < kChunks; ++kc) {
-                uint4 v = tid < rows ? feature_chunk(b, fl, kc) : make_uint4(0u, 0u, 0u, 0u);
+                uint4 v = tid < rows ? feature_chunk_lut(b, fl, kc, S.units) : make_uint4(0u, 0u, 0u, 0u);
                 *reinterpret_cast<uint4*>(S.A + kc * 2048 + tid * 16) = v;
             }
         }

@@ -419,15 +419,15 @@ int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* d
         after_cap_rows, row_players, counts_true, counts, starts, alloc, status, ctr + 0, list_a, ctr + 1,
         (B + 7) / 8, stream);
     if (rc != BG_OK) return rc;
-    // Tier 1: the (~1 %) positions whose levels did not fit, BG_MOVEGEN_CAP_MID boards per level, 2 warps per CTA.
-    // Work counts of tiers 1 and 2 are read from device memory, so no host synchronisation is needed.
-    rc = launch_movegen<BG_MOVEGEN_CAP_MID, 2 * BG_MOVEGEN_CAP_MID, 2>(
-        boards, players, dice, B, ctr + 1, list_a, replicate, flip_player, mode, offsets, max_rows, after,
-        after_cap_rows, row_players, counts_true, counts, starts, alloc, status, ctr + 2, list_b, ctr + 3, 0, stream);
+    // Tier 1: the (~1 %) positions whose levels did not fit: one 4-warp CTA per position (movegen_team.cu),
+    // BG_MOVEGEN_CAP_MID boards per level.  Work counts of tiers 1 and 2 are read from device memory, so no host
+    // synchronisation is needed.
+    rc = movegen_team_mid(boards, players, dice, ctr + 1, list_a, replicate, flip_player, mode, offsets, max_rows, after,
+                          after_cap_rows, row_players, counts_true, counts, starts, alloc, status, ctr + 2, list_b,
+                          ctr + 3, stream);
     if (rc != BG_OK) return rc;
-    // Tier 2: the rest (> BG_MOVEGEN_CAP_MID boards in a level), one warp per CTA.  Positions that do not fit even
-    // this scratch raise BG_STATUS_SCRATCH_OVERFLOW (never dropped silently).
-    return launch_movegen<BG_MOVEGEN_CAP_BIG, BG_MOVEGEN_HASH_BIG, 1>(
-        boards, players, dice, B, ctr + 3, list_b, replicate, flip_player, mode, offsets, max_rows, after,
-        after_cap_rows, row_players, counts_true, counts, starts, alloc, status, ctr + 4, nullptr, nullptr, 0, stream);
+    // Tier 2: the rest (> BG_MOVEGEN_CAP_MID boards in a level): one 16-warp CTA per position, BG_MOVEGEN_CAP_BIG
+    // boards per level.  Positions that do not fit even this raise BG_STATUS_SCRATCH_OVERFLOW (never dropped silently).
+    return movegen_team_big(boards, players, dice, ctr + 3, list_b, replicate, flip_player, mode, offsets, max_rows, after,
+                            after_cap_rows, row_players, counts_true, counts, starts, alloc, status, ctr + 4, stream);
 }

@@ -1,0 +1,407 @@
+// movegen_team.cu -- K1 for the heavy tail: one CTA ("team" of T threads) per position.
+//
+// Same algorithm and same output as movegen.cu (level-by-level expansion in the reference's order, see the
+// header of that file), for the ~1 % of positions whose levels hold more than BG_MOVEGEN_CAP_SMALL boards
+// (big doubles: up to 1,654 plays in the fixtures).  A lone warp spends ~0.3 us per generated board on such a
+// position with nothing to hide its latencies behind, which made the overflow pass as long as the main pass;
+// here T candidates are built per iteration and the whole CTA shares the level lists.
+//
+// Ordered first-wins dedupe across warps (match_any only sees one warp): every candidate of a chunk publishes
+// its key, then probes the hash set; an empty slot is claimed tentatively with PEND|tid, a slot pending for an
+// EQUAL key is taken over with atomicMin (lowest candidate index wins), a committed entry with an equal key kills
+// the candidate.  After a barrier a candidate survives iff its slot still names it; survivors are compacted in
+// candidate order (ballot + per-warp counts) and commit their slots to list indices.
+#include "bg_device.cuh"
+#include "bg_internal.h"
+
+namespace bg {
+
+namespace {
+constexpr uint32_t kEmptyT = 0xFFFFFFFFu;
+constexpr uint32_t kPend = 0x80000000u;
+
+__device__ __constant__ int8_t kRoll21T[21][2] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {2, 2}, {2, 3}, {2, 4}, {2, 5}, {2, 6},
+                                                  {3, 3}, {3, 4}, {3, 5}, {3, 6}, {4, 4}, {4, 5}, {4, 6}, {5, 5}, {5, 6}, {6, 6}};
+
+template <int CAP, int HS, int T>
+struct TeamScratch {
+    uint4 key[2 * CAP + 1];
+    uint4 ckey[T];              // keys of the current chunk's candidates
+    uint32_t occ[2 * CAP + 1];
+    uint32_t pm[CAP];
+    uint32_t hash[HS];
+    uint16_t off[CAP + 2];
+    uint32_t rootw[kBoardWords];
+    int warp_cnt[T / 32];
+    Node root;
+    Root R;
+    int bcast[4];
+};
+
+template <int CAP, int HS, int T>
+struct Team {
+    static_assert(CAP * 16 >= T * kBoardWords * 4, "a region must be able to stage T output rows");
+    static constexpr int kRoot = 2 * CAP;
+    static constexpr int kWarps = T / 32;
+    TeamScratch<CAP, HS, T>& S;
+    Root R;
+    int tid, lane, warp;
+    bool overflow;
+
+    __device__ Team(TeamScratch<CAP, HS, T>& s) : S(s), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), overflow(false) {}
+
+    __device__ __forceinline__ Node load(int i) const {
+        uint4 k = S.key[i];
+        Node n;
+        n.lo = (unsigned long long)k.x | ((unsigned long long)k.y << 32);
+        n.hi = (unsigned long long)k.z | ((unsigned long long)(k.w >> 24) << 32);
+        n.hit = k.w & 0xFFFFFFu;
+        n.occ = S.occ[i];
+        return n;
+    }
+    static __device__ __forceinline__ uint4 key_of(const Node& n) {
+        return make_uint4((uint32_t)n.lo, (uint32_t)(n.lo >> 32), (uint32_t)n.hi, n.hit | ((uint32_t)(n.hi >> 32) << 24));
+    }
+    static __device__ __forceinline__ bool eq(const uint4& a, const uint4& b) { return a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w; }
+    static __device__ __forceinline__ uint32_t hash_key(const uint4& k) {
+        uint32_t h = k.x * 0x9E3779B1u ^ k.y * 0x85EBCA77u ^ k.z * 0xC2B2AE3Du ^ k.w * 0x27D4EB2Fu;
+        return h ^ (h >> 15);
+    }
+    __device__ void clear_hash() {
+        for (int i = tid; i < HS; i += T) S.hash[i] = kEmptyT;
+        __syncthreads();
+    }
+    // exclusive prefix over the team of `v` in thread order; *total = team sum.  Two barriers.
+    __device__ __forceinline__ int team_scan(int v, int* total) {
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) S.warp_cnt[warp] = inc;
+        __syncthreads();
+        int before = 0, sum = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) { int c = S.warp_cnt[w]; sum += c; if (w < warp) before += c; }
+        __syncthreads();
+        *total = sum;
+        return before + inc - v;
+    }
+
+    __device__ int count_moves(int pbase, int np, int d) {
+        int base = 0;
+        for (int i0 = 0; i0 < np; i0 += T) {
+            int i = i0 + tid;
+            int cnt = 0;
+            if (i < np) {
+                Node n = load(pbase + i);
+                uint32_t mask; int special;
+                one_die(n, R, d, mask, special);
+                cnt = __popc(mask) + (special >= 0);
+                S.pm[i] = mask | ((uint32_t)(special + 1) << 24);
+            }
+            int sum;
+            int ex = team_scan(cnt, &sum);
+            if (i < np) S.off[i] = (uint16_t)(base + ex);
+            base += sum;
+        }
+        if (tid == 0) S.off[np] = (uint16_t)base;
+        __syncthreads();
+        return base;
+    }
+
+    __device__ int expand(int pbase, int np, int d, int total, int cbase, int nc, bool use_set) {
+        for (int c0 = 0; c0 < total; c0 += T) {
+            int idx = c0 + tid;
+            bool valid = idx < total;
+            Node ch; ch.lo = 0; ch.hi = 0; ch.hit = 0; ch.occ = 0;
+            if (valid) {
+                int lo = 0, hi = np - 1;
+                while (lo < hi) {
+                    int mid = (lo + hi + 1) >> 1;
+                    if ((int)S.off[mid] <= idx) lo = mid; else hi = mid - 1;
+                }
+                int j = idx - (int)S.off[lo];
+                uint32_t pmv = S.pm[lo];
+                Node p = load(pbase + lo);
+                ch = apply_move(p, R, d, pmv & 0xFFFFFFu, (int)(pmv >> 24) - 1, j);
+            }
+            const uint4 k = key_of(ch);
+            bool keep = valid;
+            int myslot = -1;
+            if (use_set) {
+                S.ckey[tid] = k;
+                __syncthreads();
+                if (valid) {
+                    const uint32_t me = kPend | (uint32_t)tid;
+                    uint32_t s = hash_key(k) & (HS - 1);
+                    keep = false;
+                    for (;;) {
+                        uint32_t e = *reinterpret_cast<volatile uint32_t*>(&S.hash[s]);
+                        if (e == kEmptyT) {
+                            uint32_t old = atomicCAS(&S.hash[s], kEmptyT, me);
+                            if (old == kEmptyT) { myslot = (int)s; keep = true; break; }
+                            e = old;
+                        }
+                        if (e & kPend) {
+                            if (eq(S.ckey[e & ~kPend], k)) {           // same board pending: lowest candidate index wins
+                                uint32_t old = atomicMin(&S.hash[s], me);
+                                if (old > me) { myslot = (int)s; keep = true; }
+                                break;
+                            }
+                        } else if (eq(S.key[e], k)) break;             // already in the level
+                        s = (s + 1) & (HS - 1);
+                    }
+                }
+                __syncthreads();
+                if (keep) keep = S.hash[myslot] == (kPend | (uint32_t)tid);
+            }
+            unsigned surv = __ballot_sync(kFull, keep);
+            int sum;
+            int wbefore = team_scan(lane == 0 ? __popc(surv) : 0, &sum);      // lane 0 carries the warp's count
+            wbefore = __shfl_sync(kFull, wbefore, 0);
+            if (nc + sum > CAP) { overflow = true; return nc; }
+            if (keep) {
+                int pos = cbase + nc + wbefore + __popc(surv & ((1u << lane) - 1u));
+                S.key[pos] = k; S.occ[pos] = ch.occ;
+                if (use_set) S.hash[myslot] = (uint32_t)pos;                   // commit
+            }
+            nc += sum;
+            __syncthreads();
+        }
+        return nc;
+    }
+
+    // same stage loop as Warp::generate (movegen.cu); every control variable is uniform across the CTA
+    __device__ void generate(const Node& root, int d0, int d1, int& obase, int& n) {
+        obase = 0; n = 0;
+        if (tid == 0) { S.key[kRoot] = key_of(root); S.occ[kRoot] = root.occ; }
+        const bool dbl = d0 == d1;
+        const int dhi = max(d0, d1), dlo = min(d0, d1);
+        if (!dbl) clear_hash(); else __syncthreads();
+        int pbase = kRoot, np = 1;
+        int nF = 0, nA1 = 0;
+        bool lenA2 = false, lenB2 = false;
+        for (int stage = 0; stage < 4; ++stage) {
+            const int d = dbl ? d0 : ((stage == 0 || stage == 3) ? dhi : dlo);
+            const int total = count_moves(pbase, np, d);
+            const bool first = !dbl && (stage & 1) == 0;
+            int cbase = 0, nc0 = 0;
+            bool use_set = true, do_expand = true;
+            if (dbl) {
+                if (total == 0) break;
+                cbase = (stage & 1) ? CAP : 0;
+                clear_hash();
+            } else if (first) {
+                if (total == 0) { ++stage; continue; }
+                cbase = CAP; use_set = false;
+            } else if (total > 0) {
+                nc0 = nF;
+                if (stage == 1) lenA2 = true; else lenB2 = true;
+            } else {
+                do_expand = false;
+                if (stage == 1 || !lenA2) {                        // singles are the plays (np <= 16: warp 0 does it)
+                    if (warp == 0) {
+                        Node c = load(CAP + (lane < np ? lane : 0));
+                        const uint4 k = key_of(c);
+                        bool keep = lane < np;
+                        if (keep) {
+                            uint32_t s = hash_key(k) & (HS - 1);
+                            for (;;) {
+                                uint32_t e = S.hash[s];
+                                if (e == kEmptyT) break;
+                                if (eq(S.key[e], k)) { keep = false; break; }
+                                s = (s + 1) & (HS - 1);
+                            }
+                        }
+                        unsigned surv = __ballot_sync(kFull, keep);
+                        if (keep) {
+                            int pos = nF + __popc(surv & ((1u << lane) - 1u));
+                            S.key[pos] = k; S.occ[pos] = c.occ;
+                            uint32_t s = hash_key(k) & (HS - 1);
+                            while (atomicCAS(&S.hash[s], kEmptyT, (uint32_t)pos) != kEmptyT) s = (s + 1) & (HS - 1);
+                        }
+                        if (lane == 0) S.bcast[0] = nF + __popc(surv);
+                    }
+                    __syncthreads();
+                    nF = S.bcast[0];
+                    __syncthreads();
+                    if (stage == 1) {
+                        nA1 = np;
+                        if (np == 1) { n = 1; return; }            // skip-reverse shortcut, get_all_moves.py:43-45
+                    }
+                }
+            }
+            int nc = nc0;
+            if (do_expand) nc = expand(pbase, np, d, total, cbase, nc0, use_set);
+            if (overflow) return;
+            if (dbl) { pbase = cbase; np = nc; obase = cbase; n = nc; }
+            else if (first) { pbase = CAP; np = nc; }
+            else { if (do_expand) nF = nc; pbase = kRoot; np = 1; }
+        }
+        if (!dbl) {
+            if (lenB2 && !lenA2) { obase = nA1; n = nF - nA1; }
+            else { obase = 0; n = nF; }
+        }
+    }
+};
+
+template <int CAP, int HS, int T>
+__global__ void __launch_bounds__(T) movegen_team_kernel(
+    const int8_t* __restrict__ boards, const int8_t* __restrict__ players, const int8_t* __restrict__ dice,
+    const unsigned int* __restrict__ nwork_dev, const int32_t* __restrict__ worklist,
+    int replicate, int flip_player, int mode, const long long* __restrict__ offsets, int max_rows,
+    int8_t* __restrict__ after, long long after_cap_rows, int8_t* __restrict__ row_players,
+    int32_t* __restrict__ counts_true, int32_t* __restrict__ counts, long long* __restrict__ starts,
+    unsigned long long* __restrict__ alloc, int32_t* __restrict__ status,
+    unsigned int* __restrict__ work_ctr, int32_t* __restrict__ overflow_list, unsigned int* __restrict__ overflow_ctr) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TeamScratch<CAP, HS, T>& S = *reinterpret_cast<TeamScratch<CAP, HS, T>*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long nwork = (long long)*nwork_dev;
+
+    for (;;) {
+        if (tid == 0) S.bcast[1] = (int)atomicAdd(work_ctr, 1u);
+        __syncthreads();
+        const long long wi = (long long)(unsigned int)S.bcast[1];
+        if (wi >= nwork) break;
+        const long long g = (long long)worklist[wi];
+        const long long src = replicate > 1 ? g / replicate : g;
+        const int player = (players[src] ^ flip_player) & 1;
+        int d0, d1;
+        if (replicate > 1) { const int r = (int)(g - src * replicate); d0 = kRoll21T[r][0]; d1 = kRoll21T[r][1]; }
+        else { d0 = dice[2 * g]; d1 = dice[2 * g + 1]; }
+        if (warp == 0) {                                  // root load: warp-collective, as in movegen.cu
+            const uint32_t* bw = reinterpret_cast<const uint32_t*>(boards + src * kBoardBytes);
+            uint32_t w = lane < kBoardWords ? bw[lane] : 0u;
+            if (lane < kBoardWords) S.rootw[lane] = w;
+            const int p = lane < 24 ? lane : 0;
+            uint32_t ownw = __shfl_sync(kFull, w, (player ? 6 : 0) + (p >> 2));
+            uint32_t oppw = __shfl_sync(kFull, w, (player ? 0 : 6) + (p >> 2));
+            uint32_t misc = __shfl_sync(kFull, w, 12);
+            int ownc = lane < 24 ? (int)((ownw >> (8 * (p & 3))) & 0xFFu) : 0;
+            int oppc = lane < 24 ? (int)((oppw >> (8 * (p & 3))) & 0xFFu) : 0;
+            int ownbar = (int)((misc >> (player ? 8 : 0)) & 0xFFu), ownoff = (int)((misc >> (player ? 24 : 16)) & 0xFFu);
+            Root R; Node root;
+            R.player = player;
+            R.block = __ballot_sync(kFull, oppc >= 2) & 0xFFFFFFu;
+            R.blot = __ballot_sync(kFull, oppc == 1) & 0xFFFFFFu;
+            root.occ = __ballot_sync(kFull, ownc > 0) & 0xFFFFFFu;
+            root.hit = 0;
+            uint32_t nib = (uint32_t)(ownc & 15) << (4 * (p & 7));
+            uint32_t w0 = __reduce_or_sync(kFull, (lane < 8) ? nib : 0u);
+            uint32_t w1 = __reduce_or_sync(kFull, (lane >= 8 && lane < 16) ? nib : 0u);
+            uint32_t w2 = __reduce_or_sync(kFull, (lane >= 16 && lane < 24) ? nib : 0u);
+            root.lo = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
+            root.hi = (unsigned long long)w2 | ((unsigned long long)((ownbar & 15) | ((ownoff & 15) << 4)) << 32);
+            R.tot15 = (__reduce_add_sync(kFull, ownc) + ownbar + ownoff) == 15;
+            if (lane == 0) { S.root = root; S.R = R; }   // (tier 0 already rejected malformed boards)
+        }
+        __syncthreads();
+        Team<CAP, HS, T> W(S);
+        W.R = S.R;
+        const Node root = S.root;
+        int obase = 0, n = 0;
+        W.generate(root, d0, d1, obase, n);
+        if (W.overflow) {
+            if (tid == 0) {
+                if (overflow_list) { unsigned int k = atomicAdd(overflow_ctr, 1u); overflow_list[k] = (int32_t)g; }
+                else {
+                    atomicOr(status, BG_STATUS_SCRATCH_OVERFLOW);
+                    if (counts_true) counts_true[g] = -1;
+                    if (counts) counts[g] = 0;
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+        const int nw = (max_rows > 0 && n > max_rows) ? max_rows : n;
+        if (tid == 0) {
+            long long st = 0;
+            if (mode == 1) st = offsets[g];
+            else if (mode == 2) st = (long long)atomicAdd(alloc, (unsigned long long)nw);
+            S.bcast[2] = (int)(st & 0xFFFFFFFFll); S.bcast[3] = (int)(st >> 32);
+            if (counts_true) counts_true[g] = n;
+            if (counts) counts[g] = nw;
+            if (mode == 2 && starts) starts[g] = st;
+        }
+        __syncthreads();
+        const long long start = (long long)(unsigned int)S.bcast[2] | ((long long)S.bcast[3] << 32);
+        if (mode != 0 && nw > 0) {
+            if (start + nw > after_cap_rows) {
+                if (tid == 0) { atomicOr(status, BG_STATUS_OUTPUT_OVERFLOW); if (counts) counts[g] = 0; }
+            } else {
+                uint32_t* stage = reinterpret_cast<uint32_t*>(&S.key[obase < CAP ? CAP : 0]);
+                uint32_t* gout = reinterpret_cast<uint32_t*>(after) + start * kBoardWords;
+                const int own0 = player ? 6 : 0, opp0 = player ? 0 : 6;
+                const uint32_t misc0 = S.rootw[12];
+                const uint32_t opp_bar0 = (misc0 >> (player ? 0 : 8)) & 0xFFu, opp_off0 = (misc0 >> (player ? 16 : 24)) & 0xFFu;
+                for (int r0 = 0; r0 < nw; r0 += T) {
+                    int r = r0 + tid;
+                    if (r < nw) {
+                        const uint4 k = S.key[obase + r];
+                        uint32_t* row = stage + tid * kBoardWords;
+                        row[own0 + 0] = spread_nibbles(k.x);       row[own0 + 1] = spread_nibbles(k.x >> 16);
+                        row[own0 + 2] = spread_nibbles(k.y);       row[own0 + 3] = spread_nibbles(k.y >> 16);
+                        row[own0 + 4] = spread_nibbles(k.z);       row[own0 + 5] = spread_nibbles(k.z >> 16);
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) row[opp0 + q] = S.rootw[opp0 + q] - spread_bits(k.w >> (4 * q));
+                        const uint32_t ob = (k.w >> 24) & 15u, oo = k.w >> 28;
+                        const uint32_t pb = opp_bar0 + (uint32_t)__popc(k.w & 0xFFFFFFu);
+                        row[12] = player == 0 ? (ob | (pb << 8) | (oo << 16) | (opp_off0 << 24))
+                                              : (pb | (ob << 8) | (opp_off0 << 16) | (oo << 24));
+                    }
+                    __syncthreads();
+                    int rows = min(T, nw - r0);
+                    for (int k2 = tid; k2 < rows * kBoardWords; k2 += T) gout[(long long)r0 * kBoardWords + k2] = stage[k2];
+                    if (row_players && tid < rows) row_players[start + r0 + tid] = (int8_t)player;
+                    __syncthreads();
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+}  // namespace
+
+template <int CAP, int HS, int T>
+static int launch_team(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
+                       const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
+                       int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, int32_t* counts_true,
+                       int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
+                       unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr, cudaStream_t stream) {
+    size_t smem = sizeof(TeamScratch<CAP, HS, T>);
+    auto kern = movegen_team_kernel<CAP, HS, T>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return bg_set_error(e, "movegen(team): cudaFuncSetAttribute");
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem);
+    if (occ < 1) occ = 1;
+    unsigned grid = (unsigned)(bg_sm_count() * occ);
+    kern<<<grid, T, smem, stream>>>(boards, players, dice, nwork_dev, worklist, replicate, flip_player, mode, offsets,
+                                    max_rows, after, after_cap_rows, row_players, counts_true, counts, starts, alloc,
+                                    status, work_ctr, overflow_list, overflow_ctr);
+    return bg_set_error(cudaGetLastError(), "movegen(team): launch");
+}
+
+int movegen_team_mid(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
+                     const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
+                     int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, int32_t* counts_true,
+                     int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
+                     unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr, cudaStream_t stream) {
+    return launch_team<BG_MOVEGEN_CAP_MID, 2 * BG_MOVEGEN_CAP_MID, 128>(
+        boards, players, dice, nwork_dev, worklist, replicate, flip_player, mode, offsets, max_rows, after, after_cap_rows,
+        row_players, counts_true, counts, starts, alloc, status, work_ctr, overflow_list, overflow_ctr, stream);
+}
+int movegen_team_big(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
+                     const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
+                     int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, int32_t* counts_true,
+                     int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
+                     unsigned int* work_ctr, cudaStream_t stream) {
+    return launch_team<BG_MOVEGEN_CAP_BIG, BG_MOVEGEN_HASH_BIG, 512>(
+        boards, players, dice, nwork_dev, worklist, replicate, flip_player, mode, offsets, max_rows, after, after_cap_rows,
+        row_players, counts_true, counts, starts, alloc, status, work_ctr, nullptr, nullptr, stream);
+}
+
+}  // namespace bg
