@@ -40,56 +40,54 @@ __device__ __forceinline__ void stage_boards(const int8_t* __restrict__ boards, 
     for (int i = threadIdx.x; i < rows * kBoardWords; i += kEncThreads) sm[i] = __ldg(src + i);
 }
 
-// bf16 rows.  Phase 1 (uniform, no divergence on the common path): item (row, j<48) expands point j of the row
-// (j = side*24 + point = byte j of board52) into its 4 units at element 4j (+2 for PLAYER2: the bar/off pair of
-// PLAYER1 sits at 96,97), items j>=48 write the bar/off pairs, the flag pair and the zero padding.  Phase 2: the
-// finished tile (kBfRows x ld bf16, contiguous in global memory as well) is copied out with 16-byte stores.
-constexpr int kBfRows = 64;
+// bf16 rows: one thread per 16-byte output chunk (8 features), driven by a per-chunk descriptor so that every lane
+// runs the same code: byte w of kChunkDesc[k] describes word w (2 features) of chunk k: bit 7 clear -> bits 0..5 =
+// board52 byte of the point, bit 6 = which half of its 4 units; bit 7 set -> 0 zero, 1 bar1/off1, 2 bar2/off2, 3 flags.
+// A warp's 32 chunks are contiguous in global memory (rows are contiguous), so the stores are full 512-byte runs.
+__device__ __constant__ uint32_t kChunkDesc[26] = {0x41014000u, 0x43034202u, 0x45054404u, 0x47074606u, 0x49094808u, 0x4B0B4A0Au, 0x4D0D4C0Cu, 0x4F0F4E0Eu, 0x51115010u, 0x53135212u, 0x55155414u, 0x57175616u, 0x19581881u, 0x1B5A1A59u, 0x1D5C1C5Bu, 0x1F5E1E5Du, 0x2160205Fu, 0x23622261u, 0x25642463u, 0x27662665u, 0x29682867u, 0x2B6A2A69u, 0x2D6C2C6Bu, 0x2F6E2E6Du, 0x8083826Fu, 0x80808080u};
+constexpr int kBfRows = 128;
 
 __global__ void __launch_bounds__(kEncThreads) encode_bf16_kernel(const int8_t* __restrict__ boards,
                                                                   const int8_t* __restrict__ flags, int flag_all,
                                                                   long long B, const unsigned long long* __restrict__ n_rows_dev,
                                                                   uint16_t* __restrict__ out, int cpr /* ld/8 */) {
-    extern __shared__ __align__(16) uint32_t enc_smem[];
-    uint32_t* tile = enc_smem;                                   // kBfRows x (cpr*4) words
-    uint32_t* sm = tile + kBfRows * cpr * 4;                     // kBfRows x 13 words of boards
-    int8_t* sflag = reinterpret_cast<int8_t*>(sm + kBfRows * kBoardWords);
-    __shared__ uint2 s_units[16];
-    load_units_lut(s_units);
+    __shared__ __align__(16) uint32_t sm[kBfRows * kBoardWords];
+    __shared__ int8_t sflag[kBfRows];
+    __shared__ uint32_t s_lut[32];       // [(count << 1) | half] -> two packed bf16 units
+    __shared__ uint32_t s_desc[32];
+    if (threadIdx.x < 16) { uint2 u = kUnitsBf16[threadIdx.x]; s_lut[2 * threadIdx.x] = u.x; s_lut[2 * threadIdx.x + 1] = u.y; }
+    if (threadIdx.x < 32) s_desc[threadIdx.x] = threadIdx.x < 26 ? kChunkDesc[threadIdx.x] : 0x80808080u;
     if (n_rows_dev) B = min(B, (long long)*n_rows_dev);
-    const int wpr = cpr * 4;                                     // words per output row
-    const int items = 48 + 3 + (wpr - 99);                       // points, bar/off x2, flags, zero words
     for (long long row0 = (long long)blockIdx.x * kBfRows; row0 < B; row0 += (long long)gridDim.x * kBfRows) {
         const int rows = (int)min((long long)kBfRows, B - row0);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
         for (int i = threadIdx.x; i < rows * kBoardWords; i += kEncThreads) sm[i] = __ldg(src + i);
         for (int i = threadIdx.x; i < rows; i += kEncThreads) sflag[i] = flags ? (flags[row0 + i] & 1) : (int8_t)flag_all;
         __syncthreads();
-        // warp w takes rows w, w+8, ...; lanes sweep the row's items (no integer division, near-uniform control flow)
-        for (int r = threadIdx.x >> 5; r < rows; r += kEncThreads / 32) {
-            const int8_t* b = reinterpret_cast<const int8_t*>(sm) + r * kBoardBytes;
-            uint32_t* orow = tile + r * wpr;
-            for (int j = threadIdx.x & 31; j < items; j += 32) {
-                if (j < 48) {
-                    const uint2 u = s_units[b[j] & 15];
-                    const int w = 2 * j + (j >= 24 ? 1 : 0);     // word index of element 4j (+2)
-                    orow[w] = u.x; orow[w + 1] = u.y;
-                } else if (j == 48) {
-                    orow[48] = bar_off_pair_bf16(b[48], b[50]);                                            // elements 96,97
-                } else if (j == 49) {
-                    orow[97] = bar_off_pair_bf16(b[49], b[51]);                                            // elements 194,195
-                } else if (j == 50) {
-                    orow[98] = sflag[r] == 0 ? 0x00003F80u : 0x3F800000u;                                   // elements 196,197
-                } else {
-                    orow[99 + (j - 51)] = 0u;                                                               // padding
+        uint4* dst = reinterpret_cast<uint4*>(out + row0 * (long long)cpr * 8);
+        const int total = rows * cpr;
+        for (int c = threadIdx.x; c < total; c += kEncThreads) {
+            const int r = cpr == 26 ? c / 26 : c / cpr;
+            const int k = c - r * cpr;
+            const uint32_t desc = k < 26 ? s_desc[k] : 0x80808080u;
+            const uint8_t* b = reinterpret_cast<const uint8_t*>(sm) + r * kBoardBytes;
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t d = (desc >> (8 * q)) & 0xFFu;
+                w[q] = s_lut[((b[d & 63u] & 15u) << 1) | ((d >> 6) & 1u)];
+            }
+            if (desc & 0x80808080u) {                            // chunks 12, 24, 25 (and padding): bar/off, flags, zeros
+                const uint32_t sp1 = bar_off_pair_bf16(b[48], b[50]), sp2 = bar_off_pair_bf16(b[49], b[51]);
+                const uint32_t sp3 = sflag[r] == 0 ? 0x00003F80u : 0x3F800000u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t d = (desc >> (8 * q)) & 0xFFu;
+                    if (d & 0x80u) { const uint32_t code = d & 3u; w[q] = code == 1 ? sp1 : (code == 2 ? sp2 : (code == 3 ? sp3 : 0u)); }
                 }
             }
+            dst[c] = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        __syncthreads();
-        const uint4* t4 = reinterpret_cast<const uint4*>(tile);
-        uint4* dst = reinterpret_cast<uint4*>(out + row0 * (long long)cpr * 8);
-        const int nvec = rows * cpr;
-        for (int c = threadIdx.x; c < nvec; c += kEncThreads) dst[c] = t4[c];
         __syncthreads();
     }
 }
@@ -141,14 +139,9 @@ extern "C" int bg_encode_bf16(const int8_t* boards52, const int8_t* flags, int f
     if (B == 0) return BG_OK;
     if (!boards52 || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: null pointer");
     const int cpr = (int)(ld / 8);
-    const size_t smem = (size_t)kBfRows * cpr * 16 + (size_t)kBfRows * kBoardBytes + kBfRows;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(encode_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return bg_set_error(e, "bg_encode_bf16: cudaFuncSetAttribute");
-    }
     long long tiles = (B + kBfRows - 1) / kBfRows;
-    long long grid = (long long)bg_sm_count() * 7;
+    long long grid = (long long)bg_sm_count() * 8;
     if (grid > tiles) grid = tiles;
-    encode_bf16_kernel<<<(unsigned)grid, kEncThreads, smem, (cudaStream_t)stream>>>(boards52, flags, flag_all & 1, B, n_rows_dev, out, cpr);
+    encode_bf16_kernel<<<(unsigned)grid, kEncThreads, 0, (cudaStream_t)stream>>>(boards52, flags, flag_all & 1, B, n_rows_dev, out, cpr);
     return bg_set_error(cudaGetLastError(), "bg_encode_bf16: launch");
 }

@@ -1,0 +1,35 @@
+"""Per-kernel timings on one B200 (CUDA events, warm, mean of reps): K1 / K3 / K4 on de-phased random-play positions."""
+import os, sys, time, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bg_b200
+
+def timed(fn, reps=20):
+    fn(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e3   # us
+
+dev = torch.device("cuda:0")
+N = int(os.environ.get("GAMES", 65536))
+env = bg_b200.B200BackgammonVecEnv(num_envs=N, device=dev, seed=0x5EED, check_every=0)
+env.reset()
+acts = torch.empty(N, dtype=torch.int32, device=dev)
+for t in range(128):
+    env.random_actions(7, t, out=acts); env.step_device(acts)
+env.check_status()
+rows = env.total_rows()
+print(f"games {N}, afterstate rows {rows} ({rows/N:.2f}/game)")
+print(f"K1 movegen_slab (3 tiers)      : {timed(env._refresh_legal_moves):8.1f} us")
+env.encode_resident(True, True)
+from bg_b200.engine import encode
+print(f"K3 encode_bf16 {rows} rows     : {timed(lambda: env.encode_resident(False, True)):8.1f} us   -> {rows*469/ (timed(lambda: env.encode_resident(False, True))*1e-6)/1e12:.2f} TB/s")
+print(f"K3 encode_f32 obs {N} rows      : {timed(lambda: env.encode_resident(True, False)):8.1f} us")
+net = bg_b200.ValueNet.random_init(dev)
+vb = torch.empty(rows, dtype=torch.float32, device=dev)
+t = timed(lambda: net.values(env.after52[:rows], env.row_players[:rows], out=vb))
+print(f"K4 mlp_value {rows} rows        : {t:8.1f} us   -> {rows/t*1e6/1e9:.2f} G pos/s, {rows*53504/t*1e6/1e12:.0f} TFLOP/s")
+env.random_actions(7, 999, out=acts)
+print(f"K2 step                        : {timed(lambda: env._apply_actions(acts), 5):8.1f} us (mutates state)")
+env._refresh_legal_moves(); env.check_status()
