@@ -55,6 +55,8 @@ int bg_version(void);
  *
  * workspace: bg_movegen_workspace_bytes(B) bytes of device scratch (contents undefined).
  * counts_true[b] = number of legal plays (never truncated; -1 if the position was rejected).
+ * row_features_bf16 (optional): K3 fused into K1's output stage -- the 208-wide bf16 feature row of every
+ * afterstate written (turn flag = the mover, ai/batching.py:72-74), same row index as afterstates52.
  */
 size_t bg_movegen_workspace_bytes(long long B);
 
@@ -67,15 +69,15 @@ int bg_movegen_count(const int8_t* boards52, const int8_t* players, const int8_t
 int bg_movegen_write(const int8_t* boards52, const int8_t* players, const int8_t* dice, long long B,
                      const long long* offsets, int max_rows_per_board, int8_t* afterstates52,
                      long long afterstate_capacity_rows, int8_t* row_players /*nullable: mover of each row*/,
-                     int32_t* counts_true /*nullable*/, int32_t* counts /*nullable*/, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+                     uint16_t* row_features_bf16 /*nullable: fused K3, [rows][208] bf16*/, int32_t* counts_true /*nullable*/, int32_t* counts /*nullable*/, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
 /* single-pass form used by the env: every warp reserves its rows with one atomicAdd on *alloc_rows
  * (caller zeroes it); starts[b] receives the first row.  Row blocks of different positions are in
  * arbitrary order, rows inside a block are in reference order.  counts[b] = min(true, max_rows). */
 int bg_movegen_slab(const int8_t* boards52, const int8_t* players, const int8_t* dice, long long B,
                     int max_rows_per_board, int8_t* afterstates52, long long afterstate_capacity_rows,
-                    int8_t* row_players /*nullable*/, int32_t* counts_true /*nullable*/, int32_t* counts,
-                    long long* starts,
+                    int8_t* row_players /*nullable*/, uint16_t* row_features_bf16 /*nullable*/,
+                    int32_t* counts_true /*nullable*/, int32_t* counts, long long* starts,
                     unsigned long long* alloc_rows, int32_t* status, void* workspace, size_t workspace_bytes,
                     void* stream);
 
@@ -169,8 +171,8 @@ int bg_mlp_value(const int8_t* boards52, const int8_t* flags, int flag_all, int 
  * entries; workspace must hold bg_movegen_workspace_bytes(M*21). Otherwise as bg_movegen_slab. */
 int bg_movegen_replies_slab(const int8_t* positions52, const int8_t* movers, long long M,
                             int max_rows_per_board, int8_t* replies52, long long reply_capacity_rows,
-                            int8_t* row_players /*nullable*/, int32_t* counts_true /*nullable*/, int32_t* counts,
-                            long long* starts, unsigned long long* alloc_rows, int32_t* status, void* workspace,
+                            int8_t* row_players /*nullable*/, uint16_t* row_features_bf16 /*nullable*/,
+                            int32_t* counts_true /*nullable*/, int32_t* counts, long long* starts, unsigned long long* alloc_rows, int32_t* status, void* workspace,
                             size_t workspace_bytes, void* stream);
 /* scores[i] = +win reward if movers[i] has borne off 15 in after52[i], else
  * -sum_r p_r * (max over the replies of (i,r) of leaf_values, or pass_values[i] when there is no reply) */

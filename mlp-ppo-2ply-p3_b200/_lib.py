@@ -39,14 +39,14 @@ SIGNATURES = {
     "bg_version": (_I, []),
     "bg_movegen_workspace_bytes": (_SZ, [_LL]),
     "bg_movegen_count": (_I, [_V, _V, _V, _LL, _V, _V, _V, _SZ, _V]),
-    "bg_movegen_write": (_I, [_V, _V, _V, _LL, _V, _I, _V, _LL, _V, _V, _V, _V, _V, _SZ, _V]),
-    "bg_movegen_slab": (_I, [_V, _V, _V, _LL, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
+    "bg_movegen_write": (_I, [_V, _V, _V, _LL, _V, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _SZ, _V]),
+    "bg_movegen_slab": (_I, [_V, _V, _V, _LL, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     "bg_encode_f32": (_I, [_V, _V, _I, _LL, _V, _V, _LL, _V]),
     "bg_encode_bf16": (_I, [_V, _V, _I, _LL, _V, _V, _LL, _V]),
     "bg_env_reset": (_I, [C.POINTER(EnvState), _V, _V, _V]),
     "bg_env_step": (_I, [C.POINTER(EnvState), _V, C.POINTER(StepOut), _V, _V]),
     "bg_random_actions": (_I, [_V, _LL, _U64, _U64, _U32, _V, _V]),
-    "bg_movegen_replies_slab": (_I, [_V, _V, _LL, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
+    "bg_movegen_replies_slab": (_I, [_V, _V, _LL, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     "bg_twoply_scores": (_I, [_V, _V, _V, _V, _V, _V, _LL, _V, _V]),
     "bg_segment_argmax": (_I, [_V, _V, _V, _LL, _V, _V, _V]),
     "bg_pack_w1": (_I, [_V, _V, _V]),

@@ -54,4 +54,34 @@ __device__ __forceinline__ uint4 feature_chunk_lut(const int8_t* b, int flag, in
     return o;
 }
 
+
+// ---- table-driven chunk builder (uniform code for every chunk of a row) ----------------------------------
+// byte w of kChunkDesc[k] describes word w (2 features) of 16-byte chunk k: bit 7 clear -> bits 0..5 = board52 byte
+// of the point, bit 6 = which half of its 4 units; bit 7 set -> 0 zero, 1 bar1/off1, 2 bar2/off2, 3 turn flags.
+__device__ __constant__ uint32_t kChunkDesc[26] = {0x41014000u, 0x43034202u, 0x45054404u, 0x47074606u, 0x49094808u, 0x4B0B4A0Au, 0x4D0D4C0Cu, 0x4F0F4E0Eu, 0x51115010u, 0x53135212u, 0x55155414u, 0x57175616u, 0x19581881u, 0x1B5A1A59u, 0x1D5C1C5Bu, 0x1F5E1E5Du, 0x2160205Fu, 0x23622261u, 0x25642463u, 0x27662665u, 0x29682867u, 0x2B6A2A69u, 0x2D6C2C6Bu, 0x2F6E2E6Du, 0x8083826Fu, 0x80808080u};
+
+// shared-memory copies: lut[(count << 1) | half] -> two packed bf16 units; desc[k] (k >= 26: zero chunk)
+__device__ __forceinline__ void load_chunk_tables(uint32_t* s_lut, uint32_t* s_desc) {
+    if (threadIdx.x < 16) { uint2 u = kUnitsBf16[threadIdx.x]; s_lut[2 * threadIdx.x] = u.x; s_lut[2 * threadIdx.x + 1] = u.y; }
+    if (threadIdx.x < 32) s_desc[threadIdx.x] = threadIdx.x < 26 ? kChunkDesc[threadIdx.x] : 0x80808080u;
+}
+__device__ __forceinline__ uint4 chunk_from_desc(const uint8_t* b, int flag, uint32_t desc, const uint32_t* s_lut) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t d = (desc >> (8 * q)) & 0xFFu;
+        w[q] = s_lut[((b[d & 63u] & 15u) << 1) | ((d >> 6) & 1u)];
+    }
+    if (desc & 0x80808080u) {                                // chunks 12, 24, 25 (and padding): bar/off, flags, zeros
+        const uint32_t sp1 = bar_off_pair_bf16(b[48], b[50]), sp2 = bar_off_pair_bf16(b[49], b[51]);
+        const uint32_t sp3 = flag == 0 ? 0x00003F80u : 0x3F800000u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t d = (desc >> (8 * q)) & 0xFFu;
+            if (d & 0x80u) { const uint32_t code = d & 3u; w[q] = code == 1 ? sp1 : (code == 2 ? sp2 : (code == 3 ? sp3 : 0u)); }
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 }  // namespace bg

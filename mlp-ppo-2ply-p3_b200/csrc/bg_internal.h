@@ -21,17 +21,17 @@ namespace bg {
 int movegen_run(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B, int replicate,
                 int flip_player, int mode,
                 const long long* offsets, int max_rows, int8_t* after, long long after_cap_rows,
-                int8_t* row_players, int32_t* counts_true, int32_t* counts, long long* starts, unsigned long long* alloc,
+                int8_t* row_players, uint16_t* row_feats, int32_t* counts_true, int32_t* counts, long long* starts, unsigned long long* alloc,
                 int32_t* status, void* workspace, size_t ws_bytes, cudaStream_t stream);
 // overflow tiers (movegen_team.cu): one CTA per position of worklist[0 .. *nwork_dev)
 int movegen_team_mid(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
                      const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
-                     int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, int32_t* counts_true,
+                     int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, uint16_t* row_feats, int32_t* counts_true,
                      int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
                      unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr, cudaStream_t stream);
 int movegen_team_big(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
                      const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
-                     int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, int32_t* counts_true,
+                     int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, uint16_t* row_feats, int32_t* counts_true,
                      int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
                      unsigned int* work_ctr, cudaStream_t stream);
 }

@@ -31,35 +31,38 @@ extern "C" int bg_movegen_count(const int8_t* boards52, const int8_t* players, c
                                 int32_t* counts_true, int32_t* status, void* workspace, size_t workspace_bytes,
                                 void* stream) {
     if (B > 0 && !counts_true) return bg_set_error_msg(BG_ERR_INVALID, "bg_movegen_count: null counts");
-    return bg::movegen_run(boards52, players, dice, B, 1, 0, 0, nullptr, 0, nullptr, 0, nullptr, counts_true, nullptr, nullptr,
+    return bg::movegen_run(boards52, players, dice, B, 1, 0, 0, nullptr, 0, nullptr, 0, nullptr, nullptr, counts_true, nullptr, nullptr,
                            nullptr, status, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 extern "C" int bg_movegen_write(const int8_t* boards52, const int8_t* players, const int8_t* dice, long long B,
                                 const long long* offsets, int max_rows_per_board, int8_t* afterstates52,
-                                long long afterstate_capacity_rows, int8_t* row_players, int32_t* counts_true,
-                                int32_t* counts, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+                                long long afterstate_capacity_rows, int8_t* row_players, uint16_t* row_features_bf16,
+                                int32_t* counts_true, int32_t* counts, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
     return bg::movegen_run(boards52, players, dice, B, 1, 0, 1, offsets, max_rows_per_board, afterstates52,
-                           afterstate_capacity_rows, row_players, counts_true, counts, nullptr, nullptr, status, workspace,
+                           afterstate_capacity_rows, row_players, row_features_bf16, counts_true, counts, nullptr, nullptr, status,
+                           workspace,
                            workspace_bytes, (cudaStream_t)stream);
 }
 extern "C" int bg_movegen_slab(const int8_t* boards52, const int8_t* players, const int8_t* dice, long long B,
                                int max_rows_per_board, int8_t* afterstates52, long long afterstate_capacity_rows,
-                               int8_t* row_players, int32_t* counts_true, int32_t* counts, long long* starts,
-                               unsigned long long* alloc_rows, int32_t* status, void* workspace,
+                               int8_t* row_players, uint16_t* row_features_bf16, int32_t* counts_true, int32_t* counts,
+                               long long* starts, unsigned long long* alloc_rows, int32_t* status, void* workspace,
                                size_t workspace_bytes, void* stream) {
     if (B > 0 && !counts) return bg_set_error_msg(BG_ERR_INVALID, "bg_movegen_slab: null counts");
     return bg::movegen_run(boards52, players, dice, B, 1, 0, 2, nullptr, max_rows_per_board, afterstates52,
-                           afterstate_capacity_rows, row_players, counts_true, counts, starts, alloc_rows, status, workspace,
+                           afterstate_capacity_rows, row_players, row_features_bf16, counts_true, counts, starts, alloc_rows, status,
+                           workspace,
                            workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int bg_movegen_replies_slab(const int8_t* positions52, const int8_t* movers, long long M,
                                        int max_rows_per_board, int8_t* replies52, long long reply_capacity_rows,
-                                       int8_t* row_players, int32_t* counts_true, int32_t* counts, long long* starts,
+                                       int8_t* row_players, uint16_t* row_features_bf16, int32_t* counts_true,
+                                       int32_t* counts, long long* starts,
                                        unsigned long long* alloc_rows, int32_t* status, void* workspace,
                                        size_t workspace_bytes, void* stream) {
     if (M > 0 && !counts) return bg_set_error_msg(BG_ERR_INVALID, "bg_movegen_replies_slab: null counts");
     return bg::movegen_run(positions52, movers, nullptr, M * 21, 21, 1, 2, nullptr, max_rows_per_board, replies52,
-                           reply_capacity_rows, row_players, counts_true, counts, starts, alloc_rows, status,
+                           reply_capacity_rows, row_players, row_features_bf16, counts_true, counts, starts, alloc_rows, status,
                            workspace, workspace_bytes, (cudaStream_t)stream);
 }

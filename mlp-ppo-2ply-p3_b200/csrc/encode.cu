@@ -44,7 +44,6 @@ __device__ __forceinline__ void stage_boards(const int8_t* __restrict__ boards, 
 // runs the same code: byte w of kChunkDesc[k] describes word w (2 features) of chunk k: bit 7 clear -> bits 0..5 =
 // board52 byte of the point, bit 6 = which half of its 4 units; bit 7 set -> 0 zero, 1 bar1/off1, 2 bar2/off2, 3 flags.
 // A warp's 32 chunks are contiguous in global memory (rows are contiguous), so the stores are full 512-byte runs.
-__device__ __constant__ uint32_t kChunkDesc[26] = {0x41014000u, 0x43034202u, 0x45054404u, 0x47074606u, 0x49094808u, 0x4B0B4A0Au, 0x4D0D4C0Cu, 0x4F0F4E0Eu, 0x51115010u, 0x53135212u, 0x55155414u, 0x57175616u, 0x19581881u, 0x1B5A1A59u, 0x1D5C1C5Bu, 0x1F5E1E5Du, 0x2160205Fu, 0x23622261u, 0x25642463u, 0x27662665u, 0x29682867u, 0x2B6A2A69u, 0x2D6C2C6Bu, 0x2F6E2E6Du, 0x8083826Fu, 0x80808080u};
 constexpr int kBfRows = 128;
 
 __global__ void __launch_bounds__(kEncThreads) encode_bf16_kernel(const int8_t* __restrict__ boards,
@@ -53,10 +52,8 @@ __global__ void __launch_bounds__(kEncThreads) encode_bf16_kernel(const int8_t* 
                                                                   uint16_t* __restrict__ out, int cpr /* ld/8 */) {
     __shared__ __align__(16) uint32_t sm[kBfRows * kBoardWords];
     __shared__ int8_t sflag[kBfRows];
-    __shared__ uint32_t s_lut[32];       // [(count << 1) | half] -> two packed bf16 units
-    __shared__ uint32_t s_desc[32];
-    if (threadIdx.x < 16) { uint2 u = kUnitsBf16[threadIdx.x]; s_lut[2 * threadIdx.x] = u.x; s_lut[2 * threadIdx.x + 1] = u.y; }
-    if (threadIdx.x < 32) s_desc[threadIdx.x] = threadIdx.x < 26 ? kChunkDesc[threadIdx.x] : 0x80808080u;
+    __shared__ uint32_t s_lut[32], s_desc[32];
+    load_chunk_tables(s_lut, s_desc);
     if (n_rows_dev) B = min(B, (long long)*n_rows_dev);
     for (long long row0 = (long long)blockIdx.x * kBfRows; row0 < B; row0 += (long long)gridDim.x * kBfRows) {
         const int rows = (int)min((long long)kBfRows, B - row0);
@@ -71,22 +68,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_bf16_kernel(const int8_t* 
             const int k = c - r * cpr;
             const uint32_t desc = k < 26 ? s_desc[k] : 0x80808080u;
             const uint8_t* b = reinterpret_cast<const uint8_t*>(sm) + r * kBoardBytes;
-            uint32_t w[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t d = (desc >> (8 * q)) & 0xFFu;
-                w[q] = s_lut[((b[d & 63u] & 15u) << 1) | ((d >> 6) & 1u)];
-            }
-            if (desc & 0x80808080u) {                            // chunks 12, 24, 25 (and padding): bar/off, flags, zeros
-                const uint32_t sp1 = bar_off_pair_bf16(b[48], b[50]), sp2 = bar_off_pair_bf16(b[49], b[51]);
-                const uint32_t sp3 = sflag[r] == 0 ? 0x00003F80u : 0x3F800000u;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t d = (desc >> (8 * q)) & 0xFFu;
-                    if (d & 0x80u) { const uint32_t code = d & 3u; w[q] = code == 1 ? sp1 : (code == 2 ? sp2 : (code == 3 ? sp3 : 0u)); }
-                }
-            }
-            dst[c] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[c] = chunk_from_desc(b, sflag[r], desc, s_lut);
         }
         __syncthreads();
     }

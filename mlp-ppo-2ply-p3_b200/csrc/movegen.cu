@@ -22,6 +22,7 @@
 // indices coincide, and the env's "first max_legal_moves" truncation
 // (src/environment/backgammon_env.py:218-223) is a plain prefix.
 #include "bg_device.cuh"
+#include "bg_features.cuh"
 #include "bg_internal.h"
 
 namespace bg {
@@ -234,12 +235,15 @@ __global__ void __launch_bounds__(256) movegen_kernel(
     long long B, const unsigned int* __restrict__ nwork_dev, const int32_t* __restrict__ worklist,
     int replicate, int flip_player, int mode, const long long* __restrict__ offsets, int max_rows,
     int8_t* __restrict__ after, long long after_cap_rows, int8_t* __restrict__ row_players,
-    int32_t* __restrict__ counts_true, int32_t* __restrict__ counts, long long* __restrict__ starts,
+    uint16_t* __restrict__ row_feats, int32_t* __restrict__ counts_true, int32_t* __restrict__ counts, long long* __restrict__ starts,
     unsigned long long* __restrict__ alloc, int32_t* __restrict__ status,
     unsigned int* __restrict__ work_ctr, int32_t* __restrict__ overflow_list, unsigned int* __restrict__ overflow_ctr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpScratch<CAP, HS>& S = reinterpret_cast<WarpScratch<CAP, HS>*>(smem_raw)[warp];
+    __shared__ uint32_t s_lut[32], s_desc[32];          // K3's chunk tables, for the fused feature output
+    load_chunk_tables(s_lut, s_desc);
+    __syncthreads();
     const long long nwork = nwork_dev ? (long long)*nwork_dev : B;
 
     for (;;) {
@@ -353,6 +357,16 @@ __global__ void __launch_bounds__(256) movegen_kernel(
                     int rows = min(32, nw - r0);
                     for (int k2 = lane; k2 < rows * kBoardWords; k2 += 32) gout[(long long)r0 * kBoardWords + k2] = stage[k2];
                     if (row_players && lane < rows) row_players[start + r0 + lane] = (int8_t)player;
+                    if (row_feats) {
+                        // fused K3: the 208-wide bf16 feature rows of these afterstates (mover's turn flag,
+                        // ai/batching.py:72-74), 16 bytes per lane, contiguous in global memory
+                        uint4* fdst = reinterpret_cast<uint4*>(row_feats + (start + r0) * (long long)BG_FEAT_LD_BF16);
+                        const uint8_t* sb = reinterpret_cast<const uint8_t*>(stage);
+                        for (int c = lane; c < rows * 26; c += 32) {
+                            const int r = c / 26, k = c - r * 26;
+                            fdst[c] = chunk_from_desc(sb + r * kBoardBytes, player, s_desc[k], s_lut);
+                        }
+                    }
                     __syncwarp();
                 }
             }
@@ -365,7 +379,7 @@ template <int CAP, int HS, int WARPS>
 static int launch_movegen(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B,
                           const unsigned int* nwork_dev, const int32_t* worklist, int replicate, int flip_player, int mode,
                           const long long* offsets, int max_rows, int8_t* after, long long after_cap_rows,
-                          int8_t* row_players, int32_t* counts_true, int32_t* counts, long long* starts, unsigned long long* alloc,
+                          int8_t* row_players, uint16_t* row_feats, int32_t* counts_true, int32_t* counts, long long* starts, unsigned long long* alloc,
                           int32_t* status, unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr,
                           long long grid_hint, cudaStream_t stream) {
     size_t smem = sizeof(WarpScratch<CAP, HS>) * WARPS;
@@ -379,8 +393,8 @@ static int launch_movegen(const int8_t* boards, const int8_t* players, const int
     if (grid_hint > 0 && grid > grid_hint) grid = grid_hint;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(boards, players, dice, B, nwork_dev, worklist, replicate, flip_player, mode, offsets,
-                                                       max_rows, after, after_cap_rows, row_players, counts_true, counts,
-                                                       starts, alloc, status, work_ctr, overflow_list, overflow_ctr);
+                                                       max_rows, after, after_cap_rows, row_players, row_feats,
+                                                       counts_true, counts, starts, alloc, status, work_ctr, overflow_list, overflow_ctr);
     return bg_set_error(cudaGetLastError(), "movegen: launch");
 }
 
@@ -395,7 +409,7 @@ extern "C" size_t bg_movegen_workspace_bytes(long long B) { return 64 + 2 * size
 int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B, int replicate,
                     int flip_player, int mode,
                     const long long* offsets, int max_rows, int8_t* after, long long after_cap_rows,
-                    int8_t* row_players, int32_t* counts_true, int32_t* counts, long long* starts,
+                    int8_t* row_players, uint16_t* row_feats, int32_t* counts_true, int32_t* counts, long long* starts,
                     unsigned long long* alloc, int32_t* status, void* workspace, size_t ws_bytes, cudaStream_t stream) {
     if (B < 0) return bg_set_error_msg(BG_ERR_INVALID, "movegen: negative batch");
     if (B == 0) return BG_OK;
@@ -416,18 +430,18 @@ int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* d
     // Tier 0: every position, BG_MOVEGEN_CAP_SMALL boards per level, 8 warps per CTA.
     int rc = launch_movegen<BG_MOVEGEN_CAP_SMALL, 2 * BG_MOVEGEN_CAP_SMALL, 8>(
         boards, players, dice, B, nullptr, nullptr, replicate, flip_player, mode, offsets, max_rows, after,
-        after_cap_rows, row_players, counts_true, counts, starts, alloc, status, ctr + 0, list_a, ctr + 1,
+        after_cap_rows, row_players, row_feats, counts_true, counts, starts, alloc, status, ctr + 0, list_a, ctr + 1,
         (B + 7) / 8, stream);
     if (rc != BG_OK) return rc;
     // Tier 1: the (~1 %) positions whose levels did not fit: one 4-warp CTA per position (movegen_team.cu),
     // BG_MOVEGEN_CAP_MID boards per level.  Work counts of tiers 1 and 2 are read from device memory, so no host
     // synchronisation is needed.
     rc = movegen_team_mid(boards, players, dice, ctr + 1, list_a, replicate, flip_player, mode, offsets, max_rows, after,
-                          after_cap_rows, row_players, counts_true, counts, starts, alloc, status, ctr + 2, list_b,
+                          after_cap_rows, row_players, row_feats, counts_true, counts, starts, alloc, status, ctr + 2, list_b,
                           ctr + 3, stream);
     if (rc != BG_OK) return rc;
     // Tier 2: the rest (> BG_MOVEGEN_CAP_MID boards in a level): one 16-warp CTA per position, BG_MOVEGEN_CAP_BIG
     // boards per level.  Positions that do not fit even this raise BG_STATUS_SCRATCH_OVERFLOW (never dropped silently).
     return movegen_team_big(boards, players, dice, ctr + 3, list_b, replicate, flip_player, mode, offsets, max_rows, after,
-                            after_cap_rows, row_players, counts_true, counts, starts, alloc, status, ctr + 4, stream);
+                            after_cap_rows, row_players, row_feats, counts_true, counts, starts, alloc, status, ctr + 4, stream);
 }

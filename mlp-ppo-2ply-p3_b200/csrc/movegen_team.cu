@@ -12,6 +12,7 @@
 // the candidate.  After a barrier a candidate survives iff its slot still names it; survivors are compacted in
 // candidate order (ballot + per-warp counts) and commit their slots to list indices.
 #include "bg_device.cuh"
+#include "bg_features.cuh"
 #include "bg_internal.h"
 
 namespace bg {
@@ -253,13 +254,16 @@ __global__ void __launch_bounds__(T) movegen_team_kernel(
     const unsigned int* __restrict__ nwork_dev, const int32_t* __restrict__ worklist,
     int replicate, int flip_player, int mode, const long long* __restrict__ offsets, int max_rows,
     int8_t* __restrict__ after, long long after_cap_rows, int8_t* __restrict__ row_players,
-    int32_t* __restrict__ counts_true, int32_t* __restrict__ counts, long long* __restrict__ starts,
+    uint16_t* __restrict__ row_feats, int32_t* __restrict__ counts_true, int32_t* __restrict__ counts, long long* __restrict__ starts,
     unsigned long long* __restrict__ alloc, int32_t* __restrict__ status,
     unsigned int* __restrict__ work_ctr, int32_t* __restrict__ overflow_list, unsigned int* __restrict__ overflow_ctr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TeamScratch<CAP, HS, T>& S = *reinterpret_cast<TeamScratch<CAP, HS, T>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long nwork = (long long)*nwork_dev;
+    __shared__ uint32_t s_lut[32], s_desc[32];
+    load_chunk_tables(s_lut, s_desc);
+    __syncthreads();
 
     for (;;) {
         if (tid == 0) S.bcast[1] = (int)atomicAdd(work_ctr, 1u);
@@ -356,6 +360,14 @@ __global__ void __launch_bounds__(T) movegen_team_kernel(
                     int rows = min(T, nw - r0);
                     for (int k2 = tid; k2 < rows * kBoardWords; k2 += T) gout[(long long)r0 * kBoardWords + k2] = stage[k2];
                     if (row_players && tid < rows) row_players[start + r0 + tid] = (int8_t)player;
+                    if (row_feats) {                          // fused K3 (see movegen.cu)
+                        uint4* fdst = reinterpret_cast<uint4*>(row_feats + (start + r0) * (long long)BG_FEAT_LD_BF16);
+                        const uint8_t* sb = reinterpret_cast<const uint8_t*>(stage);
+                        for (int c = tid; c < rows * 26; c += T) {
+                            const int r = c / 26, k = c - r * 26;
+                            fdst[c] = chunk_from_desc(sb + r * kBoardBytes, player, s_desc[k], s_lut);
+                        }
+                    }
                     __syncthreads();
                 }
             }
@@ -368,7 +380,8 @@ __global__ void __launch_bounds__(T) movegen_team_kernel(
 template <int CAP, int HS, int T>
 static int launch_team(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
                        const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
-                       int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, int32_t* counts_true,
+                       int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, uint16_t* row_feats,
+                       int32_t* counts_true,
                        int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
                        unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr, cudaStream_t stream) {
     size_t smem = sizeof(TeamScratch<CAP, HS, T>);
@@ -380,28 +393,30 @@ static int launch_team(const int8_t* boards, const int8_t* players, const int8_t
     if (occ < 1) occ = 1;
     unsigned grid = (unsigned)(bg_sm_count() * occ);
     kern<<<grid, T, smem, stream>>>(boards, players, dice, nwork_dev, worklist, replicate, flip_player, mode, offsets,
-                                    max_rows, after, after_cap_rows, row_players, counts_true, counts, starts, alloc,
-                                    status, work_ctr, overflow_list, overflow_ctr);
+                                    max_rows, after, after_cap_rows, row_players, row_feats, counts_true, counts, starts,
+                                    alloc, status, work_ctr, overflow_list, overflow_ctr);
     return bg_set_error(cudaGetLastError(), "movegen(team): launch");
 }
 
 int movegen_team_mid(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
                      const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
-                     int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, int32_t* counts_true,
+                     int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, uint16_t* row_feats,
+                       int32_t* counts_true,
                      int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
                      unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr, cudaStream_t stream) {
     return launch_team<BG_MOVEGEN_CAP_MID, 2 * BG_MOVEGEN_CAP_MID, 128>(
         boards, players, dice, nwork_dev, worklist, replicate, flip_player, mode, offsets, max_rows, after, after_cap_rows,
-        row_players, counts_true, counts, starts, alloc, status, work_ctr, overflow_list, overflow_ctr, stream);
+        row_players, row_feats, counts_true, counts, starts, alloc, status, work_ctr, overflow_list, overflow_ctr, stream);
 }
 int movegen_team_big(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
                      const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
-                     int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, int32_t* counts_true,
+                     int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, uint16_t* row_feats,
+                       int32_t* counts_true,
                      int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
                      unsigned int* work_ctr, cudaStream_t stream) {
     return launch_team<BG_MOVEGEN_CAP_BIG, BG_MOVEGEN_HASH_BIG, 512>(
         boards, players, dice, nwork_dev, worklist, replicate, flip_player, mode, offsets, max_rows, after, after_cap_rows,
-        row_players, counts_true, counts, starts, alloc, status, work_ctr, nullptr, nullptr, stream);
+        row_players, row_feats, counts_true, counts, starts, alloc, status, work_ctr, nullptr, nullptr, stream);
 }
 
 }  // namespace bg

@@ -100,7 +100,7 @@ def legal_moves(boards52: torch.Tensor, players: torch.Tensor, dice: torch.Tenso
         rowp = torch.empty(max(total, 1), dtype=torch.int8, device=dev) if with_row_players else None
         check(L.bg_movegen_write(boards52.data_ptr(), players.data_ptr(), dice.data_ptr(), B, offsets.data_ptr(),
                                  int(max_rows_per_board), after.data_ptr(), total,
-                                 rowp.data_ptr() if rowp is not None else None, None, None,
+                                 rowp.data_ptr() if rowp is not None else None, None, None, None,
                                  ws.status.data_ptr(), ws.buf.data_ptr(), ws.nbytes, _stream()), "bg_movegen_write")
     if check_status:
         read_status(ws.status, "legal_moves")

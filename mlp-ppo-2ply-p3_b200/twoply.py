@@ -62,7 +62,7 @@ class TwoPlySearch:
             ws.status.zero_()
             with torch.cuda.device(dev):
                 check(L.bg_movegen_replies_slab(A.data_ptr(), movers.data_ptr(), M, 0, replies.data_ptr(), cap,
-                                                rowp.data_ptr(), None, counts.data_ptr(), starts.data_ptr(),
+                                                rowp.data_ptr(), None, None, counts.data_ptr(), starts.data_ptr(),
                                                 alloc.data_ptr(), ws.status.data_ptr(), ws.buf.data_ptr(), ws.nbytes,
                                                 _stream()), "bg_movegen_replies_slab")
             st = int(ws.status.item())

@@ -100,12 +100,19 @@ class B200BackgammonVecEnv:
                         self.seed, self.stream_base, e.data_ptr() if e is not None else None,
                         e.shape[1] if e is not None else 0, self.match_length)
 
-    def _refresh_legal_moves(self):
-        """update_legal_moves (backgammon_env.py:198-243) for every game: K1 in slab mode."""
+    def _refresh_legal_moves(self, with_features: bool = False):
+        """update_legal_moves (backgammon_env.py:198-243) for every game: K1 in slab mode.  with_features also
+        writes generate_all_board_features (ai/batching.py:10-75) of every legal play as bf16 rows into
+        self.after_feats, fused into K1's output stage (no separate encoder launch)."""
         self.alloc_rows.zero_()
+        fptr = None
+        if with_features:
+            if not hasattr(self, "after_feats"):
+                self.after_feats = torch.empty((self.cap_rows, LD_BF16), dtype=torch.bfloat16, device=self.device)
+            fptr = self.after_feats.data_ptr()
         check(lib().bg_movegen_slab(self.boards52.data_ptr(), self.players.data_ptr(), self.dice.data_ptr(),
                                     self.num_envs, self.max_legal_moves, self.after52.data_ptr(), self.cap_rows,
-                                    self.row_players.data_ptr(), self.legal_counts_true.data_ptr(),
+                                    self.row_players.data_ptr(), fptr, self.legal_counts_true.data_ptr(),
                                     self.legal_counts.data_ptr(), self.legal_starts.data_ptr(),
                                     self.alloc_rows.data_ptr(), self.status.data_ptr(), self._ws.data_ptr(),
                                     self._ws_bytes, _stream()), "bg_movegen_slab")
@@ -132,7 +139,7 @@ class B200BackgammonVecEnv:
         self.check_status()
         return obs
 
-    def step(self, actions, return_obs=True):
+    def step(self, actions, return_obs=True, with_features=False):
         """vec_bg_env.py:28-49 -> (obs (N,198) f32, rewards (N,) f32, dones (N,) bool, infos)"""
         if not isinstance(actions, torch.Tensor):
             import numpy as np
@@ -142,7 +149,7 @@ class B200BackgammonVecEnv:
         if actions.shape[0] != self.num_envs:
             raise BgError("step: need one action per env")
         with torch.cuda.device(self.device):
-            self.step_device(actions)
+            self.step_device(actions, with_features)
             obs = self.observations() if return_obs else None
         self._steps += 1
         if self.check_every and self._steps % self.check_every == 0:
@@ -158,11 +165,12 @@ class B200BackgammonVecEnv:
         check(lib().bg_env_step(C.byref(st), actions_i32.data_ptr(), C.byref(out), self.status.data_ptr(), _stream()),
               "bg_env_step")
 
-    def step_device(self, actions_i32: torch.Tensor):
-        """The hot path only: K2 (step/reward/terminal/reset/dice) + K1 (legal plays of the new positions).
-        Results land in self.rewards / dones_u8 / info_* / legal_* without any host synchronisation."""
+    def step_device(self, actions_i32: torch.Tensor, with_features: bool = False):
+        """The hot path only: K2 (step/reward/terminal/reset/dice) + K1 (legal plays of the new positions,
+        optionally with their bf16 features).  Results land in self.rewards / dones_u8 / info_* / legal_* /
+        after_feats without any host synchronisation."""
         self._apply_actions(actions_i32)
-        self._refresh_legal_moves()
+        self._refresh_legal_moves(with_features)
 
     def encode_resident(self, obs=True, afterstates=True):
         """K3 into persistent buffers, no host sync: self.obs_f32 (N,198) f32 = get_observation of every game,

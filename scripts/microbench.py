@@ -33,3 +33,13 @@ print(f"K4 mlp_value {rows} rows        : {t:8.1f} us   -> {rows/t*1e6/1e9:.2f} 
 env.random_actions(7, 999, out=acts)
 print(f"K2 step                        : {timed(lambda: env._apply_actions(acts), 5):8.1f} us (mutates state)")
 env._refresh_legal_moves(); env.check_status()
+# calibration: write-only and copy bandwidth of torch on the same buffers
+f = env.after_feats[:rows]
+t = timed(lambda: f.zero_())
+print(f"torch zero_ {f.numel()*2/1e6:.0f} MB           : {t:8.1f} us   -> {f.numel()*2/t*1e6/1e12:.2f} TB/s (write only)")
+g = torch.empty_like(f)
+t = timed(lambda: g.copy_(f))
+print(f"torch copy_ {f.numel()*2/1e6:.0f} MB           : {t:8.1f} us   -> {2*f.numel()*2/t*1e6/1e12:.2f} TB/s (read+write)")
+big = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
+t = timed(lambda: big.zero_(), 5)
+print(f"torch zero_ 2 GiB              : {t:8.1f} us   -> {big.numel()*2/t*1e6/1e12:.2f} TB/s (write only)")

@@ -270,3 +270,20 @@ def test_output_overflow_is_flagged(bg):
     env = bg.B200BackgammonVecEnv(num_envs=4096, device=dev(), rows_per_game=1, check_every=0)
     with pytest.raises(bg.BgError, match="OUTPUT_OVERFLOW"):
         env.reset()
+
+
+def test_fused_afterstate_features_match_encoder(bg):
+    """K1's fused feature output (all three tiers) == K3 on the same rows."""
+    d = np.load(os.path.join(G, "adversarial.npz"))
+    sel = np.argsort(-d["counts"])[:200]                       # the heaviest positions: tiers 1 and 2 included
+    sel = np.concatenate([sel, np.arange(0, len(d["counts"]), 5)])
+    env = bg.B200BackgammonVecEnv(num_envs=len(sel), device=dev(), rows_per_game=128, max_legal_moves=5000, check_every=0)
+    env.boards52.copy_(torch.as_tensor(d["boards"][sel]).to(dev()))
+    env.players.copy_(torch.as_tensor(d["players"][sel]).to(dev()))
+    env.dice.copy_(torch.as_tensor(d["dice"][sel]).to(dev()))
+    env._refresh_legal_moves(with_features=True)
+    env.check_status()
+    assert env.legal_counts_true.cpu().tolist() == d["counts"][sel].tolist()
+    n = env.total_rows()
+    want = bg.encode(env.after52[:n], env.row_players[:n], dtype=torch.bfloat16)
+    assert torch.equal(env.after_feats[:n].view(torch.int16), want.view(torch.int16))
