@@ -8,9 +8,8 @@ Workload (BASELINE.json configs[1]): batched legal-move generation + step on 65,
 uniform-random policy, positions from the engine's own random self-play (Philox seed 0x5EED, 128 untimed
 de-phasing turns).  One "step" = one turn of every game:
     bg_random_actions -> K2 bg_env_step (apply play, reward/terminal, auto-reset, Philox dice)
-    -> K1 bg_movegen_slab (all legal afterstates of the new positions, reference order, with their bf16
-       feature rows written by the same kernel: K3 fused into K1's output stage)
-    -> K3 bg_encode_f32 (observations)
+    -> K1 bg_movegen_slab (all legal afterstates of the new positions, reference order)
+    -> K3 bg_encode_f32 (observations) + bg_encode_bf16 (ragged afterstate features)
 i.e. everything BackgammonEnv.step + update_legal_moves + get_observation do, minus the dense
 (500,198) zero padding.  Games shard across GPUs by game id with no collective ("scaling": "weak").
 
@@ -174,10 +173,10 @@ def run_engine(args):
         env._apply_actions(acts); launches[0] += 1
         if ev is not None:
             ev[0].record()
-        env._refresh_legal_moves(with_features=feats); launches[0] += 3     # K1 tiers 0/1/2 (bf16 afterstate features fused in)
+        env._refresh_legal_moves(); launches[0] += 3          # K1 tiers 0/1/2
         if ev is not None:
             ev[1].record()
-        env.encode_resident(obs=True, afterstates=False); launches[0] += 1
+        env.encode_resident(obs=True, afterstates=feats); launches[0] += 1 + int(feats)
         rows_acc.add_(env.alloc_rows)
 
     t = 0
@@ -228,7 +227,9 @@ def run_engine(args):
         h_counts.copy_(env.legal_counts)                                        # D2H (synchronous: pinned target)
         np.multiply(u[k], h_counts.numpy(), out=u[k])
         h_acts.numpy()[:] = u[k].astype(np.int32)
-        obs, rew, done, infos = env.step(h_acts, with_features=feats)           # H2D inside; obs stays on the device
+        obs, rew, done, infos = env.step(h_acts)                                # H2D inside; obs stays on the device
+        if feats:
+            env.encode_resident(obs=False, afterstates=True)
         h_rew.copy_(rew); h_done.copy_(done)                                    # D2H
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -253,8 +254,8 @@ def run_engine(args):
     e2e_value = world * N * E / (e2e_ms * 1e-3)
     peak, peak_src = load_peaks()
     # K1 algorithmic bytes per launch (DESIGN.md "K1"): per game 52 board + 1 player + 2 dice read; 4 count +
-    # 4 true count + 8 start written; per legal play 52 afterstate + 1 mover flag (+ 416 bf16 feature row) written.
-    k1_bytes = N * 71.0 + rows_per_step * (53.0 + (416.0 if feats else 0.0))
+    # 4 true count + 8 start written; per legal play 52 afterstate + 1 mover flag written.
+    k1_bytes = N * 71.0 + rows_per_step * 53.0
     achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
@@ -269,10 +270,10 @@ def run_engine(args):
         "dtype": "int8", "data": "synthetic",
         "config": {"workload": "configs[1]: batched legal-move generation + step, uniform-random policy",
                    "games_per_gpu": N, "max_legal_moves": 500, "dephase_steps": args.dephase,
-                   "afterstate_features": "bf16 ragged (ld 208), fused into K1" if feats else "off", "observations": "f32 (N,198)",
+                   "afterstate_features": "bf16 ragged (ld 208)" if feats else "off", "observations": "f32 (N,198)",
                    "legal_plays_per_step_mean": rows_per_step / N, "parallelism": f"games sharded x{world}, no collective",
                    "l2": "per-step working set (afterstates + features + observations) exceeds the 126 MB L2; no flush"},
-        "roofline": {"kernel": "K1 movegen (tier 0 warp kernel + tier 1/2 team kernels), afterstate features fused", "bound": "hbm",
+        "roofline": {"kernel": "K1 movegen (tier 0 warp kernel + tier 1/2 team kernels)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / (ms / K),
                      "algorithmic_bytes_per_launch": k1_bytes,

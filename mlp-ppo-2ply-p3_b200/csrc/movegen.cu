@@ -362,9 +362,18 @@ __global__ void __launch_bounds__(256) movegen_kernel(
                         // ai/batching.py:72-74), 16 bytes per lane, contiguous in global memory
                         uint4* fdst = reinterpret_cast<uint4*>(row_feats + (start + r0) * (long long)BG_FEAT_LD_BF16);
                         const uint8_t* sb = reinterpret_cast<const uint8_t*>(stage);
-                        for (int c = lane; c < rows * 26; c += 32) {
-                            const int r = c / 26, k = c - r * 26;
-                            fdst[c] = chunk_from_desc(sb + r * kBoardBytes, player, s_desc[k], s_lut);
+                        // lane's chunks: c = lane, lane+32, ...; (r, k) advance by (1, +6) with carry, no division
+                        int r = lane >= 26 ? 1 : 0, k = lane >= 26 ? lane - 26 : lane;
+                        const int nchunk = rows * 26;
+                        for (int c = lane; c < nchunk; c += 64) {
+                            const int k2 = k + 6 >= 26 ? k + 6 - 26 : k + 6, r2 = r + 1 + (k + 6 >= 26 ? 1 : 0);
+                            const uint4 v0 = chunk_from_desc(sb + r * kBoardBytes, player, s_desc[k], s_lut);
+                            const bool has2 = c + 32 < nchunk;
+                            uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
+                            if (has2) v1 = chunk_from_desc(sb + r2 * kBoardBytes, player, s_desc[k2], s_lut);
+                            fdst[c] = v0;
+                            if (has2) fdst[c + 32] = v1;
+                            k = k2 + 6 >= 26 ? k2 + 6 - 26 : k2 + 6; r = r2 + 1 + (k2 + 6 >= 26 ? 1 : 0);
                         }
                     }
                     __syncwarp();
