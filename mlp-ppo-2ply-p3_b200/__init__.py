@@ -9,6 +9,7 @@ from ._lib import BgError, LIB_PATH, lib  # noqa: F401
 from .build import build  # noqa: F401
 from .engine import (FEATURES, LD_BF16, MovegenWorkspace, encode, from_board52, initial_board52,  # noqa: F401
                      legal_moves, to_board52)
+from .sharding import reduce_report, shard_range  # noqa: F401
 from .value_net import ValueNet  # noqa: F401
 from .twoply import TwoPlySearch, greedy_actions, segment_argmax  # noqa: F401
 from .vec_env import B200BackgammonVecEnv, StepInfos, VectorizedBackgammonEnv  # noqa: F401
