@@ -23,17 +23,20 @@ constexpr int kHidden = BG_HIDDEN;     // UMMA N
 constexpr int kKPad = BG_FEAT_LD_BF16; // 208 = 13 x UMMA K
 constexpr int kChunks = kKPad / 8;     // 26 sixteen-byte chunks per row
 constexpr int kOperandBytes = kChunks * kTileM * 16;   // 53,248
-constexpr int kMlpThreads = 128;
+constexpr int kStages = 2;             // A tiles / TMEM accumulators in flight
+// warp roles: 0-3 epilogue (TMEM lanes 32w..32w+31), 4-11 A-tile producers (2 threads per position), 12 MMA issuer
+constexpr int kEpiThreads = 128, kProdThreads = 256;
+constexpr int kMlpThreads = kEpiThreads + kProdThreads + 32;
 
 struct MlpSmem {
-    uint8_t A[kOperandBytes];          // feature tile, rebuilt per 128 positions
+    uint8_t A[kStages][kOperandBytes]; // feature tiles (tcgen05 K-major operand layout)
     uint8_t W[kOperandBytes];          // W1 tile, resident
-    uint32_t boards[kTileM * kBoardWords];
+    uint32_t boards[kStages][kTileM * kBoardWords];
     float b1[kHidden];
     float wv[kHidden];
-    int8_t flag[kTileM];
+    int8_t flag[kStages][kTileM];
     uint2 units[16];
-    unsigned long long mbar;
+    unsigned long long a_full[kStages], a_empty[kStages], acc_full[kStages], acc_empty[kStages];
     uint32_t tmem_base;
 };
 
@@ -53,8 +56,7 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t da, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
         :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t r[32];
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
@@ -64,8 +66,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(bar)) : "memory");
 }
 
 // win reward of a finished game seen from `p`, who has just borne off 15 (environment/backgammon_env.py:156-171,365-405)
@@ -80,6 +100,12 @@ __device__ __forceinline__ float win_reward(const int8_t* b, int p) {
     return bgm ? 2.0f : 1.5f;
 }
 
+// Persistent, warp-specialised, double-buffered:
+//   producers (8 warps): wait a_empty[s] -> stage 128 boards -> expand them into A[s] -> fence.proxy.async -> arrive a_full[s]
+//   MMA (1 thread)     : wait a_full[s], acc_empty[s] -> 13 x tcgen05.mma into TMEM columns [128 s, 128 s + 128)
+//                        -> tcgen05.commit to a_empty[s] and to acc_full[s]
+//   epilogue (4 warps) : wait acc_full[s] -> tcgen05.ld the row's 128 accumulators -> bias, ReLU, value head -> store
+//                        -> arrive acc_empty[s]
 // terminal_aware: a row whose flag player has 15 men off gets the win reward instead of the network value
 // (leaf rule of the 2-ply search).
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
@@ -89,25 +115,28 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
     float* __restrict__ values) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     MlpSmem& S = *reinterpret_cast<MlpSmem*>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (n_rows_dev) B = min(B, (long long)*n_rows_dev);
 
-    // ---- one-time setup: W1 into the operand layout, biases, mbarrier, TMEM
+    // ---- one-time setup: W1 into the operand layout, biases, mbarriers, TMEM (2 x 128 columns)
     for (int c = tid; c < kChunks * kHidden; c += kMlpThreads) {
         int kc = c / kHidden, n = c - kc * kHidden;             // consecutive threads -> consecutive n: conflict-free stores
         uint4 v = *reinterpret_cast<const uint4*>(w1 + (size_t)n * kKPad + kc * 8);
         *reinterpret_cast<uint4*>(S.W + kc * 2048 + n * 16) = v;
     }
     load_units_lut(S.units);
-    S.b1[tid] = b1[tid];
-    S.wv[tid] = wv[tid];
+    if (tid < kHidden) { S.b1[tid] = b1[tid]; S.wv[tid] = wv[tid]; }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(smem_u32(&S.mbar)) : "memory");
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&S.a_full[s], kProdThreads); mbar_init(&S.a_empty[s], 1);
+            mbar_init(&S.acc_full[s], 1);          mbar_init(&S.acc_empty[s], kEpiThreads);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
-                     :: "r"(smem_u32(&S.tmem_base)), "r"((uint32_t)kHidden) : "memory");
+                     :: "r"(smem_u32(&S.tmem_base)), "r"((uint32_t)(kStages * kHidden)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // W tile visible to the tensor-core proxy
@@ -115,84 +144,97 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = S.tmem_base;
-    const uint32_t a_addr = smem_u32(S.A), w_addr = smem_u32(S.W);
-    uint32_t phase = 0;
-
     const long long n_tiles = (B + kTileM - 1) / kTileM;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long row0 = tile * kTileM;
-        const int rows = (int)min((long long)kTileM, B - row0);
-        // ---- stage boards (coalesced) and flags
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
-        for (int i = tid; i < rows * kBoardWords; i += kMlpThreads) S.boards[i] = __ldg(src + i);
-        if (tid < rows) S.flag[tid] = (int8_t)(((flags ? flags[row0 + tid] : flag_all) ^ flip_flags) & 1);
-        __syncthreads();
-        // ---- build the A tile: thread = row, 26 chunks of 16 B (rows past the end are zero)
-        {
-            const int8_t* b = reinterpret_cast<const int8_t*>(S.boards) + tid * kBoardBytes;
-            const int fl = S.flag[tid];
-#pragma unroll 2
-            for (int kc = 0; kc < kChunks; ++kc) {
-                uint4 v = tid < rows ? feature_chunk_lut(b, fl, kc, S.units) : make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(S.A + kc * 2048 + tid * 16) = v;
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        __syncthreads();
-        // ---- 13 MMAs issued by one thread, completion signalled on the mbarrier
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-#pragma unroll
-            for (int ks = 0; ks < kKPad / 16; ++ks) {
-                uint64_t da = make_smem_desc(a_addr + ks * 2 * 2048);
-                uint64_t db = make_smem_desc(w_addr + ks * 2 * 2048);
-                mma_bf16_ss(tmem, da, db, kIdesc, ks > 0 ? 1u : 0u);
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
-                         :: "r"(smem_u32(&S.mbar)) : "memory");
-        }
-        // ---- wait for the accumulator
-        {
-            uint32_t done = 0;
-            const uint32_t bar = smem_u32(&S.mbar);
-            while (!done) {
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                    "selp.u32 %0, 1, 0, p;\n\t}\n"
-                    : "=r"(done) : "r"(bar), "r"(phase) : "memory");
-            }
-            phase ^= 1u;
-        }
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        // ---- epilogue: thread t of warp w owns TMEM lane 32w+t = row 32w+t
-        float v = bv;
+
+    if (warp >= 4 && warp < 12) {
+        // ================= producers =================
+        const int ptid = tid - kEpiThreads;                    // 0..255
+        const int row = ptid & (kTileM - 1), half = ptid >> 7;  // two threads per position: chunks [13 half, 13 half + 13)
+        int k = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+            const int s = k & 1;
+            const uint32_t it = (uint32_t)(k >> 1);
+            mbar_wait(&S.a_empty[s], (it & 1u) ^ 1u);           // MMAs that read A[s] two tiles ago are done
+            const long long row0 = tile * kTileM;
+            const int rows = (int)min((long long)kTileM, B - row0);
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
+            for (int i = ptid; i < rows * kBoardWords; i += kProdThreads) S.boards[s][i] = __ldg(src + i);
+            if (ptid < rows) S.flag[s][ptid] = (int8_t)(((flags ? flags[row0 + ptid] : flag_all) ^ flip_flags) & 1);
+            asm volatile("bar.sync 1, %0;\n" :: "n"(kProdThreads) : "memory");
+            const int8_t* b = reinterpret_cast<const int8_t*>(S.boards[s]) + row * kBoardBytes;
+            const int fl = S.flag[s][row];
+            uint8_t* arow = S.A[s] + row * 16;
 #pragma unroll 1
-        for (int c0 = 0; c0 < kHidden; c0 += 32) {
-            float acc[32];
-            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+            for (int kc = half * 13; kc < half * 13 + 13; ++kc) {
+                uint4 v = row < rows ? feature_chunk_lut(b, fl, kc, S.units) : make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(arow + kc * 2048) = v;
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            mbar_arrive(&S.a_full[s]);
+        }
+    } else if (warp == 12) {
+        // ================= MMA issuer =================
+        const uint32_t w_addr = smem_u32(S.W);
+        int k = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+            const int s = k & 1;
+            const uint32_t it = (uint32_t)(k >> 1);
+            mbar_wait(&S.a_full[s], it & 1u);
+            mbar_wait(&S.acc_empty[s], (it & 1u) ^ 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(S.A[s]);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float h = acc[j] + S.b1[c0 + j];
-                v = fmaf(S.wv[c0 + j], fmaxf(h, 0.0f), v);
+                for (int ks = 0; ks < kKPad / 16; ++ks)
+                    mma_bf16_ss(tmem + (uint32_t)(s * kHidden), make_smem_desc(a_addr + ks * 2 * 2048),
+                                make_smem_desc(w_addr + ks * 2 * 2048), kIdesc, ks > 0 ? 1u : 0u);
+                umma_commit(&S.a_empty[s]);                      // A[s] may be rebuilt
+                umma_commit(&S.acc_full[s]);                     // accumulator s is complete
+            }
+            __syncwarp();
+        }
+    } else if (warp < 4) {
+        // ================= epilogue =================
+        int k = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+            const int s = k & 1;
+            const uint32_t it = (uint32_t)(k >> 1);
+            const long long row0 = tile * kTileM;
+            const int rows = (int)min((long long)kTileM, B - row0);
+            mbar_wait(&S.acc_full[s], it & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kHidden; c0 += 32) {
+                uint32_t acc[32];
+                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * kHidden + c0), acc);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(&S.b1[c0 + j]);
+                    const float4 ww = *reinterpret_cast<const float4*>(&S.wv[c0 + j]);
+                    v0 = fmaf(ww.x, fmaxf(__uint_as_float(acc[j + 0]) + bb.x, 0.0f), v0);
+                    v1 = fmaf(ww.y, fmaxf(__uint_as_float(acc[j + 1]) + bb.y, 0.0f), v1);
+                    v2 = fmaf(ww.z, fmaxf(__uint_as_float(acc[j + 2]) + bb.z, 0.0f), v2);
+                    v3 = fmaf(ww.w, fmaxf(__uint_as_float(acc[j + 3]) + bb.w, 0.0f), v3);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            mbar_arrive(&S.acc_empty[s]);                        // accumulator s may be overwritten
+            if (tid < rows) {
+                float v = bv + ((v0 + v1) + (v2 + v3));
+                if (terminal_aware) {
+                    const int8_t* b = boards + (row0 + tid) * kBoardBytes;
+                    const int fl = ((flags ? flags[row0 + tid] : flag_all) ^ flip_flags) & 1;
+                    if (b[50 + fl] == 15) v = win_reward(b, fl);
+                }
+                values[row0 + tid] = v;
             }
         }
-        if (tid < rows) {
-            if (terminal_aware) {
-                const int8_t* b = reinterpret_cast<const int8_t*>(S.boards) + tid * kBoardBytes;
-                const int fl = S.flag[tid];
-                if (b[50 + fl] == 15) v = win_reward(b, fl);
-            }
-            values[row0 + tid] = v;
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        __syncthreads();                                  // TMEM and the staging buffers are free again
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"((uint32_t)kHidden) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"((uint32_t)(kStages * kHidden)) : "memory");
 }
 
 __global__ void pack_w1_kernel(const float* __restrict__ w, uint16_t* __restrict__ out) {
