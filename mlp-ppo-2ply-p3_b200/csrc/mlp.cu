@@ -24,8 +24,10 @@ constexpr int kKPad = BG_FEAT_LD_BF16; // 208 = 13 x UMMA K
 constexpr int kChunks = kKPad / 8;     // 26 sixteen-byte chunks per row
 constexpr int kOperandBytes = kChunks * kTileM * 16;   // 53,248
 constexpr int kStages = 2;             // A tiles / TMEM accumulators in flight
-// warp roles: 0-3 epilogue (TMEM lanes 32w..32w+31), 4-11 A-tile producers (2 threads per position), 12 MMA issuer
-constexpr int kEpiThreads = 128, kProdThreads = 256;
+// warp roles: 0-7 epilogue (warp w: TMEM lanes 32(w%4).., columns 64(w/4)..), 8-15 A-tile producers (2 threads per
+// position), 16 MMA issuer
+constexpr int kEpiThreads = 256, kProdThreads = 256;
+constexpr int kEpiWarps = kEpiThreads / 32, kProdWarps = kProdThreads / 32;
 constexpr int kMlpThreads = kEpiThreads + kProdThreads + 32;
 
 struct MlpSmem {
@@ -35,6 +37,7 @@ struct MlpSmem {
     float b1[kHidden];
     float wv[kHidden];
     int8_t flag[kStages][kTileM];
+    float part[2][kTileM];             // partial value-head sums of the upper 64 hidden units
     uint2 units[16];
     unsigned long long a_full[kStages], a_empty[kStages], acc_full[kStages], acc_empty[kStages];
     uint32_t tmem_base;
@@ -100,11 +103,45 @@ __device__ __forceinline__ float win_reward(const int8_t* b, int p) {
     return bgm ? 2.0f : 1.5f;
 }
 
+// board52 byte `idx` (a compile-time constant after unrolling) of a row held as 13 words in registers
+__device__ __forceinline__ int reg_byte(const uint32_t (&w)[kBoardWords], int idx) { return (int)((w[idx >> 2] >> (8 * (idx & 3))) & 15u); }
+// chunk k of the feature row, k constant after unrolling (same content as feature_chunk_lut)
+__device__ __forceinline__ uint4 feature_chunk_regs(const uint32_t (&w)[kBoardWords], int flag, int k, const uint2* lut) {
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (k < 12) {
+        uint2 a = lut[reg_byte(w, 2 * k)], c = lut[reg_byte(w, 2 * k + 1)];
+        o = make_uint4(a.x, a.y, c.x, c.y);
+    } else if (k == 12) {
+        uint2 a = lut[reg_byte(w, 24)], c = lut[reg_byte(w, 25)];
+        o = make_uint4(bar_off_pair_bf16(reg_byte(w, 48), reg_byte(w, 50)), a.x, a.y, c.x);
+    } else if (k < 24) {
+        const int q = 2 * (k - 12) - 1;
+        uint2 a = lut[reg_byte(w, 24 + q)], c = lut[reg_byte(w, 25 + q)], e = lut[reg_byte(w, 26 + q)];
+        o = make_uint4(a.y, c.x, c.y, e.x);
+    } else if (k == 24) {
+        o.x = lut[reg_byte(w, 47)].y;
+        o.y = bar_off_pair_bf16(reg_byte(w, 49), reg_byte(w, 51));
+        o.z = flag == 0 ? 0x00003F80u : 0x3F800000u;
+    }
+    return o;
+}
+template <int HALF>
+__device__ __forceinline__ void build_half_row(const uint32_t (&w)[kBoardWords], int flag, const uint2* lut, uint8_t* arow, bool live) {
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+        const int kc = HALF * 13 + i;
+        uint4 v = feature_chunk_regs(w, flag, kc, lut);
+        if (!live) v = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(arow + kc * 2048) = v;
+    }
+}
+
 // Persistent, warp-specialised, double-buffered:
 //   producers (8 warps): wait a_empty[s] -> stage 128 boards -> expand them into A[s] -> fence.proxy.async -> arrive a_full[s]
 //   MMA (1 thread)     : wait a_full[s], acc_empty[s] -> 13 x tcgen05.mma into TMEM columns [128 s, 128 s + 128)
 //                        -> tcgen05.commit to a_empty[s] and to acc_full[s]
-//   epilogue (4 warps) : wait acc_full[s] -> tcgen05.ld the row's 128 accumulators -> bias, ReLU, value head -> store
+//   epilogue (8 warps) : wait acc_full[s] -> tcgen05.ld 64 of the row's accumulators -> bias, ReLU, value head
+//                        -> the two column halves are combined through shared memory -> store
 //                        -> arrive acc_empty[s]
 // terminal_aware: a row whose flag player has 15 men off gets the win reward instead of the network value
 // (leaf rule of the 2-ply search).
@@ -146,7 +183,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
     const uint32_t tmem = S.tmem_base;
     const long long n_tiles = (B + kTileM - 1) / kTileM;
 
-    if (warp >= 4 && warp < 12) {
+    if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
         // ================= producers =================
         const int ptid = tid - kEpiThreads;                    // 0..255
         const int row = ptid & (kTileM - 1), half = ptid >> 7;  // two threads per position: chunks [13 half, 13 half + 13)
@@ -161,18 +198,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
             for (int i = ptid; i < rows * kBoardWords; i += kProdThreads) S.boards[s][i] = __ldg(src + i);
             if (ptid < rows) S.flag[s][ptid] = (int8_t)(((flags ? flags[row0 + ptid] : flag_all) ^ flip_flags) & 1);
             asm volatile("bar.sync 1, %0;\n" :: "n"(kProdThreads) : "memory");
-            const int8_t* b = reinterpret_cast<const int8_t*>(S.boards[s]) + row * kBoardBytes;
+            uint32_t w[kBoardWords];
+#pragma unroll
+            for (int i = 0; i < kBoardWords; ++i) w[i] = S.boards[s][row * kBoardWords + i];   // stride 13 words: conflict-free
             const int fl = S.flag[s][row];
             uint8_t* arow = S.A[s] + row * 16;
-#pragma unroll 1
-            for (int kc = half * 13; kc < half * 13 + 13; ++kc) {
-                uint4 v = row < rows ? feature_chunk_lut(b, fl, kc, S.units) : make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(arow + kc * 2048) = v;
-            }
+            if (half == 0) build_half_row<0>(w, fl, S.units, arow, row < rows);
+            else           build_half_row<1>(w, fl, S.units, arow, row < rows);
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             mbar_arrive(&S.a_full[s]);
         }
-    } else if (warp == 12) {
+    } else if (warp == kEpiWarps + kProdWarps) {
         // ================= MMA issuer =================
         const uint32_t w_addr = smem_u32(S.W);
         int k = 0;
@@ -193,8 +229,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
             }
             __syncwarp();
         }
-    } else if (warp < 4) {
+    } else if (warp < kEpiWarps) {
         // ================= epilogue =================
+        const int row = (warp & 3) * 32 + lane;                 // TMEM lane = position within the tile
+        const int chalf = warp >> 2;                            // hidden units [64 chalf, 64 chalf + 64)
         int k = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
             const int s = k & 1;
@@ -204,10 +242,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
             mbar_wait(&S.acc_full[s], it & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < kHidden; c0 += 32) {
+#pragma unroll
+            for (int c0 = 64 * chalf; c0 < 64 * chalf + 64; c0 += 32) {
                 uint32_t acc[32];
-                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * kHidden + c0), acc);
+                tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * kHidden + c0), acc);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const float4 bb = *reinterpret_cast<const float4*>(&S.b1[c0 + j]);
@@ -220,14 +258,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             mbar_arrive(&S.acc_empty[s]);                        // accumulator s may be overwritten
-            if (tid < rows) {
-                float v = bv + ((v0 + v1) + (v2 + v3));
+            const float part = (v0 + v1) + (v2 + v3);
+            if (chalf == 1) S.part[k & 1][row] = part;
+            asm volatile("bar.sync 2, %0;\n" :: "n"(kEpiThreads) : "memory");
+            if (chalf == 0 && row < rows) {
+                float v = bv + (part + S.part[k & 1][row]);
                 if (terminal_aware) {
-                    const int8_t* b = boards + (row0 + tid) * kBoardBytes;
-                    const int fl = ((flags ? flags[row0 + tid] : flag_all) ^ flip_flags) & 1;
+                    const int8_t* b = boards + (row0 + row) * kBoardBytes;
+                    const int fl = ((flags ? flags[row0 + row] : flag_all) ^ flip_flags) & 1;
                     if (b[50 + fl] == 15) v = win_reward(b, fl);
                 }
-                values[row0 + tid] = v;
+                values[row0 + row] = v;
             }
         }
     }
