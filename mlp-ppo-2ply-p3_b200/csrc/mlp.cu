@@ -36,7 +36,6 @@ struct MlpSmem {
     uint32_t boards[kStages][kTileM * kBoardWords];
     float b1[kHidden];
     float wv[kHidden];
-    int8_t flag[kStages][kTileM];
     float part[2][kTileM];             // partial value-head sums of the upper 64 hidden units
     uint2 units[16];
     unsigned long long a_full[kStages], a_empty[kStages], acc_full[kStages], acc_empty[kStages];
@@ -68,8 +67,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -187,21 +191,29 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
         // ================= producers =================
         const int ptid = tid - kEpiThreads;                    // 0..255
         const int row = ptid & (kTileM - 1), half = ptid >> 7;  // two threads per position: chunks [13 half, 13 half + 13)
+        // boards (and flags) of tile k+1 are prefetched with cp.async while tile k is being expanded
+        auto prefetch = [&](long long tile, int s) {
+            const long long row0 = tile * kTileM;
+            const int rows = (int)min((long long)kTileM, B - row0);
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
+            for (int i = ptid; i < rows * kBoardWords; i += kProdThreads) cp_async4(&S.boards[s][i], src + i);
+            cp_async_commit();
+        };
+        if ((long long)blockIdx.x < n_tiles) prefetch(blockIdx.x, 0);
         int k = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
             const int s = k & 1;
             const uint32_t it = (uint32_t)(k >> 1);
-            mbar_wait(&S.a_empty[s], (it & 1u) ^ 1u);           // MMAs that read A[s] two tiles ago are done
             const long long row0 = tile * kTileM;
             const int rows = (int)min((long long)kTileM, B - row0);
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
-            for (int i = ptid; i < rows * kBoardWords; i += kProdThreads) S.boards[s][i] = __ldg(src + i);
-            if (ptid < rows) S.flag[s][ptid] = (int8_t)(((flags ? flags[row0 + ptid] : flag_all) ^ flip_flags) & 1);
-            asm volatile("bar.sync 1, %0;\n" :: "n"(kProdThreads) : "memory");
+            const int fl = row < rows ? (int)(((flags ? flags[row0 + row] : flag_all) ^ flip_flags) & 1) : 0;
+            cp_async_wait_all();                                // this thread's share of tile k's boards has landed
+            asm volatile("bar.sync 1, %0;\n" :: "n"(kProdThreads) : "memory");   // ... and everybody else's; tile k-1 is fully built
+            if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x, s ^ 1);
             uint32_t w[kBoardWords];
 #pragma unroll
             for (int i = 0; i < kBoardWords; ++i) w[i] = S.boards[s][row * kBoardWords + i];   // stride 13 words: conflict-free
-            const int fl = S.flag[s][row];
+            mbar_wait(&S.a_empty[s], (it & 1u) ^ 1u);           // MMAs that read A[s] two tiles ago are done
             uint8_t* arow = S.A[s] + row * 16;
             if (half == 0) build_half_row<0>(w, fl, S.units, arow, row < rows);
             else           build_half_row<1>(w, fl, S.units, arow, row < rows);
@@ -242,19 +254,19 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
             mbar_wait(&S.acc_full[s], it & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+            uint32_t acc[64];
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * kHidden + 64 * chalf);
+            tmem_ld32(taddr, acc);
+            tmem_ld32(taddr + 32, acc + 32);
+            tmem_ld_wait();
 #pragma unroll
-            for (int c0 = 64 * chalf; c0 < 64 * chalf + 64; c0 += 32) {
-                uint32_t acc[32];
-                tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * kHidden + c0), acc);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(&S.b1[c0 + j]);
-                    const float4 ww = *reinterpret_cast<const float4*>(&S.wv[c0 + j]);
-                    v0 = fmaf(ww.x, fmaxf(__uint_as_float(acc[j + 0]) + bb.x, 0.0f), v0);
-                    v1 = fmaf(ww.y, fmaxf(__uint_as_float(acc[j + 1]) + bb.y, 0.0f), v1);
-                    v2 = fmaf(ww.z, fmaxf(__uint_as_float(acc[j + 2]) + bb.z, 0.0f), v2);
-                    v3 = fmaf(ww.w, fmaxf(__uint_as_float(acc[j + 3]) + bb.w, 0.0f), v3);
-                }
+            for (int j = 0; j < 64; j += 4) {
+                const float4 bb = *reinterpret_cast<const float4*>(&S.b1[64 * chalf + j]);
+                const float4 ww = *reinterpret_cast<const float4*>(&S.wv[64 * chalf + j]);
+                v0 = fmaf(ww.x, fmaxf(__uint_as_float(acc[j + 0]) + bb.x, 0.0f), v0);
+                v1 = fmaf(ww.y, fmaxf(__uint_as_float(acc[j + 1]) + bb.y, 0.0f), v1);
+                v2 = fmaf(ww.z, fmaxf(__uint_as_float(acc[j + 2]) + bb.z, 0.0f), v2);
+                v3 = fmaf(ww.w, fmaxf(__uint_as_float(acc[j + 3]) + bb.w, 0.0f), v3);
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             mbar_arrive(&S.acc_empty[s]);                        // accumulator s may be overwritten
