@@ -2,15 +2,19 @@
 //
 // Replaces the value path of BackgammonPolicyNetwork.forward (src/agent/policy_network.py:58-75)
 //     v = value_head( relu( fc1(x) ) ),   x = the 198 features of a position (K3's encoding)
-// for B positions given as board52 + turn flag.  The 198-wide bf16 feature rows never touch HBM:
-// a CTA stages 128 boards in shared memory, expands them into the tcgen05 K-major operand layout,
-// multiplies by the resident W1 tile (128 hidden x 208) with 13 tcgen05.mma (M128 N128 K16,
-// bf16 x bf16 -> f32 in TMEM) and reduces the hidden layer in the epilogue straight out of TMEM
-// (tcgen05.ld): value = b_v + sum_h w_v[h] * relu(acc[h] + b1[h]).  HBM traffic: 53 B in, 4 B out per position.
+// for B positions given as board52 + turn flag.  The 198-wide bf16 feature rows never touch HBM (nor shared
+// memory): a CTA stages 128 boards, each producer thread expands its position's row in registers and writes it
+// into TENSOR MEMORY (tcgen05.st, lane = position, two bf16 per 32-bit column), the MMA thread multiplies it by
+// the W1 tile resident in shared memory with 13 tcgen05.mma (A from TMEM, B from smem; M128 N128 K16,
+// bf16 x bf16 -> f32 in TMEM), and the epilogue reduces the hidden layer straight out of TMEM (tcgen05.ld):
+// value = b_v + sum_h w_v[h] * relu(acc[h] + b1[h]).  HBM traffic: 53 B in, 4 B out per position.
+// (With both operands in shared memory one K16 step reads 8 KB per 64 cycles -- the SM's whole shared-memory
+// bandwidth -- which capped the first version at ~0.6 PFLOP/s; with A in TMEM shared memory only feeds W1.)
 //
-// Shared-memory operand layout (SWIZZLE_NONE "interleave", K-major): element (row r, column k) of a
+// W1 shared-memory operand layout (SWIZZLE_NONE "interleave", K-major): element (row r, column k) of the
 // 128 x 208 bf16 tile lives at  (k/8)*2048 + r*16 + (k%8)*2  bytes: core matrices of 8 rows x 16 bytes
 // are contiguous (128 B), 8-row groups advance by SBO = 128 B, 8-column chunks by LBO = 2048 B.
+// TMEM columns: [0,256) two f32 accumulators of 128 columns; [256, 464) two A tiles of 104 columns.
 #include <cuda_bf16.h>
 #include "bg_device.cuh"
 #include "bg_features.cuh"
@@ -24,6 +28,9 @@ constexpr int kKPad = BG_FEAT_LD_BF16; // 208 = 13 x UMMA K
 constexpr int kChunks = kKPad / 8;     // 26 sixteen-byte chunks per row
 constexpr int kOperandBytes = kChunks * kTileM * 16;   // 53,248
 constexpr int kStages = 2;             // A tiles / TMEM accumulators in flight
+constexpr int kAColsPerTile = kKPad / 2;                 // 104 TMEM columns per A tile (2 bf16 per column)
+constexpr int kTmemACol0 = kStages * kHidden;            // first A column (after the accumulators)
+constexpr int kTmemCols = 512;
 // warp roles: 0-7 epilogue (warp w: TMEM lanes 32(w%4).., columns 64(w/4)..), 8-15 A-tile producers (2 threads per
 // position), 16 MMA issuer
 constexpr int kEpiThreads = 256, kProdThreads = 256;
@@ -31,7 +38,6 @@ constexpr int kEpiWarps = kEpiThreads / 32, kProdWarps = kProdThreads / 32;
 constexpr int kMlpThreads = kEpiThreads + kProdThreads + 32;
 
 struct MlpSmem {
-    uint8_t A[kStages][kOperandBytes]; // feature tiles (tcgen05 K-major operand layout)
     uint8_t W[kOperandBytes];          // W1 tile, resident
     uint32_t boards[kStages][kTileM * kBoardWords];
     float b1[kHidden];
@@ -52,11 +58,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kHidden >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 
-__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// D[tmem_d] (+)= A[tmem_a] * B[smem desc]
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 16 bytes (8 bf16 of one row) -> 4 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint4& v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n"
+                 :: "r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -130,19 +142,20 @@ __device__ __forceinline__ uint4 feature_chunk_regs(const uint32_t (&w)[kBoardWo
     return o;
 }
 template <int HALF>
-__device__ __forceinline__ void build_half_row(const uint32_t (&w)[kBoardWords], int flag, const uint2* lut, uint8_t* arow, bool live) {
+__device__ __forceinline__ void build_half_row(const uint32_t (&w)[kBoardWords], int flag, const uint2* lut, uint32_t tmem_row, bool live) {
 #pragma unroll
     for (int i = 0; i < 13; ++i) {
         const int kc = HALF * 13 + i;
         uint4 v = feature_chunk_regs(w, flag, kc, lut);
         if (!live) v = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(arow + kc * 2048) = v;
+        tmem_st4(tmem_row + (uint32_t)(kc * 4), v);              // chunk kc = bf16 columns 8kc..8kc+7 = TMEM columns 4kc..4kc+3
     }
 }
 
 // Persistent, warp-specialised, double-buffered:
-//   producers (8 warps): wait a_empty[s] -> stage 128 boards -> expand them into A[s] -> fence.proxy.async -> arrive a_full[s]
-//   MMA (1 thread)     : wait a_full[s], acc_empty[s] -> 13 x tcgen05.mma into TMEM columns [128 s, 128 s + 128)
+//   producers (8 warps): boards of tile k+1 prefetched with cp.async; wait a_empty[s] -> expand the row in registers
+//                        -> tcgen05.st into the TMEM A tile s -> arrive a_full[s]
+//   MMA (1 thread)     : wait a_full[s], acc_empty[s] -> 13 x tcgen05.mma (A TMEM, B smem) into TMEM columns [128 s, 128 s + 128)
 //                        -> tcgen05.commit to a_empty[s] and to acc_full[s]
 //   epilogue (8 warps) : wait acc_full[s] -> tcgen05.ld 64 of the row's accumulators -> bias, ReLU, value head
 //                        -> the two column halves are combined through shared memory -> store
@@ -177,7 +190,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
-                     :: "r"(smem_u32(&S.tmem_base)), "r"((uint32_t)(kStages * kHidden)) : "memory");
+                     :: "r"(smem_u32(&S.tmem_base)), "r"((uint32_t)kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // W tile visible to the tensor-core proxy
@@ -214,10 +227,12 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
 #pragma unroll
             for (int i = 0; i < kBoardWords; ++i) w[i] = S.boards[s][row * kBoardWords + i];   // stride 13 words: conflict-free
             mbar_wait(&S.a_empty[s], (it & 1u) ^ 1u);           // MMAs that read A[s] two tiles ago are done
-            uint8_t* arow = S.A[s] + row * 16;
-            if (half == 0) build_half_row<0>(w, fl, S.units, arow, row < rows);
-            else           build_half_row<1>(w, fl, S.units, arow, row < rows);
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kTmemACol0 + s * kAColsPerTile);
+            if (half == 0) build_half_row<0>(w, fl, S.units, trow, row < rows);
+            else           build_half_row<1>(w, fl, S.units, trow, row < rows);
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             mbar_arrive(&S.a_full[s]);
         }
     } else if (warp == kEpiWarps + kProdWarps) {
@@ -231,10 +246,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
             mbar_wait(&S.acc_empty[s], (it & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             if (lane == 0) {
-                const uint32_t a_addr = smem_u32(S.A[s]);
 #pragma unroll
                 for (int ks = 0; ks < kKPad / 16; ++ks)
-                    mma_bf16_ss(tmem + (uint32_t)(s * kHidden), make_smem_desc(a_addr + ks * 2 * 2048),
+                    mma_bf16_ts(tmem + (uint32_t)(s * kHidden), tmem + (uint32_t)(kTmemACol0 + s * kAColsPerTile + ks * 8),
                                 make_smem_desc(w_addr + ks * 2 * 2048), kIdesc, ks > 0 ? 1u : 0u);
                 umma_commit(&S.a_empty[s]);                      // A[s] may be rebuilt
                 umma_commit(&S.acc_full[s]);                     // accumulator s is complete
@@ -287,7 +301,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"((uint32_t)(kStages * kHidden)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
 }
 
 __global__ void pack_w1_kernel(const float* __restrict__ w, uint16_t* __restrict__ out) {
