@@ -39,62 +39,74 @@ def greedy_actions(env, net: ValueNet):
 
 
 class TwoPlySearch:
-    def __init__(self, net: ValueNet, max_afterstates_per_chunk: int = 65536, replies_per_position: int = 40):
+    """Persistent workspaces (no allocation and no host synchronisation inside the chunk loop): the only host
+    syncs of search() are the row count after the root move generation and one status read at the end."""
+
+    def __init__(self, net: ValueNet, max_afterstates_per_chunk: int = 32768, replies_per_position: int = 40):
         self.net = net
         self.chunk = int(max_afterstates_per_chunk)
         self.rpp = int(replies_per_position)
         self.leaves_evaluated = 0
+        self._bufs = None
 
-    def _score_chunk(self, A: torch.Tensor, movers: torch.Tensor) -> torch.Tensor:
+    def _workspace(self, dev):
+        if self._bufs is None or self._bufs["dev"] != dev or self._bufs["rpp"] != self.rpp:
+            W = self.chunk * 21
+            cap = max(W * self.rpp, 4096)
+            z = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+            self._bufs = dict(dev=dev, rpp=self.rpp, cap=cap, ws=MovegenWorkspace(W, dev), counts=z(W, torch.int32),
+                              starts=z(W, torch.int64), alloc=torch.zeros(1, dtype=torch.int64, device=dev),
+                              replies=z((cap, 52), torch.int8), rowp=z(cap, torch.int8), leaf_v=z(cap, torch.float32),
+                              pass_v=z(self.chunk, torch.float32), leaves=torch.zeros(1, dtype=torch.int64, device=dev))
+        return self._bufs
+
+    def _score_chunk(self, A: torch.Tensor, movers: torch.Tensor, out: torch.Tensor):
         dev = A.device
         M = A.shape[0]
-        W = M * 21
-        ws = MovegenWorkspace(W, dev)
-        counts = torch.empty(W, dtype=torch.int32, device=dev)
-        starts = torch.empty(W, dtype=torch.int64, device=dev)
-        alloc = torch.zeros(1, dtype=torch.int64, device=dev)
-        cap = max(W * self.rpp, 4096)
+        b = self._workspace(dev)
         L = lib()
-        while True:
-            replies = torch.empty((cap, 52), dtype=torch.int8, device=dev)
-            rowp = torch.empty(cap, dtype=torch.int8, device=dev)
-            alloc.zero_()
-            ws.status.zero_()
-            with torch.cuda.device(dev):
-                check(L.bg_movegen_replies_slab(A.data_ptr(), movers.data_ptr(), M, 0, replies.data_ptr(), cap,
-                                                rowp.data_ptr(), None, None, counts.data_ptr(), starts.data_ptr(),
-                                                alloc.data_ptr(), ws.status.data_ptr(), ws.buf.data_ptr(), ws.nbytes,
-                                                _stream()), "bg_movegen_replies_slab")
-            st = int(ws.status.item())
-            if st & 4:                      # output overflow: grow and redo (never dropped silently)
-                cap *= 2
-                continue
-            if st:
-                raise BgError(f"2-ply reply generation: device status {st}: {_lib.status_message(st)}")
-            break
-        n_leaves = int(alloc.item())
-        self.leaves_evaluated += n_leaves
-        leaf_v = self.net.values(replies, rowp, terminal_aware=True, n_rows_dev=alloc)
-        pass_v = self.net.values(A, movers, flip_flags=True)
-        scores = torch.empty(M, dtype=torch.float32, device=dev)
+        b["alloc"].zero_()
         with torch.cuda.device(dev):
-            check(L.bg_twoply_scores(leaf_v.data_ptr(), starts.data_ptr(), counts.data_ptr(), pass_v.data_ptr(),
-                                     A.data_ptr(), movers.data_ptr(), M, scores.data_ptr(), _stream()), "bg_twoply_scores")
-        return scores
+            check(L.bg_movegen_replies_slab(A.data_ptr(), movers.data_ptr(), M, 0, b["replies"].data_ptr(), b["cap"],
+                                            b["rowp"].data_ptr(), None, None, b["counts"].data_ptr(), b["starts"].data_ptr(),
+                                            b["alloc"].data_ptr(), b["ws"].status.data_ptr(), b["ws"].buf.data_ptr(),
+                                            b["ws"].nbytes, _stream()), "bg_movegen_replies_slab")
+        b["leaves"].add_(b["alloc"])
+        self.net.values(b["replies"], b["rowp"], terminal_aware=True, n_rows_dev=b["alloc"], out=b["leaf_v"])
+        self.net.values(A, movers, flip_flags=True, out=b["pass_v"])
+        with torch.cuda.device(dev):
+            check(L.bg_twoply_scores(b["leaf_v"].data_ptr(), b["starts"].data_ptr(), b["counts"].data_ptr(),
+                                     b["pass_v"].data_ptr(), A.data_ptr(), movers.data_ptr(), M, out.data_ptr(), _stream()),
+                  "bg_twoply_scores")
 
     def score_afterstates(self, after52: torch.Tensor, movers: torch.Tensor) -> torch.Tensor:
         """2-ply score of every root afterstate (movers[i] = the player who made play i)."""
         M = after52.shape[0]
-        out = torch.empty(M, dtype=torch.float32, device=after52.device)
-        for m0 in range(0, M, self.chunk):
-            m1 = min(M, m0 + self.chunk)
-            out[m0:m1] = self._score_chunk(after52[m0:m1].contiguous(), movers[m0:m1].contiguous())
-        return out
+        dev = after52.device
+        out = torch.empty(M, dtype=torch.float32, device=dev)
+        if M == 0:
+            return out
+        after52, movers = after52.contiguous(), movers.contiguous()
+        while True:
+            b = self._workspace(dev)
+            b["ws"].status.zero_()
+            b["leaves"].zero_()
+            for m0 in range(0, M, self.chunk):
+                m1 = min(M, m0 + self.chunk)
+                self._score_chunk(after52[m0:m1], movers[m0:m1], out[m0:m1])
+            st = int(b["ws"].status.item())                       # the one synchronisation
+            if st & 4:                                            # reply buffer too small: grow and redo (never dropped silently)
+                self.rpp *= 2
+                continue
+            if st:
+                raise BgError(f"2-ply reply generation: device status {st}: {_lib.status_message(st)}")
+            self.leaves_evaluated += int(b["leaves"].item())
+            return out
 
     def search(self, boards52: torch.Tensor, players: torch.Tensor, dice: torch.Tensor):
         """-> best (B,) i32 index into each root's legal plays (-1 if none), scores (total,) f32,
         offsets (B+1,) i64, afterstates (total,52) i8 (reference legal_moves order)."""
         counts, offsets, A, rowp = legal_moves(boards52, players, dice, with_row_players=True)
-        scores = self.score_afterstates(A, rowp) if A.shape[0] else torch.empty(0, dtype=torch.float32, device=A.device)
+        scores = self.score_afterstates(A, rowp)
         best, _ = segment_argmax(scores, offsets[:-1].contiguous(), counts.clamp(min=0).contiguous())
         return best, scores, offsets, A
