@@ -97,8 +97,9 @@ struct Warp {
         while (atomicCAS(&S.hash[s], kEmpty, (uint32_t)idx) != kEmpty) s = (s + 1) & (HS - 1);
     }
 
-    // Count the one-die moves of the parents at [pbase, pbase+np); fills S.pm / S.off. Returns the total.
-    __device__ __forceinline__ int count_moves(int pbase, int np, int d) {
+    // Count the one-die moves of the parents at [pbase, pbase+np); parent i plays die (i < split ? dA : dB).
+    // Fills S.pm / S.off. Returns the total.
+    __device__ __forceinline__ int count_moves(int pbase, int np, int split, int dA, int dB) {
         int base = 0;
         for (int i0 = 0; i0 < np; i0 += 32) {
             int i = i0 + lane;
@@ -106,7 +107,7 @@ struct Warp {
             if (i < np) {
                 Node n = load(pbase + i);
                 uint32_t mask; int special;
-                one_die(n, R, d, mask, special);
+                one_die(n, R, i < split ? dA : dB, mask, special);
                 cnt = __popc(mask) + (special >= 0);
                 S.pm[i] = mask | ((uint32_t)(special + 1) << 24);
             }
@@ -138,10 +139,12 @@ struct Warp {
         return nc + nsurv;
     }
 
-    // Children (die d) of the parents at [pbase, pbase+np), in the reference's order, appended to the region at
-    // cbase (nc entries so far).  use_set: drop children equal to an entry of the set or to an earlier child.
-    __device__ __forceinline__ int expand(int pbase, int np, int d, int total, int cbase, int nc, bool use_set) {
-        for (int c0 = 0; c0 < total && !overflow; c0 += 32) {
+    // Children of the parents at [pbase, pbase+np) (parent i plays die i < split ? dA : dB), candidates
+    // [cfrom, total) of the count_moves numbering, in the reference's order, appended to the region at cbase
+    // (nc entries so far).  use_set: drop children equal to an entry of the set or to an earlier child.
+    __device__ __forceinline__ int expand(int pbase, int np, int split, int dA, int dB, int cfrom, int total, int cbase,
+                                          int nc, bool use_set) {
+        for (int c0 = cfrom; c0 < total && !overflow; c0 += 32) {
             int idx = c0 + lane;
             bool valid = idx < total;
             Node ch;
@@ -155,7 +158,7 @@ struct Warp {
                 int j = idx - (int)S.off[lo];
                 uint32_t pmv = S.pm[lo];
                 Node p = load(pbase + lo);
-                ch = apply_move(p, R, d, pmv & 0xFFFFFFu, (int)(pmv >> 24) - 1, j);
+                ch = apply_move(p, R, lo < split ? dA : dB, pmv & 0xFFFFFFu, (int)(pmv >> 24) - 1, j);
             }
             bool keep = valid;
             if (use_set) {
@@ -171,59 +174,76 @@ struct Warp {
     }
 
     // Full generator.  On return the legal afterstates are nodes [obase, obase+n), reference order.
-    // One stage loop serves both roll kinds so that count_moves/expand are instantiated once (code size).
+    // count_moves/expand are instantiated once (code size: the kernel must stay inside the instruction cache).
+    //
+    // Non-doubles (handle_moves.py:109-200, get_all_moves.py:28-56): the two die orders are expanded TOGETHER.
+    // Region 1 holds both first levels -- the larger-die-first boards [0,nA), then the smaller-die-first boards
+    // [nA,nA+nB) (<= 16 each) -- one count_moves gives every first-level board its second-move count with the
+    // OTHER die, and one expand sweeps the candidates of pass A, then those of pass B, in order: exactly the
+    // reference's insertion order into full_moves, with its first-wins dedupe, in half the stages.
     __device__ void generate(const Node& root, int d0, int d1, int& obase, int& n) {
         obase = 0; n = 0;
-        if (lane == 0) store(kRoot, root);
         const bool dbl = d0 == d1;
         const int dhi = max(d0, d1), dlo = min(d0, d1);            // get_all_moves.py:30
-        if (!dbl) clear_hash(); else __syncwarp();                 // non-doubles: one set for full_moves of both passes
-        int pbase = kRoot, np = 1;
-        int nF = 0, nA1 = 0;                                       // non-doubles: plays collected in region 0
-        bool lenA2 = false, lenB2 = false;
-        for (int stage = 0; stage < 4; ++stage) {
-            // doubles (handle_moves.py:203-310): stage k expands level k -> k+1, regions alternate.
-            // non-doubles (handle_moves.py:109-200): stages 0,1 = larger die first; 2,3 = smaller die first.
-            const int d = dbl ? d0 : ((stage == 0 || stage == 3) ? dhi : dlo);
-            const int total = count_moves(pbase, np, d);
-            const bool first = !dbl && (stage & 1) == 0;           // first sub-move of a non-doubles pass
-            int cbase = 0, nc0 = 0;
-            bool use_set = true, do_expand = true;
+        int pbase, np, split, dA, dB, nstages;
+        int nA = 0;
+        if (!dbl) {
+            uint32_t mA, mB; int sA, sB;
+            one_die(root, R, dhi, mA, sA);
+            one_die(root, R, dlo, mB, sB);
+            nA = __popc(mA) + (sA >= 0);
+            const int nB = __popc(mB) + (sB >= 0);
+            if (lane < nA) store(CAP + lane, apply_move(root, R, dhi, mA, sA, lane));
+            else if (lane < nA + nB) store(CAP + lane, apply_move(root, R, dlo, mB, sB, lane - nA));
+            clear_hash();                                          // (also orders the stores above)
+            if (nA + nB == 0) return;
+            pbase = CAP; np = nA + nB; split = nA; dA = dlo; dB = dhi; nstages = 1;
+        } else {
+            if (lane == 0) store(kRoot, root);
+            __syncwarp();
+            pbase = kRoot; np = 1; split = 0x7FFFFFFF; dA = dB = d0; nstages = 4;
+        }
+        for (int stage = 0; stage < nstages; ++stage) {
+            const int total = count_moves(pbase, np, split, dA, dB);
+            int cbase = 0, cfrom = 0, cto = total, nc0 = 0;
+            bool do_expand = true;
+            int nA1 = 0;
+            bool lenB2_only = false;
             if (dbl) {
+                // doubles (handle_moves.py:203-310): stage k expands level k -> k+1, regions alternate
                 if (total == 0) break;                             // dead end: the previous level is the answer
                 cbase = (stage & 1) ? CAP : 0;
                 clear_hash();
-            } else if (first) {
-                if (total == 0) { ++stage; continue; }             // no first move in this order: pass adds nothing
-                cbase = CAP; use_set = false;                      // distinct sources => distinct boards, no set
-            } else if (total > 0) {                                // two_move_sequences_exist, :145-155
-                nc0 = nF;
-                if (stage == 1) lenA2 = true; else lenB2 = true;
             } else {
-                do_expand = false;
-                if (stage == 1 || !lenA2) {                        // singles are the plays, :192-200
-                    Node c = load(CAP + (lane < np ? lane : 0));
-                    bool keep = lane < np && !in_set(key_of(c));
-                    nF = append(0, nF, keep, c, true);
-                    if (stage == 1) {
-                        nA1 = np;
-                        if (np == 1) { n = 1; return; }            // skip-reverse shortcut, get_all_moves.py:43-45
+                const int tA = (int)S.off[nA];                     // two-move candidates of the larger-die-first pass
+                const int tB = total - tA;
+                if (tA > 0) {                                      // two_move_sequences_exist (:145-155) in pass A
+                    if (tB == 0) cto = tA;                         // pass-B singles vanish in the max filter
+                } else {
+                    // pass A has only singles (:192-200): they are the first plays, in order
+                    Node c = load(CAP + (lane < nA ? lane : 0));
+                    nc0 = append(0, 0, lane < nA, c, true);
+                    if (nA == 1) { n = 1; return; }                // skip-reverse shortcut, get_all_moves.py:43-45
+                    nA1 = nA;
+                    if (tB > 0) lenB2_only = true;                 // length-1 plays of pass A are dropped by the filter
+                    else {                                         // only singles anywhere: union (add_unique_board)
+                        do_expand = false;
+                        const int nB = np - nA;
+                        Node c2 = load(CAP + nA + (lane < nB ? lane : 0));
+                        bool keep = lane < nB && !in_set(key_of(c2));
+                        nc0 = append(0, nc0, keep, c2, true);
                     }
                 }
-                // (singles of the smaller-die-first pass next to length-2 plays of the first pass are removed by the
-                //  max filter and, being last, influence nobody's dedupe: not materialised.)
+                cfrom = tA > 0 ? 0 : tA;                           // (= 0 either way: A parents own no candidates if tA == 0)
             }
             int nc = nc0;
-            if (do_expand) nc = expand(pbase, np, d, total, cbase, nc0, use_set);      // the only call site
+            if (do_expand) nc = expand(pbase, np, split, dA, dB, cfrom, cto, cbase, nc0, true);   // the only call site
             if (overflow) return;
             if (dbl) { pbase = cbase; np = nc; obase = cbase; n = nc; }
-            else if (first) { pbase = CAP; np = nc; }
-            else { if (do_expand) nF = nc; pbase = kRoot; np = 1; }
-        }
-        if (!dbl) {
-            // filter_full_moves_by_max_submoves (get_all_moves.py:73-94), applied AFTER dedupe
-            if (lenB2 && !lenA2) { obase = nA1; n = nF - nA1; }    // length-1 plays of the first pass are dropped
-            else { obase = 0; n = nF; }
+            else {
+                // filter_full_moves_by_max_submoves (get_all_moves.py:73-94), applied AFTER dedupe
+                if (lenB2_only) { obase = nA1; n = nc - nA1; } else { obase = 0; n = nc; }
+            }
         }
     }
 };
