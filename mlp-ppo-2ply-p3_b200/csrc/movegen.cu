@@ -249,7 +249,9 @@ struct Warp {
 };
 
 // mode: 0 = count only; 1 = write rows at offsets[b]; 2 = slab (atomicAdd on *alloc, writes starts[b])
-template <int CAP, int HS>
+// FEATS: also write the bf16 feature row of every afterstate (optional fused K3; a separate instantiation so that
+// the common one stays inside the instruction cache)
+template <int CAP, int HS, bool FEATS>
 __global__ void __launch_bounds__(256) movegen_kernel(
     const int8_t* __restrict__ boards, const int8_t* __restrict__ players, const int8_t* __restrict__ dice,
     long long B, const unsigned int* __restrict__ nwork_dev, const int32_t* __restrict__ worklist,
@@ -262,8 +264,7 @@ __global__ void __launch_bounds__(256) movegen_kernel(
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpScratch<CAP, HS>& S = reinterpret_cast<WarpScratch<CAP, HS>*>(smem_raw)[warp];
     __shared__ uint32_t s_lut[32], s_desc[32];          // K3's chunk tables, for the fused feature output
-    load_chunk_tables(s_lut, s_desc);
-    __syncthreads();
+    if (FEATS) { load_chunk_tables(s_lut, s_desc); __syncthreads(); }
     const long long nwork = nwork_dev ? (long long)*nwork_dev : B;
 
     for (;;) {
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(256) movegen_kernel(
                     int rows = min(32, nw - r0);
                     for (int k2 = lane; k2 < rows * kBoardWords; k2 += 32) gout[(long long)r0 * kBoardWords + k2] = stage[k2];
                     if (row_players && lane < rows) row_players[start + r0 + lane] = (int8_t)player;
-                    if (row_feats) {
+                    if (FEATS && row_feats) {
                         // fused K3: the 208-wide bf16 feature rows of these afterstates (mover's turn flag,
                         // ai/batching.py:72-74), 16 bytes per lane, contiguous in global memory
                         uint4* fdst = reinterpret_cast<uint4*>(row_feats + (start + r0) * (long long)BG_FEAT_LD_BF16);
@@ -412,7 +413,7 @@ static int launch_movegen(const int8_t* boards, const int8_t* players, const int
                           int32_t* status, unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr,
                           long long grid_hint, cudaStream_t stream) {
     size_t smem = sizeof(WarpScratch<CAP, HS>) * WARPS;
-    auto kern = movegen_kernel<CAP, HS>;
+    auto kern = row_feats ? movegen_kernel<CAP, HS, true> : movegen_kernel<CAP, HS, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return bg_set_error(e, "movegen: cudaFuncSetAttribute");
     int occ = 1;
