@@ -171,12 +171,10 @@ def run_engine(args):
     def one_step(t, ev=None):
         env.random_actions(ACT_SEED, t, out=acts); launches[0] += 1
         env._apply_actions(acts); launches[0] += 1
-        if ev is not None:
-            ev[0].record()
-        env._refresh_legal_moves(); launches[0] += 3          # K1 tiers 0/1/2
-        if ev is not None:
-            ev[1].record()
-        env.encode_resident(obs=True, afterstates=feats); launches[0] += 1 + int(feats)
+        # K1 tiers 0/1/2 + K3 (observations f32, afterstate features bf16: rows final after tier 0 are encoded on
+        # a second stream beside tiers 1/2, the rest after them) in one C call
+        env.update_legal_plays(obs=True, features=feats, overlap=not args.no_overlap, k1_events=ev)
+        launches[0] += 3 + 1 + 2 * int(feats)
         rows_acc.add_(env.alloc_rows)
 
     t = 0
@@ -187,6 +185,8 @@ def run_engine(args):
     launches[0] = 0
     K = args.steps
     k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for a, b in k1_events:                                    # create the handles (torch creates them on first record)
+        a.record(); b.record()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local)
     if rank == 0:
@@ -227,9 +227,7 @@ def run_engine(args):
         h_counts.copy_(env.legal_counts)                                        # D2H (synchronous: pinned target)
         np.multiply(u[k], h_counts.numpy(), out=u[k])
         h_acts.numpy()[:] = u[k].astype(np.int32)
-        obs, rew, done, infos = env.step(h_acts)                                # H2D inside; obs stays on the device
-        if feats:
-            env.encode_resident(obs=False, afterstates=True)
+        obs, rew, done, infos = env.step(h_acts, with_features=feats)           # H2D inside; obs stays on the device
         h_rew.copy_(rew); h_done.copy_(done)                                    # D2H
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -364,6 +362,7 @@ def main():
     ap.add_argument("--no-afterstate-features", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run the encoders after K1 on the same stream")
     ap.add_argument("--twoply-roots", type=int, default=4096)
     ap.add_argument("--twoply-chunk", type=int, default=32768)
     args = ap.parse_args()

@@ -142,6 +142,22 @@ int bg_env_step(const bg_env_state* st, const int32_t* actions, const bg_step_ou
 int bg_random_actions(const int32_t* counts, long long N, unsigned long long seed, unsigned long long stream_base,
                       uint32_t t, int32_t* actions, void* stream);
 
+/* update_legal_moves + get_observation of N games in ONE call (environment/backgammon_env.py:193-243):
+ * bg_movegen_slab, then bg_encode_bf16 of every legal play (features_bf16, nullable; rows as in afterstates52,
+ * turn flag = the mover) and bg_encode_f32 of the current positions (observations_f32, nullable; flag = player to
+ * move).  With side_stream != NULL (a second stream of the caller) the encoders run on it beside K1's latency-
+ * bound overflow tiers: fork and join are done with events inside the call, so for the caller everything is still
+ * ordered on `stream`.  side_stream == NULL: serial on `stream`.  row_players and counts are required.
+ * k1_begin_event / k1_end_event (nullable cudaEvent_t): recorded on `stream` around K1's launches, for timing K1
+ * inside a fused step (bench.py's roofline). */
+int bg_update_legal_plays(const int8_t* boards52, const int8_t* players, const int8_t* dice, long long N,
+                          int max_rows_per_board, int8_t* afterstates52, long long afterstate_capacity_rows,
+                          int8_t* row_players, int32_t* counts_true /*nullable*/, int32_t* counts, long long* starts,
+                          unsigned long long* alloc_rows, int32_t* status, void* workspace, size_t workspace_bytes,
+                          uint16_t* features_bf16 /*nullable*/, long long features_ld, float* observations_f32 /*nullable*/,
+                          long long observations_ld, void* k1_begin_event /*nullable*/, void* k1_end_event /*nullable*/,
+                          void* side_stream /*nullable*/, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K4  MLP leaf evaluator: value head of BackgammonPolicyNetwork.forward (agent/policy_network.py:58-75)
  * v = w_v . relu(W1 x + b1) + b_v, fused with the feature encoding: input is board52 + flag, the

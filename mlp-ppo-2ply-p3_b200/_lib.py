@@ -43,6 +43,7 @@ SIGNATURES = {
     "bg_movegen_slab": (_I, [_V, _V, _V, _LL, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     "bg_encode_f32": (_I, [_V, _V, _I, _LL, _V, _V, _LL, _V]),
     "bg_encode_bf16": (_I, [_V, _V, _I, _LL, _V, _V, _LL, _V]),
+    "bg_update_legal_plays": (_I, [_V, _V, _V, _LL, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _V, _SZ, _V, _LL, _V, _LL, _V, _V, _V, _V]),
     "bg_env_reset": (_I, [C.POINTER(EnvState), _V, _V, _V]),
     "bg_env_step": (_I, [C.POINTER(EnvState), _V, C.POINTER(StepOut), _V, _V]),
     "bg_random_actions": (_I, [_V, _LL, _U64, _U64, _U32, _V, _V]),

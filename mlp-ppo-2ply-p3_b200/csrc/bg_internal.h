@@ -17,18 +17,31 @@ int bg_set_error_msg(int code, const char* msg);
 int bg_sm_count();
 
 namespace bg {
+// Optional fork point of movegen_run in slab mode: after tier 0 has been launched, *rows_after_tier0 (device) receives
+// the rows allocated so far and fn(user) is called on the host so the caller can enqueue consumers of those rows.
+struct MovegenTier0Hook {
+    unsigned long long* rows_after_tier0;
+    int (*fn)(void* user);
+    void* user;
+};
 // B work items; replicate == 21: item g = (position g/21, sorted roll g%21), player = players[g/21] ^ flip_player
 int movegen_run(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B, int replicate,
                 int flip_player, int mode,
                 const long long* offsets, int max_rows, int8_t* after, long long after_cap_rows,
                 int8_t* row_players, uint16_t* row_feats, int32_t* counts_true, int32_t* counts, long long* starts, unsigned long long* alloc,
-                int32_t* status, void* workspace, size_t ws_bytes, cudaStream_t stream);
+                int32_t* status, void* workspace, size_t ws_bytes, cudaStream_t stream,
+                const MovegenTier0Hook* hook = nullptr);
+// K3 launchers (encode.cu); rows [*row_begin_dev (0 if null), min(B, *n_rows_dev)) are encoded
+int encode_bf16_launch(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
+                       const unsigned long long* row_begin_dev, const unsigned long long* n_rows_dev, uint16_t* out,
+                       long long ld, cudaStream_t stream);
 // overflow tiers (movegen_team.cu): one CTA per position of worklist[0 .. *nwork_dev)
 int movegen_team_mid(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
                      const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
                      int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, uint16_t* row_feats, int32_t* counts_true,
                      int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
-                     unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr, cudaStream_t stream);
+                     unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr, cudaStream_t stream,
+                     int team_threads_hint = 0);
 int movegen_team_big(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
                      const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
                      int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, uint16_t* row_feats, int32_t* counts_true,

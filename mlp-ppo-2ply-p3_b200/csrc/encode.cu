@@ -43,32 +43,74 @@ __device__ __forceinline__ void stage_boards(const int8_t* __restrict__ boards, 
 // bf16 rows: one thread per 16-byte output chunk (8 features), driven by a per-chunk descriptor so that every lane
 // runs the same code: byte w of kChunkDesc[k] describes word w (2 features) of chunk k: bit 7 clear -> bits 0..5 =
 // board52 byte of the point, bit 6 = which half of its 4 units; bit 7 set -> 0 zero, 1 bar1/off1, 2 bar2/off2, 3 flags.
-// A warp's 32 chunks are contiguous in global memory (rows are contiguous), so the stores are full 512-byte runs.
+// A staged row is 16 words: the 13 board words, then the row's three "special" words (bar1/off1, bar2/off2, turn
+// flags) precomputed once per row, so that a special word is one more table address and not a divergent branch with
+// constant-memory lookups.  Every output word is then two dependent shared-memory loads (count byte -> units word)
+// with a select on the address.  A warp's 32 chunks are contiguous in global memory (rows are contiguous), so the
+// stores are full 512-byte runs; each thread builds kBfUnroll chunks before storing them (stores in flight).
 constexpr int kBfRows = 128;
+constexpr int kBfRowWords = 16;
+constexpr int kBfUnroll = 4;
+
+__device__ __forceinline__ uint4 chunk_staged(const uint32_t* __restrict__ srow, uint32_t desc, const uint32_t* __restrict__ s_lut) {
+    // s_lut[0] == 0 (units of an empty point): the "zero" special word reads it
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(srow);
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t d = (desc >> (8 * q)) & 0xFFu;
+        const uint32_t cnt = b[d & 63u] & 15u;                               // (any byte for a special word)
+        const uint32_t* lut_addr = s_lut + ((cnt << 1) | ((d >> 6) & 1u));
+        const uint32_t* sp_addr = (d & 3u) ? srow + 12 + (d & 3u) : s_lut;   // words 13, 14, 15 of the staged row
+        w[q] = *((d & 0x80u) ? sp_addr : lut_addr);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
 
 __global__ void __launch_bounds__(kEncThreads) encode_bf16_kernel(const int8_t* __restrict__ boards,
                                                                   const int8_t* __restrict__ flags, int flag_all,
-                                                                  long long B, const unsigned long long* __restrict__ n_rows_dev,
+                                                                  long long B, const unsigned long long* __restrict__ row_begin_dev,
+                                                                  const unsigned long long* __restrict__ n_rows_dev,
                                                                   uint16_t* __restrict__ out, int cpr /* ld/8 */) {
-    __shared__ __align__(16) uint32_t sm[kBfRows * kBoardWords];
-    __shared__ int8_t sflag[kBfRows];
+    __shared__ __align__(16) uint32_t sm[kBfRows * kBfRowWords];
     __shared__ uint32_t s_lut[32], s_desc[32];
     load_chunk_tables(s_lut, s_desc);
     if (n_rows_dev) B = min(B, (long long)*n_rows_dev);
-    for (long long row0 = (long long)blockIdx.x * kBfRows; row0 < B; row0 += (long long)gridDim.x * kBfRows) {
+    const long long begin = row_begin_dev ? (long long)*row_begin_dev : 0;
+    for (long long row0 = begin + (long long)blockIdx.x * kBfRows; row0 < B; row0 += (long long)gridDim.x * kBfRows) {
         const int rows = (int)min((long long)kBfRows, B - row0);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
-        for (int i = threadIdx.x; i < rows * kBoardWords; i += kEncThreads) sm[i] = __ldg(src + i);
-        for (int i = threadIdx.x; i < rows; i += kEncThreads) sflag[i] = flags ? (flags[row0 + i] & 1) : (int8_t)flag_all;
+        for (int i = threadIdx.x; i < rows * kBoardWords; i += kEncThreads) {
+            const int r = i / kBoardWords;
+            sm[r * kBfRowWords + (i - r * kBoardWords)] = __ldg(src + i);
+        }
+        __syncthreads();
+        if (threadIdx.x < rows) {                                            // the row's special words
+            const int r = threadIdx.x;
+            const uint32_t misc = sm[r * kBfRowWords + 12];
+            const int flag = flags ? (flags[row0 + r] & 1) : flag_all;
+            sm[r * kBfRowWords + 13] = bar_off_pair_bf16((int)(misc & 0xFFu), (int)((misc >> 16) & 0xFFu));
+            sm[r * kBfRowWords + 14] = bar_off_pair_bf16((int)((misc >> 8) & 0xFFu), (int)(misc >> 24));
+            sm[r * kBfRowWords + 15] = flag == 0 ? 0x00003F80u : 0x3F800000u;
+        }
         __syncthreads();
         uint4* dst = reinterpret_cast<uint4*>(out + row0 * (long long)cpr * 8);
         const int total = rows * cpr;
-        for (int c = threadIdx.x; c < total; c += kEncThreads) {
-            const int r = cpr == 26 ? c / 26 : c / cpr;
-            const int k = c - r * cpr;
-            const uint32_t desc = k < 26 ? s_desc[k] : 0x80808080u;
-            const uint8_t* b = reinterpret_cast<const uint8_t*>(sm) + r * kBoardBytes;
-            dst[c] = chunk_from_desc(b, sflag[r], desc, s_lut);
+        for (int c0 = threadIdx.x; c0 < total; c0 += kEncThreads * kBfUnroll) {
+            uint4 v[kBfUnroll];
+#pragma unroll
+            for (int u = 0; u < kBfUnroll; ++u) {
+                const int c = c0 + u * kEncThreads;
+                const int cc = c < total ? c : c0;
+                const int r = cpr == 26 ? cc / 26 : cc / cpr;
+                const int k = cc - r * cpr;
+                v[u] = chunk_staged(sm + r * kBfRowWords, k < 26 ? s_desc[k] : 0x80808080u, s_lut);
+            }
+#pragma unroll
+            for (int u = 0; u < kBfUnroll; ++u) {
+                const int c = c0 + u * kEncThreads;
+                if (c < total) dst[c] = v[u];
+            }
         }
         __syncthreads();
     }
@@ -115,8 +157,9 @@ extern "C" int bg_encode_f32(const int8_t* boards52, const int8_t* flags, int fl
     return bg_set_error(cudaGetLastError(), "bg_encode_f32: launch");
 }
 
-extern "C" int bg_encode_bf16(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
-                              const unsigned long long* n_rows_dev, uint16_t* out, long long ld, void* stream) {
+int bg::encode_bf16_launch(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
+                           const unsigned long long* row_begin_dev, const unsigned long long* n_rows_dev, uint16_t* out,
+                           long long ld, cudaStream_t stream) {
     if (B < 0 || ld < 200 || (ld & 7) || ld > 1024) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: bad B or ld (need ld >= 200, multiple of 8)");
     if (B == 0) return BG_OK;
     if (!boards52 || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: null pointer");
@@ -124,6 +167,11 @@ extern "C" int bg_encode_bf16(const int8_t* boards52, const int8_t* flags, int f
     long long tiles = (B + kBfRows - 1) / kBfRows;
     long long grid = (long long)bg_sm_count() * 8;
     if (grid > tiles) grid = tiles;
-    encode_bf16_kernel<<<(unsigned)grid, kEncThreads, 0, (cudaStream_t)stream>>>(boards52, flags, flag_all & 1, B, n_rows_dev, out, cpr);
+    encode_bf16_kernel<<<(unsigned)grid, kEncThreads, 0, stream>>>(boards52, flags, flag_all & 1, B, row_begin_dev, n_rows_dev, out, cpr);
     return bg_set_error(cudaGetLastError(), "bg_encode_bf16: launch");
+}
+
+extern "C" int bg_encode_bf16(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
+                              const unsigned long long* n_rows_dev, uint16_t* out, long long ld, void* stream) {
+    return bg::encode_bf16_launch(boards52, flags, flag_all, B, nullptr, n_rows_dev, out, ld, (cudaStream_t)stream);
 }

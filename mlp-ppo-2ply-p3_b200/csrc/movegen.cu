@@ -142,8 +142,10 @@ struct Warp {
     // Children of the parents at [pbase, pbase+np) (parent i plays die i < split ? dA : dB), candidates
     // [cfrom, total) of the count_moves numbering, in the reference's order, appended to the region at cbase
     // (nc entries so far).  use_set: drop children equal to an entry of the set or to an earlier child.
+    // use_hash: also consult / feed the hash set (needed only when the stage has more than one chunk of candidates
+    // or entries appended before it; a single chunk is deduped by match_any alone).
     __device__ __forceinline__ int expand(int pbase, int np, int split, int dA, int dB, int cfrom, int total, int cbase,
-                                          int nc, bool use_set) {
+                                          int nc, bool use_set, bool use_hash) {
         for (int c0 = cfrom; c0 < total && !overflow; c0 += 32) {
             int idx = c0 + lane;
             bool valid = idx < total;
@@ -166,9 +168,9 @@ struct Warp {
                 unsigned m = __match_any_sync(kFull, ch.lo) &
                              __match_any_sync(kFull, (unsigned long long)k.z | ((unsigned long long)k.w << 32));
                 keep = valid && (__ffs(m) - 1 == lane);
-                if (keep && in_set(k)) keep = false;
+                if (use_hash && keep && in_set(k)) keep = false;
             }
-            nc = append(cbase, nc, keep, ch, use_set);
+            nc = append(cbase, nc, keep, ch, use_hash);
         }
         return nc;
     }
@@ -195,7 +197,7 @@ struct Warp {
             const int nB = __popc(mB) + (sB >= 0);
             if (lane < nA) store(CAP + lane, apply_move(root, R, dhi, mA, sA, lane));
             else if (lane < nA + nB) store(CAP + lane, apply_move(root, R, dlo, mB, sB, lane - nA));
-            clear_hash();                                          // (also orders the stores above)
+            __syncwarp();
             if (nA + nB == 0) return;
             pbase = CAP; np = nA + nB; split = nA; dA = dlo; dB = dhi; nstages = 1;
         } else {
@@ -206,21 +208,27 @@ struct Warp {
         for (int stage = 0; stage < nstages; ++stage) {
             const int total = count_moves(pbase, np, split, dA, dB);
             int cbase = 0, cfrom = 0, cto = total, nc0 = 0;
-            bool do_expand = true;
+            bool do_expand = true, use_hash = true;
             int nA1 = 0;
             bool lenB2_only = false;
             if (dbl) {
                 // doubles (handle_moves.py:203-310): stage k expands level k -> k+1, regions alternate
                 if (total == 0) break;                             // dead end: the previous level is the answer
                 cbase = (stage & 1) ? CAP : 0;
-                clear_hash();
+                use_hash = total > 32;                             // one chunk: match_any alone dedupes it
+                if (use_hash) clear_hash();
             } else {
                 const int tA = (int)S.off[nA];                     // two-move candidates of the larger-die-first pass
                 const int tB = total - tA;
                 if (tA > 0) {                                      // two_move_sequences_exist (:145-155) in pass A
                     if (tB == 0) cto = tA;                         // pass-B singles vanish in the max filter
+                    use_hash = cto > 32;
+                    if (use_hash) clear_hash();
                 } else {
-                    // pass A has only singles (:192-200): they are the first plays, in order
+                    // pass A has only singles (:192-200): they are the first plays, in order.  (They stay in the
+                    // set while pass B's two-move boards are added, as in add_unique_board; a one-move board can
+                    // never equal a two-move board, but the dedupe is kept literal.)
+                    clear_hash();
                     Node c = load(CAP + (lane < nA ? lane : 0));
                     nc0 = append(0, 0, lane < nA, c, true);
                     if (nA == 1) { n = 1; return; }                // skip-reverse shortcut, get_all_moves.py:43-45
@@ -237,7 +245,7 @@ struct Warp {
                 cfrom = tA > 0 ? 0 : tA;                           // (= 0 either way: A parents own no candidates if tA == 0)
             }
             int nc = nc0;
-            if (do_expand) nc = expand(pbase, np, split, dA, dB, cfrom, cto, cbase, nc0, true);   // the only call site
+            if (do_expand) nc = expand(pbase, np, split, dA, dB, cfrom, cto, cbase, nc0, true, use_hash);   // the only call site
             if (overflow) return;
             if (dbl) { pbase = cbase; np = nc; obase = cbase; n = nc; }
             else {
@@ -440,7 +448,8 @@ int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* d
                     int flip_player, int mode,
                     const long long* offsets, int max_rows, int8_t* after, long long after_cap_rows,
                     int8_t* row_players, uint16_t* row_feats, int32_t* counts_true, int32_t* counts, long long* starts,
-                    unsigned long long* alloc, int32_t* status, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+                    unsigned long long* alloc, int32_t* status, void* workspace, size_t ws_bytes, cudaStream_t stream,
+                    const MovegenTier0Hook* hook) {
     if (B < 0) return bg_set_error_msg(BG_ERR_INVALID, "movegen: negative batch");
     if (B == 0) return BG_OK;
     if (replicate < 1) replicate = 1;
@@ -463,14 +472,22 @@ int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* d
         after_cap_rows, row_players, row_feats, counts_true, counts, starts, alloc, status, ctr + 0, list_a, ctr + 1,
         (B + 7) / 8, stream);
     if (rc != BG_OK) return rc;
-    // Tier 1: the (~1 %) positions whose levels did not fit: one 4-warp CTA per position (movegen_team.cu),
+    // Slab mode: rows [0, *alloc) are final once tier 0 is done (tiers 1/2 only append).  A caller that wants to
+    // consume them while the latency-bound overflow tiers run gets the row count snapshot and a fork point here.
+    if (hook && mode == 2) {
+        e = cudaMemcpyAsync(hook->rows_after_tier0, alloc, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream);
+        if (e != cudaSuccess) return bg_set_error(e, "movegen: snapshot");
+        rc = hook->fn(hook->user);
+        if (rc != BG_OK) return rc;
+    }
+    // Tier 1: the (~1 %) positions whose levels did not fit: one CTA per position (movegen_team.cu),
     // BG_MOVEGEN_CAP_MID boards per level.  Work counts of tiers 1 and 2 are read from device memory, so no host
     // synchronisation is needed.
     rc = movegen_team_mid(boards, players, dice, ctr + 1, list_a, replicate, flip_player, mode, offsets, max_rows, after,
                           after_cap_rows, row_players, row_feats, counts_true, counts, starts, alloc, status, ctr + 2, list_b,
-                          ctr + 3, stream);
+                          ctr + 3, stream, (hook && mode == 2) ? 128 : 0);
     if (rc != BG_OK) return rc;
-    // Tier 2: the rest (> BG_MOVEGEN_CAP_MID boards in a level): one 16-warp CTA per position, BG_MOVEGEN_CAP_BIG
+    // Tier 2: the rest (> BG_MOVEGEN_CAP_MID boards in a level): one big CTA per position, BG_MOVEGEN_CAP_BIG
     // boards per level.  Positions that do not fit even this raise BG_STATUS_SCRATCH_OVERFLOW (never dropped silently).
     return movegen_team_big(boards, players, dice, ctr + 3, list_b, replicate, flip_player, mode, offsets, max_rows, after,
                             after_cap_rows, row_players, row_feats, counts_true, counts, starts, alloc, status, ctr + 4, stream);

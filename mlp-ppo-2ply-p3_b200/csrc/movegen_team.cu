@@ -11,6 +11,7 @@
 // EQUAL key is taken over with atomicMin (lowest candidate index wins), a committed entry with an equal key kills
 // the candidate.  After a barrier a candidate survives iff its slot still names it; survivors are compacted in
 // candidate order (ballot + per-warp counts) and commit their slots to list indices.
+#include <cstdlib>
 #include "bg_device.cuh"
 #include "bg_features.cuh"
 #include "bg_internal.h"
@@ -41,7 +42,9 @@ struct TeamScratch {
 
 template <int CAP, int HS, int T>
 struct Team {
-    static_assert(CAP * 16 >= T * kBoardWords * 4, "a region must be able to stage T output rows");
+    // output rows staged per iteration: what one region (CAP keys of 16 B) can hold, at most one per thread
+    static constexpr int kStageRows = (CAP * 16 / kBoardBytes) / 32 * 32 < T ? (CAP * 16 / kBoardBytes) / 32 * 32 : T;
+    static_assert(kStageRows >= 32, "a region must be able to stage at least 32 output rows");
     static constexpr int kRoot = 2 * CAP;
     static constexpr int kWarps = T / 32;
     TeamScratch<CAP, HS, T>& S;
@@ -341,9 +344,10 @@ __global__ void __launch_bounds__(T) movegen_team_kernel(
                 const int own0 = player ? 6 : 0, opp0 = player ? 0 : 6;
                 const uint32_t misc0 = S.rootw[12];
                 const uint32_t opp_bar0 = (misc0 >> (player ? 0 : 8)) & 0xFFu, opp_off0 = (misc0 >> (player ? 16 : 24)) & 0xFFu;
-                for (int r0 = 0; r0 < nw; r0 += T) {
+                constexpr int SR = Team<CAP, HS, T>::kStageRows;
+                for (int r0 = 0; r0 < nw; r0 += SR) {
                     int r = r0 + tid;
-                    if (r < nw) {
+                    if (tid < SR && r < nw) {
                         const uint4 k = S.key[obase + r];
                         uint32_t* row = stage + tid * kBoardWords;
                         row[own0 + 0] = spread_nibbles(k.x);       row[own0 + 1] = spread_nibbles(k.x >> 16);
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(T) movegen_team_kernel(
                                               : (pb | (ob << 8) | (opp_off0 << 16) | (oo << 24));
                     }
                     __syncthreads();
-                    int rows = min(T, nw - r0);
+                    int rows = min(SR, nw - r0);
                     for (int k2 = tid; k2 < rows * kBoardWords; k2 += T) gout[(long long)r0 * kBoardWords + k2] = stage[k2];
                     if (row_players && tid < rows) row_players[start + r0 + tid] = (int8_t)player;
                     if (row_feats) {                          // fused K3 (see movegen.cu)
@@ -376,6 +380,12 @@ __global__ void __launch_bounds__(T) movegen_team_kernel(
     }
 }
 }  // namespace
+
+// team size override for tuning runs (threads per position); the defaults are the measured best
+static int team_size_env(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
 
 template <int CAP, int HS, int T>
 static int launch_team(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
@@ -403,10 +413,19 @@ int movegen_team_mid(const int8_t* boards, const int8_t* players, const int8_t* 
                      int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, uint16_t* row_feats,
                        int32_t* counts_true,
                      int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
-                     unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr, cudaStream_t stream) {
-    return launch_team<BG_MOVEGEN_CAP_MID, 2 * BG_MOVEGEN_CAP_MID, 128>(
-        boards, players, dice, nwork_dev, worklist, replicate, flip_player, mode, offsets, max_rows, after, after_cap_rows,
-        row_players, row_feats, counts_true, counts, starts, alloc, status, work_ctr, overflow_list, overflow_ctr, stream);
+                     unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr, cudaStream_t stream,
+                     int team_threads_hint) {
+#define BG_TEAM_MID(T) launch_team<BG_MOVEGEN_CAP_MID, 2 * BG_MOVEGEN_CAP_MID, T>( \
+        boards, players, dice, nwork_dev, worklist, replicate, flip_player, mode, offsets, max_rows, after, after_cap_rows, \
+        row_players, row_feats, counts_true, counts, starts, alloc, status, work_ctr, overflow_list, overflow_ctr, stream)
+    // 256 threads per position is the fastest alone; when an encoder runs beside the tiers (bg_update_legal_plays)
+    // 128 leaves it more of the SMs' thread slots and the pair finishes sooner
+    static const int t1_env = team_size_env("BG_TEAM_MID", 0);
+    const int t1 = t1_env ? t1_env : (team_threads_hint ? team_threads_hint : 256);
+    if (t1 == 128) return BG_TEAM_MID(128);
+    if (t1 == 512) return BG_TEAM_MID(512);
+    return BG_TEAM_MID(256);
+#undef BG_TEAM_MID
 }
 int movegen_team_big(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
                      const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
@@ -414,9 +433,13 @@ int movegen_team_big(const int8_t* boards, const int8_t* players, const int8_t* 
                        int32_t* counts_true,
                      int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
                      unsigned int* work_ctr, cudaStream_t stream) {
-    return launch_team<BG_MOVEGEN_CAP_BIG, BG_MOVEGEN_HASH_BIG, 512>(
-        boards, players, dice, nwork_dev, worklist, replicate, flip_player, mode, offsets, max_rows, after, after_cap_rows,
-        row_players, row_feats, counts_true, counts, starts, alloc, status, work_ctr, nullptr, nullptr, stream);
+#define BG_TEAM_BIG(T) launch_team<BG_MOVEGEN_CAP_BIG, BG_MOVEGEN_HASH_BIG, T>( \
+        boards, players, dice, nwork_dev, worklist, replicate, flip_player, mode, offsets, max_rows, after, after_cap_rows, \
+        row_players, row_feats, counts_true, counts, starts, alloc, status, work_ctr, nullptr, nullptr, stream)
+    static const int t2 = team_size_env("BG_TEAM_BIG", 512);
+    if (t2 == 1024) return BG_TEAM_BIG(1024);
+    return BG_TEAM_BIG(512);
+#undef BG_TEAM_BIG
 }
 
 }  // namespace bg

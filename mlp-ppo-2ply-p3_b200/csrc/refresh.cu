@@ -1,0 +1,112 @@
+// refresh.cu -- update_legal_moves + get_observation for a whole batch in one call, with the encoders overlapped
+// with K1's overflow tiers.
+//
+// Replaces BackgammonEnv.update_legal_moves (src/environment/backgammon_env.py:198-243: get_all_possible_moves +
+// generate_all_board_features) and get_observation (:193-196) for N games.  K1's tier 0 (all SMs busy, issue
+// bound) produces ~99 % of the rows; tiers 1/2 (the few huge doubles positions, one CTA each) are latency bound
+// and leave the GPU nearly idle, so the HBM-bound encoder of the rows that are already final runs beside them
+// on a second stream:
+//
+//   stream : [K1 tier 0] -> snapshot rows -> [tier 1] -> [tier 2] -> [K3 bf16 rows (snapshot, end)] -> join
+//   side   : [K3 f32 observations] ........ -> [K3 bf16 rows [0, snapshot)] ------------------------^
+#include "bg_device.cuh"
+#include "bg_internal.h"
+
+namespace {
+struct ForkJoin {
+    cudaEvent_t start = nullptr, tier0 = nullptr, side_done = nullptr;
+    int device = -1;
+};
+thread_local ForkJoin g_fj[16];
+
+ForkJoin* fork_join_events() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    ForkJoin& f = g_fj[dev];
+    if (f.device != dev) {
+        if (cudaEventCreateWithFlags(&f.start, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&f.tier0, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&f.side_done, cudaEventDisableTiming) != cudaSuccess)
+            return nullptr;
+        f.device = dev;
+    }
+    return &f;
+}
+
+struct HookCtx {
+    ForkJoin* fj;
+    cudaStream_t stream, side;
+    const int8_t* after52;
+    const int8_t* row_players;
+    long long cap_rows;
+    const unsigned long long* rows_t0;
+    uint16_t* feats;
+    long long ld;
+    int rc;
+};
+
+int after_tier0(void* user) {
+    HookCtx* c = static_cast<HookCtx*>(user);
+    cudaError_t e = cudaEventRecord(c->fj->tier0, c->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->side, c->fj->tier0, 0);
+    if (e != cudaSuccess) return bg_set_error(e, "bg_update_legal_plays: fork");
+    // rows [0, *rows_t0) are final: encode them beside tiers 1/2
+    return bg::encode_bf16_launch(c->after52, c->row_players, 0, c->cap_rows, nullptr, c->rows_t0, c->feats, c->ld, c->side);
+}
+}  // namespace
+
+extern "C" int bg_update_legal_plays(const int8_t* boards52, const int8_t* players, const int8_t* dice, long long N,
+                                     int max_rows_per_board, int8_t* afterstates52, long long afterstate_capacity_rows,
+                                     int8_t* row_players, int32_t* counts_true, int32_t* counts, long long* starts,
+                                     unsigned long long* alloc_rows, int32_t* status, void* workspace,
+                                     size_t workspace_bytes, uint16_t* features_bf16, long long features_ld,
+                                     float* observations_f32, long long observations_ld, void* k1_begin_event,
+                                     void* k1_end_event, void* side_stream, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_, side = (cudaStream_t)side_stream;
+    if (N < 0) return bg_set_error_msg(BG_ERR_INVALID, "bg_update_legal_plays: negative batch");
+    if (N == 0) return BG_OK;
+    if (!counts || !row_players) return bg_set_error_msg(BG_ERR_INVALID, "bg_update_legal_plays: null counts / row_players");
+    if (workspace_bytes < bg_movegen_workspace_bytes(N) || !workspace)
+        return bg_set_error_msg(BG_ERR_INVALID, "bg_update_legal_plays: workspace too small");
+    ForkJoin* fj = (side && side != stream) ? fork_join_events() : nullptr;
+    if (!fj) {                                                     // serial form
+        if (k1_begin_event) cudaEventRecord((cudaEvent_t)k1_begin_event, stream);
+        int rc = bg::movegen_run(boards52, players, dice, N, 1, 0, 2, nullptr, max_rows_per_board, afterstates52,
+                                 afterstate_capacity_rows, row_players, nullptr, counts_true, counts, starts, alloc_rows,
+                                 status, workspace, workspace_bytes, stream);
+        if (k1_end_event) cudaEventRecord((cudaEvent_t)k1_end_event, stream);
+        if (rc != BG_OK) return rc;
+        if (observations_f32) {
+            rc = bg_encode_f32(boards52, players, 0, N, nullptr, observations_f32, observations_ld, stream);
+            if (rc != BG_OK) return rc;
+        }
+        if (features_bf16)
+            rc = bg::encode_bf16_launch(afterstates52, row_players, 0, afterstate_capacity_rows, nullptr, alloc_rows,
+                                        features_bf16, features_ld, stream);
+        return rc;
+    }
+    cudaError_t e = cudaEventRecord(fj->start, stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(side, fj->start, 0);
+    if (e != cudaSuccess) return bg_set_error(e, "bg_update_legal_plays: fork");
+    int rc = BG_OK;
+    if (observations_f32) {
+        rc = bg_encode_f32(boards52, players, 0, N, nullptr, observations_f32, observations_ld, side);
+        if (rc != BG_OK) return rc;
+    }
+    unsigned long long* rows_t0 = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(workspace) + 40);
+    HookCtx ctx{fj, stream, side, afterstates52, row_players, afterstate_capacity_rows, rows_t0, features_bf16, features_ld, BG_OK};
+    bg::MovegenTier0Hook hook{rows_t0, after_tier0, &ctx};
+    if (k1_begin_event) cudaEventRecord((cudaEvent_t)k1_begin_event, stream);
+    rc = bg::movegen_run(boards52, players, dice, N, 1, 0, 2, nullptr, max_rows_per_board, afterstates52,
+                         afterstate_capacity_rows, row_players, nullptr, counts_true, counts, starts, alloc_rows, status,
+                         workspace, workspace_bytes, stream, features_bf16 ? &hook : nullptr);
+    if (k1_end_event) cudaEventRecord((cudaEvent_t)k1_end_event, stream);
+    if (rc == BG_OK && features_bf16)                              // rows appended by tiers 1/2
+        rc = bg::encode_bf16_launch(afterstates52, row_players, 0, afterstate_capacity_rows, rows_t0, alloc_rows,
+                                    features_bf16, features_ld, stream);
+    // join (always, so that `side` never runs ahead of the caller's stream order)
+    e = cudaEventRecord(fj->side_done, side);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, fj->side_done, 0);
+    if (e != cudaSuccess && rc == BG_OK) rc = bg_set_error(e, "bg_update_legal_plays: join");
+    return rc;
+}

@@ -86,6 +86,7 @@ class B200BackgammonVecEnv:
         self._ws_bytes = int(lib().bg_movegen_workspace_bytes(max(N, 1)))
         self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=device)
         self._ext_dice = None
+        self._side = None
         self._steps = 0
         # reference attributes (vec_bg_env.py:16-18); gym is not a dependency, so plain descriptors
         self.observation_space = {"shape": (FEATURES,), "low": -1.0, "high": 1.0, "dtype": "float32"}
@@ -117,6 +118,37 @@ class B200BackgammonVecEnv:
                                     self.alloc_rows.data_ptr(), self.status.data_ptr(), self._ws.data_ptr(),
                                     self._ws_bytes, _stream()), "bg_movegen_slab")
 
+    def update_legal_plays(self, obs: bool = True, features: bool = False, overlap: bool = True, k1_events=None):
+        """update_legal_moves + get_observation (backgammon_env.py:193-243) in one C call (bg_update_legal_plays):
+        K1, then K3 into the persistent buffers self.obs_f32 (N,198) f32 and self.after_feats (cap_rows,208) bf16
+        (rows [0, alloc_rows) valid).  overlap=True runs the encoders on a second stream beside K1's latency-bound
+        overflow tiers (fork/join inside the call; for the caller everything stays ordered on the current stream).
+        k1_events: optional pair of torch.cuda.Event (timing enabled, already recorded once) bracketing K1."""
+        self.alloc_rows.zero_()
+        optr = fptr = None
+        if obs:
+            if not hasattr(self, "obs_f32"):
+                self.obs_f32 = torch.empty((self.num_envs, FEATURES), dtype=torch.float32, device=self.device)
+            optr = self.obs_f32.data_ptr()
+        if features:
+            if not hasattr(self, "after_feats"):
+                self.after_feats = torch.empty((self.cap_rows, LD_BF16), dtype=torch.bfloat16, device=self.device)
+            fptr = self.after_feats.data_ptr()
+        side = None
+        if overlap:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            side = self._side.cuda_stream
+        e0 = k1_events[0].cuda_event if k1_events is not None else None
+        e1 = k1_events[1].cuda_event if k1_events is not None else None
+        check(lib().bg_update_legal_plays(self.boards52.data_ptr(), self.players.data_ptr(), self.dice.data_ptr(),
+                                          self.num_envs, self.max_legal_moves, self.after52.data_ptr(), self.cap_rows,
+                                          self.row_players.data_ptr(), self.legal_counts_true.data_ptr(),
+                                          self.legal_counts.data_ptr(), self.legal_starts.data_ptr(),
+                                          self.alloc_rows.data_ptr(), self.status.data_ptr(), self._ws.data_ptr(),
+                                          self._ws_bytes, fptr, LD_BF16, optr, FEATURES, e0, e1, side, _stream()),
+              "bg_update_legal_plays")
+
     def check_status(self):
         s = int(self.status.item())
         if s:
@@ -134,8 +166,8 @@ class B200BackgammonVecEnv:
         with torch.cuda.device(self.device):
             st = self._state()
             check(lib().bg_env_reset(C.byref(st), None, self.status.data_ptr(), _stream()), "bg_env_reset")
-            self._refresh_legal_moves()
-            obs = self.observations()
+            self.update_legal_plays(obs=True, features=False)
+            obs = self.obs_f32.clone()
         self.check_status()
         return obs
 
@@ -149,8 +181,9 @@ class B200BackgammonVecEnv:
         if actions.shape[0] != self.num_envs:
             raise BgError("step: need one action per env")
         with torch.cuda.device(self.device):
-            self.step_device(actions, with_features)
-            obs = self.observations() if return_obs else None
+            self._apply_actions(actions)
+            self.update_legal_plays(obs=return_obs, features=with_features)
+            obs = self.obs_f32.clone() if return_obs else None          # fresh tensor per call, as the reference returns
         self._steps += 1
         if self.check_every and self._steps % self.check_every == 0:
             self.check_status()

@@ -24,6 +24,8 @@ print(f"games {N}, afterstate rows {rows} ({rows/N:.2f}/game)")
 print(f"K1 movegen_slab (3 tiers)      : {timed(env._refresh_legal_moves):8.1f} us")
 print(f"K1 movegen_slab + fused bf16   : {timed(lambda: env._refresh_legal_moves(with_features=True)):8.1f} us")
 env.encode_resident(True, True)
+print(f"K1+K3 update_legal_plays serial : {timed(lambda: env.update_legal_plays(True, True, overlap=False)):8.1f} us")
+print(f"K1+K3 update_legal_plays overlap: {timed(lambda: env.update_legal_plays(True, True, overlap=True)):8.1f} us")
 from bg_b200.engine import encode
 print(f"K3 encode_bf16 {rows} rows     : {timed(lambda: env.encode_resident(False, True)):8.1f} us   -> {rows*469/ (timed(lambda: env.encode_resident(False, True))*1e-6)/1e12:.2f} TB/s")
 print(f"K3 encode_f32 obs {N} rows      : {timed(lambda: env.encode_resident(True, False)):8.1f} us")
