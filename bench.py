@@ -222,13 +222,16 @@ def run_engine(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    stream = torch.cuda.current_stream()
+    h_counts.copy_(env.legal_counts, non_blocking=True)
     t0 = time.perf_counter()
     for k in range(E):
-        h_counts.copy_(env.legal_counts)                                        # D2H (synchronous: pinned target)
-        np.multiply(u[k], h_counts.numpy(), out=u[k])
-        h_acts.numpy()[:] = u[k].astype(np.int32)
+        stream.synchronize()                                                    # results of the previous step are on the host
+        np.multiply(u[k], h_counts.numpy(), out=u[k])                           # host-side policy: uniform over the legal plays
+        h_acts.numpy()[:] = u[k]                                                # (float -> int32 truncation)
         obs, rew, done, infos = env.step(h_acts, with_features=feats)           # H2D inside; obs stays on the device
-        h_rew.copy_(rew); h_done.copy_(done)                                    # D2H
+        h_rew.copy_(rew, non_blocking=True); h_done.copy_(done, non_blocking=True)      # D2H into pinned memory
+        h_counts.copy_(env.legal_counts, non_blocking=True)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     env.check_status()

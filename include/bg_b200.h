@@ -42,6 +42,7 @@ extern "C" {
 #define BG_BOARD_BYTES 52
 #define BG_HIDDEN 128                 /* agent/config.py HIDDEN_SIZE, agent/policy_network.py:44 */
 #define BG_FEAT_LD_BF16 208           /* 198 padded to a multiple of 16 (one tcgen05 K step) */
+#define BG_ACTIONS 500                /* action slots = max_legal_moves (agent/train.py: action_size=500) */
 
 const char* bg_last_error(void);
 int bg_version(void);
@@ -174,6 +175,28 @@ int bg_mlp_value(const int8_t* boards52, const int8_t* flags, int flag_all, int 
                  const unsigned long long* n_rows_dev /*nullable*/, const uint16_t* w1_bf16,
                  const float* b1 /*[128]*/, const float* wv /*[128]*/, float bv, int terminal_aware,
                  float* values, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * N1  policy/value forward of the PPO rollout: BackgammonPPOAgent.select_action (agent/ppo_agent.py:138-191) =
+ * BackgammonPolicyNetwork.forward (agent/policy_network.py:58-75) + log(mask + 1e-45) + softmax +
+ * Categorical.sample / argmax + log_prob, for B positions given as board52 + turn flag, in one kernel: both
+ * GEMMs (198->128, 128->500) on the tcgen05 tensor cores, logits reduced on chip (never written unless
+ * logits_out != NULL).  The mask is the env's prefix mask: slot k is legal iff k < legal_counts[b]
+ * (environment/backgammon_env.py:228-231); legal_counts == NULL = all 500 legal.  With no legal slot (a pass) the
+ * reference samples from all 500 slots; so does this.
+ *   wa_bf16: [512][128] bf16, row n = action_head.weight[n] (rows 500..511 zero; bg_pack_wa), ba: [500] f32.
+ *   sampling: Gumbel-max with Philox4x32-10 keyed by seed, counter (stream_base + b, step, slot): reproducible
+ *   and independent of the batch split; greedy = 1 takes argmax (lowest slot on ties) like the inference mode.
+ *   outputs: actions [B] i32, log_probs [B] f32 (nullable), values [B] f32 (nullable),
+ *            logits_out [B][500] f32 (nullable; unmasked logits, for parity checks).
+ */
+int bg_pack_wa(const float* action_head_weight /*[500][128] f32*/, uint16_t* wa_bf16 /*[512][128]*/, void* stream);
+int bg_policy_sample(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
+                     const int32_t* legal_counts /*nullable*/, const uint16_t* w1_bf16, const float* b1,
+                     const uint16_t* wa_bf16, const float* ba, const float* wv, float bv, unsigned long long seed,
+                     unsigned long long stream_base, uint32_t step, int greedy, int32_t* actions,
+                     float* log_probs /*nullable*/, float* values /*nullable*/, float* logits_out /*nullable*/,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K5  2-ply search (the reference's own 2-ply, moves/expect_minmax.py:1-206, is

@@ -50,6 +50,8 @@ SIGNATURES = {
     "bg_movegen_replies_slab": (_I, [_V, _V, _LL, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     "bg_twoply_scores": (_I, [_V, _V, _V, _V, _V, _V, _LL, _V, _V]),
     "bg_segment_argmax": (_I, [_V, _V, _V, _LL, _V, _V, _V]),
+    "bg_pack_wa": (_I, [_V, _V, _V]),
+    "bg_policy_sample": (_I, [_V, _V, _I, _LL, _V, _V, _V, _V, _V, _V, _F, _U64, _U64, _U32, _I, _V, _V, _V, _V, _V]),
     "bg_pack_w1": (_I, [_V, _V, _V]),
     "bg_mlp_value": (_I, [_V, _V, _I, _I, _LL, _V, _V, _V, _V, _F, _I, _V, _V]),
 }

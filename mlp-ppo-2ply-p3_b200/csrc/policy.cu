@@ -1,0 +1,294 @@
+// policy.cu -- the policy/value forward of the PPO rollout on the tcgen05 tensor cores, fused with the feature
+// encoding, the action mask, the softmax and the sampling.
+//
+// Replaces, for B positions at once, BackgammonPPOAgent.select_action (src/agent/ppo_agent.py:138-191):
+//     logits, value = BackgammonPolicyNetwork.forward(obs)        (src/agent/policy_network.py:58-75)
+//     masked = logits + log(mask + 1e-45);  probs = softmax(masked)
+//     action ~ Categorical(probs)  (training)   |   argmax(probs)  (inference);   log_prob(action)
+// with obs = the 198 features of (board52, turn flag) and mask = the env's prefix mask (slot k legal iff
+// k < legal_counts[b], src/environment/backgammon_env.py:228-231).
+//
+// Per tile of 128 positions (one CTA, 16 warps, everything on chip):
+//   A  boards -> shared memory
+//   B  8 warps expand the feature rows in registers and tcgen05.st them into TENSOR MEMORY (A1, as in K4)
+//   C  13 x tcgen05.mma  acc1[128x128] = A1 (TMEM) x W1^T (smem)
+//   D  16 warps read acc1 (tcgen05.ld), add b1, ReLU; value head partial sums; hidden activations rounded to bf16
+//      and written back to TMEM as the A operand of the second GEMM (A2, 64 columns, aliasing A1)
+//   E  4 chunks of 128 actions: 8 x tcgen05.mma  acc2[c&1] = A2 x Wa[128c..]^T, double buffered in TMEM; while
+//      chunk c+1 multiplies, the 16 warps reduce chunk c straight out of TMEM: + bias, mask offset, online
+//      max / sum-exp, and Gumbel-max sampling (argmax_i logit_i + g_i, g_i = -log(-log u_i), u_i from Philox4x32-10
+//      keyed by (seed; global row, step, slot)) -- a single pass, the 500 logits of a row never leave the SM
+//   F  the four column-quarter warps of a row are combined through shared memory -> action, log-prob, value
+// HBM traffic per position: 53 B board + 4 B count in, 12 B out.
+// TMEM columns: [0,128) acc1; [128,232) A1 / [128,192) A2; [256,384) and [384,512) acc2 ping/pong.
+#include <cuda_bf16.h>
+#include "bg_device.cuh"
+#include "bg_features.cuh"
+#include "bg_tcgen05.cuh"
+#include "bg_internal.h"
+
+namespace bg {
+
+constexpr int kActions = BG_ACTIONS;       // 500
+constexpr int kActPad = 512;
+constexpr int kPolThreads = 512;
+constexpr int kWaBytes = (kHidden / 8) * kActPad * 16;      // 131,072: (k/8)*8192 + n*16 + (k%8)*2
+constexpr int kW1Bytes = kChunks * kTileM * 16;             // 53,248
+constexpr float kMaskLog = -103.27893f;                     // log(1e-45f) in f32 (1e-45 is the smallest denormal)
+constexpr uint32_t kTagGumbel = 0x47554D42u;                // "GUMB"
+constexpr int kColAcc1 = 0, kColA = 128, kColAcc2 = 256;
+
+struct PolSmem {
+    uint8_t W1[kW1Bytes];
+    uint8_t Wa[kWaBytes];
+    uint32_t boards[kTileM * kBoardWords];
+    float b1[kHidden], wv[kHidden], ba[kActPad];
+    float part[4][kTileM];
+    float red_m[4][kTileM], red_s[4][kTileM], red_g[4][kTileM], red_l[4][kTileM];
+    int red_i[4][kTileM];
+    uint2 units[16];
+    unsigned long long bar1, bar2[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+}
+
+__global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
+    const int8_t* __restrict__ boards, const int8_t* __restrict__ flags, int flag_all, long long B,
+    const int32_t* __restrict__ legal_counts, const uint16_t* __restrict__ w1, const float* __restrict__ b1,
+    const uint16_t* __restrict__ wa, const float* __restrict__ ba, const float* __restrict__ wv, float bv,
+    unsigned long long seed, unsigned long long stream_base, uint32_t step, int greedy,
+    int32_t* __restrict__ actions, float* __restrict__ logp, float* __restrict__ values, float* __restrict__ logits_out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    PolSmem& S = *reinterpret_cast<PolSmem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- one-time setup: weights into the tcgen05 operand layouts, biases, barriers, TMEM
+    for (int c = tid; c < kChunks * kHidden; c += kPolThreads) {
+        const int kc = c / kHidden, n = c - kc * kHidden;
+        *reinterpret_cast<uint4*>(S.W1 + kc * 2048 + n * 16) = *reinterpret_cast<const uint4*>(w1 + (size_t)n * kKPad + kc * 8);
+    }
+    for (int c = tid; c < (kHidden / 8) * kActPad; c += kPolThreads) {
+        const int kc = c / kActPad, n = c - kc * kActPad;
+        *reinterpret_cast<uint4*>(S.Wa + kc * (kActPad * 16) + n * 16) = *reinterpret_cast<const uint4*>(wa + (size_t)n * kHidden + kc * 8);
+    }
+    load_units_lut(S.units);
+    if (tid < kHidden) { S.b1[tid] = b1[tid]; S.wv[tid] = wv[tid]; }
+    S.ba[tid] = tid < kActions ? ba[tid] : 0.0f;                 // kPolThreads == kActPad
+    if (tid == 0) {
+        mbar_init(&S.bar1, 1); mbar_init(&S.bar2[0], 1); mbar_init(&S.bar2[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
+                     :: "r"(smem_u32(&S.tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = S.tmem_base;
+    const uint32_t w1_addr = smem_u32(S.W1), wa_addr = smem_u32(S.Wa);
+    const long long n_tiles = (B + kTileM - 1) / kTileM;
+    const int q = warp & 3, cq = warp >> 2;                      // TMEM lane quadrant, column quarter
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t ph1 = 0, ph2[2] = {0, 0};
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long row0 = tile * kTileM;
+        const int rows = (int)min((long long)kTileM, B - row0);
+        // ---- A: stage the boards
+        {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
+            for (int i = tid; i < kTileM * kBoardWords; i += kPolThreads) S.boards[i] = i < rows * kBoardWords ? __ldg(src + i) : 0u;
+        }
+        __syncthreads();
+        // ---- B: feature rows -> TMEM (two threads per position; warps 0-3 chunks 0-12, warps 4-7 chunks 13-25)
+        if (warp < 8) {
+            const int prow = tid & (kTileM - 1), half = tid >> 7;
+            uint32_t w[kBoardWords];
+#pragma unroll
+            for (int i = 0; i < kBoardWords; ++i) w[i] = S.boards[prow * kBoardWords + i];
+            const int fl = prow < rows ? (int)((flags ? flags[row0 + prow] : flag_all) & 1) : 0;
+            const uint32_t trow = lane_base + (uint32_t)kColA;
+            if (half == 0) build_half_row<0>(w, fl, S.units, trow, prow < rows);
+            else           build_half_row<1>(w, fl, S.units, trow, prow < rows);
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        // ---- C: hidden layer GEMM
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+            for (int ks = 0; ks < kKPad / 16; ++ks)
+                mma_bf16_ts(tmem + kColAcc1, tmem + (uint32_t)(kColA + ks * 8), make_smem_desc(w1_addr + ks * 2 * 2048), kIdesc,
+                            ks > 0 ? 1u : 0u);
+            umma_commit(&S.bar1);
+        }
+        mbar_wait(&S.bar1, ph1); ph1 ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        // ---- D: bias + ReLU, value-head partials, hidden -> bf16 -> TMEM (A operand of the policy GEMM)
+        {
+            uint32_t acc[32];
+            tmem_ld32(lane_base + (uint32_t)(kColAcc1 + 32 * cq), acc);
+            tmem_ld_wait();
+            float v = 0.0f;
+            uint32_t hw[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const float h0 = fmaxf(__uint_as_float(acc[j]) + S.b1[32 * cq + j], 0.0f);
+                const float h1 = fmaxf(__uint_as_float(acc[j + 1]) + S.b1[32 * cq + j + 1], 0.0f);
+                v = fmaf(S.wv[32 * cq + j], h0, v);
+                v = fmaf(S.wv[32 * cq + j + 1], h1, v);
+                hw[j >> 1] = pack_bf16x2(h0, h1);
+            }
+            S.part[cq][row] = v;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                tmem_st4(lane_base + (uint32_t)(kColA + 16 * cq + 4 * i), make_uint4(hw[4 * i], hw[4 * i + 1], hw[4 * i + 2], hw[4 * i + 3]));
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        // ---- E: policy GEMM in 4 chunks of 128 actions + fused masked softmax / Gumbel-max
+        auto issue_chunk = [&](int c) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+            for (int ks = 0; ks < kHidden / 16; ++ks)
+                mma_bf16_ts(tmem + (uint32_t)(kColAcc2 + 128 * (c & 1)), tmem + (uint32_t)(kColA + ks * 8),
+                            make_smem_desc_kmajor(wa_addr + c * (128 * 16) + ks * 2 * (kActPad * 16), kActPad * 16, 128), kIdesc,
+                            ks > 0 ? 1u : 0u);
+            umma_commit(&S.bar2[c & 1]);
+        };
+        if (tid == 0) { issue_chunk(0); issue_chunk(1); }
+        const long long gid = row0 + row;                         // row index within this call
+        const int n_legal = (row < rows && legal_counts) ? legal_counts[gid] : (legal_counts ? 1 : kActions);
+        const unsigned long long sid = stream_base + (unsigned long long)gid;   // global stream id (game id)
+        float m = -INFINITY, s = 0.0f, gbest = -INFINITY, lbest = 0.0f;
+        int ibest = 0;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            mbar_wait(&S.bar2[c & 1], ph2[c & 1]); ph2[c & 1] ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            uint32_t acc[32];
+            tmem_ld32(lane_base + (uint32_t)(kColAcc2 + 128 * (c & 1) + 32 * cq), acc);
+            tmem_ld_wait();
+            const int base = 128 * c + 32 * cq;                    // action slot of acc[0]
+            float x[32];
+            float cm = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int i = base + j;
+                float l = __uint_as_float(acc[j]) + S.ba[i];
+                if (logits_out && row < rows && i < kActions) logits_out[gid * kActions + i] = l;
+                if (i >= n_legal) l += kMaskLog;                   // logits + log(mask + 1e-45), ppo_agent.py:165
+                if (i >= kActions) l = -INFINITY;                  // padding slots do not exist
+                x[j] = l;
+                cm = fmaxf(cm, l);
+            }
+            if (cm > -INFINITY) {
+                const float mn = fmaxf(m, cm);
+                float add = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) add += __expf(x[j] - mn);
+                s = s * __expf(m - mn) + add;
+                m = mn;
+            }
+            // sampling: argmax_i x_i + Gumbel_i (lowest slot on ties); a masked slot (offset -103) can only win when
+            // every slot is masked (a pass: the reference samples from all 500 then), so its noise is skipped otherwise
+            if (greedy) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (x[j] > gbest) { gbest = x[j]; ibest = base + j; lbest = x[j]; }
+            } else {
+                const int lim = n_legal > 0 ? min(n_legal, kActions) : kActions;
+#pragma unroll
+                for (int g4 = 0; g4 < 8; ++g4) {
+                    if (base + 4 * g4 < lim) {
+                        uint32_t r[4];
+                        philox4x32_10((uint32_t)sid, ((uint32_t)(sid >> 32) << 8) | (uint32_t)((base >> 2) + g4), step, kTagGumbel,
+                                      (uint32_t)seed, (uint32_t)(seed >> 32), r);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = 4 * g4 + e;
+                            const float u = ((float)(r[e] >> 8) + 0.5f) * (1.0f / 16777216.0f);      // (0,1), 24 bits
+                            const float key = x[j] - __logf(-__logf(u));
+                            if (base + j < lim && key > gbest) { gbest = key; ibest = base + j; lbest = x[j]; }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncthreads();                                       // every warp has read acc2[c & 1]
+            if (tid == 0 && c + 2 < 4) issue_chunk(c + 2);
+        }
+        // ---- F: combine the four column quarters of each row
+        S.red_m[cq][row] = m; S.red_s[cq][row] = s; S.red_g[cq][row] = gbest; S.red_l[cq][row] = lbest; S.red_i[cq][row] = ibest;
+        __syncthreads();
+        if (tid < rows) {
+            const int r = tid;
+            float M = S.red_m[0][r];
+#pragma unroll
+            for (int k = 1; k < 4; ++k) M = fmaxf(M, S.red_m[k][r]);
+            float sum = 0.0f, gb = -INFINITY, lb = 0.0f;
+            int ib = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (S.red_m[k][r] > -INFINITY) sum += S.red_s[k][r] * __expf(S.red_m[k][r] - M);
+                const float g = S.red_g[k][r];
+                if (g > gb || (g == gb && g > -INFINITY && S.red_i[k][r] < ib)) { gb = g; lb = S.red_l[k][r]; ib = S.red_i[k][r]; }
+            }
+            actions[row0 + r] = ib;
+            if (logp) logp[row0 + r] = lb - (M + __logf(sum));
+            if (values) values[row0 + r] = bv + ((S.part[0][r] + S.part[1][r]) + (S.part[2][r] + S.part[3][r]));
+        }
+        __syncthreads();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(512u) : "memory");
+}
+
+__global__ void pack_wa_kernel(const float* __restrict__ w, uint16_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kActPad * kHidden) return;
+    const int n = i / kHidden;
+    out[i] = n < kActions ? __bfloat16_as_ushort(__float2bfloat16_rn(w[i])) : (uint16_t)0;
+}
+
+}  // namespace bg
+
+using namespace bg;
+
+extern "C" int bg_pack_wa(const float* action_head_weight, uint16_t* wa_bf16, void* stream) {
+    if (!action_head_weight || !wa_bf16) return bg_set_error_msg(BG_ERR_INVALID, "bg_pack_wa: null pointer");
+    pack_wa_kernel<<<(kActPad * kHidden + 255) / 256, 256, 0, (cudaStream_t)stream>>>(action_head_weight, wa_bf16);
+    return bg_set_error(cudaGetLastError(), "bg_pack_wa: launch");
+}
+
+extern "C" int bg_policy_sample(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
+                                const int32_t* legal_counts, const uint16_t* w1_bf16, const float* b1,
+                                const uint16_t* wa_bf16, const float* ba, const float* wv, float bv,
+                                unsigned long long seed, unsigned long long stream_base, uint32_t step, int greedy,
+                                int32_t* actions, float* log_probs, float* values, float* logits_out, void* stream) {
+    if (B < 0) return bg_set_error_msg(BG_ERR_INVALID, "bg_policy_sample: negative batch");
+    if (B == 0) return BG_OK;
+    if (!boards52 || !w1_bf16 || !b1 || !wa_bf16 || !ba || !wv || !actions)
+        return bg_set_error_msg(BG_ERR_INVALID, "bg_policy_sample: null pointer");
+    const size_t smem = sizeof(PolSmem) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return bg_set_error(e, "bg_policy_sample: cudaFuncSetAttribute");
+    long long tiles = (B + kTileM - 1) / kTileM;
+    long long grid = bg_sm_count();
+    if (grid > tiles) grid = tiles;
+    policy_kernel<<<(unsigned)grid, kPolThreads, smem, (cudaStream_t)stream>>>(
+        boards52, flags, flag_all & 1, B, legal_counts, w1_bf16, b1, wa_bf16, ba, wv, bv, seed, stream_base, step, greedy,
+        actions, log_probs, values, logits_out);
+    return bg_set_error(cudaGetLastError(), "bg_policy_sample: launch");
+}

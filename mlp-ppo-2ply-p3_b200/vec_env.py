@@ -166,13 +166,16 @@ class B200BackgammonVecEnv:
         with torch.cuda.device(self.device):
             st = self._state()
             check(lib().bg_env_reset(C.byref(st), None, self.status.data_ptr(), _stream()), "bg_env_reset")
+            self.obs_f32 = torch.empty((self.num_envs, FEATURES), dtype=torch.float32, device=self.device)
             self.update_legal_plays(obs=True, features=False)
-            obs = self.obs_f32.clone()
+            obs = self.obs_f32
         self.check_status()
         return obs
 
     def step(self, actions, return_obs=True, with_features=False):
-        """vec_bg_env.py:28-49 -> (obs (N,198) f32, rewards (N,) f32, dones (N,) bool, infos)"""
+        """vec_bg_env.py:28-49 -> (obs (N,198) f32, rewards (N,) f32, dones (N,) bool, infos).
+        Every returned tensor is a fresh allocation (as in the reference) that the kernels write directly: no
+        staging copies.  with_features also refreshes self.after_feats (bf16 features of every legal play)."""
         if not isinstance(actions, torch.Tensor):
             import numpy as np
             acts = [0 if a is None else int(a) for a in actions] if not isinstance(actions, np.ndarray) else actions
@@ -180,15 +183,23 @@ class B200BackgammonVecEnv:
         actions = actions.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
         if actions.shape[0] != self.num_envs:
             raise BgError("step: need one action per env")
-        with torch.cuda.device(self.device):
+        N, dev = self.num_envs, self.device
+        with torch.cuda.device(dev):
+            # fresh result tensors; the persistent attributes alias them until the next step
+            self.rewards = torch.empty(N, dtype=torch.float32, device=dev)
+            dones = torch.empty(N, dtype=torch.bool, device=dev)                # K2 writes 0/1 bytes
+            self.dones_u8 = dones.view(torch.uint8)
+            info = torch.empty((4, N), dtype=torch.int8, device=dev)
+            self.info_player, self.winner, self.game_score, self.flags = info[0], info[1], info[2], info[3].view(torch.uint8)
+            if return_obs:
+                self.obs_f32 = torch.empty((N, FEATURES), dtype=torch.float32, device=dev)
             self._apply_actions(actions)
             self.update_legal_plays(obs=return_obs, features=with_features)
-            obs = self.obs_f32.clone() if return_obs else None          # fresh tensor per call, as the reference returns
         self._steps += 1
         if self.check_every and self._steps % self.check_every == 0:
             self.check_status()
-        infos = StepInfos(self.info_player.clone(), self.winner.clone(), self.game_score.clone(), self.flags.clone())
-        return obs, self.rewards.clone(), self.dones_u8.to(torch.bool), infos
+        infos = StepInfos(self.info_player, self.winner, self.game_score, self.flags)
+        return (self.obs_f32 if return_obs else None), self.rewards, dones, infos
 
     def _apply_actions(self, actions_i32: torch.Tensor):
         """K2: step / reward / terminal / auto-reset / dice for every game."""
