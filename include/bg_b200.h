@@ -198,6 +198,13 @@ int bg_policy_sample(const int8_t* boards52, const int8_t* flags, int flag_all, 
                      float* log_probs /*nullable*/, float* values /*nullable*/, float* logits_out /*nullable*/,
                      void* stream);
 
+/* N2  discounted returns / GAE(lambda) per game over a rollout stored step-major [T][N]; replaces
+ * BackgammonPPOAgent.compute_returns (agent/ppo_agent.py:206-216).  values / last_values nullable (= 0):
+ * lambda = 1, last_values = NULL is compute_returns for each game; T = T*N, N = 1 is the reference's walk over its
+ * interleaved memory (agent/train.py:64-66).  returns / advantages: either may be NULL. */
+int bg_gae(const float* rewards, const uint8_t* dones, const float* values /*nullable*/, const float* last_values /*nullable*/,
+           int T, long long N, float gamma, float lambda, float* returns, float* advantages, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K5  2-ply search (the reference's own 2-ply, moves/expect_minmax.py:1-206, is
  * commented-out code, so the definition is the build's, on the reference's live primitives).

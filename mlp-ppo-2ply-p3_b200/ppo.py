@@ -1,0 +1,296 @@
+"""PPO self-play on the device: rollout buffer, returns/GAE, the clipped-surrogate update and the data-parallel
+trainer (BASELINE config 5).
+
+Mirrors the reference's learner:
+    BackgammonPPOAgent.select_action   src/agent/ppo_agent.py:138-191   -> PolicyValueNet.act (one fused kernel)
+    per-sample python `memory` dicts   src/agent/ppo_agent.py:175-186   -> RolloutBuffer, [T][N] device tensors
+    compute_returns                    src/agent/ppo_agent.py:206-216   -> bg_gae (per game; lambda = 1 = the reference)
+    update (4 full-batch epochs)       src/agent/ppo_agent.py:218-366   -> ppo_loss + PPOLearner.update
+    train_agent                        src/agent/train.py:30-123        -> PPOTrainer.train
+    hyper-parameters                   src/agent/config.py:4-22         -> PPOConfig defaults
+
+Games shard across GPUs by game id (no data-path collective); the ONLY collective is the gradient all-reduce of
+one flat 90,101-element f32 bucket per optimiser step (NCCL over NVLink), plus three scalars for the return
+normalisation.  The rollout side (env step, legal moves, policy forward, sampling, returns) is hand-written CUDA;
+the update's forward/backward are plain library GEMMs through torch autograd under bf16 autocast, as the reference
+runs them (`torch.amp.autocast`, ppo_agent.py:269).
+
+Documented divergences from the reference: returns are computed per game, not over the interleaved
+memory of all envs as one sequence (`returns_mode="interleaved"` reproduces that for parity tests); games in flight
+are kept across updates unless `reset_each_update=True` (train.py:40 resets them); no GradScaler (bf16 needs none).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import math
+
+import torch
+import torch.nn.functional as F
+
+from ._lib import BgError, StepOut, check, lib
+from .engine import _stream, encode
+from .policy_net import ACTIONS, KEYS, PolicyValueNet
+
+MASK_LOG = -103.27893          # log(1e-45) in f32: the reference's log(mask + 1e-45) for an illegal slot
+
+
+@dataclasses.dataclass
+class PPOConfig:                                   # src/agent/config.py:4-22
+    t_horizon: int = 512
+    num_epochs: int = 4
+    learning_rate: float = 1e-3
+    gamma: float = 0.99
+    lam: float = 1.0                               # 1.0 = Monte-Carlo returns as the reference (no GAE there)
+    bootstrap: bool = False                        # reference: R = 0 at the end of the memory
+    eps_clip: float = 0.25
+    value_loss_coef: float = 0.5
+    entropy_coef_start: float = 0.15
+    entropy_coef_end: float = 0.01
+    entropy_anneal_episodes: int = 400_000
+    num_minibatches: int = 1                       # reference: full batch
+    returns_mode: str = "per_game"                 # or "interleaved" (the reference's walk, for parity tests)
+    reset_each_update: bool = False                # reference: True (train.py:40)
+    autocast: bool = True
+
+
+# --------------------------------------------------------------------------------------------- pure torch math
+
+def policy_value_forward(params, x):
+    """BackgammonPolicyNetwork.forward (policy_network.py:58-75) on features x (B,198+) -> logits (B,500), values (B,)"""
+    h = F.relu(F.linear(x[:, :198], params["fc1.weight"], params["fc1.bias"]))
+    logits = F.linear(h, params["action_head.weight"], params["action_head.bias"])
+    values = F.linear(h, params["value_head.weight"], params["value_head.bias"]).squeeze(-1)
+    return logits, values
+
+
+def ppo_loss(params, x, counts, actions, old_logp, returns, advantages, eps_clip, value_coef, entropy_coef,
+             autocast=True):
+    """The loss of one epoch of BackgammonPPOAgent.update (ppo_agent.py:268-299).  counts = legal slots per sample
+    (prefix mask, backgammon_env.py:228-231).  Runs on any device (the CPU path exists for the host-logic tests)."""
+    dev_type = x.device.type
+    with torch.autocast(device_type=dev_type, dtype=torch.bfloat16, enabled=autocast):
+        logits, values = policy_value_forward(params, x)
+        slot = torch.arange(ACTIONS, device=x.device)[None, :]
+        masked = logits.float() + torch.where(slot < counts[:, None], 0.0, MASK_LOG)       # logits + log(mask + 1e-45)
+        logp_all = torch.log_softmax(masked, dim=-1)
+        new_logp = logp_all.gather(1, actions.long()[:, None])[:, 0]
+        ratios = torch.exp(new_logp - old_logp)
+        surr1 = ratios * advantages
+        surr2 = torch.clamp(ratios, 1 - eps_clip, 1 + eps_clip) * advantages
+        policy_loss = -torch.min(surr1, surr2).mean()
+        value_loss = F.mse_loss(values.float(), returns)
+        p = logp_all.exp()
+        entropy = -(p * logp_all).sum(-1).mean()
+        loss = policy_loss + value_coef * value_loss - entropy_coef * entropy
+    return loss, policy_loss.detach(), value_loss.detach(), entropy.detach()
+
+
+def discounted_returns(rewards, dones, values, last_values, gamma, lam):
+    """bg_gae on CUDA tensors ([T][N], step-major) -> (returns, advantages)."""
+    T, N = rewards.shape
+    ret, adv = torch.empty_like(rewards), torch.empty_like(rewards)
+    with torch.cuda.device(rewards.device):
+        check(lib().bg_gae(rewards.data_ptr(), dones.data_ptr(), values.data_ptr() if values is not None else None,
+                           last_values.data_ptr() if last_values is not None else None, T, N, float(gamma), float(lam),
+                           ret.data_ptr(), adv.data_ptr(), _stream()), "bg_gae")
+    return ret, adv
+
+
+class FlatParams:
+    """The network's f32 master weights as views into ONE flat buffer (and their grads into another), so that the
+    data-parallel gradient exchange is a single all-reduce of 90,101 floats."""
+
+    def __init__(self, state_dict, device):
+        shapes = [(k, tuple(state_dict[k].shape)) for k in KEYS]
+        n = sum(math.prod(s) for _, s in shapes)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=device)
+        self.params, o = {}, 0
+        for k, s in shapes:
+            m = math.prod(s)
+            self.flat[o:o + m].copy_(torch.as_tensor(state_dict[k], dtype=torch.float32).reshape(-1))
+            p = self.flat[o:o + m].view(s).requires_grad_(True)
+            p.grad = self.flat_grad[o:o + m].view(s)
+            self.params[k] = p
+            o += m
+        self.numel = n
+
+    def all_reduce_grads(self, dist=None):
+        if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat_grad)                     # one flat bucket (sum) ...
+            self.flat_grad.div_(dist.get_world_size())          # ... averaged: every rank holds the same shard size
+
+
+class PPOLearner:
+    """Clipped-surrogate PPO update over a finished rollout (ppo_agent.py:218-366), data parallel."""
+
+    def __init__(self, state_dict, device, cfg: PPOConfig | None = None, dist=None):
+        self.cfg = cfg or PPOConfig()
+        self.device = torch.device(device)
+        self.dist = dist
+        self.fp = FlatParams(state_dict, self.device)
+        self.optimizer = torch.optim.Adam(list(self.fp.params.values()), lr=self.cfg.learning_rate)   # ppo_agent.py:83
+        self.total_episodes = 0
+        self.total_steps = 0
+        self.entropy_coef = self.cfg.entropy_coef_start
+        self.last = {}
+
+    def update_entropy_coef(self):                                                                   # ppo_agent.py:193-204
+        c = self.cfg
+        progress = min(1.0, self.total_episodes / c.entropy_anneal_episodes)
+        self.entropy_coef = c.entropy_coef_start - progress * (c.entropy_coef_start - c.entropy_coef_end)
+
+    def _global_mean_std(self, x):
+        """mean and unbiased std of x over ALL ranks (returns.mean() / returns.std(), ppo_agent.py:256)."""
+        s = torch.stack([x.sum().double(), (x.double() ** 2).sum(), torch.tensor(float(x.numel()), device=x.device, dtype=torch.float64)])
+        if self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size() > 1:
+            self.dist.all_reduce(s)
+        n = s[2]
+        mean = s[0] / n
+        var = (s[1] - n * mean * mean) / torch.clamp(n - 1, min=1.0)
+        return mean.float(), var.clamp(min=0).sqrt().float()
+
+    def update(self, x, counts, actions, old_logp, old_values, returns):
+        """x (B,198+) features, the rest (B,).  Normalises the returns, advantages = returns - V_old (ppo_agent.py:256-259),
+        then num_epochs passes over the batch (full batch, or num_minibatches slices)."""
+        c = self.cfg
+        mean, std = self._global_mean_std(returns)
+        returns = (returns - mean) / (std + 1e-5)
+        adv = returns - old_values
+        B = x.shape[0]
+        mb = max(1, int(c.num_minibatches))
+        stats = torch.zeros(4, device=x.device)
+        for _ in range(c.num_epochs):
+            for k in range(mb):
+                sl = slice(k * B // mb, (k + 1) * B // mb)
+                loss, pl, vl, ent = ppo_loss(self.fp.params, x[sl], counts[sl], actions[sl], old_logp[sl], returns[sl], adv[sl],
+                                             c.eps_clip, c.value_loss_coef, self.entropy_coef, autocast=c.autocast)
+                self.fp.flat_grad.zero_()
+                loss.backward()
+                self.fp.all_reduce_grads(self.dist)
+                self.optimizer.step()
+                stats += torch.stack([pl.float(), vl.float(), ent.float(), loss.detach().float()])
+                self.total_steps += 1
+        stats /= c.num_epochs * mb
+        self.last = dict(zip(("policy_loss", "value_loss", "entropy", "total_loss"), stats.tolist()))
+        self.update_entropy_coef()
+        return self.last
+
+    def state_dict(self):
+        return {k: v.detach().clone() for k, v in self.fp.params.items()}
+
+
+class RolloutBuffer:
+    """[T][N] device tensors replacing the per-sample python dicts of ppo_agent.py:175-186.  Observations are kept as
+    board52 + player (53 B instead of 792 B of f32 features); the learner re-encodes them with K3."""
+
+    def __init__(self, T, N, device):
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
+        self.T, self.N = T, N
+        self.boards, self.players = z((T, N, 52), torch.int8), z((T, N), torch.int8)
+        self.counts, self.actions = z((T, N), torch.int32), z((T, N), torch.int32)
+        self.logp, self.values = z((T, N), torch.float32), z((T, N), torch.float32)
+        self.rewards, self.dones = z((T, N), torch.float32), z((T, N), torch.uint8)
+        self.winner, self.info_player = z((T, N), torch.int8), z((T, N), torch.int8)
+        self.game_score, self.flags = z((T, N), torch.int8), z((T, N), torch.uint8)
+
+
+class PPOTrainer:
+    """Self-play PPO (train.py:30-123) with every game of this rank resident on its GPU."""
+
+    def __init__(self, env, net: PolicyValueNet, cfg: PPOConfig | None = None, dist=None, seed: int = 0):
+        self.env, self.net, self.cfg, self.dist = env, net, cfg or PPOConfig(), dist
+        self.device = env.device
+        self.learner = PPOLearner(net.params, self.device, self.cfg, dist)
+        # the net's master weights ARE the learner's parameters from here on
+        net.params = {k: v.detach() for k, v in self.learner.fp.params.items()}
+        net.sync()
+        self.buf = RolloutBuffer(self.cfg.t_horizon, env.num_envs, self.device)
+        self.seed = int(seed)
+        self.global_step = 0
+        self.episodes = 0
+        self.history = []
+
+    def collect(self):
+        """T steps of self-play: policy kernel -> K2 -> K1, results written straight into the rollout buffer."""
+        env, buf, net = self.env, self.buf, self.net
+        L = lib()
+        with torch.cuda.device(self.device):
+            if self.cfg.reset_each_update:
+                env.reset()
+            for t in range(buf.T):
+                buf.boards[t].copy_(env.boards52); buf.players[t].copy_(env.players); buf.counts[t].copy_(env.legal_counts)
+                net.act(env.boards52, env.players, env.legal_counts, seed=self.seed, stream_base=env.stream_base,
+                        step=self.global_step, out=(buf.actions[t], buf.logp[t], buf.values[t]))
+                st = env._state()
+                out = StepOut(buf.rewards[t].data_ptr(), buf.dones[t].data_ptr(), buf.info_player[t].data_ptr(),
+                              buf.winner[t].data_ptr(), buf.game_score[t].data_ptr(), buf.flags[t].data_ptr())
+                check(L.bg_env_step(C.byref(st), buf.actions[t].data_ptr(), C.byref(out), env.status.data_ptr(), _stream()),
+                      "bg_env_step")
+                env._refresh_legal_moves()
+                self.global_step += 1
+            last_v = net.values(env.boards52, env.players) if self.cfg.bootstrap else None
+            if self.cfg.returns_mode == "interleaved":
+                T, N = buf.T, buf.N
+                ret, _ = discounted_returns(buf.rewards.view(T * N, 1), buf.dones.view(T * N, 1), None, None, self.cfg.gamma, 1.0)
+                ret = ret.view(T, N)
+            else:
+                ret, _ = discounted_returns(buf.rewards, buf.dones, buf.values if self.cfg.lam < 1.0 or self.cfg.bootstrap else None,
+                                            last_v, self.cfg.gamma, self.cfg.lam)
+        return ret
+
+    def update(self, returns):
+        buf = self.buf
+        B = buf.T * buf.N
+        x = encode(buf.boards.view(B, 52), buf.players.view(B), dtype=torch.bfloat16 if self.cfg.autocast else torch.float32)
+        if not self.cfg.autocast:
+            x = x[:, :198]
+        stats = self.learner.update(x, buf.counts.view(B), buf.actions.view(B), buf.logp.view(B), buf.values.view(B), returns.reshape(B))
+        self.net.sync()
+        return stats
+
+    def train(self, num_updates: int, log_every: int = 1, log=print):
+        for u in range(num_updates):
+            ret = self.collect()
+            done = self.buf.dones.bool()
+            n_done = int(done.sum().item())
+            self.episodes += n_done
+            self.learner.total_episodes = self.episodes
+            stats = self.update(ret)
+            stats.update(update=u, episodes=self.episodes, steps=self.global_step * self.env.num_envs,
+                         mean_reward_per_game=float(self.buf.rewards.sum().item()) / max(1, n_done),
+                         entropy_coef=self.learner.entropy_coef)
+            self.env.check_status()
+            self.history.append(stats)
+            if log and u % log_every == 0:
+                log(stats)
+        return self.history
+
+
+@torch.no_grad()
+def evaluate_vs_random(net: PolicyValueNet, num_games: int = 4096, device=None, seed: int = 1234, max_steps: int = 2000,
+                       greedy: bool = True):
+    """Win rate (and mean points) of the policy as PLAYER1 against a uniform-random PLAYER2: each env plays exactly one
+    game; a learning-curve metric for parity with the reference's `Win Rate` scalar (ppo_agent.py:490-520)."""
+    from .vec_env import B200BackgammonVecEnv
+    device = torch.device(device or net.device)
+    env = B200BackgammonVecEnv(num_envs=num_games, device=device, seed=seed, check_every=0)
+    env.reset()
+    finished = torch.zeros(num_games, dtype=torch.bool, device=device)
+    won = torch.zeros(num_games, dtype=torch.bool, device=device)
+    points = torch.zeros(num_games, dtype=torch.float32, device=device)
+    for t in range(max_steps):
+        a_pol, _, _ = net.act(env.boards52, env.players, env.legal_counts, seed=seed, step=t, greedy=greedy)
+        a_rnd = env.random_actions(seed + 1, t)
+        acts = torch.where(env.players == 0, a_pol, a_rnd).contiguous()
+        env.step_device(acts)
+        d = env.dones_u8.bool() & ~finished
+        won |= d & (env.winner == 0)
+        points += torch.where(d, torch.where(env.winner == 0, env.game_score.float(), -env.game_score.float()), torch.zeros_like(points))
+        finished |= d
+        if t % 64 == 63 and bool(finished.all()):
+            break
+    env.check_status()
+    n = int(finished.sum().item())
+    return {"games": n, "win_rate": float(won.sum().item()) / max(1, n), "mean_points": float(points.sum().item()) / max(1, n)}
