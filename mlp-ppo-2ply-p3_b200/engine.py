@@ -51,6 +51,42 @@ def initial_board52(n: int, device) -> torch.Tensor:
     return b
 
 
+def render_board52(b52, tokens=("X", "O")) -> str:
+    """ASCII dump of one position in the layout of BackgammonEnv.render (environment/backgammon_env.py:253-355): points
+    12..23 on top (PLAYER2's home board 18..23 on the right), 11..0 below.  The reference indexes the bar / borne-off
+    men as `tensor[player, 24]` / `[player, 25]`, columns that do not exist in its (4,24) tensor (so its render
+    raises); here they are read from rows 2 and 3 where the board keeps them (board/immutable_board.py:20-27)."""
+    b = [int(v) for v in (b52.tolist() if hasattr(b52, "tolist") else b52)]
+    pts, col = [], []
+    for i in range(24):
+        c1, c2 = b[i], b[24 + i]
+        if c1 > 0 and c2 > 0:
+            pts.append(0); col.append("?")
+        elif c1 > 0:
+            pts.append(c1); col.append(tokens[0])
+        elif c2 > 0:
+            pts.append(c2); col.append(tokens[1])
+        else:
+            pts.append(0); col.append(" ")
+
+    def half(points, colors, player):
+        bar, off = b[48 + player], b[50 + player]
+        lines = []
+        for i in range(max([0] + points + [bar, off])):
+            row = [c if n > i else " " for n, c in zip(points, colors)]
+            lines.append("|  " + " | ".join(f"{r:^3}" for r in row[:6]) + f" | {(tokens[player] if bar > i else ' '):^3} | "
+                         + " | ".join(f"{r:^3}" for r in row[6:]) + f" | {(tokens[player] if off > i else ' '):^3} |")
+        return lines
+    out = ["| 12 | 13 | 14 | 15 | 16 | 17 | BAR | 18 | 19 | 20 | 21 | 22 | 23 | OFF |",
+           f"|------------Outer Board-------------|     |-----------P={tokens[1]} Home Board----------|     |"]
+    out += half(pts[12:], col[12:], 1)
+    out.append("|------------------------------------|     |-----------------------------------|     |")
+    out += half(pts[:12][::-1], col[:12][::-1], 0)
+    out += [f"|------------Outer Board-------------|     |-----------P={tokens[0]} Home Board----------|     |",
+            "| 11 | 10 | 9  | 8  | 7  | 6  | BAR | 5  | 4  | 3  | 2  | 1  | 0  | OFF |", ""]
+    return "\n".join(out)
+
+
 def read_status(status: torch.Tensor, what: str = "kernel"):
     s = int(status.item())
     if s:

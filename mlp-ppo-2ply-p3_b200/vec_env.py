@@ -258,8 +258,18 @@ class B200BackgammonVecEnv:
     def close(self):
         self.check_status()
 
-    def render(self):
-        raise NotImplementedError("render is out of scope (the reference's own render is broken, SURVEY.md section 2)")
+    def render(self, index: int = 0, mode: str = "human"):
+        """BackgammonEnv.render (backgammon_env.py:253-355) of game `index`; returns the text it prints."""
+        if mode != "human":
+            raise NotImplementedError("Only 'human' mode is supported")
+        from .engine import render_board52
+        text = render_board52(self.boards52[index].cpu().numpy())
+        print(text)
+        return text
+
+    def match_scores(self):
+        """(N,2) i32 match points of PLAYER1 / PLAYER2 (backgammon_env.py:42-45,173-181) and (N,) match-over flags."""
+        return self.scores, self.match_over.bool()
 
     # ------------------------------------------------------------------ ragged extras
     def total_rows(self) -> int:

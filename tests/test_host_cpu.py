@@ -71,3 +71,20 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 for needle in ("import oracle", "from oracle", "bg_oracle", "libbg_oracle", "oracle/"):
                     assert needle not in txt, f"{f} references the oracle ({needle})"
+
+
+def test_render_initial_position():
+    import numpy as np
+    import bg_b200
+    from bg_b200.engine import render_board52
+    b = np.zeros(52, np.int8)
+    for p, c in ((0, 2), (11, 5), (16, 3), (18, 5), (24 + 23, 2), (24 + 12, 5), (24 + 7, 3), (24 + 5, 5)):
+        b[p] = c
+    b[48], b[51] = 1, 2                                  # one PLAYER1 man on the bar, two PLAYER2 men borne off
+    text = render_board52(b)
+    lines = text.split("\n")
+    assert lines[0].startswith("| 12 | 13 |") and "P=O Home Board" in lines[1]
+    top = lines[2]                                       # first row of the top half: points 12..17 | bar | 18..23 | off
+    cells = [c.strip() for c in top.strip("|").split("|")]
+    assert cells == ["O", "", "", "", "X", "", "", "X", "", "", "", "", "O", "O"]
+    assert sum(l.count("X") for l in lines) == 2 + 5 + 3 + 5 + 1 + 1    # 15 men + the bar token + the legend
