@@ -206,6 +206,14 @@ def run_engine(args):
     clocks = sampler.stop() if rank == 0 else None
     env.check_status()
     k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / K
+    # the same K1 launches alone (no encoder beside the overflow tiers), same positions: explains the in-step figure
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env._refresh_legal_moves(); torch.cuda.synchronize()
+    ea.record()
+    for _ in range(20):
+        env._refresh_legal_moves()
+    eb.record(); torch.cuda.synchronize()
+    k1_alone_ms = ea.elapsed_time(eb) / 20
     rows_per_step = float(rows_acc.item()) / K
     n_launch = launches[0]
 
@@ -238,13 +246,13 @@ def run_engine(args):
 
     extra = run_extras(bg_b200, env, torch, dev, args) if (world == 1 and not args.no_extras) else None
 
-    tm = torch.tensor([ms, e2e_s * 1e3, k1_ms], dtype=torch.float64, device=dev)
+    tm = torch.tensor([ms, e2e_s * 1e3, k1_ms, k1_alone_ms], dtype=torch.float64, device=dev)
     rw = torch.tensor([rows_per_step], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dist.all_reduce(rw, op=dist.ReduceOp.SUM)
         rw /= world
-    ms, e2e_ms, k1_ms = [float(x) for x in tm.tolist()]
+    ms, e2e_ms, k1_ms, k1_alone_ms = [float(x) for x in tm.tolist()]
     rows_per_step = float(rw.item())
     if rank != 0:
         if world > 1:
@@ -277,9 +285,14 @@ def run_engine(args):
         "roofline": {"kernel": "K1 movegen (tier 0 warp kernel + tier 1/2 team kernels)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / (ms / K),
+                     "k1_ms_per_launch_alone": k1_alone_ms, "achieved_alone": k1_bytes / (k1_alone_ms * 1e-3) / 1e9,
                      "algorithmic_bytes_per_launch": k1_bytes,
-                     "note": "K1 is integer/latency-bound (SURVEY 8(d)); the HBM fraction is reported as required. Its traffic is "
-                             "almost all writes: this GPU's write-only ceiling (torch zero_) is ~3.9 TB/s, the copy peak 6.46"},
+                     "note": "K1 is integer-issue bound (SURVEY 8(d)); the HBM fraction is reported as required. In the step "
+                             "the encoders (K3) run on a second stream beside K1's overflow tiers, so k1_ms_per_launch (CUDA "
+                             "events around K1's three launches inside the step) includes that sharing; *_alone is the same "
+                             "launch sequence with nothing beside it. traffic = dram bytes of the tier 0 + tier 1 launches "
+                             "(ncu --set full, profiles/): below the algorithmic bytes because the afterstate rows are still in "
+                             "the 126 MB L2 when the encoder reads them"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * N * 4, "d2h_bytes_per_step": world * N * 9,
                 "steps": E, "what": "B200BackgammonVecEnv.step(actions from pinned host memory); rewards, dones and "
                                     "legal-play counts copied to the host every step; observations stay on the device "
@@ -330,6 +343,21 @@ def run_extras(bg_b200, env, torch, dev, args):
         env.step_device(acts.clamp_(min=0))
     t = timed(greedy_step, 30)
     out["greedy_1ply"] = {"env_steps_per_s": env.num_envs / t, "ms_per_step": t * 1e3, "games": env.num_envs}
+    # N1 policy/value rollout forward (select_action) and the PPO rollout step (configs[4] rollout side): policy kernel -> K2 -> K1
+    pnet = bg_b200.PolicyValueNet.random_init(dev, seed=0)
+    N = env.num_envs
+    pout = (torch.empty(N, dtype=torch.int32, device=dev), torch.empty(N, dtype=torch.float32, device=dev),
+            torch.empty(N, dtype=torch.float32, device=dev))
+    step_ctr = [0]
+    t = timed(lambda: pnet.act(env.boards52, env.players, env.legal_counts, seed=1, step=0, out=pout), 20)
+    out["policy_sample"] = {"positions_per_s": N / t, "ms": t * 1e3, "tflops_bf16": N * (53504.0 + 2 * 128 * 512) / t / 1e12}
+    def ppo_rollout_step():
+        step_ctr[0] += 1
+        pnet.act(env.boards52, env.players, env.legal_counts, seed=1, stream_base=env.stream_base, step=step_ctr[0], out=pout)
+        env.step_device(pout[0])
+    t = timed(ppo_rollout_step, 30)
+    out["ppo_rollout"] = {"env_steps_per_s": N / t, "ms_per_step": t * 1e3, "games": N,
+                          "what": "sampled policy (fused policy/value kernel) -> K2 -> K1, no feature tensors in HBM"}
     # 2-ply (configs[3]): roots = the first R games' positions with their actual dice
     R = min(args.twoply_roots, env.num_envs)
     search = bg_b200.TwoPlySearch(net, max_afterstates_per_chunk=args.twoply_chunk)

@@ -220,6 +220,15 @@ int bg_movegen_replies_slab(const int8_t* positions52, const int8_t* movers, lon
                             int8_t* row_players /*nullable*/, uint16_t* row_features_bf16 /*nullable*/,
                             int32_t* counts_true /*nullable*/, int32_t* counts, long long* starts, unsigned long long* alloc_rows, int32_t* status, void* workspace,
                             size_t workspace_bytes, void* stream);
+/* The inner step of the search for M root afterstates in ONE call: bg_movegen_replies_slab, bg_mlp_value on the
+ * replies (terminal_aware, flag = the replying player) -> leaf_values[row], and bg_mlp_value on the positions with the
+ * flag flipped -> pass_values[i].  With side_stream != NULL the leaf evaluation of the rows that are final after K1's
+ * tier 0 runs beside the latency-bound overflow tiers (fork/join inside, as in bg_update_legal_plays). */
+int bg_twoply_replies_values(const int8_t* positions52, const int8_t* movers, long long M, int8_t* replies52,
+                             long long reply_capacity_rows, int8_t* row_players, int32_t* counts, long long* starts,
+                             unsigned long long* alloc_rows, int32_t* status, void* workspace, size_t workspace_bytes,
+                             const uint16_t* w1_bf16, const float* b1, const float* wv, float bv, float* leaf_values,
+                             float* pass_values, void* side_stream /*nullable*/, void* stream);
 /* scores[i] = +win reward if movers[i] has borne off 15 in after52[i], else
  * -sum_r p_r * (max over the replies of (i,r) of leaf_values, or pass_values[i] when there is no reply) */
 int bg_twoply_scores(const float* leaf_values, const long long* reply_starts, const int32_t* reply_counts,

@@ -35,6 +35,11 @@ int movegen_run(const int8_t* boards, const int8_t* players, const int8_t* dice,
 int encode_bf16_launch(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
                        const unsigned long long* row_begin_dev, const unsigned long long* n_rows_dev, uint16_t* out,
                        long long ld, cudaStream_t stream);
+// K4 launcher (mlp.cu); rows [*row_begin_dev (0 if null), min(B, *n_rows_dev)) are evaluated
+int mlp_value_launch(const int8_t* boards52, const int8_t* flags, int flag_all, int flip_flags, long long B,
+                     const unsigned long long* row_begin_dev, const unsigned long long* n_rows_dev,
+                     const uint16_t* w1_bf16, const float* b1, const float* wv, float bv, int terminal_aware,
+                     float* values, cudaStream_t stream);
 // overflow tiers (movegen_team.cu): one CTA per position of worklist[0 .. *nwork_dev)
 int movegen_team_mid(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
                      const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,

@@ -40,47 +40,47 @@ __device__ __forceinline__ void stage_boards(const int8_t* __restrict__ boards, 
     for (int i = threadIdx.x; i < rows * kBoardWords; i += kEncThreads) sm[i] = __ldg(src + i);
 }
 
-// bf16 rows: one thread per 16-byte output chunk (8 features), driven by a per-chunk descriptor so that every lane
-// runs the same code: byte w of kChunkDesc[k] describes word w (2 features) of chunk k: bit 7 clear -> bits 0..5 =
-// board52 byte of the point, bit 6 = which half of its 4 units; bit 7 set -> 0 zero, 1 bar1/off1, 2 bar2/off2, 3 flags.
-// A staged row is 16 words: the 13 board words, then the row's three "special" words (bar1/off1, bar2/off2, turn
-// flags) precomputed once per row, so that a special word is one more table address and not a divergent branch with
-// constant-memory lookups.  Every output word is then two dependent shared-memory loads (count byte -> units word)
-// with a select on the address.  A warp's 32 chunks are contiguous in global memory (rows are contiguous), so the
-// stores are full 512-byte runs; each thread builds kBfUnroll chunks before storing them (stores in flight).
+// bf16 rows.  Output = 16-byte chunks (8 features); chunk k of a row is described by kChunkDesc[k]: byte w of it
+// describes word w (2 features): bit 7 clear -> bits 0..5 = board52 byte of the point, bit 6 = which half of its 4
+// units; bit 7 set -> 0 zero, 1 bar1/off1, 2 bar2/off2, 3 turn flags.
+// Thread t of a CTA owns chunk column k = t % cpr for rows t / cpr, t / cpr + 16, ... of the tile, so the descriptor
+// is decoded ONCE per thread (four byte offsets, four table offsets) and a chunk costs four (count byte -> units
+// word) pairs of shared-memory loads and one 16-byte store; consecutive threads write consecutive chunks (rows are
+// contiguous), i.e. full 512-byte runs per warp.  A staged row is 16 words: the 13 board words, then the row's
+// three "special" words (bar1/off1, bar2/off2, turn flags) precomputed once per row, so that a special word is just
+// another address -- no divergent branch, no constant-memory lookups.
 constexpr int kBfRows = 128;
 constexpr int kBfRowWords = 16;
+constexpr int kBfRowsPerPass = 16;
+constexpr int kBfThreads = kBfRowsPerPass * 26;       // 416 = 13 warps (ld = 208); other ld: threads beyond 16*cpr idle
 constexpr int kBfUnroll = 4;
 
-__device__ __forceinline__ uint4 chunk_staged(const uint32_t* __restrict__ srow, uint32_t desc, const uint32_t* __restrict__ s_lut) {
-    // s_lut[0] == 0 (units of an empty point): the "zero" special word reads it
-    const uint8_t* b = reinterpret_cast<const uint8_t*>(srow);
-    uint32_t w[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const uint32_t d = (desc >> (8 * q)) & 0xFFu;
-        const uint32_t cnt = b[d & 63u] & 15u;                               // (any byte for a special word)
-        const uint32_t* lut_addr = s_lut + ((cnt << 1) | ((d >> 6) & 1u));
-        const uint32_t* sp_addr = (d & 3u) ? srow + 12 + (d & 3u) : s_lut;   // words 13, 14, 15 of the staged row
-        w[q] = *((d & 0x80u) ? sp_addr : lut_addr);
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-__global__ void __launch_bounds__(kEncThreads) encode_bf16_kernel(const int8_t* __restrict__ boards,
-                                                                  const int8_t* __restrict__ flags, int flag_all,
-                                                                  long long B, const unsigned long long* __restrict__ row_begin_dev,
-                                                                  const unsigned long long* __restrict__ n_rows_dev,
-                                                                  uint16_t* __restrict__ out, int cpr /* ld/8 */) {
+__global__ void __launch_bounds__(kBfThreads, 3) encode_bf16_kernel(const int8_t* __restrict__ boards,
+                                                                 const int8_t* __restrict__ flags, int flag_all,
+                                                                 long long B, const unsigned long long* __restrict__ row_begin_dev,
+                                                                 const unsigned long long* __restrict__ n_rows_dev,
+                                                                 uint16_t* __restrict__ out, int cpr /* ld/8 */) {
     __shared__ __align__(16) uint32_t sm[kBfRows * kBfRowWords];
     __shared__ uint32_t s_lut[32], s_desc[32];
     load_chunk_tables(s_lut, s_desc);
     if (n_rows_dev) B = min(B, (long long)*n_rows_dev);
     const long long begin = row_begin_dev ? (long long)*row_begin_dev : 0;
+    // this thread's chunk column and its decoded descriptor
+    const int rpp = cpr <= 26 ? kBfRowsPerPass : kBfThreads / cpr;      // rows per pass
+    const int tr = threadIdx.x / cpr, tk = threadIdx.x - tr * cpr;
+    const bool active = tr < rpp;
+    const uint32_t desc = tk < 26 ? kChunkDesc[tk] : 0x80808080u;
+    uint32_t boff[4], loff[4];                                          // byte offset in the row; table offset / special
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t d = (desc >> (8 * q)) & 0xFFu;
+        boff[q] = d & 63u;
+        loff[q] = (d & 0x80u) ? (0x100u | (d & 3u)) : ((d >> 6) & 1u);
+    }
     for (long long row0 = begin + (long long)blockIdx.x * kBfRows; row0 < B; row0 += (long long)gridDim.x * kBfRows) {
         const int rows = (int)min((long long)kBfRows, B - row0);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
-        for (int i = threadIdx.x; i < rows * kBoardWords; i += kEncThreads) {
+        for (int i = threadIdx.x; i < rows * kBoardWords; i += kBfThreads) {
             const int r = i / kBoardWords;
             sm[r * kBfRowWords + (i - r * kBoardWords)] = __ldg(src + i);
         }
@@ -94,22 +94,31 @@ __global__ void __launch_bounds__(kEncThreads) encode_bf16_kernel(const int8_t* 
             sm[r * kBfRowWords + 15] = flag == 0 ? 0x00003F80u : 0x3F800000u;
         }
         __syncthreads();
-        uint4* dst = reinterpret_cast<uint4*>(out + row0 * (long long)cpr * 8);
-        const int total = rows * cpr;
-        for (int c0 = threadIdx.x; c0 < total; c0 += kEncThreads * kBfUnroll) {
-            uint4 v[kBfUnroll];
+        if (active) {
+            uint4* dst = reinterpret_cast<uint4*>(out + row0 * (long long)cpr * 8) + tk;
+            for (int r0 = tr; r0 < rows; r0 += rpp * kBfUnroll) {
+                uint4 v[kBfUnroll];
 #pragma unroll
-            for (int u = 0; u < kBfUnroll; ++u) {
-                const int c = c0 + u * kEncThreads;
-                const int cc = c < total ? c : c0;
-                const int r = cpr == 26 ? cc / 26 : cc / cpr;
-                const int k = cc - r * cpr;
-                v[u] = chunk_staged(sm + r * kBfRowWords, k < 26 ? s_desc[k] : 0x80808080u, s_lut);
-            }
+                for (int u = 0; u < kBfUnroll; ++u) {
+                    const int r = min(r0 + u * rpp, rows - 1);
+                    const uint32_t* srow = sm + r * kBfRowWords;
+                    const uint8_t* b = reinterpret_cast<const uint8_t*>(srow);
+                    uint32_t w[4];
 #pragma unroll
-            for (int u = 0; u < kBfUnroll; ++u) {
-                const int c = c0 + u * kEncThreads;
-                if (c < total) dst[c] = v[u];
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t cnt = b[boff[q]] & 15u;
+                        // special: code 0 -> s_lut[0] (= 0), codes 1..3 -> words 13..15 of the staged row
+                        const uint32_t* a = (loff[q] & 0x100u) ? ((loff[q] & 3u) ? srow + 12 + (loff[q] & 3u) : s_lut)
+                                                               : s_lut + ((cnt << 1) | loff[q]);
+                        w[q] = *a;
+                    }
+                    v[u] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+#pragma unroll
+                for (int u = 0; u < kBfUnroll; ++u) {
+                    const int r = r0 + u * rpp;
+                    if (r < rows) dst[(long long)r * cpr] = v[u];
+                }
             }
         }
         __syncthreads();
@@ -160,14 +169,14 @@ extern "C" int bg_encode_f32(const int8_t* boards52, const int8_t* flags, int fl
 int bg::encode_bf16_launch(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
                            const unsigned long long* row_begin_dev, const unsigned long long* n_rows_dev, uint16_t* out,
                            long long ld, cudaStream_t stream) {
-    if (B < 0 || ld < 200 || (ld & 7) || ld > 1024) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: bad B or ld (need ld >= 200, multiple of 8)");
+    if (B < 0 || ld < 200 || (ld & 7) || ld > 3328) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: bad B or ld (need ld >= 200, multiple of 8)");
     if (B == 0) return BG_OK;
     if (!boards52 || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: null pointer");
     const int cpr = (int)(ld / 8);
     long long tiles = (B + kBfRows - 1) / kBfRows;
-    long long grid = (long long)bg_sm_count() * 8;
+    long long grid = (long long)bg_sm_count() * 3;
     if (grid > tiles) grid = tiles;
-    encode_bf16_kernel<<<(unsigned)grid, kEncThreads, 0, stream>>>(boards52, flags, flag_all & 1, B, row_begin_dev, n_rows_dev, out, cpr);
+    encode_bf16_kernel<<<(unsigned)grid, kBfThreads, 0, stream>>>(boards52, flags, flag_all & 1, B, row_begin_dev, n_rows_dev, out, cpr);
     return bg_set_error(cudaGetLastError(), "bg_encode_bf16: launch");
 }
 

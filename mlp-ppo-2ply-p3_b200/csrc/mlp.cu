@@ -69,13 +69,15 @@ __device__ __forceinline__ float win_reward(const int8_t* b, int p) {
 // (leaf rule of the 2-ply search).
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
     const int8_t* __restrict__ boards, const int8_t* __restrict__ flags, int flag_all, int flip_flags, long long B,
-    const unsigned long long* __restrict__ n_rows_dev, const uint16_t* __restrict__ w1 /*[128][208] bf16*/,
+    const unsigned long long* __restrict__ row_begin_dev, const unsigned long long* __restrict__ n_rows_dev,
+    const uint16_t* __restrict__ w1 /*[128][208] bf16*/,
     const float* __restrict__ b1, const float* __restrict__ wv, float bv, int terminal_aware,
     float* __restrict__ values) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     MlpSmem& S = *reinterpret_cast<MlpSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (n_rows_dev) B = min(B, (long long)*n_rows_dev);
+    const long long begin = row_begin_dev ? min(B, (long long)*row_begin_dev) : 0;      // rows [begin, B)
 
     // ---- one-time setup: W1 into the operand layout, biases, mbarriers, TMEM (2 x 128 columns)
     for (int c = tid; c < kChunks * kHidden; c += kMlpThreads) {
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = S.tmem_base;
-    const long long n_tiles = (B + kTileM - 1) / kTileM;
+    const long long n_tiles = (B - begin + kTileM - 1) / kTileM;
 
     if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
         // ================= producers =================
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
         const int row = ptid & (kTileM - 1), half = ptid >> 7;  // two threads per position: chunks [13 half, 13 half + 13)
         // boards (and flags) of tile k+1 are prefetched with cp.async while tile k is being expanded
         auto prefetch = [&](long long tile, int s) {
-            const long long row0 = tile * kTileM;
+            const long long row0 = begin + tile * kTileM;
             const int rows = (int)min((long long)kTileM, B - row0);
             const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
             for (int i = ptid; i < rows * kBoardWords; i += kProdThreads) cp_async4(&S.boards[s][i], src + i);
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
             const int s = k & 1;
             const uint32_t it = (uint32_t)(k >> 1);
-            const long long row0 = tile * kTileM;
+            const long long row0 = begin + tile * kTileM;
             const int rows = (int)min((long long)kTileM, B - row0);
             const int fl = row < rows ? (int)(((flags ? flags[row0 + row] : flag_all) ^ flip_flags) & 1) : 0;
             cp_async_wait_all();                                // this thread's share of tile k's boards has landed
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
             const int s = k & 1;
             const uint32_t it = (uint32_t)(k >> 1);
-            const long long row0 = tile * kTileM;
+            const long long row0 = begin + tile * kTileM;
             const int rows = (int)min((long long)kTileM, B - row0);
             mbar_wait(&S.acc_full[s], it & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -226,9 +228,10 @@ extern "C" int bg_pack_w1(const float* fc1_weight, uint16_t* w1_bf16, void* stre
     return bg_set_error(cudaGetLastError(), "bg_pack_w1: launch");
 }
 
-extern "C" int bg_mlp_value(const int8_t* boards52, const int8_t* flags, int flag_all, int flip_flags, long long B,
-                            const unsigned long long* n_rows_dev, const uint16_t* w1_bf16, const float* b1,
-                            const float* wv, float bv, int terminal_aware, float* values, void* stream) {
+int bg::mlp_value_launch(const int8_t* boards52, const int8_t* flags, int flag_all, int flip_flags, long long B,
+                         const unsigned long long* row_begin_dev, const unsigned long long* n_rows_dev,
+                         const uint16_t* w1_bf16, const float* b1, const float* wv, float bv, int terminal_aware,
+                         float* values, cudaStream_t stream) {
     if (B < 0) return bg_set_error_msg(BG_ERR_INVALID, "bg_mlp_value: negative batch");
     if (B == 0) return BG_OK;
     if (!boards52 || !w1_bf16 || !b1 || !wv || !values) return bg_set_error_msg(BG_ERR_INVALID, "bg_mlp_value: null pointer");
@@ -238,7 +241,14 @@ extern "C" int bg_mlp_value(const int8_t* boards52, const int8_t* flags, int fla
     long long tiles = (B + kTileM - 1) / kTileM;
     long long grid = bg_sm_count();
     if (grid > tiles) grid = tiles;
-    mlp_value_kernel<<<(unsigned)grid, kMlpThreads, smem, (cudaStream_t)stream>>>(
-        boards52, flags, flag_all & 1, flip_flags & 1, B, n_rows_dev, w1_bf16, b1, wv, bv, terminal_aware, values);
+    mlp_value_kernel<<<(unsigned)grid, kMlpThreads, smem, stream>>>(
+        boards52, flags, flag_all & 1, flip_flags & 1, B, row_begin_dev, n_rows_dev, w1_bf16, b1, wv, bv, terminal_aware, values);
     return bg_set_error(cudaGetLastError(), "bg_mlp_value: launch");
+}
+
+extern "C" int bg_mlp_value(const int8_t* boards52, const int8_t* flags, int flag_all, int flip_flags, long long B,
+                            const unsigned long long* n_rows_dev, const uint16_t* w1_bf16, const float* b1,
+                            const float* wv, float bv, int terminal_aware, float* values, void* stream) {
+    return bg::mlp_value_launch(boards52, flags, flag_all, flip_flags, B, nullptr, n_rows_dev, w1_bf16, b1, wv, bv,
+                                terminal_aware, values, (cudaStream_t)stream);
 }

@@ -34,7 +34,7 @@ struct TeamScratch {
     uint32_t hash[HS];
     uint16_t off[CAP + 2];
     uint32_t rootw[kBoardWords];
-    int warp_cnt[T / 32];
+    int warp_cnt[2][T / 32];     // alternating buffers: one barrier per team_scan
     Node root;
     Root R;
     int bcast[4];
@@ -50,9 +50,10 @@ struct Team {
     TeamScratch<CAP, HS, T>& S;
     Root R;
     int tid, lane, warp;
+    int scan_buf;
     bool overflow;
 
-    __device__ Team(TeamScratch<CAP, HS, T>& s) : S(s), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), overflow(false) {}
+    __device__ Team(TeamScratch<CAP, HS, T>& s) : S(s), tid(threadIdx.x), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), scan_buf(0), overflow(false) {}
 
     __device__ __forceinline__ Node load(int i) const {
         uint4 k = S.key[i];
@@ -75,7 +76,9 @@ struct Team {
         for (int i = tid; i < HS; i += T) S.hash[i] = kEmptyT;
         __syncthreads();
     }
-    // exclusive prefix over the team of `v` in thread order; *total = team sum.  Two barriers.
+    // exclusive prefix over the team of `v` in thread order; *total = team sum.  ONE barrier: the per-warp counts
+    // alternate between two buffers, and a buffer is rewritten only two scans later, i.e. after every thread has
+    // passed the barrier of the scan in between and therefore finished reading it.
     __device__ __forceinline__ int team_scan(int v, int* total) {
         int inc = v;
 #pragma unroll
@@ -83,12 +86,13 @@ struct Team {
             int u = __shfl_up_sync(kFull, inc, o);
             if (lane >= o) inc += u;
         }
-        if (lane == 31) S.warp_cnt[warp] = inc;
+        int* cnt = S.warp_cnt[scan_buf];
+        scan_buf ^= 1;
+        if (lane == 31) cnt[warp] = inc;
         __syncthreads();
         int before = 0, sum = 0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) { int c = S.warp_cnt[w]; sum += c; if (w < warp) before += c; }
-        __syncthreads();
+        for (int w = 0; w < kWarps; ++w) { int c = cnt[w]; sum += c; if (w < warp) before += c; }
         *total = sum;
         return before + inc - v;
     }
@@ -172,8 +176,10 @@ struct Team {
                 if (use_set) S.hash[myslot] = (uint32_t)pos;                   // commit
             }
             nc += sum;
-            __syncthreads();
+            // no barrier here: the next iteration's first barrier (after its ckey stores / its scan) also orders these
+            // commits before any probe that could read them; nothing read in between is written above
         }
+        __syncthreads();                                                       // the new level is complete
         return nc;
     }
 

@@ -110,3 +110,69 @@ extern "C" int bg_update_legal_plays(const int8_t* boards52, const int8_t* playe
     if (e != cudaSuccess && rc == BG_OK) rc = bg_set_error(e, "bg_update_legal_plays: join");
     return rc;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// 2-ply inner step for M root afterstates: replies to all 21 rolls (K1, replicate mode) + leaf values (K4) + pass
+// values (K4 with the flag flipped), with K4 on the rows that are final after K1's tier 0 overlapped with the
+// overflow tiers, exactly like the encoder above.
+namespace {
+struct LeafCtx {
+    ForkJoin* fj;
+    cudaStream_t stream, side;
+    const int8_t* replies52;
+    const int8_t* row_players;
+    long long cap_rows;
+    const unsigned long long* rows_t0;
+    const uint16_t* w1; const float* b1; const float* wv; float bv;
+    float* leaf_values;
+};
+int leaves_after_tier0(void* user) {
+    LeafCtx* c = static_cast<LeafCtx*>(user);
+    cudaError_t e = cudaEventRecord(c->fj->tier0, c->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->side, c->fj->tier0, 0);
+    if (e != cudaSuccess) return bg_set_error(e, "bg_twoply_replies_values: fork");
+    return bg::mlp_value_launch(c->replies52, c->row_players, 0, 0, c->cap_rows, nullptr, c->rows_t0, c->w1, c->b1, c->wv, c->bv,
+                                1, c->leaf_values, c->side);
+}
+}  // namespace
+
+extern "C" int bg_twoply_replies_values(const int8_t* positions52, const int8_t* movers, long long M, int8_t* replies52,
+                                        long long reply_capacity_rows, int8_t* row_players, int32_t* counts,
+                                        long long* starts, unsigned long long* alloc_rows, int32_t* status,
+                                        void* workspace, size_t workspace_bytes, const uint16_t* w1_bf16, const float* b1,
+                                        const float* wv, float bv, float* leaf_values, float* pass_values,
+                                        void* side_stream, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_, side = (cudaStream_t)side_stream;
+    if (M < 0) return bg_set_error_msg(BG_ERR_INVALID, "bg_twoply_replies_values: negative batch");
+    if (M == 0) return BG_OK;
+    if (!counts || !row_players || !leaf_values || !pass_values || !workspace)
+        return bg_set_error_msg(BG_ERR_INVALID, "bg_twoply_replies_values: null pointer");
+    if (workspace_bytes < bg_movegen_workspace_bytes(M * 21))
+        return bg_set_error_msg(BG_ERR_INVALID, "bg_twoply_replies_values: workspace too small");
+    ForkJoin* fj = (side && side != stream) ? fork_join_events() : nullptr;
+    cudaStream_t aux = fj ? side : stream;
+    int rc = BG_OK;
+    if (fj) {
+        cudaError_t e = cudaEventRecord(fj->start, stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(side, fj->start, 0);
+        if (e != cudaSuccess) return bg_set_error(e, "bg_twoply_replies_values: fork");
+    }
+    // value of the position with the opponent to move = the roll's value when the opponent has no reply
+    rc = bg::mlp_value_launch(positions52, movers, 0, 1, M, nullptr, nullptr, w1_bf16, b1, wv, bv, 0, pass_values, aux);
+    if (rc != BG_OK) return rc;
+    unsigned long long* rows_t0 = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(workspace) + 40);
+    LeafCtx ctx{fj, stream, side, replies52, row_players, reply_capacity_rows, rows_t0, w1_bf16, b1, wv, bv, leaf_values};
+    bg::MovegenTier0Hook hook{rows_t0, leaves_after_tier0, &ctx};
+    rc = bg::movegen_run(positions52, movers, nullptr, M * 21, 21, 1, 2, nullptr, 0, replies52, reply_capacity_rows,
+                         row_players, nullptr, nullptr, counts, starts, alloc_rows, status, workspace, workspace_bytes,
+                         stream, fj ? &hook : nullptr);
+    if (rc == BG_OK)                                               // all rows (serial) / the rows appended by tiers 1, 2
+        rc = bg::mlp_value_launch(replies52, row_players, 0, 0, reply_capacity_rows, fj ? rows_t0 : nullptr, alloc_rows, w1_bf16,
+                                  b1, wv, bv, 1, leaf_values, stream);
+    if (fj) {
+        cudaError_t e = cudaEventRecord(fj->side_done, side);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, fj->side_done, 0);
+        if (e != cudaSuccess && rc == BG_OK) rc = bg_set_error(e, "bg_twoply_replies_values: join");
+    }
+    return rc;
+}

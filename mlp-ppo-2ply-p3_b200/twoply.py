@@ -42,12 +42,15 @@ class TwoPlySearch:
     """Persistent workspaces (no allocation and no host synchronisation inside the chunk loop): the only host
     syncs of search() are the row count after the root move generation and one status read at the end."""
 
-    def __init__(self, net: ValueNet, max_afterstates_per_chunk: int = 32768, replies_per_position: int = 40):
+    def __init__(self, net: ValueNet, max_afterstates_per_chunk: int = 32768, replies_per_position: int = 40,
+                 overlap: bool = True):
         self.net = net
         self.chunk = int(max_afterstates_per_chunk)
         self.rpp = int(replies_per_position)
         self.leaves_evaluated = 0
         self._bufs = None
+        self._side = None
+        self.overlap = bool(overlap)
 
     def _workspace(self, dev):
         if self._bufs is None or self._bufs["dev"] != dev or self._bufs["rpp"] != self.rpp:
@@ -66,14 +69,19 @@ class TwoPlySearch:
         b = self._workspace(dev)
         L = lib()
         b["alloc"].zero_()
+        net = self.net
+        if self._side is None and self.overlap:
+            self._side = torch.cuda.Stream(device=dev)
         with torch.cuda.device(dev):
-            check(L.bg_movegen_replies_slab(A.data_ptr(), movers.data_ptr(), M, 0, b["replies"].data_ptr(), b["cap"],
-                                            b["rowp"].data_ptr(), None, None, b["counts"].data_ptr(), b["starts"].data_ptr(),
-                                            b["alloc"].data_ptr(), b["ws"].status.data_ptr(), b["ws"].buf.data_ptr(),
-                                            b["ws"].nbytes, _stream()), "bg_movegen_replies_slab")
+            # K1 (replies to the 21 rolls) + K4 (leaf values, pass values) in one call; K4 overlaps K1's overflow tiers
+            check(L.bg_twoply_replies_values(A.data_ptr(), movers.data_ptr(), M, b["replies"].data_ptr(), b["cap"],
+                                             b["rowp"].data_ptr(), b["counts"].data_ptr(), b["starts"].data_ptr(),
+                                             b["alloc"].data_ptr(), b["ws"].status.data_ptr(), b["ws"].buf.data_ptr(),
+                                             b["ws"].nbytes, net.w1_bf16.data_ptr(), net.b1.data_ptr(), net.wv.data_ptr(),
+                                             net.bv, b["leaf_v"].data_ptr(), b["pass_v"].data_ptr(),
+                                             self._side.cuda_stream if self.overlap else None, _stream()),
+                  "bg_twoply_replies_values")
         b["leaves"].add_(b["alloc"])
-        self.net.values(b["replies"], b["rowp"], terminal_aware=True, n_rows_dev=b["alloc"], out=b["leaf_v"])
-        self.net.values(A, movers, flip_flags=True, out=b["pass_v"])
         with torch.cuda.device(dev):
             check(L.bg_twoply_scores(b["leaf_v"].data_ptr(), b["starts"].data_ptr(), b["counts"].data_ptr(),
                                      b["pass_v"].data_ptr(), A.data_ptr(), movers.data_ptr(), M, out.data_ptr(), _stream()),

@@ -33,6 +33,12 @@ net = bg_b200.ValueNet.random_init(dev)
 vb = torch.empty(rows, dtype=torch.float32, device=dev)
 t = timed(lambda: net.values(env.after52[:rows], env.row_players[:rows], out=vb))
 print(f"K4 mlp_value {rows} rows        : {t:8.1f} us   -> {rows/t*1e6/1e9:.2f} G pos/s, {rows*53504/t*1e6/1e12:.0f} TFLOP/s")
+pnet = bg_b200.PolicyValueNet.random_init(dev)
+pout = (torch.empty(N, dtype=torch.int32, device=dev), torch.empty(N, dtype=torch.float32, device=dev), torch.empty(N, dtype=torch.float32, device=dev))
+t = timed(lambda: pnet.act(env.boards52, env.players, env.legal_counts, seed=1, step=2, out=pout))
+print(f"N1 policy_sample {N} rows       : {t:8.1f} us   -> {N/t*1e6/1e9:.2f} G pos/s, {N*(53504+2*128*512)/t*1e6/1e12:.0f} TFLOP/s")
+t = timed(lambda: pnet.act(env.boards52, env.players, env.legal_counts, seed=1, step=2, greedy=True, out=pout))
+print(f"N1 policy greedy {N} rows       : {t:8.1f} us")
 env.random_actions(7, 999, out=acts)
 print(f"K2 step                        : {timed(lambda: env._apply_actions(acts), 5):8.1f} us (mutates state)")
 env._refresh_legal_moves(); env.check_status()
