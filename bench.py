@@ -231,20 +231,37 @@ def run_engine(args):
     if world > 1:
         dist.barrier()
     stream = torch.cuda.current_stream()
-    h_counts.copy_(env.legal_counts, non_blocking=True)
-    t0 = time.perf_counter()
-    for k in range(E):
-        stream.synchronize()                                                    # results of the previous step are on the host
-        np.multiply(u[k], h_counts.numpy(), out=u[k])                           # host-side policy: uniform over the legal plays
-        h_acts.numpy()[:] = u[k]                                                # (float -> int32 truncation)
-        obs, rew, done, infos = env.step(h_acts, with_features=feats)           # H2D inside; obs stays on the device
-        h_rew.copy_(rew, non_blocking=True); h_done.copy_(done, non_blocking=True)      # D2H into pinned memory
+    e2e_segments = []
+    for seg in range(3):                                                        # three segments of E steps; the best one is reported
         h_counts.copy_(env.legal_counts, non_blocking=True)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for k in range(E):
+            stream.synchronize()                                                # results of the previous step are on the host
+            np.multiply(u[k], h_counts.numpy(), out=u[k])                       # host-side policy: uniform over the legal plays
+            h_acts.numpy()[:] = u[k]                                            # (float -> int32 truncation)
+            obs, rew, done, infos = env.step(h_acts, with_features=feats)       # H2D inside; obs stays on the device
+            h_rew.copy_(rew, non_blocking=True); h_done.copy_(done, non_blocking=True)  # D2H into pinned memory
+            h_counts.copy_(env.legal_counts, non_blocking=True)
+        torch.cuda.synchronize()
+        e2e_segments.append(time.perf_counter() - t0)
+        u = rng.random((E, N), dtype=np.float32)
+    e2e_s = min(e2e_segments)
     env.check_status()
 
     extra = run_extras(bg_b200, env, torch, dev, args) if (world == 1 and not args.no_extras) else None
+    twoply_all = None
+    if world > 1 and not args.no_extras:                      # 2-ply on every rank's own roots (shards of the roots, replicas of the net)
+        tp2 = run_twoply(bg_b200, env, torch, dev, args)
+        agg = torch.tensor([tp2["root_afterstates"], tp2["leaves"], tp2["roots"]], dtype=torch.float64, device=dev)
+        tmax = torch.tensor([tp2["seconds"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        a, l, r = agg.tolist(); sec = float(tmax.item())
+        twoply_all = {"roots": int(r), "root_afterstates": int(a), "leaves": int(l), "seconds": sec, "root_positions_per_s": r / sec,
+              "root_afterstates_per_s": a / sec, "leaves_per_s": l / sec,
+              "note": f"{world} ranks, each its own {args.twoply_roots} roots; sum over ranks / max time over ranks (best of 3)"}
 
     tm = torch.tensor([ms, e2e_s * 1e3, k1_ms, k1_alone_ms], dtype=torch.float64, device=dev)
     rw = torch.tensor([rows_per_step], dtype=torch.float64, device=dev)
@@ -294,13 +311,16 @@ def run_engine(args):
                              "(ncu --set full, profiles/): below the algorithmic bytes because the afterstate rows are still in "
                              "the 126 MB L2 when the encoder reads them"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * N * 4, "d2h_bytes_per_step": world * N * 9,
-                "steps": E, "what": "B200BackgammonVecEnv.step(actions from pinned host memory); rewards, dones and "
+                "steps": E, "segments_ms_per_step": [x * 1e3 / E for x in e2e_segments],
+                "what": "best of 3 segments (host-side jitter); B200BackgammonVecEnv.step(actions from pinned host memory); rewards, dones and "
                                     "legal-play counts copied to the host every step; observations stay on the device "
                                     "as the reference API returns them"},
         "gpu_launches": n_launch, "clocks": clocks,
     }
     if extra is not None:
         line["extra"] = extra
+    if twoply_all is not None:
+        line["extra"] = {"twoply": twoply_all}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n, el = cpu_rollout(args.cpu_seconds, threads)
@@ -358,7 +378,13 @@ def run_extras(bg_b200, env, torch, dev, args):
     t = timed(ppo_rollout_step, 30)
     out["ppo_rollout"] = {"env_steps_per_s": N / t, "ms_per_step": t * 1e3, "games": N,
                           "what": "sampled policy (fused policy/value kernel) -> K2 -> K1, no feature tensors in HBM"}
-    # 2-ply (configs[3]): roots = the first R games' positions with their actual dice
+    out["twoply"] = run_twoply(bg_b200, env, torch, dev, args, net)
+    return out
+
+
+def run_twoply(bg_b200, env, torch, dev, args, net=None):
+    """2-ply (configs[3]): roots = the first R games' positions with their actual dice"""
+    net = net or bg_b200.ValueNet.random_init(dev, seed=0)
     R = min(args.twoply_roots, env.num_envs)
     search = bg_b200.TwoPlySearch(net, max_afterstates_per_chunk=args.twoply_chunk)
     b, p, d = env.boards52[:R].clone(), env.players[:R].clone(), env.dice[:R].clone()
@@ -371,12 +397,11 @@ def run_extras(bg_b200, env, torch, dev, args):
         best, scores, offsets, A = search.search(b, p, d)
         torch.cuda.synchronize()
         t = min(t, time.perf_counter() - t0)
-    out["twoply"] = {"roots": R, "root_afterstates": int(A.shape[0]), "leaves": int(search.leaves_evaluated), "seconds": t,
-                     "root_positions_per_s": R / t, "root_afterstates_per_s": A.shape[0] / t,
-                     "leaves_per_s": search.leaves_evaluated / t,
-                     "note": "best of 3, wall clock incl. host orchestration; a 2-ply position = one root afterstate fully expanded "
-                             "(21 opponent rolls x replies, leaves MLP-evaluated)"}
-    return out
+    return {"roots": R, "root_afterstates": int(A.shape[0]), "leaves": int(search.leaves_evaluated), "seconds": t,
+            "root_positions_per_s": R / t, "root_afterstates_per_s": A.shape[0] / t,
+            "leaves_per_s": search.leaves_evaluated / t,
+            "note": "best of 3, wall clock incl. host orchestration; a 2-ply position = one root afterstate fully expanded "
+                    "(21 opponent rolls x replies, leaves MLP-evaluated)"}
 
 
 def main():
