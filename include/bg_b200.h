@@ -205,6 +205,17 @@ int bg_policy_sample(const int8_t* boards52, const int8_t* flags, int flag_all, 
 int bg_gae(const float* rewards, const uint8_t* dones, const float* values /*nullable*/, const float* last_values /*nullable*/,
            int T, long long N, float gamma, float lambda, float* returns, float* advantages, void* stream);
 
+/* N2  loss of one PPO epoch (agent/ppo_agent.py:271-299: log(mask + 1e-45), softmax, log_prob, entropy, ratio, clipped
+ * surrogate, MSE, their weighted sum) and its gradient w.r.t. the network outputs, one pass over the logits:
+ *   logits / dlogits: [B][ld] bf16 (logits_bf16 = 1) or f32, ld >= 500 and a multiple of 4; values, returns, advantages,
+ *   old_log_probs: [B] f32; counts: legal slots per sample (prefix mask); actions: taken slot.
+ *   dlogits = d loss / d logits, dvalues = d loss / d values (both already divided by B);
+ *   sums[0..2] += sum_i policy term, sum_i (v - R)^2, sum_i entropy  (caller zeroes; loss = (s0 + c_v s1 - c_e s2) / B). */
+int bg_ppo_loss_grad(const void* logits, int logits_bf16, long long ld, const float* values, const int32_t* counts,
+                     const int32_t* actions, const float* old_log_probs, const float* advantages, const float* returns,
+                     long long B, float eps_clip, float value_coef, float entropy_coef, void* dlogits, float* dvalues,
+                     float* sums, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K5  2-ply search (the reference's own 2-ply, moves/expect_minmax.py:1-206, is
  * commented-out code, so the definition is the build's, on the reference's live primitives).

@@ -58,17 +58,63 @@ class PPOConfig:                                   # src/agent/config.py:4-22
 
 def policy_value_forward(params, x):
     """BackgammonPolicyNetwork.forward (policy_network.py:58-75) on features x (B,198+) -> logits (B,500), values (B,)"""
-    h = F.relu(F.linear(x[:, :198], params["fc1.weight"], params["fc1.bias"]))
+    w1 = params["fc1.weight"]
+    if x.shape[1] > w1.shape[1]:                   # K3's bf16 rows are padded to 208 columns (zeros): pad the weight, not a copy of x
+        w1 = F.pad(w1, (0, x.shape[1] - w1.shape[1]))
+    h = F.relu(F.linear(x, w1, params["fc1.bias"]))
     logits = F.linear(h, params["action_head.weight"], params["action_head.bias"])
     values = F.linear(h, params["value_head.weight"], params["value_head.bias"]).squeeze(-1)
     return logits, values
 
 
+class _FusedPPOLoss(torch.autograd.Function):
+    """bg_ppo_loss_grad: the masked-softmax / clipped-surrogate / MSE / entropy loss and its gradient w.r.t. the logits
+    and values in one pass over the logits (csrc/ppo.cu)."""
+
+    @staticmethod
+    def forward(ctx, logits, values, counts, actions, old_logp, adv, returns, eps_clip, value_coef, entropy_coef):
+        if logits.dtype not in (torch.bfloat16, torch.float32):
+            logits = logits.float()
+        logits = logits.contiguous()
+        B = logits.shape[0]
+        dev = logits.device
+        v32 = values.float().contiguous()
+        dlogits, dvalues = torch.empty_like(logits), torch.empty(B, dtype=torch.float32, device=dev)
+        sums = torch.zeros(3, dtype=torch.float32, device=dev)
+        f = lambda t, dt: t.to(dt).contiguous()
+        with torch.cuda.device(dev):
+            check(lib().bg_ppo_loss_grad(logits.data_ptr(), int(logits.dtype == torch.bfloat16), logits.shape[1], v32.data_ptr(),
+                                         f(counts, torch.int32).data_ptr(), f(actions, torch.int32).data_ptr(),
+                                         f(old_logp, torch.float32).data_ptr(), f(adv, torch.float32).data_ptr(),
+                                         f(returns, torch.float32).data_ptr(), B, float(eps_clip), float(value_coef),
+                                         float(entropy_coef), dlogits.data_ptr(), dvalues.data_ptr(), sums.data_ptr(), _stream()),
+                  "bg_ppo_loss_grad")
+        ctx.save_for_backward(dlogits, dvalues)
+        ctx.values_dtype = values.dtype
+        means = sums / B
+        loss = means[0] + value_coef * means[1] - entropy_coef * means[2]
+        return loss, means[0], means[1], means[2]
+
+    @staticmethod
+    def backward(ctx, g, *_unused):
+        dlogits, dvalues = ctx.saved_tensors
+        return (dlogits * g.to(dlogits.dtype), (dvalues * g).to(ctx.values_dtype), None, None, None, None, None, None, None, None)
+
+
 def ppo_loss(params, x, counts, actions, old_logp, returns, advantages, eps_clip, value_coef, entropy_coef,
-             autocast=True):
+             autocast=True, fused=None):
     """The loss of one epoch of BackgammonPPOAgent.update (ppo_agent.py:268-299).  counts = legal slots per sample
-    (prefix mask, backgammon_env.py:228-231).  Runs on any device (the CPU path exists for the host-logic tests)."""
+    (prefix mask, backgammon_env.py:228-231).  On CUDA the part after the two linear layers is ONE kernel
+    (bg_ppo_loss_grad; fused=False keeps the torch chain, which is also the CPU path of the host-logic tests)."""
     dev_type = x.device.type
+    if fused is None:
+        fused = x.is_cuda
+    if fused:
+        with torch.autocast(device_type=dev_type, dtype=torch.bfloat16, enabled=autocast):
+            logits, values = policy_value_forward(params, x)
+        loss, pl, vl, ent = _FusedPPOLoss.apply(logits, values, counts, actions, old_logp, advantages, returns, eps_clip,
+                                                value_coef, entropy_coef)
+        return loss, pl.detach(), vl.detach(), ent.detach()
     with torch.autocast(device_type=dev_type, dtype=torch.bfloat16, enabled=autocast):
         logits, values = policy_value_forward(params, x)
         slot = torch.arange(ACTIONS, device=x.device)[None, :]

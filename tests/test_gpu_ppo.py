@@ -88,3 +88,34 @@ def test_trainer_smoke_and_checkpoint_roundtrip(tmp_path):
     assert all(torch.equal(x, y) for x, y in zip(a1, a2))
     ev = evaluate_vs_random(net, num_games=256, device=dev)
     assert ev["games"] == 256 and 0.0 <= ev["win_rate"] <= 1.0
+
+
+def test_fused_loss_kernel_matches_torch_chain():
+    """bg_ppo_loss_grad (one pass over the logits) == the torch restatement of ppo_agent.py:271-299, values and gradients"""
+    import bg_b200
+    from bg_b200.ppo import ppo_loss
+    g = np.load(GOLDEN)
+    sd0 = {k[3:]: torch.tensor(g[k]).cuda() for k in g.files if k.startswith("w0.")}
+    t = lambda k, dt: torch.tensor(g[k]).to(dt).cuda()
+    x, counts, actions, logp, values = t("obs", torch.float32), t("counts", torch.int32), t("actions", torch.int32), t("logp", torch.float32), t("values", torch.float32)
+    ret = t("returns_interleaved", torch.float32)
+    ret = (ret - ret.mean()) / (ret.std() + 1e-5)
+    adv = ret - values
+    logp = logp + 0.3 * torch.randn_like(logp)                   # push some ratios outside the clip range
+    for autocast, tol in ((False, 2e-5), (True, 3e-3)):
+        grads = []
+        for fused in (False, True):
+            p = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+            loss, pl, vl, ent = ppo_loss(p, x, counts, actions, logp, ret, adv, 0.25, 0.5, 0.15, autocast=autocast, fused=fused)
+            loss.backward()
+            grads.append((loss.item(), pl.item(), vl.item(), ent.item(), {k: v.grad.clone() for k, v in p.items()}))
+        a, b = grads
+        assert max(abs(a[i] - b[i]) for i in range(4)) < tol, (a[:4], b[:4])
+        for k in a[4]:
+            scale = a[4][k].abs().max().item() + 1e-8
+            assert (a[4][k] - b[4][k]).abs().max().item() < (1e-4 if not autocast else 3e-2) * scale, k
+    # want: the reference's own epoch losses (lr = 0 golden) through the fused path as well
+    p = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    loss, pl, vl, ent = ppo_loss(p, x, counts, actions, t("logp", torch.float32), ret, adv, 0.25, 0.5, float(g["entropy_coef"]), autocast=True, fused=True)
+    got = np.array([pl.item(), vl.item(), ent.item(), loss.item()])
+    assert np.abs(got - g["loss_lr0"]).max() < 5e-3, (got, g["loss_lr0"])
