@@ -40,6 +40,7 @@ struct Node {
     unsigned long long hi;  // bits 0..31 own points 16..23; bits 32..35 own bar; bits 36..39 own off
     uint32_t occ;           // bit p set <=> own count at point p > 0
     uint32_t hit;           // bit p set <=> the opponent blot on point p has been hit this turn
+    uint32_t last;          // source point of the sub-move that first produced this board (31: none / bar / bear-off)
 };
 
 // Per-root (warp-uniform) constants.
@@ -48,6 +49,10 @@ struct Root {
     uint32_t blot;    // opponent has exactly 1 man on point p (conditions.py:51-53)
     int player;       // mover: 0 = PLAYER1 (moves +), 1 = PLAYER2 (moves -)
     int tot15;        // own points + bar + off == 15 (needed by all_checkers_home, conditions.py:147)
+    // duplicate pruning (prune_mask below)
+    int prune;        // the whole turn stays in the NORMAL state: no man on the bar, too many men outside home to bear off
+    uint32_t mA;      // non-doubles: ordinary sources of the LARGER die at the root
+    uint32_t cnt2;    // own count at point p >= 2 at the root
 };
 
 BG_HD int node_bar(const Node& n) { return (int)((n.hi >> 32) & 15ull); }
@@ -88,6 +93,23 @@ BG_HD void one_die(const Node& n, const Root& R, int d, uint32_t& mask, int& spe
 // Index of the j-th (0-based) set bit of a 24-bit mask, j < popc(m).  Branch-free 12/6/3 bisection on popcounts
 // plus a 2-bit-per-entry table for the last 3 bits (a data-dependent "clear lowest bit j times" loop cost ~5
 // instructions per iteration of the slowest lane of the warp).
+// ---------------------------------------------------------------------------------------------------------------
+// Candidates that are PROVABLY duplicates of an earlier candidate of the same level can be dropped before they are
+// built: that changes neither the surviving boards nor their order (the reference keeps the first sequence that
+// reaches a board, handle_moves.py:313-341).  Valid while every list of the turn is a NORMAL list (ascending
+// sources, move_logic.py:47-92): no man on the bar and bearing off out of reach (Root::prune).
+//
+// Doubles.  Board P was first reached by a sequence ending with the move from point m.  A further move from s < m
+// whose man does not owe its presence to m's arrival (NOT (s == dest(m) and P has exactly one man on s)) can be
+// played BEFORE m: (..., s) reaches a board P'' whose first sequence is lexicographically smaller than P's, so
+// P'' precedes P in the level and (P'', m) produced the same board earlier.
+// Non-doubles.  Smaller-die-first board (root + lo from s2), then the larger die from s1: if s1 is a larger-die
+// source at the root and the two moves use different men (s1 != s2 or two men on s2), the larger-die-first pass
+// (which is enumerated first) already produced the board as (hi from s1, lo from s2).
+// Everything else still goes through the exact dedupe.  tests: the rule never drops a first occurrence on 97 M
+// candidates of random-play positions and on the golden corpora (tests/test_kernel_algorithm_cpu.py).
+BG_HD uint32_t prune_mask(uint32_t mask, const Node& n, const Root& R, int d, bool doubles, bool smaller_die_first_parent);
+
 BG_HD int nth_set_bit(uint32_t m, int j) {
     int pos = 0, t;
     t = BG_POPC(m & 0xFFFu);          if (j >= t) { j -= t; pos = 12; }
@@ -101,12 +123,27 @@ BG_HD int nth_set_bit(uint32_t m, int j) {
     return pos + (int)((kSel3 >> (2 * (r * 3 + (uint32_t)j))) & 3ull);
 }
 
+BG_HD uint32_t prune_mask(uint32_t mask, const Node& n, const Root& R, int d, bool doubles, bool smaller_die_first_parent) {
+    if (!R.prune || n.last >= 24u) return mask;
+    if (doubles) {
+        uint32_t drop = mask & ((1u << n.last) - 1u);
+        if (R.player != 0) {                                         // PLAYER2 lands below its source
+            const int dest = (int)n.last - d;
+            if (dest >= 0 && ((drop >> dest) & 1u) && node_count(n, dest) == 1) drop &= ~(1u << dest);
+        }
+        return mask & ~drop;
+    }
+    if (!smaller_die_first_parent) return mask;
+    return mask & ~(R.mA & ~((1u << n.last) & ~R.cnt2));
+}
+
 // Apply move number j of the (mask, special) list with die d  (move_checker, immutable_board.py:42-89).
 BG_HD Node apply_move(const Node& n, const Root& R, int d, uint32_t mask, int special, int j) {
     Node c = n;
     int nm = BG_POPC(mask);
     int s, t;
-    if (j < nm) { s = nth_set_bit(mask, j); t = R.player == 0 ? s + d : s - d; }
+    c.last = 31u;
+    if (j < nm) { s = nth_set_bit(mask, j); t = R.player == 0 ? s + d : s - d; c.last = (uint32_t)s; }
     else if (special == kBar) { s = kBar; t = R.player == 0 ? d - 1 : 24 - d; }
     else { s = special; t = kOff; }
     if (s == kBar) c.hi -= 1ull << 32;

@@ -64,13 +64,15 @@ struct Warp {
         n.lo = (unsigned long long)k.x | ((unsigned long long)k.y << 32);
         n.hi = (unsigned long long)k.z | ((unsigned long long)(k.w >> 24) << 32);
         n.hit = k.w & 0xFFFFFFu;
-        n.occ = S.occ[i];
+        const uint32_t o = S.occ[i];                                 // occupancy | last source << 24
+        n.occ = o & 0xFFFFFFu;
+        n.last = o >> 24;
         return n;
     }
     static __device__ __forceinline__ uint4 key_of(const Node& n) {
         return make_uint4((uint32_t)n.lo, (uint32_t)(n.lo >> 32), (uint32_t)n.hi, n.hit | ((uint32_t)(n.hi >> 32) << 24));
     }
-    __device__ __forceinline__ void store(int i, const Node& n) { S.key[i] = key_of(n); S.occ[i] = n.occ; }
+    __device__ __forceinline__ void store(int i, const Node& n) { S.key[i] = key_of(n); S.occ[i] = n.occ | (n.last << 24); }
     __device__ __forceinline__ bool same(int i, const uint4& k) const {
         uint4 e = S.key[i];
         return e.x == k.x && e.y == k.y && e.z == k.z && e.w == k.w;
@@ -108,6 +110,7 @@ struct Warp {
                 Node n = load(pbase + i);
                 uint32_t mask; int special;
                 one_die(n, R, i < split ? dA : dB, mask, special);
+                mask = prune_mask(mask, n, R, dA, dA == dB, i >= split);     // drop provably duplicate candidates
                 cnt = __popc(mask) + (special >= 0);
                 S.pm[i] = mask | ((uint32_t)(special + 1) << 24);
             }
@@ -150,7 +153,7 @@ struct Warp {
             int idx = c0 + lane;
             bool valid = idx < total;
             Node ch;
-            ch.lo = ~0ull - (unsigned long long)lane; ch.hi = 0; ch.hit = 0; ch.occ = 0;   // impossible board
+            ch.lo = ~0ull - (unsigned long long)lane; ch.hi = 0; ch.hit = 0; ch.occ = 0; ch.last = 31u;   // impossible board
             if (valid) {
                 int lo = 0, hi = np - 1;                       // largest parent with off[parent] <= idx
                 while (lo < hi) {
@@ -193,6 +196,7 @@ struct Warp {
             uint32_t mA, mB; int sA, sB;
             one_die(root, R, dhi, mA, sA);
             one_die(root, R, dlo, mB, sB);
+            R.mA = mA;
             nA = __popc(mA) + (sA >= 0);
             const int nB = __popc(mB) + (sB >= 0);
             if (lane < nA) store(CAP + lane, apply_move(root, R, dhi, mA, sA, lane));
@@ -307,6 +311,14 @@ __global__ void __launch_bounds__(256) movegen_kernel(
         Node root;
         root.occ = __ballot_sync(kFull, ownc > 0) & 0xFFFFFFu;
         root.hit = 0;
+        root.last = 31u;
+        W.R.cnt2 = __ballot_sync(kFull, ownc >= 2) & 0xFFFFFFu;
+        W.R.mA = 0;
+        {   // duplicate pruning is valid while the whole turn stays in the NORMAL state (bg_device.cuh, prune_mask)
+            const bool home = player ? lane < 6 : (lane >= 18 && lane < 24);
+            const int outside = __reduce_add_sync(kFull, home ? 0 : ownc);
+            W.R.prune = ownbar == 0 && outside >= (d0 == d1 ? 4 : 2);
+        }
         uint32_t nib = (uint32_t)(ownc & 15) << (4 * (p & 7));
         uint32_t w0 = __reduce_or_sync(kFull, (lane < 8) ? nib : 0u);
         uint32_t w1 = __reduce_or_sync(kFull, (lane >= 8 && lane < 16) ? nib : 0u);

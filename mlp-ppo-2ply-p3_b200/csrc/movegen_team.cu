@@ -61,7 +61,9 @@ struct Team {
         n.lo = (unsigned long long)k.x | ((unsigned long long)k.y << 32);
         n.hi = (unsigned long long)k.z | ((unsigned long long)(k.w >> 24) << 32);
         n.hit = k.w & 0xFFFFFFu;
-        n.occ = S.occ[i];
+        const uint32_t o = S.occ[i];                                 // occupancy | last source << 24
+        n.occ = o & 0xFFFFFFu;
+        n.last = o >> 24;
         return n;
     }
     static __device__ __forceinline__ uint4 key_of(const Node& n) {
@@ -97,7 +99,7 @@ struct Team {
         return before + inc - v;
     }
 
-    __device__ int count_moves(int pbase, int np, int d) {
+    __device__ int count_moves(int pbase, int np, int d, bool dbl, bool second_of_b) {
         int base = 0;
         for (int i0 = 0; i0 < np; i0 += T) {
             int i = i0 + tid;
@@ -106,6 +108,7 @@ struct Team {
                 Node n = load(pbase + i);
                 uint32_t mask; int special;
                 one_die(n, R, d, mask, special);
+                mask = prune_mask(mask, n, R, d, dbl, second_of_b);          // drop provably duplicate candidates (bg_device.cuh)
                 cnt = __popc(mask) + (special >= 0);
                 S.pm[i] = mask | ((uint32_t)(special + 1) << 24);
             }
@@ -123,7 +126,7 @@ struct Team {
         for (int c0 = 0; c0 < total; c0 += T) {
             int idx = c0 + tid;
             bool valid = idx < total;
-            Node ch; ch.lo = 0; ch.hi = 0; ch.hit = 0; ch.occ = 0;
+            Node ch; ch.lo = 0; ch.hi = 0; ch.hit = 0; ch.occ = 0; ch.last = 31u;
             if (valid) {
                 int lo = 0, hi = np - 1;
                 while (lo < hi) {
@@ -172,7 +175,7 @@ struct Team {
             if (nc + sum > CAP) { overflow = true; return nc; }
             if (keep) {
                 int pos = cbase + nc + wbefore + __popc(surv & ((1u << lane) - 1u));
-                S.key[pos] = k; S.occ[pos] = ch.occ;
+                S.key[pos] = k; S.occ[pos] = ch.occ | (ch.last << 24);
                 if (use_set) S.hash[myslot] = (uint32_t)pos;                   // commit
             }
             nc += sum;
@@ -186,7 +189,7 @@ struct Team {
     // same stage loop as Warp::generate (movegen.cu); every control variable is uniform across the CTA
     __device__ void generate(const Node& root, int d0, int d1, int& obase, int& n) {
         obase = 0; n = 0;
-        if (tid == 0) { S.key[kRoot] = key_of(root); S.occ[kRoot] = root.occ; }
+        if (tid == 0) { S.key[kRoot] = key_of(root); S.occ[kRoot] = root.occ | (31u << 24); }
         const bool dbl = d0 == d1;
         const int dhi = max(d0, d1), dlo = min(d0, d1);
         if (!dbl) clear_hash(); else __syncthreads();
@@ -195,7 +198,7 @@ struct Team {
         bool lenA2 = false, lenB2 = false;
         for (int stage = 0; stage < 4; ++stage) {
             const int d = dbl ? d0 : ((stage == 0 || stage == 3) ? dhi : dlo);
-            const int total = count_moves(pbase, np, d);
+            const int total = count_moves(pbase, np, d, dbl, !dbl && stage == 3);
             const bool first = !dbl && (stage & 1) == 0;
             int cbase = 0, nc0 = 0;
             bool use_set = true, do_expand = true;
@@ -228,7 +231,7 @@ struct Team {
                         unsigned surv = __ballot_sync(kFull, keep);
                         if (keep) {
                             int pos = nF + __popc(surv & ((1u << lane) - 1u));
-                            S.key[pos] = k; S.occ[pos] = c.occ;
+                            S.key[pos] = k; S.occ[pos] = c.occ | (c.last << 24);
                             uint32_t s = hash_key(k) & (HS - 1);
                             while (atomicCAS(&S.hash[s], kEmptyT, (uint32_t)pos) != kEmptyT) s = (s + 1) & (HS - 1);
                         }
@@ -302,6 +305,14 @@ __global__ void __launch_bounds__(T) movegen_team_kernel(
             R.blot = __ballot_sync(kFull, oppc == 1) & 0xFFFFFFu;
             root.occ = __ballot_sync(kFull, ownc > 0) & 0xFFFFFFu;
             root.hit = 0;
+            root.last = 31u;
+            R.cnt2 = __ballot_sync(kFull, ownc >= 2) & 0xFFFFFFu;
+            {   // duplicate pruning is valid while the whole turn stays in the NORMAL state (bg_device.cuh, prune_mask)
+                const bool home = player ? lane < 6 : (lane >= 18 && lane < 24);
+                const int outside = __reduce_add_sync(kFull, home ? 0 : ownc);
+                R.prune = ownbar == 0 && outside >= (d0 == d1 ? 4 : 2);
+                R.mA = 0;
+            }
             uint32_t nib = (uint32_t)(ownc & 15) << (4 * (p & 7));
             uint32_t w0 = __reduce_or_sync(kFull, (lane < 8) ? nib : 0u);
             uint32_t w1 = __reduce_or_sync(kFull, (lane >= 8 && lane < 16) ? nib : 0u);
@@ -309,6 +320,7 @@ __global__ void __launch_bounds__(T) movegen_team_kernel(
             root.lo = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
             root.hi = (unsigned long long)w2 | ((unsigned long long)((ownbar & 15) | ((ownoff & 15) << 4)) << 32);
             R.tot15 = (__reduce_add_sync(kFull, ownc) + ownbar + ownoff) == 15;
+            if (d0 != d1) { uint32_t mA; int sA; one_die(root, R, max(d0, d1), mA, sA); R.mA = mA; }   // larger-die sources at the root
             if (lane == 0) { S.root = root; S.R = R; }   // (tier 0 already rejected malformed boards)
         }
         __syncthreads();

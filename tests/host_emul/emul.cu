@@ -9,11 +9,13 @@ using namespace bg;
 static bool same(const Node& a, const Node& b) { return a.lo == b.lo && a.hi == b.hi && a.hit == b.hit; }
 
 // children of `parents` with die d appended to `out` (deduped against everything already in `out`), reference order
-static int expand(const std::vector<Node>& parents, const Root& R, int d, std::vector<Node>& out) {
+static int expand(const std::vector<Node>& parents, const Root& R, int d, std::vector<Node>& out, bool doubles = false,
+                  bool second_of_b = false) {
     int total = 0;
     for (const Node& p : parents) {
         uint32_t mask; int special;
         one_die(p, R, d, mask, special);
+        mask = prune_mask(mask, p, R, d, doubles, second_of_b);      // the kernel's duplicate pruning (bg_device.cuh)
         int cnt = BG_POPC(mask) + (special >= 0);
         total += cnt;
         for (int j = 0; j < cnt; ++j) {
@@ -31,10 +33,12 @@ extern "C" int emul_legal_moves(const int8_t* b52, int player, int d0, int d1, i
     memcpy(rootw, b52, 52);
     const int8_t* own = b52 + (player ? 24 : 0);
     const int8_t* opp = b52 + (player ? 0 : 24);
-    Root R; R.player = player; R.block = 0; R.blot = 0;
-    Node root; root.lo = 0; root.hi = 0; root.occ = 0; root.hit = 0;
-    int total = 0;
+    Root R; R.player = player; R.block = 0; R.blot = 0; R.mA = 0; R.cnt2 = 0;
+    Node root; root.lo = 0; root.hi = 0; root.occ = 0; root.hit = 0; root.last = 31u;
+    int total = 0, outside = 0;
     for (int p = 0; p < 24; ++p) {
+        if (own[p] >= 2) R.cnt2 |= 1u << p;
+        if (!(player ? p < 6 : p >= 18)) outside += own[p];
         if (opp[p] >= 2) R.block |= 1u << p;
         if (opp[p] == 1) R.blot |= 1u << p;
         if (own[p] > 0) root.occ |= 1u << p;
@@ -45,6 +49,8 @@ extern "C" int emul_legal_moves(const int8_t* b52, int player, int d0, int d1, i
     int ownbar = b52[48 + player], ownoff = b52[50 + player];
     root.hi |= (unsigned long long)((ownbar & 15) | ((ownoff & 15) << 4)) << 32;
     R.tot15 = (total + ownbar + ownoff) == 15;
+    R.prune = ownbar == 0 && outside >= (d0 == d1 ? 4 : 2);
+    if (d0 != d1) { uint32_t mA; int sA; one_die(root, R, d0 > d1 ? d0 : d1, mA, sA); R.mA = mA; }
 
     std::vector<Node> F;     // result
     size_t from = 0;
@@ -67,7 +73,7 @@ extern "C" int emul_legal_moves(const int8_t* b52, int player, int d0, int d1, i
             if (!L1b.empty()) {
                 int t2 = 0;
                 for (const Node& p : L1b) { uint32_t m; int s; one_die(p, R, hi, m, s); t2 += BG_POPC(m) + (s >= 0); }
-                if (t2) { expand(L1b, R, hi, F); lenB2 = true; }
+                if (t2) { expand(L1b, R, hi, F, false, true); lenB2 = true; }
                 else if (!lenA2) {
                     for (const Node& c : L1b) { bool dup = false; for (const Node& o : F) if (same(o, c)) dup = true; if (!dup) F.push_back(c); }
                 }
@@ -78,7 +84,7 @@ extern "C" int emul_legal_moves(const int8_t* b52, int player, int d0, int d1, i
         std::vector<Node> cur{root};
         for (int depth = 1; depth <= 4; ++depth) {
             std::vector<Node> nxt;
-            int t = expand(cur, R, d0, nxt);
+            int t = expand(cur, R, d0, nxt, true);
             if (t == 0) break;
             cur = nxt; F = cur;
         }
