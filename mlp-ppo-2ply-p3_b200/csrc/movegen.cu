@@ -314,11 +314,6 @@ __global__ void __launch_bounds__(256) movegen_kernel(
         root.last = 31u;
         W.R.cnt2 = __ballot_sync(kFull, ownc >= 2) & 0xFFFFFFu;
         W.R.mA = 0;
-        {   // duplicate pruning is valid while the whole turn stays in the NORMAL state (bg_device.cuh, prune_mask)
-            const bool home = player ? lane < 6 : (lane >= 18 && lane < 24);
-            const int outside = __reduce_add_sync(kFull, home ? 0 : ownc);
-            W.R.prune = ownbar == 0 && outside >= (d0 == d1 ? 4 : 2);
-        }
         uint32_t nib = (uint32_t)(ownc & 15) << (4 * (p & 7));
         uint32_t w0 = __reduce_or_sync(kFull, (lane < 8) ? nib : 0u);
         uint32_t w1 = __reduce_or_sync(kFull, (lane >= 8 && lane < 16) ? nib : 0u);

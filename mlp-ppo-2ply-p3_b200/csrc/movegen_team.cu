@@ -307,12 +307,7 @@ __global__ void __launch_bounds__(T) movegen_team_kernel(
             root.hit = 0;
             root.last = 31u;
             R.cnt2 = __ballot_sync(kFull, ownc >= 2) & 0xFFFFFFu;
-            {   // duplicate pruning is valid while the whole turn stays in the NORMAL state (bg_device.cuh, prune_mask)
-                const bool home = player ? lane < 6 : (lane >= 18 && lane < 24);
-                const int outside = __reduce_add_sync(kFull, home ? 0 : ownc);
-                R.prune = ownbar == 0 && outside >= (d0 == d1 ? 4 : 2);
-                R.mA = 0;
-            }
+            R.mA = 0;
             uint32_t nib = (uint32_t)(ownc & 15) << (4 * (p & 7));
             uint32_t w0 = __reduce_or_sync(kFull, (lane < 8) ? nib : 0u);
             uint32_t w1 = __reduce_or_sync(kFull, (lane >= 8 && lane < 16) ? nib : 0u);

@@ -35,10 +35,9 @@ extern "C" int emul_legal_moves(const int8_t* b52, int player, int d0, int d1, i
     const int8_t* opp = b52 + (player ? 0 : 24);
     Root R; R.player = player; R.block = 0; R.blot = 0; R.mA = 0; R.cnt2 = 0;
     Node root; root.lo = 0; root.hi = 0; root.occ = 0; root.hit = 0; root.last = 31u;
-    int total = 0, outside = 0;
+    int total = 0;
     for (int p = 0; p < 24; ++p) {
         if (own[p] >= 2) R.cnt2 |= 1u << p;
-        if (!(player ? p < 6 : p >= 18)) outside += own[p];
         if (opp[p] >= 2) R.block |= 1u << p;
         if (opp[p] == 1) R.blot |= 1u << p;
         if (own[p] > 0) root.occ |= 1u << p;
@@ -49,7 +48,6 @@ extern "C" int emul_legal_moves(const int8_t* b52, int player, int d0, int d1, i
     int ownbar = b52[48 + player], ownoff = b52[50 + player];
     root.hi |= (unsigned long long)((ownbar & 15) | ((ownoff & 15) << 4)) << 32;
     R.tot15 = (total + ownbar + ownoff) == 15;
-    R.prune = ownbar == 0 && outside >= (d0 == d1 ? 4 : 2);
     if (d0 != d1) { uint32_t mA; int sA; one_die(root, R, d0 > d1 ? d0 : d1, mA, sA); R.mA = mA; }
 
     std::vector<Node> F;     // result
