@@ -274,7 +274,7 @@ def run_engine(args):
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
-        return
+        return None
 
     value = world * N * K / (ms * 1e-3)
     e2e_value = world * N * E / (e2e_ms * 1e-3)
@@ -327,9 +327,9 @@ def run_engine(args):
         line["cpu_baseline"] = {"value": n / el, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{n} env steps of the same uniform-random workload in {el:.1f} s over {threads} "
                                           "threads (oracle/bg_oracle.c; the Python reference measures ~50 steps/s/core, BASELINE.md)"}
-    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 def run_extras(bg_b200, env, torch, dev, args):
@@ -404,6 +404,23 @@ def run_twoply(bg_b200, env, torch, dev, args, net=None):
                     "(21 opponent rolls x replies, leaves MLP-evaluated)"}
 
 
+class StdoutToStderr:
+    """Everything written to fd 1 while active (NCCL's version banner, library chatter) goes to stderr, so that the ONE
+    JSON line is the only thing on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -431,7 +448,10 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    run_engine(args)
+    with StdoutToStderr():
+        line = run_engine(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
