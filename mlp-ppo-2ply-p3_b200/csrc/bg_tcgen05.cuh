@@ -50,6 +50,12 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4_s(uint32_t smem_addr, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(smem_addr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_addr, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(smem_addr), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -102,16 +108,18 @@ __device__ __forceinline__ uint4 feature_chunk_regs(const uint32_t (&w)[kBoardWo
         o.x = lut[reg_byte(w, 47)].y;
         o.y = bar_off_pair_bf16(reg_byte(w, 49), reg_byte(w, 51));
         o.z = flag == 0 ? 0x00003F80u : 0x3F800000u;
+        o.w = 0x3F803F80u;                           // columns 198, 199 = 1.0: multiply the folded bias (hi, lo) of W1
     }
     return o;
 }
+// (rows beyond the batch in the last tile are built from whatever the staging buffer holds: their accumulators are
+// finite and never stored)
 template <int HALF>
-__device__ __forceinline__ void build_half_row(const uint32_t (&w)[kBoardWords], int flag, const uint2* lut, uint32_t tmem_row, bool live) {
+__device__ __forceinline__ void build_half_row(const uint32_t (&w)[kBoardWords], int flag, const uint2* lut, uint32_t tmem_row) {
 #pragma unroll
     for (int i = 0; i < 13; ++i) {
         const int kc = HALF * 13 + i;
-        uint4 v = feature_chunk_regs(w, flag, kc, lut);
-        if (!live) v = make_uint4(0u, 0u, 0u, 0u);
+        const uint4 v = feature_chunk_regs(w, flag, kc, lut);
         tmem_st4(tmem_row + (uint32_t)(kc * 4), v);              // chunk kc = bf16 columns 8kc..8kc+7 = TMEM columns 4kc..4kc+3
     }
 }

@@ -67,6 +67,7 @@ __device__ __forceinline__ float win_reward(const int8_t* b, int p) {
 //                        -> arrive acc_empty[s]
 // terminal_aware: a row whose flag player has 15 men off gets the win reward instead of the network value
 // (leaf rule of the 2-ply search).
+template <bool BIAS>
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
     const int8_t* __restrict__ boards, const int8_t* __restrict__ flags, int flag_all, int flip_flags, long long B,
     const unsigned long long* __restrict__ row_begin_dev, const unsigned long long* __restrict__ n_rows_dev,
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
         *reinterpret_cast<uint4*>(S.W + kc * 2048 + n * 16) = v;
     }
     load_units_lut(S.units);
-    if (tid < kHidden) { S.b1[tid] = b1[tid]; S.wv[tid] = wv[tid]; }
+    if (tid < kHidden) { S.b1[tid] = BIAS ? b1[tid] : 0.0f; S.wv[tid] = wv[tid]; }
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
@@ -112,11 +113,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
         const int ptid = tid - kEpiThreads;                    // 0..255
         const int row = ptid & (kTileM - 1), half = ptid >> 7;  // two threads per position: chunks [13 half, 13 half + 13)
         // boards (and flags) of tile k+1 are prefetched with cp.async while tile k is being expanded
+        const uint32_t boards_s[2] = {smem_u32(&S.boards[0][0]), smem_u32(&S.boards[1][0])};
         auto prefetch = [&](long long tile, int s) {
             const long long row0 = begin + tile * kTileM;
             const int rows = (int)min((long long)kTileM, B - row0);
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
-            for (int i = ptid; i < rows * kBoardWords; i += kProdThreads) cp_async4(&S.boards[s][i], src + i);
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(boards + row0 * kBoardBytes);
+            const int bytes = rows * kBoardBytes;
+            // 16-byte copies for the aligned bulk (always the case when the rows start at a multiple of 4), words for the rest
+            const int n16 = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 ? bytes >> 4 : 0;
+            for (int i = ptid; i < n16; i += kProdThreads) cp_async16_s(boards_s[s] + 16u * i, src + 16 * i);
+            for (int i = 4 * n16 + ptid; i < (bytes >> 2); i += kProdThreads) cp_async4_s(boards_s[s] + 4u * i, src + 4 * i);
             cp_async_commit();
         };
         if ((long long)blockIdx.x < n_tiles) prefetch(blockIdx.x, 0);
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
             const uint32_t it = (uint32_t)(k >> 1);
             const long long row0 = begin + tile * kTileM;
             const int rows = (int)min((long long)kTileM, B - row0);
-            const int fl = row < rows ? (int)(((flags ? flags[row0 + row] : flag_all) ^ flip_flags) & 1) : 0;
+            const int fl = row < rows ? (int)(((flags ? __ldg(flags + row0 + row) : flag_all) ^ flip_flags) & 1) : 0;
             cp_async_wait_all();                                // this thread's share of tile k's boards has landed
             asm volatile("bar.sync 1, %0;\n" :: "n"(kProdThreads) : "memory");   // ... and everybody else's; tile k-1 is fully built
             if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x, s ^ 1);
@@ -136,8 +142,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
             mbar_wait(&S.a_empty[s], (it & 1u) ^ 1u);           // MMAs that read A[s] two tiles ago are done
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kTmemACol0 + s * kAColsPerTile);
-            if (half == 0) build_half_row<0>(w, fl, S.units, trow, row < rows);
-            else           build_half_row<1>(w, fl, S.units, trow, row < rows);
+            if (half == 0) build_half_row<0>(w, fl, S.units, trow);
+            else           build_half_row<1>(w, fl, S.units, trow);
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             mbar_arrive(&S.a_full[s]);
@@ -182,12 +188,19 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 64; j += 4) {
-                const float4 bb = *reinterpret_cast<const float4*>(&S.b1[64 * chalf + j]);
                 const float4 ww = *reinterpret_cast<const float4*>(&S.wv[64 * chalf + j]);
-                v0 = fmaf(ww.x, fmaxf(__uint_as_float(acc[j + 0]) + bb.x, 0.0f), v0);
-                v1 = fmaf(ww.y, fmaxf(__uint_as_float(acc[j + 1]) + bb.y, 0.0f), v1);
-                v2 = fmaf(ww.z, fmaxf(__uint_as_float(acc[j + 2]) + bb.z, 0.0f), v2);
-                v3 = fmaf(ww.w, fmaxf(__uint_as_float(acc[j + 3]) + bb.w, 0.0f), v3);
+                if (BIAS) {
+                    const float4 bb = *reinterpret_cast<const float4*>(&S.b1[64 * chalf + j]);
+                    v0 = fmaf(ww.x, fmaxf(__uint_as_float(acc[j + 0]) + bb.x, 0.0f), v0);
+                    v1 = fmaf(ww.y, fmaxf(__uint_as_float(acc[j + 1]) + bb.y, 0.0f), v1);
+                    v2 = fmaf(ww.z, fmaxf(__uint_as_float(acc[j + 2]) + bb.z, 0.0f), v2);
+                    v3 = fmaf(ww.w, fmaxf(__uint_as_float(acc[j + 3]) + bb.w, 0.0f), v3);
+                } else {                                             // the bias came out of the GEMM (columns 198, 199)
+                    v0 = fmaf(ww.x, fmaxf(__uint_as_float(acc[j + 0]), 0.0f), v0);
+                    v1 = fmaf(ww.y, fmaxf(__uint_as_float(acc[j + 1]), 0.0f), v1);
+                    v2 = fmaf(ww.z, fmaxf(__uint_as_float(acc[j + 2]), 0.0f), v2);
+                    v3 = fmaf(ww.w, fmaxf(__uint_as_float(acc[j + 3]), 0.0f), v3);
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             mbar_arrive(&S.acc_empty[s]);                        // accumulator s may be overwritten
@@ -211,20 +224,25 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
 }
 
-__global__ void pack_w1_kernel(const float* __restrict__ w, uint16_t* __restrict__ out) {
+// columns 198 / 199 carry the bias as a bf16 hi / lo pair (the A tile has 1.0 there): b ~ hi + lo to 2^-17 relative
+__global__ void pack_w1_kernel(const float* __restrict__ w, const float* __restrict__ b, uint16_t* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= kHidden * kKPad) return;
     int h = i / kKPad, k = i - h * kKPad;
-    out[i] = k < BG_FEATURES ? __bfloat16_as_ushort(__float2bfloat16_rn(w[h * BG_FEATURES + k])) : (uint16_t)0;
+    uint16_t v = 0;
+    if (k < BG_FEATURES) v = __bfloat16_as_ushort(__float2bfloat16_rn(w[h * BG_FEATURES + k]));
+    else if (b && k == BG_FEATURES) v = __bfloat16_as_ushort(__float2bfloat16_rn(b[h]));
+    else if (b && k == BG_FEATURES + 1) v = __bfloat16_as_ushort(__float2bfloat16_rn(b[h] - __bfloat162float(__float2bfloat16_rn(b[h]))));
+    out[i] = v;
 }
 
 }  // namespace bg
 
 using namespace bg;
 
-extern "C" int bg_pack_w1(const float* fc1_weight, uint16_t* w1_bf16, void* stream) {
+extern "C" int bg_pack_w1(const float* fc1_weight, const float* fc1_bias, uint16_t* w1_bf16, void* stream) {
     if (!fc1_weight || !w1_bf16) return bg_set_error_msg(BG_ERR_INVALID, "bg_pack_w1: null pointer");
-    pack_w1_kernel<<<(kHidden * kKPad + 255) / 256, 256, 0, (cudaStream_t)stream>>>(fc1_weight, w1_bf16);
+    pack_w1_kernel<<<(kHidden * kKPad + 255) / 256, 256, 0, (cudaStream_t)stream>>>(fc1_weight, fc1_bias, w1_bf16);
     return bg_set_error(cudaGetLastError(), "bg_pack_w1: launch");
 }
 
@@ -234,14 +252,15 @@ int bg::mlp_value_launch(const int8_t* boards52, const int8_t* flags, int flag_a
                          float* values, cudaStream_t stream) {
     if (B < 0) return bg_set_error_msg(BG_ERR_INVALID, "bg_mlp_value: negative batch");
     if (B == 0) return BG_OK;
-    if (!boards52 || !w1_bf16 || !b1 || !wv || !values) return bg_set_error_msg(BG_ERR_INVALID, "bg_mlp_value: null pointer");
+    if (!boards52 || !w1_bf16 || !wv || !values) return bg_set_error_msg(BG_ERR_INVALID, "bg_mlp_value: null pointer");
     size_t smem = sizeof(MlpSmem) + 1024;
-    cudaError_t e = cudaFuncSetAttribute(mlp_value_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = b1 ? mlp_value_kernel<true> : mlp_value_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return bg_set_error(e, "bg_mlp_value: cudaFuncSetAttribute");
     long long tiles = (B + kTileM - 1) / kTileM;
     long long grid = bg_sm_count();
     if (grid > tiles) grid = tiles;
-    mlp_value_kernel<<<(unsigned)grid, kMlpThreads, smem, stream>>>(
+    kern<<<(unsigned)grid, kMlpThreads, smem, stream>>>(
         boards52, flags, flag_all & 1, flip_flags & 1, B, row_begin_dev, n_rows_dev, w1_bf16, b1, wv, bv, terminal_aware, values);
     return bg_set_error(cudaGetLastError(), "bg_mlp_value: launch");
 }

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
         *reinterpret_cast<uint4*>(S.Wa + kc * (kActPad * 16) + n * 16) = *reinterpret_cast<const uint4*>(wa + (size_t)n * kHidden + kc * 8);
     }
     load_units_lut(S.units);
-    if (tid < kHidden) { S.b1[tid] = b1[tid]; S.wv[tid] = wv[tid]; }
+    if (tid < kHidden) { S.b1[tid] = b1 ? b1[tid] : 0.0f; S.wv[tid] = wv[tid]; }   // b1 == NULL: folded into W1 (bg_pack_w1)
     S.ba[tid] = tid < kActions ? ba[tid] : 0.0f;                 // kPolThreads == kActPad
     if (tid == 0) {
         mbar_init(&S.bar1, 1); mbar_init(&S.bar2[0], 1); mbar_init(&S.bar2[1], 1);
@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
             for (int i = 0; i < kBoardWords; ++i) w[i] = S.boards[prow * kBoardWords + i];
             const int fl = prow < rows ? (int)((flags ? flags[row0 + prow] : flag_all) & 1) : 0;
             const uint32_t trow = lane_base + (uint32_t)kColA;
-            if (half == 0) build_half_row<0>(w, fl, S.units, trow, prow < rows);
-            else           build_half_row<1>(w, fl, S.units, trow, prow < rows);
+            if (half == 0) build_half_row<0>(w, fl, S.units, trow);
+            else           build_half_row<1>(w, fl, S.units, trow);
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -279,7 +279,7 @@ extern "C" int bg_policy_sample(const int8_t* boards52, const int8_t* flags, int
                                 int32_t* actions, float* log_probs, float* values, float* logits_out, void* stream) {
     if (B < 0) return bg_set_error_msg(BG_ERR_INVALID, "bg_policy_sample: negative batch");
     if (B == 0) return BG_OK;
-    if (!boards52 || !w1_bf16 || !b1 || !wa_bf16 || !ba || !wv || !actions)
+    if (!boards52 || !w1_bf16 || !wa_bf16 || !ba || !wv || !actions)
         return bg_set_error_msg(BG_ERR_INVALID, "bg_policy_sample: null pointer");
     const size_t smem = sizeof(PolSmem) + 1024;
     cudaError_t e = cudaFuncSetAttribute(policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -44,7 +44,7 @@ class PolicyValueNet(ValueNet):
         self.wv = p["value_head.weight"].reshape(HIDDEN)
         self.bv = float(p["value_head.bias"].reshape(-1)[0])    # (one small D2H read per sync)
         with torch.cuda.device(self.device):
-            check(lib().bg_pack_w1(p["fc1.weight"].data_ptr(), self.w1_bf16.data_ptr(), _stream()), "bg_pack_w1")
+            check(lib().bg_pack_w1(p["fc1.weight"].data_ptr(), p["fc1.bias"].data_ptr(), self.w1_bf16.data_ptr(), _stream()), "bg_pack_w1")
             check(lib().bg_pack_wa(p["action_head.weight"].data_ptr(), self.wa_bf16.data_ptr(), _stream()), "bg_pack_wa")
 
     @classmethod
@@ -95,7 +95,7 @@ class PolicyValueNet(ValueNet):
         actions, logp, values = out
         logits = torch.empty((B, ACTIONS), dtype=torch.float32, device=dev) if want_logits else None
         with torch.cuda.device(dev):
-            check(lib().bg_policy_sample(boards52.data_ptr(), fptr, fall, B, cptr, self.w1_bf16.data_ptr(), self.b1.data_ptr(),
+            check(lib().bg_policy_sample(boards52.data_ptr(), fptr, fall, B, cptr, self.w1_bf16.data_ptr(), None,
                                          self.wa_bf16.data_ptr(), self.ba.data_ptr(), self.wv.data_ptr(), self.bv,
                                          int(seed), int(stream_base), int(step), int(greedy), actions.data_ptr(),
                                          logp.data_ptr(), values.data_ptr(), logits.data_ptr() if want_logits else None,

@@ -77,7 +77,7 @@ class TwoPlySearch:
             check(L.bg_twoply_replies_values(A.data_ptr(), movers.data_ptr(), M, b["replies"].data_ptr(), b["cap"],
                                              b["rowp"].data_ptr(), b["counts"].data_ptr(), b["starts"].data_ptr(),
                                              b["alloc"].data_ptr(), b["ws"].status.data_ptr(), b["ws"].buf.data_ptr(),
-                                             b["ws"].nbytes, net.w1_bf16.data_ptr(), net.b1.data_ptr(), net.wv.data_ptr(),
+                                             b["ws"].nbytes, net.w1_bf16.data_ptr(), None, net.wv.data_ptr(),
                                              net.bv, b["leaf_v"].data_ptr(), b["pass_v"].data_ptr(),
                                              self._side.cuda_stream if self.overlap else None, _stream()),
                   "bg_twoply_replies_values")

@@ -31,7 +31,7 @@ class ValueNet:
         self.bv = float(torch.as_tensor(value_bias).reshape(-1)[0])
         self.w1_bf16 = torch.empty((HIDDEN, LD), dtype=torch.bfloat16, device=device)
         with torch.cuda.device(device):
-            check(lib().bg_pack_w1(w.data_ptr(), self.w1_bf16.data_ptr(), _stream()), "bg_pack_w1")
+            check(lib().bg_pack_w1(w.data_ptr(), self.b1.data_ptr(), self.w1_bf16.data_ptr(), _stream()), "bg_pack_w1")   # bias folded into columns 198/199
 
     @classmethod
     def from_state_dict(cls, sd, device):
@@ -72,6 +72,6 @@ class ValueNet:
         with torch.cuda.device(boards52.device):
             check(lib().bg_mlp_value(boards52.data_ptr(), fptr, fall, int(flip_flags), B,
                                      n_rows_dev.data_ptr() if n_rows_dev is not None else None,
-                                     self.w1_bf16.data_ptr(), self.b1.data_ptr(), self.wv.data_ptr(), self.bv,
+                                     self.w1_bf16.data_ptr(), None, self.wv.data_ptr(), self.bv,
                                      int(terminal_aware), out.data_ptr(), _stream()), "bg_mlp_value")
         return out
