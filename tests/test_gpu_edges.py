@@ -1,0 +1,101 @@
+"""Edge cases of the entry points added after the first parity suite: one-call K1+K3 (serial / overlapped) on the
+heaviest fixtures, other feature strides, empty and tiny batches, argument errors, policy kernel without a mask."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_update_legal_plays_heavy_fixtures_serial_and_overlapped():
+    """all three K1 tiers + both encoder launches: golden counts/afterstates in order, features == encoder, both modes"""
+    import bg_b200 as bg
+    d = np.load(os.path.join(G, "adversarial.npz"))
+    sel = np.concatenate([np.argsort(-d["counts"])[:150], np.arange(0, len(d["counts"]), 7)])
+    for overlap in (False, True):
+        env = bg.B200BackgammonVecEnv(num_envs=len(sel), device=dev(), rows_per_game=160, max_legal_moves=5000, check_every=0)
+        env.boards52.copy_(torch.as_tensor(d["boards"][sel]).to(dev()))
+        env.players.copy_(torch.as_tensor(d["players"][sel]).to(dev()))
+        env.dice.copy_(torch.as_tensor(d["dice"][sel]).to(dev()))
+        env.update_legal_plays(obs=True, features=True, overlap=overlap)
+        torch.cuda.synchronize()
+        env.check_status()
+        assert env.legal_counts_true.cpu().tolist() == d["counts"][sel].tolist()
+        rows = env.after52.cpu().numpy()
+        starts = env.legal_starts.cpu().numpy()
+        for k, i in enumerate(sel[:60]):
+            lo, hi = d["offsets"][i], d["offsets"][i + 1]
+            assert np.array_equal(rows[starts[k]:starts[k] + (hi - lo)], d["after"][lo:hi]), (overlap, int(i))
+        n = env.total_rows()
+        want = bg.encode(env.after52[:n], env.row_players[:n], dtype=torch.bfloat16)
+        assert torch.equal(env.after_feats[:n].view(torch.int16), want.view(torch.int16))
+        assert torch.equal(env.obs_f32, bg.encode(env.boards52, env.players))
+
+
+def test_encode_bf16_other_strides_and_tiny_batches():
+    import bg_b200 as bg
+    from oracle import bg_oracle as O
+    d = np.load(os.path.join(G, "encode.npz"))
+    b52 = torch.as_tensor(d["boards"]).to(dev())
+    flags = (torch.arange(b52.shape[0], device=dev()) % 2).to(torch.int8)
+    ref = bg.encode(b52, flags, dtype=torch.float32)
+    gold = np.where((flags.cpu().numpy() == 0)[:, None], d["feat_p1"], d["feat_p2"])       # the reference's own vectors
+    assert np.array_equal(ref.cpu().numpy(), gold)
+    for ld in (200, 208, 256, 512):
+        for B in (1, 2, 17, 129, b52.shape[0]):
+            out = bg.encode(b52[:B], flags[:B], dtype=torch.bfloat16, ld=ld)
+            assert out.shape == (B, ld)
+            assert torch.equal(out[:, :198], ref[:B].to(torch.bfloat16)) and bool((out[:, 198:] == 0).all())
+    assert bg.encode(b52[:0], 0, dtype=torch.bfloat16).shape[0] == 0
+
+
+def test_env_single_game_and_odd_sizes():
+    import bg_b200 as bg
+    from oracle import bg_oracle as O
+    for N in (1, 5, 33):
+        env = bg.B200BackgammonVecEnv(num_envs=N, device=dev(), seed=21, check_every=1)
+        obs = env.reset()
+        assert obs.shape == (N, 198)
+        for t in range(30):
+            obs, rew, done, infos = env.step(env.random_actions(4, t), with_features=True)
+            assert obs.shape == (N, 198) and rew.shape == (N,) and done.dtype == torch.bool and len(infos) == N
+            b52, pl, dc = env.boards52.cpu().numpy(), env.players.cpu().numpy(), env.dice.cpu().numpy()
+            counts, offsets, after = O.legal_moves_batch(O.unpack52(b52), pl, dc)
+            assert np.array_equal(env.legal_counts_true.cpu().numpy(), counts)
+            assert np.array_equal(obs.cpu().numpy(), O.encode(O.unpack52(b52), pl))
+        assert isinstance(infos[0], dict) and "current_player" in infos[0]
+
+
+def test_new_entry_points_reject_bad_arguments():
+    import bg_b200 as bg
+    L = bg.lib()
+    assert L.bg_update_legal_plays(None, None, None, 4, 0, None, 0, None, None, None, None, None, None, None, 0, None, 208, None, 198,
+                                   None, None, None, None) == -1
+    assert L.bg_update_legal_plays(None, None, None, 0, 0, None, 0, None, None, None, None, None, None, None, 0, None, 208, None, 198,
+                                   None, None, None, None) == 0
+    assert L.bg_policy_sample(None, None, 0, 4, None, None, None, None, None, None, 0.0, 0, 0, 0, 0, None, None, None, None, None) == -1
+    assert L.bg_policy_sample(None, None, 0, 0, None, None, None, None, None, None, 0.0, 0, 0, 0, 0, None, None, None, None, None) == 0
+    assert L.bg_gae(None, None, None, None, 4, 4, 0.99, 1.0, None, None, None) == -1
+    assert L.bg_ppo_loss_grad(None, 1, 499, None, None, None, None, None, None, 4, 0.2, 0.5, 0.01, None, None, None, None) == -1
+    assert L.bg_twoply_replies_values(None, None, 4, None, 0, None, None, None, None, None, None, 0, None, None, None, 0.0, None, None,
+                                      None, None) == -1
+
+
+def test_policy_without_mask_and_single_row():
+    import bg_b200 as bg
+    net = bg.PolicyValueNet.random_init(dev(), seed=4)
+    b = bg.initial_board52(1, dev())
+    a, lp, v, logits = net.act(b, 0, None, greedy=True, want_logits=True)
+    assert int(a[0]) == int(logits[0].argmax()) and abs(float(lp[0]) - float(torch.log_softmax(logits[0], -1).max())) < 1e-4
+    counts = torch.tensor([3], dtype=torch.int32, device=dev())
+    a, lp, v = net.act(b, 0, counts, greedy=True)
+    assert int(a[0]) == int(logits[0, :3].argmax())
+    # value head agrees with K4 on the same position
+    assert abs(float(v[0]) - float(net.values(b, 0)[0])) < 1e-4
