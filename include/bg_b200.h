@@ -195,12 +195,17 @@ int bg_mlp_value(const int8_t* boards52, const int8_t* flags, int flag_all, int 
  *            logits_out [B][500] f32 (nullable; unmasked logits, for parity checks).
  */
 int bg_pack_wa(const float* action_head_weight /*[500][128] f32*/, uint16_t* wa_bf16 /*[512][128]*/, void* stream);
+size_t bg_policy_workspace_bytes(long long B);
+/* workspace (nullable): bg_policy_workspace_bytes(B) bytes of device scratch; with it (and a mask, and logits_out == NULL)
+ * the rows are split into those with 1..128 legal slots, which need one quarter of the policy GEMM and only the legal
+ * part of its epilogue, and the rest (passes, > 128 slots).  Results do not depend on it beyond rounding (illegal slots
+ * are then left out of the softmax instead of entering it with exp(-103)). */
 int bg_policy_sample(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
                      const int32_t* legal_counts /*nullable*/, const uint16_t* w1_bf16, const float* b1,
                      const uint16_t* wa_bf16, const float* ba, const float* wv, float bv, unsigned long long seed,
                      unsigned long long stream_base, uint32_t step, int greedy, int32_t* actions,
                      float* log_probs /*nullable*/, float* values /*nullable*/, float* logits_out /*nullable*/,
-                     void* stream);
+                     void* workspace /*nullable*/, size_t workspace_bytes, void* stream);
 
 /* N2  discounted returns / GAE(lambda) per game over a rollout stored step-major [T][N]; replaces
  * BackgammonPPOAgent.compute_returns (agent/ppo_agent.py:206-216).  values / last_values nullable (= 0):

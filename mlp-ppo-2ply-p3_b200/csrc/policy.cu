@@ -19,6 +19,13 @@
 //      max / sum-exp, and Gumbel-max sampling (argmax_i logit_i + g_i, g_i = -log(-log u_i), u_i from Philox4x32-10
 //      keyed by (seed; global row, step, slot)) -- a single pass, the 500 logits of a row never leave the SM
 //   F  the four column-quarter warps of a row are combined through shared memory -> action, log-prob, value
+// Rows are processed in two classes so that the work follows the mask instead of the 500 slots: class A = rows with
+// 1..128 legal slots (99 % of a self-play batch; mean 18.5): ONE chunk of the policy GEMM, and a warp whose 32 slots
+// are illegal for all its rows skips its part of the epilogue altogether; illegal slots are left out of the softmax
+// (the reference adds log(1e-45) = -103.3 to them: a relative change below 1e-38 of the normaliser).  Class B = rows
+// with no legal slot (a pass: the reference samples among all 500 slots) or more than 128: all four chunks, mask
+// offset applied literally.  policy_partition_kernel builds the two row lists (one array, A from the front, B from
+// the back); tiles gather their rows through it and scatter their results.
 // HBM traffic per position: 53 B board + 4 B count in, 12 B out.
 // TMEM columns: [0,128) acc1; [128,232) A1 / [128,192) A2; [256,384) and [384,512) acc2 ping/pong.
 #include <cuda_bf16.h>
@@ -47,6 +54,7 @@ struct PolSmem {
     float red_m[4][kTileM], red_s[4][kTileM], red_g[4][kTileM], red_l[4][kTileM];
     int red_i[4][kTileM];
     uint2 units[16];
+    int rowidx[kTileM];                     // global row of each tile row (-1: none)
     unsigned long long bar1, bar2[2];
     uint32_t tmem_base;
 };
@@ -60,6 +68,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
     const int32_t* __restrict__ legal_counts, const uint16_t* __restrict__ w1, const float* __restrict__ b1,
     const uint16_t* __restrict__ wa, const float* __restrict__ ba, const float* __restrict__ wv, float bv,
     unsigned long long seed, unsigned long long stream_base, uint32_t step, int greedy,
+    const int32_t* __restrict__ row_list, const unsigned int* __restrict__ n_class_a_dev,
     int32_t* __restrict__ actions, float* __restrict__ logp, float* __restrict__ values, float* __restrict__ logits_out) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     PolSmem& S = *reinterpret_cast<PolSmem*>(smem_raw);
@@ -92,19 +101,34 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = S.tmem_base;
     const uint32_t w1_addr = smem_u32(S.W1), wa_addr = smem_u32(S.Wa);
-    const long long n_tiles = (B + kTileM - 1) / kTileM;
+    // class A rows = row_list[0 .. nA), class B rows = row_list[B-1 .. nA] (from the back); without a list every row is B
+    const long long nA = row_list ? (long long)*n_class_a_dev : 0;
+    const long long tilesA = (nA + kTileM - 1) / kTileM, tilesB = (B - nA + kTileM - 1) / kTileM;
+    const long long n_tiles = tilesA + tilesB;
     const int q = warp & 3, cq = warp >> 2;                      // TMEM lane quadrant, column quarter
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t ph1 = 0, ph2[2] = {0, 0};
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long row0 = tile * kTileM;
-        const int rows = (int)min((long long)kTileM, B - row0);
-        // ---- A: stage the boards
-        {
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
-            for (int i = tid; i < kTileM * kBoardWords; i += kPolThreads) S.boards[i] = i < rows * kBoardWords ? __ldg(src + i) : 0u;
+        const bool class_a = tile < tilesA;
+        const long long first = class_a ? tile * kTileM : (tile - tilesA) * kTileM;      // position in the class
+        const int rows = (int)min((long long)kTileM, (class_a ? nA : B - nA) - first);
+        const int n_chunks = class_a ? 1 : 4;
+        // ---- A: the tile's rows, then their boards (gathered)
+        if (tid < kTileM) {
+            int g = -1;
+            if (tid < rows) {
+                const long long pos = class_a ? first + tid : (row_list ? B - 1 - (first + tid) : first + tid);
+                g = row_list ? row_list[pos] : (int)pos;
+            }
+            S.rowidx[tid] = g;
+        }
+        __syncthreads();
+        for (int i = tid; i < kTileM * kBoardWords; i += kPolThreads) {
+            const int r = i / kBoardWords, wd = i - r * kBoardWords;
+            const int g = S.rowidx[r];
+            S.boards[i] = g >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(boards + (long long)g * kBoardBytes) + wd) : 0u;
         }
         __syncthreads();
         // ---- B: feature rows -> TMEM (two threads per position; warps 0-3 chunks 0-12, warps 4-7 chunks 13-25)
@@ -113,7 +137,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
             uint32_t w[kBoardWords];
 #pragma unroll
             for (int i = 0; i < kBoardWords; ++i) w[i] = S.boards[prow * kBoardWords + i];
-            const int fl = prow < rows ? (int)((flags ? flags[row0 + prow] : flag_all) & 1) : 0;
+            const int pg = S.rowidx[prow];
+            const int fl = pg >= 0 ? (int)((flags ? flags[pg] : flag_all) & 1) : 0;
             const uint32_t trow = lane_base + (uint32_t)kColA;
             if (half == 0) build_half_row<0>(w, fl, S.units, trow);
             else           build_half_row<1>(w, fl, S.units, trow);
@@ -165,16 +190,19 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
                             ks > 0 ? 1u : 0u);
             umma_commit(&S.bar2[c & 1]);
         };
-        if (tid == 0) { issue_chunk(0); issue_chunk(1); }
-        const long long gid = row0 + row;                         // row index within this call
-        const int n_legal = (row < rows && legal_counts) ? legal_counts[gid] : (legal_counts ? 1 : kActions);
-        const unsigned long long sid = stream_base + (unsigned long long)gid;   // global stream id (game id)
+        if (tid == 0) { issue_chunk(0); if (n_chunks > 1) issue_chunk(1); }
+        const long long gid = S.rowidx[row];                      // row index within this call (-1: none)
+        const int n_legal = (gid >= 0 && legal_counts) ? legal_counts[gid] : (legal_counts ? 1 : kActions);
+        const unsigned long long sid = stream_base + (unsigned long long)(gid >= 0 ? gid : 0);   // global stream id (game id)
+        // class A: this warp's 32 slots of chunk 0 matter only if some row of the warp has more than 32 cq legal slots
+        const bool warp_active = !class_a || __any_sync(kFull, n_legal > 32 * cq);
         float m = -INFINITY, s = 0.0f, gbest = -INFINITY, lbest = 0.0f;
         int ibest = 0;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < n_chunks; ++c) {
             mbar_wait(&S.bar2[c & 1], ph2[c & 1]); ph2[c & 1] ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (warp_active) {
             uint32_t acc[32];
             tmem_ld32(lane_base + (uint32_t)(kColAcc2 + 128 * (c & 1) + 32 * cq), acc);
             tmem_ld_wait();
@@ -185,8 +213,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
             for (int j = 0; j < 32; ++j) {
                 const int i = base + j;
                 float l = __uint_as_float(acc[j]) + S.ba[i];
-                if (logits_out && row < rows && i < kActions) logits_out[gid * kActions + i] = l;
-                if (i >= n_legal) l += kMaskLog;                   // logits + log(mask + 1e-45), ppo_agent.py:165
+                if (logits_out && gid >= 0 && i < kActions) logits_out[gid * kActions + i] = l;
+                if (i >= n_legal) l = class_a ? -INFINITY : l + kMaskLog;   // logits + log(mask + 1e-45), ppo_agent.py:165
                 if (i >= kActions) l = -INFINITY;                  // padding slots do not exist
                 x[j] = l;
                 cm = fmaxf(cm, l);
@@ -223,9 +251,10 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
                     }
                 }
             }
+            }   // warp_active
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             __syncthreads();                                       // every warp has read acc2[c & 1]
-            if (tid == 0 && c + 2 < 4) issue_chunk(c + 2);
+            if (tid == 0 && c + 2 < n_chunks) issue_chunk(c + 2);
         }
         // ---- F: combine the four column quarters of each row
         S.red_m[cq][row] = m; S.red_s[cq][row] = s; S.red_g[cq][row] = gbest; S.red_l[cq][row] = lbest; S.red_i[cq][row] = ibest;
@@ -243,9 +272,10 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
                 const float g = S.red_g[k][r];
                 if (g > gb || (g == gb && g > -INFINITY && S.red_i[k][r] < ib)) { gb = g; lb = S.red_l[k][r]; ib = S.red_i[k][r]; }
             }
-            actions[row0 + r] = ib;
-            if (logp) logp[row0 + r] = lb - (M + __logf(sum));
-            if (values) values[row0 + r] = bv + ((S.part[0][r] + S.part[1][r]) + (S.part[2][r] + S.part[3][r]));
+            const long long g = S.rowidx[r];
+            actions[g] = ib;
+            if (logp) logp[g] = lb - (M + __logf(sum));
+            if (values) values[g] = bv + ((S.part[0][r] + S.part[1][r]) + (S.part[2][r] + S.part[3][r]));
         }
         __syncthreads();
     }
@@ -253,6 +283,23 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(512u) : "memory");
+}
+
+// Row lists of the two classes in ONE array: rows with 1..128 legal slots from the front, the others from the back.
+// Order inside a class is arbitrary (atomics); results do not depend on it (the random stream is keyed by the row).
+__global__ void __launch_bounds__(256) policy_partition_kernel(const int32_t* __restrict__ counts, long long B,
+                                                               int32_t* __restrict__ row_list, unsigned int* __restrict__ ctr /*[2]*/) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int n = g < B ? counts[g] : -1;
+    const bool a = g < B && n >= 1 && n <= 128, b = g < B && !a;
+    const unsigned ma = __ballot_sync(kFull, a), mb = __ballot_sync(kFull, b);
+    unsigned int base_a = 0, base_b = 0;
+    if (lane == 0) { if (ma) base_a = atomicAdd(&ctr[0], (unsigned)__popc(ma)); if (mb) base_b = atomicAdd(&ctr[1], (unsigned)__popc(mb)); }
+    base_a = __shfl_sync(kFull, base_a, 0); base_b = __shfl_sync(kFull, base_b, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (a) row_list[base_a + __popc(ma & below)] = (int32_t)g;
+    if (b) row_list[B - 1 - (long long)(base_b + __popc(mb & below))] = (int32_t)g;
 }
 
 __global__ void pack_wa_kernel(const float* __restrict__ w, uint16_t* __restrict__ out) {
@@ -272,23 +319,39 @@ extern "C" int bg_pack_wa(const float* action_head_weight, uint16_t* wa_bf16, vo
     return bg_set_error(cudaGetLastError(), "bg_pack_wa: launch");
 }
 
+extern "C" size_t bg_policy_workspace_bytes(long long B) { return 16 + sizeof(int32_t) * (size_t)(B > 0 ? B : 1); }
+
 extern "C" int bg_policy_sample(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
                                 const int32_t* legal_counts, const uint16_t* w1_bf16, const float* b1,
                                 const uint16_t* wa_bf16, const float* ba, const float* wv, float bv,
                                 unsigned long long seed, unsigned long long stream_base, uint32_t step, int greedy,
-                                int32_t* actions, float* log_probs, float* values, float* logits_out, void* stream) {
+                                int32_t* actions, float* log_probs, float* values, float* logits_out, void* workspace,
+                                size_t workspace_bytes, void* stream) {
     if (B < 0) return bg_set_error_msg(BG_ERR_INVALID, "bg_policy_sample: negative batch");
     if (B == 0) return BG_OK;
+    if (B > 0x7FFFFFF0LL) return bg_set_error_msg(BG_ERR_INVALID, "bg_policy_sample: batch too large");
     if (!boards52 || !w1_bf16 || !wa_bf16 || !ba || !wv || !actions)
         return bg_set_error_msg(BG_ERR_INVALID, "bg_policy_sample: null pointer");
     const size_t smem = sizeof(PolSmem) + 1024;
     cudaError_t e = cudaFuncSetAttribute(policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return bg_set_error(e, "bg_policy_sample: cudaFuncSetAttribute");
-    long long tiles = (B + kTileM - 1) / kTileM;
+    // two row classes (1..128 legal slots / the rest) when there is a mask, a workspace, and the logits are not wanted
+    const int32_t* row_list = nullptr;
+    const unsigned int* n_a = nullptr;
+    if (legal_counts && workspace && !logits_out) {
+        if (workspace_bytes < bg_policy_workspace_bytes(B)) return bg_set_error_msg(BG_ERR_INVALID, "bg_policy_sample: workspace too small");
+        unsigned int* ctr = static_cast<unsigned int*>(workspace);
+        int32_t* list = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(workspace) + 16);
+        e = cudaMemsetAsync(ctr, 0, 16, (cudaStream_t)stream);
+        if (e != cudaSuccess) return bg_set_error(e, "bg_policy_sample: memset");
+        policy_partition_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(legal_counts, B, list, ctr);
+        row_list = list; n_a = ctr;
+    }
+    long long tiles = (B + kTileM - 1) / kTileM + 1;
     long long grid = bg_sm_count();
     if (grid > tiles) grid = tiles;
     policy_kernel<<<(unsigned)grid, kPolThreads, smem, (cudaStream_t)stream>>>(
         boards52, flags, flag_all & 1, B, legal_counts, w1_bf16, b1, wa_bf16, ba, wv, bv, seed, stream_base, step, greedy,
-        actions, log_probs, values, logits_out);
+        row_list, n_a, actions, log_probs, values, logits_out);
     return bg_set_error(cudaGetLastError(), "bg_policy_sample: launch");
 }

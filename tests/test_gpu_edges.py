@@ -80,8 +80,8 @@ def test_new_entry_points_reject_bad_arguments():
                                    None, None, None, None) == -1
     assert L.bg_update_legal_plays(None, None, None, 0, 0, None, 0, None, None, None, None, None, None, None, 0, None, 208, None, 198,
                                    None, None, None, None) == 0
-    assert L.bg_policy_sample(None, None, 0, 4, None, None, None, None, None, None, 0.0, 0, 0, 0, 0, None, None, None, None, None) == -1
-    assert L.bg_policy_sample(None, None, 0, 0, None, None, None, None, None, None, 0.0, 0, 0, 0, 0, None, None, None, None, None) == 0
+    assert L.bg_policy_sample(None, None, 0, 4, None, None, None, None, None, None, 0.0, 0, 0, 0, 0, None, None, None, None, None, 0, None) == -1
+    assert L.bg_policy_sample(None, None, 0, 0, None, None, None, None, None, None, 0.0, 0, 0, 0, 0, None, None, None, None, None, 0, None) == 0
     assert L.bg_gae(None, None, None, None, 4, 4, 0.99, 1.0, None, None, None) == -1
     assert L.bg_ppo_loss_grad(None, 1, 499, None, None, None, None, None, None, 4, 0.2, 0.5, 0.01, None, None, None, None) == -1
     assert L.bg_twoply_replies_values(None, None, 4, None, 0, None, None, None, None, None, None, 0, None, None, None, 0.0, None, None,
