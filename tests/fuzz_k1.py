@@ -2,7 +2,8 @@
 """Differential fuzz of K1 (GPU, all tiers, through the C ABI) against the CPU oracle at scale: positions from the
 engine's own random self-play x all 36 ordered rolls (plus the positions' own dice), afterstate lists compared IN ORDER.
 The oracle (oracle/bg_oracle.c) is pinned to the reference by tests/test_oracle_golden.py; this script is a checker,
-not a product path.     python scripts/fuzz_k1.py [--positions 20000] [--threads 16]
+not a product path (it lives under tests/ because it uses the oracle).   python tests/fuzz_k1.py [--positions 20000] [--threads 16]
+tests/test_gpu_fuzz_large.py runs it at 30,000 positions (1.08 M pairs); profiles/r1_l_fuzz_*.json are 30 k / 200 k runs.
 Prints one JSON line; exit code 1 on any difference."""
 import argparse, json, os, sys, time
 from concurrent.futures import ThreadPoolExecutor
