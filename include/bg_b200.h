@@ -164,9 +164,10 @@ int bg_update_legal_plays(const int8_t* boards52, const int8_t* players, const i
  * v = w_v . relu(W1 x + b1) + b_v, fused with the feature encoding: input is board52 + flag, the
  * 198-wide bf16 rows are built in shared memory and multiplied on the tcgen05 tensor cores
  * (bf16 x bf16 -> f32 in TMEM); the hidden layer is reduced in the epilogue straight out of TMEM.
- *   w1_bf16: [128][208] bf16, row h = fc1.weight[h, :198], then (bg_pack_w1 with fc1_bias != NULL) the bias as a bf16
- *   hi/lo pair in columns 198, 199 -- the kernels put 1.0 there in the A tile, so the bias comes out of the GEMM and
- *   b1 must then be passed as NULL -- then zeros.  With fc1_bias == NULL the columns are zero and b1 is added explicitly.
+ *   w1_bf16: [128][208] bf16 as written by bg_pack_w1 -- an OPAQUE operand tile: fc1.weight in the kernels' internal K
+ *   order (points first, bar/off/flags last), then (fc1_bias != NULL) the bias as a bf16 hi/lo pair in columns 198, 199
+ *   -- the kernels put 1.0 there in the A tile, so the bias comes out of the GEMM and b1 must then be passed as NULL --
+ *   then zeros.  With fc1_bias == NULL those columns are zero and b1 is added explicitly.
  *   flags / flag_all as in K3; flip_flags = 1 evaluates every row with the OTHER player's flag.
  *   terminal_aware = 1: a row whose flag player has borne off 15 men gets the win reward 1 / 1.5 / 2
  *   (environment/backgammon_env.py:156-171) instead of the network value (2-ply leaf rule).

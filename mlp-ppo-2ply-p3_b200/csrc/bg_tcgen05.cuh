@@ -89,28 +89,38 @@ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// board52 byte `idx` (a compile-time constant after unrolling) of a row held as 13 words in registers
-__device__ __forceinline__ int reg_byte(const uint32_t (&w)[kBoardWords], int idx) { return (int)((w[idx >> 2] >> (8 * (idx & 3))) & 15u); }
-// chunk k of the feature row, k constant after unrolling (same content as feature_chunk_lut)
-__device__ __forceinline__ uint4 feature_chunk_regs(const uint32_t (&w)[kBoardWords], int flag, int k, const uint2* lut) {
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (k < 12) {
-        uint2 a = lut[reg_byte(w, 2 * k)], c = lut[reg_byte(w, 2 * k + 1)];
-        o = make_uint4(a.x, a.y, c.x, c.y);
-    } else if (k == 12) {
-        uint2 a = lut[reg_byte(w, 24)], c = lut[reg_byte(w, 25)];
-        o = make_uint4(bar_off_pair_bf16(reg_byte(w, 48), reg_byte(w, 50)), a.x, a.y, c.x);
-    } else if (k < 24) {
-        const int q = 2 * (k - 12) - 1;
-        uint2 a = lut[reg_byte(w, 24 + q)], c = lut[reg_byte(w, 25 + q)], e = lut[reg_byte(w, 26 + q)];
-        o = make_uint4(a.y, c.x, c.y, e.x);
-    } else if (k == 24) {
-        o.x = lut[reg_byte(w, 47)].y;
-        o.y = bar_off_pair_bf16(reg_byte(w, 49), reg_byte(w, 51));
-        o.z = flag == 0 ? 0x00003F80u : 0x3F800000u;
-        o.w = 0x3F803F80u;                           // columns 198, 199 = 1.0: multiply the folded bias (hi, lo) of W1
+// ---------------------------------------------------------------------------------------------------------------
+// The A tile of the first layer.  The tensor-core kernels are free to order the K dimension as they like as long as
+// the A tile and the packed W1 agree, so internally the 198 features are permuted so that every 16-byte chunk (8
+// bf16) of a row is exactly TWO WHOLE POINTS:
+//     internal column  0.. 95   PLAYER1 points 0..23, 4 units each      (reference features   0.. 95)
+//                     96..191   PLAYER2 points 0..23                    (reference features  98..193)
+//                    192..197   bar1/2, off1/15, bar2/2, off2/15, turn flags  (features 96, 97, 194, 195, 196, 197)
+//                    198, 199   1.0, 1.0 (they multiply the folded bias hi / lo of W1);   200..207 zero
+// (bg_w1_source_column below is the same map for bg_pack_w1.)  Chunk k < 24 is then two 8-byte loads from the 16-entry
+// units table (128 bytes = one entry per bank pair: conflict-free for any index pattern), indexed by the two adjacent
+// count bytes of board word k/2.  (A 256-entry table of point PAIRS, one 16-byte load per chunk, was measured slower:
+// random 16-byte entries conflict in the banks -- 80 us vs 77 us per 1.2 M rows.)
+__host__ __device__ __forceinline__ int bg_w1_source_column(int j) {      // internal column -> reference feature (-1: none)
+    if (j < 96) return j;
+    if (j < 192) return j + 2;
+    switch (j) { case 192: return 96; case 193: return 97; case 194: return 194; case 195: return 195; case 196: return 196; case 197: return 197; }
+    return -1;
+}
+// chunk kc (compile-time constant after unrolling) of the internal feature row of a position held as 13 words
+__device__ __forceinline__ uint4 feature_chunk_regs(const uint32_t (&w)[kBoardWords], int flag, int kc, const uint2* lut) {
+    if (kc < 24) {
+        const uint32_t x = w[kc >> 1] >> (16 * (kc & 1));                    // counts of points 2kc, 2kc+1 in the low two bytes
+        const uint2 a = lut[x & 15u], c = lut[(x >> 8) & 15u];
+        return make_uint4(a.x, a.y, c.x, c.y);
     }
-    return o;
+    if (kc == 24) {
+        const uint32_t m = w[12];                                            // bar1, bar2, off1, off2
+        return make_uint4(bar_off_pair_bf16((int)(m & 15u), (int)((m >> 16) & 15u)),
+                          bar_off_pair_bf16((int)((m >> 8) & 15u), (int)((m >> 24) & 15u)),
+                          flag == 0 ? 0x00003F80u : 0x3F800000u, 0x3F803F80u);
+    }
+    return make_uint4(0u, 0u, 0u, 0u);
 }
 // (rows beyond the batch in the last tile are built from whatever the staging buffer holds: their accumulators are
 // finite and never stored)

@@ -224,13 +224,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"((uint32_t)kTmemCols) : "memory");
 }
 
-// columns 198 / 199 carry the bias as a bf16 hi / lo pair (the A tile has 1.0 there): b ~ hi + lo to 2^-17 relative
+// W1 in the kernels' internal K order (bg_tcgen05.cuh): points first, bar/off/flags in columns 192..197, and the bias
+// as a bf16 hi / lo pair in columns 198 / 199 (the A tile has 1.0 there): b ~ hi + lo to 2^-17 relative
 __global__ void pack_w1_kernel(const float* __restrict__ w, const float* __restrict__ b, uint16_t* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= kHidden * kKPad) return;
     int h = i / kKPad, k = i - h * kKPad;
+    const int src = bg_w1_source_column(k);
     uint16_t v = 0;
-    if (k < BG_FEATURES) v = __bfloat16_as_ushort(__float2bfloat16_rn(w[h * BG_FEATURES + k]));
+    if (src >= 0) v = __bfloat16_as_ushort(__float2bfloat16_rn(w[h * BG_FEATURES + src]));
     else if (b && k == BG_FEATURES) v = __bfloat16_as_ushort(__float2bfloat16_rn(b[h]));
     else if (b && k == BG_FEATURES + 1) v = __bfloat16_as_ushort(__float2bfloat16_rn(b[h] - __bfloat162float(__float2bfloat16_rn(b[h]))));
     out[i] = v;
