@@ -107,8 +107,23 @@ __host__ __device__ __forceinline__ int bg_w1_source_column(int j) {      // int
     switch (j) { case 192: return 96; case 193: return 97; case 194: return 194; case 195: return 195; case 196: return 196; case 197: return 197; }
     return -1;
 }
+// shared-memory copy of the bar/2 and off/15 tables, placed right after the 16 units entries: lut[16 + k/2] holds
+// entries k of both tables for two k (a per-thread index into __constant__ memory is a serialised, long-latency load:
+// it was a third of the producers' stall samples)
+struct FeatureLut {
+    uint2 units[16];
+    uint16_t half[16];
+    uint16_t off15[16];
+};
+__device__ __forceinline__ void load_feature_lut(FeatureLut* t) {
+    if (threadIdx.x < 16) { t->units[threadIdx.x] = kUnitsBf16[threadIdx.x]; t->half[threadIdx.x] = kHalfBf16[threadIdx.x]; t->off15[threadIdx.x] = kOff15Bf16[threadIdx.x]; }
+}
+__device__ __forceinline__ uint32_t bar_off_pair_s(uint32_t bar, uint32_t off, const FeatureLut* t) {
+    return (uint32_t)t->half[bar & 15u] | ((uint32_t)t->off15[off & 15u] << 16);
+}
 // chunk kc (compile-time constant after unrolling) of the internal feature row of a position held as 13 words
-__device__ __forceinline__ uint4 feature_chunk_regs(const uint32_t (&w)[kBoardWords], int flag, int kc, const uint2* lut) {
+__device__ __forceinline__ uint4 feature_chunk_regs(const uint32_t (&w)[kBoardWords], int flag, int kc, const FeatureLut* ft) {
+    const uint2* lut = ft->units;
     if (kc < 24) {
         const uint32_t x = w[kc >> 1] >> (16 * (kc & 1));                    // counts of points 2kc, 2kc+1 in the low two bytes
         const uint2 a = lut[x & 15u], c = lut[(x >> 8) & 15u];
@@ -116,8 +131,7 @@ __device__ __forceinline__ uint4 feature_chunk_regs(const uint32_t (&w)[kBoardWo
     }
     if (kc == 24) {
         const uint32_t m = w[12];                                            // bar1, bar2, off1, off2
-        return make_uint4(bar_off_pair_bf16((int)(m & 15u), (int)((m >> 16) & 15u)),
-                          bar_off_pair_bf16((int)((m >> 8) & 15u), (int)((m >> 24) & 15u)),
+        return make_uint4(bar_off_pair_s(m, m >> 16, ft), bar_off_pair_s(m >> 8, m >> 24, ft),
                           flag == 0 ? 0x00003F80u : 0x3F800000u, 0x3F803F80u);
     }
     return make_uint4(0u, 0u, 0u, 0u);
@@ -125,7 +139,7 @@ __device__ __forceinline__ uint4 feature_chunk_regs(const uint32_t (&w)[kBoardWo
 // (rows beyond the batch in the last tile are built from whatever the staging buffer holds: their accumulators are
 // finite and never stored)
 template <int HALF>
-__device__ __forceinline__ void build_half_row(const uint32_t (&w)[kBoardWords], int flag, const uint2* lut, uint32_t tmem_row) {
+__device__ __forceinline__ void build_half_row(const uint32_t (&w)[kBoardWords], int flag, const FeatureLut* lut, uint32_t tmem_row) {
 #pragma unroll
     for (int i = 0; i < 13; ++i) {
         const int kc = HALF * 13 + i;

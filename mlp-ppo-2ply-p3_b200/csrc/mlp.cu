@@ -40,7 +40,7 @@ struct MlpSmem {
     float b1[kHidden];
     float wv[kHidden];
     float part[2][kTileM];             // partial value-head sums of the upper 64 hidden units
-    uint2 units[16];
+    FeatureLut flut;
     unsigned long long a_full[kStages], a_empty[kStages], acc_full[kStages], acc_empty[kStages];
     uint32_t tmem_base;
 };
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
         uint4 v = *reinterpret_cast<const uint4*>(w1 + (size_t)n * kKPad + kc * 8);
         *reinterpret_cast<uint4*>(S.W + kc * 2048 + n * 16) = v;
     }
-    load_units_lut(S.units);
+    load_feature_lut(&S.flut);
     if (tid < kHidden) { S.b1[tid] = BIAS ? b1[tid] : 0.0f; S.wv[tid] = wv[tid]; }
     if (tid == 0) {
 #pragma unroll
@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
             mbar_wait(&S.a_empty[s], (it & 1u) ^ 1u);           // MMAs that read A[s] two tiles ago are done
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kTmemACol0 + s * kAColsPerTile);
-            if (half == 0) build_half_row<0>(w, fl, S.units, trow);
-            else           build_half_row<1>(w, fl, S.units, trow);
+            if (half == 0) build_half_row<0>(w, fl, &S.flut, trow);
+            else           build_half_row<1>(w, fl, &S.flut, trow);
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             mbar_arrive(&S.a_full[s]);

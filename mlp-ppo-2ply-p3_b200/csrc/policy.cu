@@ -53,7 +53,7 @@ struct PolSmem {
     float part[4][kTileM];
     float red_m[4][kTileM], red_s[4][kTileM], red_g[4][kTileM], red_l[4][kTileM];
     int red_i[4][kTileM];
-    uint2 units[16];
+    FeatureLut flut;
     int rowidx[kTileM];                     // global row of each tile row (-1: none)
     unsigned long long bar1, bar2[2];
     uint32_t tmem_base;
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
         const int kc = c / kActPad, n = c - kc * kActPad;
         *reinterpret_cast<uint4*>(S.Wa + kc * (kActPad * 16) + n * 16) = *reinterpret_cast<const uint4*>(wa + (size_t)n * kHidden + kc * 8);
     }
-    load_units_lut(S.units);
+    load_feature_lut(&S.flut);
     if (tid < kHidden) { S.b1[tid] = b1 ? b1[tid] : 0.0f; S.wv[tid] = wv[tid]; }   // b1 == NULL: folded into W1 (bg_pack_w1)
     S.ba[tid] = tid < kActions ? ba[tid] : 0.0f;                 // kPolThreads == kActPad
     if (tid == 0) {
@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
             const int pg = S.rowidx[prow];
             const int fl = pg >= 0 ? (int)((flags ? flags[pg] : flag_all) & 1) : 0;
             const uint32_t trow = lane_base + (uint32_t)kColA;
-            if (half == 0) build_half_row<0>(w, fl, S.units, trow);
-            else           build_half_row<1>(w, fl, S.units, trow);
+            if (half == 0) build_half_row<0>(w, fl, &S.flut, trow);
+            else           build_half_row<1>(w, fl, &S.flut, trow);
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
