@@ -164,8 +164,9 @@ int bg_update_legal_plays(const int8_t* boards52, const int8_t* players, const i
  * v = w_v . relu(W1 x + b1) + b_v, fused with the feature encoding: input is board52 + flag, the
  * 198-wide bf16 rows are built in shared memory and multiplied on the tcgen05 tensor cores
  * (bf16 x bf16 -> f32 in TMEM); the hidden layer is reduced in the epilogue straight out of TMEM.
- *   w1_bf16: [128][208] bf16 as written by bg_pack_w1 -- an OPAQUE operand tile: fc1.weight in the kernels' internal K
- *   order (points first, bar/off/flags last), then (fc1_bias != NULL) the bias as a bf16 hi/lo pair in columns 198, 199
+ *   w1_bf16: 128 x 208 bf16 as written by bg_pack_w1 -- an OPAQUE operand tile (tcgen05 K-major no-swizzle layout, so
+ *   that a kernel loads it with a straight copy): fc1.weight in the kernels' internal K order (points first,
+ *   bar/off/flags last), then (fc1_bias != NULL) the bias as a bf16 hi/lo pair in columns 198, 199
  *   -- the kernels put 1.0 there in the A tile, so the bias comes out of the GEMM and b1 must then be passed as NULL --
  *   then zeros.  With fc1_bias == NULL those columns are zero and b1 is added explicitly.
  *   flags / flag_all as in K3; flip_flags = 1 evaluates every row with the OTHER player's flag.
@@ -188,7 +189,8 @@ int bg_mlp_value(const int8_t* boards52, const int8_t* flags, int flag_all, int 
  * logits_out != NULL).  The mask is the env's prefix mask: slot k is legal iff k < legal_counts[b]
  * (environment/backgammon_env.py:228-231); legal_counts == NULL = all 500 legal.  With no legal slot (a pass) the
  * reference samples from all 500 slots; so does this.
- *   wa_bf16: [512][128] bf16, row n = action_head.weight[n] (rows 500..511 zero; bg_pack_wa), ba: [500] f32;
+ *   wa_bf16: 512 x 128 bf16 as written by bg_pack_wa (opaque: action_head.weight, rows 500..511 zero, in the tcgen05
+ *   operand layout), ba: [500] f32;
  *   w1_bf16 / b1 as in bg_mlp_value (b1 == NULL: bias folded into w1_bf16).
  *   sampling: Gumbel-max with Philox4x32-10 keyed by seed, counter (stream_base + b, step, slot): reproducible
  *   and independent of the batch split; greedy = 1 takes argmax (lowest slot on ties) like the inference mode.

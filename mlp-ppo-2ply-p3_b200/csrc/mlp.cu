@@ -81,10 +81,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
     const long long begin = row_begin_dev ? min(B, (long long)*row_begin_dev) : 0;      // rows [begin, B)
 
     // ---- one-time setup: W1 into the operand layout, biases, mbarriers, TMEM (2 x 128 columns)
-    for (int c = tid; c < kChunks * kHidden; c += kMlpThreads) {
-        int kc = c / kHidden, n = c - kc * kHidden;             // consecutive threads -> consecutive n: conflict-free stores
-        uint4 v = *reinterpret_cast<const uint4*>(w1 + (size_t)n * kKPad + kc * 8);
-        *reinterpret_cast<uint4*>(S.W + kc * 2048 + n * 16) = v;
+    {   // w1 is stored in global memory in the operand layout (bg_pack_w1): a straight, coalesced, asynchronous copy
+        const uint32_t w_s = smem_u32(S.W);
+        for (int c = tid; c < kOperandBytes / 16; c += kMlpThreads) cp_async16_s(w_s + 16u * c, reinterpret_cast<const unsigned char*>(w1) + 16 * c);
+        cp_async_commit();
+        cp_async_wait_all();
     }
     load_feature_lut(&S.flut);
     if (tid < kHidden) { S.b1[tid] = BIAS ? b1[tid] : 0.0f; S.wv[tid] = wv[tid]; }
@@ -229,13 +230,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
 __global__ void pack_w1_kernel(const float* __restrict__ w, const float* __restrict__ b, uint16_t* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= kHidden * kKPad) return;
-    int h = i / kKPad, k = i - h * kKPad;
+    int h = i / kKPad, k = i - h * kKPad;                    // hidden unit (operand row), internal K column
     const int src = bg_w1_source_column(k);
     uint16_t v = 0;
     if (src >= 0) v = __bfloat16_as_ushort(__float2bfloat16_rn(w[h * BG_FEATURES + src]));
     else if (b && k == BG_FEATURES) v = __bfloat16_as_ushort(__float2bfloat16_rn(b[h]));
     else if (b && k == BG_FEATURES + 1) v = __bfloat16_as_ushort(__float2bfloat16_rn(b[h] - __bfloat162float(__float2bfloat16_rn(b[h]))));
-    out[i] = v;
+    out[(k >> 3) * (kHidden * 8) + h * 8 + (k & 7)] = v;      // tcgen05 K-major no-swizzle operand layout: (k/8)*2048 B + row*16 B + (k%8)*2 B
 }
 
 }  // namespace bg
