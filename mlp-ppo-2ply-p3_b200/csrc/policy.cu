@@ -48,13 +48,13 @@ constexpr int kColAcc1 = 0, kColA = 128, kColAcc2 = 256;
 struct PolSmem {
     uint8_t W1[kW1Bytes];
     uint8_t Wa[kWaBytes];
-    uint32_t boards[kTileM * kBoardWords];
+    uint32_t boards[2][kTileM * kBoardWords];   // double buffered: the next tile's rows are gathered during this tile's GEMMs
     float b1[kHidden], wv[kHidden], ba[kActPad];
     float part[4][kTileM];
     float red_m[4][kTileM], red_s[4][kTileM], red_g[4][kTileM], red_l[4][kTileM];
     int red_i[4][kTileM];
     FeatureLut flut;
-    int rowidx[kTileM];                     // global row of each tile row (-1: none)
+    int rowidx[2][kTileM];                  // global row of each tile row (-1: none)
     unsigned long long bar1, bar2[2];
     uint32_t tmem_base;
 };
@@ -110,42 +110,59 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t ph1 = 0, ph2[2] = {0, 0};
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const bool class_a = tile < tilesA;
-        const long long first = class_a ? tile * kTileM : (tile - tilesA) * kTileM;      // position in the class
-        const int rows = (int)min((long long)kTileM, (class_a ? nA : B - nA) - first);
-        const int n_chunks = class_a ? 1 : 4;
-        // ---- A: the tile's rows, then their boards (gathered)
-        if (tid < kTileM) {
-            int g = -1;
-            if (tid < rows) {
-                const long long pos = class_a ? first + tid : (row_list ? B - 1 - (first + tid) : first + tid);
-                g = row_list ? row_list[pos] : (int)pos;
-            }
-            S.rowidx[tid] = g;
-        }
-        __syncthreads();
+    // rows of a tile: class, position in its class, number of rows, global row of tile row r
+    auto tile_row = [&](long long tile, int r) -> int {
+        const bool ca = tile < tilesA;
+        const long long first = ca ? tile * kTileM : (tile - tilesA) * kTileM;
+        const long long n_class = ca ? nA : B - nA;
+        if (first + r >= n_class) return -1;
+        const long long pos = ca ? first + r : (row_list ? B - 1 - (first + r) : first + r);
+        return row_list ? row_list[pos] : (int)pos;
+    };
+    const uint32_t boards_s[2] = {smem_u32(&S.boards[0][0]), smem_u32(&S.boards[1][0])};
+    // gather the boards of the rows listed in S.rowidx[b] into S.boards[b] (asynchronously)
+    auto gather = [&](int b) {
         for (int i = tid; i < kTileM * kBoardWords; i += kPolThreads) {
             const int r = i / kBoardWords, wd = i - r * kBoardWords;
-            const int g = S.rowidx[r];
-            S.boards[i] = g >= 0 ? __ldg(reinterpret_cast<const uint32_t*>(boards + (long long)g * kBoardBytes) + wd) : 0u;
+            const int g = S.rowidx[b][r];
+            if (g >= 0) cp_async4_s(boards_s[b] + 4u * i, reinterpret_cast<const uint32_t*>(boards + (long long)g * kBoardBytes) + wd);
+            else S.boards[b][i] = 0u;
         }
+        cp_async_commit();
+    };
+    if ((long long)blockIdx.x < n_tiles) {                          // prologue: the first tile
+        if (tid < kTileM) S.rowidx[0][tid] = tile_row(blockIdx.x, tid);
+        __syncthreads();
+        gather(0);
+    }
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int bsel = it & 1;
+        const bool class_a = tile < tilesA;
+        const int n_chunks = class_a ? 1 : 4;
+        const long long next_tile = tile + gridDim.x;
+        // ---- A: this tile's boards have been gathered during the previous tile; the list of the next tile is read now
+        int next_g = -1;
+        if (tid < kTileM && next_tile < n_tiles) next_g = tile_row(next_tile, tid);
+        cp_async_wait_all();
         __syncthreads();
         // ---- B: feature rows -> TMEM (two threads per position; warps 0-3 chunks 0-12, warps 4-7 chunks 13-25)
         if (warp < 8) {
             const int prow = tid & (kTileM - 1), half = tid >> 7;
             uint32_t w[kBoardWords];
 #pragma unroll
-            for (int i = 0; i < kBoardWords; ++i) w[i] = S.boards[prow * kBoardWords + i];
-            const int pg = S.rowidx[prow];
+            for (int i = 0; i < kBoardWords; ++i) w[i] = S.boards[bsel][prow * kBoardWords + i];
+            const int pg = S.rowidx[bsel][prow];
             const int fl = pg >= 0 ? (int)((flags ? flags[pg] : flag_all) & 1) : 0;
             const uint32_t trow = lane_base + (uint32_t)kColA;
             if (half == 0) build_half_row<0>(w, fl, &S.flut, trow);
             else           build_half_row<1>(w, fl, &S.flut, trow);
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         }
+        if (tid < kTileM) S.rowidx[bsel ^ 1][tid] = next_g;
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
         __syncthreads();
+        if (next_tile < n_tiles) gather(bsel ^ 1);                 // lands while the GEMMs and the epilogues of this tile run
         // ---- C: hidden layer GEMM
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -191,7 +208,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
             umma_commit(&S.bar2[c & 1]);
         };
         if (tid == 0) { issue_chunk(0); if (n_chunks > 1) issue_chunk(1); }
-        const long long gid = S.rowidx[row];                      // row index within this call (-1: none)
+        const long long gid = S.rowidx[bsel][row];                      // row index within this call (-1: none)
         const int n_legal = (gid >= 0 && legal_counts) ? legal_counts[gid] : (legal_counts ? 1 : kActions);
         const unsigned long long sid = stream_base + (unsigned long long)(gid >= 0 ? gid : 0);   // global stream id (game id)
         // class A: this warp's 32 slots of chunk 0 matter only if some row of the warp has more than 32 cq legal slots
@@ -259,7 +276,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
         // ---- F: combine the four column quarters of each row
         S.red_m[cq][row] = m; S.red_s[cq][row] = s; S.red_g[cq][row] = gbest; S.red_l[cq][row] = lbest; S.red_i[cq][row] = ibest;
         __syncthreads();
-        if (tid < rows) {
+        if (tid < kTileM && S.rowidx[bsel][tid] >= 0) {
             const int r = tid;
             float M = S.red_m[0][r];
 #pragma unroll
@@ -272,7 +289,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
                 const float g = S.red_g[k][r];
                 if (g > gb || (g == gb && g > -INFINITY && S.red_i[k][r] < ib)) { gb = g; lb = S.red_l[k][r]; ib = S.red_i[k][r]; }
             }
-            const long long g = S.rowidx[r];
+            const long long g = S.rowidx[bsel][r];
             actions[g] = ib;
             if (logp) logp[g] = lb - (M + __logf(sum));
             if (values) values[g] = bv + ((S.part[0][r] + S.part[1][r]) + (S.part[2][r] + S.part[3][r]));
