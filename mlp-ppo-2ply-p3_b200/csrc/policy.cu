@@ -57,6 +57,7 @@ struct PolSmem {
     int rowidx[2][kTileM];                  // global row of each tile row (-1: none)
     unsigned long long bar1, bar2[2];
     uint32_t tmem_base;
+    unsigned int tile_slot;                 // next tile index (dynamic schedule), broadcast by thread 0
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
     const int32_t* __restrict__ legal_counts, const uint16_t* __restrict__ w1, const float* __restrict__ b1,
     const uint16_t* __restrict__ wa, const float* __restrict__ ba, const float* __restrict__ wv, float bv,
     unsigned long long seed, unsigned long long stream_base, uint32_t step, int greedy,
-    const int32_t* __restrict__ row_list, const unsigned int* __restrict__ n_class_a_dev,
+    const int32_t* __restrict__ row_list, const unsigned int* __restrict__ n_class_a_dev, unsigned int* __restrict__ tile_ctr,
     int32_t* __restrict__ actions, float* __restrict__ logp, float* __restrict__ values, float* __restrict__ logits_out) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     PolSmem& S = *reinterpret_cast<PolSmem*>(smem_raw);
@@ -111,9 +112,11 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
     uint32_t ph1 = 0, ph2[2] = {0, 0};
 
     // rows of a tile: class, position in its class, number of rows, global row of tile row r
+    // tile order: the (few, 5-6 x more expensive) class B tiles first, then class A; with a tile counter the CTAs pull
+    // tiles dynamically so that a CTA holding a heavy tile takes fewer light ones
     auto tile_row = [&](long long tile, int r) -> int {
-        const bool ca = tile < tilesA;
-        const long long first = ca ? tile * kTileM : (tile - tilesA) * kTileM;
+        const bool ca = tile >= tilesB;
+        const long long first = ca ? (tile - tilesB) * kTileM : tile * kTileM;
         const long long n_class = ca ? nA : B - nA;
         if (first + r >= n_class) return -1;
         const long long pos = ca ? first + r : (row_list ? B - 1 - (first + r) : first + r);
@@ -130,22 +133,28 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
         }
         cp_async_commit();
     };
-    if ((long long)blockIdx.x < n_tiles) {                          // prologue: the first tile
-        if (tid < kTileM) S.rowidx[0][tid] = tile_row(blockIdx.x, tid);
+    long long tile = blockIdx.x;
+    if (tile_ctr) {
+        if (tid == 0) S.tile_slot = atomicAdd(tile_ctr, 1u);
+        __syncthreads();
+        tile = S.tile_slot;
+    }
+    if (tile < n_tiles) {                                           // prologue: the first tile
+        if (tid < kTileM) S.rowidx[0][tid] = tile_row(tile, tid);
         __syncthreads();
         gather(0);
     }
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (int it = 0; tile < n_tiles; ++it) {
         const int bsel = it & 1;
-        const bool class_a = tile < tilesA;
+        const bool class_a = tile >= tilesB;
         const int n_chunks = class_a ? 1 : 4;
-        const long long next_tile = tile + gridDim.x;
-        // ---- A: this tile's boards have been gathered during the previous tile; the list of the next tile is read now
-        int next_g = -1;
-        if (tid < kTileM && next_tile < n_tiles) next_g = tile_row(next_tile, tid);
+        // ---- A: this tile's boards have been gathered during the previous tile; the next tile is chosen and its row list read now
+        if (tile_ctr && tid == 0) S.tile_slot = atomicAdd(tile_ctr, 1u);
         cp_async_wait_all();
         __syncthreads();
+        const long long next_tile = tile_ctr ? (long long)S.tile_slot : tile + gridDim.x;
+        int next_g = -1;
+        if (tid < kTileM && next_tile < n_tiles) next_g = tile_row(next_tile, tid);
         // ---- B: feature rows -> TMEM (two threads per position; warps 0-3 chunks 0-12, warps 4-7 chunks 13-25)
         if (warp < 8) {
             const int prow = tid & (kTileM - 1), half = tid >> 7;
@@ -295,6 +304,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
             if (values) values[g] = bv + ((S.part[0][r] + S.part[1][r]) + (S.part[2][r] + S.part[3][r]));
         }
         __syncthreads();
+        tile = next_tile;
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
@@ -353,23 +363,28 @@ extern "C" int bg_policy_sample(const int8_t* boards52, const int8_t* flags, int
     const size_t smem = sizeof(PolSmem) + 1024;
     cudaError_t e = cudaFuncSetAttribute(policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return bg_set_error(e, "bg_policy_sample: cudaFuncSetAttribute");
-    // two row classes (1..128 legal slots / the rest) when there is a mask, a workspace, and the logits are not wanted
+    // with a workspace: dynamic tile schedule, and -- when there is a mask and the logits are not wanted -- the two row
+    // classes (1..128 legal slots / the rest)
     const int32_t* row_list = nullptr;
     const unsigned int* n_a = nullptr;
-    if (legal_counts && workspace && !logits_out) {
+    unsigned int* tile_ctr = nullptr;
+    if (workspace) {
         if (workspace_bytes < bg_policy_workspace_bytes(B)) return bg_set_error_msg(BG_ERR_INVALID, "bg_policy_sample: workspace too small");
-        unsigned int* ctr = static_cast<unsigned int*>(workspace);
-        int32_t* list = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(workspace) + 16);
+        unsigned int* ctr = static_cast<unsigned int*>(workspace);      // [0] class A rows, [1] class B rows, [2] next tile
         e = cudaMemsetAsync(ctr, 0, 16, (cudaStream_t)stream);
         if (e != cudaSuccess) return bg_set_error(e, "bg_policy_sample: memset");
-        policy_partition_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(legal_counts, B, list, ctr);
-        row_list = list; n_a = ctr;
+        tile_ctr = ctr + 2;
+        if (legal_counts && !logits_out) {
+            int32_t* list = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(workspace) + 16);
+            policy_partition_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(legal_counts, B, list, ctr);
+            row_list = list; n_a = ctr;
+        }
     }
     long long tiles = (B + kTileM - 1) / kTileM + 1;
     long long grid = bg_sm_count();
     if (grid > tiles) grid = tiles;
     policy_kernel<<<(unsigned)grid, kPolThreads, smem, (cudaStream_t)stream>>>(
         boards52, flags, flag_all & 1, B, legal_counts, w1_bf16, b1, wa_bf16, ba, wv, bv, seed, stream_base, step, greedy,
-        row_list, n_a, actions, log_probs, values, logits_out);
+        row_list, n_a, tile_ctr, actions, log_probs, values, logits_out);
     return bg_set_error(cudaGetLastError(), "bg_policy_sample: launch");
 }
