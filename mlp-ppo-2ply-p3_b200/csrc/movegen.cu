@@ -22,15 +22,13 @@
 // indices coincide, and the env's "first max_legal_moves" truncation
 // (src/environment/backgammon_env.py:218-223) is a plain prefix.
 #include "bg_device.cuh"
+#include "bg_movegen_common.cuh"
 #include "bg_features.cuh"
 #include "bg_internal.h"
 
 namespace bg {
 
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
-
-__device__ __constant__ int8_t kRoll21[21][2] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {2, 2}, {2, 3}, {2, 4}, {2, 5}, {2, 6},
-                                                {3, 3}, {3, 4}, {3, 5}, {3, 6}, {4, 4}, {4, 5}, {4, 6}, {5, 5}, {5, 6}, {6, 6}};
 
 // Per-warp scratch.  Two level lists ("regions") of CAP boards each plus one slot for the root:
 // node i of region r lives at index r*CAP + i, the root at 2*CAP.  A board is a 16-byte key
@@ -286,44 +284,15 @@ __global__ void __launch_bounds__(256) movegen_kernel(
         if ((long long)wi >= nwork) break;
         const long long g = worklist ? (long long)worklist[wi] : (long long)wi;
 
-        // ---- load the root (13 words, coalesced) and build the mover-relative view
-        // replicate == 21: work item g is (position g / 21, sorted roll g % 21) -- the 2-ply opponent expansion
-        // in the roll order of get_all_dice_rolls_tensor (moves/get_all_dice_rolls.py:19-32)
+        // ---- the work item, its root (13 words, coalesced) and the mover-relative view (bg_movegen_common.cuh)
         const long long src = replicate > 1 ? g / replicate : g;
-        const uint32_t* bw = reinterpret_cast<const uint32_t*>(boards + src * kBoardBytes);
-        uint32_t w = lane < kBoardWords ? bw[lane] : 0u;
-        if (lane < kBoardWords) S.rootw[lane] = w;
-        const int player = (players[src] ^ flip_player) & 1;
-        int d0, d1;
-        if (replicate > 1) { const int r = (int)(g - src * replicate); d0 = kRoll21[r][0]; d1 = kRoll21[r][1]; }
-        else { d0 = dice[2 * g]; d1 = dice[2 * g + 1]; }
-        const int p = lane < 24 ? lane : 0;
-        uint32_t ownw = __shfl_sync(kFull, w, (player ? 6 : 0) + (p >> 2));
-        uint32_t oppw = __shfl_sync(kFull, w, (player ? 0 : 6) + (p >> 2));
-        uint32_t misc = __shfl_sync(kFull, w, 12);
-        int ownc = lane < 24 ? (int)((ownw >> (8 * (p & 3))) & 0xFFu) : 0;
-        int oppc = lane < 24 ? (int)((oppw >> (8 * (p & 3))) & 0xFFu) : 0;
-        int ownbar = (int)((misc >> (player ? 8 : 0)) & 0xFFu), ownoff = (int)((misc >> (player ? 24 : 16)) & 0xFFu);
+        const uint32_t bword = load_board_word(boards, src, lane);
+        const WorkItem item = decode_work_item(g, src, replicate, flip_player, players, dice);
+        const int player = item.player, d0 = item.d0, d1 = item.d1;
         Warp<CAP, HS> W(S, lane);
-        W.R.player = player;
-        W.R.block = __ballot_sync(kFull, oppc >= 2) & 0xFFFFFFu;
-        W.R.blot = __ballot_sync(kFull, oppc == 1) & 0xFFFFFFu;
         Node root;
-        root.occ = __ballot_sync(kFull, ownc > 0) & 0xFFFFFFu;
-        root.hit = 0;
-        root.last = 31u;
-        W.R.cnt2 = __ballot_sync(kFull, ownc >= 2) & 0xFFFFFFu;
-        W.R.mA = 0;
-        uint32_t nib = (uint32_t)(ownc & 15) << (4 * (p & 7));
-        uint32_t w0 = __reduce_or_sync(kFull, (lane < 8) ? nib : 0u);
-        uint32_t w1 = __reduce_or_sync(kFull, (lane >= 8 && lane < 16) ? nib : 0u);
-        uint32_t w2 = __reduce_or_sync(kFull, (lane >= 16 && lane < 24) ? nib : 0u);
-        root.lo = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
-        root.hi = (unsigned long long)w2 | ((unsigned long long)((ownbar & 15) | ((ownoff & 15) << 4)) << 32);
-        int total = __reduce_add_sync(kFull, ownc) + ownbar + ownoff;
-        W.R.tot15 = total == 15;
-        bool bad = __any_sync(kFull, ownc > 15 || oppc > 15) || ownbar > 15 || ownoff > 15 ||
-                   d0 < 1 || d0 > 6 || d1 < 1 || d1 > 6;
+        const bool bad = !build_root(bword, player, lane, S.rootw, W.R, root) ||
+                         d0 < 1 || d0 > 6 || d1 < 1 || d1 > 6;
         __syncwarp();
 
         int obase = 0, n = 0;
@@ -371,23 +340,11 @@ __global__ void __launch_bounds__(256) movegen_kernel(
                 // stage 32 rows x 13 words in the region that does not hold the result, then copy out coalesced
                 uint32_t* stage = reinterpret_cast<uint32_t*>(&S.key[obase < CAP ? CAP : 0]);
                 uint32_t* gout = reinterpret_cast<uint32_t*>(after) + start * kBoardWords;
-                const int own0 = player ? 6 : 0, opp0 = player ? 0 : 6;
-                const uint32_t misc0 = S.rootw[12];
-                const uint32_t opp_bar0 = (misc0 >> (player ? 0 : 8)) & 0xFFu, opp_off0 = (misc0 >> (player ? 16 : 24)) & 0xFFu;
+                const RowContext rc = make_row_context(player, S.rootw);
                 for (int r0 = 0; r0 < nw; r0 += 32) {
                     int r = r0 + lane;
                     if (r < nw) {
-                        const uint4 k = S.key[obase + r];
-                        uint32_t* row = stage + lane * kBoardWords;
-                        row[own0 + 0] = spread_nibbles(k.x);       row[own0 + 1] = spread_nibbles(k.x >> 16);
-                        row[own0 + 2] = spread_nibbles(k.y);       row[own0 + 3] = spread_nibbles(k.y >> 16);
-                        row[own0 + 4] = spread_nibbles(k.z);       row[own0 + 5] = spread_nibbles(k.z >> 16);
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) row[opp0 + q] = S.rootw[opp0 + q] - spread_bits(k.w >> (4 * q));
-                        const uint32_t ob = (k.w >> 24) & 15u, oo = k.w >> 28;
-                        const uint32_t pb = opp_bar0 + (uint32_t)__popc(k.w & 0xFFFFFFu);
-                        row[12] = player == 0 ? (ob | (pb << 8) | (oo << 16) | (opp_off0 << 24))
-                                              : (pb | (ob << 8) | (opp_off0 << 16) | (oo << 24));
+                        build_row(S.key[obase + r], player, rc, S.rootw, stage + lane * kBoardWords);
                     }
                     __syncwarp();
                     int rows = min(32, nw - r0);

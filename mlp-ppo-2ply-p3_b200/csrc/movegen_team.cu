@@ -13,6 +13,7 @@
 // candidate order (ballot + per-warp counts) and commit their slots to list indices.
 #include <cstdlib>
 #include "bg_device.cuh"
+#include "bg_movegen_common.cuh"
 #include "bg_features.cuh"
 #include "bg_internal.h"
 
@@ -21,9 +22,6 @@ namespace bg {
 namespace {
 constexpr uint32_t kEmptyT = 0xFFFFFFFFu;
 constexpr uint32_t kPend = 0x80000000u;
-
-__device__ __constant__ int8_t kRoll21T[21][2] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {2, 2}, {2, 3}, {2, 4}, {2, 5}, {2, 6},
-                                                  {3, 3}, {3, 4}, {3, 5}, {3, 6}, {4, 4}, {4, 5}, {4, 6}, {5, 5}, {5, 6}, {6, 6}};
 
 template <int CAP, int HS, int T>
 struct TeamScratch {
@@ -283,40 +281,13 @@ __global__ void __launch_bounds__(T) movegen_team_kernel(
         const long long wi = (long long)(unsigned int)S.bcast[1];
         if (wi >= nwork) break;
         const long long g = (long long)worklist[wi];
-        const long long src = replicate > 1 ? g / replicate : g;
-        const int player = (players[src] ^ flip_player) & 1;
-        int d0, d1;
-        if (replicate > 1) { const int r = (int)(g - src * replicate); d0 = kRoll21T[r][0]; d1 = kRoll21T[r][1]; }
-        else { d0 = dice[2 * g]; d1 = dice[2 * g + 1]; }
-        if (warp == 0) {                                  // root load: warp-collective, as in movegen.cu
-            const uint32_t* bw = reinterpret_cast<const uint32_t*>(boards + src * kBoardBytes);
-            uint32_t w = lane < kBoardWords ? bw[lane] : 0u;
-            if (lane < kBoardWords) S.rootw[lane] = w;
-            const int p = lane < 24 ? lane : 0;
-            uint32_t ownw = __shfl_sync(kFull, w, (player ? 6 : 0) + (p >> 2));
-            uint32_t oppw = __shfl_sync(kFull, w, (player ? 0 : 6) + (p >> 2));
-            uint32_t misc = __shfl_sync(kFull, w, 12);
-            int ownc = lane < 24 ? (int)((ownw >> (8 * (p & 3))) & 0xFFu) : 0;
-            int oppc = lane < 24 ? (int)((oppw >> (8 * (p & 3))) & 0xFFu) : 0;
-            int ownbar = (int)((misc >> (player ? 8 : 0)) & 0xFFu), ownoff = (int)((misc >> (player ? 24 : 16)) & 0xFFu);
+        const WorkItem item = decode_work_item(g, replicate > 1 ? g / replicate : g, replicate, flip_player, players, dice);
+        const int player = item.player, d0 = item.d0, d1 = item.d1;
+        if (warp == 0) {                                  // root: warp-collective, shared with movegen.cu (tier 0 already rejected malformed boards)
             Root R; Node root;
-            R.player = player;
-            R.block = __ballot_sync(kFull, oppc >= 2) & 0xFFFFFFu;
-            R.blot = __ballot_sync(kFull, oppc == 1) & 0xFFFFFFu;
-            root.occ = __ballot_sync(kFull, ownc > 0) & 0xFFFFFFu;
-            root.hit = 0;
-            root.last = 31u;
-            R.cnt2 = __ballot_sync(kFull, ownc >= 2) & 0xFFFFFFu;
-            R.mA = 0;
-            uint32_t nib = (uint32_t)(ownc & 15) << (4 * (p & 7));
-            uint32_t w0 = __reduce_or_sync(kFull, (lane < 8) ? nib : 0u);
-            uint32_t w1 = __reduce_or_sync(kFull, (lane >= 8 && lane < 16) ? nib : 0u);
-            uint32_t w2 = __reduce_or_sync(kFull, (lane >= 16 && lane < 24) ? nib : 0u);
-            root.lo = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
-            root.hi = (unsigned long long)w2 | ((unsigned long long)((ownbar & 15) | ((ownoff & 15) << 4)) << 32);
-            R.tot15 = (__reduce_add_sync(kFull, ownc) + ownbar + ownoff) == 15;
+            build_root(load_board_word(boards, item.src, lane), player, lane, S.rootw, R, root);
             if (d0 != d1) { uint32_t mA; int sA; one_die(root, R, max(d0, d1), mA, sA); R.mA = mA; }   // larger-die sources at the root
-            if (lane == 0) { S.root = root; S.R = R; }   // (tier 0 already rejected malformed boards)
+            if (lane == 0) { S.root = root; S.R = R; }
         }
         __syncthreads();
         Team<CAP, HS, T> W(S);
@@ -354,24 +325,12 @@ __global__ void __launch_bounds__(T) movegen_team_kernel(
             } else {
                 uint32_t* stage = reinterpret_cast<uint32_t*>(&S.key[obase < CAP ? CAP : 0]);
                 uint32_t* gout = reinterpret_cast<uint32_t*>(after) + start * kBoardWords;
-                const int own0 = player ? 6 : 0, opp0 = player ? 0 : 6;
-                const uint32_t misc0 = S.rootw[12];
-                const uint32_t opp_bar0 = (misc0 >> (player ? 0 : 8)) & 0xFFu, opp_off0 = (misc0 >> (player ? 16 : 24)) & 0xFFu;
+                const RowContext rc = make_row_context(player, S.rootw);
                 constexpr int SR = Team<CAP, HS, T>::kStageRows;
                 for (int r0 = 0; r0 < nw; r0 += SR) {
                     int r = r0 + tid;
                     if (tid < SR && r < nw) {
-                        const uint4 k = S.key[obase + r];
-                        uint32_t* row = stage + tid * kBoardWords;
-                        row[own0 + 0] = spread_nibbles(k.x);       row[own0 + 1] = spread_nibbles(k.x >> 16);
-                        row[own0 + 2] = spread_nibbles(k.y);       row[own0 + 3] = spread_nibbles(k.y >> 16);
-                        row[own0 + 4] = spread_nibbles(k.z);       row[own0 + 5] = spread_nibbles(k.z >> 16);
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) row[opp0 + q] = S.rootw[opp0 + q] - spread_bits(k.w >> (4 * q));
-                        const uint32_t ob = (k.w >> 24) & 15u, oo = k.w >> 28;
-                        const uint32_t pb = opp_bar0 + (uint32_t)__popc(k.w & 0xFFFFFFu);
-                        row[12] = player == 0 ? (ob | (pb << 8) | (oo << 16) | (opp_off0 << 24))
-                                              : (pb | (ob << 8) | (opp_off0 << 16) | (oo << 24));
+                        build_row(S.key[obase + r], player, rc, S.rootw, stage + tid * kBoardWords);
                     }
                     __syncthreads();
                     int rows = min(SR, nw - r0);
