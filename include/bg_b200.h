@@ -221,12 +221,16 @@ int bg_gae(const float* rewards, const uint8_t* dones, const float* values /*nul
  * surrogate, MSE, their weighted sum) and its gradient w.r.t. the network outputs, one pass over the logits:
  *   logits / dlogits: [B][ld] bf16 (logits_bf16 = 1) or f32, ld >= 500 and a multiple of 4; values, returns, advantages,
  *   old_log_probs: [B] f32; counts: legal slots per sample (prefix mask); actions: taken slot.
- *   dlogits = d loss / d logits, dvalues = d loss / d values (both already divided by B);
+ *   dlogits = d loss / d logits (columns 500 .. ld-1 are written as zeros), dvalues = d loss / d values (both already
+ *   divided by B); dbias[0..min(ld,512)-1] += column sums of dlogits = d loss / d action_head.bias (nullable; caller zeroes).
+ *   values == NULL: the value head was computed as row 500 of the action head's GEMM -- the value is read from column 500
+ *   of the logits (ld >= 504), d loss / d value is written to column 500 of dlogits (and to dvalues if non-null) and its
+ *   sum to dbias[500], so the value head's backward rides through the action head's backward GEMMs.
  *   sums[0..2] += sum_i policy term, sum_i (v - R)^2, sum_i entropy  (caller zeroes; loss = (s0 + c_v s1 - c_e s2) / B). */
 int bg_ppo_loss_grad(const void* logits, int logits_bf16, long long ld, const float* values, const int32_t* counts,
                      const int32_t* actions, const float* old_log_probs, const float* advantages, const float* returns,
                      long long B, float eps_clip, float value_coef, float entropy_coef, void* dlogits, float* dvalues,
-                     float* sums, void* stream);
+                     float* dbias /*nullable*/, float* sums, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K5  2-ply search (the reference's own 2-ply, moves/expect_minmax.py:1-206, is

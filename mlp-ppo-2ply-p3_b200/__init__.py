@@ -12,8 +12,8 @@ from .engine import (FEATURES, LD_BF16, MovegenWorkspace, encode, from_board52, 
 from .sharding import reduce_report, shard_range  # noqa: F401
 from .value_net import ValueNet  # noqa: F401
 from .policy_net import PolicyValueNet  # noqa: F401
-from .ppo import PPOConfig, PPOLearner, PPOTrainer, evaluate_vs_random  # noqa: F401
+from .ppo import ManualUpdate, PPOConfig, PPOLearner, PPOTrainer, evaluate_vs_random  # noqa: F401
 from .twoply import TwoPlySearch, greedy_actions, segment_argmax  # noqa: F401
-from .vec_env import B200BackgammonVecEnv, StepInfos, VectorizedBackgammonEnv  # noqa: F401
+from .vec_env import B200BackgammonVecEnv, HostStepBuffers, StepInfos, VectorizedBackgammonEnv  # noqa: F401
 
 __version__ = "0.1.0"

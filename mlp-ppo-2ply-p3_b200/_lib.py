@@ -55,7 +55,7 @@ SIGNATURES = {
     "bg_policy_workspace_bytes": (_SZ, [_LL]),
     "bg_policy_sample": (_I, [_V, _V, _I, _LL, _V, _V, _V, _V, _V, _V, _F, _U64, _U64, _U32, _I, _V, _V, _V, _V, _V, _SZ, _V]),
     "bg_gae": (_I, [_V, _V, _V, _V, _I, _LL, _F, _F, _V, _V, _V]),
-    "bg_ppo_loss_grad": (_I, [_V, _I, _LL, _V, _V, _V, _V, _V, _V, _LL, _F, _F, _F, _V, _V, _V, _V]),
+    "bg_ppo_loss_grad": (_I, [_V, _I, _LL, _V, _V, _V, _V, _V, _V, _LL, _F, _F, _F, _V, _V, _V, _V, _V]),
     "bg_pack_w1": (_I, [_V, _V, _V, _V]),
     "bg_mlp_value": (_I, [_V, _V, _I, _I, _LL, _V, _V, _V, _V, _F, _I, _V, _V]),
 }

@@ -51,12 +51,17 @@ __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewa
 // (torch.min splits the gradient of a tie in halves, which sums to the same thing: inside the range both branches are r A.)
 template <typename T> struct Vec4;
 template <> struct Vec4<float> {
-    static __device__ __forceinline__ void load(const float* p, float (&x)[4]) { float4 v = *reinterpret_cast<const float4*>(p); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+    using Raw = float4;
+    static __device__ __forceinline__ Raw zero() { return make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+    static __device__ __forceinline__ Raw load_raw(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+    static __device__ __forceinline__ void unpack(const Raw& v, float (&x)[4]) { x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
     static __device__ __forceinline__ void store(float* p, const float (&x)[4]) { *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]); }
 };
 template <> struct Vec4<__nv_bfloat16> {
-    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&x)[4]) {
-        uint2 v = *reinterpret_cast<const uint2*>(p);
+    using Raw = uint2;
+    static __device__ __forceinline__ Raw zero() { return make_uint2(0u, 0u); }
+    static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+    static __device__ __forceinline__ void unpack(const Raw& v, float (&x)[4]) {
         x[0] = __uint_as_float(v.x << 16); x[1] = __uint_as_float(v.x & 0xFFFF0000u);
         x[2] = __uint_as_float(v.y << 16); x[3] = __uint_as_float(v.y & 0xFFFF0000u);
     }
@@ -67,86 +72,182 @@ template <> struct Vec4<__nv_bfloat16> {
     }
 };
 
+// A warp per sample, persistent warps striding over the rows; lane l holds slots 128 q + 4 l + e (q, e < 4), so that every
+// load / store instruction of the warp covers 256 (bf16) or 512 (f32) contiguous bytes, and the next row's logits and
+// scalars are fetched before the current row is worked on (the kernel needs ~125 registers, i.e. 16 warps per SM: one
+// row in flight per warp left it latency bound at 1.9 TB/s).  d loss / d logits also gives the gradient of
+// action_head.bias (its column sums): each warp adds up its rows in registers, the warps of a CTA are combined through
+// shared memory and one atomicAdd per column and CTA goes to dbias (nullable).
+constexpr int kLossWarps = 8;
+
+template <typename T> struct LossRow {
+    typename Vec4<T>::Raw x[4];
+    int n, a;
+    float adv, old_logp, ret, v;
+};
+// Quads of 128 slots a row needs: the mask is a prefix (n legal slots), and a masked slot's probability
+// exp(logit - 103.28 - lse) is below 1e-38 relative to the legal ones -- it changes neither the sums nor, in bf16 / f32,
+// its own gradient (0) -- so only the quads that hold legal slots are read and computed (the policy kernel does the
+// same).  Passes (n == 0: the reference's arithmetic gives a softmax over all 500 slots) and rows whose stored action
+// is not a legal slot keep all four quads and the literal arithmetic.
+__device__ __forceinline__ int loss_active_quads(int n, int a) { return (n <= 0 || a >= n) ? 4 : (n + 127) >> 7; }
+
 template <typename T>
-__global__ void __launch_bounds__(256) ppo_loss_grad_kernel(
+__device__ __forceinline__ void loss_row_load(LossRow<T>& r, long long row, int n, int a, int lane, const T* __restrict__ logits,
+                                              long long ld, const float* __restrict__ values, const float* __restrict__ old_logp,
+                                              const float* __restrict__ adv, const float* __restrict__ returns) {
+    const T* src = logits + row * ld;
+    const int nq = loss_active_quads(n, a);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i0 = 128 * q + 4 * lane;
+        const bool need = q < nq || (q == 3 && !values && lane == 29);               // lane 29 of quad 3: column 500 = the value
+        r.x[q] = (need && i0 < ld) ? Vec4<T>::load_raw(src + i0) : Vec4<T>::zero();
+    }
+    r.n = n; r.a = a;
+    r.adv = __ldg(adv + row); r.old_logp = __ldg(old_logp + row); r.ret = __ldg(returns + row);
+    r.v = values ? __ldg(values + row) : 0.0f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_kernel(
     const T* __restrict__ logits, long long ld, const float* __restrict__ values, const int32_t* __restrict__ counts,
     const int32_t* __restrict__ actions, const float* __restrict__ old_logp, const float* __restrict__ adv,
     const float* __restrict__ returns, long long B, float eps_clip, float value_coef, float entropy_coef,
-    T* __restrict__ dlogits, float* __restrict__ dvalues, float* __restrict__ sums) {
+    T* __restrict__ dlogits, float* __restrict__ dvalues, float* __restrict__ dbias, float* __restrict__ sums) {
     constexpr float kMaskLog = -103.27893f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long row = (long long)blockIdx.x * 8 + warp;
-    __shared__ float s_part[8][3];
+    __shared__ float s_part[kLossWarps][3];
+    __shared__ float s_col[kLossWarps][512];
     float pl = 0.0f, vl = 0.0f, ent = 0.0f;
-    if (row < B) {
-        const int n = counts[row], a = actions[row];
-        const float invB = 1.0f / (float)B;
-        float z[16];
-        const T* src = logits + row * ld + 16 * lane;
+    float colsum[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) colsum[k] = 0.0f;
+    const float invB = 1.0f / (float)B;
+    const float ce = entropy_coef * invB;
+    const long long S = (long long)gridDim.x * kLossWarps;          // persistent warps stride over the rows
+    long long row = (long long)blockIdx.x * kLossWarps + warp;
+    // software pipeline: counts / actions two rows ahead (they decide which quads the prefetch reads), logits one row ahead
+    LossRow<T> nx;
+    int n1 = 0, a1 = 0;
+    if (row < B) loss_row_load(nx, row, __ldg(counts + row), __ldg(actions + row), lane, logits, ld, values, old_logp, adv, returns);
+    if (row + S < B) { n1 = __ldg(counts + row + S); a1 = __ldg(actions + row + S); }
+#pragma unroll 1
+    for (; row < B; row += S) {
+        const LossRow<T> cur = nx;
+        if (row + S < B) loss_row_load(nx, row + S, n1, a1, lane, logits, ld, values, old_logp, adv, returns);
+        if (row + 2 * S < B) { n1 = __ldg(counts + row + 2 * S); a1 = __ldg(actions + row + 2 * S); }
+        const int n = cur.n, a = cur.a;
+        const int nq = loss_active_quads(n, a);
+        float z[16], xv = 0.0f;
+        float m = -INFINITY;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (16 * lane + 4 * q < BG_ACTIONS) Vec4<T>::load(src + 4 * q, x);            // 500 = 4 * 125: whole quads only
+            const int i0 = 128 * q + 4 * lane;
+            float x[4];
+            Vec4<T>::unpack(cur.x[q], x);                                               // 500 = 4 * 125: whole quads only
+            if (q == 3) xv = x[0];                                                      // lane 29: column 500
+            if (q < nq) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int i = 16 * lane + 4 * q + e;
-                z[4 * q + e] = i < BG_ACTIONS ? (i >= n ? x[e] + kMaskLog : x[e]) : -INFINITY;
+                for (int e = 0; e < 4; ++e) {
+                    const int i = i0 + e;
+                    z[4 * q + e] = i < BG_ACTIONS ? (i >= n ? x[e] + kMaskLog : x[e]) : -INFINITY;
+                    m = fmaxf(m, z[4 * q + e]);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) z[4 * q + e] = -INFINITY;
             }
         }
-        float m = z[0];
-#pragma unroll
-        for (int k = 1; k < 16; ++k) m = fmaxf(m, z[k]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
         float ssum = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) ssum += __expf(z[k] - m);
+        for (int q = 0; q < 4; ++q)
+            if (q < nq) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ssum += __expf(z[4 * q + e] - m);
+            }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(kFull, ssum, o);
         const float lse = m + __logf(ssum);
         float h = 0.0f, lpa = 0.0f;
         float p[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float lp = z[k] - lse;                       // (-inf for the 12 padding slots)
-            p[k] = __expf(lp);
-            if (p[k] > 0.0f) h -= p[k] * lp;
-            if (16 * lane + k == a) lpa = lp;
-            z[k] = lp;
+        for (int q = 0; q < 4; ++q) {
+            if (q < nq) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = 4 * q + e;
+                    const float lp = z[k] - lse;                   // (-inf for the 12 padding slots)
+                    p[k] = __expf(lp);
+                    if (p[k] > 0.0f) h -= p[k] * lp;
+                    if (128 * q + 4 * lane + e == a) lpa = lp;
+                    z[k] = lp;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) p[4 * q + e] = 0.0f;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { h += __shfl_xor_sync(kFull, h, o); lpa += __shfl_xor_sync(kFull, lpa, o); }
-        const float A = adv[row];
-        const float r = __expf(lpa - old_logp[row]);
+        const float A = cur.adv;
+        const float r = __expf(lpa - cur.old_logp);
         const float rc = fminf(fmaxf(r, 1.0f - eps_clip), 1.0f + eps_clip);
         const float s1 = r * A, s2 = rc * A;
         const bool through = (r >= 1.0f - eps_clip && r <= 1.0f + eps_clip) || s1 < s2;
         const float g = through ? -A * r * invB : 0.0f;
-        const float ce = entropy_coef * invB;
-        T* dst = dlogits + row * ld + 16 * lane;
+        // value head: its own array, or (values == NULL) column 500 of the logits -- the value head computed as row 500 of
+        // the action head's GEMM; its gradient then goes to column 500 of dlogits and rides through the backward GEMMs
+        const float v = values ? cur.v : __shfl_sync(kFull, xv, 29);
+        const float dv = v - cur.ret;
+        const float dvalue = 2.0f * value_coef * dv * invB;
+        T* dst = dlogits + row * ld;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            float x[4];
+            const int i0 = 128 * q + 4 * lane;
+            float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (q < nq) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int k = 4 * q + e;
-                const float pk = p[k];
-                float d = -g * pk + (pk > 0.0f ? ce * pk * (z[k] + h) : 0.0f);
-                if (16 * lane + k == a) d += g;
-                x[e] = d;
+                for (int e = 0; e < 4; ++e) {
+                    const int k = 4 * q + e;
+                    const float pk = p[k];
+                    float d = -g * pk + (pk > 0.0f ? ce * pk * (z[k] + h) : 0.0f);
+                    if (i0 + e == a) d += g;
+                    x[e] = d;
+                }
             }
-            if (16 * lane + 4 * q < BG_ACTIONS) Vec4<T>::store(dst + 4 * q, x);
+            if (q == 3 && !values && i0 == BG_ACTIONS) x[0] = dvalue;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) colsum[4 * q + e] += x[e];
+            if (i0 < ld) Vec4<T>::store(dst + i0, x);          // masked quads and slots 500 .. ld-1 (padding of the GEMM's N): exact zeros
         }
-        const float v = values[row], dv = v - returns[row];
-        if (lane == 0) { dvalues[row] = 2.0f * value_coef * dv * invB; pl = -fminf(s1, s2); vl = dv * dv; ent = h; }
+        if (lane == 0) {
+            if (dvalues) dvalues[row] = dvalue;
+            pl -= fminf(s1, s2); vl += dv * dv; ent += h;
+        }
     }
     if (lane == 0) { s_part[warp][0] = pl; s_part[warp][1] = vl; s_part[warp][2] = ent; }
+    if (dbias) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s_col[warp][128 * (k >> 2) + 4 * lane + (k & 3)] = colsum[k];
+    }
     __syncthreads();
     if (threadIdx.x < 3) {
         float t = 0.0f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
+        for (int w = 0; w < kLossWarps; ++w) t += s_part[w][threadIdx.x];
         atomicAdd(&sums[threadIdx.x], t);
+    }
+    if (dbias) {
+        const int ncol = ld < 512 ? (int)ld : 512;
+        for (int c = threadIdx.x; c < ncol; c += kLossWarps * 32) {
+            float t = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kLossWarps; ++w) t += s_col[w][c];
+            atomicAdd(&dbias[c], t);
+        }
     }
 }
 
@@ -155,20 +256,23 @@ __global__ void __launch_bounds__(256) ppo_loss_grad_kernel(
 extern "C" int bg_ppo_loss_grad(const void* logits, int logits_bf16, long long ld, const float* values, const int32_t* counts,
                                 const int32_t* actions, const float* old_log_probs, const float* advantages,
                                 const float* returns, long long B, float eps_clip, float value_coef, float entropy_coef,
-                                void* dlogits, float* dvalues, float* sums, void* stream) {
+                                void* dlogits, float* dvalues, float* dbias, float* sums, void* stream) {
     if (B < 0 || ld < BG_ACTIONS || (ld & 3)) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_loss_grad: bad B or ld (need ld >= 500, multiple of 4)");
     if (B == 0) return BG_OK;
-    if (!logits || !values || !counts || !actions || !old_log_probs || !advantages || !returns || !dlogits || !dvalues || !sums)
+    if (!logits || !counts || !actions || !old_log_probs || !advantages || !returns || !dlogits || !sums || (values && !dvalues))
         return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_loss_grad: null pointer");
-    const unsigned grid = (unsigned)((B + 7) / 8);
+    if (!values && ld <= BG_ACTIONS) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_loss_grad: values == NULL needs the value in column 500 (ld >= 504)");
+    const long long need = (B + bg::kLossWarps - 1) / bg::kLossWarps;
+    const long long resident = (long long)bg_sm_count() * 2;                   // ~125 registers x 256 threads: two CTAs per SM
+    const unsigned grid = (unsigned)(need < resident ? need : resident);
     if (logits_bf16)
-        bg::ppo_loss_grad_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        bg::ppo_loss_grad_kernel<__nv_bfloat16><<<grid, bg::kLossWarps * 32, 0, (cudaStream_t)stream>>>(
             (const __nv_bfloat16*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
-            entropy_coef, (__nv_bfloat16*)dlogits, dvalues, sums);
+            entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums);
     else
-        bg::ppo_loss_grad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        bg::ppo_loss_grad_kernel<float><<<grid, bg::kLossWarps * 32, 0, (cudaStream_t)stream>>>(
             (const float*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
-            entropy_coef, (float*)dlogits, dvalues, sums);
+            entropy_coef, (float*)dlogits, dvalues, dbias, sums);
     return bg_set_error(cudaGetLastError(), "bg_ppo_loss_grad: launch");
 }
 

@@ -52,6 +52,7 @@ class PPOConfig:                                   # src/agent/config.py:4-22
     returns_mode: str = "per_game"                 # or "interleaved" (the reference's walk, for parity tests)
     reset_each_update: bool = False                # reference: True (train.py:40)
     autocast: bool = True
+    manual_backward: bool = True                   # CUDA + autocast: ManualUpdate (explicit GEMMs) instead of torch autograd
 
 
 # --------------------------------------------------------------------------------------------- pure torch math
@@ -87,7 +88,7 @@ class _FusedPPOLoss(torch.autograd.Function):
                                          f(counts, torch.int32).data_ptr(), f(actions, torch.int32).data_ptr(),
                                          f(old_logp, torch.float32).data_ptr(), f(adv, torch.float32).data_ptr(),
                                          f(returns, torch.float32).data_ptr(), B, float(eps_clip), float(value_coef),
-                                         float(entropy_coef), dlogits.data_ptr(), dvalues.data_ptr(), sums.data_ptr(), _stream()),
+                                         float(entropy_coef), dlogits.data_ptr(), dvalues.data_ptr(), None, sums.data_ptr(), _stream()),
                   "bg_ppo_loss_grad")
         ctx.save_for_backward(dlogits, dvalues)
         ctx.values_dtype = values.dtype
@@ -130,6 +131,79 @@ def ppo_loss(params, x, counts, actions, old_logp, returns, advantages, eps_clip
         entropy = -(p * logp_all).sum(-1).mean()
         loss = policy_loss + value_coef * value_loss - entropy_coef * entropy
     return loss, policy_loss.detach(), value_loss.detach(), entropy.detach()
+
+
+class ManualUpdate:
+    """One epoch of BackgammonPPOAgent.update (ppo_agent.py:268-305: forward, loss, backward) without autograd, for bf16
+    feature rows x (B,208) from K3 whose spare column 198 has been set to 1.0:
+
+        h      = relu(x @ W1p^T)                 W1p (128,208) bf16: fc1.weight | fc1.bias in column 198
+        logits = h @ Wap^T + bap                 Wap (512,128) bf16: action_head.weight | value_head.weight as row 500
+        bg_ppo_loss_grad(values = NULL)          value = column 500; writes d loss / d logits (bf16), its column sums (f32)
+        dWap = dlogits^T @ h   dh = dlogits @ Wap   dpre = dh * (h > 0)   dW1p = dpre^T @ x
+
+    five library GEMMs (bf16 operands as under the reference's autocast; the two weight gradients accumulate and are
+    returned in f32), one elementwise pass and our loss kernel.  The value head and both biases ride inside the GEMMs /
+    the loss kernel, so nothing else touches a (B, .) tensor: no dlogits * grad_output pass, no bias column sums over
+    (B,500), no separate value-head matmuls."""
+
+    LD = 512
+    ONE_COL = 198
+
+    def __init__(self, device):
+        self.device = device
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
+        self.w1p, self.wap, self.bap = z((128, 208), torch.bfloat16), z((self.LD, 128), torch.bfloat16), z((self.LD,), torch.bfloat16)
+        self.dbias, self.sums = z((self.LD,), torch.float32), z((3,), torch.float32)
+        self.B = -1
+        self.f32_out = None                      # torch.mm(..., out_dtype=f32) available?
+
+    def _buffers(self, B):
+        if B != self.B:
+            e = lambda shape: torch.empty(shape, dtype=torch.bfloat16, device=self.device)
+            self.h, self.logits, self.dlogits, self.dh = e((B, 128)), e((B, self.LD)), e((B, self.LD)), e((B, 128))
+            self.B = B
+
+    def _mm_f32(self, a, b):
+        if self.f32_out is None:
+            try:
+                r = torch.mm(a, b, out_dtype=torch.float32)
+                self.f32_out = True
+                return r
+            except (TypeError, RuntimeError):
+                self.f32_out = False
+        if self.f32_out:
+            return torch.mm(a, b, out_dtype=torch.float32)
+        return torch.mm(a, b).float()
+
+    @torch.no_grad()
+    def epoch(self, params, grads, x, counts, actions, old_logp, adv, returns, eps_clip, value_coef, entropy_coef):
+        """params / grads: dicts of f32 tensors under the reference's keys; grads are overwritten.  counts / actions i32,
+        the other per-sample vectors f32, all contiguous.  -> f32 tensor (policy_loss, value_loss, entropy, total_loss)."""
+        B = x.shape[0]
+        self._buffers(B)
+        w1p, wap, bap = self.w1p, self.wap, self.bap
+        w1p[:, :198].copy_(params["fc1.weight"]); w1p[:, self.ONE_COL].copy_(params["fc1.bias"])
+        wap[:ACTIONS].copy_(params["action_head.weight"]); wap[ACTIONS].copy_(params["value_head.weight"][0])
+        bap[:ACTIONS].copy_(params["action_head.bias"]); bap[ACTIONS:ACTIONS + 1].copy_(params["value_head.bias"])
+        torch.mm(x, w1p.t(), out=self.h)
+        self.h.relu_()
+        torch.addmm(bap, self.h, wap.t(), out=self.logits)
+        self.dbias.zero_(); self.sums.zero_()
+        with torch.cuda.device(self.device):
+            check(lib().bg_ppo_loss_grad(self.logits.data_ptr(), 1, self.LD, None, counts.data_ptr(), actions.data_ptr(),
+                                         old_logp.data_ptr(), adv.data_ptr(), returns.data_ptr(), B, float(eps_clip),
+                                         float(value_coef), float(entropy_coef), self.dlogits.data_ptr(), None,
+                                         self.dbias.data_ptr(), self.sums.data_ptr(), _stream()), "bg_ppo_loss_grad")
+        dwap = self._mm_f32(self.dlogits.t(), self.h)                       # (512,128)
+        torch.mm(self.dlogits, wap, out=self.dh)                            # (B,128)
+        dpre = torch.ops.aten.threshold_backward(self.dh, self.h, 0)        # relu backward
+        dw1p = self._mm_f32(dpre.t(), x)                                    # (128,208)
+        grads["fc1.weight"].copy_(dw1p[:, :198]); grads["fc1.bias"].copy_(dw1p[:, self.ONE_COL])
+        grads["action_head.weight"].copy_(dwap[:ACTIONS]); grads["action_head.bias"].copy_(self.dbias[:ACTIONS])
+        grads["value_head.weight"].copy_(dwap[ACTIONS:ACTIONS + 1]); grads["value_head.bias"].copy_(self.dbias[ACTIONS:ACTIONS + 1])
+        m = self.sums / B
+        return torch.stack([m[0], m[1], m[2], m[0] + value_coef * m[1] - entropy_coef * m[2]])
 
 
 def discounted_returns(rewards, dones, values, last_values, gamma, lam):
@@ -181,6 +255,7 @@ class PPOLearner:
         self.total_steps = 0
         self.entropy_coef = self.cfg.entropy_coef_start
         self.last = {}
+        self._manual = None
 
     def update_entropy_coef(self):                                                                   # ppo_agent.py:193-204
         c = self.cfg
@@ -207,16 +282,30 @@ class PPOLearner:
         B = x.shape[0]
         mb = max(1, int(c.num_minibatches))
         stats = torch.zeros(4, device=x.device)
+        manual = (c.manual_backward and c.autocast and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2
+                  and x.shape[1] == 208 and x.is_contiguous())
+        if manual:
+            if self._manual is None:
+                self._manual = ManualUpdate(self.device)
+            x[:, ManualUpdate.ONE_COL] = 1.0                  # spare (zero) column of K3's rows: carries fc1.bias through the GEMMs
+            counts, actions = counts.to(torch.int32).contiguous(), actions.to(torch.int32).contiguous()
+            old_logp, returns, adv = old_logp.float().contiguous(), returns.float().contiguous(), adv.float().contiguous()
+            grads = {k: p.grad for k, p in self.fp.params.items()}
         for _ in range(c.num_epochs):
             for k in range(mb):
                 sl = slice(k * B // mb, (k + 1) * B // mb)
-                loss, pl, vl, ent = ppo_loss(self.fp.params, x[sl], counts[sl], actions[sl], old_logp[sl], returns[sl], adv[sl],
-                                             c.eps_clip, c.value_loss_coef, self.entropy_coef, autocast=c.autocast)
-                self.fp.flat_grad.zero_()
-                loss.backward()
+                if manual:
+                    st = self._manual.epoch(self.fp.params, grads, x[sl], counts[sl], actions[sl], old_logp[sl], adv[sl], returns[sl],
+                                            c.eps_clip, c.value_loss_coef, self.entropy_coef)
+                else:
+                    loss, pl, vl, ent = ppo_loss(self.fp.params, x[sl], counts[sl], actions[sl], old_logp[sl], returns[sl], adv[sl],
+                                                 c.eps_clip, c.value_loss_coef, self.entropy_coef, autocast=c.autocast)
+                    self.fp.flat_grad.zero_()
+                    loss.backward()
+                    st = torch.stack([pl.float(), vl.float(), ent.float(), loss.detach().float()])
                 self.fp.all_reduce_grads(self.dist)
                 self.optimizer.step()
-                stats += torch.stack([pl.float(), vl.float(), ent.float(), loss.detach().float()])
+                stats += st
                 self.total_steps += 1
         stats /= c.num_epochs * mb
         self.last = dict(zip(("policy_loss", "value_loss", "entropy", "total_loss"), stats.tolist()))

@@ -57,6 +57,29 @@ class StepInfos:
         return (self[i] for i in range(len(self)))
 
 
+class HostStepBuffers:
+    """Pinned host mirrors of what a host-side policy needs from every step -- rewards, dones and the legal-play counts
+    of the new positions -- filled by `env.step(actions, host=buffers)` on a copy stream as soon as K2 and K1 have
+    finished, i.e. while the encoders (K3: observations, afterstate features) of the same step are still running.
+    `wait()` blocks until the three arrays of the latest step are on the host; the device tensors step() returned stay
+    asynchronous as usual."""
+
+    def __init__(self, env):
+        N, dev = env.num_envs, env.device
+        self.rewards = torch.empty(N, dtype=torch.float32).pin_memory()
+        self.dones = torch.empty(N, dtype=torch.bool).pin_memory()
+        self.legal_counts = torch.empty(N, dtype=torch.int32).pin_memory()
+        self.stream = torch.cuda.Stream(device=dev)
+        self.stepped = torch.cuda.Event()                  # K2 of the step done: rewards / dones final
+        self.legal_ready = torch.cuda.Event()              # K1 of the step done (recorded inside bg_update_legal_plays)
+        self.ready = torch.cuda.Event()                    # ... and everything copied to the host
+        with torch.cuda.device(dev):
+            self.stepped.record(); self.legal_ready.record(); self.ready.record()   # torch creates the handles on the first record
+
+    def wait(self):
+        self.ready.synchronize()
+
+
 class B200BackgammonVecEnv:
     def __init__(self, num_envs=1, match_length=15, max_legal_moves=500, device=None, seed=0x5EED,
                  stream_base=0, rows_per_game=64, dense_budget_bytes=4 << 30, check_every=16):
@@ -87,6 +110,7 @@ class B200BackgammonVecEnv:
         self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=device)
         self._ext_dice = None
         self._side = None
+        self._next_out = None
         self._steps = 0
         # reference attributes (vec_bg_env.py:16-18); gym is not a dependency, so plain descriptors
         self.observation_space = {"shape": (FEATURES,), "low": -1.0, "high": 1.0, "dtype": "float32"}
@@ -139,8 +163,8 @@ class B200BackgammonVecEnv:
             if self._side is None:
                 self._side = torch.cuda.Stream(device=self.device)
             side = self._side.cuda_stream
-        e0 = k1_events[0].cuda_event if k1_events is not None else None
-        e1 = k1_events[1].cuda_event if k1_events is not None else None
+        e0 = k1_events[0].cuda_event if k1_events is not None and k1_events[0] is not None else None
+        e1 = k1_events[1].cuda_event if k1_events is not None and k1_events[1] is not None else None
         check(lib().bg_update_legal_plays(self.boards52.data_ptr(), self.players.data_ptr(), self.dice.data_ptr(),
                                           self.num_envs, self.max_legal_moves, self.after52.data_ptr(), self.cap_rows,
                                           self.row_players.data_ptr(), self.legal_counts_true.data_ptr(),
@@ -172,10 +196,22 @@ class B200BackgammonVecEnv:
         self.check_status()
         return obs
 
-    def step(self, actions, return_obs=True, with_features=False):
+    def _alloc_outputs(self, return_obs):
+        N, dev = self.num_envs, self.device
+        return (return_obs, torch.empty(N, dtype=torch.float32, device=dev), torch.empty(N, dtype=torch.bool, device=dev),   # K2 writes 0/1 bytes
+                torch.empty((4, N), dtype=torch.int8, device=dev),
+                torch.empty((N, FEATURES), dtype=torch.float32, device=dev) if return_obs else None)
+
+    def step(self, actions, return_obs=True, with_features=False, host: HostStepBuffers | None = None, overlap: bool | None = None):
         """vec_bg_env.py:28-49 -> (obs (N,198) f32, rewards (N,) f32, dones (N,) bool, infos).
         Every returned tensor is a fresh allocation (as in the reference) that the kernels write directly: no
-        staging copies.  with_features also refreshes self.after_feats (bf16 features of every legal play)."""
+        staging copies.  with_features also refreshes self.after_feats (bf16 features of every legal play).
+        host: rewards / dones / new legal-play counts are also copied into these pinned buffers as soon as K2 + K1 are
+        done (host.wait()), without waiting for the encoders.  overlap=False runs the encoders after K1 instead of beside
+        its overflow tiers: K1 finishes earlier, which is what a host waiting for the counts wants (the default with
+        `host`; without it the default is the overlapped form, which is the shorter one for the GPU)."""
+        if overlap is None:
+            overlap = host is None
         if not isinstance(actions, torch.Tensor):
             import numpy as np
             acts = [0 if a is None else int(a) for a in actions] if not isinstance(actions, np.ndarray) else actions
@@ -185,16 +221,30 @@ class B200BackgammonVecEnv:
             raise BgError("step: need one action per env")
         N, dev = self.num_envs, self.device
         with torch.cuda.device(dev):
-            # fresh result tensors; the persistent attributes alias them until the next step
-            self.rewards = torch.empty(N, dtype=torch.float32, device=dev)
-            dones = torch.empty(N, dtype=torch.bool, device=dev)                # K2 writes 0/1 bytes
+            # fresh result tensors (allocated at the end of the previous step, off the launch path); the persistent
+            # attributes alias them until the next step
+            out = self._next_out if self._next_out is not None and self._next_out[0] == return_obs else self._alloc_outputs(return_obs)
+            _, self.rewards, dones, info, obs = out
             self.dones_u8 = dones.view(torch.uint8)
-            info = torch.empty((4, N), dtype=torch.int8, device=dev)
             self.info_player, self.winner, self.game_score, self.flags = info[0], info[1], info[2], info[3].view(torch.uint8)
             if return_obs:
-                self.obs_f32 = torch.empty((N, FEATURES), dtype=torch.float32, device=dev)
+                self.obs_f32 = obs
             self._apply_actions(actions)
-            self.update_legal_plays(obs=return_obs, features=with_features)
+            if host is not None:                                                # rewards / dones are final after K2
+                host.stepped.record()
+            self.update_legal_plays(obs=return_obs, features=with_features, overlap=overlap,
+                                    k1_events=(None, host.legal_ready) if host is not None else None)
+            if host is not None:
+                cs = host.stream
+                cs.wait_event(host.stepped)
+                with torch.cuda.stream(cs):
+                    host.rewards.copy_(self.rewards, non_blocking=True)
+                    host.dones.copy_(dones, non_blocking=True)
+                    cs.wait_event(host.legal_ready)
+                    host.legal_counts.copy_(self.legal_counts, non_blocking=True)
+                    host.ready.record(cs)
+                self.rewards.record_stream(cs); dones.record_stream(cs)
+            self._next_out = self._alloc_outputs(return_obs)
         self._steps += 1
         if self.check_every and self._steps % self.check_every == 0:
             self.check_status()

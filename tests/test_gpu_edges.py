@@ -83,7 +83,7 @@ def test_new_entry_points_reject_bad_arguments():
     assert L.bg_policy_sample(None, None, 0, 4, None, None, None, None, None, None, 0.0, 0, 0, 0, 0, None, None, None, None, None, 0, None) == -1
     assert L.bg_policy_sample(None, None, 0, 0, None, None, None, None, None, None, 0.0, 0, 0, 0, 0, None, None, None, None, None, 0, None) == 0
     assert L.bg_gae(None, None, None, None, 4, 4, 0.99, 1.0, None, None, None) == -1
-    assert L.bg_ppo_loss_grad(None, 1, 499, None, None, None, None, None, None, 4, 0.2, 0.5, 0.01, None, None, None, None) == -1
+    assert L.bg_ppo_loss_grad(None, 1, 499, None, None, None, None, None, None, 4, 0.2, 0.5, 0.01, None, None, None, None, None) == -1
     assert L.bg_twoply_replies_values(None, None, 4, None, 0, None, None, None, None, None, None, 0, None, None, None, 0.0, None, None,
                                       None, None) == -1
 
@@ -99,3 +99,27 @@ def test_policy_without_mask_and_single_row():
     assert int(a[0]) == int(logits[0, :3].argmax())
     # value head agrees with K4 on the same position
     assert abs(float(v[0]) - float(net.values(b, 0)[0])) < 1e-4
+
+
+def test_host_step_buffers_mirror_the_device_results():
+    """step(actions, host=HostStepBuffers): rewards / dones / new legal counts reach pinned host memory behind K1 (while K3
+    is still running) and equal the device tensors of the same step; trajectories are unchanged by the early copy."""
+    import bg_b200
+    dev = torch.device("cuda:0")
+    envs = [bg_b200.B200BackgammonVecEnv(num_envs=3000, device=dev, seed=11, check_every=0) for _ in range(2)]
+    [e.reset() for e in envs]
+    host = bg_b200.HostStepBuffers(envs[0])
+    h_acts = torch.empty(3000, dtype=torch.int32).pin_memory()
+    rng = np.random.default_rng(5)
+    counts = envs[0].legal_counts.cpu().numpy()
+    for t in range(150):
+        h_acts.numpy()[:] = (rng.random(3000) * counts).astype(np.int32)
+        obs, rew, done, _ = envs[0].step(h_acts, with_features=True, host=host)
+        obs2, rew2, done2, _ = envs[1].step(h_acts.clone())
+        host.wait()
+        counts = host.legal_counts.numpy().copy()
+        assert np.array_equal(host.rewards.numpy(), rew.cpu().numpy()) and np.array_equal(host.dones.numpy(), done.cpu().numpy())
+        assert np.array_equal(counts, envs[0].legal_counts.cpu().numpy())
+        assert torch.equal(obs, obs2) and torch.equal(rew, rew2) and torch.equal(done, done2)
+    assert float(envs[0].rewards.min()) >= 0.0
+    [e.check_status() for e in envs]

@@ -119,3 +119,43 @@ def test_fused_loss_kernel_matches_torch_chain():
     loss, pl, vl, ent = ppo_loss(p, x, counts, actions, t("logp", torch.float32), ret, adv, 0.25, 0.5, float(g["entropy_coef"]), autocast=True, fused=True)
     got = np.array([pl.item(), vl.item(), ent.item(), loss.item()])
     assert np.abs(got - g["loss_lr0"]).max() < 5e-3, (got, g["loss_lr0"])
+
+
+def test_manual_update_matches_autograd():
+    """ManualUpdate (explicit GEMMs + bg_ppo_loss_grad with the value head as column 500, biases folded) == torch autograd
+    over the torch restatement of ppo_agent.py:268-305 under bf16 autocast: losses, every gradient, and a whole update()"""
+    from bg_b200.ppo import ManualUpdate, PPOConfig, PPOLearner, ppo_loss
+    g = np.load(GOLDEN)
+    sd0 = {k[3:]: torch.tensor(g[k]).cuda() for k in g.files if k.startswith("w0.")}
+    t = lambda k, dt: torch.tensor(g[k]).to(dt).cuda()
+    obs, counts, actions, logp, values = t("obs", torch.float32), t("counts", torch.int32), t("actions", torch.int32), t("logp", torch.float32), t("values", torch.float32)
+    B = obs.shape[0]
+    x = torch.zeros((B, 208), dtype=torch.bfloat16, device="cuda")
+    x[:, :198] = obs
+    ret = t("returns_interleaved", torch.float32)
+    retn = (ret - ret.mean()) / (ret.std() + 1e-5)
+    adv = retn - values
+    logp2 = logp + 0.3 * torch.randn_like(logp)
+    p = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    loss, pl, vl, ent = ppo_loss(p, x, counts, actions, logp2, retn, adv, 0.25, 0.5, 0.15, autocast=True, fused=False)
+    loss.backward()
+    want = {k: v.grad.clone() for k, v in p.items()}
+    grads = {k: torch.zeros_like(v) for k, v in sd0.items()}
+    xm = x.clone(); xm[:, ManualUpdate.ONE_COL] = 1.0
+    st = ManualUpdate(torch.device("cuda:0")).epoch(sd0, grads, xm, counts, actions, logp2, adv.contiguous(), retn.contiguous(), 0.25, 0.5, 0.15)
+    got = st.cpu().numpy()
+    assert np.abs(got - np.array([pl.item(), vl.item(), ent.item(), loss.item()])).max() < 3e-3, got
+    for k in want:
+        scale = want[k].abs().max().item() + 1e-8
+        assert (want[k] - grads[k]).abs().max().item() < 3e-2 * scale, (k, (want[k] - grads[k]).abs().max().item(), scale)
+    # a whole four-epoch update through both paths ends at (nearly) the same weights
+    outs = []
+    for manual in (False, True):
+        L = PPOLearner(sd0, "cuda:0", PPOConfig(manual_backward=manual))
+        L.update(x.clone(), counts, actions, logp, values, ret)
+        outs.append((L.state_dict(), L.last))
+    for k in sd0:
+        moved = (outs[0][0][k] - sd0[k]).abs().mean().item()          # (Adam steps are sign-like: compare means, not maxima)
+        assert (outs[0][0][k] - outs[1][0][k]).abs().mean().item() < 0.25 * moved + 1e-6, k
+    for key in ("policy_loss", "value_loss", "entropy", "total_loss"):
+        assert abs(outs[0][1][key] - outs[1][1][key]) < 5e-3, (key, outs[0][1], outs[1][1])
