@@ -12,8 +12,9 @@ Mirrors the reference's learner:
 Games shard across GPUs by game id (no data-path collective); the ONLY collective is the gradient all-reduce of
 one flat 90,101-element f32 bucket per optimiser step (NCCL over NVLink), plus three scalars for the return
 normalisation.  The rollout side (env step, legal moves, policy forward, sampling, returns) is hand-written CUDA;
-the update's forward/backward are plain library GEMMs through torch autograd under bf16 autocast, as the reference
-runs them (`torch.amp.autocast`, ppo_agent.py:269).
+the update is ManualUpdate: five library GEMMs on bf16 operands (what the reference's `torch.amp.autocast`,
+ppo_agent.py:269, makes of its linear layers) around one kernel of ours (bg_ppo_loss_grad) for the loss and its
+gradient; `manual_backward=False` keeps torch autograd over the same math.
 
 Documented divergences from the reference: returns are computed per game, not over the interleaved
 memory of all envs as one sequence (`returns_mode="interleaved"` reproduces that for parity tests); games in flight
