@@ -92,19 +92,28 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------- CPU arm
 
-def cpu_rollout(seconds: float, threads: int, chunk: int = 2000, encode: bool = True):
-    """Uniform-random self-play through the oracle's restatement of BackgammonEnv (same Philox dice / action
-    conventions as the engine), `threads` envs in parallel (ctypes releases the GIL).  -> (steps, elapsed s)"""
+def cpu_envs(threads: int):
     from oracle import bg_oracle as O
     O.lib()
+    envs = []
+    for i in range(threads):
+        e = O.Env()
+        e.set_philox(SEED, i)
+        e.reset()
+        envs.append(e)
+    return envs
+
+
+def cpu_rollout(seconds: float, threads: int, chunk: int = 2000, encode: bool = True, envs=None):
+    """Uniform-random self-play through the oracle's restatement of BackgammonEnv (same Philox dice / action
+    conventions as the engine), `threads` envs in parallel (ctypes releases the GIL).  -> (steps, elapsed s)"""
+    envs = envs or cpu_envs(threads)
     done_steps = [0] * threads
     t_end = [0.0] * threads
     start = time.perf_counter()
 
     def work(i):
-        e = O.Env()
-        e.set_philox(SEED, i)
-        e.reset()
+        e = envs[i]
         n = 0
         while time.perf_counter() - start < seconds:
             e.random_rollout(chunk, ACT_SEED, encode)
@@ -123,13 +132,14 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    per_step_s = max(0.5, min(8.0, 90.0 / max(1, args.steps + args.warmup)))
-    for _ in range(args.warmup):
-        cpu_rollout(per_step_s, threads)
-    total, el = 0, 0.0
-    for _ in range(args.steps):
-        n, e = cpu_rollout(per_step_s, threads)
-        total += n; el += e
+    # each "step" of this arm is a bounded sample of the workload: the whole run is ~60 s of rollout whatever K and W are
+    per_step_s = max(0.02, min(8.0, 60.0 / max(1, args.steps + args.warmup)))
+    chunk = max(100, min(2000, int(per_step_s * 7000)))          # ~70 k steps/s/thread: a chunk is about a tenth of a step
+    envs = cpu_envs(threads)
+    # the K steps run back to back inside one threaded region (no thread start/join between steps)
+    if args.warmup:
+        cpu_rollout(per_step_s * args.warmup, threads, chunk, envs=envs)
+    total, el = cpu_rollout(per_step_s * args.steps, threads, chunk, envs=envs)
     v = total / el
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / max(1, args.steps), "higher_is_better": True,
@@ -140,7 +150,7 @@ def run_reference(args):
                        "games": threads, "policy": "uniform random (Philox)"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{total} env steps in {el:.1f} s over {threads} threads, each step of this arm = "
-                                       f"{per_step_s:.1f} s of rollout per thread"},
+                                       f"{per_step_s:.2f} s of rollout per thread"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
