@@ -14,3 +14,7 @@ ncu --set full --clock-control none --import-source on -k regex:movegen_kernel -
   python scripts/microbench.py > gpurun_out/ncu_k1_$TAG.log 2>&1
 fi
 tail -3 gpurun_out/pytest_$TAG.log; cat gpurun_out/mb_$TAG.log; cat gpurun_out/bench_$TAG.json
+if [ "${NCU:-1}" = "1" ]; then
+ncu --set full --clock-control none --import-source on -k regex:ppo_loss_grad -s 5 -c 1 -o gpurun_out/prof_loss_$TAG -f \
+  python scripts/profile_ppo_update.py > gpurun_out/ncu_loss_$TAG.log 2>&1
+fi

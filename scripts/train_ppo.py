@@ -4,7 +4,7 @@
     python scripts/train_ppo.py --games 16384 --horizon 64 --updates 20
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 scripts/train_ppo.py ...
 
-Rollout (env step, legal moves, policy forward + sampling, returns) = hand-written CUDA; update = torch autograd;
+Rollout (env step, legal moves, policy forward + sampling, returns) = hand-written CUDA; update = ManualUpdate (library GEMMs + bg_ppo_loss_grad);
 the only collective is the flat-bucket gradient all-reduce (NCCL).  Prints one JSON line per update from rank 0."""
 import argparse
 import json
