@@ -221,6 +221,8 @@ class B200BackgammonVecEnv:
             raise BgError("step: need one action per env")
         N, dev = self.num_envs, self.device
         with torch.cuda.device(dev):
+            if host is not None:                                                # K1 rewrites legal_counts: not before the previous
+                torch.cuda.current_stream().wait_event(host.ready)              # step's copy has read it (a no-op after host.wait())
             # fresh result tensors (allocated at the end of the previous step, off the launch path); the persistent
             # attributes alias them until the next step
             out = self._next_out if self._next_out is not None and self._next_out[0] == return_obs else self._alloc_outputs(return_obs)

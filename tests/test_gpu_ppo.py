@@ -159,3 +159,70 @@ def test_manual_update_matches_autograd():
         assert (outs[0][0][k] - outs[1][0][k]).abs().mean().item() < 0.25 * moved + 1e-6, k
     for key in ("policy_loss", "value_loss", "entropy", "total_loss"):
         assert abs(outs[0][1][key] - outs[1][1][key]) < 5e-3, (key, outs[0][1], outs[1][1])
+
+
+def _loss_reference(logits, values, counts, actions, old_logp, adv, returns, eps, vc, ec):
+    """ppo_agent.py:271-299 in f64 torch, with autograd for the gradients w.r.t. logits and values"""
+    lg = logits.double().clone().requires_grad_(True)
+    v = values.double().clone().requires_grad_(True)
+    slot = torch.arange(500, device=lg.device)[None, :]
+    masked = lg + torch.where(slot < counts[:, None], 0.0, float(np.log(np.float32(1e-45))))
+    lp = torch.log_softmax(masked, -1)
+    new = lp.gather(1, actions.long()[:, None])[:, 0]
+    r = torch.exp(new - old_logp.double())
+    pl = -torch.min(r * adv.double(), torch.clamp(r, 1 - eps, 1 + eps) * adv.double()).mean()
+    vl = ((v - returns.double()) ** 2).mean()
+    ent = -(lp.exp() * lp).sum(-1).mean()
+    (pl + vc * vl - ec * ent).backward()
+    return pl.item(), vl.item(), ent.item(), lg.grad, v.grad
+
+
+@pytest.mark.parametrize("ld,bf16", [(500, False), (512, False), (512, True), (504, True)])
+def test_loss_kernel_edge_rows(ld, bf16):
+    """bg_ppo_loss_grad on synthetic rows: passes (count 0: softmax over all 500 slots), 1 / 128 / 129 / 500 legal slots, a stored
+    action outside the legal prefix, ratios on both sides of the clip range; separate value array and value-in-column-500 mode;
+    f32 and bf16 logits, ld 500 / 504 / 512 -- against an f64 torch restatement of ppo_agent.py:271-299."""
+    from bg_b200._lib import check, lib
+    torch.manual_seed(ld + bf16)
+    B = 777
+    dev = "cuda"
+    counts = torch.tensor([0, 1, 2, 17, 127, 128, 129, 256, 257, 384, 385, 499, 500], device=dev, dtype=torch.int32).repeat(B // 13 + 1)[:B].contiguous()
+    actions = (torch.rand(B, device=dev) * counts.clamp(min=1)).to(torch.int32)
+    actions[5] = 300; counts[5] = 40                                   # stored action outside the legal prefix: literal arithmetic
+    actions[0] = 123                                                   # a pass: any slot
+    dt = torch.bfloat16 if bf16 else torch.float32
+    logits = torch.zeros((B, ld), device=dev, dtype=dt)
+    logits[:, :500] = (2.0 * torch.randn(B, 500, device=dev)).to(dt)
+    values = torch.randn(B, device=dev)
+    if ld > 500:
+        logits[:, 500] = values.to(dt)
+        values_col = logits[:, 500].float()
+    adv, ret = torch.randn(B, device=dev), torch.randn(B, device=dev)
+    lsm = torch.log_softmax(logits[:, :500].float() + torch.where(torch.arange(500, device=dev)[None, :] < counts[:, None], 0.0, -103.27893), -1)
+    old = (lsm.gather(1, actions.long()[:, None])[:, 0] + 0.4 * torch.randn(B, device=dev)).contiguous()
+    eps, vc, ec = 0.25, 0.5, 0.15
+    for value_in_col in ([False, True] if ld > 500 else [False]):
+        v_used = values_col if value_in_col else values
+        pl, vl, ent, dl_want, dv_want = _loss_reference(logits[:, :500].float(), v_used, counts, actions, old, adv, ret, eps, vc, ec)
+        dlogits = torch.full((B, ld), 7.0, device=dev, dtype=dt)
+        dvalues = torch.zeros(B, device=dev)
+        dbias, sums = torch.zeros(512, device=dev), torch.zeros(3, device=dev)
+        check(lib().bg_ppo_loss_grad(logits.data_ptr(), int(bf16), ld, None if value_in_col else values.data_ptr(), counts.data_ptr(),
+                                     actions.data_ptr(), old.data_ptr(), adv.data_ptr(), ret.data_ptr(), B, eps, vc, ec,
+                                     dlogits.data_ptr(), dvalues.data_ptr(), dbias.data_ptr(), sums.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream), "bg_ppo_loss_grad")
+        got = (sums / B).cpu().numpy()
+        assert np.abs(got - np.array([pl, vl, ent])).max() < 2e-5 * (1 + abs(pl) + vl + ent), (got, pl, vl, ent)
+        tol = 1e-2 if bf16 else 1e-5                                   # bf16: the output rounding of dlogits
+        scale = dl_want.abs().max().item()
+        assert (dlogits[:, :500].double() - dl_want).abs().max().item() < tol * scale
+        assert (dvalues.double() - dv_want).abs().max().item() < 1e-6
+        if ld > 500:
+            pad = dlogits[:, 500:].float()
+            if value_in_col:
+                assert (pad[:, 0].double() - dv_want).abs().max().item() < (1e-2 if bf16 else 1e-6) * dv_want.abs().max().item() + 1e-9
+                assert float(pad[:, 1:].abs().max()) == 0.0
+                assert abs(dbias[500].item() - dv_want.sum().item()) < 1e-5
+            else:
+                assert float(pad.abs().max()) == 0.0
+        assert (dbias[:500].double() - dl_want.sum(0)).abs().max().item() < (2e-5 if not bf16 else 2e-5) * B * scale
