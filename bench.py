@@ -291,11 +291,21 @@ def run_engine(args):
     # 4 true count + 8 start written; per legal play 52 afterstate + 1 mover flag written.
     k1_bytes = N * 71.0 + rows_per_step * 53.0
     achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, issue = None, None
     tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            kt = json.load(open(tp))
+            traffic = kt.get("dram_bytes_per_launch")
+            if kt.get("warp_inst_per_launch") and N == 65536:
+                # what actually bounds K1: warp-instruction issue (4 schedulers per SM, one instruction per cycle each)
+                sm_clock_ghz = (clocks or {}).get("sm_mhz") or 1965.0
+                peak_issue = 148 * 4 * sm_clock_ghz / 1e3                      # G warp-instructions / s
+                ach = kt["warp_inst_per_launch"] / (k1_alone_ms * 1e-3) / 1e9
+                issue = {"bound": "warp-instruction issue", "warp_inst_per_launch": kt["warp_inst_per_launch"],
+                         "achieved_ginst_s": ach, "peak_ginst_s": peak_issue, "frac": ach / peak_issue,
+                         "what": "instructions per K1 call from the ncu captures named in profiles/k1_traffic.json / "
+                                 "k1_ms_per_launch_alone; peak = 148 SMs x 4 schedulers x the SM clock sampled during the run"}
         except Exception:
             traffic = None
     line = {
@@ -317,7 +327,7 @@ def run_engine(args):
                              "events around K1's three launches inside the step) includes that sharing; *_alone is the same "
                              "launch sequence with nothing beside it. traffic = dram bytes of the tier 0 + tier 1 launches "
                              "(ncu --set full, profiles/): below the algorithmic bytes because the afterstate rows are still in "
-                             "the 126 MB L2 when the encoder reads them"},
+                             "the 126 MB L2 when the encoder reads them", "issue": issue},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * N * 4, "d2h_bytes_per_step": world * N * 9,
                 "steps": E, "segments_ms_per_step": [x * 1e3 / E for x in e2e_segments],
                 "what": "best of 3 segments (host-side jitter); B200BackgammonVecEnv.step(actions from pinned host memory, "

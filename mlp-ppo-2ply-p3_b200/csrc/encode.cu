@@ -17,27 +17,12 @@
 namespace bg {
 
 constexpr int kEncRows = 128;     // boards per CTA tile
-constexpr int kEncThreads = 256;
 
 __device__ __forceinline__ float4 point_units_f32(int c) {
     float4 r;
     r.x = c >= 1 ? 1.0f : 0.0f; r.y = c >= 2 ? 1.0f : 0.0f; r.z = c >= 3 ? 1.0f : 0.0f;
     r.w = c >= 3 ? ((float)c - 3.0f) * 0.5f : 0.0f;                       // batching.py:117-119 (/2 is exact)
     return r;
-}
-
-// float2 pair j (features 2j, 2j+1) of the f32 row
-__device__ __forceinline__ float2 f32_pair(const int8_t* b, int flag, int j) {
-    if (j < 48) { float4 u = point_units_f32(b[j >> 1]); return (j & 1) ? make_float2(u.z, u.w) : make_float2(u.x, u.y); }
-    if (j == 48) return make_float2((float)b[48] * 0.5f, __uint_as_float(kOff15F32[b[50] & 15]));
-    if (j < 97) { int r = j - 49; float4 u = point_units_f32(b[24 + (r >> 1)]); return (r & 1) ? make_float2(u.z, u.w) : make_float2(u.x, u.y); }
-    if (j == 97) return make_float2((float)b[49] * 0.5f, __uint_as_float(kOff15F32[b[51] & 15]));
-    return flag == 0 ? make_float2(1.0f, 0.0f) : make_float2(0.0f, 1.0f);
-}
-
-__device__ __forceinline__ void stage_boards(const int8_t* __restrict__ boards, long long row0, int rows, uint32_t* sm) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
-    for (int i = threadIdx.x; i < rows * kBoardWords; i += kEncThreads) sm[i] = __ldg(src + i);
 }
 
 // bf16 rows.  Output = 16-byte chunks (8 features); chunk k of a row is described by kChunkDesc[k]: byte w of it
@@ -125,23 +110,54 @@ __global__ void __launch_bounds__(kBfThreads, 3) encode_bf16_kernel(const int8_t
     }
 }
 
-__global__ void __launch_bounds__(kEncThreads) encode_f32_kernel(const int8_t* __restrict__ boards,
+// f32 rows (the reference's own layout).  Thread t owns the float2 pair column j = t % 99 (features 2j, 2j+1) for rows
+// t / 99, +4, ... of the tile: the column is decoded once (board byte + which half of its four units, or one of the three
+// special pairs), a pair is then one byte load + one 8-byte table load and an 8-byte store; consecutive threads write
+// consecutive pairs of a row (792 contiguous bytes per row).
+constexpr int kF32RowsPerPass = 4;
+constexpr int kF32Threads = kF32RowsPerPass * 99;     // 396
+
+__global__ void __launch_bounds__(kF32Threads) encode_f32_kernel(const int8_t* __restrict__ boards,
                                                                  const int8_t* __restrict__ flags, int flag_all,
                                                                  long long B, const unsigned long long* __restrict__ n_rows_dev,
                                                                  float* __restrict__ out, long long ld) {
     __shared__ __align__(16) uint32_t sm[kEncRows * kBoardWords];
     __shared__ int8_t sflag[kEncRows];
+    __shared__ float2 s_units[32];                                           // [(count << 1) | half]
+    if (threadIdx.x < 32) {
+        const float4 u = point_units_f32((int)(threadIdx.x >> 1));
+        s_units[threadIdx.x] = (threadIdx.x & 1) ? make_float2(u.z, u.w) : make_float2(u.x, u.y);
+    }
     if (n_rows_dev) B = min(B, (long long)*n_rows_dev);
+    const int tr = threadIdx.x / 99, j = threadIdx.x - tr * 99;
+    // kind 0: point pair (board byte bidx, half); 1: bar/2, off/15 of player `half`; 2: turn flags
+    int kind = 0, bidx = 0, half = 0;
+    if (j < 48) { bidx = j >> 1; half = j & 1; }
+    else if (j == 48) { kind = 1; half = 0; }
+    else if (j < 97) { bidx = 24 + ((j - 49) >> 1); half = (j - 49) & 1; }
+    else if (j == 97) { kind = 1; half = 1; }
+    else kind = 2;
     for (long long row0 = (long long)blockIdx.x * kEncRows; row0 < B; row0 += (long long)gridDim.x * kEncRows) {
-        int rows = (int)min((long long)kEncRows, B - row0);
-        stage_boards(boards, row0, rows, sm);
-        for (int i = threadIdx.x; i < rows; i += kEncThreads) sflag[i] = flags ? (flags[row0 + i] & 1) : (int8_t)flag_all;
+        const int rows = (int)min((long long)kEncRows, B - row0);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
+        for (int i = threadIdx.x; i < rows * kBoardWords; i += kF32Threads) sm[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < rows; i += kF32Threads) sflag[i] = flags ? (flags[row0 + i] & 1) : (int8_t)flag_all;
         __syncthreads();
-        const int total = rows * 99;
-        for (int c = threadIdx.x; c < total; c += kEncThreads) {
-            int r = c / 99, j = c - r * 99;
-            float2 v = f32_pair(reinterpret_cast<const int8_t*>(sm) + r * kBoardBytes, sflag[r], j);
-            *reinterpret_cast<float2*>(out + (row0 + r) * ld + 2 * j) = v;
+        float* dst = out + row0 * ld + 2 * j;
+#pragma unroll 4
+        for (int r = tr; r < rows; r += kF32RowsPerPass) {
+            const int8_t* b = reinterpret_cast<const int8_t*>(sm) + r * kBoardBytes;
+            float2 v;
+            if (kind == 0) {
+                const int c = b[bidx];
+                if ((unsigned)c < 16u) v = s_units[(c << 1) | half];
+                else { const float4 u = point_units_f32(c); v = half ? make_float2(u.z, u.w) : make_float2(u.x, u.y); }
+            } else if (kind == 1) {
+                v = make_float2((float)b[48 + half] * 0.5f, __uint_as_float(kOff15F32[b[50 + half] & 15]));
+            } else {
+                v = sflag[r] == 0 ? make_float2(1.0f, 0.0f) : make_float2(0.0f, 1.0f);
+            }
+            *reinterpret_cast<float2*>(dst + (long long)r * ld) = v;
         }
         __syncthreads();
     }
@@ -162,7 +178,7 @@ extern "C" int bg_encode_f32(const int8_t* boards52, const int8_t* flags, int fl
     if (B < 0 || ld < BG_FEATURES || (ld & 1)) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_f32: bad B or ld (need even ld >= 198)");
     if (B == 0) return BG_OK;
     if (!boards52 || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_f32: null pointer");
-    encode_f32_kernel<<<enc_grid(B), kEncThreads, 0, (cudaStream_t)stream>>>(boards52, flags, flag_all & 1, B, n_rows_dev, out, ld);
+    encode_f32_kernel<<<enc_grid(B), kF32Threads, 0, (cudaStream_t)stream>>>(boards52, flags, flag_all & 1, B, n_rows_dev, out, ld);
     return bg_set_error(cudaGetLastError(), "bg_encode_f32: launch");
 }
 
