@@ -22,3 +22,16 @@ best, scores, offsets, A = s.search(env.boards52[:48].clone(), env.players[:48].
 env.check_status()
 torch.cuda.synchronize()
 print("sanitize workload ok", int(best.shape[0]), int(A.shape[0]), s.leaves_evaluated)
+# N1 / N2: policy kernel, PPO rollout + GAE + ManualUpdate (bg_ppo_loss_grad), host step buffers
+from bg_b200.ppo import PPOConfig, PPOTrainer
+pnet = bg_b200.PolicyValueNet.random_init(dev, seed=0)
+tr = PPOTrainer(env, pnet, PPOConfig(t_horizon=6, num_epochs=2), seed=1)
+tr.train(2, log=None)
+host = bg_b200.HostStepBuffers(env)
+h_acts = torch.zeros(512, dtype=torch.int32).pin_memory()
+for t in range(4):
+    env.step(h_acts, with_features=True, host=host); host.wait()
+    h_acts.numpy()[:] = np.minimum(host.legal_counts.numpy() - 1, 3).clip(0)
+env.check_status()
+torch.cuda.synchronize()
+print("sanitize workload 2 ok", tr.learner.last)
