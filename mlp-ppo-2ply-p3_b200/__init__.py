@@ -7,7 +7,7 @@ The directory is named after the reference (mlp-ppo-2ply-p3_b200); import it as 
 """
 from ._lib import BgError, LIB_PATH, lib  # noqa: F401
 from .build import build  # noqa: F401
-from .engine import (FEATURES, LD_BF16, MovegenWorkspace, encode, from_board52, initial_board52,  # noqa: F401
+from .engine import (FEATURES, LD_BF16, MovegenWorkspace, as_board52, encode, from_board52, initial_board52,  # noqa: F401
                      legal_moves, to_board52)
 from .sharding import reduce_report, shard_range  # noqa: F401
 from .value_net import ValueNet  # noqa: F401

@@ -34,6 +34,14 @@ def to_board52(boards_4x24: torch.Tensor) -> torch.Tensor:
     return torch.cat([b[:, 0], b[:, 1], b[:, 2, 0:2], b[:, 3, 0:2]], dim=1).contiguous()
 
 
+def as_board52(boards: torch.Tensor) -> torch.Tensor:
+    """Packed (B,52) rows from either layout: the reference's (B,4,24) / (4,24) tensors are converted, (B,52) / (52,)
+    pass through."""
+    if boards.dim() >= 2 and tuple(boards.shape[-2:]) == (4, 24):
+        return to_board52(boards)
+    return boards.reshape(-1, 52).to(torch.int8).contiguous()
+
+
 def from_board52(b52: torch.Tensor) -> torch.Tensor:
     b52 = b52.reshape(-1, 52)
     out = torch.zeros((b52.shape[0], 4, 24), dtype=torch.int8, device=b52.device)
@@ -113,7 +121,7 @@ def legal_moves(boards52: torch.Tensor, players: torch.Tensor, dice: torch.Tenso
     counts_true is never truncated.
     """
     _require_cuda(boards52, players, dice)
-    boards52 = boards52.reshape(-1, 52).contiguous()
+    boards52 = as_board52(boards52)                       # the reference's (B,4,24) layout is accepted too
     B = boards52.shape[0]
     players = players.to(torch.int8).contiguous()
     dice = dice.to(torch.int8).reshape(B, 2).contiguous()
@@ -153,7 +161,7 @@ def encode(boards52: torch.Tensor, flags, dtype=torch.float32, ld: int | None = 
     default, columns 198.. zero (the MLP's K padding).  `out` reuses a buffer; `n_rows_dev` (1-element int64
     CUDA tensor) bounds the rows on the device, e.g. the env's alloc_rows counter."""
     _require_cuda(boards52)
-    boards52 = boards52.reshape(-1, 52).contiguous()
+    boards52 = as_board52(boards52)                       # the reference's (B,4,24) layout is accepted too
     B = boards52.shape[0]
     dev = boards52.device
     if isinstance(flags, torch.Tensor):

@@ -339,6 +339,24 @@ class B200BackgammonVecEnv:
         n = self.total_rows()
         return encode(self.after52[:n], self.row_players[:n], dtype=dtype)
 
+    @property
+    def legal_offsets(self) -> torch.Tensor:
+        """(N+1,) i64 CSR offsets of the legal plays in game order (exclusive prefix sum of legal_counts) -- the layout
+        afterstates_csr() returns.  (In the env's own buffer game g's rows start at legal_starts[g]: blocks are in
+        completion order, not game order.)"""
+        off = torch.zeros(self.num_envs + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(self.legal_counts, 0, out=off[1:])
+        return off
+
+    def afterstates_csr(self):
+        """-> (offsets (N+1,) i64, afterstates (total,52) i8) with the games' blocks in game order (a gather of the
+        env's buffer; rows of a game in the reference's legal_moves order)."""
+        off = self.legal_offsets
+        total = int(off[-1].item())
+        games = torch.repeat_interleave(torch.arange(self.num_envs, device=self.device), self.legal_counts.long(), output_size=total)
+        rows = self.legal_starts[games] + (torch.arange(total, device=self.device) - off[games])
+        return off, self.after52[rows]
+
     def _ragged_features(self, dtype):
         from .engine import encode
         counts = self.legal_counts.to(torch.int64)
@@ -367,6 +385,17 @@ class B200BackgammonVecEnv:
             self._ext_dice = d
         self.draws.zero_()
 
+    def set_dice(self, dice):
+        """Overwrite the current roll of every game ((N,2) int, values 1..6) and refresh the legal plays: the
+        one-step form of dice injection (the reference: assigning env.dice before update_legal_moves)."""
+        d = torch.as_tensor(dice).to(self.device, torch.int8).reshape(-1, 2)
+        if d.shape[0] != self.num_envs:
+            raise BgError("set_dice: need (N, 2)")
+        self.dice.copy_(d)
+        with torch.cuda.device(self.device):
+            self.update_legal_plays(obs=False, features=False)
+        self.check_status()
+
     def load_positions(self, boards, players, dice):
         """Overwrite every game's position (reference-layout (N,4,24) or packed (N,52)), mover and roll, then
         refresh the legal plays."""
@@ -377,6 +406,8 @@ class B200BackgammonVecEnv:
         with torch.cuda.device(self.device):
             self._refresh_legal_moves()
         self.check_status()
+
+    load_boards = load_positions                      # the name SURVEY.md 8(b) uses
 
 
 # The reference's class name, for callers that do `VectorizedBackgammonEnv(num_envs, ...)` (train.py:128-133)

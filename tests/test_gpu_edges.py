@@ -123,3 +123,28 @@ def test_host_step_buffers_mirror_the_device_results():
         assert torch.equal(obs, obs2) and torch.equal(rew, rew2) and torch.equal(done, done2)
     assert float(envs[0].rewards.min()) >= 0.0
     [e.check_status() for e in envs]
+
+
+def test_reference_layout_inputs_set_dice_and_csr_accessors():
+    """legal_moves / encode accept the reference's (B,4,24) tensors; set_dice overrides the roll and refreshes the legal
+    plays; afterstates_csr() = the env's blocks gathered in game order == legal_moves() of the same positions."""
+    import bg_b200
+    dev = torch.device("cuda:0")
+    env = bg_b200.B200BackgammonVecEnv(num_envs=700, device=dev, seed=21, check_every=0)
+    env.reset()
+    for t in range(40):
+        env.step(env.random_actions(3, t))
+    b424 = env.boards()                                           # (N,4,24) reference layout
+    c1, o1, a1 = bg_b200.legal_moves(b424, env.players, env.dice, max_rows_per_board=500)
+    c2, o2, a2 = bg_b200.legal_moves(env.boards52, env.players, env.dice, max_rows_per_board=500)
+    assert torch.equal(c1, c2) and torch.equal(o1, o2) and torch.equal(a1, a2)
+    assert torch.equal(bg_b200.encode(b424, env.players), bg_b200.encode(env.boards52, env.players))
+    off, rows = env.afterstates_csr()
+    assert torch.equal(off, o2) and torch.equal(rows, a2) and torch.equal(off, env.legal_offsets)
+    dice = torch.randint(1, 7, (700, 2), dtype=torch.int8, device=dev)
+    env.set_dice(dice)
+    c3, o3, a3 = bg_b200.legal_moves(env.boards52, env.players, dice, max_rows_per_board=500)
+    off, rows = env.afterstates_csr()
+    assert torch.equal(env.legal_counts, c3.clamp(max=500)) and torch.equal(off, o3) and torch.equal(rows, a3)
+    with pytest.raises(bg_b200.BgError):
+        env.set_dice(dice[:5])
