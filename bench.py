@@ -224,6 +224,16 @@ def run_engine(args):
         env._refresh_legal_moves()
     eb.record(); torch.cuda.synchronize()
     k1_alone_ms = ea.elapsed_time(eb) / 20
+    # ... and whole steps with the encoders AFTER K1 (nothing overlapped): K1's share of this serialised step is what the
+    # ncu launch list (profiles/, kernels serialised by the profiler) shows
+    overlap_saved, args.no_overlap = args.no_overlap, True
+    ea.record()
+    for _ in range(20):
+        one_step(t); t += 1
+    eb.record(); torch.cuda.synchronize()
+    args.no_overlap = overlap_saved
+    step_serial_ms = ea.elapsed_time(eb) / 20
+    launches[0] -= 20 * 8
     rows_per_step = float(rows_acc.item()) / K
     n_launch = launches[0]
 
@@ -271,13 +281,13 @@ def run_engine(args):
               "root_afterstates_per_s": a / sec, "leaves_per_s": l / sec,
               "note": f"{world} ranks, each its own {args.twoply_roots} roots; sum over ranks / max time over ranks (best of 3)"}
 
-    tm = torch.tensor([ms, e2e_s * 1e3, k1_ms, k1_alone_ms], dtype=torch.float64, device=dev)
+    tm = torch.tensor([ms, e2e_s * 1e3, k1_ms, k1_alone_ms, step_serial_ms], dtype=torch.float64, device=dev)
     rw = torch.tensor([rows_per_step], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dist.all_reduce(rw, op=dist.ReduceOp.SUM)
         rw /= world
-    ms, e2e_ms, k1_ms, k1_alone_ms = [float(x) for x in tm.tolist()]
+    ms, e2e_ms, k1_ms, k1_alone_ms, step_serial_ms = [float(x) for x in tm.tolist()]
     rows_per_step = float(rw.item())
     if rank != 0:
         if world > 1:
@@ -321,11 +331,13 @@ def run_engine(args):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / (ms / K),
                      "k1_ms_per_launch_alone": k1_alone_ms, "achieved_alone": k1_bytes / (k1_alone_ms * 1e-3) / 1e9,
+                     "ms_per_step_serial": step_serial_ms, "k1_share_of_step_serial": k1_alone_ms / step_serial_ms,
                      "algorithmic_bytes_per_launch": k1_bytes,
                      "note": "K1 is integer-issue bound (SURVEY 8(d)); the HBM fraction is reported as required. In the step "
                              "the encoders (K3) run on a second stream beside K1's overflow tiers, so k1_ms_per_launch (CUDA "
                              "events around K1's three launches inside the step) includes that sharing; *_alone is the same "
-                             "launch sequence with nothing beside it. traffic = dram bytes of the tier 0 + tier 1 launches "
+                             "launch sequence with nothing beside it, and k1_share_of_step_serial = that / a step with the encoders "
+                             "after K1 -- the share the profiler's serialised launch list shows (profiles/). traffic = dram bytes of the tier 0 + tier 1 launches "
                              "(ncu --set full, profiles/): below the algorithmic bytes because the afterstate rows are still in "
                              "the 126 MB L2 when the encoder reads them", "issue": issue},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * N * 4, "d2h_bytes_per_step": world * N * 9,
