@@ -148,4 +148,21 @@ __device__ __forceinline__ void build_half_row(const uint32_t (&w)[kBoardWords],
     }
 }
 
+// chunks [K0, K1) of the row (compile-time bounds): the share of one of several producer threads of a position; only the
+// board words those chunks read are loaded from the staged row
+template <int K0, int K1>
+__device__ __forceinline__ void build_row_chunks(const uint32_t* srow, int flag, const FeatureLut* lut, uint32_t tmem_row) {
+    uint32_t w[kBoardWords];
+#pragma unroll
+    for (int i = 0; i < kBoardWords; ++i) {
+        const bool used = (i < 12 && 2 * i + 1 >= K0 && 2 * i < K1) || (i == 12 && K1 > 24);
+        w[i] = used ? srow[i] : 0u;
+    }
+#pragma unroll
+    for (int kc = K0; kc < K1; ++kc) {
+        const uint4 v = feature_chunk_regs(w, flag, kc, lut);
+        tmem_st4(tmem_row + (uint32_t)(kc * 4), v);
+    }
+}
+
 }  // namespace bg

@@ -28,9 +28,9 @@ constexpr int kStages = 2;             // A tiles / TMEM accumulators in flight
 constexpr int kAColsPerTile = kKPad / 2;                 // 104 TMEM columns per A tile (2 bf16 per column)
 constexpr int kTmemACol0 = kStages * kHidden;            // first A column (after the accumulators)
 constexpr int kTmemCols = 512;
-// warp roles: 0-7 epilogue (warp w: TMEM lanes 32(w%4).., columns 64(w/4)..), 8-15 A-tile producers (2 threads per
-// position), 16 MMA issuer
-constexpr int kEpiThreads = 256, kProdThreads = 256;
+// warp roles: 0-7 epilogue (warp w: TMEM lanes 32(w%4).., columns 64(w/4)..), 8-23 A-tile producers (4 threads per
+// position), 24 MMA issuer
+constexpr int kEpiThreads = 256, kProdThreads = 512;
 constexpr int kEpiWarps = kEpiThreads / 32, kProdWarps = kProdThreads / 32;
 constexpr int kMlpThreads = kEpiThreads + kProdThreads + 32;
 
@@ -112,18 +112,24 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
     if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
         // ================= producers =================
         const int ptid = tid - kEpiThreads;                    // 0..255
-        const int row = ptid & (kTileM - 1), half = ptid >> 7;  // two threads per position: chunks [13 half, 13 half + 13)
+        const int row = ptid & (kTileM - 1), quarter = ptid >> 7;  // four threads per position: chunks [7 q, min(7 q + 7, 26))
         // boards (and flags) of tile k+1 are prefetched with cp.async while tile k is being expanded
         const uint32_t boards_s[2] = {smem_u32(&S.boards[0][0]), smem_u32(&S.boards[1][0])};
+        const unsigned char* bsrc = reinterpret_cast<const unsigned char*>(boards + begin * kBoardBytes);
+        const bool base16 = (reinterpret_cast<uintptr_t>(bsrc) & 15u) == 0;   // tiles are 6,656 B apart: one alignment for all
+        const long long nrows = B - begin;
         auto prefetch = [&](long long tile, int s) {
-            const long long row0 = begin + tile * kTileM;
-            const int rows = (int)min((long long)kTileM, B - row0);
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(boards + row0 * kBoardBytes);
-            const int bytes = rows * kBoardBytes;
-            // 16-byte copies for the aligned bulk (always the case when the rows start at a multiple of 4), words for the rest
-            const int n16 = (reinterpret_cast<uintptr_t>(src) & 15u) == 0 ? bytes >> 4 : 0;
-            for (int i = ptid; i < n16; i += kProdThreads) cp_async16_s(boards_s[s] + 16u * i, src + 16 * i);
-            for (int i = 4 * n16 + ptid; i < (bytes >> 2); i += kProdThreads) cp_async4_s(boards_s[s] + 4u * i, src + 4 * i);
+            const unsigned char* src = bsrc + tile * (kTileM * kBoardBytes);
+            const long long left = nrows - tile * kTileM;
+            if (base16 && left >= kTileM) {
+                // a full, 16-byte aligned tile (every tile but the last when the rows start at a multiple of 4): 416 copies of 16 bytes
+                if (ptid < kTileM * kBoardBytes / 16) cp_async16_s(boards_s[s] + 16u * ptid, src + 16 * ptid);
+            } else {
+                const int bytes = (int)min((long long)kTileM, left) * kBoardBytes;
+                const int n16 = base16 ? bytes >> 4 : 0;
+                for (int i = ptid; i < n16; i += kProdThreads) cp_async16_s(boards_s[s] + 16u * i, src + 16 * i);
+                for (int i = 4 * n16 + ptid; i < (bytes >> 2); i += kProdThreads) cp_async4_s(boards_s[s] + 4u * i, src + 4 * i);
+            }
             cp_async_commit();
         };
         if ((long long)blockIdx.x < n_tiles) prefetch(blockIdx.x, 0);
@@ -131,20 +137,21 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
             const int s = k & 1;
             const uint32_t it = (uint32_t)(k >> 1);
-            const long long row0 = begin + tile * kTileM;
-            const int rows = (int)min((long long)kTileM, B - row0);
-            const int fl = row < rows ? (int)(((flags ? __ldg(flags + row0 + row) : flag_all) ^ flip_flags) & 1) : 0;
+            // the turn flag is part of chunk 24: only the last quarter's thread needs it (issued early, consumed late)
+            int fl = flag_all;
+            if (quarter == 3 && flags) { const long long r = begin + tile * kTileM + row; fl = r < B ? (int)__ldg(flags + r) : 0; }
+            fl = (fl ^ flip_flags) & 1;
             cp_async_wait_all();                                // this thread's share of tile k's boards has landed
             asm volatile("bar.sync 1, %0;\n" :: "n"(kProdThreads) : "memory");   // ... and everybody else's; tile k-1 is fully built
             if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x, s ^ 1);
-            uint32_t w[kBoardWords];
-#pragma unroll
-            for (int i = 0; i < kBoardWords; ++i) w[i] = S.boards[s][row * kBoardWords + i];   // stride 13 words: conflict-free
+            const uint32_t* srow = &S.boards[s][row * kBoardWords];              // stride 13 words: conflict-free
             mbar_wait(&S.a_empty[s], (it & 1u) ^ 1u);           // MMAs that read A[s] two tiles ago are done
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kTmemACol0 + s * kAColsPerTile);
-            if (half == 0) build_half_row<0>(w, fl, &S.flut, trow);
-            else           build_half_row<1>(w, fl, &S.flut, trow);
+            if (quarter == 0)      build_row_chunks<0, 7>(srow, fl, &S.flut, trow);
+            else if (quarter == 1) build_row_chunks<7, 14>(srow, fl, &S.flut, trow);
+            else if (quarter == 2) build_row_chunks<14, 21>(srow, fl, &S.flut, trow);
+            else                   build_row_chunks<21, 26>(srow, fl, &S.flut, trow);
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             mbar_arrive(&S.a_full[s]);
@@ -182,25 +189,27 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
             mbar_wait(&S.acc_full[s], it & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
-            uint32_t acc[64];
+            uint32_t acc[32];
             const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * kHidden + 64 * chalf);
-            tmem_ld32(taddr, acc);
-            tmem_ld32(taddr + 32, acc + 32);
-            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-                const float4 ww = *reinterpret_cast<const float4*>(&S.wv[64 * chalf + j]);
-                if (BIAS) {
-                    const float4 bb = *reinterpret_cast<const float4*>(&S.b1[64 * chalf + j]);
-                    v0 = fmaf(ww.x, fmaxf(__uint_as_float(acc[j + 0]) + bb.x, 0.0f), v0);
-                    v1 = fmaf(ww.y, fmaxf(__uint_as_float(acc[j + 1]) + bb.y, 0.0f), v1);
-                    v2 = fmaf(ww.z, fmaxf(__uint_as_float(acc[j + 2]) + bb.z, 0.0f), v2);
-                    v3 = fmaf(ww.w, fmaxf(__uint_as_float(acc[j + 3]) + bb.w, 0.0f), v3);
-                } else {                                             // the bias came out of the GEMM (columns 198, 199)
-                    v0 = fmaf(ww.x, fmaxf(__uint_as_float(acc[j + 0]), 0.0f), v0);
-                    v1 = fmaf(ww.y, fmaxf(__uint_as_float(acc[j + 1]), 0.0f), v1);
-                    v2 = fmaf(ww.z, fmaxf(__uint_as_float(acc[j + 2]), 0.0f), v2);
-                    v3 = fmaf(ww.w, fmaxf(__uint_as_float(acc[j + 3]), 0.0f), v3);
+            for (int pass = 0; pass < 2; ++pass) {
+                tmem_ld32(taddr + 32 * pass, acc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 ww = *reinterpret_cast<const float4*>(&S.wv[64 * chalf + 32 * pass + j]);
+                    if (BIAS) {
+                        const float4 bb = *reinterpret_cast<const float4*>(&S.b1[64 * chalf + 32 * pass + j]);
+                        v0 = fmaf(ww.x, fmaxf(__uint_as_float(acc[j + 0]) + bb.x, 0.0f), v0);
+                        v1 = fmaf(ww.y, fmaxf(__uint_as_float(acc[j + 1]) + bb.y, 0.0f), v1);
+                        v2 = fmaf(ww.z, fmaxf(__uint_as_float(acc[j + 2]) + bb.z, 0.0f), v2);
+                        v3 = fmaf(ww.w, fmaxf(__uint_as_float(acc[j + 3]) + bb.w, 0.0f), v3);
+                    } else {                                             // the bias came out of the GEMM (columns 198, 199)
+                        v0 = fmaf(ww.x, fmaxf(__uint_as_float(acc[j + 0]), 0.0f), v0);
+                        v1 = fmaf(ww.y, fmaxf(__uint_as_float(acc[j + 1]), 0.0f), v1);
+                        v2 = fmaf(ww.z, fmaxf(__uint_as_float(acc[j + 2]), 0.0f), v2);
+                        v3 = fmaf(ww.w, fmaxf(__uint_as_float(acc[j + 3]), 0.0f), v3);
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
