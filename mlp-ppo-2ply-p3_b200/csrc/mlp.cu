@@ -28,7 +28,7 @@ constexpr int kStages = 2;             // A tiles / TMEM accumulators in flight
 constexpr int kAColsPerTile = kKPad / 2;                 // 104 TMEM columns per A tile (2 bf16 per column)
 constexpr int kTmemACol0 = kStages * kHidden;            // first A column (after the accumulators)
 constexpr int kTmemCols = 512;
-// warp roles: 0-7 epilogue (warp w: TMEM lanes 32(w%4).., columns 64(w/4)..), 8-23 A-tile producers (4 threads per
+// warp roles: 0-7 epilogue (warp w: TMEM lanes 32(w%4).., tiles of parity w/4), 8-23 A-tile producers (4 threads per
 // position), 24 MMA issuer
 constexpr int kEpiThreads = 256, kProdThreads = 512;
 constexpr int kEpiWarps = kEpiThreads / 32, kProdWarps = kProdThreads / 32;
@@ -39,7 +39,6 @@ struct MlpSmem {
     uint32_t boards[kStages][kTileM * kBoardWords];
     float b1[kHidden];
     float wv[kHidden];
-    float part[2][kTileM];             // partial value-head sums of the upper 64 hidden units
     FeatureLut flut;
     unsigned long long a_full[kStages], a_empty[kStages], acc_full[kStages], acc_empty[kStages];
     uint32_t tmem_base;
@@ -93,7 +92,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&S.a_full[s], kProdThreads); mbar_init(&S.a_empty[s], 1);
-            mbar_init(&S.acc_full[s], 1);          mbar_init(&S.acc_empty[s], kEpiThreads);
+            mbar_init(&S.acc_full[s], 1);          mbar_init(&S.acc_empty[s], kEpiThreads / 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -178,28 +177,29 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
         }
     } else if (warp < kEpiWarps) {
         // ================= epilogue =================
+        // warps 0-3 take the even tiles of this CTA (accumulator 0), warps 4-7 the odd ones (accumulator 1); a warp reads all 128
+        // hidden units of its 32 rows in four passes of 32 columns: no partial sums to combine across warps, no CTA-level barrier,
+        // and two tile times to finish a tile
         const int row = (warp & 3) * 32 + lane;                 // TMEM lane = position within the tile
-        const int chalf = warp >> 2;                            // hidden units [64 chalf, 64 chalf + 64)
-        int k = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
-            const int s = k & 1;
+        const int s = warp >> 2;                                // accumulator / parity of the tiles this warp handles
+        int k = s;
+        for (long long tile = blockIdx.x + (long long)s * gridDim.x; tile < n_tiles; tile += 2 * (long long)gridDim.x, k += 2) {
             const uint32_t it = (uint32_t)(k >> 1);
-            const long long row0 = begin + tile * kTileM;
-            const int rows = (int)min((long long)kTileM, B - row0);
+            const long long r = begin + tile * kTileM + row;
             mbar_wait(&S.acc_full[s], it & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
             uint32_t acc[32];
-            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * kHidden + 64 * chalf);
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(s * kHidden);
 #pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
+            for (int pass = 0; pass < 4; ++pass) {
                 tmem_ld32(taddr + 32 * pass, acc);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 ww = *reinterpret_cast<const float4*>(&S.wv[64 * chalf + 32 * pass + j]);
+                    const float4 ww = *reinterpret_cast<const float4*>(&S.wv[32 * pass + j]);
                     if (BIAS) {
-                        const float4 bb = *reinterpret_cast<const float4*>(&S.b1[64 * chalf + 32 * pass + j]);
+                        const float4 bb = *reinterpret_cast<const float4*>(&S.b1[32 * pass + j]);
                         v0 = fmaf(ww.x, fmaxf(__uint_as_float(acc[j + 0]) + bb.x, 0.0f), v0);
                         v1 = fmaf(ww.y, fmaxf(__uint_as_float(acc[j + 1]) + bb.y, 0.0f), v1);
                         v2 = fmaf(ww.z, fmaxf(__uint_as_float(acc[j + 2]) + bb.z, 0.0f), v2);
@@ -214,17 +214,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_value_kernel(
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             mbar_arrive(&S.acc_empty[s]);                        // accumulator s may be overwritten
-            const float part = (v0 + v1) + (v2 + v3);
-            if (chalf == 1) S.part[k & 1][row] = part;
-            asm volatile("bar.sync 2, %0;\n" :: "n"(kEpiThreads) : "memory");
-            if (chalf == 0 && row < rows) {
-                float v = bv + (part + S.part[k & 1][row]);
+            if (r < B) {
+                float v = bv + ((v0 + v1) + (v2 + v3));
                 if (terminal_aware) {
-                    const int8_t* b = boards + (row0 + row) * kBoardBytes;
-                    const int fl = ((flags ? flags[row0 + row] : flag_all) ^ flip_flags) & 1;
+                    const int8_t* b = boards + r * kBoardBytes;
+                    const int fl = ((flags ? flags[r] : flag_all) ^ flip_flags) & 1;
                     if (b[50 + fl] == 15) v = win_reward(b, fl);
                 }
-                values[row0 + row] = v;
+                values[r] = v;
             }
         }
     }
