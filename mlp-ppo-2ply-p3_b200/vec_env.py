@@ -73,8 +73,11 @@ class HostStepBuffers:
         self.stepped = torch.cuda.Event()                  # K2 of the step done: rewards / dones final
         self.legal_ready = torch.cuda.Event()              # K1 of the step done (recorded inside bg_update_legal_plays)
         self.ready = torch.cuda.Event()                    # ... and everything copied to the host
+        self.obs_ready = torch.cuda.Event()                # observations of the step encoded (side stream)
+        self.actions_up = torch.cuda.Event()               # the step's actions copied to the device (copy stream)
         with torch.cuda.device(dev):
-            self.stepped.record(); self.legal_ready.record(); self.ready.record()   # torch creates the handles on the first record
+            for e in (self.stepped, self.legal_ready, self.ready, self.obs_ready, self.actions_up):
+                e.record()                                 # (handles are created on the first record)
 
     def wait(self):
         self.ready.synchronize()
@@ -216,9 +219,18 @@ class B200BackgammonVecEnv:
             import numpy as np
             acts = [0 if a is None else int(a) for a in actions] if not isinstance(actions, np.ndarray) else actions
             actions = torch.as_tensor(acts)
-        actions = actions.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
         if actions.shape[0] != self.num_envs:
             raise BgError("step: need one action per env")
+        if host is not None and not actions.is_cuda:
+            # host actions go up on the copy stream, i.e. beside the encoders of the previous step that are still running on
+            # the main stream, not behind them
+            with torch.cuda.stream(host.stream):
+                actions = actions.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
+                host.actions_up.record(host.stream)
+            torch.cuda.current_stream(self.device).wait_event(host.actions_up)
+            actions.record_stream(torch.cuda.current_stream(self.device))
+        else:
+            actions = actions.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
         N, dev = self.num_envs, self.device
         with torch.cuda.device(dev):
             if host is not None:                                                # K1 rewrites legal_counts: not before the previous
@@ -234,8 +246,20 @@ class B200BackgammonVecEnv:
             self._apply_actions(actions)
             if host is not None:                                                # rewards / dones are final after K2
                 host.stepped.record()
-            self.update_legal_plays(obs=return_obs, features=with_features, overlap=overlap,
+            obs_beside_k1 = host is not None and return_obs and not overlap
+            if obs_beside_k1:
+                # the observations depend on K2 only: encode them on the side stream beside K1's issue-bound tier 0 (20 us of
+                # HBM writes that cost K1 nothing) instead of after K1
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=dev)
+                self._side.wait_event(host.stepped)
+                check(lib().bg_encode_f32(self.boards52.data_ptr(), self.players.data_ptr(), 0, N, None, self.obs_f32.data_ptr(),
+                                          FEATURES, self._side.cuda_stream), "bg_encode_f32")
+                host.obs_ready.record(self._side)
+            self.update_legal_plays(obs=return_obs and not obs_beside_k1, features=with_features, overlap=overlap,
                                     k1_events=(None, host.legal_ready) if host is not None else None)
+            if obs_beside_k1:
+                torch.cuda.current_stream().wait_event(host.obs_ready)
             if host is not None:
                 cs = host.stream
                 cs.wait_event(host.stepped)
