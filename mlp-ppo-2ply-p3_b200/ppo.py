@@ -246,9 +246,13 @@ class FlatParams:
 class PPOLearner:
     """Clipped-surrogate PPO update over a finished rollout (ppo_agent.py:218-366), data parallel."""
 
-    def __init__(self, state_dict, device, cfg: PPOConfig | None = None, dist=None):
+    def __init__(self, state_dict, device, cfg: PPOConfig | None = None, dist=None, host_logic_test: bool = False):
         self.cfg = cfg or PPOConfig()
         self.device = torch.device(device)
+        if self.device.type != "cuda" and not host_logic_test:
+            # no CPU fallback: the learner runs on the GPU.  The CPU suite exercises the host logic (flat bucket, gloo
+            # all-reduce, return normalisation, the reference's loss arithmetic in torch) by saying so explicitly.
+            raise BgError("PPOLearner needs a CUDA device (host_logic_test=True is for the CPU test-suite only)")
         self.dist = dist
         self.fp = FlatParams(state_dict, self.device)
         self.optimizer = torch.optim.Adam(list(self.fp.params.values()), lr=self.cfg.learning_rate)   # ppo_agent.py:83

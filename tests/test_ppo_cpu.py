@@ -74,7 +74,7 @@ def test_update_moves_weights_like_reference():
     from bg_b200.ppo import PPOConfig, PPOLearner
     g, sd0, sd1 = _golden()
     x, counts, actions, logp, values, ret = _batch(g)
-    L = PPOLearner(sd0, "cpu", PPOConfig())
+    L = PPOLearner(sd0, "cpu", PPOConfig(), host_logic_test=True)
     stats = L.update(x, counts, actions, logp, values, ret)
     want = g["loss_lr1e3"]
     got = np.array([stats["policy_loss"], stats["value_loss"], stats["entropy"], stats["total_loss"]])
@@ -99,7 +99,7 @@ def _dp_worker(rank, world, port, q):
     x, counts, actions, logp, values, ret = _batch(g)
     n = x.shape[0] // world
     sl = slice(rank * n, (rank + 1) * n)                          # this rank's shard of the samples
-    L = PPOLearner(sd0, "cpu", PPOConfig(autocast=False), dist=dist)
+    L = PPOLearner(sd0, "cpu", PPOConfig(autocast=False), dist=dist, host_logic_test=True)
     L.update(x[sl], counts[sl], actions[sl], logp[sl], values[sl], ret[sl])
     flat = L.fp.flat.detach().clone()
     gathered = [torch.zeros_like(flat) for _ in range(world)]
@@ -128,7 +128,7 @@ def test_data_parallel_update_equals_single_process():
     x, counts, actions, logp, values, ret = _batch(g)
     n = (x.shape[0] // world) * world
     torch.set_num_threads(1)
-    L = PPOLearner(sd0, "cpu", PPOConfig(autocast=False))
+    L = PPOLearner(sd0, "cpu", PPOConfig(autocast=False), host_logic_test=True)
     L.update(x[:n], counts[:n], actions[:n], logp[:n], values[:n], ret[:n])
     single = L.fp.flat.detach().numpy()
     assert L.fp.numel == 90101                                    # 90,101 parameters = one 360 KB bucket
@@ -136,3 +136,12 @@ def test_data_parallel_update_equals_single_process():
     # the bulk must agree tightly
     diff = np.abs(single - flats[0])
     assert np.quantile(diff, 0.99) < 2e-4 and diff.max() < 1e-2, (np.quantile(diff, 0.99), diff.max())
+
+
+def test_learner_refuses_cpu_unless_host_logic_test():
+    from bg_b200 import BgError
+    from bg_b200.ppo import PPOConfig, PPOLearner
+    g = np.load(GOLDEN)
+    sd0 = {k[3:]: torch.tensor(g[k]) for k in g.files if k.startswith("w0.")}
+    with pytest.raises(BgError):
+        PPOLearner(sd0, "cpu", PPOConfig())
