@@ -226,7 +226,8 @@ int bg_gae(const float* rewards, const uint8_t* dones, const float* values /*nul
  *   values == NULL: the value head was computed as row 500 of the action head's GEMM -- the value is read from column 500
  *   of the logits (ld >= 504), d loss / d value is written to column 500 of dlogits (and to dvalues if non-null) and its
  *   sum to dbias[500], so the value head's backward rides through the action head's backward GEMMs.
- *   sums[0..2] += sum_i policy term, sum_i (v - R)^2, sum_i entropy  (caller zeroes; loss = (s0 + c_v s1 - c_e s2) / B). */
+ *   sums[0..2] += sum_i policy term, sum_i (v - R)^2, sum_i entropy  (caller zeroes; loss = (s0 + c_v s1 - c_e s2) / B).
+ *   Two launches on `stream`: rows with 1..128 legal slots and the action inside the prefix, four per warp; then the rest. */
 int bg_ppo_loss_grad(const void* logits, int logits_bf16, long long ld, const float* values, const int32_t* counts,
                      const int32_t* actions, const float* old_log_probs, const float* advantages, const float* returns,
                      long long B, float eps_clip, float value_coef, float entropy_coef, void* dlogits, float* dvalues,

@@ -9,6 +9,7 @@
 // lambda = 1 and last_values = NULL give exactly compute_returns for each game (ret_t = sum_k gamma^k r_{t+k} up
 // to the end of the game or of the rollout).  The reference walks its memory -- steps of all envs interleaved,
 // src/agent/train.py:64-66 -- as ONE sequence; that is reproduced by calling this with T = T*N, N = 1.
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "bg_device.cuh"
 #include "bg_internal.h"
@@ -92,6 +93,11 @@ template <typename T> struct LossRow {
 // is not a legal slot keep all four quads and the literal arithmetic.
 __device__ __forceinline__ int loss_active_quads(int n, int a) { return (n <= 0 || a >= n) ? 4 : (n + 127) >> 7; }
 
+// Rows the packed kernel takes: 1..128 legal slots (one quad) and a stored action inside the legal prefix.
+__device__ __forceinline__ bool loss_row_is_packed(int n, int a) { return n >= 1 && n <= 128 && a >= 0 && a < n; }
+__device__ __forceinline__ float loss_scalar(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float loss_scalar(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
 template <typename T>
 __device__ __forceinline__ void loss_row_load(LossRow<T>& r, long long row, int n, int a, int lane, const T* __restrict__ logits,
                                               long long ld, const float* __restrict__ values, const float* __restrict__ old_logp,
@@ -109,12 +115,164 @@ __device__ __forceinline__ void loss_row_load(LossRow<T>& r, long long row, int 
     r.v = values ? __ldg(values + row) : 0.0f;
 }
 
+// The common rows (loss_row_is_packed: 94 % of a self-play batch, mean 18 legal slots), FOUR per warp: eight lanes per row,
+// lane s of a row holding slots 16 s .. 16 s + 15 of the only quad that has legal slots, reductions over 8 lanes; columns
+// 128 .. ld-1 of dlogits are written as zeros (column 500 = d loss / d value when the value rides in the logits).  One row per
+// warp spent ~470 warp-instructions on a row whatever its mask; here it is ~85.  Same arithmetic as the general kernel below.
+template <typename T> struct LossPacked {
+    typename Vec4<T>::Raw x[4];
+    int n, a;
+    float adv, old_logp, ret, v;
+};
+template <typename T>
+__device__ __forceinline__ void loss_packed_load(LossPacked<T>& d, long long r, long long B, int sub, const T* __restrict__ logits, long long ld,
+                                                 const float* __restrict__ values, const int32_t* __restrict__ counts,
+                                                 const int32_t* __restrict__ actions, const float* __restrict__ old_logp,
+                                                 const float* __restrict__ adv, const float* __restrict__ returns) {
+    d.n = 0; d.a = 0; d.adv = 0.0f; d.old_logp = 0.0f; d.ret = 0.0f; d.v = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d.x[k] = Vec4<T>::zero();
+    if (r < B) {
+        const T* src = logits + r * ld;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d.x[k] = Vec4<T>::load_raw(src + 16 * sub + 4 * k);     // (read whatever the row's class: no dependent load)
+        d.n = __ldg(counts + r); d.a = __ldg(actions + r);
+        d.adv = __ldg(adv + r); d.old_logp = __ldg(old_logp + r); d.ret = __ldg(returns + r);
+        d.v = values ? __ldg(values + r) : loss_scalar(src + BG_ACTIONS);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
+    const T* __restrict__ logits, long long ld, const float* __restrict__ values, const int32_t* __restrict__ counts,
+    const int32_t* __restrict__ actions, const float* __restrict__ old_logp, const float* __restrict__ adv,
+    const float* __restrict__ returns, long long B, float eps_clip, float value_coef, float entropy_coef,
+    T* __restrict__ dlogits, float* __restrict__ dvalues, float* __restrict__ dbias, float* __restrict__ sums) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
+    __shared__ float s_part[kLossWarps][3];
+    __shared__ float s_col[kLossWarps][129];                         // 128 slot columns + the value column
+    float pl = 0.0f, vl = 0.0f, ent = 0.0f, vsum = 0.0f;
+    float colsum[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) colsum[k] = 0.0f;
+    const float invB = 1.0f / (float)B;
+    const float ce = entropy_coef * invB;
+    const long long S = (long long)gridDim.x * kLossWarps;          // persistent warps stride over groups of 4 rows
+    long long g4 = (long long)blockIdx.x * kLossWarps + warp;
+    LossPacked<T> nx;
+    loss_packed_load(nx, g4 * 4 + grp, B, sub, logits, ld, values, counts, actions, old_logp, adv, returns);
+#pragma unroll 1
+    for (; g4 * 4 < B; g4 += S) {
+        const LossPacked<T> cur = nx;
+        loss_packed_load(nx, (g4 + S) * 4 + grp, B, sub, logits, ld, values, counts, actions, old_logp, adv, returns);
+        const long long row = g4 * 4 + grp;
+        const bool act = row < B && loss_row_is_packed(cur.n, cur.a);
+        const int n = act ? cur.n : 1, a = act ? cur.a : 0;         // (idle lanes compute on a finite dummy row)
+        float z[16];
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float x[4];
+            Vec4<T>::unpack(cur.x[k], x);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = 16 * sub + 4 * k + e;
+                z[4 * k + e] = i < n ? (act ? x[e] : 0.0f) : -INFINITY;
+                m = fmaxf(m, z[4 * k + e]);
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+        float ssum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) ssum += __expf(z[k] - m);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) ssum += __shfl_xor_sync(kFull, ssum, o);
+        const float lse = m + __logf(ssum);
+        float h = 0.0f, lpa = 0.0f;
+        float p[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float lp = z[k] - lse;
+            p[k] = __expf(lp);
+            if (p[k] > 0.0f) h -= p[k] * lp;
+            if (16 * sub + k == a) lpa = lp;
+            z[k] = lp;
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) { h += __shfl_xor_sync(kFull, h, o); lpa += __shfl_xor_sync(kFull, lpa, o); }
+        const float A = cur.adv;
+        const float r = __expf(lpa - cur.old_logp);
+        const float rc = fminf(fmaxf(r, 1.0f - eps_clip), 1.0f + eps_clip);
+        const float s1 = r * A, s2 = rc * A;
+        const bool through = (r >= 1.0f - eps_clip && r <= 1.0f + eps_clip) || s1 < s2;
+        const float g = through ? -A * r * invB : 0.0f;
+        const float dv = cur.v - cur.ret;
+        const float dvalue = 2.0f * value_coef * dv * invB;
+        if (act) {
+            T* dst = dlogits + row * ld;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float x[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int kk = 4 * k + e;
+                    const float pk = p[kk];
+                    float d = -g * pk + (pk > 0.0f ? ce * pk * (z[kk] + h) : 0.0f);
+                    if (16 * sub + kk == a) d += g;
+                    x[e] = d;
+                    colsum[kk] += d;
+                }
+                Vec4<T>::store(dst + 16 * sub + 4 * k, x);
+            }
+            // quads 1..3 and the padding of the GEMM's N: exact zeros; column 500 carries d loss / d value when the value rides there
+            for (int c = 128 + 4 * sub; c < ld; c += 32) {
+                float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                if (!values && c == BG_ACTIONS) { x[0] = dvalue; vsum += dvalue; }
+                Vec4<T>::store(dst + c, x);
+            }
+            if (sub == 0) {
+                if (dvalues) dvalues[row] = dvalue;
+                pl -= fminf(s1, s2); vl += dv * dv; ent += h;
+            }
+        }
+    }
+    // the four rows of a warp hold the same columns: add them up, then the warps of the CTA, then one atomic per column
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) colsum[k] += __shfl_xor_sync(kFull, colsum[k], o);
+        pl += __shfl_xor_sync(kFull, pl, o); vl += __shfl_xor_sync(kFull, vl, o); ent += __shfl_xor_sync(kFull, ent, o);
+        vsum += __shfl_xor_sync(kFull, vsum, o);
+    }
+    if (lane == 0) { s_part[warp][0] = pl; s_part[warp][1] = vl; s_part[warp][2] = ent; }
+    if (grp == 0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s_col[warp][16 * sub + k] = colsum[k];
+    }
+    if (lane == 5) s_col[warp][128] = vsum;                          // (BG_ACTIONS - 128) % 32 == 4 * 5: lane group 5 writes column 500
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kLossWarps; ++w) t += s_part[w][threadIdx.x];
+        atomicAdd(&sums[threadIdx.x], t);
+    }
+    if (dbias && threadIdx.x < 129) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kLossWarps; ++w) t += s_col[w][threadIdx.x];
+        if (threadIdx.x < 128) atomicAdd(&dbias[threadIdx.x], t);
+        else if (!values) atomicAdd(&dbias[BG_ACTIONS], t);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_kernel(
     const T* __restrict__ logits, long long ld, const float* __restrict__ values, const int32_t* __restrict__ counts,
     const int32_t* __restrict__ actions, const float* __restrict__ old_logp, const float* __restrict__ adv,
     const float* __restrict__ returns, long long B, float eps_clip, float value_coef, float entropy_coef,
-    T* __restrict__ dlogits, float* __restrict__ dvalues, float* __restrict__ dbias, float* __restrict__ sums) {
+    T* __restrict__ dlogits, float* __restrict__ dvalues, float* __restrict__ dbias, float* __restrict__ sums, int all_rows) {
     constexpr float kMaskLog = -103.27893f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ float s_part[kLossWarps][3];
@@ -125,18 +283,34 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_kernel(
     for (int k = 0; k < 16; ++k) colsum[k] = 0.0f;
     const float invB = 1.0f / (float)B;
     const float ce = entropy_coef * invB;
-    const long long S = (long long)gridDim.x * kLossWarps;          // persistent warps stride over the rows
-    long long row = (long long)blockIdx.x * kLossWarps + warp;
-    // software pipeline: counts / actions two rows ahead (they decide which quads the prefetch reads), logits one row ahead
-    LossRow<T> nx;
-    int n1 = 0, a1 = 0;
-    if (row < B) loss_row_load(nx, row, __ldg(counts + row), __ldg(actions + row), lane, logits, ld, values, old_logp, adv, returns);
-    if (row + S < B) { n1 = __ldg(counts + row + S); a1 = __ldg(actions + row + S); }
+    const long long S = (long long)gridDim.x * kLossWarps;          // persistent warps stride over blocks of 32 rows
+    // This kernel handles the rows the packed kernel leaves out (loss_row_is_packed: passes, more than 128 legal slots, an
+    // action outside the legal prefix -- a few per cent of a self-play batch): every lane looks at one row of the block, the
+    // warp then works through the flagged rows one after the other, the next flagged row of the block being fetched while
+    // the current one is worked on.
+    long long blk = (long long)blockIdx.x * kLossWarps + warp;
+    int nl_next = 0, al_next = 0;                                   // counts / actions one block ahead
+    if (blk * 32 + lane < B) { nl_next = __ldg(counts + blk * 32 + lane); al_next = __ldg(actions + blk * 32 + lane); }
 #pragma unroll 1
-    for (; row < B; row += S) {
+    for (; blk * 32 < B; blk += S) {
+      const long long rl = blk * 32 + lane;
+      const int nl = nl_next, al = al_next;
+      if ((blk + S) * 32 + lane < B) { nl_next = __ldg(counts + (blk + S) * 32 + lane); al_next = __ldg(actions + (blk + S) * 32 + lane); }
+      unsigned todo = __ballot_sync(kFull, rl < B && (all_rows || !loss_row_is_packed(nl, al)));
+      LossRow<T> nx;
+      if (todo) {
+          const int j = __ffs(todo) - 1;
+          loss_row_load(nx, blk * 32 + j, __shfl_sync(kFull, nl, j), __shfl_sync(kFull, al, j), lane, logits, ld, values, old_logp, adv, returns);
+      }
+#pragma unroll 1
+      while (todo) {
+        const long long row = blk * 32 + (__ffs(todo) - 1);
+        todo &= todo - 1;
         const LossRow<T> cur = nx;
-        if (row + S < B) loss_row_load(nx, row + S, n1, a1, lane, logits, ld, values, old_logp, adv, returns);
-        if (row + 2 * S < B) { n1 = __ldg(counts + row + 2 * S); a1 = __ldg(actions + row + 2 * S); }
+        if (todo) {
+            const int j = __ffs(todo) - 1;
+            loss_row_load(nx, blk * 32 + j, __shfl_sync(kFull, nl, j), __shfl_sync(kFull, al, j), lane, logits, ld, values, old_logp, adv, returns);
+        }
         const int n = cur.n, a = cur.a;
         const int nq = loss_active_quads(n, a);
         float z[16], xv = 0.0f;
@@ -227,6 +401,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_kernel(
             if (dvalues) dvalues[row] = dvalue;
             pl -= fminf(s1, s2); vl += dv * dv; ent += h;
         }
+      }
     }
     if (lane == 0) { s_part[warp][0] = pl; s_part[warp][1] = vl; s_part[warp][2] = ent; }
     if (dbias) {
@@ -262,17 +437,30 @@ extern "C" int bg_ppo_loss_grad(const void* logits, int logits_bf16, long long l
     if (!logits || !counts || !actions || !old_log_probs || !advantages || !returns || !dlogits || !sums || (values && !dvalues))
         return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_loss_grad: null pointer");
     if (!values && ld <= BG_ACTIONS) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_loss_grad: values == NULL needs the value in column 500 (ld >= 504)");
-    const long long need = (B + bg::kLossWarps - 1) / bg::kLossWarps;
+    // two launches: the packed kernel for the common rows (four per warp), the general kernel for the others (BG_LOSS_GENERAL_ONLY=1:
+    // every row through the general kernel -- for tests / comparison)
+    static const int general_only = getenv("BG_LOSS_GENERAL_ONLY") ? atoi(getenv("BG_LOSS_GENERAL_ONLY")) : 0;
     const long long resident = (long long)bg_sm_count() * 2;                   // ~125 registers x 256 threads: two CTAs per SM
-    const unsigned grid = (unsigned)(need < resident ? need : resident);
-    if (logits_bf16)
-        bg::ppo_loss_grad_kernel<__nv_bfloat16><<<grid, bg::kLossWarps * 32, 0, (cudaStream_t)stream>>>(
+    const long long need_p = (B + 4 * bg::kLossWarps - 1) / (4 * bg::kLossWarps), need_g = (B + 32 * bg::kLossWarps - 1) / (32 * bg::kLossWarps);
+    const unsigned grid_p = (unsigned)(need_p < resident ? need_p : resident), grid_g = (unsigned)(need_g < resident ? need_g : resident);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (logits_bf16) {
+        if (!general_only)
+            bg::ppo_loss_grad_packed_kernel<__nv_bfloat16><<<grid_p, bg::kLossWarps * 32, 0, st>>>(
+                (const __nv_bfloat16*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
+                entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums);
+        bg::ppo_loss_grad_kernel<__nv_bfloat16><<<grid_g, bg::kLossWarps * 32, 0, st>>>(
             (const __nv_bfloat16*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
-            entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums);
-    else
-        bg::ppo_loss_grad_kernel<float><<<grid, bg::kLossWarps * 32, 0, (cudaStream_t)stream>>>(
+            entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums, general_only);
+    } else {
+        if (!general_only)
+            bg::ppo_loss_grad_packed_kernel<float><<<grid_p, bg::kLossWarps * 32, 0, st>>>(
+                (const float*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
+                entropy_coef, (float*)dlogits, dvalues, dbias, sums);
+        bg::ppo_loss_grad_kernel<float><<<grid_g, bg::kLossWarps * 32, 0, st>>>(
             (const float*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
-            entropy_coef, (float*)dlogits, dvalues, dbias, sums);
+            entropy_coef, (float*)dlogits, dvalues, dbias, sums, general_only);
+    }
     return bg_set_error(cudaGetLastError(), "bg_ppo_loss_grad: launch");
 }
 
