@@ -166,6 +166,8 @@ class ManualUpdate:
             self.B = B
 
     def _mm_f32(self, a, b):
+        """a @ b for bf16 operands with the f32 accumulator returned as is (torch.mm(..., out_dtype=float32), torch >= 2.8);
+        older torch: the bf16 result widened, as autograd under autocast would give."""
         if self.f32_out is None:
             try:
                 r = torch.mm(a, b, out_dtype=torch.float32)
@@ -173,9 +175,7 @@ class ManualUpdate:
                 return r
             except (TypeError, RuntimeError):
                 self.f32_out = False
-        if self.f32_out:
-            return torch.mm(a, b, out_dtype=torch.float32)
-        return torch.mm(a, b).float()
+        return torch.mm(a, b, out_dtype=torch.float32) if self.f32_out else torch.mm(a, b).float()
 
     @torch.no_grad()
     def epoch(self, params, grads, x, counts, actions, old_logp, adv, returns, eps_clip, value_coef, entropy_coef):
