@@ -449,7 +449,7 @@ int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* d
     // synchronisation is needed.
     rc = movegen_team_mid(boards, players, dice, ctr + 1, list_a, replicate, flip_player, mode, offsets, max_rows, after,
                           after_cap_rows, row_players, row_feats, counts_true, counts, starts, alloc, status, ctr + 2, list_b,
-                          ctr + 3, stream, (hook && mode == 2) ? 128 : 0);
+                          ctr + 3, stream, ((hook && mode == 2) || B >= 262144) ? 128 : 0);   // 128 threads per position when something shares the GPU or the list is long (throughput, not latency)
     if (rc != BG_OK) return rc;
     // Tier 2: the rest (> BG_MOVEGEN_CAP_MID boards in a level): one big CTA per position, BG_MOVEGEN_CAP_BIG
     // boards per level.  Positions that do not fit even this raise BG_STATUS_SCRATCH_OVERFLOW (never dropped silently).
