@@ -471,7 +471,7 @@ def main():
     ap.add_argument("--e2e-overlap-encoders", action="store_true",
                     help="e2e loop: encoders beside K1's overflow tiers (shorter GPU step, but K1 -- which the host waits for -- ends later)")
     ap.add_argument("--twoply-roots", type=int, default=4096)
-    ap.add_argument("--twoply-chunk", type=int, default=32768)
+    ap.add_argument("--twoply-chunk", type=int, default=98304)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
