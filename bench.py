@@ -270,8 +270,24 @@ def run_engine(args):
     env.check_status()
 
     extra = run_extras(bg_b200, env, torch, dev, args) if (world == 1 and not args.no_extras) else None
-    twoply_all = None
-    if world > 1 and not args.no_extras:                      # 2-ply on every rank's own roots (shards of the roots, replicas of the net)
+    twoply_all, greedy_all = None, None
+    if world > 1 and not args.no_extras:
+        # 1-ply greedy self-play (configs[2]: games sharded, the value net replicated), device events, max over ranks
+        gnet = bg_b200.ValueNet.random_init(dev, seed=0)
+        def greedy_step():
+            a_, _ = bg_b200.greedy_actions(env, gnet)
+            env.step_device(a_.clamp_(min=0))
+        greedy_step(); torch.cuda.synchronize(); dist.barrier()
+        ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ga.record()
+        for _ in range(30):
+            greedy_step()
+        gb.record(); torch.cuda.synchronize()
+        gt = torch.tensor([ga.elapsed_time(gb) / 30], dtype=torch.float64, device=dev)
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        greedy_all = {"env_steps_per_s": world * N / (float(gt.item()) * 1e-3), "ms_per_step": float(gt.item()), "games": world * N,
+                      "what": "K4 on every legal afterstate + segment argmax + K2 + K1; max over ranks"}
+        # 2-ply on every rank's own roots (shards of the roots, replicas of the net)
         tp2 = run_twoply(bg_b200, env, torch, dev, args)
         agg = torch.tensor([tp2["root_afterstates"], tp2["leaves"], tp2["roots"]], dtype=torch.float64, device=dev)
         tmax = torch.tensor([tp2["seconds"]], dtype=torch.float64, device=dev)
@@ -352,7 +368,7 @@ def run_engine(args):
     if extra is not None:
         line["extra"] = extra
     if twoply_all is not None:
-        line["extra"] = {"twoply": twoply_all}
+        line["extra"] = {"twoply": twoply_all, "greedy_1ply": greedy_all}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n, el = cpu_rollout(args.cpu_seconds, threads)
