@@ -28,6 +28,7 @@
 // the back); tiles gather their rows through it and scatter their results.
 // HBM traffic per position: 53 B board + 4 B count in, 12 B out.
 // TMEM columns: [0,128) acc1; [128,232) A1 / [128,192) A2; [256,384) and [384,512) acc2 ping/pong.
+#include <type_traits>
 #include <cuda_bf16.h>
 #include "bg_device.cuh"
 #include "bg_features.cuh"
@@ -69,7 +70,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
     const int32_t* __restrict__ legal_counts, const uint16_t* __restrict__ w1, const float* __restrict__ b1,
     const uint16_t* __restrict__ wa, const float* __restrict__ ba, const float* __restrict__ wv, float bv,
     unsigned long long seed, unsigned long long stream_base, uint32_t step, int greedy,
-    const int32_t* __restrict__ row_list, const unsigned int* __restrict__ n_class_a_dev, unsigned int* __restrict__ tile_ctr,
+    const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_list2, const unsigned int* __restrict__ class_ctr,
+    unsigned int* __restrict__ tile_ctr,
     int32_t* __restrict__ actions, float* __restrict__ logp, float* __restrict__ values, float* __restrict__ logits_out) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     PolSmem& S = *reinterpret_cast<PolSmem*>(smem_raw);
@@ -102,10 +104,12 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = S.tmem_base;
     const uint32_t w1_addr = smem_u32(S.W1), wa_addr = smem_u32(S.Wa);
-    // class A rows = row_list[0 .. nA), class B rows = row_list[B-1 .. nA] (from the back); without a list every row is B
-    const long long nA = row_list ? (long long)*n_class_a_dev : 0;
-    const long long tilesA = (nA + kTileM - 1) / kTileM, tilesB = (B - nA + kTileM - 1) / kTileM;
-    const long long n_tiles = tilesA + tilesB;
+    // class A1 rows (1..32 legal slots) = row_list[0 .. nA1), class B rows = row_list[B-1 .. ] (from the back), class A2 rows
+    // (33..128 legal slots) = row_list2[0 .. nA2); without lists every row is class B
+    const long long nA1 = row_list ? (long long)class_ctr[0] : 0, nA2 = row_list ? (long long)class_ctr[3] : 0;
+    const long long nB = B - nA1 - nA2;
+    const long long tilesA1 = (nA1 + kTileM - 1) / kTileM, tilesA2 = (nA2 + kTileM - 1) / kTileM, tilesB = (nB + kTileM - 1) / kTileM;
+    const long long n_tiles = tilesB + tilesA2 + tilesA1;
     const int q = warp & 3, cq = warp >> 2;                      // TMEM lane quadrant, column quarter
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
@@ -115,12 +119,17 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
     // tile order: the (few, 5-6 x more expensive) class B tiles first, then class A; with a tile counter the CTAs pull
     // tiles dynamically so that a CTA holding a heavy tile takes fewer light ones
     auto tile_row = [&](long long tile, int r) -> int {
-        const bool ca = tile >= tilesB;
-        const long long first = ca ? (tile - tilesB) * kTileM : tile * kTileM;
-        const long long n_class = ca ? nA : B - nA;
-        if (first + r >= n_class) return -1;
-        const long long pos = ca ? first + r : (row_list ? B - 1 - (first + r) : first + r);
-        return row_list ? row_list[pos] : (int)pos;
+        if (tile < tilesB) {
+            const long long i = tile * kTileM + r;
+            if (i >= nB) return -1;
+            return row_list ? row_list[B - 1 - i] : (int)i;
+        }
+        if (tile < tilesB + tilesA2) {
+            const long long i = (tile - tilesB) * kTileM + r;
+            return i < nA2 ? row_list2[i] : -1;
+        }
+        const long long i = (tile - tilesB - tilesA2) * kTileM + r;
+        return i < nA1 ? row_list[i] : -1;
     };
     const uint32_t boards_s[2] = {smem_u32(&S.boards[0][0]), smem_u32(&S.boards[1][0])};
     // gather the boards of the rows listed in S.rowidx[b] into S.boards[b] (asynchronously)
@@ -146,7 +155,8 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
     }
     for (int it = 0; tile < n_tiles; ++it) {
         const int bsel = it & 1;
-        const bool class_a = tile >= tilesB;
+        const bool class_a = tile >= tilesB;                      // one chunk of the policy GEMM
+        const bool narrow = tile >= tilesB + tilesA2;             // ... and at most 32 legal slots: 8 slots per column warp
         const int n_chunks = class_a ? 1 : 4;
         // ---- A: this tile's boards have been gathered during the previous tile; the next tile is chosen and its row list read now
         if (tile_ctr && tid == 0) S.tile_slot = atomicAdd(tile_ctr, 1u);
@@ -220,23 +230,17 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
         const long long gid = S.rowidx[bsel][row];                      // row index within this call (-1: none)
         const int n_legal = (gid >= 0 && legal_counts) ? legal_counts[gid] : (legal_counts ? 1 : kActions);
         const unsigned long long sid = stream_base + (unsigned long long)(gid >= 0 ? gid : 0);   // global stream id (game id)
-        // class A: this warp's 32 slots of chunk 0 matter only if some row of the warp has more than 32 cq legal slots
-        const bool warp_active = !class_a || __any_sync(kFull, n_legal > 32 * cq);
+        // class A: this warp's slots of chunk 0 (32 of them, or 8 in a narrow tile) matter only if some row of the warp has that many
+        const bool warp_active = !class_a || __any_sync(kFull, n_legal > (narrow ? 8 : 32) * cq);
         float m = -INFINITY, s = 0.0f, gbest = -INFINITY, lbest = 0.0f;
         int ibest = 0;
-#pragma unroll 1
-        for (int c = 0; c < n_chunks; ++c) {
-            mbar_wait(&S.bar2[c & 1], ph2[c & 1]); ph2[c & 1] ^= 1u;
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            if (warp_active) {
-            uint32_t acc[32];
-            tmem_ld32(lane_base + (uint32_t)(kColAcc2 + 128 * (c & 1) + 32 * cq), acc);
-            tmem_ld_wait();
-            const int base = 128 * c + 32 * cq;                    // action slot of acc[0]
-            float x[32];
+        // W accumulator columns acc[0..W) = action slots base .. base + W - 1 of this thread's row
+        auto reduce_block = [&](const uint32_t* acc, int base, auto wtag) {
+            constexpr int W = decltype(wtag)::value;
+            float x[W];
             float cm = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < W; ++j) {
                 const int i = base + j;
                 float l = __uint_as_float(acc[j]) + S.ba[i];
                 if (logits_out && gid >= 0 && i < kActions) logits_out[gid * kActions + i] = l;
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
                 const float mn = fmaxf(m, cm);
                 float add = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) add += __expf(x[j] - mn);
+                for (int j = 0; j < W; ++j) add += __expf(x[j] - mn);
                 s = s * __expf(m - mn) + add;
                 m = mn;
             }
@@ -257,12 +261,12 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
             // every slot is masked (a pass: the reference samples from all 500 then), so its noise is skipped otherwise
             if (greedy) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
+                for (int j = 0; j < W; ++j)
                     if (x[j] > gbest) { gbest = x[j]; ibest = base + j; lbest = x[j]; }
             } else {
                 const int lim = n_legal > 0 ? min(n_legal, kActions) : kActions;
 #pragma unroll
-                for (int g4 = 0; g4 < 8; ++g4) {
+                for (int g4 = 0; g4 < W / 4; ++g4) {
                     if (base + 4 * g4 < lim) {
                         uint32_t r[4];
                         philox4x32_10((uint32_t)sid, ((uint32_t)(sid >> 32) << 8) | (uint32_t)((base >> 2) + g4), step, kTagGumbel,
@@ -277,7 +281,24 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
                     }
                 }
             }
-            }   // warp_active
+        };
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; ++c) {
+            mbar_wait(&S.bar2[c & 1], ph2[c & 1]); ph2[c & 1] ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (warp_active) {
+                if (narrow) {                                      // slots 8 cq .. 8 cq + 7: the 32 slots of a narrow tile spread over all four column warps
+                    uint32_t acc[8];
+                    tmem_ld8(lane_base + (uint32_t)(kColAcc2 + 8 * cq), acc);
+                    tmem_ld_wait();
+                    reduce_block(acc, 8 * cq, std::integral_constant<int, 8>{});
+                } else {
+                    uint32_t acc[32];
+                    tmem_ld32(lane_base + (uint32_t)(kColAcc2 + 128 * (c & 1) + 32 * cq), acc);
+                    tmem_ld_wait();
+                    reduce_block(acc, 128 * c + 32 * cq, std::integral_constant<int, 32>{});
+                }
+            }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             __syncthreads();                                       // every warp has read acc2[c & 1]
             if (tid == 0 && c + 2 < n_chunks) issue_chunk(c + 2);
@@ -312,20 +333,27 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(512u) : "memory");
 }
 
-// Row lists of the two classes in ONE array: rows with 1..128 legal slots from the front, the others from the back.
-// Order inside a class is arbitrary (atomics); results do not depend on it (the random stream is keyed by the row).
+// Row lists of the three classes: rows with 1..32 legal slots from the front of row_list, rows with none or more than 128
+// from its back, rows with 33..128 from the front of row_list2.  Order inside a class is arbitrary (atomics); results do not
+// depend on it (the random stream is keyed by the row).  ctr: [0] class A1 rows, [1] class B rows, [3] class A2 rows.
 __global__ void __launch_bounds__(256) policy_partition_kernel(const int32_t* __restrict__ counts, long long B,
-                                                               int32_t* __restrict__ row_list, unsigned int* __restrict__ ctr /*[2]*/) {
+                                                               int32_t* __restrict__ row_list, int32_t* __restrict__ row_list2,
+                                                               unsigned int* __restrict__ ctr) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int n = g < B ? counts[g] : -1;
-    const bool a = g < B && n >= 1 && n <= 128, b = g < B && !a;
-    const unsigned ma = __ballot_sync(kFull, a), mb = __ballot_sync(kFull, b);
-    unsigned int base_a = 0, base_b = 0;
-    if (lane == 0) { if (ma) base_a = atomicAdd(&ctr[0], (unsigned)__popc(ma)); if (mb) base_b = atomicAdd(&ctr[1], (unsigned)__popc(mb)); }
-    base_a = __shfl_sync(kFull, base_a, 0); base_b = __shfl_sync(kFull, base_b, 0);
+    const bool a1 = g < B && n >= 1 && n <= 32, a2 = g < B && n > 32 && n <= 128, b = g < B && !a1 && !a2;
+    const unsigned m1 = __ballot_sync(kFull, a1), m2 = __ballot_sync(kFull, a2), mb = __ballot_sync(kFull, b);
+    unsigned int base1 = 0, base2 = 0, base_b = 0;
+    if (lane == 0) {
+        if (m1) base1 = atomicAdd(&ctr[0], (unsigned)__popc(m1));
+        if (m2) base2 = atomicAdd(&ctr[3], (unsigned)__popc(m2));
+        if (mb) base_b = atomicAdd(&ctr[1], (unsigned)__popc(mb));
+    }
+    base1 = __shfl_sync(kFull, base1, 0); base2 = __shfl_sync(kFull, base2, 0); base_b = __shfl_sync(kFull, base_b, 0);
     const unsigned below = (1u << lane) - 1u;
-    if (a) row_list[base_a + __popc(ma & below)] = (int32_t)g;
+    if (a1) row_list[base1 + __popc(m1 & below)] = (int32_t)g;
+    if (a2) row_list2[base2 + __popc(m2 & below)] = (int32_t)g;
     if (b) row_list[B - 1 - (long long)(base_b + __popc(mb & below))] = (int32_t)g;
 }
 
@@ -347,7 +375,7 @@ extern "C" int bg_pack_wa(const float* action_head_weight, uint16_t* wa_bf16, vo
     return bg_set_error(cudaGetLastError(), "bg_pack_wa: launch");
 }
 
-extern "C" size_t bg_policy_workspace_bytes(long long B) { return 16 + sizeof(int32_t) * (size_t)(B > 0 ? B : 1); }
+extern "C" size_t bg_policy_workspace_bytes(long long B) { return 16 + 2 * sizeof(int32_t) * (size_t)(B > 0 ? B : 1); }
 
 extern "C" int bg_policy_sample(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
                                 const int32_t* legal_counts, const uint16_t* w1_bf16, const float* b1,
@@ -366,25 +394,26 @@ extern "C" int bg_policy_sample(const int8_t* boards52, const int8_t* flags, int
     // with a workspace: dynamic tile schedule, and -- when there is a mask and the logits are not wanted -- the two row
     // classes (1..128 legal slots / the rest)
     const int32_t* row_list = nullptr;
-    const unsigned int* n_a = nullptr;
+    const int32_t* row_list2 = nullptr;
+    const unsigned int* class_ctr = nullptr;
     unsigned int* tile_ctr = nullptr;
     if (workspace) {
         if (workspace_bytes < bg_policy_workspace_bytes(B)) return bg_set_error_msg(BG_ERR_INVALID, "bg_policy_sample: workspace too small");
-        unsigned int* ctr = static_cast<unsigned int*>(workspace);      // [0] class A rows, [1] class B rows, [2] next tile
+        unsigned int* ctr = static_cast<unsigned int*>(workspace);      // [0] class A1 rows, [1] class B rows, [2] next tile, [3] class A2 rows
         e = cudaMemsetAsync(ctr, 0, 16, (cudaStream_t)stream);
         if (e != cudaSuccess) return bg_set_error(e, "bg_policy_sample: memset");
         tile_ctr = ctr + 2;
         if (legal_counts && !logits_out) {
             int32_t* list = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(workspace) + 16);
-            policy_partition_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(legal_counts, B, list, ctr);
-            row_list = list; n_a = ctr;
+            policy_partition_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(legal_counts, B, list, list + B, ctr);
+            row_list = list; row_list2 = list + B; class_ctr = ctr;
         }
     }
-    long long tiles = (B + kTileM - 1) / kTileM + 1;
+    long long tiles = (B + kTileM - 1) / kTileM + 2;
     long long grid = bg_sm_count();
     if (grid > tiles) grid = tiles;
     policy_kernel<<<(unsigned)grid, kPolThreads, smem, (cudaStream_t)stream>>>(
         boards52, flags, flag_all & 1, B, legal_counts, w1_bf16, b1, wa_bf16, ba, wv, bv, seed, stream_base, step, greedy,
-        row_list, n_a, tile_ctr, actions, log_probs, values, logits_out);
+        row_list, row_list2, class_ctr, tile_ctr, actions, log_probs, values, logits_out);
     return bg_set_error(cudaGetLastError(), "bg_policy_sample: launch");
 }
