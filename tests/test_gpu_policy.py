@@ -102,3 +102,28 @@ def test_policy_sampling_distribution_and_reproducibility():
         chi2 = float(((emp[keep] - exp[keep]) ** 2 / exp[keep]).sum())
         dof = int(keep.sum()) - 1
         assert chi2 < dof + 6 * (2 * dof) ** 0.5 + 10, (r, chi2, dof)
+
+
+def test_policy_class_paths_logp_and_values():
+    """The row-class paths (no logits requested: A1 = 1..32 legal slots on 8-slot column warps, A2 = 33..128, B = passes / more):
+    the log-prob returned for the sampled action and the value must equal the reference's masked log-softmax / value head for
+    every row, the sampled slot must be legal, and greedy must pick the reference's argmax."""
+    import bg_b200
+    env = _positions(3000, seed=4)
+    net = bg_b200.PolicyValueNet.random_init("cuda:0", seed=6)
+    net.params["action_head.weight"].mul_(6.0); net.sync()
+    n = env.legal_counts.long()
+    assert int(((n >= 1) & (n <= 32)).sum()) > 0 and int(((n > 32) & (n <= 128)).sum()) > 0 and int((n == 0).sum()) > 0
+    ref_logits, ref_lsm, ref_v, masked = _reference(net, env, bf16_operands=True)
+    for step in (0, 1):
+        a, lp, v = net.act(env.boards52, env.players, env.legal_counts, seed=21, step=step)
+        al = a.long()
+        ok = torch.where(n > 0, al < n, al < 500) & (al >= 0)
+        assert bool(ok.all()), "sampled an illegal slot"
+        assert (lp - ref_lsm.gather(1, al[:, None])[:, 0]).abs().max().item() < 1e-2
+        assert (v - ref_v).abs().max().item() < 1e-3
+    g, glp, _ = net.act(env.boards52, env.players, env.legal_counts, greedy=True)
+    best = masked.max(-1).values
+    picked = masked.gather(1, g.long()[:, None])[:, 0]
+    assert (best - picked).abs().max().item() < 1e-2                # (ties / bf16 boundary cases: the value, not the index)
+    assert (glp - ref_lsm.gather(1, g.long()[:, None])[:, 0]).abs().max().item() < 1e-2
