@@ -165,17 +165,16 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_kernel(
         const long long next_tile = tile_ctr ? (long long)S.tile_slot : tile + gridDim.x;
         int next_g = -1;
         if (tid < kTileM && next_tile < n_tiles) next_g = tile_row(next_tile, tid);
-        // ---- B: feature rows -> TMEM (two threads per position; warps 0-3 chunks 0-12, warps 4-7 chunks 13-25)
-        if (warp < 8) {
-            const int prow = tid & (kTileM - 1), half = tid >> 7;
-            uint32_t w[kBoardWords];
-#pragma unroll
-            for (int i = 0; i < kBoardWords; ++i) w[i] = S.boards[bsel][prow * kBoardWords + i];
-            const int pg = S.rowidx[bsel][prow];
-            const int fl = pg >= 0 ? (int)((flags ? flags[pg] : flag_all) & 1) : 0;
+        // ---- B: feature rows -> TMEM (four threads per position: column-warp cq builds chunks 7 cq .. 7 cq + 6 of its rows)
+        {
+            const uint32_t* srow = &S.boards[bsel][row * kBoardWords];
+            int fl = 0;
+            if (cq == 3) { const int pg = S.rowidx[bsel][row]; fl = pg >= 0 ? (int)((flags ? flags[pg] : flag_all) & 1) : 0; }   // chunk 24 holds the turn flags
             const uint32_t trow = lane_base + (uint32_t)kColA;
-            if (half == 0) build_half_row<0>(w, fl, &S.flut, trow);
-            else           build_half_row<1>(w, fl, &S.flut, trow);
+            if (cq == 0)      build_row_chunks<0, 7>(srow, fl, &S.flut, trow);
+            else if (cq == 1) build_row_chunks<7, 14>(srow, fl, &S.flut, trow);
+            else if (cq == 2) build_row_chunks<14, 21>(srow, fl, &S.flut, trow);
+            else              build_row_chunks<21, 26>(srow, fl, &S.flut, trow);
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
         }
         if (tid < kTileM) S.rowidx[bsel ^ 1][tid] = next_g;
