@@ -9,6 +9,7 @@
 // HBM-bound: 52 B read, 792 B (f32) or 2*ld B (bf16) written per row.  A CTA stages ROWS boards in
 // shared memory with coalesced loads, then every thread produces 16-byte (bf16) / 8-byte (f32) output
 // vectors so that a warp's stores cover contiguous 512 / 256 bytes.
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include "bg_device.cuh"
 #include "bg_features.cuh"
@@ -110,6 +111,106 @@ __global__ void __launch_bounds__(kBfThreads, 3) encode_bf16_kernel(const int8_t
     }
 }
 
+// bf16 rows, version 5 (ld = 208 only): whole feature tiles built POINT BY POINT in shared memory and handed to the copy
+// engine.  The chunk-per-thread kernel above spends ~38 instructions on a 16-byte chunk (four generic count -> units lookups
+// with the special words folded in) -- 76 M warp-instructions per 1.2 M rows, which, not HBM, is what bounds it (a memset
+// of the same bytes runs at 7.2 TB/s).  Here a builder thread owns one of the 48 points (its board byte and its two
+// destination words are thread constants), a unit of work is one byte load, one 8-byte table load and the store of the
+// point's two words into the tile (~6 instructions per 8 bytes); warp 6 writes the rows' special words (bar/off pairs, turn
+// flags, zero padding); the finished 13.3 KB tile (32 rows) leaves with ONE cp.async.bulk shared -> global.  Boards of the next
+// tile are prefetched with cp.async, tiles are double buffered, six CTAs per SM (measured: 64 rows x 3 CTAs 102.8 us, 32 x 6
+// 97.7, 32 x 7 102.8, 16 x 9 113.8 per 1.2 M rows).
+constexpr int kV5Rows = 32;
+constexpr int kV5Words = 104;                 // 208 bf16 = 104 words per row
+constexpr int kV5Builders = 192;              // 4 rows x 48 points per pass
+constexpr int kV5Threads = 224;               // + warp 6: special words
+struct V5Smem {
+    uint32_t tile[2][kV5Rows * kV5Words];     // 2 x 13,312 B
+    uint32_t boards[2][kV5Rows * kBoardWords];
+    uint2 units[16];
+    uint16_t half[16], off15[16];
+};
+
+__global__ void __launch_bounds__(kV5Threads, 6) encode_bf16_v5_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ flags,
+                                                                      int flag_all, long long B,
+                                                                      const unsigned long long* __restrict__ row_begin_dev,
+                                                                      const unsigned long long* __restrict__ n_rows_dev,
+                                                                      uint16_t* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char v5_raw[];
+    V5Smem& S = *reinterpret_cast<V5Smem*>(v5_raw);
+    const int t = threadIdx.x;
+    if (t < 16) { S.units[t] = kUnitsBf16[t]; S.half[t] = kHalfBf16[t]; S.off15[t] = kOff15Bf16[t]; }
+    if (n_rows_dev) B = min(B, (long long)*n_rows_dev);
+    const long long begin = row_begin_dev ? (long long)*row_begin_dev : 0;
+    const long long stride = (long long)gridDim.x * kV5Rows;
+    const int tr = t / 48, tp = t - tr * 48;                         // builder: rows tr, tr + 4, ...; point tp (board byte tp)
+    const int dw = tp < 24 ? 2 * tp : 2 * tp + 1;                    // first destination word: P1 points at 0.., P2 points at 49..
+    const int sr = t - kV5Builders;                                  // warp 6: rows sr and sr + 32
+    auto prefetch = [&](long long row0, int b, int (&fl)[2]) {
+        if (row0 < B) {
+            const int rows = (int)min((long long)kV5Rows, B - row0);
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + row0 * kBoardBytes);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.boards[b][0]);
+            for (int i = t; i < rows * kBoardWords; i += kV5Threads)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(dst + 4u * (uint32_t)i), "l"(src + i) : "memory");
+            if (sr >= 0) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = sr + 32 * h;
+                    fl[h] = (r < rows && flags) ? (__ldg(flags + row0 + r) & 1) : flag_all;
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    int fl_cur[2] = {0, 0}, fl_next[2] = {0, 0};
+    long long row0 = begin + (long long)blockIdx.x * kV5Rows;
+    prefetch(row0, 0, fl_cur);
+    for (int it = 0; row0 < B; row0 += stride, ++it) {
+        const int rows = (int)min((long long)kV5Rows, B - row0);
+        const int b = it & 1;
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");              // this thread's share of the tile's boards has landed
+        if (t == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");   // tile[b]'s previous store has left shared memory
+        __syncthreads();                                                      // ... everybody's boards; the previous tile is fully built
+        prefetch(row0 + stride, b ^ 1, fl_next);
+        uint32_t* tl = S.tile[b];
+        const uint8_t* sb = reinterpret_cast<const uint8_t*>(S.boards[b]);
+        if (t < kV5Builders) {
+#pragma unroll 4
+            for (int r = tr; r < rows; r += 4) {
+                const uint2 u = S.units[sb[r * kBoardBytes + tp] & 15u];
+                tl[r * kV5Words + dw] = u.x;
+                tl[r * kV5Words + dw + 1] = u.y;
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = sr + 32 * h;
+                if (r < rows) {
+                    const uint32_t misc = S.boards[b][r * kBoardWords + 12];    // bar1, bar2, off1, off2
+                    uint32_t* w = tl + r * kV5Words;
+                    w[48] = (uint32_t)S.half[misc & 15u] | ((uint32_t)S.off15[(misc >> 16) & 15u] << 16);
+                    w[97] = (uint32_t)S.half[(misc >> 8) & 15u] | ((uint32_t)S.off15[(misc >> 24) & 15u] << 16);
+                    w[98] = fl_cur[h] == 0 ? 0x00003F80u : 0x3F800000u;
+                    w[99] = 0u; w[100] = 0u; w[101] = 0u; w[102] = 0u; w[103] = 0u;
+                }
+            }
+            fl_cur[0] = fl_next[0]; fl_cur[1] = fl_next[1];
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic-proxy writes -> visible to the copy engine
+        __syncthreads();
+        if (t == 0) {
+            const uint32_t s_addr = (uint32_t)__cvta_generic_to_shared(tl);
+            uint16_t* g_addr = out + row0 * (long long)(2 * kV5Words);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                         :: "l"(g_addr), "r"(s_addr), "r"((uint32_t)(rows * kV5Words * 4)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    if (t == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // shared memory must outlive the copies
+}
+
 // f32 rows (the reference's own layout).  Thread t owns the float2 pair column j = t % 99 (features 2j, 2j+1) for rows
 // t / 99, +4, ... of the tile: the column is decoded once (board byte + which half of its four units, or one of the three
 // special pairs), a pair is then one byte load + one 8-byte table load and an 8-byte store; consecutive threads write
@@ -188,6 +289,16 @@ int bg::encode_bf16_launch(const int8_t* boards52, const int8_t* flags, int flag
     if (B < 0 || ld < 200 || (ld & 7) || ld > 3328) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: bad B or ld (need ld >= 200, multiple of 8)");
     if (B == 0) return BG_OK;
     if (!boards52 || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_encode_bf16: null pointer");
+    static const int v5_env = getenv("BG_ENCODE_V5") ? atoi(getenv("BG_ENCODE_V5")) : 1;   // 0: the chunk-per-thread kernel for every ld
+    if (v5_env && ld == BG_FEAT_LD_BF16 && !(reinterpret_cast<uintptr_t>(out) & 15u)) {
+        const size_t smem = sizeof(V5Smem);
+        cudaError_t e = cudaFuncSetAttribute(encode_bf16_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return bg_set_error(e, "bg_encode_bf16: cudaFuncSetAttribute");
+        long long tiles = (B + kV5Rows - 1) / kV5Rows, grid = (long long)bg_sm_count() * 6;
+        if (grid > tiles) grid = tiles;
+        encode_bf16_v5_kernel<<<(unsigned)grid, kV5Threads, smem, stream>>>(boards52, flags, flag_all & 1, B, row_begin_dev, n_rows_dev, out);
+        return bg_set_error(cudaGetLastError(), "bg_encode_bf16: launch");
+    }
     const int cpr = (int)(ld / 8);
     long long tiles = (B + kBfRows - 1) / kBfRows;
     long long grid = (long long)bg_sm_count() * 3;
