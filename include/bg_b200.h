@@ -219,7 +219,7 @@ int bg_gae(const float* rewards, const uint8_t* dones, const float* values /*nul
 
 /* N2  loss of one PPO epoch (agent/ppo_agent.py:271-299: log(mask + 1e-45), softmax, log_prob, entropy, ratio, clipped
  * surrogate, MSE, their weighted sum) and its gradient w.r.t. the network outputs, one pass over the logits:
- *   logits / dlogits: [B][ld] bf16 (logits_bf16 = 1) or f32, ld >= 500 and a multiple of 4; values, returns, advantages,
+ *   logits / dlogits: [B][ld] bf16 (flags & BG_LOSS_LOGITS_BF16) or f32, ld >= 500 and a multiple of 4; values, returns, advantages,
  *   old_log_probs: [B] f32; counts: legal slots per sample (prefix mask); actions: taken slot.
  *   dlogits = d loss / d logits (columns 500 .. ld-1 are written as zeros), dvalues = d loss / d values (both already
  *   divided by B); dbias[0..min(ld,512)-1] += column sums of dlogits = d loss / d action_head.bias (nullable; caller zeroes).
@@ -228,7 +228,11 @@ int bg_gae(const float* rewards, const uint8_t* dones, const float* values /*nul
  *   sum to dbias[500], so the value head's backward rides through the action head's backward GEMMs.
  *   sums[0..2] += sum_i policy term, sum_i (v - R)^2, sum_i entropy  (caller zeroes; loss = (s0 + c_v s1 - c_e s2) / B).
  *   Two launches on `stream`: rows with 1..128 legal slots and the action inside the prefix, four per warp; then the rest. */
-int bg_ppo_loss_grad(const void* logits, int logits_bf16, long long ld, const float* values, const int32_t* counts,
+#define BG_LOSS_LOGITS_BF16 1          /* logits / dlogits are bf16 (else f32) */
+#define BG_LOSS_DLOGITS_PREZEROED 2    /* dlogits already holds zeros wherever this call would write zeros for a row with 1..128 legal slots
+                                         (columns 128 .. ld-1 except the value column): they are not written again.  For a buffer that is
+                                         reused with the SAME rows (the epochs of one update), zeroed once. */
+int bg_ppo_loss_grad(const void* logits, int flags /* BG_LOSS_* */, long long ld, const float* values, const int32_t* counts,
                      const int32_t* actions, const float* old_log_probs, const float* advantages, const float* returns,
                      long long B, float eps_clip, float value_coef, float entropy_coef, void* dlogits, float* dvalues,
                      float* dbias /*nullable*/, float* sums, void* stream);

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
     const T* __restrict__ logits, long long ld, const float* __restrict__ values, const int32_t* __restrict__ counts,
     const int32_t* __restrict__ actions, const float* __restrict__ old_logp, const float* __restrict__ adv,
     const float* __restrict__ returns, long long B, float eps_clip, float value_coef, float entropy_coef,
-    T* __restrict__ dlogits, float* __restrict__ dvalues, float* __restrict__ dbias, float* __restrict__ sums) {
+    T* __restrict__ dlogits, float* __restrict__ dvalues, float* __restrict__ dbias, float* __restrict__ sums, int prezeroed) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
     __shared__ float s_part[kLossWarps][3];
     __shared__ float s_col[kLossWarps][129];                         // 128 slot columns + the value column
@@ -226,10 +226,19 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
                 Vec4<T>::store(dst + 16 * sub + 4 * k, x);
             }
             // quads 1..3 and the padding of the GEMM's N: exact zeros; column 500 carries d loss / d value when the value rides there
-            for (int c = 128 + 4 * sub; c < ld; c += 32) {
+            // (prezeroed: the caller guarantees zeros there already -- only the value column is written)
+            if (!prezeroed) {
+                for (int c = 128 + 4 * sub; c < ld; c += 32) {
+                    float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    if (!values && c == BG_ACTIONS) { x[0] = dvalue; vsum += dvalue; }
+                    Vec4<T>::store(dst + c, x);
+                }
+            } else if (!values && sub >= 4) {
+                // the value column's whole 32-byte sector (columns 496 .. 511: a lone 8-byte store would cost a read-modify-write)
+                const int c = BG_ACTIONS - 4 + 4 * (sub - 4);
                 float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                if (!values && c == BG_ACTIONS) { x[0] = dvalue; vsum += dvalue; }
-                Vec4<T>::store(dst + c, x);
+                if (sub == 5) { x[0] = dvalue; vsum += dvalue; }
+                if (c < ld) Vec4<T>::store(dst + c, x);
             }
             if (sub == 0) {
                 if (dvalues) dvalues[row] = dvalue;
@@ -428,7 +437,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_kernel(
 
 }  // namespace bg
 
-extern "C" int bg_ppo_loss_grad(const void* logits, int logits_bf16, long long ld, const float* values, const int32_t* counts,
+extern "C" int bg_ppo_loss_grad(const void* logits, int flags, long long ld, const float* values, const int32_t* counts,
                                 const int32_t* actions, const float* old_log_probs, const float* advantages,
                                 const float* returns, long long B, float eps_clip, float value_coef, float entropy_coef,
                                 void* dlogits, float* dvalues, float* dbias, float* sums, void* stream) {
@@ -439,6 +448,7 @@ extern "C" int bg_ppo_loss_grad(const void* logits, int logits_bf16, long long l
     if (!values && ld <= BG_ACTIONS) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_loss_grad: values == NULL needs the value in column 500 (ld >= 504)");
     // two launches: the packed kernel for the common rows (four per warp), the general kernel for the others (BG_LOSS_GENERAL_ONLY=1:
     // every row through the general kernel -- for tests / comparison)
+    const int logits_bf16 = flags & BG_LOSS_LOGITS_BF16, prezeroed = (flags & BG_LOSS_DLOGITS_PREZEROED) ? 1 : 0;
     static const int general_only = getenv("BG_LOSS_GENERAL_ONLY") ? atoi(getenv("BG_LOSS_GENERAL_ONLY")) : 0;
     const long long resident = (long long)bg_sm_count() * 2;                   // ~125 registers x 256 threads: two CTAs per SM
     const long long need_p = (B + 4 * bg::kLossWarps - 1) / (4 * bg::kLossWarps), need_g = (B + 32 * bg::kLossWarps - 1) / (32 * bg::kLossWarps);
@@ -448,7 +458,7 @@ extern "C" int bg_ppo_loss_grad(const void* logits, int logits_bf16, long long l
         if (!general_only)
             bg::ppo_loss_grad_packed_kernel<__nv_bfloat16><<<grid_p, bg::kLossWarps * 32, 0, st>>>(
                 (const __nv_bfloat16*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
-                entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums);
+                entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums, prezeroed);
         bg::ppo_loss_grad_kernel<__nv_bfloat16><<<grid_g, bg::kLossWarps * 32, 0, st>>>(
             (const __nv_bfloat16*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
             entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums, general_only);
@@ -456,7 +466,7 @@ extern "C" int bg_ppo_loss_grad(const void* logits, int logits_bf16, long long l
         if (!general_only)
             bg::ppo_loss_grad_packed_kernel<float><<<grid_p, bg::kLossWarps * 32, 0, st>>>(
                 (const float*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
-                entropy_coef, (float*)dlogits, dvalues, dbias, sums);
+                entropy_coef, (float*)dlogits, dvalues, dbias, sums, prezeroed);
         bg::ppo_loss_grad_kernel<float><<<grid_g, bg::kLossWarps * 32, 0, st>>>(
             (const float*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
             entropy_coef, (float*)dlogits, dvalues, dbias, sums, general_only);

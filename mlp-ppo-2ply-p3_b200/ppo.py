@@ -158,12 +158,18 @@ class ManualUpdate:
         self.dbias, self.sums = z((self.LD,), torch.float32), z((3,), torch.float32)
         self.B = -1
         self.f32_out = None                      # torch.mm(..., out_dtype=f32) available?
+        self._zero_key = None                    # rows the zero part of self.dlogits is valid for
 
     def _buffers(self, B):
         if B != self.B:
             e = lambda shape: torch.empty(shape, dtype=torch.bfloat16, device=self.device)
             self.h, self.logits, self.dlogits, self.dh = e((B, 128)), e((B, self.LD)), e((B, self.LD)), e((B, 128))
             self.B = B
+            self._zero_key = None
+
+    def invalidate(self):
+        """New rollout data: the zeros kept in dlogits belong to the previous rows."""
+        self._zero_key = None
 
     def _mm_f32(self, a, b):
         """a @ b for bf16 operands with the f32 accumulator returned as is (torch.mm(..., out_dtype=float32), torch >= 2.8);
@@ -191,8 +197,14 @@ class ManualUpdate:
         self.h.relu_()
         torch.addmm(bap, self.h, wap.t(), out=self.logits)
         self.dbias.zero_(); self.sums.zero_()
+        # dlogits is mostly zeros (a row with n <= 128 legal slots has 128 live columns + the value column): they are written
+        # once per set of rows (a fill at 7 TB/s) and left alone in the following epochs (BG_LOSS_DLOGITS_PREZEROED)
+        key = (counts.data_ptr(), B)
+        if key != self._zero_key:
+            self.dlogits.view(torch.int32).zero_()
+            self._zero_key = key
         with torch.cuda.device(self.device):
-            check(lib().bg_ppo_loss_grad(self.logits.data_ptr(), 1, self.LD, None, counts.data_ptr(), actions.data_ptr(),
+            check(lib().bg_ppo_loss_grad(self.logits.data_ptr(), 1 | 2, self.LD, None, counts.data_ptr(), actions.data_ptr(),
                                          old_logp.data_ptr(), adv.data_ptr(), returns.data_ptr(), B, float(eps_clip),
                                          float(value_coef), float(entropy_coef), self.dlogits.data_ptr(), None,
                                          self.dbias.data_ptr(), self.sums.data_ptr(), _stream()), "bg_ppo_loss_grad")
@@ -292,6 +304,7 @@ class PPOLearner:
         if manual:
             if self._manual is None:
                 self._manual = ManualUpdate(self.device)
+            self._manual.invalidate()
             x[:, ManualUpdate.ONE_COL] = 1.0                  # spare (zero) column of K3's rows: carries fc1.bias through the GEMMs
             counts, actions = counts.to(torch.int32).contiguous(), actions.to(torch.int32).contiguous()
             old_logp, returns, adv = old_logp.float().contiguous(), returns.float().contiguous(), adv.float().contiguous()

@@ -226,3 +226,12 @@ def test_loss_kernel_edge_rows(ld, bf16):
             else:
                 assert float(pad.abs().max()) == 0.0
         assert (dbias[:500].double() - dl_want.sum(0)).abs().max().item() < (2e-5 if not bf16 else 2e-5) * B * scale
+        # BG_LOSS_DLOGITS_PREZEROED: the same numbers into a buffer the caller has zeroed
+        dl2 = torch.zeros((B, ld), device=dev, dtype=dt)
+        dv2, db2, s2 = torch.zeros(B, device=dev), torch.zeros(512, device=dev), torch.zeros(3, device=dev)
+        check(lib().bg_ppo_loss_grad(logits.data_ptr(), int(bf16) | 2, ld, None if value_in_col else values.data_ptr(), counts.data_ptr(),
+                                     actions.data_ptr(), old.data_ptr(), adv.data_ptr(), ret.data_ptr(), B, eps, vc, ec,
+                                     dl2.data_ptr(), dv2.data_ptr(), db2.data_ptr(), s2.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream), "bg_ppo_loss_grad")
+        assert torch.equal(dl2, dlogits) and torch.equal(dv2, dvalues)
+        assert (db2 - dbias).abs().max().item() <= 1e-6 * (1 + dbias.abs().max().item()) and (s2 - sums).abs().max().item() <= 1e-3
