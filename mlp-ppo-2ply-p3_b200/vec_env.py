@@ -113,6 +113,7 @@ class B200BackgammonVecEnv:
         self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=device)
         self._ext_dice = None
         self._side = None
+        self._st_cache = None
         self._next_out = None
         self._steps = 0
         # reference attributes (vec_bg_env.py:16-18); gym is not a dependency, so plain descriptors
@@ -127,6 +128,13 @@ class B200BackgammonVecEnv:
                         self.after52.data_ptr(), self.legal_starts.data_ptr(), self.legal_counts.data_ptr(),
                         self.seed, self.stream_base, e.data_ptr() if e is not None else None,
                         e.shape[1] if e is not None else 0, self.match_length)
+
+    def _state_cached(self) -> EnvState:
+        """The state struct of _state(), built once: every pointer in it is a persistent buffer (set_dice_stream, the only
+        thing that swaps one, drops the cache)."""
+        if self._st_cache is None:
+            self._st_cache = self._state()
+        return self._st_cache
 
     def _refresh_legal_moves(self, with_features: bool = False):
         """update_legal_moves (backgammon_env.py:198-243) for every game: K1 in slab mode.  with_features also
@@ -239,11 +247,14 @@ class B200BackgammonVecEnv:
             # attributes alias them until the next step
             out = self._next_out if self._next_out is not None and self._next_out[0] == return_obs else self._alloc_outputs(return_obs)
             _, self.rewards, dones, info, obs = out
-            self.dones_u8 = dones.view(torch.uint8)
-            self.info_player, self.winner, self.game_score, self.flags = info[0], info[1], info[2], info[3].view(torch.uint8)
             if return_obs:
                 self.obs_f32 = obs
-            self._apply_actions(actions)
+            # K2 first, from raw pointers (info is (4,N) int8: player, winner, game score, flags) and the cached state struct;
+            # the python views of the outputs are made after the launches, off the host's critical path
+            ip = info.data_ptr()
+            so = StepOut(self.rewards.data_ptr(), dones.data_ptr(), ip, ip + N, ip + 2 * N, ip + 3 * N)
+            check(lib().bg_env_step(C.byref(self._state_cached()), actions.data_ptr(), C.byref(so), self.status.data_ptr(), _stream()),
+                  "bg_env_step")
             if host is not None:                                                # rewards / dones are final after K2
                 host.stepped.record()
             obs_beside_k1 = host is not None and return_obs and not overlap
@@ -270,6 +281,8 @@ class B200BackgammonVecEnv:
                     host.legal_counts.copy_(self.legal_counts, non_blocking=True)
                     host.ready.record(cs)
                 self.rewards.record_stream(cs); dones.record_stream(cs)
+            self.dones_u8 = dones.view(torch.uint8)
+            self.info_player, self.winner, self.game_score, self.flags = info[0], info[1], info[2], info[3].view(torch.uint8)
             self._next_out = self._alloc_outputs(return_obs)
         self._steps += 1
         if self.check_every and self._steps % self.check_every == 0:
@@ -407,6 +420,7 @@ class B200BackgammonVecEnv:
             if d.dim() != 3 or d.shape[0] != self.num_envs or d.shape[2] != 2:
                 raise BgError("set_dice_stream: need (N, L, 2)")
             self._ext_dice = d
+        self._st_cache = None
         self.draws.zero_()
 
     def set_dice(self, dice):
