@@ -22,6 +22,16 @@ from ._lib import BgError, EnvState, StepOut, check, lib
 from .engine import FEATURES, LD_BF16, from_board52, to_board52, _stream
 
 
+_CUDART = None
+
+
+def _cudart():
+    global _CUDART
+    if _CUDART is None:
+        _CUDART = C.CDLL("libcudart.so")
+    return _CUDART
+
+
 class StepInfos:
     """Lazy list-of-dicts view of the per-game info tensors (reference: list of dicts, vec_bg_env.py:40).
 
@@ -114,6 +124,7 @@ class B200BackgammonVecEnv:
         self._ext_dice = None
         self._side = None
         self._st_cache = None
+        self._act_dev = None
         self._next_out = None
         self._steps = 0
         # reference attributes (vec_bg_env.py:16-18); gym is not a dependency, so plain descriptors
@@ -232,11 +243,23 @@ class B200BackgammonVecEnv:
         if host is not None and not actions.is_cuda:
             # host actions go up on the copy stream, i.e. beside the encoders of the previous step that are still running on
             # the main stream, not behind them
-            with torch.cuda.stream(host.stream):
-                actions = actions.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
+            if actions.dtype == torch.int32 and actions.is_pinned() and actions.is_contiguous():
+                # pinned int32 actions: one cudaMemcpyAsync into a persistent device buffer (no allocation, no stream context)
+                if self._act_dev is None:
+                    self._act_dev = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+                host.stream.wait_event(host.stepped)                           # K2 of the previous step has read the buffer
+                rc = _cudart().cudaMemcpyAsync(C.c_void_p(self._act_dev.data_ptr()), C.c_void_p(actions.data_ptr()),
+                                               C.c_size_t(4 * self.num_envs), 1, C.c_void_p(host.stream.cuda_stream))
+                if rc != 0:
+                    raise BgError(f"cudaMemcpyAsync(actions) failed: {rc}")
                 host.actions_up.record(host.stream)
+                actions = self._act_dev
+            else:
+                with torch.cuda.stream(host.stream):
+                    actions = actions.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
+                    host.actions_up.record(host.stream)
+                actions.record_stream(torch.cuda.current_stream(self.device))
             torch.cuda.current_stream(self.device).wait_event(host.actions_up)
-            actions.record_stream(torch.cuda.current_stream(self.device))
         else:
             actions = actions.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
         N, dev = self.num_envs, self.device
