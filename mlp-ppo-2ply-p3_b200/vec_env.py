@@ -125,6 +125,7 @@ class B200BackgammonVecEnv:
         self._side = None
         self._st_cache = None
         self._act_dev = None
+        self._pinned_ptr = -1
         self._next_out = None
         self._steps = 0
         # reference attributes (vec_bg_env.py:16-18); gym is not a dependency, so plain descriptors
@@ -243,7 +244,12 @@ class B200BackgammonVecEnv:
         if host is not None and not actions.is_cuda:
             # host actions go up on the copy stream, i.e. beside the encoders of the previous step that are still running on
             # the main stream, not behind them
-            if actions.dtype == torch.int32 and actions.is_pinned() and actions.is_contiguous():
+            # (is_pinned() asks the driver: remember the buffer that passed)
+            ptr = actions.data_ptr()
+            pinned = ptr == self._pinned_ptr
+            if not pinned and actions.dtype == torch.int32 and actions.is_contiguous() and actions.is_pinned():
+                self._pinned_ptr, pinned = ptr, True
+            if pinned and actions.dtype == torch.int32 and actions.is_contiguous():
                 # pinned int32 actions: one cudaMemcpyAsync into a persistent device buffer (no allocation, no stream context)
                 if self._act_dev is None:
                     self._act_dev = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
