@@ -93,7 +93,8 @@ int bg_movegen_slab(const int8_t* boards52, const int8_t* players, const int8_t*
 int bg_encode_f32(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
                   const unsigned long long* n_rows_dev /*nullable*/, float* out, long long ld /* even, >= 198 */,
                   void* stream);
-/* bf16 rows, ld >= 198 elements and a multiple of 8; columns 198..ld-1 are written as zeros. */
+/* bf16 rows, ld >= 200 elements and a multiple of 8; columns 198..ld-1 are written as zeros.  ld = 208 (13 tensor-core
+ * K-steps; `out` 16-byte aligned) takes the fast path: feature tiles built in shared memory, bulk asynchronous stores. */
 int bg_encode_bf16(const int8_t* boards52, const int8_t* flags, int flag_all, long long B,
                    const unsigned long long* n_rows_dev /*nullable*/, uint16_t* out, long long ld, void* stream);
 
