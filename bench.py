@@ -13,15 +13,19 @@ de-phasing turns).  One "step" = one turn of every game:
 i.e. everything BackgammonEnv.step + update_legal_moves + get_observation do, minus the dense
 (500,198) zero padding.  Games shard across GPUs by game id with no collective ("scaling": "weak").
 
-Prints ONE JSON line (see the keys below).  `--impl reference` times the CPU port of the reference's
-path (oracle/, kind "port": the reference itself is Python and cannot travel to the GPU box) on all
-host cores for the same metric.
+Prints ONE JSON line.  The timed region is R x K steps (R chosen so that it lasts >= --min-seconds), bracketed once
+by barrier + synchronize; `ms_per_step` is its device time / (R K), max over ranks.
+`--impl reference` times the reference's path on the host cores: the C port (oracle/, kind "port") for `value`, and
+beside it the UNMODIFIED Python reference staged under baseline/_ref (kind "reference-python"), one BackgammonEnv per
+process on every core.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -35,14 +39,21 @@ SEED = 0x5EED
 ACT_SEED = 0xAC7
 METRIC = "env steps/sec w/ legal-move gen"
 UNIT = "env_steps/s"
+REF_STAGED = os.path.join(ROOT, "baseline", "_ref")
+
+# algorithmic bytes per unit; N = games, rows = legal plays of the step
+K1_BYTES_PER_GAME, K1_BYTES_PER_ROW = 71.0, 53.0      # board 52 + player 1 + dice 2 read, counts 4 + 4 + start 8 written; row 52 + mover 1
+K2_BYTES_PER_GAME = 120.0
+K3_OBS_BYTES_PER_GAME = 53.0 + 792.0                  # board + flag read, 198 f32 written
+K3_FEAT_BYTES_PER_ROW = 53.0 + 416.0                  # row + flag read, 208 bf16 written
 
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", d
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", {}
 
 
 class ClockSampler:
@@ -57,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -90,7 +101,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ----------------------------------------------------------------------------------------- CPU arm
+# ----------------------------------------------------------------------------------------- CPU arms
 
 def cpu_envs(threads: int):
     from oracle import bg_oracle as O
@@ -127,6 +138,96 @@ def cpu_rollout(seconds: float, threads: int, chunk: int = 2000, encode: bool = 
     return sum(done_steps), max(t_end) - start
 
 
+def reference_dir():
+    """The UNMODIFIED reference tree: the copy build() stages under baseline/_ref (git-ignored, travels to the GPU box
+    with the snapshot), else /root/reference when this runs in the build container."""
+    for d in (REF_STAGED, "/root/reference"):
+        if os.path.isdir(os.path.join(d, "src", "moves")):
+            return d
+    return None
+
+
+def _pyref_worker(ref, seconds, seed, barrier, q):
+    """One process = one BackgammonEnv of the reference (backgammon_env.py:78-191), uniform-random policy."""
+    try:
+        sys.stdout = open(os.devnull, "w")
+        import numpy as np
+        import torch
+        torch.set_num_threads(1)
+        sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+        import ref_loader
+        ref_loader.load(ref)
+        from src.environment.backgammon_env import BackgammonEnv
+        env = BackgammonEnv()
+        env.seed(seed)
+        rng = np.random.RandomState(seed)
+        env.reset()
+        for _ in range(5):                                          # warm-up (imports, allocator)
+            n = len(env.legal_moves)
+            _, _, done, _ = env.step(int(rng.randint(0, n)) if n else None)
+            if done:
+                env.reset()
+        barrier.wait(timeout=600)
+        t0 = time.perf_counter()
+        steps = 0
+        while time.perf_counter() - t0 < seconds:
+            n = len(env.legal_moves)
+            _, _, done, _ = env.step(int(rng.randint(0, n)) if n else None)
+            steps += 1
+            if done:
+                env.reset()                                         # vec_bg_env.py:35-36
+        q.put((steps, time.perf_counter() - t0))
+    except Exception as e:                                          # noqa: BLE001
+        try:
+            barrier.abort()
+        except Exception:
+            pass
+        q.put(("error", repr(e)))
+
+
+def python_reference_rollout(seconds: float, procs: int):
+    """The reference's own Python path on `procs` host processes for `seconds` each -> dict (or {"unavailable": why})."""
+    ref = reference_dir()
+    if ref is None:
+        return {"kind": "reference-python", "unavailable": "reference tree not staged (baseline/_ref missing)"}
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    barrier, q = ctx.Barrier(procs), ctx.Queue()
+    ps = [ctx.Process(target=_pyref_worker, args=(ref, seconds, 1000 + i, barrier, q), daemon=True) for i in range(procs)]
+    t_spawn = time.perf_counter()
+    [p.start() for p in ps]
+    res = []
+    try:
+        for _ in ps:
+            res.append(q.get(timeout=600 + seconds))
+    except Exception as e:                                          # noqa: BLE001
+        return {"kind": "reference-python", "unavailable": f"workers did not report: {e!r}"}
+    finally:
+        for p in ps:
+            p.join(timeout=5)
+            if p.is_alive():
+                p.terminate()
+    bad = [r for r in res if r[0] == "error"]
+    if bad:
+        return {"kind": "reference-python", "unavailable": bad[0][1][:200]}
+    steps, el = sum(r[0] for r in res), max(r[1] for r in res)
+    return {"kind": "reference-python", "value": steps / el, "unit": UNIT, "cores": procs,
+            "per_process": steps / el / procs,
+            "sample": f"{steps} env steps of the UNMODIFIED reference (BackgammonEnv.step + reset on done, uniform-random policy, "
+                      f"torch threads 1) in {el:.1f} s on {procs} processes, one env each; staged copy {os.path.relpath(ref, ROOT) if ref.startswith(ROOT) else ref}; "
+                      f"start-up {time.perf_counter() - t_spawn - el:.0f} s not counted"}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -141,16 +242,18 @@ def run_reference(args):
         cpu_rollout(per_step_s * args.warmup, threads, chunk, envs=envs)
     total, el = cpu_rollout(per_step_s * args.steps, threads, chunk, envs=envs)
     v = total / el
+    py = python_reference_rollout(args.pyref_seconds, threads) if args.pyref_seconds > 0 else None
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int8", "data": "synthetic",
-            "config": {"workload": "uniform-random self-play, BackgammonEnv.step + update_legal_moves + encoders, CPU port of "
-                                   "the reference path (oracle/bg_oracle.c); the Python reference itself (~50 steps/s/core, "
-                                   "BASELINE.md) cannot travel to the GPU box",
-                       "games": threads, "policy": "uniform random (Philox)"},
+            "config": {"workload": "uniform-random self-play, BackgammonEnv.step + update_legal_moves + encoders on the host cores: "
+                                   "`value` = the C port of the reference path (oracle/bg_oracle.c, the faster baseline); "
+                                   "`cpu_baseline.python_reference` = the unmodified Python reference in the same run",
+                       "games": threads, "policy": "uniform random (Philox)", "cpu_model": cpu_model()},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{total} env steps in {el:.1f} s over {threads} threads, each step of this arm = "
-                                       f"{per_step_s:.2f} s of rollout per thread"},
+                                       f"{per_step_s:.2f} s of rollout per thread",
+                             "python_reference": py},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -158,7 +261,17 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------- GPU arm
 
+def make_env(bg_b200, dev, games_per_gpu: int, rank: int, world: int, rows_per_game: int):
+    """This rank's shard of the world*games_per_gpu games: contiguous global game ids [base, base+count); dice / action
+    streams are keyed by the GLOBAL id (stream_base), so the union of trajectories does not depend on `world`."""
+    base, count = bg_b200.shard_range(world * games_per_gpu, rank, world)
+    env = bg_b200.B200BackgammonVecEnv(num_envs=count, device=dev, seed=SEED, stream_base=base,
+                                       rows_per_game=rows_per_game, check_every=0)
+    return env
+
+
 def run_engine(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     import bg_b200
@@ -169,35 +282,46 @@ def run_engine(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    N = args.games
-    env = bg_b200.B200BackgammonVecEnv(num_envs=N, device=dev, seed=SEED, stream_base=rank * N,
-                                       rows_per_game=args.rows_per_game, check_every=0)
+    ddist = dist if world > 1 else None
+    env = make_env(bg_b200, dev, args.games, rank, world, args.rows_per_game)
+    N = env.num_envs
     env.reset()
     acts = torch.empty(N, dtype=torch.int32, device=dev)
     rows_acc = torch.zeros(1, dtype=torch.int64, device=dev)
-    launches = [0]
     feats = not args.no_afterstate_features
+    LAUNCHES_PER_STEP = 1 + 1 + 3 + 1 + 2 * int(feats)        # actions, K2, K1 tiers 0/1/2, K3 f32, K3 bf16 (two row ranges)
 
-    def one_step(t, ev=None):
-        env.random_actions(ACT_SEED, t, out=acts); launches[0] += 1
-        env._apply_actions(acts); launches[0] += 1
+    def one_step(t, ev=None, overlap=True, count_rows=False):
+        env.random_actions(ACT_SEED, t, out=acts)
+        env._apply_actions(acts)
         # K1 tiers 0/1/2 + K3 (observations f32, afterstate features bf16: rows final after tier 0 are encoded on
         # a second stream beside tiers 1/2, the rest after them) in one C call
-        env.update_legal_plays(obs=True, features=feats, overlap=not args.no_overlap, k1_events=ev)
-        launches[0] += 3 + 1 + 2 * int(feats)
-        rows_acc.add_(env.alloc_rows)
+        env.update_legal_plays(obs=True, features=feats, overlap=overlap, k1_events=ev)
+        if count_rows:
+            rows_acc.add_(env.alloc_rows)
 
+    ev = lambda: torch.cuda.Event(enable_timing=True)
     t = 0
-    for _ in range(args.dephase + args.warmup):               # de-phase the games, then W warm-up steps (untimed)
+    for _ in range(args.dephase):                             # de-phase the games (untimed)
         one_step(t); t += 1
     env.check_status()
-    rows_acc.zero_()
-    launches[0] = 0
     K = args.steps
-    k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    # W warm-up steps (untimed for the result; timed to choose R so that the timed region lasts >= min_seconds)
+    W = max(args.warmup, 1)
+    wa, wb = ev(), ev()
+    torch.cuda.synchronize(); wa.record()
+    for _ in range(W):
+        one_step(t, overlap=not args.no_overlap); t += 1
+    wb.record(); torch.cuda.synchronize()
+    est = torch.tensor([wa.elapsed_time(wb) / W], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    R = max(1, min(args.max_reps, math.ceil(args.min_seconds * 1e3 / (float(est.item()) * K))))
+    n_timed = R * K
+    k1_events = [(ev(), ev()) for _ in range(n_timed)]
     for a, b in k1_events:                                    # create the handles (torch creates them on first record)
         a.record(); b.record()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = ev(), ev()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -206,51 +330,51 @@ def run_engine(args):
         dist.barrier()
     torch.cuda.synchronize()
     e0.record()
-    for k in range(K):
-        one_step(t, k1_events[k]); t += 1
+    for k in range(n_timed):
+        one_step(t, k1_events[k], overlap=not args.no_overlap, count_rows=True); t += 1
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
+    rows_per_step = float(rows_acc.item()) / n_timed          # snapshot: nothing after this line adds to it
     clocks = sampler.stop() if rank == 0 else None
     env.check_status()
-    k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / K
-    # the same K1 launches alone (no encoder beside the overflow tiers), same positions: explains the in-step figure
-    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    env._refresh_legal_moves(); torch.cuda.synchronize()
-    ea.record()
-    for _ in range(20):
-        env._refresh_legal_moves()
-    eb.record(); torch.cuda.synchronize()
-    k1_alone_ms = ea.elapsed_time(eb) / 20
-    # ... and whole steps with the encoders AFTER K1 (nothing overlapped): K1's share of this serialised step is what the
-    # ncu launch list (profiles/, kernels serialised by the profiler) shows
-    overlap_saved, args.no_overlap = args.no_overlap, True
-    ea.record()
-    for _ in range(20):
-        one_step(t); t += 1
-    eb.record(); torch.cuda.synchronize()
-    args.no_overlap = overlap_saved
-    step_serial_ms = ea.elapsed_time(eb) / 20
-    launches[0] -= 20 * 8
-    rows_per_step = float(rows_acc.item()) / K
-    n_launch = launches[0]
+    k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / n_timed
+
+    # ---- per-kernel device times, each kernel alone on the stream (event pairs, 20 serial steps on the same games)
+    names = ("actions", "k2_step", "k1_movegen", "k3_obs_f32", "k3_feats_bf16")
+    acc = dict.fromkeys(names, 0.0)
+    PK = 20
+    pe = [[ev() for _ in range(len(names) + 1)] for _ in range(PK)]
+    for row in pe:
+        row[0].record()
+        env.random_actions(ACT_SEED, t, out=acts); row[1].record()
+        env._apply_actions(acts); row[2].record()
+        env._refresh_legal_moves(); row[3].record()
+        env.encode_resident(obs=True, afterstates=False); row[4].record()
+        if feats:
+            env.encode_resident(obs=False, afterstates=True)
+        row[5].record()
+        t += 1
+    torch.cuda.synchronize()
+    for row in pe:
+        for i, nme in enumerate(names):
+            acc[nme] += row[i].elapsed_time(row[i + 1]) / PK
+    k1_alone_ms = acc["k1_movegen"]
+    step_serial_ms = sum(acc.values())
+    env.check_status()
 
     # ---- end to end through the public API with host buffers: actions from pinned host memory every step,
     # rewards / dones / legal-play counts read back to the host every step (what a host-side policy needs).
-    E = max(1, min(args.e2e_steps, K))
-    import numpy as np
+    E = max(1, args.e2e_steps)
     host = bg_b200.HostStepBuffers(env)                                         # pinned rewards / dones / legal counts
     h_acts = torch.empty(N, dtype=torch.int32).pin_memory()
     rng = np.random.default_rng(1)
-    u = rng.integers(0, 65536, size=(E, N), dtype=np.int32)
     acts_np, counts_np, tmp = h_acts.numpy(), host.legal_counts.numpy(), np.empty(N, dtype=np.int32)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     e2e_segments = []
-    for seg in range(3):                                                        # three segments of E steps; the best one is reported
+    for seg in range(args.e2e_segments + 1):                                    # segment 0 is an untimed warm-up of the e2e path
+        u = rng.integers(0, 65536, size=(E, N), dtype=np.int32)
         host.legal_counts.copy_(env.legal_counts, non_blocking=True)
         torch.cuda.synchronize()
         if world > 1:
@@ -264,59 +388,40 @@ def run_engine(args):
             obs, rew, done, infos = env.step(h_acts, with_features=feats, host=host, overlap=args.e2e_overlap_encoders)
         host.wait()
         torch.cuda.synchronize()                                                # the last step's encoders are inside the timed region
-        e2e_segments.append(time.perf_counter() - t0)
-        u = rng.integers(0, 65536, size=(E, N), dtype=np.int32)
-    e2e_s = min(e2e_segments)
+        if seg > 0:
+            e2e_segments.append(time.perf_counter() - t0)
+    seg_t = torch.tensor(e2e_segments, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(seg_t, op=dist.ReduceOp.MAX)                            # per segment: the slowest rank
+    e2e_segments = seg_t.tolist()
+    e2e_s = statistics.median(e2e_segments)
     env.check_status()
 
-    extra = run_extras(bg_b200, env, torch, dev, args) if (world == 1 and not args.no_extras) else None
-    twoply_all, greedy_all = None, None
-    if world > 1 and not args.no_extras:
-        # 1-ply greedy self-play (configs[2]: games sharded, the value net replicated), device events, max over ranks
-        gnet = bg_b200.ValueNet.random_init(dev, seed=0)
-        def greedy_step():
-            a_, _ = bg_b200.greedy_actions(env, gnet)
-            env.step_device(a_.clamp_(min=0))
-        greedy_step(); torch.cuda.synchronize(); dist.barrier()
-        ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ga.record()
-        for _ in range(30):
-            greedy_step()
-        gb.record(); torch.cuda.synchronize()
-        gt = torch.tensor([ga.elapsed_time(gb) / 30], dtype=torch.float64, device=dev)
-        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
-        greedy_all = {"env_steps_per_s": world * N / (float(gt.item()) * 1e-3), "ms_per_step": float(gt.item()), "games": world * N,
-                      "what": "K4 on every legal afterstate + segment argmax + K2 + K1; max over ranks"}
-        # 2-ply on every rank's own roots (shards of the roots, replicas of the net)
-        tp2 = run_twoply(bg_b200, env, torch, dev, args)
-        agg = torch.tensor([tp2["root_afterstates"], tp2["leaves"], tp2["roots"]], dtype=torch.float64, device=dev)
-        tmax = torch.tensor([tp2["seconds"]], dtype=torch.float64, device=dev)
-        dist.all_reduce(agg, op=dist.ReduceOp.SUM); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        a, l, r = agg.tolist(); sec = float(tmax.item())
-        twoply_all = {"roots": int(r), "root_afterstates": int(a), "leaves": int(l), "seconds": sec, "root_positions_per_s": r / sec,
-              "root_afterstates_per_s": a / sec, "leaves_per_s": l / sec,
-              "note": f"{world} ranks, each its own {args.twoply_roots} roots; sum over ranks / max time over ranks (best of 3)"}
+    extra = run_extras(bg_b200, env, torch, dev, args, ddist, rank, world) if not args.no_extras else None
 
-    tm = torch.tensor([ms, e2e_s * 1e3, k1_ms, k1_alone_ms, step_serial_ms], dtype=torch.float64, device=dev)
+    tm = torch.tensor([ms, k1_ms, k1_alone_ms, step_serial_ms] + [acc[n] for n in names], dtype=torch.float64, device=dev)
     rw = torch.tensor([rows_per_step], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dist.all_reduce(rw, op=dist.ReduceOp.SUM)
         rw /= world
-    ms, e2e_ms, k1_ms, k1_alone_ms, step_serial_ms = [float(x) for x in tm.tolist()]
+    tl = [float(x) for x in tm.tolist()]
+    ms, k1_ms, k1_alone_ms, step_serial_ms = tl[:4]
+    acc = dict(zip(names, tl[4:]))
     rows_per_step = float(rw.item())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return None
 
-    value = world * N * K / (ms * 1e-3)
-    e2e_value = world * N * E / (e2e_ms * 1e-3)
-    peak, peak_src = load_peaks()
-    # K1 algorithmic bytes per launch (DESIGN.md "K1"): per game 52 board + 1 player + 2 dice read; 4 count +
-    # 4 true count + 8 start written; per legal play 52 afterstate + 1 mover flag written.
-    k1_bytes = N * 71.0 + rows_per_step * 53.0
+    ms_step = ms / n_timed
+    value = world * N / (ms_step * 1e-3)
+    e2e_value = world * N * E / e2e_s
+    peak, peak_src, peaks = load_peaks()
+    k1_bytes = N * K1_BYTES_PER_GAME + rows_per_step * K1_BYTES_PER_ROW
     achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
+    step_bytes = (N * (K2_BYTES_PER_GAME + K1_BYTES_PER_GAME + K3_OBS_BYTES_PER_GAME)
+                  + rows_per_step * (K1_BYTES_PER_ROW + (K3_FEAT_BYTES_PER_ROW if feats else 0.0)))
     traffic, issue = None, None
     tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(tp):
@@ -325,131 +430,233 @@ def run_engine(args):
             traffic = kt.get("dram_bytes_per_launch")
             if kt.get("warp_inst_per_launch") and N == 65536:
                 # what actually bounds K1: warp-instruction issue (4 schedulers per SM, one instruction per cycle each)
-                sm_clock_ghz = (clocks or {}).get("sm_mhz") or 1965.0
-                peak_issue = 148 * 4 * sm_clock_ghz / 1e3                      # G warp-instructions / s
+                sm_clock_ghz = ((clocks or {}).get("sm_mhz") or 1965.0) / 1e3
+                peak_issue = 148 * 4 * sm_clock_ghz                             # G warp-instructions / s
                 ach = kt["warp_inst_per_launch"] / (k1_alone_ms * 1e-3) / 1e9
-                issue = {"bound": "warp-instruction issue", "warp_inst_per_launch": kt["warp_inst_per_launch"],
-                         "achieved_ginst_s": ach, "peak_ginst_s": peak_issue, "frac": ach / peak_issue,
-                         "what": "instructions per K1 call from the ncu captures named in profiles/k1_traffic.json / "
+                issue = {"warp_inst_per_launch": kt["warp_inst_per_launch"], "achieved": ach, "peak": peak_issue,
+                         "unit": "G warp-inst/s", "frac": ach / peak_issue,
+                         "what": "instructions of one K1 call from the ncu capture named in profiles/k1_traffic.json / "
                                  "k1_ms_per_launch_alone; peak = 148 SMs x 4 schedulers x the SM clock sampled during the run"}
         except Exception:
             traffic = None
+    us = lambda x: round(x * 1e3, 2)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int8", "data": "synthetic",
         "config": {"workload": "configs[1]: batched legal-move generation + step, uniform-random policy",
                    "games_per_gpu": N, "max_legal_moves": 500, "dephase_steps": args.dephase,
                    "afterstate_features": "bf16 ragged (ld 208)" if feats else "off", "observations": "f32 (N,198)",
                    "legal_plays_per_step_mean": rows_per_step / N, "parallelism": f"games sharded x{world}, no collective",
-                   "l2": "per-step working set (afterstates + features + observations) exceeds the 126 MB L2; no flush"},
-        "roofline": {"kernel": "K1 movegen (tier 0 warp kernel + tier 1/2 team kernels)", "bound": "hbm",
+                   "timed_region": f"{R} x {K} = {n_timed} steps back to back ({ms * 1e-3:.3f} s), one barrier + synchronize on each side; "
+                                   f"R chosen from the warm-up so that the region lasts >= {args.min_seconds} s",
+                   "timed_steps": n_timed, "timed_region_s": ms * 1e-3,
+                   "l2": "per-step working set (afterstates + features + observations, ~0.6 GB) exceeds the 126 MB L2; no flush"},
+        "roofline": {"kernel": "K1 movegen (tier 0 warp kernel + tier 1/2 team kernels), the dominant kernel",
+                     "bound": "issue", "bound_note": "K1 is integer-issue bound (SURVEY 8(d)): roofline.issue is the binding figure; "
+                     "achieved/peak/frac here are the HBM figure the contract asks for",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / (ms / K),
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": k1_bytes,
+                     "algorithmic_bytes_formula": f"{K1_BYTES_PER_GAME:.0f} B x {N} games + {K1_BYTES_PER_ROW:.0f} B x {rows_per_step:.0f} legal plays",
+                     "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / ms_step,
                      "k1_ms_per_launch_alone": k1_alone_ms, "achieved_alone": k1_bytes / (k1_alone_ms * 1e-3) / 1e9,
+                     "frac_alone": k1_bytes / (k1_alone_ms * 1e-3) / 1e9 / peak,
                      "ms_per_step_serial": step_serial_ms, "k1_share_of_step_serial": k1_alone_ms / step_serial_ms,
-                     "algorithmic_bytes_per_launch": k1_bytes,
-                     "note": "K1 is integer-issue bound (SURVEY 8(d)); the HBM fraction is reported as required. In the step "
-                             "the encoders (K3) run on a second stream beside K1's overflow tiers, so k1_ms_per_launch (CUDA "
-                             "events around K1's three launches inside the step) includes that sharing; *_alone is the same "
-                             "launch sequence with nothing beside it, and k1_share_of_step_serial = that / a step with the encoders "
-                             "after K1 -- the share the profiler's serialised launch list shows (profiles/). traffic = dram bytes of the tier 0 + tier 1 launches "
-                             "(ncu --set full, profiles/): below the algorithmic bytes because the afterstate rows are still in "
-                             "the 126 MB L2 when the encoder reads them", "issue": issue},
+                     "issue": issue,
+                     "step_hbm": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
+                                  "peak": peak, "unit": "GB/s", "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                                  "what": "whole step: K2 120 B + K1 71 B + K3 observations 845 B per game, K1 53 B + K3 features 469 B per legal play"},
+                     "kernels_us": {k: us(v) for k, v in acc.items()},
+                     "kernels_hbm_frac": {
+                         "k2_step": N * K2_BYTES_PER_GAME / (acc["k2_step"] * 1e-3) / 1e9 / peak,
+                         "k1_movegen": k1_bytes / (acc["k1_movegen"] * 1e-3) / 1e9 / peak,
+                         "k3_obs_f32": N * K3_OBS_BYTES_PER_GAME / (acc["k3_obs_f32"] * 1e-3) / 1e9 / peak,
+                         "k3_feats_bf16": (rows_per_step * K3_FEAT_BYTES_PER_ROW / (acc["k3_feats_bf16"] * 1e-3) / 1e9 / peak) if feats else None},
+                     "note": "k1_ms_per_launch: CUDA events around K1's three launches inside the timed steps, where the encoders (K3) run "
+                             "on a second stream beside K1's overflow tiers; *_alone / kernels_us: every kernel alone on the stream "
+                             "(20 serial steps on the same games) -- the shares the profiler's serialised launch list shows (profiles/). "
+                             "traffic = dram bytes of one K1 call (ncu --set full, profiles/k1_traffic.json): below the algorithmic bytes "
+                             "because the afterstate rows are still in the 126 MB L2 when the encoder reads them"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * N * 4, "d2h_bytes_per_step": world * N * 9,
                 "steps": E, "segments_ms_per_step": [x * 1e3 / E for x in e2e_segments],
-                "what": "best of 3 segments (host-side jitter); B200BackgammonVecEnv.step(actions from pinned host memory, "
-                                    "host=HostStepBuffers): rewards, dones and legal-play counts are copied to pinned host memory every "
-                                    "step as soon as K2 + K1 are done and the host waits for them before choosing the next actions; "
-                                    "observations / afterstate features (K3) stay on the device as the reference API returns them, "
-                                    "run after K1 and finish while the host prepares the next step"},
-        "gpu_launches": n_launch, "clocks": clocks,
+                "what": f"median of {len(e2e_segments)} segments of {E} steps after one untimed warm segment (per segment: the slowest rank); "
+                        "B200BackgammonVecEnv.step(actions from pinned host memory, host=HostStepBuffers): rewards, dones and legal-play "
+                        "counts are copied to pinned host memory every step as soon as K2 + K1 are done and the host waits for them before "
+                        "choosing the next actions; observations / afterstate features (K3) stay on the device as the reference API returns "
+                        "them, run after K1 and finish while the host prepares the next step"},
+        "gpu_launches": n_timed * LAUNCHES_PER_STEP, "clocks": clocks,
     }
     if extra is not None:
         line["extra"] = extra
-    if twoply_all is not None:
-        line["extra"] = {"twoply": twoply_all, "greedy_1ply": greedy_all}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n, el = cpu_rollout(args.cpu_seconds, threads)
-        line["cpu_baseline"] = {"value": n / el, "unit": UNIT, "cores": threads, "kind": "port",
+        line["cpu_baseline"] = {"value": n / el, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model(),
                                 "sample": f"{n} env steps of the same uniform-random workload in {el:.1f} s over {threads} "
-                                          "threads (oracle/bg_oracle.c; the Python reference measures ~50 steps/s/core, BASELINE.md)"}
+                                          "threads (oracle/bg_oracle.c, the C port of the reference path)",
+                                "python_reference": python_reference_rollout(args.pyref_seconds, threads) if args.pyref_seconds > 0 else None}
     if world > 1:
         dist.destroy_process_group()
     return line
 
 
-def run_extras(bg_b200, env, torch, dev, args):
-    """Secondary figures of the same path (BASELINE.json: "2-ply positions evaluated/sec"; configs[2], configs[3]):
-    K4 leaf evaluator alone, 1-ply greedy self-play steps, 2-ply search.  Random-init weights of the reference
-    architecture (198-128-1 value path), positions = the de-phased random-play games of the main run."""
+def run_extras(bg_b200, env, torch, dev, args, dist, rank, world):
+    """Secondary figures of the same path (BASELINE.json: "2-ply positions evaluated/sec"; configs[2..4]), every one timed
+    with CUDA events (max over ranks, units summed over ranks): K4 leaf evaluator alone, 1-ply greedy self-play at the main
+    run's size and at configs[2]'s 131,072 games per GPU, the policy kernel, the PPO rollout step, a 3-update PPO loop
+    (configs[4]) and the 2-ply search (configs[3]).  Random-init weights of the reference architecture."""
     def timed(fn, reps):
         fn()
         torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(reps):
             fn()
         b.record()
         torch.cuda.synchronize()
-        return a.elapsed_time(b) / reps * 1e-3
+        t = torch.tensor([a.elapsed_time(b) / reps * 1e-3], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def total(x):
+        v = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        return float(v.item())
+    peaks = load_peaks()[2]
     net = bg_b200.ValueNet.random_init(dev, seed=0)
-    out = {}
-    # K4: value of every current afterstate (ragged buffer, ~1.2 M rows), fused encode + tcgen05 GEMM + value head
+    N = env.num_envs
+    out = {"ranks": world}
+    # K4: value of every current afterstate (ragged buffer, ~1.2 M rows per GPU), fused encode + tcgen05 GEMM + value head
     rows = env.total_rows()
     vbuf = torch.empty(rows, dtype=torch.float32, device=dev)
     t = timed(lambda: net.values(env.after52[:rows], env.row_players[:rows], out=vbuf), 20)
-    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    tf = rows * 53504.0 / t / 1e12
-    out["mlp_value"] = {"positions_per_s": rows / t, "rows": rows, "ms": t * 1e3, "tflops_bf16": tf,
-                        "tensor_peak_tflops": peaks.get("bf16_tflops"), "frac_of_tensor_peak": (tf / peaks["bf16_tflops"]) if peaks.get("bf16_tflops") else None,
-                        "hbm_gbs": rows * 57.0 / t / 1e9}
-    # 1-ply greedy self-play (configs[2] per GPU): K4 on the afterstates + segment argmax + K2 + K1
-    def greedy_step():
-        acts, _ = bg_b200.greedy_actions(env, net)
-        env.step_device(acts.clamp_(min=0))
-    t = timed(greedy_step, 30)
-    out["greedy_1ply"] = {"env_steps_per_s": env.num_envs / t, "ms_per_step": t * 1e3, "games": env.num_envs}
+    rows_all = total(rows)
+    tf = rows_all * 53504.0 / t / 1e12
+    out["mlp_value"] = {"positions_per_s": rows_all / t, "rows": int(rows_all), "ms": t * 1e3, "tflops_bf16": tf,
+                        "tflops_bf16_per_gpu": tf / world, "useful_tflops_bf16_per_gpu": rows_all * 50944.0 / t / 1e12 / world,
+                        "tensor_peak_tflops": peaks.get("bf16_tflops"),
+                        "frac_of_tensor_peak": (tf / world / peaks["bf16_tflops"]) if peaks.get("bf16_tflops") else None,
+                        "flop_per_position": "53,504 executed (K padded to 208, bias folded into the GEMM); 50,944 useful (SURVEY 8(d))"}
+
+    # 1-ply greedy self-play (configs[2]): K4 on the afterstates + segment argmax + K2 + K1
+    def greedy_on(e):
+        def f():
+            a_, _ = bg_b200.greedy_actions(e, net)
+            e.step_device(a_.clamp_(min=0))
+        return f
+    t = timed(greedy_on(env), 30)
+    out["greedy_1ply"] = {"env_steps_per_s": total(N) / t, "ms_per_step": t * 1e3, "games": int(total(N)),
+                          "what": "K4 on every legal afterstate + segment argmax + K2 + K1; max over ranks"}
+    if args.config2_games > 0:
+        # configs[2] as written: 1,048,576 games on 8 GPUs = 131,072 per GPU (the value net replicated, games sharded)
+        env2 = make_env(bg_b200, dev, args.config2_games, rank, world, args.rows_per_game)
+        env2.reset()
+        a2 = torch.empty(env2.num_envs, dtype=torch.int32, device=dev)
+        for tt in range(args.dephase):
+            env2.random_actions(ACT_SEED, tt, out=a2)
+            env2.step_device(a2)
+        t = timed(greedy_on(env2), 20)
+        env2.check_status()
+        out["greedy_1ply_config2"] = {"env_steps_per_s": total(env2.num_envs) / t, "ms_per_step": t * 1e3, "games": int(total(env2.num_envs)),
+                                      "games_per_gpu": env2.num_envs,
+                                      "what": "configs[2]: MLP value net 1-ply greedy self-play with on-GPU feature encoding (K4 reads boards, "
+                                              "features are built in tensor memory), 131,072 games per GPU = 1,048,576 on 8"}
+        del env2, a2
     # N1 policy/value rollout forward (select_action) and the PPO rollout step (configs[4] rollout side): policy kernel -> K2 -> K1
     pnet = bg_b200.PolicyValueNet.random_init(dev, seed=0)
-    N = env.num_envs
     pout = (torch.empty(N, dtype=torch.int32, device=dev), torch.empty(N, dtype=torch.float32, device=dev),
             torch.empty(N, dtype=torch.float32, device=dev))
     step_ctr = [0]
     t = timed(lambda: pnet.act(env.boards52, env.players, env.legal_counts, seed=1, step=0, out=pout), 20)
-    out["policy_sample"] = {"positions_per_s": N / t, "ms": t * 1e3, "tflops_bf16": N * (53504.0 + 2 * 128 * 512) / t / 1e12}
+    out["policy_sample"] = {"positions_per_s": total(N) / t, "ms": t * 1e3,
+                            "what": "fused policy/value kernel: encode + 198->128 + 128->500 on tcgen05, prefix mask, softmax, Gumbel-max sample"}
+
     def ppo_rollout_step():
         step_ctr[0] += 1
         pnet.act(env.boards52, env.players, env.legal_counts, seed=1, stream_base=env.stream_base, step=step_ctr[0], out=pout)
         env.step_device(pout[0])
     t = timed(ppo_rollout_step, 30)
-    out["ppo_rollout"] = {"env_steps_per_s": N / t, "ms_per_step": t * 1e3, "games": N,
+    out["ppo_rollout"] = {"env_steps_per_s": total(N) / t, "ms_per_step": t * 1e3, "games": int(total(N)),
                           "what": "sampled policy (fused policy/value kernel) -> K2 -> K1, no feature tensors in HBM"}
-    out["twoply"] = run_twoply(bg_b200, env, torch, dev, args, net)
+    env.check_status()
+    if args.ppo_updates > 0:
+        out["ppo_loop"] = run_ppo_loop(bg_b200, env, pnet, torch, dev, args, dist, world)
+    out["twoply"] = run_twoply(bg_b200, env, torch, dev, args, net, dist, world)
     return out
 
 
-def run_twoply(bg_b200, env, torch, dev, args, net=None):
-    """2-ply (configs[3]): roots = the first R games' positions with their actual dice"""
-    net = net or bg_b200.ValueNet.random_init(dev, seed=0)
+def run_ppo_loop(bg_b200, env, pnet, torch, dev, args, dist, world):
+    """configs[4]: full PPO self-play loop -- rollout (policy kernel -> K2 -> K1, T steps), returns (bg_gae), update
+    (num_epochs full-batch epochs, flat-bucket gradient all-reduce over NCCL) -- on the main run's games."""
+    from bg_b200.ppo import PPOConfig, PPOTrainer
+    cfg = PPOConfig(t_horizon=args.ppo_horizon)
+    tr = PPOTrainer(env, pnet, cfg, dist, seed=0)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    ret = tr.collect(); tr.count_episodes(); tr.update(ret)             # warm-up update (allocations, cuBLAS handles)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    marks = [[ev(), ev(), ev()] for _ in range(args.ppo_updates)]
+    for m in marks:
+        m[0].record()
+        ret = tr.collect()
+        m[1].record()
+        tr.count_episodes()
+        stats = tr.update(ret)
+        m[2].record()
+    torch.cuda.synchronize()
+    ar0, ar1 = ev(), ev()
+    ar0.record()
+    for _ in range(20):
+        tr.learner.fp.all_reduce_grads(dist)
+    ar1.record(); torch.cuda.synchronize()
+    env.check_status()
+    t = torch.tensor([sum(m[0].elapsed_time(m[1]) for m in marks), sum(m[1].elapsed_time(m[2]) for m in marks),
+                      ar0.elapsed_time(ar1) / 20], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    roll_ms, upd_ms, ar_ms = [float(x) for x in t.tolist()]
+    U, T, N = args.ppo_updates, cfg.t_horizon, env.num_envs
+    return {"env_steps_per_s": world * N * T * U / ((roll_ms + upd_ms) * 1e-3), "updates": U, "horizon": T, "games_per_gpu": N,
+            "samples_per_update_per_gpu": N * T, "epochs": cfg.num_epochs,
+            "rollout_ms_per_update": roll_ms / U, "update_ms_per_update": upd_ms / U,
+            "allreduce_ms_per_call": ar_ms, "allreduce_calls_per_update": cfg.num_epochs * cfg.num_minibatches,
+            "allreduce_bytes": tr.learner.fp.numel * 4, "last_stats": {k: v for k, v in stats.items() if isinstance(v, float)},
+            "what": "configs[4]: rollout + GAE + update, one 90,101-float NCCL all-reduce per optimiser step (the only collective); "
+                    "CUDA events, max over ranks"}
+
+
+def run_twoply(bg_b200, env, torch, dev, args, net, dist, world):
+    """2-ply (configs[3]): roots = the first R games' positions of every rank with their actual dice"""
     R = min(args.twoply_roots, env.num_envs)
     search = bg_b200.TwoPlySearch(net, max_afterstates_per_chunk=args.twoply_chunk)
     b, p, d = env.boards52[:R].clone(), env.players[:R].clone(), env.dice[:R].clone()
     search.search(b, p, d)                                    # warm-up: allocates the persistent workspaces
     torch.cuda.synchronize()
-    t, reps = 1e30, 3
-    for _ in range(reps):
+    times = []
+    for _ in range(5):
         search.leaves_evaluated = 0
+        if dist is not None:
+            dist.barrier()
         t0 = time.perf_counter()
         best, scores, offsets, A = search.search(b, p, d)
         torch.cuda.synchronize()
-        t = min(t, time.perf_counter() - t0)
-    return {"roots": R, "root_afterstates": int(A.shape[0]), "leaves": int(search.leaves_evaluated), "seconds": t,
-            "root_positions_per_s": R / t, "root_afterstates_per_s": A.shape[0] / t,
-            "leaves_per_s": search.leaves_evaluated / t,
-            "note": "best of 3, wall clock incl. host orchestration; a 2-ply position = one root afterstate fully expanded "
-                    "(21 opponent rolls x replies, leaves MLP-evaluated)"}
+        times.append(time.perf_counter() - t0)
+    tt = torch.tensor(times, dtype=torch.float64, device=dev)
+    agg = torch.tensor([A.shape[0], search.leaves_evaluated, R], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    t = statistics.median(tt.tolist())
+    a, l, r = agg.tolist()
+    return {"roots": int(r), "root_afterstates": int(a), "leaves": int(l), "seconds": t, "seconds_all": tt.tolist(),
+            "root_positions_per_s": r / t, "root_afterstates_per_s": a / t, "leaves_per_s": l / t,
+            "leaf_tflops_bf16_per_gpu": l * 53504.0 / t / 1e12 / world,
+            "note": f"{world} rank(s), each its own {R} roots; median of 5 searches, wall clock incl. host orchestration, per search "
+                    "the slowest rank; a 2-ply position = one root afterstate fully expanded (21 opponent rolls x replies, leaves MLP-evaluated)"}
 
 
 class StdoutToStderr:
@@ -469,17 +676,21 @@ class StdoutToStderr:
         return False
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games", type=int, default=65536, help="games per GPU")
     ap.add_argument("--dephase", type=int, default=128)
     ap.add_argument("--rows-per-game", type=int, default=64)
+    ap.add_argument("--min-seconds", type=float, default=0.5, help="minimum length of the timed region (R x K steps)")
+    ap.add_argument("--max-reps", type=int, default=400)
     ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--e2e-segments", type=int, default=7)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--pyref-seconds", type=float, default=20.0, help="seconds of the Python reference per process (0 = skip)")
     ap.add_argument("--no-afterstate-features", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
@@ -488,7 +699,14 @@ def main():
                     help="e2e loop: encoders beside K1's overflow tiers (shorter GPU step, but K1 -- which the host waits for -- ends later)")
     ap.add_argument("--twoply-roots", type=int, default=4096)
     ap.add_argument("--twoply-chunk", type=int, default=98304)
-    args = ap.parse_args()
+    ap.add_argument("--config2-games", type=int, default=131072, help="games per GPU of the configs[2] greedy extra (0 = skip)")
+    ap.add_argument("--ppo-updates", type=int, default=3, help="timed updates of the configs[4] PPO loop extra (0 = skip)")
+    ap.add_argument("--ppo-horizon", type=int, default=64)
+    return ap.parse_args(argv)
+
+
+def main():
+    args = parse_args()
     if args.impl == "reference":
         run_reference(args)
         return

@@ -82,6 +82,11 @@ int bg_movegen_slab(const int8_t* boards52, const int8_t* players, const int8_t*
                     unsigned long long* alloc_rows, int32_t* status, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* Tuning / test hook: threads per position of K1's overflow tiers (tier 1: 128, 256 or 512; tier 2: 512 or 1024; 0 = the
+ * default choice).  Results never depend on it: the race tests run the heavy fixtures under every setting and require
+ * bit-identical output.  Process-wide; not meant for production callers. */
+int bg_set_team_threads(int mid, int big);
+
 /* ------------------------------------------------------------------------------------------------
  * K3  feature encoding.  Replaces get_board_features_batch_from_tensors (ai/batching.py:78-147) ==
  * ImmutableBoard.get_board_features (board/immutable_board.py:171-212).  flags[b] = player whose
@@ -124,6 +129,12 @@ typedef struct bg_env_state {
     const int8_t* ext_dice;
     long long ext_len;
     int32_t match_length;
+    /* no_auto_reset != 0: BackgammonEnv semantics instead of VectorizedBackgammonEnv's (backgammon_env.py:119-121,
+     * 156-181 vs vec_bg_env.py:35-36): a win leaves the terminal position in place with the WINNER still to move
+     * (the observation the reference returns), sets game_over[g], and the NEXT step of that game resets it and
+     * returns reward 0, done 1 (flags bit 2).  game_over is then required.  0 = auto-reset inside the step. */
+    int32_t no_auto_reset;
+    int8_t* game_over;       /* [N] latch, only with no_auto_reset */
 } bg_env_state;
 
 typedef struct bg_step_out {
@@ -132,7 +143,7 @@ typedef struct bg_step_out {
     int8_t* info_player;     /* [N] player to move at entry (info["current_player"], :117) */
     int8_t* winner;          /* [N] -1 = none */
     int8_t* game_score;      /* [N] 0, 1, 2, 3 */
-    uint8_t* flags;          /* [N] bit0 passed, bit1 invalid action */
+    uint8_t* flags;          /* [N] bit0 passed, bit1 invalid action, bit2 step on a finished game = reset (no_auto_reset) */
 } bg_step_out;
 
 /* reset all games (mask == NULL) or those with mask[g] != 0: initial position + opening protocol
@@ -140,6 +151,10 @@ typedef struct bg_step_out {
 int bg_env_reset(const bg_env_state* st, const uint8_t* mask, int32_t* status, void* stream);
 /* one step of every game with actions[g] (int32 index into its legal plays; ignored on a pass). */
 int bg_env_step(const bg_env_state* st, const int32_t* actions, const bg_step_out* out, int32_t* status, void* stream);
+/* actions from (pinned) host memory to the device: one plain cudaMemcpyAsync of n int32 on `stream` (the host-side
+ * policy's upload of VectorizedBackgammonEnv.step(actions), vec_bg_env.py:28-33), issued from this library so that the
+ * caller needs no second CUDA runtime binding. */
+int bg_copy_actions_async(int32_t* actions_dev, const int32_t* host_actions, long long n, void* stream);
 /* uniform random policy: actions[g] = mulhi(Philox(seed, stream_base+g, t; "ACT1"), counts[g]) (0 if none). */
 int bg_random_actions(const int32_t* counts, long long N, unsigned long long seed, unsigned long long stream_base,
                       uint32_t t, int32_t* actions, void* stream);

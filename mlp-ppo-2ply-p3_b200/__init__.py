@@ -9,11 +9,12 @@ from ._lib import BgError, LIB_PATH, lib  # noqa: F401
 from .build import build  # noqa: F401
 from .engine import (FEATURES, LD_BF16, MovegenWorkspace, as_board52, encode, from_board52, initial_board52,  # noqa: F401
                      legal_moves, to_board52)
-from .sharding import reduce_report, shard_range  # noqa: F401
+from .sharding import shard_range  # noqa: F401
 from .value_net import ValueNet  # noqa: F401
 from .policy_net import PolicyValueNet  # noqa: F401
 from .ppo import ManualUpdate, PPOConfig, PPOLearner, PPOTrainer, evaluate_vs_random  # noqa: F401
 from .twoply import TwoPlySearch, greedy_actions, segment_argmax  # noqa: F401
+from .single_env import BackgammonEnv, BoardView, Player  # noqa: F401
 from .vec_env import B200BackgammonVecEnv, HostStepBuffers, StepInfos, VectorizedBackgammonEnv  # noqa: F401
 
 __version__ = "0.1.0"

@@ -23,7 +23,8 @@ class EnvState(C.Structure):
                 ("scores", C.c_void_p), ("draws", C.c_void_p), ("match_over", C.c_void_p),
                 ("afterstates52", C.c_void_p), ("starts", C.c_void_p), ("counts", C.c_void_p),
                 ("seed", C.c_ulonglong), ("stream_base", C.c_ulonglong), ("ext_dice", C.c_void_p),
-                ("ext_len", C.c_longlong), ("match_length", C.c_int32)]
+                ("ext_len", C.c_longlong), ("match_length", C.c_int32), ("no_auto_reset", C.c_int32),
+                ("game_over", C.c_void_p)]
 
 
 class StepOut(C.Structure):
@@ -41,12 +42,14 @@ SIGNATURES = {
     "bg_movegen_count": (_I, [_V, _V, _V, _LL, _V, _V, _V, _SZ, _V]),
     "bg_movegen_write": (_I, [_V, _V, _V, _LL, _V, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     "bg_movegen_slab": (_I, [_V, _V, _V, _LL, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
+    "bg_set_team_threads": (_I, [_I, _I]),
     "bg_encode_f32": (_I, [_V, _V, _I, _LL, _V, _V, _LL, _V]),
     "bg_encode_bf16": (_I, [_V, _V, _I, _LL, _V, _V, _LL, _V]),
     "bg_update_legal_plays": (_I, [_V, _V, _V, _LL, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _V, _SZ, _V, _LL, _V, _LL, _V, _V, _V, _V]),
     "bg_env_reset": (_I, [C.POINTER(EnvState), _V, _V, _V]),
     "bg_env_step": (_I, [C.POINTER(EnvState), _V, C.POINTER(StepOut), _V, _V]),
     "bg_random_actions": (_I, [_V, _LL, _U64, _U64, _U32, _V, _V]),
+    "bg_copy_actions_async": (_I, [_V, _V, _LL, _V]),
     "bg_movegen_replies_slab": (_I, [_V, _V, _LL, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     "bg_twoply_replies_values": (_I, [_V, _V, _LL, _V, _LL, _V, _V, _V, _V, _V, _V, _SZ, _V, _V, _V, _F, _V, _V, _V, _V]),
     "bg_twoply_scores": (_I, [_V, _V, _V, _V, _V, _V, _LL, _V, _V]),

@@ -404,9 +404,10 @@ static int launch_movegen(const int8_t* boards, const int8_t* players, const int
 
 using namespace bg;
 
-// Workspace layout (bytes): [0] work_ctr0, [4] overflow_ctr A, [8] work_ctr1, [12] overflow_ctr B, [16] work_ctr2,
-// [64 ..] overflow list A int32[B], then overflow list B int32[B]
-extern "C" size_t bg_movegen_workspace_bytes(long long B) { return 64 + 2 * sizeof(int32_t) * (size_t)(B > 0 ? B : 1); }
+// Workspace layout (bytes; constants in bg_internal.h): [0] work_ctr0, [4] overflow_ctr A, [8] work_ctr1, [12] overflow_ctr B,
+// [16] work_ctr2, [BG_WS_ROWS_AFTER_TIER0 = 40] u64 row-count snapshot after tier 0 (written by callers that fork there),
+// [BG_WS_LISTS = 64 ..] overflow list A int32[B], then overflow list B int32[B]
+extern "C" size_t bg_movegen_workspace_bytes(long long B) { return BG_WS_LISTS + 2 * sizeof(int32_t) * (size_t)(B > 0 ? B : 1); }
 
 int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B, int replicate,
                     int flip_player, int mode,
@@ -426,9 +427,9 @@ int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* d
     if (B > 0x7FFFFFF0LL) return bg_set_error_msg(BG_ERR_INVALID, "movegen: batch too large");
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     unsigned int* ctr = reinterpret_cast<unsigned int*>(ws);
-    int32_t* list_a = reinterpret_cast<int32_t*>(ws + 64);
+    int32_t* list_a = reinterpret_cast<int32_t*>(ws + BG_WS_LISTS);
     int32_t* list_b = list_a + B;
-    cudaError_t e = cudaMemsetAsync(ws, 0, 64, stream);
+    cudaError_t e = cudaMemsetAsync(ws, 0, BG_WS_LISTS, stream);
     if (e != cudaSuccess) return bg_set_error(e, "movegen: memset");
     // Tier 0: every position, BG_MOVEGEN_CAP_SMALL boards per level, 8 warps per CTA.
     int rc = launch_movegen<BG_MOVEGEN_CAP_SMALL, 2 * BG_MOVEGEN_CAP_SMALL, 8>(

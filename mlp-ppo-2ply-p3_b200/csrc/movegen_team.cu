@@ -358,6 +358,9 @@ static int team_size_env(const char* name, int dflt) {
     const char* v = getenv(name);
     return v ? atoi(v) : dflt;
 }
+// ... and for the race tests (bg_set_team_threads): the cross-warp claim / atomicMin protocol must give bit-identical
+// output whatever the team size
+static int g_team_mid_override = 0, g_team_big_override = 0;
 
 template <int CAP, int HS, int T>
 static int launch_team(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
@@ -393,7 +396,7 @@ int movegen_team_mid(const int8_t* boards, const int8_t* players, const int8_t* 
     // 256 threads per position is the fastest alone; when an encoder runs beside the tiers (bg_update_legal_plays)
     // 128 leaves it more of the SMs' thread slots and the pair finishes sooner
     static const int t1_env = team_size_env("BG_TEAM_MID", 0);
-    const int t1 = t1_env ? t1_env : (team_threads_hint ? team_threads_hint : 256);
+    const int t1 = g_team_mid_override ? g_team_mid_override : (t1_env ? t1_env : (team_threads_hint ? team_threads_hint : 256));
     if (t1 == 128) return BG_TEAM_MID(128);
     if (t1 == 512) return BG_TEAM_MID(512);
     return BG_TEAM_MID(256);
@@ -408,10 +411,18 @@ int movegen_team_big(const int8_t* boards, const int8_t* players, const int8_t* 
 #define BG_TEAM_BIG(T) launch_team<BG_MOVEGEN_CAP_BIG, BG_MOVEGEN_HASH_BIG, T>( \
         boards, players, dice, nwork_dev, worklist, replicate, flip_player, mode, offsets, max_rows, after, after_cap_rows, \
         row_players, row_feats, counts_true, counts, starts, alloc, status, work_ctr, nullptr, nullptr, stream)
-    static const int t2 = team_size_env("BG_TEAM_BIG", 512);
+    static const int t2_env = team_size_env("BG_TEAM_BIG", 512);
+    const int t2 = g_team_big_override ? g_team_big_override : t2_env;
     if (t2 == 1024) return BG_TEAM_BIG(1024);
     return BG_TEAM_BIG(512);
 #undef BG_TEAM_BIG
 }
 
 }  // namespace bg
+
+extern "C" int bg_set_team_threads(int mid, int big) {
+    if ((mid != 0 && mid != 128 && mid != 256 && mid != 512) || (big != 0 && big != 512 && big != 1024))
+        return bg_set_error_msg(BG_ERR_INVALID, "bg_set_team_threads: mid must be 0/128/256/512, big 0/512/1024");
+    bg::g_team_mid_override = mid; bg::g_team_big_override = big;
+    return BG_OK;
+}

@@ -88,19 +88,20 @@ extern "C" int bg_update_legal_plays(const int8_t* boards52, const int8_t* playe
     cudaError_t e = cudaEventRecord(fj->start, stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(side, fj->start, 0);
     if (e != cudaSuccess) return bg_set_error(e, "bg_update_legal_plays: fork");
+    // from here on `side` is forked: every exit, failures included, goes through the join below
     int rc = BG_OK;
-    if (observations_f32) {
+    if (observations_f32)
         rc = bg_encode_f32(boards52, players, 0, N, nullptr, observations_f32, observations_ld, side);
-        if (rc != BG_OK) return rc;
-    }
-    unsigned long long* rows_t0 = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(workspace) + 40);
+    unsigned long long* rows_t0 = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(workspace) + BG_WS_ROWS_AFTER_TIER0);
     HookCtx ctx{fj, stream, side, afterstates52, row_players, afterstate_capacity_rows, rows_t0, features_bf16, features_ld, BG_OK};
     bg::MovegenTier0Hook hook{rows_t0, after_tier0, &ctx};
-    if (k1_begin_event) cudaEventRecord((cudaEvent_t)k1_begin_event, stream);
-    rc = bg::movegen_run(boards52, players, dice, N, 1, 0, 2, nullptr, max_rows_per_board, afterstates52,
-                         afterstate_capacity_rows, row_players, nullptr, counts_true, counts, starts, alloc_rows, status,
-                         workspace, workspace_bytes, stream, features_bf16 ? &hook : nullptr);
-    if (k1_end_event) cudaEventRecord((cudaEvent_t)k1_end_event, stream);
+    if (rc == BG_OK) {
+        if (k1_begin_event) cudaEventRecord((cudaEvent_t)k1_begin_event, stream);
+        rc = bg::movegen_run(boards52, players, dice, N, 1, 0, 2, nullptr, max_rows_per_board, afterstates52,
+                             afterstate_capacity_rows, row_players, nullptr, counts_true, counts, starts, alloc_rows, status,
+                             workspace, workspace_bytes, stream, features_bf16 ? &hook : nullptr);
+        if (k1_end_event) cudaEventRecord((cudaEvent_t)k1_end_event, stream);
+    }
     if (rc == BG_OK && features_bf16)                              // rows appended by tiers 1/2
         rc = bg::encode_bf16_launch(afterstates52, row_players, 0, afterstate_capacity_rows, rows_t0, alloc_rows,
                                     features_bf16, features_ld, stream);
@@ -158,14 +159,15 @@ extern "C" int bg_twoply_replies_values(const int8_t* positions52, const int8_t*
         if (e != cudaSuccess) return bg_set_error(e, "bg_twoply_replies_values: fork");
     }
     // value of the position with the opponent to move = the roll's value when the opponent has no reply
+    // (after the fork every exit, failures included, goes through the join at the end)
     rc = bg::mlp_value_launch(positions52, movers, 0, 1, M, nullptr, nullptr, w1_bf16, b1, wv, bv, 0, pass_values, aux);
-    if (rc != BG_OK) return rc;
-    unsigned long long* rows_t0 = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(workspace) + 40);
+    unsigned long long* rows_t0 = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(workspace) + BG_WS_ROWS_AFTER_TIER0);
     LeafCtx ctx{fj, stream, side, replies52, row_players, reply_capacity_rows, rows_t0, w1_bf16, b1, wv, bv, leaf_values};
     bg::MovegenTier0Hook hook{rows_t0, leaves_after_tier0, &ctx};
-    rc = bg::movegen_run(positions52, movers, nullptr, M * 21, 21, 1, 2, nullptr, 0, replies52, reply_capacity_rows,
-                         row_players, nullptr, nullptr, counts, starts, alloc_rows, status, workspace, workspace_bytes,
-                         stream, fj ? &hook : nullptr);
+    if (rc == BG_OK)
+        rc = bg::movegen_run(positions52, movers, nullptr, M * 21, 21, 1, 2, nullptr, 0, replies52, reply_capacity_rows,
+                             row_players, nullptr, nullptr, counts, starts, alloc_rows, status, workspace, workspace_bytes,
+                             stream, fj ? &hook : nullptr);
     if (rc == BG_OK)                                               // all rows (serial) / the rows appended by tiers 1, 2
         rc = bg::mlp_value_launch(replies52, row_players, 0, 0, reply_capacity_rows, fj ? rows_t0 : nullptr, alloc_rows, w1_bf16,
                                   b1, wv, bv, 1, leaf_values, stream);

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) reset_kernel(bg_env_state st, const uint8
                st.ext_dice ? st.ext_dice + 2 * st.ext_len * g : nullptr, st.ext_len, st.draws[g], status};
     new_game(st, g, ds);
     st.draws[g] = ds.draw;
+    if (st.game_over) st.game_over[g] = 0;
 }
 
 __global__ void __launch_bounds__(256) step_kernel(bg_env_state st, const int32_t* __restrict__ actions,
@@ -66,7 +67,11 @@ __global__ void __launch_bounds__(256) step_kernel(bg_env_state st, const int32_
     int done = 0, winner = -1, gs = 0, flags = 0;
     DiceSrc ds{st.seed, st.stream_base + (unsigned long long)g,
                st.ext_dice ? st.ext_dice + 2 * st.ext_len * g : nullptr, st.ext_len, st.draws[g], status};
-    if (n == 0) {                                             // pass: backgammon_env.py:124-140
+    if (st.no_auto_reset && st.game_over[g]) {                // step on a finished game: reset, reward 0, done (:119-121)
+        flags = 4; done = 1;
+        st.game_over[g] = 0;
+        new_game(st, g, ds);
+    } else if (n == 0) {                                             // pass: backgammon_env.py:124-140
         flags = 1;
         st.players[g] = (int8_t)(cur ^ 1);
         int d0, d1; ds.roll(d0, d1);
@@ -93,7 +98,14 @@ __global__ void __launch_bounds__(256) step_kernel(bg_env_state st, const int32_
             int sc = st.scores[2 * g + cur] + gs;                                     // :173
             st.scores[2 * g + cur] = sc;
             if (sc >= st.match_length) st.match_over[g] = 1;                          // :178-181
-            new_game(st, g, ds);                              // auto-reset: vec_bg_env.py:35-36
+            if (st.no_auto_reset) {                           // BackgammonEnv: terminal board stays, winner to move (:152-153,190)
+                uint32_t* bw = reinterpret_cast<uint32_t*>(st.boards52 + g * kBoardBytes);
+#pragma unroll
+                for (int k = 0; k < kBoardWords; ++k) bw[k] = w[k];
+                st.game_over[g] = 1;
+            } else {
+                new_game(st, g, ds);                          // auto-reset: vec_bg_env.py:35-36
+            }
         } else {                                              // :182-188
             uint32_t* bw = reinterpret_cast<uint32_t*>(st.boards52 + g * kBoardBytes);
 #pragma unroll
@@ -131,6 +143,7 @@ static int check_state(const bg_env_state* st, const char* who) {
     if (st->n_games > 0 && (!st->boards52 || !st->players || !st->dice || !st->scores || !st->draws || !st->match_over))
         return bg_set_error_msg(BG_ERR_INVALID, who);
     if (st->ext_dice && st->ext_len <= 0) return bg_set_error_msg(BG_ERR_INVALID, who);
+    if (st->no_auto_reset && st->n_games > 0 && !st->game_over) return bg_set_error_msg(BG_ERR_INVALID, who);
     return BG_OK;
 }
 
@@ -155,6 +168,13 @@ extern "C" int bg_env_step(const bg_env_state* st, const int32_t* actions, const
     unsigned grid = (unsigned)((st->n_games + 255) / 256);
     step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*st, actions, *out, status);
     return bg_set_error(cudaGetLastError(), "bg_env_step: launch");
+}
+
+extern "C" int bg_copy_actions_async(int32_t* actions_dev, const int32_t* host_actions, long long n, void* stream) {
+    if (n < 0 || (n > 0 && (!actions_dev || !host_actions))) return bg_set_error_msg(BG_ERR_INVALID, "bg_copy_actions_async: bad args");
+    if (n == 0) return BG_OK;
+    return bg_set_error(cudaMemcpyAsync(actions_dev, host_actions, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice,
+                                        (cudaStream_t)stream), "bg_copy_actions_async");
 }
 
 extern "C" int bg_random_actions(const int32_t* counts, long long N, unsigned long long seed,

@@ -95,8 +95,9 @@ class PolicyValueNet(ValueNet):
         actions, logp, values = out
         logits = torch.empty((B, ACTIONS), dtype=torch.float32, device=dev) if want_logits else None
         ws = getattr(self, "_ws", None)                           # row-class lists (persistent scratch)
-        if ws is None or ws.numel() < 16 + 4 * B or ws.device != dev:
-            ws = self._ws = torch.empty(int(lib().bg_policy_workspace_bytes(max(B, 1))), dtype=torch.uint8, device=dev)
+        need = int(lib().bg_policy_workspace_bytes(max(B, 1)))    # the C ABI's own requirement (two int32 row lists)
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             check(lib().bg_policy_sample(boards52.data_ptr(), fptr, fall, B, cptr, self.w1_bf16.data_ptr(), None,
                                          self.wa_bf16.data_ptr(), self.ba.data_ptr(), self.wv.data_ptr(), self.bv,

@@ -403,17 +403,27 @@ class PPOTrainer:
         self.net.sync()
         return stats
 
+    def count_episodes(self):
+        """Finished games and reward sum of the rollout just collected, summed over ALL ranks (the reference anneals the
+        entropy coefficient on its global episode count, ppo_agent.py:193, train.py:73): every rank then holds the same
+        total_episodes and uses the same entropy_coef for the same all-reduced step.  -> (n_done, reward_sum, world)"""
+        t = torch.stack([self.buf.dones.sum(dtype=torch.float64), self.buf.rewards.sum(dtype=torch.float64)])
+        world = 1
+        if self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size() > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            world = self.dist.get_world_size()
+        n_done, reward_sum = int(t[0].item()), float(t[1].item())
+        self.episodes += n_done
+        self.learner.total_episodes = self.episodes
+        return n_done, reward_sum, world
+
     def train(self, num_updates: int, log_every: int = 1, log=print):
         for u in range(num_updates):
             ret = self.collect()
-            done = self.buf.dones.bool()
-            n_done = int(done.sum().item())
-            self.episodes += n_done
-            self.learner.total_episodes = self.episodes
+            n_done, reward_sum, world = self.count_episodes()
             stats = self.update(ret)
-            stats.update(update=u, episodes=self.episodes, steps=self.global_step * self.env.num_envs,
-                         mean_reward_per_game=float(self.buf.rewards.sum().item()) / max(1, n_done),
-                         entropy_coef=self.learner.entropy_coef)
+            stats.update(update=u, episodes=self.episodes, steps=self.global_step * self.env.num_envs * world,
+                         mean_reward_per_game=reward_sum / max(1, n_done), entropy_coef=self.learner.entropy_coef)
             self.env.check_status()
             self.history.append(stats)
             if log and u % log_every == 0:

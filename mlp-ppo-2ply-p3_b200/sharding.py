@@ -1,6 +1,7 @@
 """Multi-GPU host logic: games shard by contiguous global game id, one process per GPU, NO data-path
 collective.  Dice/action streams are keyed by the GLOBAL game id (stream_base + local index),
-so the union of trajectories is the same for 1, 2, 4 or 8 GPUs.  The only reductions are for reporting."""
+so the union of trajectories is the same for 1, 2, 4 or 8 GPUs.  Used by bench.py and scripts/train_ppo.py to
+place every rank's env (`stream_base` = the shard's first global id)."""
 from __future__ import annotations
 
 
@@ -12,15 +13,3 @@ def shard_range(total_games: int, rank: int, world: int):
     count = q + (1 if rank < r else 0)
     base = rank * q + min(rank, r)
     return base, count
-
-
-def reduce_report(local_ms: float, local_units: float, dist=None, device=None):
-    """(max over ranks of the elapsed time, sum over ranks of the processed units) -- what bench.py reports."""
-    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
-        return float(local_ms), float(local_units)
-    import torch
-    t = torch.tensor([local_ms], dtype=torch.float64, device=device)
-    u = torch.tensor([local_units], dtype=torch.float64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dist.all_reduce(u, op=dist.ReduceOp.SUM)
-    return float(t.item()), float(u.item())

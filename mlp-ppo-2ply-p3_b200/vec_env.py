@@ -22,16 +22,6 @@ from ._lib import BgError, EnvState, StepOut, check, lib
 from .engine import FEATURES, LD_BF16, from_board52, to_board52, _stream
 
 
-_CUDART = None
-
-
-def _cudart():
-    global _CUDART
-    if _CUDART is None:
-        _CUDART = C.CDLL("libcudart.so")
-    return _CUDART
-
-
 class StepInfos:
     """Lazy list-of-dicts view of the per-game info tensors (reference: list of dicts, vec_bg_env.py:40).
 
@@ -95,7 +85,7 @@ class HostStepBuffers:
 
 class B200BackgammonVecEnv:
     def __init__(self, num_envs=1, match_length=15, max_legal_moves=500, device=None, seed=0x5EED,
-                 stream_base=0, rows_per_game=64, dense_budget_bytes=4 << 30, check_every=16):
+                 stream_base=0, rows_per_game=64, dense_budget_bytes=4 << 30, check_every=16, auto_reset=True):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
         device = torch.device(device) if device is not None else None
@@ -109,6 +99,10 @@ class B200BackgammonVecEnv:
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
         self.boards52, self.players, self.dice = z((N, 52), torch.int8), z((N,), torch.int8), z((N, 2), torch.int8)
         self.scores, self.draws, self.match_over = z((N, 2), torch.int32), z((N,), torch.int32), z((N,), torch.int8)
+        # auto_reset=False: BackgammonEnv's terminal behaviour (backgammon_env.py:119-121,156-181) instead of the vec env's
+        # (vec_bg_env.py:35-36): finished games keep their terminal board until their next step() resets them (single_env.py)
+        self.auto_reset = bool(auto_reset)
+        self.game_over = None if self.auto_reset else z((N,), torch.int8)
         self.cap_rows = max(N * int(rows_per_game), 4096)
         self.after52 = z((self.cap_rows, 52), torch.int8)
         self.row_players = z((self.cap_rows,), torch.int8)
@@ -139,7 +133,8 @@ class B200BackgammonVecEnv:
                         self.scores.data_ptr(), self.draws.data_ptr(), self.match_over.data_ptr(),
                         self.after52.data_ptr(), self.legal_starts.data_ptr(), self.legal_counts.data_ptr(),
                         self.seed, self.stream_base, e.data_ptr() if e is not None else None,
-                        e.shape[1] if e is not None else 0, self.match_length)
+                        e.shape[1] if e is not None else 0, self.match_length, 0 if self.auto_reset else 1,
+                        None if self.auto_reset else self.game_over.data_ptr())
 
     def _state_cached(self) -> EnvState:
         """The state struct of _state(), built once: every pointer in it is a persistent buffer (set_dice_stream, the only
@@ -254,10 +249,8 @@ class B200BackgammonVecEnv:
                 if self._act_dev is None:
                     self._act_dev = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
                 host.stream.wait_event(host.stepped)                           # K2 of the previous step has read the buffer
-                rc = _cudart().cudaMemcpyAsync(C.c_void_p(self._act_dev.data_ptr()), C.c_void_p(actions.data_ptr()),
-                                               C.c_size_t(4 * self.num_envs), 1, C.c_void_p(host.stream.cuda_stream))
-                if rc != 0:
-                    raise BgError(f"cudaMemcpyAsync(actions) failed: {rc}")
+                check(lib().bg_copy_actions_async(self._act_dev.data_ptr(), actions.data_ptr(), self.num_envs,
+                                                  host.stream.cuda_stream), "bg_copy_actions_async")
                 host.actions_up.record(host.stream)
                 actions = self._act_dev
             else:

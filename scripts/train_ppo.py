@@ -16,6 +16,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def make_env(bg_b200, dev, games_per_gpu, rank, world, seed):
+    """This rank's shard of the world * games_per_gpu games (contiguous global game ids; Philox streams keyed by them)."""
+    base, count = bg_b200.shard_range(world * games_per_gpu, rank, world)
+    return bg_b200.B200BackgammonVecEnv(num_envs=count, device=dev, seed=0x5EED + seed, stream_base=base, check_every=0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--games", type=int, default=16384, help="games per GPU")
@@ -39,7 +45,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    env = bg_b200.B200BackgammonVecEnv(num_envs=args.games, device=dev, seed=0x5EED + args.seed, stream_base=rank * args.games, check_every=0)
+    env = make_env(bg_b200, dev, args.games, rank, world, args.seed)
     env.reset()
     net = bg_b200.PolicyValueNet.random_init(dev, seed=args.seed)          # same weights on every rank
     cfg = PPOConfig(t_horizon=args.horizon, num_epochs=args.epochs, num_minibatches=args.minibatches, lam=args.lam, bootstrap=args.bootstrap)
@@ -48,9 +54,7 @@ def main():
         torch.cuda.synchronize(); t0 = time.perf_counter()
         ret = tr.collect()
         torch.cuda.synchronize(); t1 = time.perf_counter()
-        n_done = int(tr.buf.dones.sum().item())
-        tr.episodes += n_done * world
-        tr.learner.total_episodes = tr.episodes
+        tr.count_episodes()                                                # global (all-reduced) episode count -> entropy anneal
         stats = tr.update(ret)
         torch.cuda.synchronize(); t2 = time.perf_counter()
         env.check_status()
