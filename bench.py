@@ -635,28 +635,36 @@ def run_twoply(bg_b200, env, torch, dev, args, net, dist, world):
     R = min(args.twoply_roots, env.num_envs)
     search = bg_b200.TwoPlySearch(net, max_afterstates_per_chunk=args.twoply_chunk)
     b, p, d = env.boards52[:R].clone(), env.players[:R].clone(), env.dice[:R].clone()
-    search.search(b, p, d)                                    # warm-up: allocates the persistent workspaces
+    f = search.search_device(b, p, d)                         # warm-up: allocates the persistent buffers
     torch.cuda.synchronize()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     times = []
-    for _ in range(5):
-        search.leaves_evaluated = 0
+    for _ in range(7):
         if dist is not None:
             dist.barrier()
-        t0 = time.perf_counter()
-        best, scores, offsets, A = search.search(b, p, d)
         torch.cuda.synchronize()
-        times.append(time.perf_counter() - t0)
+        ea.record()
+        f = search.search_device(b, p, d)                     # bg_twoply: one C call, no host synchronisation inside
+        eb.record()
+        torch.cuda.synchronize()
+        times.append(ea.elapsed_time(eb) * 1e-3)
+    st = int(f["status"].item())
+    if st:
+        raise RuntimeError(f"2-ply search: device status {st}")
+    n_after, n_leaves, ovf_items, ovf_leaves = (int(x) for x in f["stats"].tolist())
     tt = torch.tensor(times, dtype=torch.float64, device=dev)
-    agg = torch.tensor([A.shape[0], search.leaves_evaluated, R], dtype=torch.float64, device=dev)
+    agg = torch.tensor([n_after, n_leaves, R, ovf_items, ovf_leaves], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(agg, op=dist.ReduceOp.SUM)
     t = statistics.median(tt.tolist())
-    a, l, r = agg.tolist()
+    a, l, r, oi, ol = agg.tolist()
     return {"roots": int(r), "root_afterstates": int(a), "leaves": int(l), "seconds": t, "seconds_all": tt.tolist(),
             "root_positions_per_s": r / t, "root_afterstates_per_s": a / t, "leaves_per_s": l / t,
             "leaf_tflops_bf16_per_gpu": l * 53504.0 / t / 1e12 / world,
-            "note": f"{world} rank(s), each its own {R} roots; median of 5 searches, wall clock incl. host orchestration, per search "
-                    "the slowest rank; a 2-ply position = one root afterstate fully expanded (21 opponent rolls x replies, leaves MLP-evaluated)"}
+            "overflow_items": int(oi), "overflow_items_frac": oi / max(1.0, a * 21), "overflow_leaves_frac": ol / max(1.0, l),
+            "note": f"{world} rank(s), each its own {R} roots; bg_twoply (root move generation + fused on-chip expansion / leaf MLP / max + "
+                    "scores + argmax in one call); median of 7 searches, CUDA events, per search the slowest rank; a 2-ply position = one "
+                    "root afterstate fully expanded (21 opponent rolls x replies, leaves MLP-evaluated)"}
 
 
 class StdoutToStderr:

@@ -256,9 +256,9 @@ int bg_ppo_loss_grad(const void* logits, int flags /* BG_LOSS_* */, long long ld
 /* ------------------------------------------------------------------------------------------------
  * K5  2-ply search (the reference's own 2-ply, moves/expect_minmax.py:1-206, is
  * commented-out code, so the definition is the build's, on the reference's live primitives).
- * Pipeline (mlp-ppo-2ply-p3_b200/twoply.py): K1 on the roots -> bg_movegen_replies_slab on the root
- * afterstates -> bg_mlp_value on the replies (terminal_aware) and on the afterstates (pass value)
- * -> bg_twoply_scores -> bg_segment_argmax.
+ * bg_twoply (below) is the search; the pieces of the unfused pipeline stay exported (they are what the fused kernel is
+ * tested against): K1 on the roots -> bg_movegen_replies_slab on the root afterstates -> bg_mlp_value on the replies
+ * (terminal_aware) and on the afterstates (pass value) -> bg_twoply_scores -> bg_segment_argmax.
  */
 /* replies of the OPPONENT of movers[i] to each of M positions for each of the 21 sorted rolls
  * (moves/get_all_dice_rolls.py:5-34 order): work item i*21+r; counts/starts/counts_true have M*21
@@ -282,6 +282,31 @@ int bg_twoply_replies_values(const int8_t* positions52, const int8_t* movers, lo
 int bg_twoply_scores(const float* leaf_values, const long long* reply_starts, const int32_t* reply_counts,
                      const float* pass_values, const int8_t* after52, const int8_t* movers, long long M,
                      float* scores, void* stream);
+/* The whole search in ONE call, no host synchronisation (intent of the reference:
+ * moves/expect_minmax.py:184 expectiminimax(board, depth 2, ...), dead code there): K1 on the B roots (slab form) ->
+ * twoply_fused_kernel (csrc/twoply_fused.cu): every root afterstate decoded once, its replies to the 21 rolls generated
+ * in shared memory, expanded into feature rows in TENSOR MEMORY, multiplied on the tcgen05 tensor cores and max-reduced
+ * per (afterstate, roll) on chip -- no reply row, feature row or leaf value crosses HBM -- -> scores -> best play.
+ * The few (afterstate, roll) items too large for the on-chip scratch go through K1's team tiers + K4 inside the call.
+ *   outputs (device, caller-owned): afterstates52 [max_afterstates][52] (rows of root b at starts[b], reference
+ *   legal_moves order), scores [max_afterstates] (same rows), counts [B], starts [B], best [B] (index into the root's
+ *   plays, lowest on ties, -1 = no legal play), best_score [B] (nullable), stats [4] (nullable: root afterstates, leaves
+ *   evaluated, (afterstate, roll) items sent through the overflow path, leaves of those).  status: BG_STATUS_OUTPUT_OVERFLOW if the roots have more than max_afterstates plays in total or the
+ *   overflow slab (64 rows per afterstate + 262,144) was too small -- results are then incomplete, call again with more room.
+ *   workspace: bg_twoply_workspace_bytes(B, max_afterstates) bytes; bg_workspace_bytes(BG_WS_TWOPLY, B) sizes it for
+ *   max_afterstates = BG_TWOPLY_DEFAULT_ROWS_PER_ROOT * B + 4096 (the mean is 18.6 plays per position). */
+#define BG_WS_MOVEGEN 0                 /* = bg_movegen_workspace_bytes(B) */
+#define BG_WS_POLICY 1                  /* = bg_policy_workspace_bytes(B) */
+#define BG_WS_TWOPLY 2
+#define BG_TWOPLY_DEFAULT_ROWS_PER_ROOT 64
+size_t bg_workspace_bytes(int kind, long long B);
+size_t bg_twoply_workspace_bytes(long long B, long long max_afterstates);
+int bg_twoply(const int8_t* boards52, const int8_t* players, const int8_t* dice, long long B,
+              const uint16_t* w1_bf16 /* bg_pack_w1 with the bias folded in */, const float* wv, float bv,
+              long long max_afterstates, int8_t* afterstates52, float* scores, int32_t* counts, long long* starts,
+              int32_t* best, float* best_score /*nullable*/, unsigned long long* stats /*nullable*/, int32_t* status,
+              void* workspace, size_t workspace_bytes, void* stream);
+
 /* best[b] = lowest index (within block b) of the maximum of scores[starts[b] .. +counts[b]), -1 if empty */
 int bg_segment_argmax(const float* scores, const long long* starts, const int32_t* counts, long long B,
                       int32_t* best, float* best_score /*nullable*/, void* stream);

@@ -53,6 +53,9 @@ SIGNATURES = {
     "bg_movegen_replies_slab": (_I, [_V, _V, _LL, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     "bg_twoply_replies_values": (_I, [_V, _V, _LL, _V, _LL, _V, _V, _V, _V, _V, _V, _SZ, _V, _V, _V, _F, _V, _V, _V, _V]),
     "bg_twoply_scores": (_I, [_V, _V, _V, _V, _V, _V, _LL, _V, _V]),
+    "bg_workspace_bytes": (_SZ, [_I, _LL]),
+    "bg_twoply_workspace_bytes": (_SZ, [_LL, _LL]),
+    "bg_twoply": (_I, [_V, _V, _V, _LL, _V, _V, _F, _LL, _V, _V, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     "bg_segment_argmax": (_I, [_V, _V, _V, _LL, _V, _V, _V]),
     "bg_pack_wa": (_I, [_V, _V, _V]),
     "bg_policy_workspace_bytes": (_SZ, [_LL]),

@@ -80,6 +80,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     }
 }
+// one try (the hardware suspends the thread for a bounded time while the phase is pending): true = the phase with `parity` is complete
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(smem_u32(bar)) : "memory");
 }

@@ -115,10 +115,68 @@ class TwoPlySearch:
             self.leaves_evaluated += int(b["leaves"].item())
             return out
 
-    def search(self, boards52: torch.Tensor, players: torch.Tensor, dice: torch.Tensor):
-        """-> best (B,) i32 index into each root's legal plays (-1 if none), scores (total,) f32,
-        offsets (B+1,) i64, afterstates (total,52) i8 (reference legal_moves order)."""
+    def search_unfused(self, boards52: torch.Tensor, players: torch.Tensor, dice: torch.Tensor):
+        """The search through the unfused pipeline (replies materialised in HBM, chunked): what bg_twoply is tested
+        against.  Same return value as search()."""
         counts, offsets, A, rowp = legal_moves(boards52, players, dice, with_row_players=True)
         scores = self.score_afterstates(A, rowp)
         best, _ = segment_argmax(scores, offsets[:-1].contiguous(), counts.clamp(min=0).contiguous())
         return best, scores, offsets, A
+
+    # ------------------------------------------------------------------ the fused search: ONE C call, no host sync
+    def _fused_buffers(self, B, dev, rows_per_root):
+        cap = int(rows_per_root) * B + 4096
+        f = getattr(self, "_fb", None)
+        if f is None or f["dev"] != dev or f["B"] < B or f["cap"] < cap:
+            z = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+            nbytes = int(lib().bg_twoply_workspace_bytes(B, cap))
+            f = self._fb = dict(dev=dev, B=B, cap=cap, after=z((cap, 52), torch.int8), scores=z(cap, torch.float32),
+                                counts=z(B, torch.int32), starts=z(B, torch.int64), best=z(B, torch.int32),
+                                best_score=z(B, torch.float32), stats=torch.zeros(4, dtype=torch.int64, device=dev),
+                                status=torch.zeros(1, dtype=torch.int32, device=dev), ws=z(nbytes, torch.uint8), nbytes=nbytes)
+        return f
+
+    def search_device(self, boards52: torch.Tensor, players: torch.Tensor, dice: torch.Tensor, rows_per_root: int = 64):
+        """bg_twoply: K1 on the roots -> fused on-chip expansion / leaf evaluation / max -> scores -> argmax, one C call,
+        nothing synchronised.  -> dict of persistent device buffers: best (B,), best_score (B,), counts (B,), starts (B,)
+        (root b's plays are rows starts[b] .. +counts[b] of `after` / `scores`, reference legal_moves order), stats
+        (4,) i64 = (root afterstates, leaves evaluated, overflow items, overflow leaves), status (1,) i32 (check with check_status)."""
+        boards52 = boards52.reshape(-1, 52).to(torch.int8).contiguous()
+        B, dev = boards52.shape[0], boards52.device
+        players = players.to(torch.int8).contiguous()
+        dice = dice.to(torch.int8).reshape(B, 2).contiguous()
+        f = self._fused_buffers(B, dev, rows_per_root)
+        f["status"].zero_()
+        net = self.net
+        with torch.cuda.device(dev):
+            check(lib().bg_twoply(boards52.data_ptr(), players.data_ptr(), dice.data_ptr(), B, net.w1_bf16.data_ptr(),
+                                  net.wv.data_ptr(), net.bv, f["cap"], f["after"].data_ptr(), f["scores"].data_ptr(),
+                                  f["counts"].data_ptr(), f["starts"].data_ptr(), f["best"].data_ptr(),
+                                  f["best_score"].data_ptr(), f["stats"].data_ptr(), f["status"].data_ptr(),
+                                  f["ws"].data_ptr(), f["nbytes"], _stream()), "bg_twoply")
+        f["n_roots"] = B
+        return f
+
+    def search(self, boards52: torch.Tensor, players: torch.Tensor, dice: torch.Tensor, rows_per_root: int = 64):
+        """-> best (B,) i32 index into each root's legal plays (-1 if none), scores (total,) f32,
+        offsets (B+1,) i64, afterstates (total,52) i8 (reference legal_moves order, roots in order).
+        The search itself is search_device (one call, no sync); this wrapper reads the status, grows the buffers if the
+        roots had more plays than expected, and gathers the slab-ordered rows into CSR order."""
+        B = boards52.reshape(-1, 52).shape[0]
+        while True:
+            f = self.search_device(boards52, players, dice, rows_per_root)
+            st = int(f["status"].item())
+            if st & 4:                                            # more plays than room: grow and redo (never dropped silently)
+                rows_per_root *= 2
+                continue
+            if st:
+                raise BgError(f"2-ply search: device status {st}: {_lib.status_message(st)}")
+            break
+        n_after, n_leaves, self.overflow_items, self.overflow_leaves = (int(x) for x in f["stats"].tolist())
+        self.leaves_evaluated += n_leaves
+        counts = f["counts"][:B].to(torch.int64)
+        offsets = torch.zeros(B + 1, dtype=torch.int64, device=counts.device)
+        torch.cumsum(counts, 0, out=offsets[1:])
+        roots = torch.repeat_interleave(torch.arange(B, device=counts.device), counts, output_size=n_after)
+        rows = f["starts"][:B][roots] + (torch.arange(n_after, device=counts.device) - offsets[roots])
+        return f["best"][:B].clone(), f["scores"][rows], offsets, f["after"][rows]

@@ -1,0 +1,11 @@
+#!/bin/bash
+# round 2, session B: fused 2-ply -- tests (under a timeout: a protocol bug would hang), microbench, ncu
+set -u
+mkdir -p gpurun_out
+TAG=${1:-r2b}
+timeout 300 python -m pytest tests/test_gpu_mlp_twoply.py -x -q > gpurun_out/pytest_$TAG.log 2>&1; RC=$?; echo "pytest rc=$RC"
+tail -25 gpurun_out/pytest_$TAG.log
+if [ $RC -ne 0 ]; then exit 0; fi
+timeout 200 python scripts/microbench_twoply.py > gpurun_out/mb2_$TAG.log 2>&1; echo "mb rc=$?"; cat gpurun_out/mb2_$TAG.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:twoply_fused -s 1 -c 1 -o gpurun_out/prof_fused_$TAG -f \
+  python scripts/microbench_twoply.py > gpurun_out/ncu_fused_$TAG.log 2>&1; echo "ncu rc=$?"

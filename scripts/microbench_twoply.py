@@ -39,3 +39,22 @@ for ov in (False, True):
     s.overlap = ov
     t = timed(lambda: s._score_chunk(A, rowp, out))
     print(f"score_chunk overlap={ov!s:5}: {t:8.1f} us  -> {M/t:.2f} M root afterstates/s")
+
+# ---- the whole search: bg_twoply (fused, one call) vs the unfused chunked pipeline, 4,096 roots
+R = 4096
+rb, rp, rd = env.boards52[:R].clone(), env.players[:R].clone(), env.dice[:R].clone()
+f = s.search_device(rb, rp, rd); torch.cuda.synchronize()
+assert int(f["status"].item()) == 0, int(f["status"].item())
+na, nl, oi, ol = (int(x) for x in f["stats"].tolist())
+tf = timed(lambda: s.search_device(rb, rp, rd), reps=10)
+print(f"bg_twoply fused          : {tf:8.1f} us  -> {na/tf:.2f} M root afterstates/s, {nl/tf/1e3:.2f} G leaves/s "
+      f"({na} afterstates, {nl} leaves, overflow items {oi} = {oi/(na*21)*100:.2f} %, overflow leaves {ol/nl*100:.1f} %)")
+u = bg_b200.TwoPlySearch(net, max_afterstates_per_chunk=98304)
+u.search_unfused(rb, rp, rd); torch.cuda.synchronize()
+import time
+t0 = time.perf_counter()
+for _ in range(5):
+    u.search_unfused(rb, rp, rd)
+torch.cuda.synchronize()
+tu = (time.perf_counter() - t0) / 5 * 1e6
+print(f"unfused search (wall)    : {tu:8.1f} us  -> {na/tu:.2f} M root afterstates/s")

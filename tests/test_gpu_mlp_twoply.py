@@ -152,3 +152,38 @@ def test_greedy_one_ply_vs_oracle(bg, O, net, weights):
         srt = np.sort(ref)[::-1]
         if n == 1 or srt[0] - srt[1] > 2 * TOL_F32:
             assert acts[g] == int(np.argmax(ref))
+
+
+def test_fused_twoply_equals_unfused_pipeline_bitwise(bg, net):
+    """bg_twoply (one call: root K1 -> on-chip replies / features / tcgen05 MLP / per-(afterstate, roll) max -> scores ->
+    argmax) against the unfused pipeline (replies and leaf values through HBM, chunked): leaf values are computed with
+    the same operand tiles and the same arithmetic, so scores and choices must be IDENTICAL, bit for bit -- on
+    random-play positions with their own dice, on the heaviest doubles fixtures (overflow path) and for a tiny batch."""
+    dev = torch.device("cuda:0")
+    env = bg.B200BackgammonVecEnv(num_envs=3072, device=dev, seed=4321, check_every=0)
+    env.reset()
+    for t in range(90):
+        env.step_device(env.random_actions(9, t))
+    d = np.load(os.path.join(G, "adversarial.npz"))
+    top = np.argsort(-d["counts"])[:24]
+    cases = [(env.boards52.clone(), env.players.clone(), env.dice.clone()),
+             (torch.as_tensor(d["boards"][top]).to(dev), torch.as_tensor(d["players"][top]).to(dev), torch.as_tensor(d["dice"][top]).to(dev)),
+             (env.boards52[:3].clone(), env.players[:3].clone(), env.dice[:3].clone())]
+    for b, p, dc in cases:
+        s = bg.TwoPlySearch(net)
+        best, scores, offsets, A = s.search(b, p, dc)
+        u = bg.TwoPlySearch(net, max_afterstates_per_chunk=16384)
+        ubest, uscores, uoffsets, uA = u.search_unfused(b, p, dc)
+        torch.cuda.synchronize()
+        assert torch.equal(offsets, uoffsets) and torch.equal(A, uA)
+        assert torch.equal(scores.view(torch.int32), uscores.view(torch.int32)), float((scores - uscores).abs().max())
+        assert torch.equal(best, ubest)
+        assert s.leaves_evaluated == u.leaves_evaluated and s.leaves_evaluated > 0
+
+
+def test_bg_workspace_bytes_kinds(bg):
+    L = bg.lib()
+    assert L.bg_workspace_bytes(0, 1000) == L.bg_movegen_workspace_bytes(1000)
+    assert L.bg_workspace_bytes(1, 1000) == L.bg_policy_workspace_bytes(1000)
+    assert L.bg_workspace_bytes(2, 1000) == L.bg_twoply_workspace_bytes(1000, 64 * 1000 + 4096)
+    assert L.bg_workspace_bytes(99, 1000) == 0
