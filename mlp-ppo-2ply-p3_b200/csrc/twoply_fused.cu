@@ -71,10 +71,10 @@ __device__ __forceinline__ void build_leaf_row(const uint4& k, int p, const uint
     const uint2* lut = ft->units;
     const uint32_t own_col = p ? 48u : 0u, oth_col = p ? 0u : 48u;
     const uint32_t* othw = rootw + (p ? 0 : 6);
-    const uint32_t kw[3] = {k.x, k.y, k.z};
-#pragma unroll
+    // (a rolled loop on purpose: the generator warps' hot code has to fit the 32 KB instruction cache)
+#pragma unroll 1
     for (int c = 0; c < 12; ++c) {
-        const uint32_t x = kw[c >> 2] >> (8 * (c & 3));                       // nibbles of points 2c, 2c+1
+        const uint32_t x = (c < 4 ? k.x : (c < 8 ? k.y : k.z)) >> (8 * (c & 3));   // nibbles of points 2c, 2c+1
         const uint2 a = lut[x & 15u], b = lut[(x >> 4) & 15u];
         tmem_st4(trow + own_col + 4u * c, make_uint4(a.x, a.y, b.x, b.y));
         const uint32_t ow = othw[c >> 1] >> (16 * (c & 1));                    // count bytes of the other side's points 2c, 2c+1
@@ -87,61 +87,36 @@ __device__ __forceinline__ void build_leaf_row(const uint4& k, int p, const uint
     tmem_st4(trow + 96u, make_uint4(p ? oth_pair : own_pair, p ? own_pair : oth_pair, p == 0 ? 0x00003F80u : 0x3F800000u, 0x3F803F80u));
 }
 
-struct Sink {                                    // a generator warp's view of the shared tile pipeline
-    FusedSmem& sm;
-    int warp, lane, q;
-    uint32_t tmem;
-    // the afterstate being expanded
-    long long i;
-    int p;                                       // replying player
-    const uint32_t* rootw;
-    uint32_t oth_bar0, oth_off0, oth_home;       // the other side (the root mover): bar, off, has men in p's home board
-
-    __device__ __forceinline__ void lock() {
-        if (lane == 0) while (atomicCAS(&sm.lock[q], 0, 1) != 0) __nanosleep(40);
-        __syncwarp();
+// One quarter (32 rows, this warp's TMEM lane quarter q) of the class's next tile t = ticket[q]; the caller holds the class
+// lock, which is released here.  fill: expand `key` (of replying player p) into the A tile; else the rows are left as they
+// are (an empty quarter contributed by a warp that has run out of work).  code: what the epilogue needs to know about the
+// row -- (i*21 + r) | reward code << 29, or kInvalid.  ONE copy of this code in the kernel (__noinline__): the generator
+// warps' hot loop must stay inside the instruction cache (with the builder inlined at every call site the kernel was
+// 62 KB of SASS and stalled on instruction fetch 7.6 cycles per issue).
+__device__ __noinline__ void tile_quarter(FusedSmem* smp, int q, int lane, uint32_t tmem, bool fill, uint4 key, uint32_t code, int p,
+                                          const uint32_t* rootw, uint32_t oth_bar0, uint32_t oth_off0) {
+    FusedSmem& sm = *smp;
+    const int t = *reinterpret_cast<volatile int*>(&sm.ticket[q]);
+    const int b = t & 1;
+    const uint32_t k = (uint32_t)(t >> 1);
+    mbar_wait(&sm.a_empty[b], (k & 1u) ^ 1u);                                  // the MMAs of tile t-2 have read A[b]
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (fill) {
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(kACol0 + b * kACols);
+        build_leaf_row(key, p, rootw, oth_bar0, oth_off0, &sm.flut, trow);
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
     }
-    __device__ __forceinline__ void unlock(int t_next) {
-        __syncwarp();
-        if (lane == 0) {
-            *reinterpret_cast<volatile int*>(&sm.ticket[q]) = t_next;
-            __threadfence_block();
-            atomicExch(&sm.lock[q], 0);
-        }
-        __syncwarp();
+    sm.seg[t & 3][q * 32 + lane] = code;
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    mbar_arrive(&sm.a_full[b]);
+    __syncwarp();
+    if (lane == 0) {                                                           // next tile of this class; release the class lock
+        *reinterpret_cast<volatile int*>(&sm.ticket[q]) = t + 1;
+        __threadfence_block();
+        atomicExch(&sm.lock[q], 0);
     }
-    // with the class lock held: this warp's quarter of tile t = ticket[q].  fill: write the rows, else leave them (empty quarter)
-    __device__ __forceinline__ void quarter(bool fill, const uint4& key, bool valid, int r, const Root& R) {
-        const int t = *reinterpret_cast<volatile int*>(&sm.ticket[q]);
-        const int b = t & 1;
-        const uint32_t k = (uint32_t)(t >> 1);
-        mbar_wait(&sm.a_empty[b], (k & 1u) ^ 1u);                              // the MMAs of tile t-2 have read A[b]
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        uint32_t code = kInvalid;
-        if (fill) {
-            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(kACol0 + b * kACols);
-            build_leaf_row(key, p, rootw, oth_bar0, oth_off0, &sm.flut, trow);
-            if (valid) {
-                code = (uint32_t)(i * 21 + r);
-                if ((key.w >> 28) == 15u) {                                    // p has borne off 15: the leaf is a finished game
-                    // environment/backgammon_env.py:156-171, 365-405: 1 normal, 1.5 gammon, 2 backgammon
-                    const bool men_home = ((R.block | (R.blot & ~key.w)) & oth_home) != 0u;
-                    const bool on_bar = oth_bar0 + (uint32_t)__popc(key.w & 0xFFFFFFu) > 0u;
-                    code |= (oth_off0 != 0u ? 1u : ((men_home || on_bar) ? 3u : 2u)) << 29;
-                }
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-        }
-        sm.seg[t & 3][q * 32 + lane] = code;
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-        mbar_arrive(&sm.a_full[b]);
-        unlock(t + 1);
-    }
-    __device__ __forceinline__ void submit(const uint4& key, bool valid, int r, const Root& R) {
-        lock();
-        quarter(true, key, valid, r, R);
-    }
-};
+    __syncwarp();
+}
 
 __global__ void __launch_bounds__(kFusedThreads, 1) twoply_fused_kernel(
     const int8_t* __restrict__ after52, const int8_t* __restrict__ movers, long long M_cap,
@@ -196,7 +171,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) twoply_fused_kernel(
         // ================= generators =================
         WarpScratch<kFCap, kFHash>& S = sm.ws[warp];
         Warp<kFCap, kFHash> W(S, lane);
-        Sink K{sm, warp, lane, warp & 3, tmem, 0, 0, S.rootw, 0u, 0u, 0u};
+        const int q = warp & 3;
         uint4* ckey = sm.carry_key[warp];
         uint8_t* croll = sm.carry_roll[warp];
         unsigned long long nleaves = 0;
@@ -207,49 +182,69 @@ __global__ void __launch_bounds__(kFusedThreads, 1) twoply_fused_kernel(
             if ((long long)wi >= M) break;
             const long long i = (long long)wi;
             const uint32_t bword = load_board_word(after52, i, lane);
-            const int me = movers[i] & 1, p = me ^ 1;
+            const int me = movers[i] & 1, p = me ^ 1;                          // p: the replying player
             Node root;
             const bool ok = build_root(bword, p, lane, S.rootw, W.R, root);
             __syncwarp();
             if (!ok) { if (lane == 0) atomicOr(status, BG_STATUS_BAD_INPUT); continue; }
             const uint32_t misc = S.rootw[12];
             if (((misc >> (me ? 24 : 16)) & 0xFFu) == 15u) continue;           // A_i already won by the mover: scored by the scores kernel
-            K.i = i; K.p = p;
-            K.oth_bar0 = (misc >> (p ? 0 : 8)) & 0xFFu; K.oth_off0 = (misc >> (p ? 16 : 24)) & 0xFFu;
-            K.oth_home = p == 0 ? 0xFC0000u : 0x00003Fu;
+            // the other side (the root mover): men on the bar / borne off, and the points of p's home board it occupies
+            const uint32_t oth_bar0 = (misc >> (p ? 0 : 8)) & 0xFFu, oth_off0 = (misc >> (p ? 16 : 24)) & 0xFFu;
+            const uint32_t home = p == 0 ? 0xFC0000u : 0x00003Fu;
+            const uint32_t block_home = W.R.block & home, blot_home = W.R.blot & home;
             int carry = 0;
-            for (int r = 0; r < 21; ++r) {
-                W.overflow = false;
+            // r = 21 is the flush of the replies still waiting for a full group of 32
+            for (int r = 0; r <= 21; ++r) {
                 int obase = 0, n = 0;
-                W.generate(root, kRoll21[r][0], kRoll21[r][1], obase, n);
-                if (W.overflow) {                                              // too many boards per level for this scratch: the ordinary path
-                    if (lane == 0) { const unsigned int k = atomicAdd(ovf_ctr, 1u); ovf_list[k] = (int32_t)(i * 21 + r); }
+                const bool flush = r == 21;
+                if (!flush) {
+                    W.overflow = false;
+                    W.generate(root, kRoll21[r][0], kRoll21[r][1], obase, n);
+                    if (W.overflow) {                                          // too many boards per level for this scratch: the ordinary path
+                        if (lane == 0) { const unsigned int k = atomicAdd(ovf_ctr, 1u); ovf_list[k] = (int32_t)(i * 21 + r); }
+                        __syncwarp();
+                        continue;
+                    }
+                    if (n == 0) continue;
+                    nleaves += (unsigned long long)n;
+                } else if (carry == 0) break;
+                // rows [-carry, 0) are the waiting replies, [0, n) this roll's; groups of 32 go to the tile pipeline
+                int pos = -carry;
+                while (n - pos >= 32 || (flush && n - pos > 0)) {
+                    const int idx = pos + lane;
+                    const bool valid = idx < n;
+                    uint4 key = make_uint4(0u, 0u, 0u, 0u);
+                    int rr = r;
+                    if (valid) {
+                        if (idx < 0) { key = ckey[carry + idx]; rr = (int)croll[carry + idx]; }
+                        else key = S.key[obase + idx];
+                    }
+                    uint32_t code = kInvalid;
+                    if (valid) {
+                        code = (uint32_t)(i * 21 + rr);
+                        if ((key.w >> 28) == 15u) {                            // p has borne off 15: the leaf is a finished game
+                            // environment/backgammon_env.py:156-171, 365-405: 1 normal, 1.5 gammon, 2 backgammon
+                            const bool men_home = (block_home | (blot_home & ~key.w)) != 0u;
+                            const bool on_bar = oth_bar0 + (uint32_t)__popc(key.w & 0xFFFFFFu) > 0u;
+                            code |= (oth_off0 != 0u ? 1u : ((men_home || on_bar) ? 3u : 2u)) << 29;
+                        }
+                    }
                     __syncwarp();
-                    continue;
-                }
-                if (n == 0) continue;
-                nleaves += (unsigned long long)n;
-                int pos = 0;
-                if (carry > 0 && carry + n >= 32) {                            // top the waiting replies up to a full group
-                    const bool c = lane < carry;
-                    const uint4 key = c ? ckey[lane] : S.key[obase + lane - carry];
-                    const int rr = c ? (int)croll[lane] : r;
+                    if (lane == 0) while (atomicCAS(&sm.lock[q], 0, 1) != 0) __nanosleep(64);   // this class's turn
                     __syncwarp();
-                    K.submit(key, true, rr, W.R);
-                    pos = 32 - carry; carry = 0;
+                    tile_quarter(&sm, q, lane, tmem, true, key, code, p, S.rootw, oth_bar0, oth_off0);
+                    pos += 32;
                 }
-                for (; n - pos >= 32; pos += 32) K.submit(S.key[obase + pos + lane], true, r, W.R);
-                const int rem = n - pos;                                       // < 32, and carry + rem < 32
-                if (lane < rem) { ckey[carry + lane] = S.key[obase + pos + lane]; croll[carry + lane] = (uint8_t)r; }
-                carry += rem;
+                if (pos < 0) {                                                 // no group formed: this roll's replies join the waiting ones
+                    if (lane < n) { ckey[carry + lane] = S.key[obase + lane]; croll[carry + lane] = (uint8_t)r; }
+                    carry += n;
+                } else {
+                    const int rem = max(n - pos, 0);
+                    if (lane < rem) { ckey[lane] = S.key[obase + pos + lane]; croll[lane] = (uint8_t)r; }
+                    carry = rem;
+                }
                 __syncwarp();
-            }
-            if (carry > 0) {
-                const bool c = lane < carry;
-                const uint4 key = c ? ckey[lane] : make_uint4(0u, 0u, 0u, 0u);
-                const int rr = c ? (int)croll[lane] : 0;
-                __syncwarp();
-                K.submit(key, c, rr, W.R);
             }
         }
         if (lane == 0) {
@@ -260,18 +255,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) twoply_fused_kernel(
         // out of work: keep the tile pipeline complete for the classes that are still producing
         for (;;) {
             int act = 0;                                                       // 1: contribute an empty quarter (lock held), 2: all done
-            if (lane == 0 && atomicCAS(&sm.lock[K.q], 0, 1) == 0) {
+            if (lane == 0 && atomicCAS(&sm.lock[q], 0, 1) == 0) {
                 volatile int* tk = sm.ticket;
                 const int t0 = tk[0], t1 = tk[1], t2 = tk[2], t3 = tk[3];
-                const int mine = tk[K.q], mx = max(max(t0, t1), max(t2, t3));
+                const int mine = tk[q], mx = max(max(t0, t1), max(t2, t3));
                 if (mine < mx) act = 1;
                 else {
-                    atomicExch(&sm.lock[K.q], 0);
+                    atomicExch(&sm.lock[q], 0);
                     if (*reinterpret_cast<volatile int*>(&sm.finished) == kGenWarps && t0 == t1 && t1 == t2 && t2 == t3) act = 2;
                 }
             }
             act = __shfl_sync(kFull, act, 0);
-            if (act == 1) K.quarter(false, make_uint4(0u, 0u, 0u, 0u), false, 0, W.R);
+            if (act == 1) tile_quarter(&sm, q, lane, tmem, false, make_uint4(0u, 0u, 0u, 0u), kInvalid, 0, S.rootw, 0u, 0u);
             else if (act == 2) break;
             else __nanosleep(256);
         }
@@ -283,14 +278,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) twoply_fused_kernel(
             const int s = t & 1;
             const uint32_t it = (uint32_t)(t >> 1);
             bool stop = false;
-            while (!mbar_try_wait(&sm.a_full[s], it & 1u))
+            while (!mbar_try_wait(&sm.a_full[s], it & 1u)) {
                 if (*reinterpret_cast<volatile int*>(&sm.final_tiles) == t) { stop = true; break; }
+                __nanosleep(64);
+            }
             if (stop) break;
             mbar_wait(&sm.acc_empty[s], (it & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             if (lane == 0) {
-#pragma unroll
-                for (int ks = 0; ks < kKPad / 16; ++ks)
+#pragma unroll 1
+                for (int ks = 0; ks < kKPad / 16; ++ks)                        // (rolled: code size)
                     mma_bf16_ts(tmem + (uint32_t)(s * kHidden), tmem + (uint32_t)(kACol0 + s * kACols + ks * 8),
                                 make_smem_desc(w_addr + ks * 2 * 2048), kIdesc, ks > 0 ? 1u : 0u);
                 umma_commit(&sm.a_empty[s]);
@@ -305,16 +302,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) twoply_fused_kernel(
             const int s = t & 1;
             const uint32_t it = (uint32_t)(t >> 1);
             bool stop = false;
-            while (!mbar_try_wait(&sm.acc_full[s], it & 1u))
+            while (!mbar_try_wait(&sm.acc_full[s], it & 1u)) {
                 if (*reinterpret_cast<volatile int*>(&sm.final_tiles) == t) { stop = true; break; }
+                __nanosleep(64);
+            }
             if (stop) break;
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t code = sm.seg[t & 3][q * 32 + lane];
             float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
             uint32_t acc[32];
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kHidden);
-#pragma unroll
-            for (int pass = 0; pass < 4; ++pass) {
+#pragma unroll 1
+            for (int pass = 0; pass < 4; ++pass) {                             // (rolled: code size, see build_leaf_row)
                 tmem_ld32(taddr + 32 * pass, acc);
                 tmem_ld_wait();
 #pragma unroll

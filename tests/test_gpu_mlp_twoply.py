@@ -178,7 +178,9 @@ def test_fused_twoply_equals_unfused_pipeline_bitwise(bg, net):
         assert torch.equal(offsets, uoffsets) and torch.equal(A, uA)
         assert torch.equal(scores.view(torch.int32), uscores.view(torch.int32)), float((scores - uscores).abs().max())
         assert torch.equal(best, ubest)
-        assert s.leaves_evaluated == u.leaves_evaluated and s.leaves_evaluated > 0
+        # (the fused kernel does not expand afterstates the mover has already won; the unfused pipeline generates -- and then
+        # ignores -- replies for them, so its leaf count is slightly larger)
+        assert 0 < s.leaves_evaluated <= u.leaves_evaluated and s.leaves_evaluated > 0.98 * u.leaves_evaluated
 
 
 def test_bg_workspace_bytes_kinds(bg):
