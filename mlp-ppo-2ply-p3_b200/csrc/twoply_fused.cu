@@ -41,10 +41,14 @@ constexpr int kWBytes = kChunks * kTileM * 16;   // 53,248: the W1 operand tile 
 constexpr int kACols = kKPad / 2;                // 104 TMEM columns per A tile
 constexpr int kACol0 = 2 * kHidden;              // after the two f32 accumulators
 constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+// Quarters of one class in flight at a time: tiles t, t+1 being written (one per A buffer) and t+2, t+3 waiting for the MMAs of
+// t, t+1.  More would alias the phase parity of the a_empty barriers (a wait for "two phases ahead" passes immediately).
+constexpr int kInFlight = 4;
 
 struct FusedSmem {
     uint8_t W[kWBytes];
     WarpScratch<kFCap, kFHash> ws[kGenWarps];
+    uint4 oth_chunk[kGenWarps][12];              // the 12 feature chunks of the NON-moving side of the warp's afterstate (no blot hit)
     uint4 carry_key[kGenWarps][32];              // replies waiting for a full group of 32 (always of the warp's current afterstate)
     uint8_t carry_roll[kGenWarps][32];
     uint32_t seg[4][kTileM];                     // per tile (t & 3): row -> (i*21 + r) | reward code << 29, kInvalid for an empty row
@@ -52,11 +56,13 @@ struct FusedSmem {
     FeatureLut flut;
     unsigned long long a_full[2], a_empty[2], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
-    int ticket[4];                               // per class: quarters contributed so far = index of the next tile
-    int lock[4];
+    int ticket[4];                               // per class: quarters handed out so far = index of the class's next tile
+    int sem[4];                                  // per class: quarters that may still be in flight (kInFlight when idle)
     int finished;                                // generator warps that have run out of work
     int final_tiles;                             // -1 until the end: total number of tiles
 };
+
+static_assert(sizeof(FusedSmem) + 1024 <= 227 * 1024, "twoply_fused_kernel: shared memory over the 227 KB per-CTA limit");
 
 // order-preserving map f32 -> u32 (0 is below every finite value: "no reply yet")
 __device__ __forceinline__ uint32_t enc_max(float v) { const uint32_t b = __float_as_uint(v); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
@@ -66,8 +72,8 @@ __device__ __forceinline__ float dec_max(uint32_t k) { return __uint_as_float((k
 // with key k, replying player p to move: p's side from the key's nibbles, the other side from the afterstate's own
 // rows minus the blots hit by this reply.  25 chunks of 16 bytes -> TMEM columns [0, 100) of the row (chunk 25 is zero,
 // written once at kernel start).
-__device__ __forceinline__ void build_leaf_row(const uint4& k, int p, const uint32_t* rootw, uint32_t oth_bar0, uint32_t oth_off0,
-                                               const FeatureLut* ft, uint32_t trow) {
+__device__ __forceinline__ void build_leaf_row(const uint4& k, int p, const uint32_t* rootw, const uint4* oth_chunk, uint32_t oth_bar0,
+                                               uint32_t oth_off0, const FeatureLut* ft, uint32_t trow) {
     const uint2* lut = ft->units;
     const uint32_t own_col = p ? 48u : 0u, oth_col = p ? 0u : 48u;
     const uint32_t* othw = rootw + (p ? 0 : 6);
@@ -77,45 +83,54 @@ __device__ __forceinline__ void build_leaf_row(const uint4& k, int p, const uint
         const uint32_t x = (c < 4 ? k.x : (c < 8 ? k.y : k.z)) >> (8 * (c & 3));   // nibbles of points 2c, 2c+1
         const uint2 a = lut[x & 15u], b = lut[(x >> 4) & 15u];
         tmem_st4(trow + own_col + 4u * c, make_uint4(a.x, a.y, b.x, b.y));
-        const uint32_t ow = othw[c >> 1] >> (16 * (c & 1));                    // count bytes of the other side's points 2c, 2c+1
-        const uint32_t h = k.w >> (2 * c);                                     // ... and whether their blot was hit
-        const uint2 e = lut[((ow & 15u) - (h & 1u)) & 15u], f = lut[(((ow >> 8) & 15u) - ((h >> 1) & 1u)) & 15u];
-        tmem_st4(trow + oth_col + 4u * c, make_uint4(e.x, e.y, f.x, f.y));
+        // the other side only differs from the afterstate's own rows where this reply hit a blot (rare)
+        uint4 o = oth_chunk[c];
+        const uint32_t h = (k.w >> (2 * c)) & 3u;
+        if (h) {
+            const uint32_t ow = othw[c >> 1] >> (16 * (c & 1));                // count bytes of the other side's points 2c, 2c+1
+            const uint2 e = lut[((ow & 15u) - (h & 1u)) & 15u], f = lut[(((ow >> 8) & 15u) - (h >> 1)) & 15u];
+            o = make_uint4(e.x, e.y, f.x, f.y);
+        }
+        tmem_st4(trow + oth_col + 4u * c, o);
     }
     const uint32_t own_pair = bar_off_pair_s((k.w >> 24) & 15u, k.w >> 28, ft);
     const uint32_t oth_pair = bar_off_pair_s(oth_bar0 + (uint32_t)__popc(k.w & 0xFFFFFFu), oth_off0, ft);
     tmem_st4(trow + 96u, make_uint4(p ? oth_pair : own_pair, p ? own_pair : oth_pair, p == 0 ? 0x00003F80u : 0x3F800000u, 0x3F803F80u));
 }
 
-// One quarter (32 rows, this warp's TMEM lane quarter q) of the class's next tile t = ticket[q]; the caller holds the class
-// lock, which is released here.  fill: expand `key` (of replying player p) into the A tile; else the rows are left as they
-// are (an empty quarter contributed by a warp that has run out of work).  code: what the epilogue needs to know about the
-// row -- (i*21 + r) | reward code << 29, or kInvalid.  ONE copy of this code in the kernel (__noinline__): the generator
-// warps' hot loop must stay inside the instruction cache (with the builder inlined at every call site the kernel was
-// 62 KB of SASS and stalled on instruction fetch 7.6 cycles per issue).
-__device__ __noinline__ void tile_quarter(FusedSmem* smp, int q, int lane, uint32_t tmem, bool fill, uint4 key, uint32_t code, int p,
-                                          const uint32_t* rootw, uint32_t oth_bar0, uint32_t oth_off0) {
+// One quarter (32 rows, this warp's TMEM lane quarter q) of tile t of the class (the caller took the ticket and a slot of
+// the class's semaphore, which is released here).  fill: expand `key` (of replying player p) into the A tile; else the rows
+// are left as they are (an empty quarter contributed by a warp that has run out of work).  code: what the epilogue needs
+// to know about the row -- (i*21 + r) | reward code << 29, or kInvalid.  ONE copy of this code in the kernel
+// (__noinline__): the generator warps' hot loop must stay inside the instruction cache (with the builder inlined at every
+// call site the kernel was 62 KB of SASS and stalled on instruction fetch 7.6 cycles per issue).
+__device__ __noinline__ void tile_quarter(FusedSmem* smp, int q, int lane, uint32_t tmem, int t, bool fill, uint4 key, uint32_t code, int p,
+                                          const uint32_t* rootw, const uint4* oth_chunk, uint32_t oth_bar0, uint32_t oth_off0) {
     FusedSmem& sm = *smp;
-    const int t = *reinterpret_cast<volatile int*>(&sm.ticket[q]);
     const int b = t & 1;
     const uint32_t k = (uint32_t)(t >> 1);
     mbar_wait(&sm.a_empty[b], (k & 1u) ^ 1u);                                  // the MMAs of tile t-2 have read A[b]
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     if (fill) {
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(kACol0 + b * kACols);
-        build_leaf_row(key, p, rootw, oth_bar0, oth_off0, &sm.flut, trow);
+        build_leaf_row(key, p, rootw, oth_chunk, oth_bar0, oth_off0, &sm.flut, trow);
         asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
     }
     sm.seg[t & 3][q * 32 + lane] = code;
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     mbar_arrive(&sm.a_full[b]);
     __syncwarp();
-    if (lane == 0) {                                                           // next tile of this class; release the class lock
-        *reinterpret_cast<volatile int*>(&sm.ticket[q]) = t + 1;
-        __threadfence_block();
-        atomicExch(&sm.lock[q], 0);
+    if (lane == 0) atomicAdd(&sm.sem[q], 1);
+}
+
+// a slot of class q's semaphore and the class's next tile index (lane 0 spins; the warp gets the ticket)
+__device__ __forceinline__ int take_ticket(FusedSmem& sm, int q, int lane) {
+    int t = 0;
+    if (lane == 0) {
+        while (atomicSub(&sm.sem[q], 1) <= 0) { atomicAdd(&sm.sem[q], 1); __nanosleep(128); }
+        t = atomicAdd(&sm.ticket[q], 1);
     }
-    __syncwarp();
+    return __shfl_sync(kFull, t, 0);
 }
 
 __global__ void __launch_bounds__(kFusedThreads, 1) twoply_fused_kernel(
@@ -143,7 +158,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) twoply_fused_kernel(
             mbar_init(&sm.a_full[s], kTileM);  mbar_init(&sm.a_empty[s], 1);
             mbar_init(&sm.acc_full[s], 1);     mbar_init(&sm.acc_empty[s], kTileM);
         }
-        for (int c = 0; c < 4; ++c) { sm.ticket[c] = 0; sm.lock[c] = 0; }
+        for (int c = 0; c < 4; ++c) { sm.ticket[c] = 0; sm.sem[c] = kInFlight; }
         sm.finished = 0; sm.final_tiles = -1;
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -193,6 +208,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) twoply_fused_kernel(
             const uint32_t oth_bar0 = (misc >> (p ? 0 : 8)) & 0xFFu, oth_off0 = (misc >> (p ? 16 : 24)) & 0xFFu;
             const uint32_t home = p == 0 ? 0xFC0000u : 0x00003Fu;
             const uint32_t block_home = W.R.block & home, blot_home = W.R.blot & home;
+            if (lane < 12) {                                                   // the other side's feature chunks, once per afterstate
+                const uint32_t ow = S.rootw[(p ? 0 : 6) + (lane >> 1)] >> (16 * (lane & 1));
+                const uint2 e = sm.flut.units[ow & 15u], f = sm.flut.units[(ow >> 8) & 15u];
+                sm.oth_chunk[warp][lane] = make_uint4(e.x, e.y, f.x, f.y);
+            }
+            __syncwarp();
             int carry = 0;
             // r = 21 is the flush of the replies still waiting for a full group of 32
             for (int r = 0; r <= 21; ++r) {
@@ -231,9 +252,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) twoply_fused_kernel(
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) while (atomicCAS(&sm.lock[q], 0, 1) != 0) __nanosleep(64);   // this class's turn
-                    __syncwarp();
-                    tile_quarter(&sm, q, lane, tmem, true, key, code, p, S.rootw, oth_bar0, oth_off0);
+                    const int t = take_ticket(sm, q, lane);
+                    tile_quarter(&sm, q, lane, tmem, t, true, key, code, p, S.rootw, sm.oth_chunk[warp], oth_bar0, oth_off0);
                     pos += 32;
                 }
                 if (pos < 0) {                                                 // no group formed: this roll's replies join the waiting ones
@@ -254,19 +274,21 @@ __global__ void __launch_bounds__(kFusedThreads, 1) twoply_fused_kernel(
         __syncwarp();
         // out of work: keep the tile pipeline complete for the classes that are still producing
         for (;;) {
-            int act = 0;                                                       // 1: contribute an empty quarter (lock held), 2: all done
-            if (lane == 0 && atomicCAS(&sm.lock[q], 0, 1) == 0) {
+            int act = 0, t = 0;                                                // 1: contribute an empty quarter (tile t), 2: all done
+            if (lane == 0) {
                 volatile int* tk = sm.ticket;
                 const int t0 = tk[0], t1 = tk[1], t2 = tk[2], t3 = tk[3];
                 const int mine = tk[q], mx = max(max(t0, t1), max(t2, t3));
-                if (mine < mx) act = 1;
-                else {
-                    atomicExch(&sm.lock[q], 0);
-                    if (*reinterpret_cast<volatile int*>(&sm.finished) == kGenWarps && t0 == t1 && t1 == t2 && t2 == t3) act = 2;
-                }
+                if (mine < mx) {                                               // another class is ahead: take this class's next quarter
+                    // (two idle warps of a class may both decide to fill and the second one run one tile ahead of everybody: an
+                    // all-empty tile is harmless, the other classes then catch up the same way)
+                    if (atomicSub(&sm.sem[q], 1) > 0) { t = atomicAdd(&sm.ticket[q], 1); act = 1; }
+                    else atomicAdd(&sm.sem[q], 1);
+                } else if (*reinterpret_cast<volatile int*>(&sm.finished) == kGenWarps && t0 == t1 && t1 == t2 && t2 == t3) act = 2;
             }
             act = __shfl_sync(kFull, act, 0);
-            if (act == 1) tile_quarter(&sm, q, lane, tmem, false, make_uint4(0u, 0u, 0u, 0u), kInvalid, 0, S.rootw, 0u, 0u);
+            t = __shfl_sync(kFull, t, 0);
+            if (act == 1) tile_quarter(&sm, q, lane, tmem, t, false, make_uint4(0u, 0u, 0u, 0u), kInvalid, 0, S.rootw, sm.oth_chunk[warp], 0u, 0u);
             else if (act == 2) break;
             else __nanosleep(256);
         }
