@@ -41,9 +41,10 @@ constexpr int kWBytes = kChunks * kTileM * 16;   // 53,248: the W1 operand tile 
 constexpr int kACols = kKPad / 2;                // 104 TMEM columns per A tile
 constexpr int kACol0 = 2 * kHidden;              // after the two f32 accumulators
 constexpr uint32_t kInvalid = 0xFFFFFFFFu;
-// Quarters of one class in flight at a time: tiles t, t+1 being written (one per A buffer) and t+2, t+3 waiting for the MMAs of
-// t, t+1.  More would alias the phase parity of the a_empty barriers (a wait for "two phases ahead" passes immediately).
-constexpr int kInFlight = 4;
+// Quarters of one class in flight at a time: tiles t and t+1, one per A buffer.  A third one (t+2) would wait on the same
+// a_empty barrier as t for the NEXT phase, and a parity wait for "two phases ahead" passes immediately while t is still
+// waiting for the MMAs of t-2 (measured: that version hung).
+constexpr int kInFlight = 2;
 
 struct FusedSmem {
     uint8_t W[kWBytes];
