@@ -124,14 +124,34 @@ __device__ __noinline__ void tile_quarter(FusedSmem* smp, int q, int lane, uint3
     if (lane == 0) atomicAdd(&sm.sem[q], 1);
 }
 
-// a slot of class q's semaphore and the class's next tile index (lane 0 spins; the warp gets the ticket)
-__device__ __forceinline__ int take_ticket(FusedSmem& sm, int q, int lane) {
-    int t = 0;
-    if (lane == 0) {
-        while (atomicSub(&sm.sem[q], 1) <= 0) { atomicAdd(&sm.sem[q], 1); __nanosleep(128); }
-        t = atomicAdd(&sm.ticket[q], 1);
+// A slot of class q's semaphore and the class's next tile index.  While the class is saturated (both of its quarters in
+// flight are waiting for older tiles to be multiplied), the pipeline is being held up by a class that has not yet taken
+// its quarter of such a tile -- its warps are all busy generating.  An EMPTY quarter needs no tensor-memory write, so any
+// warp may contribute it on the laggard's behalf (same semaphore / ticket protocol): the tile completes with 32 unused
+// rows (the tensor pipe has plenty of slack) instead of stalling three classes.
+__device__ __forceinline__ int take_ticket(FusedSmem* smp, int q, int lane, uint32_t tmem, const uint32_t* rootw, const uint4* oth_chunk) {
+    FusedSmem& sm = *smp;
+    for (;;) {
+        int got = 0, help = -1, t = 0;
+        if (lane == 0) {
+            if (atomicSub(&sm.sem[q], 1) > 0) { t = atomicAdd(&sm.ticket[q], 1); got = 1; }
+            else {
+                atomicAdd(&sm.sem[q], 1);
+                volatile int* tk = sm.ticket;
+                const int mine = tk[q];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (help < 0 && c != q && tk[c] <= mine - 3) {
+                        if (atomicSub(&sm.sem[c], 1) > 0) { t = atomicAdd(&sm.ticket[c], 1); help = c; }
+                        else atomicAdd(&sm.sem[c], 1);
+                    }
+            }
+        }
+        got = __shfl_sync(kFull, got, 0); help = __shfl_sync(kFull, help, 0); t = __shfl_sync(kFull, t, 0);
+        if (got) return t;
+        if (help >= 0) tile_quarter(smp, help, lane, tmem, t, false, make_uint4(0u, 0u, 0u, 0u), kInvalid, 0, rootw, oth_chunk, 0u, 0u);
+        else __nanosleep(128);
     }
-    return __shfl_sync(kFull, t, 0);
 }
 
 __global__ void __launch_bounds__(kFusedThreads, 1) twoply_fused_kernel(
@@ -253,7 +273,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) twoply_fused_kernel(
                         }
                     }
                     __syncwarp();
-                    const int t = take_ticket(sm, q, lane);
+                    const int t = take_ticket(&sm, q, lane, tmem, S.rootw, sm.oth_chunk[warp]);
                     tile_quarter(&sm, q, lane, tmem, t, true, key, code, p, S.rootw, sm.oth_chunk[warp], oth_bar0, oth_off0);
                     pos += 32;
                 }
