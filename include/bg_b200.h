@@ -253,6 +253,48 @@ int bg_ppo_loss_grad(const void* logits, int flags /* BG_LOSS_* */, long long ld
                      long long B, float eps_clip, float value_coef, float entropy_coef, void* dlogits, float* dvalues,
                      float* dbias /*nullable*/, float* sums, void* stream);
 
+/* N2  the linear algebra of one PPO epoch (agent/ppo_agent.py:268-305: forward of both layers, loss.backward()) as
+ * hand-written tcgen05 GEMMs (csrc/ppo_gemm.cu) -- no library GEMM on the update path.  The caller keeps the batch sorted
+ * by class: rows [0, n_a) = class A (1..128 legal slots, stored action among them), rows [n_a, B) = class B (passes, more
+ * slots).  bf16 row-major buffers: x [B][208] (K3's rows with column 198 = 1.0: the bias), h / dpre [B][128],
+ * logits / dlogits of class A [n_a][144] (slots 0..127, value head in column 128), of class B [B - n_a][512] (value head
+ * in column 500).  Row ranges are absolute rows of x / h / dpre; the class buffers are indexed from their own row 0, so
+ * pass them offset: e.g. LOGITS_B with A = h, out = logits_b - n_a * 512 (the kernel only touches rows in range).
+ *   bg_ppo_pack_weights: flat f32 master weights (fc1.weight, fc1.bias, action_head.weight, action_head.bias,
+ *     value_head.weight, value_head.bias: 90,101 floats) -> bf16 operand tiles w1p [26][128][8], wap_a [16][144][8],
+ *     wap_b [16][512][8] and the f32 bias rows bias_a [144], bias_b [512].
+ *   bg_ppo_gemm_nt(op): out = epilogue(A . W^T) for rows [row_begin, row_end):
+ *     HIDDEN   h = relu(x w1p^T);  LOGITS_A / _B  logits = h wap^T + bias;  DPRE_A / _B  dpre = (dlogits wap) * [h > 0]
+ *     (W = the matching tile; bias for the LOGITS ops; h_mask = h for the DPRE ops).
+ *   bg_ppo_gemm_tn(op): flat_grad += A^T . B over rows [row_begin, row_end) (f32 atomics; caller zeroes flat_grad):
+ *     GRAD_WA_A  A = h, B = dlogits_a -> action_head.weight[0..127], value_head.weight;  GRAD_WA_B  A = h, B = dlogits_b
+ *     -> action_head.weight, value_head.weight;  GRAD_W1  A = dpre, B = x -> fc1.weight, fc1.bias.
+ *   bg_ppo_loss_grad_classes: bg_ppo_loss_grad on the two class buffers (means over B; dbias [512]: columns 0..499 =
+ *     action_head.bias, 500 = value_head.bias).
+ *   bg_adam_step: torch.optim.Adam's update (ppo_agent.py:83) of the flat parameters, one kernel; step counts from 1;
+ *     grads are multiplied by grad_scale first (1 / world size after a summing all-reduce). */
+#define BG_PPO_OP_HIDDEN 0
+#define BG_PPO_OP_LOGITS_A 1
+#define BG_PPO_OP_LOGITS_B 2
+#define BG_PPO_OP_DPRE_A 3
+#define BG_PPO_OP_DPRE_B 4
+#define BG_PPO_OP_GRAD_WA_A 5
+#define BG_PPO_OP_GRAD_WA_B 6
+#define BG_PPO_OP_GRAD_W1 7
+#define BG_PPO_NUM_PARAMS 90101
+int bg_ppo_pack_weights(const float* flat_params, uint16_t* w1p, uint16_t* wap_a, uint16_t* wap_b, float* bias_a, float* bias_b,
+                        void* stream);
+int bg_ppo_gemm_nt(int op, const uint16_t* A, long long row_begin, long long row_end, const uint16_t* W, const float* bias,
+                   const uint16_t* h_mask, uint16_t* out, void* stream);
+int bg_ppo_gemm_tn(int op, const uint16_t* A, const uint16_t* B, long long row_begin, long long row_end, float* flat_grad,
+                   void* stream);
+int bg_ppo_loss_grad_classes(const void* logits_a, void* dlogits_a, const void* logits_b, void* dlogits_b, long long n_a, long long B,
+                             const int32_t* counts, const int32_t* actions, const float* old_log_probs, const float* advantages,
+                             const float* returns, float eps_clip, float value_coef, float entropy_coef, float* dbias /*[512]*/,
+                             float* sums /*[3]*/, void* stream);
+int bg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                 float beta2, float eps, int step, float grad_scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K5  2-ply search (the reference's own 2-ply, moves/expect_minmax.py:1-206, is
  * commented-out code, so the definition is the build's, on the reference's live primitives).

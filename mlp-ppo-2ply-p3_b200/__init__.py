@@ -12,7 +12,7 @@ from .engine import (FEATURES, LD_BF16, MovegenWorkspace, as_board52, encode, fr
 from .sharding import shard_range  # noqa: F401
 from .value_net import ValueNet  # noqa: F401
 from .policy_net import PolicyValueNet  # noqa: F401
-from .ppo import ManualUpdate, PPOConfig, PPOLearner, PPOTrainer, evaluate_vs_random  # noqa: F401
+from .ppo import ManualUpdate, PPOConfig, PPOLearner, PPOTrainer, TensorCoreUpdate, evaluate_vs_random  # noqa: F401
 from .twoply import TwoPlySearch, greedy_actions, segment_argmax  # noqa: F401
 from .single_env import BackgammonEnv, BoardView, Player  # noqa: F401
 from .vec_env import B200BackgammonVecEnv, HostStepBuffers, StepInfos, VectorizedBackgammonEnv  # noqa: F401

@@ -62,6 +62,11 @@ SIGNATURES = {
     "bg_policy_sample": (_I, [_V, _V, _I, _LL, _V, _V, _V, _V, _V, _V, _F, _U64, _U64, _U32, _I, _V, _V, _V, _V, _V, _SZ, _V]),
     "bg_gae": (_I, [_V, _V, _V, _V, _I, _LL, _F, _F, _V, _V, _V]),
     "bg_ppo_loss_grad": (_I, [_V, _I, _LL, _V, _V, _V, _V, _V, _V, _LL, _F, _F, _F, _V, _V, _V, _V, _V]),
+    "bg_ppo_pack_weights": (_I, [_V, _V, _V, _V, _V, _V, _V]),
+    "bg_ppo_gemm_nt": (_I, [_I, _V, _LL, _LL, _V, _V, _V, _V, _V]),
+    "bg_ppo_gemm_tn": (_I, [_I, _V, _V, _LL, _LL, _V, _V]),
+    "bg_ppo_loss_grad_classes": (_I, [_V, _V, _V, _V, _LL, _LL, _V, _V, _V, _V, _V, _F, _F, _F, _V, _V, _V]),
+    "bg_adam_step": (_I, [_V, _V, _V, _V, _LL, _F, _F, _F, _F, _I, _F, _V]),
     "bg_pack_w1": (_I, [_V, _V, _V, _V]),
     "bg_mlp_value": (_I, [_V, _V, _I, _I, _LL, _V, _V, _V, _V, _F, _I, _V, _V]),
 }

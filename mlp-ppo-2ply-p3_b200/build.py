@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbg_b200.so")
-SOURCES = ["capi.cu", "movegen.cu", "movegen_team.cu", "step.cu", "encode.cu", "refresh.cu", "mlp.cu", "policy.cu", "ppo.cu", "twoply.cu", "twoply_fused.cu"]
+SOURCES = ["capi.cu", "movegen.cu", "movegen_team.cu", "step.cu", "encode.cu", "refresh.cu", "mlp.cu", "policy.cu", "ppo.cu", "ppo_gemm.cu", "twoply.cu", "twoply_fused.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--use_fast_math=false"]
 

@@ -128,7 +128,7 @@ template <typename T>
 __device__ __forceinline__ void loss_packed_load(LossPacked<T>& d, long long r, long long B, int sub, const T* __restrict__ logits, long long ld,
                                                  const float* __restrict__ values, const int32_t* __restrict__ counts,
                                                  const int32_t* __restrict__ actions, const float* __restrict__ old_logp,
-                                                 const float* __restrict__ adv, const float* __restrict__ returns) {
+                                                 const float* __restrict__ adv, const float* __restrict__ returns, int value_col) {
     d.n = 0; d.a = 0; d.adv = 0.0f; d.old_logp = 0.0f; d.ret = 0.0f; d.v = 0.0f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) d.x[k] = Vec4<T>::zero();
@@ -138,7 +138,7 @@ __device__ __forceinline__ void loss_packed_load(LossPacked<T>& d, long long r, 
         for (int k = 0; k < 4; ++k) d.x[k] = Vec4<T>::load_raw(src + 16 * sub + 4 * k);     // (read whatever the row's class: no dependent load)
         d.n = __ldg(counts + r); d.a = __ldg(actions + r);
         d.adv = __ldg(adv + r); d.old_logp = __ldg(old_logp + r); d.ret = __ldg(returns + r);
-        d.v = values ? __ldg(values + r) : loss_scalar(src + BG_ACTIONS);
+        d.v = values ? __ldg(values + r) : loss_scalar(src + value_col);
     }
 }
 
@@ -147,7 +147,11 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
     const T* __restrict__ logits, long long ld, const float* __restrict__ values, const int32_t* __restrict__ counts,
     const int32_t* __restrict__ actions, const float* __restrict__ old_logp, const float* __restrict__ adv,
     const float* __restrict__ returns, long long B, float eps_clip, float value_coef, float entropy_coef,
-    T* __restrict__ dlogits, float* __restrict__ dvalues, float* __restrict__ dbias, float* __restrict__ sums, int prezeroed) {
+    T* __restrict__ dlogits, float* __restrict__ dvalues, float* __restrict__ dbias, float* __restrict__ sums, int prezeroed,
+    int value_col, long long B_norm) {
+    // value_col: column of the logits / dlogits row that carries the value head when values == NULL (500 in the 512-wide
+    // layout, 128 in the 144-wide class A layout of ppo_gemm.cu); B_norm: the batch size the means are taken over (this call
+    // may cover only a part of the batch)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & 7, grp = lane >> 3;
     __shared__ float s_part[kLossWarps][3];
     __shared__ float s_col[kLossWarps][129];                         // 128 slot columns + the value column
@@ -155,16 +159,16 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
     float colsum[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) colsum[k] = 0.0f;
-    const float invB = 1.0f / (float)B;
+    const float invB = 1.0f / (float)B_norm;
     const float ce = entropy_coef * invB;
     const long long S = (long long)gridDim.x * kLossWarps;          // persistent warps stride over groups of 4 rows
     long long g4 = (long long)blockIdx.x * kLossWarps + warp;
     LossPacked<T> nx;
-    loss_packed_load(nx, g4 * 4 + grp, B, sub, logits, ld, values, counts, actions, old_logp, adv, returns);
+    loss_packed_load(nx, g4 * 4 + grp, B, sub, logits, ld, values, counts, actions, old_logp, adv, returns, value_col);
 #pragma unroll 1
     for (; g4 * 4 < B; g4 += S) {
         const LossPacked<T> cur = nx;
-        loss_packed_load(nx, (g4 + S) * 4 + grp, B, sub, logits, ld, values, counts, actions, old_logp, adv, returns);
+        loss_packed_load(nx, (g4 + S) * 4 + grp, B, sub, logits, ld, values, counts, actions, old_logp, adv, returns, value_col);
         const long long row = g4 * 4 + grp;
         const bool act = row < B && loss_row_is_packed(cur.n, cur.a);
         const int n = act ? cur.n : 1, a = act ? cur.a : 0;         // (idle lanes compute on a finite dummy row)
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
             if (!prezeroed) {
                 for (int c = 128 + 4 * sub; c < ld; c += 32) {
                     float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                    if (!values && c == BG_ACTIONS) { x[0] = dvalue; vsum += dvalue; }
+                    if (!values && c == value_col) { x[0] = dvalue; vsum += dvalue; }
                     Vec4<T>::store(dst + c, x);
                 }
             } else if (!values && sub >= 4) {
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
 #pragma unroll
         for (int k = 0; k < 16; ++k) s_col[warp][16 * sub + k] = colsum[k];
     }
-    if (lane == 5) s_col[warp][128] = vsum;                          // (BG_ACTIONS - 128) % 32 == 4 * 5: lane group 5 writes column 500
+    if (lane == ((value_col - 128) & 31) >> 2) s_col[warp][128] = vsum;   // the lane group that wrote the value column (500: group 5, 128: group 0)
     __syncthreads();
     if (threadIdx.x < 3) {
         float t = 0.0f;
@@ -281,7 +285,8 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_kernel(
     const T* __restrict__ logits, long long ld, const float* __restrict__ values, const int32_t* __restrict__ counts,
     const int32_t* __restrict__ actions, const float* __restrict__ old_logp, const float* __restrict__ adv,
     const float* __restrict__ returns, long long B, float eps_clip, float value_coef, float entropy_coef,
-    T* __restrict__ dlogits, float* __restrict__ dvalues, float* __restrict__ dbias, float* __restrict__ sums, int all_rows) {
+    T* __restrict__ dlogits, float* __restrict__ dvalues, float* __restrict__ dbias, float* __restrict__ sums, int all_rows,
+    long long B_norm) {
     constexpr float kMaskLog = -103.27893f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ float s_part[kLossWarps][3];
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_kernel(
     float colsum[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) colsum[k] = 0.0f;
-    const float invB = 1.0f / (float)B;
+    const float invB = 1.0f / (float)B_norm;
     const float ce = entropy_coef * invB;
     const long long S = (long long)gridDim.x * kLossWarps;          // persistent warps stride over blocks of 32 rows
     // This kernel handles the rows the packed kernel leaves out (loss_row_is_packed: passes, more than 128 legal slots, an
@@ -458,20 +463,49 @@ extern "C" int bg_ppo_loss_grad(const void* logits, int flags, long long ld, con
         if (!general_only)
             bg::ppo_loss_grad_packed_kernel<__nv_bfloat16><<<grid_p, bg::kLossWarps * 32, 0, st>>>(
                 (const __nv_bfloat16*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
-                entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums, prezeroed);
+                entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums, prezeroed, BG_ACTIONS, B);
         bg::ppo_loss_grad_kernel<__nv_bfloat16><<<grid_g, bg::kLossWarps * 32, 0, st>>>(
             (const __nv_bfloat16*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
-            entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums, general_only);
+            entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums, general_only, B);
     } else {
         if (!general_only)
             bg::ppo_loss_grad_packed_kernel<float><<<grid_p, bg::kLossWarps * 32, 0, st>>>(
                 (const float*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
-                entropy_coef, (float*)dlogits, dvalues, dbias, sums, prezeroed);
+                entropy_coef, (float*)dlogits, dvalues, dbias, sums, prezeroed, BG_ACTIONS, B);
         bg::ppo_loss_grad_kernel<float><<<grid_g, bg::kLossWarps * 32, 0, st>>>(
             (const float*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
-            entropy_coef, (float*)dlogits, dvalues, dbias, sums, general_only);
+            entropy_coef, (float*)dlogits, dvalues, dbias, sums, general_only, B);
     }
     return bg_set_error(cudaGetLastError(), "bg_ppo_loss_grad: launch");
+}
+
+// The loss over a batch that ppo_gemm.cu keeps sorted by class: rows [0, n_a) in the 144-column class A layout (128 slots,
+// value head in column 128) through the packed kernel, rows [n_a, B) in the 512-column layout (value head in column 500)
+// through the general kernel; every mean is taken over B.  bf16 logits / dlogits, value head inside the logits.
+extern "C" int bg_ppo_loss_grad_classes(const void* logits_a, void* dlogits_a, const void* logits_b, void* dlogits_b, long long n_a,
+                                        long long B, const int32_t* counts, const int32_t* actions, const float* old_log_probs,
+                                        const float* advantages, const float* returns, float eps_clip, float value_coef,
+                                        float entropy_coef, float* dbias, float* sums, void* stream) {
+    if (B < 0 || n_a < 0 || n_a > B) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_loss_grad_classes: bad sizes");
+    if (B == 0) return BG_OK;
+    if (!counts || !actions || !old_log_probs || !advantages || !returns || !sums || (n_a > 0 && (!logits_a || !dlogits_a)) ||
+        (n_a < B && (!logits_b || !dlogits_b)))
+        return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_loss_grad_classes: null pointer");
+    const long long resident = (long long)bg_sm_count() * 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_a > 0) {
+        const long long need = (n_a + 4 * bg::kLossWarps - 1) / (4 * bg::kLossWarps);
+        bg::ppo_loss_grad_packed_kernel<__nv_bfloat16><<<(unsigned)(need < resident ? need : resident), bg::kLossWarps * 32, 0, st>>>(
+            (const __nv_bfloat16*)logits_a, 144, nullptr, counts, actions, old_log_probs, advantages, returns, n_a, eps_clip, value_coef,
+            entropy_coef, (__nv_bfloat16*)dlogits_a, nullptr, dbias, sums, 0, 128, B);
+    }
+    if (n_a < B) {
+        const long long nb = B - n_a, need = (nb + 32 * bg::kLossWarps - 1) / (32 * bg::kLossWarps);
+        bg::ppo_loss_grad_kernel<__nv_bfloat16><<<(unsigned)(need < resident ? need : resident), bg::kLossWarps * 32, 0, st>>>(
+            (const __nv_bfloat16*)logits_b, 512, nullptr, counts + n_a, actions + n_a, old_log_probs + n_a, advantages + n_a, returns + n_a,
+            nb, eps_clip, value_coef, entropy_coef, (__nv_bfloat16*)dlogits_b, nullptr, dbias, sums, 1, B);
+    }
+    return bg_set_error(cudaGetLastError(), "bg_ppo_loss_grad_classes: launch");
 }
 
 extern "C" int bg_gae(const float* rewards, const uint8_t* dones, const float* values, const float* last_values, int T,

@@ -1,0 +1,414 @@
+// ppo_gemm.cu -- N2: the GEMMs of the PPO update on the tcgen05 tensor cores, hand-written (no cuBLAS on the update path).
+//
+// Replaces, for one epoch over B samples, the linear algebra of BackgammonPPOAgent.update (src/agent/ppo_agent.py:268-305:
+// policy_network forward, loss.backward()) around the loss kernel of ppo.cu:
+//     h      = relu(x W1p^T)                    bg_ppo_gemm_nt(HIDDEN)        x (B,208) bf16 = K3's rows, column 198 = 1 (bias)
+//     logits = h Wap^T + b                      bg_ppo_gemm_nt(LOGITS_A / _B)
+//     dpre   = (dlogits Wap) * [h > 0]          bg_ppo_gemm_nt(DPRE_A / _B)
+//     dWap  += dlogits^T h                      bg_ppo_gemm_tn(GRAD_WA_A / _B)
+//     dW1p  += dpre^T x                         bg_ppo_gemm_tn(GRAD_W1)
+// The work follows the action mask, as in the policy kernel: the caller sorts the samples into class A (1..128 legal slots
+// and the stored action among them: ~94 % of a self-play batch, mean 18 legal slots) and class B (passes -- the reference's
+// arithmetic is a softmax over all 500 slots -- and > 128 slots).  Class A rows only ever touch action slots 0..127, so
+// their logits / dlogits are 144 columns wide (128 slots, the value head in column 128, zero padding) instead of 512:
+// a quarter of the head's FLOPs and of its HBM traffic.  Class B rows use the full 512-column layout (value in column 500).
+//
+// Operands are staged in shared memory in ONE physical layout, 16-byte chunks [column / 8][row][8 columns] (the tcgen05
+// no-swizzle "interleave"), which serves both majors: read as K-major (rows = M or N, columns = K: LBO = chunk stride,
+// SBO = 128) for the forward GEMMs, and as MN-major (columns = M or N, rows = K: SBO = chunk stride, LBO = 128) for the
+// transposed products -- dlogits^T h, dpre^T x and dlogits Wap all read the very same tiles without a transpose.
+// Both operands come from shared memory (tcgen05.mma SS form), accumulators live in TMEM; the kernels are HBM-bound
+// (they stream 0.3 .. 1 KB per sample), so the pipeline is a plain double buffer: cp.async of stage i+1 while the
+// MMAs of stage i run, epilogue out of TMEM.
+#include <cuda_bf16.h>
+#include "bg_device.cuh"
+#include "bg_tcgen05.cuh"
+#include "bg_internal.h"
+
+namespace bg {
+namespace {
+
+constexpr int kGT = 256;                 // threads per CTA
+constexpr int kRows = 128;               // sample rows per tile = UMMA M (NT) / UMMA K per tile (TN)
+constexpr int kChunk = kRows * 16;       // bytes of one 16-byte-chunk column of a 128-row tile
+
+// flat parameter / gradient layout (policy_net.KEYS order, agent/policy_network.py:44-56)
+constexpr int kOffW1 = 0, kOffB1 = 128 * 198, kOffWa = kOffB1 + 128, kOffBa = kOffWa + 500 * 128, kOffWv = kOffBa + 500,
+              kOffBv = kOffWv + 128, kNumParams = kOffBv + 1;
+static_assert(kNumParams == 90101, "flat parameter layout");
+
+__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16; a_mn / b_mn = 1: the operand is MN-major (bits 15 / 16)
+__device__ __forceinline__ uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u : (n <= 64 ? 64u : (n <= 128 ? 128u : (n <= 256 ? 256u : 512u))); }
+
+// rows [row0, row0 + 128) x columns [col0, col0 + 8 nch) of a row-major bf16 matrix -> the chunk layout at `dst` (shared address).
+// A warp moves 8 rows x 4 chunks per instruction: 64 contiguous bytes per row in global memory, 128 contiguous bytes per
+// chunk column in shared memory.  Rows >= row_end are zero-filled.
+__device__ __forceinline__ void stage_tile(uint32_t dst, unsigned char* dst_generic, const uint16_t* __restrict__ src, long long ld,
+                                           long long row0, long long row_end, int col0, int nch, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int cblocks = (nch + 3) >> 2;
+    for (int u = warp; u < 16 * cblocks; u += kGT / 32) {
+        const int rb = u & 15, cb = u >> 4;
+        const int r = 8 * rb + (lane & 7), c8 = 4 * cb + (lane >> 3);
+        if (c8 < nch) {
+            const long long row = row0 + r;
+            const uint32_t off = (uint32_t)(c8 * kChunk + r * 16);
+            if (row < row_end) cp_async16_s(dst + off, src + row * ld + col0 + 8 * c8);
+            else *reinterpret_cast<uint4*>(dst_generic + off) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// C[rows x N] = epilogue( A[rows x K] . W^T ),  M = 128 rows per tile
+struct NtArgs {
+    const uint16_t* A; long long lda;          // source rows (global, bf16), rows [row_begin, row_end)
+    long long row_begin, row_end;
+    const uint16_t* W; int w_bytes; int w_rows;   // packed weight tile (chunk layout) and its number of rows
+    int N, K, KC;                              // output columns (<= 512), reduction length, K per stage (K % KC == 0, KC % 16 == 0)
+    int b_mn;                                  // 0: W rows = N, columns = K (K-major B);  1: W rows = K, columns = N = 128 (MN-major B)
+    int epi;                                   // 0 relu, 1 + bias, 2 * [mask > 0]
+    const float* bias; const uint16_t* mask; long long ldm;
+    uint16_t* out; long long ldo;
+};
+
+__global__ void __launch_bounds__(kGT, 1) ppo_gemm_nt_kernel(const NtArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ unsigned long long bar[2];
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int stage_bytes = (a.KC >> 3) * kChunk;
+    unsigned char* Wg = smem;
+    unsigned char* Ag[2] = {smem + ((a.w_bytes + 1023) & ~1023), smem + ((a.w_bytes + 1023) & ~1023) + stage_bytes};
+    const uint32_t Ws = smem_u32(Wg), As[2] = {smem_u32(Ag[0]), smem_u32(Ag[1])};
+    for (int c = tid; c < a.w_bytes / 16; c += kGT) cp_async16_s(Ws + 16u * c, reinterpret_cast<const unsigned char*>(a.W) + 16 * c);
+    cp_async_commit();
+    if (tid == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    const uint32_t ncols = tmem_cols_for(a.N);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(&s_tmem)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const long long n_tiles = (a.row_end - a.row_begin + kRows - 1) / kRows;
+    const int n_kc = a.K / a.KC, nch = a.KC >> 3;
+    // steps of this CTA: (tile, K chunk), tiles blockIdx.x, + gridDim.x, ...
+    long long my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long n_steps = my_tiles * n_kc;
+    auto step_tile = [&](long long s) { return blockIdx.x + (s / n_kc) * gridDim.x; };
+    auto load = [&](long long s, int b) {
+        const long long row0 = a.row_begin + step_tile(s) * kRows;
+        stage_tile(As[b], Ag[b], a.A, a.lda, row0, a.row_end, (int)(s % n_kc) * a.KC, nch, tid);
+        cp_async_commit();
+    };
+    uint32_t ph[2] = {0u, 0u};
+    bool pending[2] = {false, false};
+    auto ensure_done = [&](int b) { if (pending[b]) { mbar_wait(&bar[b], ph[b]); ph[b] ^= 1u; pending[b] = false; } };
+    const int q = warp & 3, half = warp >> 2;
+    if (n_steps > 0) load(0, 0);
+    for (long long s = 0; s < n_steps; ++s) {
+        const int b = (int)(s & 1);
+        const int kc = (int)(s % n_kc);
+        cp_async_wait_all();                                           // this thread's share of stage s (and of W) has landed
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); // ... and is visible to the tensor-core proxy
+        __syncthreads();
+        ensure_done(b ^ 1);                                            // the MMAs that read the other buffer (stage s-1)
+        if (s + 1 < n_steps) load(s + 1, b ^ 1);
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            for (int ks = 0; ks < a.KC / 16; ++ks) {
+                const int kg = kc * a.KC + ks * 16;                    // first reduction index of this MMA
+                const uint64_t da = make_smem_desc_kmajor(As[b] + (uint32_t)(ks * 2 * kChunk), kChunk, 128);
+                const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
+                if (a.b_mn) {
+                    // W rows = reduction index (action slots), columns = N = 128 hidden units: MN-major, K groups 128 B apart
+                    const uint64_t db = make_smem_desc_kmajor(Ws + (uint32_t)(kg * 16), 128, (uint32_t)(a.w_rows * 16));
+                    mma_bf16_ss(tmem, da, db, idesc_bf16(128, a.N, 0, 1), acc);
+                } else {
+                    for (int n0 = 0; n0 < a.N; n0 += 256) {
+                        const int nn = a.N - n0 < 256 ? a.N - n0 : 256;
+                        const uint64_t db = make_smem_desc_kmajor(Ws + (uint32_t)((kg >> 3) * a.w_rows * 16 + n0 * 16), (uint32_t)(a.w_rows * 16), 128);
+                        mma_bf16_ss(tmem + (uint32_t)n0, da, db, idesc_bf16(128, nn, 0, 0), acc);
+                    }
+                }
+            }
+            umma_commit(&bar[b]);
+        }
+        pending[b] = true;
+        if (kc == n_kc - 1) {
+            // ---- epilogue of the tile: thread = row (TMEM lane), the two warps of a lane quarter split the columns
+            ensure_done(b);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const long long row = a.row_begin + step_tile(s) * kRows + q * 32 + lane;
+            const bool live = row < a.row_end;
+            const int nblk = (a.N + 31) >> 5;                          // blocks of 32 columns (the last may be 16 wide: N = 144)
+            for (int blk = half; blk < nblk; blk += 2) {
+                const int c0 = 32 * blk, w = a.N - c0 < 32 ? a.N - c0 : 32;
+                uint32_t acc[32];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                if (w == 32) tmem_ld32(taddr, acc);
+                else { tmem_ld8(taddr, acc); tmem_ld8(taddr + 8, acc + 8); }       // w == 16
+                tmem_ld_wait();
+                if (live) {
+                    uint32_t mk[16];
+                    if (a.epi == 2) {
+                        const uint4* mp = reinterpret_cast<const uint4*>(a.mask + row * a.ldm + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) { const uint4 v = (4 * j * 2 < w) ? __ldg(mp + j) : make_uint4(0u, 0u, 0u, 0u); mk[4 * j] = v.x; mk[4 * j + 1] = v.y; mk[4 * j + 2] = v.z; mk[4 * j + 3] = v.w; }
+                    }
+                    uint32_t o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float v0 = __uint_as_float(acc[2 * j]), v1 = __uint_as_float(acc[2 * j + 1]);
+                        if (a.epi == 0) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+                        else if (a.epi == 1) { if (2 * j < w) { v0 += __ldg(a.bias + c0 + 2 * j); v1 += __ldg(a.bias + c0 + 2 * j + 1); } }
+                        else {                                                       // relu'(h): h is bf16 >= 0, so "> 0" is "!= 0"
+                            if ((mk[j] & 0x0000FFFFu) == 0u) v0 = 0.0f;
+                            if ((mk[j] & 0xFFFF0000u) == 0u) v1 = 0.0f;
+                        }
+                        o[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v1)) << 16);
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(a.out + row * a.ldo + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (8 * j < w) op[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncthreads();                                           // everybody has read the accumulators: the next tile may overwrite them
+        }
+    }
+    ensure_done(0); ensure_done(1);
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(ncols) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// G[128 x N] += A[rows x 128]^T . B[rows x N]   (split over the sample rows across the CTAs; f32 atomics into the flat gradient)
+struct TnArgs {
+    const uint16_t* A; long long lda;          // rows x 128 (hidden units: h or dpre)
+    const uint16_t* B; long long ldb; int N;   // rows x N  (dlogits or x); N % 16 == 0, <= 256
+    long long row_begin, row_end;
+    int mode;                                  // 0 dWap class A (N = 144: 128 slots, value head at column 128), 1 dWap class B (slot = col_base + n), 2 dW1p (N = 208)
+    int col_base;
+    float* grad;                               // flat f32 gradient (kNumParams)
+};
+
+__global__ void __launch_bounds__(kGT, 1) ppo_gemm_tn_kernel(const TnArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ unsigned long long bar[2];
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int a_bytes = 16 * kChunk, b_bytes = (a.N >> 3) * kChunk;
+    unsigned char* Ag[2] = {smem, smem + a_bytes + b_bytes};
+    unsigned char* Bg[2] = {smem + a_bytes, smem + 2 * a_bytes + b_bytes};
+    const uint32_t As[2] = {smem_u32(Ag[0]), smem_u32(Ag[1])}, Bs[2] = {smem_u32(Bg[0]), smem_u32(Bg[1])};
+    if (tid == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    const uint32_t ncols = tmem_cols_for(a.N);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(&s_tmem)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const long long n_tiles = (a.row_end - a.row_begin + kRows - 1) / kRows;
+    const long long n_steps = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto load = [&](long long s, int b) {
+        const long long row0 = a.row_begin + (blockIdx.x + s * gridDim.x) * kRows;
+        stage_tile(As[b], Ag[b], a.A, a.lda, row0, a.row_end, 0, 16, tid);
+        stage_tile(Bs[b], Bg[b], a.B, a.ldb, row0, a.row_end, 0, a.N >> 3, tid);
+        cp_async_commit();
+    };
+    uint32_t ph[2] = {0u, 0u};
+    bool pending[2] = {false, false};
+    auto ensure_done = [&](int b) { if (pending[b]) { mbar_wait(&bar[b], ph[b]); ph[b] ^= 1u; pending[b] = false; } };
+    if (n_steps > 0) load(0, 0);
+    const uint32_t idesc = idesc_bf16(128, a.N, 1, 1);
+    for (long long s = 0; s < n_steps; ++s) {
+        const int b = (int)(s & 1);
+        cp_async_wait_all();
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncthreads();
+        ensure_done(b ^ 1);
+        if (s + 1 < n_steps) load(s + 1, b ^ 1);
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll 1
+            for (int ks = 0; ks < kRows / 16; ++ks) {
+                // both tiles are read MN-major: the reduction index is the ROW (sample); 16 rows = two 8-row groups 128 B apart
+                const uint64_t da = make_smem_desc_kmajor(As[b] + (uint32_t)(ks * 256), 128, kChunk);
+                const uint64_t db = make_smem_desc_kmajor(Bs[b] + (uint32_t)(ks * 256), 128, kChunk);
+                mma_bf16_ss(tmem, da, db, idesc, (s > 0 || ks > 0) ? 1u : 0u);
+            }
+            umma_commit(&bar[b]);
+        }
+        pending[b] = true;
+    }
+    ensure_done(0); ensure_done(1);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (n_steps > 0) {
+        // accumulator: lane = hidden unit m, column = n.  Thread = (m, half of the columns).
+        const int q = warp & 3, half = warp >> 2;
+        const int m = q * 32 + lane;
+        const int nblk = a.N >> 3;
+        for (int blk = half; blk < nblk; blk += 2) {
+            uint32_t acc[8];
+            tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(8 * blk), acc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = 8 * blk + j;
+                const float v = __uint_as_float(acc[j]);
+                float* dst = nullptr;
+                if (a.mode == 0) { if (n < 128) dst = a.grad + kOffWa + n * 128 + m; else if (n == 128) dst = a.grad + kOffWv + m; }
+                else if (a.mode == 1) { const int slot = a.col_base + n; if (slot < 500) dst = a.grad + kOffWa + slot * 128 + m; else if (slot == 500) dst = a.grad + kOffWv + m; }
+                else { if (n < 198) dst = a.grad + kOffW1 + m * 198 + n; else if (n == 198) dst = a.grad + kOffB1 + m; }
+                if (dst) atomicAdd(dst, v);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(ncols) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 operand tiles (chunk layout [k / 8][row][8]) and f32 bias rows from the flat f32 master weights
+__global__ void ppo_pack_kernel(const float* __restrict__ p, uint16_t* __restrict__ w1p, uint16_t* __restrict__ wap_a,
+                                uint16_t* __restrict__ wap_b, float* __restrict__ bias_a, float* __restrict__ bias_b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    auto bf = [](float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); };
+    if (i < 128 * 208) {                                              // W1p: rows = hidden units, K = 208 (198 features, bias, zeros)
+        const int n = i / 208, k = i - n * 208;
+        const float v = k < 198 ? p[kOffW1 + n * 198 + k] : (k == 198 ? p[kOffB1 + n] : 0.0f);
+        w1p[(k >> 3) * (128 * 8) + n * 8 + (k & 7)] = bf(v);
+    }
+    if (i < 144 * 128) {                                              // class A head: 128 slots, the value head as row 128, zeros
+        const int s = i >> 7, k = i & 127;
+        const float v = s < 128 ? p[kOffWa + s * 128 + k] : (s == 128 ? p[kOffWv + k] : 0.0f);
+        wap_a[(k >> 3) * (144 * 8) + s * 8 + (k & 7)] = bf(v);
+    }
+    if (i < 512 * 128) {                                              // class B head: 500 slots, the value head as row 500, zeros
+        const int s = i >> 7, k = i & 127;
+        const float v = s < 500 ? p[kOffWa + s * 128 + k] : (s == 500 ? p[kOffWv + k] : 0.0f);
+        wap_b[(k >> 3) * (512 * 8) + s * 8 + (k & 7)] = bf(v);
+    }
+    if (i < 144) bias_a[i] = i < 128 ? p[kOffBa + i] : (i == 128 ? p[kOffBv] : 0.0f);
+    if (i < 512) bias_b[i] = i < 500 ? p[kOffBa + i] : (i == 500 ? p[kOffBv] : 0.0f);
+}
+
+// torch.optim.Adam (no weight decay, no amsgrad): one thread per parameter (ppo_agent.py:83,301-305)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int n,
+                            float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+}
+
+}  // namespace
+}  // namespace bg
+
+using namespace bg;
+
+extern "C" int bg_ppo_pack_weights(const float* flat_params, uint16_t* w1p, uint16_t* wap_a, uint16_t* wap_b, float* bias_a,
+                                   float* bias_b, void* stream) {
+    if (!flat_params || !w1p || !wap_a || !wap_b || !bias_a || !bias_b) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_pack_weights: null pointer");
+    ppo_pack_kernel<<<(512 * 128 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(flat_params, w1p, wap_a, wap_b, bias_a, bias_b);
+    return bg_set_error(cudaGetLastError(), "bg_ppo_pack_weights: launch");
+}
+
+extern "C" int bg_ppo_gemm_nt(int op, const uint16_t* A, long long row_begin, long long row_end, const uint16_t* W,
+                              const float* bias, const uint16_t* h_mask, uint16_t* out, void* stream) {
+    if (row_begin < 0 || row_end < row_begin) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: bad row range");
+    if (row_end == row_begin) return BG_OK;
+    if (!A || !W || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: null pointer");
+    NtArgs a{};
+    a.A = A; a.row_begin = row_begin; a.row_end = row_end; a.W = W; a.bias = bias; a.mask = h_mask; a.ldm = 128; a.out = out;
+    switch (op) {
+        case BG_PPO_OP_HIDDEN:   a.lda = 208; a.N = 128; a.K = 208; a.KC = 208; a.w_rows = 128; a.b_mn = 0; a.epi = 0; a.ldo = 128; break;
+        case BG_PPO_OP_LOGITS_A: a.lda = 128; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 1; a.ldo = 144; break;
+        case BG_PPO_OP_LOGITS_B: a.lda = 128; a.N = 512; a.K = 128; a.KC = 128; a.w_rows = 512; a.b_mn = 0; a.epi = 1; a.ldo = 512; break;
+        case BG_PPO_OP_DPRE_A:   a.lda = 144; a.N = 128; a.K = 144; a.KC = 144; a.w_rows = 144; a.b_mn = 1; a.epi = 2; a.ldo = 128; break;
+        case BG_PPO_OP_DPRE_B:   a.lda = 512; a.N = 128; a.K = 512; a.KC = 128; a.w_rows = 512; a.b_mn = 1; a.epi = 2; a.ldo = 128; break;
+        default: return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: unknown op");
+    }
+    if (a.epi == 1 && !bias) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: the logits ops need the bias row");
+    if (a.epi == 2 && !h_mask) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: the dpre ops need h");
+    a.w_bytes = (op == BG_PPO_OP_HIDDEN ? 26 : 16) * a.w_rows * 16;
+    const size_t smem = ((size_t)(a.w_bytes + 1023) & ~(size_t)1023) + 2 * (size_t)(a.KC >> 3) * kChunk;
+    cudaError_t e = cudaFuncSetAttribute(ppo_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return bg_set_error(e, "bg_ppo_gemm_nt: cudaFuncSetAttribute");
+    const long long tiles = (row_end - row_begin + kRows - 1) / kRows;
+    long long grid = (long long)bg_sm_count() * (smem <= 100 * 1024 ? 2 : 1);
+    if (grid > tiles) grid = tiles;
+    ppo_gemm_nt_kernel<<<(unsigned)grid, kGT, smem, (cudaStream_t)stream>>>(a);
+    return bg_set_error(cudaGetLastError(), "bg_ppo_gemm_nt: launch");
+}
+
+extern "C" int bg_ppo_gemm_tn(int op, const uint16_t* A, const uint16_t* B, long long row_begin, long long row_end,
+                              float* flat_grad, void* stream) {
+    if (row_begin < 0 || row_end < row_begin) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_tn: bad row range");
+    if (row_end == row_begin) return BG_OK;
+    if (!A || !B || !flat_grad) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_tn: null pointer");
+    cudaError_t e = cudaFuncSetAttribute(ppo_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return bg_set_error(e, "bg_ppo_gemm_tn: cudaFuncSetAttribute");
+    const long long tiles = (row_end - row_begin + kRows - 1) / kRows;
+    auto launch = [&](TnArgs a) -> int {
+        const size_t smem = 2 * ((size_t)16 * kChunk + (size_t)(a.N >> 3) * kChunk);
+        long long grid = (long long)bg_sm_count() * (smem <= 100 * 1024 ? 2 : 1);
+        if (grid > tiles) grid = tiles;
+        ppo_gemm_tn_kernel<<<(unsigned)grid, kGT, smem, (cudaStream_t)stream>>>(a);
+        return bg_set_error(cudaGetLastError(), "bg_ppo_gemm_tn: launch");
+    };
+    TnArgs a{};
+    a.A = A; a.lda = 128; a.B = B; a.row_begin = row_begin; a.row_end = row_end; a.grad = flat_grad;
+    switch (op) {
+        case BG_PPO_OP_GRAD_WA_A: a.ldb = 144; a.N = 144; a.mode = 0; return launch(a);
+        case BG_PPO_OP_GRAD_W1:   a.ldb = 208; a.N = 208; a.mode = 2; return launch(a);
+        case BG_PPO_OP_GRAD_WA_B:
+            for (int cb = 0; cb < 4; ++cb) {                          // four blocks of 128 action slots (value head = slot 500, in the last)
+                a.ldb = 512; a.N = 128; a.mode = 1; a.col_base = 128 * cb; a.B = B + 128 * cb;
+                const int rc = launch(a);
+                if (rc != BG_OK) return rc;
+            }
+            return BG_OK;
+        default: return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_tn: unknown op");
+    }
+}
+
+extern "C" int bg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                            float beta2, float eps, int step, float grad_scale, void* stream) {
+    if (n < 0 || step < 1) return bg_set_error_msg(BG_ERR_INVALID, "bg_adam_step: bad n / step (step counts from 1)");
+    if (n == 0) return BG_OK;
+    if (!params || !grads || !exp_avg || !exp_avg_sq) return bg_set_error_msg(BG_ERR_INVALID, "bg_adam_step: null pointer");
+    const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, (int)n, lr, beta1, beta2,
+                                                                             eps, bc1, sqrtf(bc2), grad_scale);
+    return bg_set_error(cudaGetLastError(), "bg_adam_step: launch");
+}

@@ -53,7 +53,9 @@ class PPOConfig:                                   # src/agent/config.py:4-22
     returns_mode: str = "per_game"                 # or "interleaved" (the reference's walk, for parity tests)
     reset_each_update: bool = False                # reference: True (train.py:40)
     autocast: bool = True
-    manual_backward: bool = True                   # CUDA + autocast: ManualUpdate (explicit GEMMs) instead of torch autograd
+    manual_backward: bool = True                   # CUDA + autocast: explicit GEMMs + bg_ppo_loss_grad instead of torch autograd
+    update_impl: str = "tcgen05"                   # the explicit path's GEMMs: "tcgen05" = our kernels (TensorCoreUpdate, with our Adam
+                                                   # kernel), "cublas" = library GEMMs (ManualUpdate, torch.optim.Adam): kept for comparison
 
 
 # --------------------------------------------------------------------------------------------- pure torch math
@@ -219,6 +221,114 @@ class ManualUpdate:
         return torch.stack([m[0], m[1], m[2], m[0] + value_coef * m[1] - entropy_coef * m[2]])
 
 
+class TensorCoreUpdate:
+    """One epoch of BackgammonPPOAgent.update (ppo_agent.py:268-305: forward, loss, backward) with NO library GEMM: every
+    product runs on the tcgen05 tensor cores in kernels of ours (csrc/ppo_gemm.cu) around the loss kernels of csrc/ppo.cu.
+
+    The work follows the action mask: the samples are sorted once per rollout into class A (1..128 legal slots and the
+    stored action among them -- ~94 % of a self-play batch) and class B (passes, whose reference arithmetic is a softmax over
+    all 500 slots, and rows with more slots).  Class A rows only touch slots 0..127, so their logits / dlogits are 144
+    columns wide (128 slots + the value head in column 128) instead of 512: a quarter of the head's FLOPs and traffic.
+
+        h       = relu(x W1p^T)                                   bg_ppo_gemm_nt HIDDEN      (fc1.bias rides in column 198 of x)
+        logits  = h Wap^T + b          per class                   bg_ppo_gemm_nt LOGITS_A / _B (value head = one more row of Wap)
+        dlogits = d loss / d logits    per class                   bg_ppo_loss_grad_classes
+        dpre    = (dlogits Wap) [h>0]  per class                   bg_ppo_gemm_nt DPRE_A / _B
+        dWap   += dlogits^T h          per class                   bg_ppo_gemm_tn GRAD_WA_A / _B   -> flat f32 gradient
+        dW1p   += dpre^T x                                         bg_ppo_gemm_tn GRAD_W1
+    """
+
+    ONE_COL = 198
+
+    def __init__(self, device):
+        self.device = device
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
+        self.w1p, self.wap_a, self.wap_b = z((26 * 128 * 8,), torch.bfloat16), z((16 * 144 * 8,), torch.bfloat16), z((16 * 512 * 8,), torch.bfloat16)
+        self.bias_a, self.bias_b = z((144,), torch.float32), z((512,), torch.float32)
+        self.gflat, self.pflat = z((90101,), torch.float32), z((90101,), torch.float32)
+        self.dbias, self.sums = z((512,), torch.float32), z((3,), torch.float32)
+        self.B = -1
+        self._sorted_key = None
+
+    # the class of a sample: csrc/ppo.cu loss_row_is_packed
+    @staticmethod
+    def class_a(counts, actions):
+        return (counts >= 1) & (counts <= 128) & (actions >= 0) & (actions < counts)
+
+    def sort_by_class(self, counts, actions):
+        """-> (perm (B,) i64: class A rows first, original order inside a class; n_a).  One host read (n_a)."""
+        a = self.class_a(counts, actions)
+        perm = torch.argsort((~a).to(torch.int8), stable=True)
+        return perm, int(a.sum().item())
+
+    def _buffers(self, B, n_a):
+        if B != self.B:
+            e = lambda shape: torch.empty(shape, dtype=torch.bfloat16, device=self.device)
+            self.h, self.dpre = e((B, 128)), e((B, 128))
+            self.la, self.dla = e((B, 144)), e((B, 144))              # class A logits / dlogits (rows [0, n_a))
+            self.B = B
+            self.lb = self.dlb = None
+        nb = B - n_a
+        if self.lb is None or self.lb.shape[0] < nb:
+            cap = max(nb, B // 8, 1)
+            self.lb = torch.empty((cap, 512), dtype=torch.bfloat16, device=self.device)
+            self.dlb = torch.empty((cap, 512), dtype=torch.bfloat16, device=self.device)
+
+    @torch.no_grad()
+    def epoch(self, params, grads, x, counts, actions, old_logp, adv, returns, eps_clip, value_coef, entropy_coef, n_a=None,
+              flat_params=None, flat_grads=None):
+        """Same contract as ManualUpdate.epoch.  n_a: the rows are already sorted by class (class A = rows [0, n_a)); None =
+        sort here (a gather of every per-sample array: the learner does it once per rollout instead).  flat_params /
+        flat_grads: the learner's flat f32 buffers (KEYS order) -- read / written in place instead of through the dicts."""
+        B = x.shape[0]
+        if n_a is None:
+            perm, n_a = self.sort_by_class(counts, actions)
+            x, counts, actions = x[perm].contiguous(), counts[perm].contiguous(), actions[perm].contiguous()
+            old_logp, adv, returns = old_logp[perm].contiguous(), adv[perm].contiguous(), returns[perm].contiguous()
+        self._buffers(B, n_a)
+        L = lib()
+        if flat_params is None:
+            o = 0
+            for k in KEYS:
+                n = params[k].numel()
+                self.pflat[o:o + n].copy_(params[k].reshape(-1))
+                o += n
+            flat_params = self.pflat
+        gflat = flat_grads if flat_grads is not None else self.gflat
+        gflat.zero_(); self.dbias.zero_(); self.sums.zero_()
+        st = _stream()
+        xp, hp, dp = x.data_ptr(), self.h.data_ptr(), self.dpre.data_ptr()
+        # class B buffers are indexed from their own row 0: pass them offset by -n_a rows (only rows in range are touched)
+        lb_off, dlb_off = self.lb.data_ptr() - n_a * 512 * 2, self.dlb.data_ptr() - n_a * 512 * 2
+        with torch.cuda.device(self.device):
+            check(L.bg_ppo_pack_weights(flat_params.data_ptr(), self.w1p.data_ptr(), self.wap_a.data_ptr(), self.wap_b.data_ptr(),
+                                        self.bias_a.data_ptr(), self.bias_b.data_ptr(), st), "bg_ppo_pack_weights")
+            check(L.bg_ppo_gemm_nt(0, xp, 0, B, self.w1p.data_ptr(), None, None, hp, st), "ppo gemm HIDDEN")
+            check(L.bg_ppo_gemm_nt(1, hp, 0, n_a, self.wap_a.data_ptr(), self.bias_a.data_ptr(), None, self.la.data_ptr(), st), "ppo gemm LOGITS_A")
+            check(L.bg_ppo_gemm_nt(2, hp, n_a, B, self.wap_b.data_ptr(), self.bias_b.data_ptr(), None, lb_off, st), "ppo gemm LOGITS_B")
+            check(L.bg_ppo_loss_grad_classes(self.la.data_ptr(), self.dla.data_ptr(), self.lb.data_ptr(), self.dlb.data_ptr(), n_a, B,
+                                             counts.data_ptr(), actions.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
+                                             returns.data_ptr(), float(eps_clip), float(value_coef), float(entropy_coef),
+                                             self.dbias.data_ptr(), self.sums.data_ptr(), st), "bg_ppo_loss_grad_classes")
+            check(L.bg_ppo_gemm_nt(3, self.dla.data_ptr(), 0, n_a, self.wap_a.data_ptr(), None, hp, dp, st), "ppo gemm DPRE_A")
+            check(L.bg_ppo_gemm_nt(4, dlb_off, n_a, B, self.wap_b.data_ptr(), None, hp, dp, st), "ppo gemm DPRE_B")
+            check(L.bg_ppo_gemm_tn(5, hp, self.dla.data_ptr(), 0, n_a, gflat.data_ptr(), st), "ppo gemm GRAD_WA_A")
+            check(L.bg_ppo_gemm_tn(6, hp, dlb_off, n_a, B, gflat.data_ptr(), st), "ppo gemm GRAD_WA_B")
+            check(L.bg_ppo_gemm_tn(7, dp, xp, 0, B, gflat.data_ptr(), st), "ppo gemm GRAD_W1")
+        # bias gradients = column sums of dlogits, accumulated by the loss kernels
+        OFF_BA, OFF_BV = 128 * 198 + 128 + 500 * 128, 128 * 198 + 128 + 500 * 128 + 500 + 128
+        gflat[OFF_BA:OFF_BA + ACTIONS].copy_(self.dbias[:ACTIONS])
+        gflat[OFF_BV:OFF_BV + 1].copy_(self.dbias[ACTIONS:ACTIONS + 1])
+        if flat_grads is None:
+            o = 0
+            for k in KEYS:
+                n = grads[k].numel()
+                grads[k].copy_(gflat[o:o + n].view(grads[k].shape))
+                o += n
+        m = self.sums / B
+        return torch.stack([m[0], m[1], m[2], m[0] + value_coef * m[1] - entropy_coef * m[2]])
+
+
 def discounted_returns(rewards, dones, values, last_values, gamma, lam):
     """bg_gae on CUDA tensors ([T][N], step-major) -> (returns, advantages)."""
     T, N = rewards.shape
@@ -274,6 +384,21 @@ class PPOLearner:
         self.last = {}
         self._manual = None
 
+    def _adam_step(self):
+        """torch.optim.Adam's step (ppo_agent.py:83,301-305) as ONE kernel over the flat bucket, after the single flat
+        all-reduce (the division by the world size is folded into the kernel)."""
+        world = 1
+        if self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size() > 1:
+            self.dist.all_reduce(self.fp.flat_grad)
+            world = self.dist.get_world_size()
+        if not hasattr(self, "_adam_m"):
+            self._adam_m, self._adam_v, self._adam_t = torch.zeros_like(self.fp.flat), torch.zeros_like(self.fp.flat), 0
+        self._adam_t += 1
+        with torch.cuda.device(self.device):
+            check(lib().bg_adam_step(self.fp.flat.data_ptr(), self.fp.flat_grad.data_ptr(), self._adam_m.data_ptr(),
+                                     self._adam_v.data_ptr(), self.fp.numel, float(self.cfg.learning_rate), 0.9, 0.999, 1e-8,
+                                     self._adam_t, 1.0 / world, _stream()), "bg_adam_step")
+
     def update_entropy_coef(self):                                                                   # ppo_agent.py:193-204
         c = self.cfg
         progress = min(1.0, self.total_episodes / c.entropy_anneal_episodes)
@@ -301,18 +426,30 @@ class PPOLearner:
         stats = torch.zeros(4, device=x.device)
         manual = (c.manual_backward and c.autocast and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2
                   and x.shape[1] == 208 and x.is_contiguous())
+        tc = manual and c.update_impl == "tcgen05" and mb == 1
+        n_a = None
         if manual:
-            if self._manual is None:
-                self._manual = ManualUpdate(self.device)
-            self._manual.invalidate()
+            if self._manual is None or isinstance(self._manual, TensorCoreUpdate) != tc:
+                self._manual = TensorCoreUpdate(self.device) if tc else ManualUpdate(self.device)
             x[:, ManualUpdate.ONE_COL] = 1.0                  # spare (zero) column of K3's rows: carries fc1.bias through the GEMMs
             counts, actions = counts.to(torch.int32).contiguous(), actions.to(torch.int32).contiguous()
             old_logp, returns, adv = old_logp.float().contiguous(), returns.float().contiguous(), adv.float().contiguous()
             grads = {k: p.grad for k, p in self.fp.params.items()}
+            if tc:
+                # sort the rollout by class once (the epochs reuse it): class A rows first
+                perm, n_a = self._manual.sort_by_class(counts, actions)
+                x, counts, actions = x[perm].contiguous(), counts[perm].contiguous(), actions[perm].contiguous()
+                old_logp, returns, adv = old_logp[perm].contiguous(), returns[perm].contiguous(), adv[perm].contiguous()
+            else:
+                self._manual.invalidate()
         for _ in range(c.num_epochs):
             for k in range(mb):
                 sl = slice(k * B // mb, (k + 1) * B // mb)
-                if manual:
+                if tc:
+                    st = self._manual.epoch(self.fp.params, grads, x, counts, actions, old_logp, adv, returns, c.eps_clip,
+                                            c.value_loss_coef, self.entropy_coef, n_a=n_a, flat_params=self.fp.flat,
+                                            flat_grads=self.fp.flat_grad)
+                elif manual:
                     st = self._manual.epoch(self.fp.params, grads, x[sl], counts[sl], actions[sl], old_logp[sl], adv[sl], returns[sl],
                                             c.eps_clip, c.value_loss_coef, self.entropy_coef)
                 else:
@@ -321,8 +458,11 @@ class PPOLearner:
                     self.fp.flat_grad.zero_()
                     loss.backward()
                     st = torch.stack([pl.float(), vl.float(), ent.float(), loss.detach().float()])
-                self.fp.all_reduce_grads(self.dist)
-                self.optimizer.step()
+                if tc:
+                    self._adam_step()                         # all-reduce (sum) + our Adam kernel (the 1 / world average folded in)
+                else:
+                    self.fp.all_reduce_grads(self.dist)
+                    self.optimizer.step()
                 stats += st
                 self.total_steps += 1
         stats /= c.num_epochs * mb
