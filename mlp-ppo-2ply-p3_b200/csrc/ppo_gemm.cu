@@ -48,21 +48,27 @@ __device__ __forceinline__ uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn)
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
+__device__ __forceinline__ void cp_async_wait_but(int newest) {          // wait until at most `newest` (0 or 1) commit groups are pending
+    if (newest >= 1) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
 __device__ __forceinline__ uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u : (n <= 64 ? 64u : (n <= 128 ? 128u : (n <= 256 ? 256u : 512u))); }
 
-// rows [row0, row0 + 128) x columns [col0, col0 + 8 nch) of a row-major bf16 matrix -> the chunk layout at `dst` (shared address).
+// rows [row0, row0 + ROWS) x columns [col0, col0 + 8 nch) of a row-major bf16 matrix -> the chunk layout at `dst` (shared address).
 // A warp moves 8 rows x 4 chunks per instruction: 64 contiguous bytes per row in global memory, 128 contiguous bytes per
 // chunk column in shared memory.  Rows >= row_end are zero-filled.
+template <int ROWS>
 __device__ __forceinline__ void stage_tile(uint32_t dst, unsigned char* dst_generic, const uint16_t* __restrict__ src, long long ld,
                                            long long row0, long long row_end, int col0, int nch, int tid) {
     const int warp = tid >> 5, lane = tid & 31;
     const int cblocks = (nch + 3) >> 2;
-    for (int u = warp; u < 16 * cblocks; u += kGT / 32) {
-        const int rb = u & 15, cb = u >> 4;
+    constexpr int RB = ROWS / 8;
+    for (int u = warp; u < RB * cblocks; u += kGT / 32) {
+        const int rb = u % RB, cb = u / RB;
         const int r = 8 * rb + (lane & 7), c8 = 4 * cb + (lane >> 3);
         if (c8 < nch) {
             const long long row = row0 + r;
-            const uint32_t off = (uint32_t)(c8 * kChunk + r * 16);
+            const uint32_t off = (uint32_t)(c8 * (ROWS * 16) + r * 16);
             if (row < row_end) cp_async16_s(dst + off, src + row * ld + col0 + 8 * c8);
             else *reinterpret_cast<uint4*>(dst_generic + off) = make_uint4(0u, 0u, 0u, 0u);
         }
@@ -77,6 +83,7 @@ struct NtArgs {
     const uint16_t* W; int w_bytes; int w_rows;   // packed weight tile (chunk layout) and its number of rows
     int N, K, KC;                              // output columns (<= 512), reduction length, K per stage (K % KC == 0, KC % 16 == 0)
     int b_mn;                                  // 0: W rows = N, columns = K (K-major B);  1: W rows = K, columns = N = 128 (MN-major B)
+    int D, LA;                                 // ring of D stage buffers, LA stages loading ahead of the one being multiplied (D > LA)
     int epi;                                   // 0 relu, 1 + bias, 2 * [mask > 0]
     const float* bias; const uint16_t* mask; long long ldm;
     uint16_t* out; long long ldo;
@@ -84,17 +91,17 @@ struct NtArgs {
 
 __global__ void __launch_bounds__(kGT, 1) ppo_gemm_nt_kernel(const NtArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ unsigned long long bar[2];
+    __shared__ unsigned long long bar[4];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int stage_bytes = (a.KC >> 3) * kChunk;
     unsigned char* Wg = smem;
-    unsigned char* Ag[2] = {smem + ((a.w_bytes + 1023) & ~1023), smem + ((a.w_bytes + 1023) & ~1023) + stage_bytes};
-    const uint32_t Ws = smem_u32(Wg), As[2] = {smem_u32(Ag[0]), smem_u32(Ag[1])};
+    unsigned char* A0 = smem + ((a.w_bytes + 1023) & ~1023);
+    const uint32_t Ws = smem_u32(Wg), As0 = smem_u32(A0);
     for (int c = tid; c < a.w_bytes / 16; c += kGT) cp_async16_s(Ws + 16u * c, reinterpret_cast<const unsigned char*>(a.W) + 16 * c);
-    cp_async_commit();
+    // (W travels in the first stage's commit group)
     if (tid == 0) {
-        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     const uint32_t ncols = tmem_cols_for(a.N);
@@ -112,29 +119,34 @@ __global__ void __launch_bounds__(kGT, 1) ppo_gemm_nt_kernel(const NtArgs a) {
     long long my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const long long n_steps = my_tiles * n_kc;
     auto step_tile = [&](long long s) { return blockIdx.x + (s / n_kc) * gridDim.x; };
-    auto load = [&](long long s, int b) {
-        const long long row0 = a.row_begin + step_tile(s) * kRows;
-        stage_tile(As[b], Ag[b], a.A, a.lda, row0, a.row_end, (int)(s % n_kc) * a.KC, nch, tid);
+    // stage s (if it exists) -> buffer s % D; always one commit group per call, so that "all but the newest LA-1 groups" = stage s
+    auto load = [&](long long s) {
+        if (s < n_steps) {
+            const int b = (int)(s % a.D);
+            const long long row0 = a.row_begin + step_tile(s) * kRows;
+            stage_tile<kRows>(As0 + (uint32_t)(b * stage_bytes), A0 + b * stage_bytes, a.A, a.lda, row0, a.row_end, (int)(s % n_kc) * a.KC, nch, tid);
+        }
         cp_async_commit();
     };
-    uint32_t ph[2] = {0u, 0u};
-    bool pending[2] = {false, false};
+    uint32_t ph[4] = {0u, 0u, 0u, 0u};
+    bool pending[4] = {false, false, false, false};
     auto ensure_done = [&](int b) { if (pending[b]) { mbar_wait(&bar[b], ph[b]); ph[b] ^= 1u; pending[b] = false; } };
     const int q = warp & 3, half = warp >> 2;
-    if (n_steps > 0) load(0, 0);
+    for (int j = 0; j < a.LA; ++j) load(j);
     for (long long s = 0; s < n_steps; ++s) {
-        const int b = (int)(s & 1);
+        const int b = (int)(s % a.D);
         const int kc = (int)(s % n_kc);
-        cp_async_wait_all();                                           // this thread's share of stage s (and of W) has landed
+        cp_async_wait_but(a.LA - 1);                                   // this thread's share of stage s (and of W) has landed
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); // ... and is visible to the tensor-core proxy
         __syncthreads();
-        ensure_done(b ^ 1);                                            // the MMAs that read the other buffer (stage s-1)
-        if (s + 1 < n_steps) load(s + 1, b ^ 1);
+        ensure_done((int)((s + a.LA) % a.D));                          // the MMAs that last read the buffer stage s + LA goes into
+        load(s + a.LA);
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t Ab = As0 + (uint32_t)(b * stage_bytes);
             for (int ks = 0; ks < a.KC / 16; ++ks) {
                 const int kg = kc * a.KC + ks * 16;                    // first reduction index of this MMA
-                const uint64_t da = make_smem_desc_kmajor(As[b] + (uint32_t)(ks * 2 * kChunk), kChunk, 128);
+                const uint64_t da = make_smem_desc_kmajor(Ab + (uint32_t)(ks * 2 * kChunk), kChunk, 128);
                 const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
                 if (a.b_mn) {
                     // W rows = reduction index (action slots), columns = N = 128 hidden units: MN-major, K groups 128 B apart
@@ -194,7 +206,8 @@ __global__ void __launch_bounds__(kGT, 1) ppo_gemm_nt_kernel(const NtArgs a) {
             __syncthreads();                                           // everybody has read the accumulators: the next tile may overwrite them
         }
     }
-    ensure_done(0); ensure_done(1);
+    for (int i = 0; i < 4; ++i) ensure_done(i);
+    cp_async_wait_but(0);
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(ncols) : "memory");
@@ -211,17 +224,18 @@ struct TnArgs {
     float* grad;                               // flat f32 gradient (kNumParams)
 };
 
+constexpr int kTnRows = 64;               // sample rows per stage of the TN kernel (four MMA K-steps)
+constexpr int kTnD = 4, kTnLA = 2;        // ring of four stage buffers, two stages loading ahead
 __global__ void __launch_bounds__(kGT, 1) ppo_gemm_tn_kernel(const TnArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ unsigned long long bar[2];
+    __shared__ unsigned long long bar[kTnD];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int a_bytes = 16 * kChunk, b_bytes = (a.N >> 3) * kChunk;
-    unsigned char* Ag[2] = {smem, smem + a_bytes + b_bytes};
-    unsigned char* Bg[2] = {smem + a_bytes, smem + 2 * a_bytes + b_bytes};
-    const uint32_t As[2] = {smem_u32(Ag[0]), smem_u32(Ag[1])}, Bs[2] = {smem_u32(Bg[0]), smem_u32(Bg[1])};
+    constexpr int CS = kTnRows * 16;                                   // chunk-column stride of a stage tile
+    const int a_bytes = 16 * CS, b_bytes = (a.N >> 3) * CS, stage_bytes = a_bytes + b_bytes;
+    const uint32_t S0 = smem_u32(smem);
     if (tid == 0) {
-        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        for (int i = 0; i < kTnD; ++i) mbar_init(&bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     const uint32_t ncols = tmem_cols_for(a.N);
@@ -233,40 +247,45 @@ __global__ void __launch_bounds__(kGT, 1) ppo_gemm_tn_kernel(const TnArgs a) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = s_tmem;
-    const long long n_tiles = (a.row_end - a.row_begin + kRows - 1) / kRows;
+    const long long n_tiles = (a.row_end - a.row_begin + kTnRows - 1) / kTnRows;
     const long long n_steps = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    auto load = [&](long long s, int b) {
-        const long long row0 = a.row_begin + (blockIdx.x + s * gridDim.x) * kRows;
-        stage_tile(As[b], Ag[b], a.A, a.lda, row0, a.row_end, 0, 16, tid);
-        stage_tile(Bs[b], Bg[b], a.B, a.ldb, row0, a.row_end, 0, a.N >> 3, tid);
+    auto load = [&](long long s) {
+        if (s < n_steps) {
+            const int b = (int)(s % kTnD);
+            const long long row0 = a.row_begin + (blockIdx.x + s * gridDim.x) * kTnRows;
+            stage_tile<kTnRows>(S0 + (uint32_t)(b * stage_bytes), smem + b * stage_bytes, a.A, a.lda, row0, a.row_end, 0, 16, tid);
+            stage_tile<kTnRows>(S0 + (uint32_t)(b * stage_bytes + a_bytes), smem + b * stage_bytes + a_bytes, a.B, a.ldb, row0, a.row_end, 0, a.N >> 3, tid);
+        }
         cp_async_commit();
     };
-    uint32_t ph[2] = {0u, 0u};
-    bool pending[2] = {false, false};
+    uint32_t ph[kTnD] = {0u, 0u, 0u, 0u};
+    bool pending[kTnD] = {false, false, false, false};
     auto ensure_done = [&](int b) { if (pending[b]) { mbar_wait(&bar[b], ph[b]); ph[b] ^= 1u; pending[b] = false; } };
-    if (n_steps > 0) load(0, 0);
+    for (int j = 0; j < kTnLA; ++j) load(j);
     const uint32_t idesc = idesc_bf16(128, a.N, 1, 1);
     for (long long s = 0; s < n_steps; ++s) {
-        const int b = (int)(s & 1);
-        cp_async_wait_all();
+        const int b = (int)(s % kTnD);
+        cp_async_wait_but(kTnLA - 1);
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncthreads();
-        ensure_done(b ^ 1);
-        if (s + 1 < n_steps) load(s + 1, b ^ 1);
+        ensure_done((int)((s + kTnLA) % kTnD));                        // (the MMAs of stage s - 2: long done)
+        load(s + kTnLA);
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t Ab = S0 + (uint32_t)(b * stage_bytes), Bb = Ab + (uint32_t)a_bytes;
 #pragma unroll 1
-            for (int ks = 0; ks < kRows / 16; ++ks) {
+            for (int ks = 0; ks < kTnRows / 16; ++ks) {
                 // both tiles are read MN-major: the reduction index is the ROW (sample); 16 rows = two 8-row groups 128 B apart
-                const uint64_t da = make_smem_desc_kmajor(As[b] + (uint32_t)(ks * 256), 128, kChunk);
-                const uint64_t db = make_smem_desc_kmajor(Bs[b] + (uint32_t)(ks * 256), 128, kChunk);
+                const uint64_t da = make_smem_desc_kmajor(Ab + (uint32_t)(ks * 256), 128, CS);
+                const uint64_t db = make_smem_desc_kmajor(Bb + (uint32_t)(ks * 256), 128, CS);
                 mma_bf16_ss(tmem, da, db, idesc, (s > 0 || ks > 0) ? 1u : 0u);
             }
             umma_commit(&bar[b]);
         }
         pending[b] = true;
     }
-    ensure_done(0); ensure_done(1);
+    for (int i = 0; i < kTnD; ++i) ensure_done(i);
+    cp_async_wait_but(0);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     if (n_steps > 0) {
         // accumulator: lane = hidden unit m, column = n.  Thread = (m, half of the columns).
@@ -351,21 +370,23 @@ extern "C" int bg_ppo_gemm_nt(int op, const uint16_t* A, long long row_begin, lo
     NtArgs a{};
     a.A = A; a.row_begin = row_begin; a.row_end = row_end; a.W = W; a.bias = bias; a.mask = h_mask; a.ldm = 128; a.out = out;
     switch (op) {
-        case BG_PPO_OP_HIDDEN:   a.lda = 208; a.N = 128; a.K = 208; a.KC = 208; a.w_rows = 128; a.b_mn = 0; a.epi = 0; a.ldo = 128; break;
-        case BG_PPO_OP_LOGITS_A: a.lda = 128; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 1; a.ldo = 144; break;
-        case BG_PPO_OP_LOGITS_B: a.lda = 128; a.N = 512; a.K = 128; a.KC = 128; a.w_rows = 512; a.b_mn = 0; a.epi = 1; a.ldo = 512; break;
-        case BG_PPO_OP_DPRE_A:   a.lda = 144; a.N = 128; a.K = 144; a.KC = 144; a.w_rows = 144; a.b_mn = 1; a.epi = 2; a.ldo = 128; break;
-        case BG_PPO_OP_DPRE_B:   a.lda = 512; a.N = 128; a.K = 512; a.KC = 128; a.w_rows = 512; a.b_mn = 1; a.epi = 2; a.ldo = 128; break;
+        // (ring D / stages in flight LA: what fits beside the weight tile in 220 KB)
+        case BG_PPO_OP_HIDDEN:   a.lda = 208; a.N = 128; a.K = 208; a.KC = 208; a.w_rows = 128; a.b_mn = 0; a.epi = 0; a.ldo = 128; a.D = 3; a.LA = 2; break;
+        case BG_PPO_OP_LOGITS_A: a.lda = 128; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 1; a.ldo = 144; a.D = 4; a.LA = 2; break;
+        case BG_PPO_OP_LOGITS_B: a.lda = 128; a.N = 512; a.K = 128; a.KC = 128; a.w_rows = 512; a.b_mn = 0; a.epi = 1; a.ldo = 512; a.D = 2; a.LA = 1; break;
+        case BG_PPO_OP_DPRE_A:   a.lda = 144; a.N = 128; a.K = 144; a.KC = 144; a.w_rows = 144; a.b_mn = 1; a.epi = 2; a.ldo = 128; a.D = 4; a.LA = 2; break;
+        case BG_PPO_OP_DPRE_B:   a.lda = 512; a.N = 128; a.K = 512; a.KC = 128; a.w_rows = 512; a.b_mn = 1; a.epi = 2; a.ldo = 128; a.D = 2; a.LA = 1; break;
         default: return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: unknown op");
     }
     if (a.epi == 1 && !bias) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: the logits ops need the bias row");
     if (a.epi == 2 && !h_mask) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: the dpre ops need h");
     a.w_bytes = (op == BG_PPO_OP_HIDDEN ? 26 : 16) * a.w_rows * 16;
-    const size_t smem = ((size_t)(a.w_bytes + 1023) & ~(size_t)1023) + 2 * (size_t)(a.KC >> 3) * kChunk;
+    const size_t smem = ((size_t)(a.w_bytes + 1023) & ~(size_t)1023) + (size_t)a.D * (size_t)(a.KC >> 3) * kChunk;
     cudaError_t e = cudaFuncSetAttribute(ppo_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return bg_set_error(e, "bg_ppo_gemm_nt: cudaFuncSetAttribute");
+    if (smem > 220 * 1024) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: stage ring does not fit shared memory");
     const long long tiles = (row_end - row_begin + kRows - 1) / kRows;
-    long long grid = (long long)bg_sm_count() * (smem <= 100 * 1024 ? 2 : 1);
+    long long grid = (long long)bg_sm_count();
     if (grid > tiles) grid = tiles;
     ppo_gemm_nt_kernel<<<(unsigned)grid, kGT, smem, (cudaStream_t)stream>>>(a);
     return bg_set_error(cudaGetLastError(), "bg_ppo_gemm_nt: launch");
@@ -378,10 +399,10 @@ extern "C" int bg_ppo_gemm_tn(int op, const uint16_t* A, const uint16_t* B, long
     if (!A || !B || !flat_grad) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_tn: null pointer");
     cudaError_t e = cudaFuncSetAttribute(ppo_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return bg_set_error(e, "bg_ppo_gemm_tn: cudaFuncSetAttribute");
-    const long long tiles = (row_end - row_begin + kRows - 1) / kRows;
+    const long long tiles = (row_end - row_begin + kTnRows - 1) / kTnRows;
     auto launch = [&](TnArgs a) -> int {
-        const size_t smem = 2 * ((size_t)16 * kChunk + (size_t)(a.N >> 3) * kChunk);
-        long long grid = (long long)bg_sm_count() * (smem <= 100 * 1024 ? 2 : 1);
+        const size_t smem = (size_t)kTnD * ((size_t)16 + (size_t)(a.N >> 3)) * (kTnRows * 16);
+        long long grid = (long long)bg_sm_count();
         if (grid > tiles) grid = tiles;
         ppo_gemm_tn_kernel<<<(unsigned)grid, kGT, smem, (cudaStream_t)stream>>>(a);
         return bg_set_error(cudaGetLastError(), "bg_ppo_gemm_tn: launch");
