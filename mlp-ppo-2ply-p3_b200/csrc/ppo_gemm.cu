@@ -18,8 +18,8 @@
 // SBO = 128) for the forward GEMMs, and as MN-major (columns = M or N, rows = K: SBO = chunk stride, LBO = 128) for the
 // transposed products -- dlogits^T h, dpre^T x and dlogits Wap all read the very same tiles without a transpose.
 // Both operands come from shared memory (tcgen05.mma SS form), accumulators live in TMEM; the kernels are HBM-bound
-// (they stream 0.3 .. 1 KB per sample), so the pipeline is a plain double buffer: cp.async of stage i+1 while the
-// MMAs of stage i run, epilogue out of TMEM.
+// (they stream 0.3 .. 1 KB per sample).  Inside a CTA a step is serial -- cp.async of the next stage(s) is issued, the
+// MMAs of the current one run, the epilogue reads TMEM -- and the phases of different CTAs overlap: two CTAs per SM.
 #include <cuda_bf16.h>
 #include "bg_device.cuh"
 #include "bg_tcgen05.cuh"
@@ -60,18 +60,22 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u 
 template <int ROWS>
 __device__ __forceinline__ void stage_tile(uint32_t dst, unsigned char* dst_generic, const uint16_t* __restrict__ src, long long ld,
                                            long long row0, long long row_end, int col0, int nch, int tid) {
-    const int warp = tid >> 5, lane = tid & 31;
-    const int cblocks = (nch + 3) >> 2;
-    constexpr int RB = ROWS / 8;
-    for (int u = warp; u < RB * cblocks; u += kGT / 32) {
-        const int rb = u % RB, cb = u / RB;
-        const int r = 8 * rb + (lane & 7), c8 = 4 * cb + (lane >> 3);
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    constexpr int RB = ROWS / 8;                                       // 8-row blocks of the tile
+    const int r_in = lane & 7, c_in = lane >> 3;
+    const uint16_t* base = src + row0 * ld + col0;
+    // unit u = (row block rb, chunk block cb), rb fastest; a warp walks units warp, warp + nwarps, ... without divisions
+    int rb = warp % RB, cb = warp / RB;
+    const int drb = nwarps % RB, dcb = nwarps / RB;
+    for (; 4 * cb < nch; ) {
+        const int r = 8 * rb + r_in, c8 = 4 * cb + c_in;
         if (c8 < nch) {
-            const long long row = row0 + r;
             const uint32_t off = (uint32_t)(c8 * (ROWS * 16) + r * 16);
-            if (row < row_end) cp_async16_s(dst + off, src + row * ld + col0 + 8 * c8);
+            if (row0 + r < row_end) cp_async16_s(dst + off, base + (long long)r * ld + 8 * c8);
             else *reinterpret_cast<uint4*>(dst_generic + off) = make_uint4(0u, 0u, 0u, 0u);
         }
+        rb += drb; cb += dcb;
+        if (rb >= RB) { rb -= RB; ++cb; }
     }
 }
 
@@ -89,7 +93,7 @@ struct NtArgs {
     uint16_t* out; long long ldo;
 };
 
-__global__ void __launch_bounds__(kGT, 1) ppo_gemm_nt_kernel(const NtArgs a) {
+__global__ void __launch_bounds__(512, 1) ppo_gemm_nt_kernel(const NtArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ unsigned long long bar[4];
     __shared__ uint32_t s_tmem;
@@ -98,7 +102,7 @@ __global__ void __launch_bounds__(kGT, 1) ppo_gemm_nt_kernel(const NtArgs a) {
     unsigned char* Wg = smem;
     unsigned char* A0 = smem + ((a.w_bytes + 1023) & ~1023);
     const uint32_t Ws = smem_u32(Wg), As0 = smem_u32(A0);
-    for (int c = tid; c < a.w_bytes / 16; c += kGT) cp_async16_s(Ws + 16u * c, reinterpret_cast<const unsigned char*>(a.W) + 16 * c);
+    for (int c = tid; c < a.w_bytes / 16; c += blockDim.x) cp_async16_s(Ws + 16u * c, reinterpret_cast<const unsigned char*>(a.W) + 16 * c);
     // (W travels in the first stage's commit group)
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(kGT, 1) ppo_gemm_nt_kernel(const NtArgs a) {
     uint32_t ph[4] = {0u, 0u, 0u, 0u};
     bool pending[4] = {false, false, false, false};
     auto ensure_done = [&](int b) { if (pending[b]) { mbar_wait(&bar[b], ph[b]); ph[b] ^= 1u; pending[b] = false; } };
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, part = warp >> 2, nparts = (int)(blockDim.x >> 7);   // the warps of a TMEM lane quarter split the columns
     for (int j = 0; j < a.LA; ++j) load(j);
     for (long long s = 0; s < n_steps; ++s) {
         const int b = (int)(s % a.D);
@@ -164,13 +168,13 @@ __global__ void __launch_bounds__(kGT, 1) ppo_gemm_nt_kernel(const NtArgs a) {
         }
         pending[b] = true;
         if (kc == n_kc - 1) {
-            // ---- epilogue of the tile: thread = row (TMEM lane), the two warps of a lane quarter split the columns
+            // ---- epilogue of the tile: thread = row (TMEM lane), the warps of a lane quarter split the columns
             ensure_done(b);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const long long row = a.row_begin + step_tile(s) * kRows + q * 32 + lane;
             const bool live = row < a.row_end;
             const int nblk = (a.N + 31) >> 5;                          // blocks of 32 columns (the last may be 16 wide: N = 144)
-            for (int blk = half; blk < nblk; blk += 2) {
+            for (int blk = part; blk < nblk; blk += nparts) {
                 const int c0 = 32 * blk, w = a.N - c0 < 32 ? a.N - c0 : 32;
                 uint32_t acc[32];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -225,8 +229,8 @@ struct TnArgs {
 };
 
 constexpr int kTnRows = 64;               // sample rows per stage of the TN kernel (four MMA K-steps)
-constexpr int kTnD = 4, kTnLA = 2;        // ring of four stage buffers, two stages loading ahead
-__global__ void __launch_bounds__(kGT, 1) ppo_gemm_tn_kernel(const TnArgs a) {
+constexpr int kTnD = 2, kTnLA = 1;        // double buffer per CTA; two or three CTAs per SM overlap each other's phases
+__global__ void __launch_bounds__(512, 1) ppo_gemm_tn_kernel(const TnArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ unsigned long long bar[kTnD];
     __shared__ uint32_t s_tmem;
@@ -258,8 +262,8 @@ __global__ void __launch_bounds__(kGT, 1) ppo_gemm_tn_kernel(const TnArgs a) {
         }
         cp_async_commit();
     };
-    uint32_t ph[kTnD] = {0u, 0u, 0u, 0u};
-    bool pending[kTnD] = {false, false, false, false};
+    uint32_t ph[kTnD] = {};
+    bool pending[kTnD] = {};
     auto ensure_done = [&](int b) { if (pending[b]) { mbar_wait(&bar[b], ph[b]); ph[b] ^= 1u; pending[b] = false; } };
     for (int j = 0; j < kTnLA; ++j) load(j);
     const uint32_t idesc = idesc_bf16(128, a.N, 1, 1);
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(kGT, 1) ppo_gemm_tn_kernel(const TnArgs a) {
         cp_async_wait_but(kTnLA - 1);
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncthreads();
-        ensure_done((int)((s + kTnLA) % kTnD));                        // (the MMAs of stage s - 2: long done)
+        ensure_done((int)((s + kTnLA) % kTnD));                        // the MMAs that last read that buffer
         load(s + kTnLA);
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -289,10 +293,10 @@ __global__ void __launch_bounds__(kGT, 1) ppo_gemm_tn_kernel(const TnArgs a) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     if (n_steps > 0) {
         // accumulator: lane = hidden unit m, column = n.  Thread = (m, half of the columns).
-        const int q = warp & 3, half = warp >> 2;
+        const int q = warp & 3, part = warp >> 2, nparts = (int)(blockDim.x >> 7);
         const int m = q * 32 + lane;
         const int nblk = a.N >> 3;
-        for (int blk = half; blk < nblk; blk += 2) {
+        for (int blk = part; blk < nblk; blk += nparts) {
             uint32_t acc[8];
             tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(8 * blk), acc);
             tmem_ld_wait();
@@ -368,14 +372,17 @@ extern "C" int bg_ppo_gemm_nt(int op, const uint16_t* A, long long row_begin, lo
     if (row_end == row_begin) return BG_OK;
     if (!A || !W || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: null pointer");
     NtArgs a{};
+    int threads = 256, per_sm = 1;
     a.A = A; a.row_begin = row_begin; a.row_end = row_end; a.W = W; a.bias = bias; a.mask = h_mask; a.ldm = 128; a.out = out;
     switch (op) {
         // (ring D / stages in flight LA: what fits beside the weight tile in 220 KB)
-        case BG_PPO_OP_HIDDEN:   a.lda = 208; a.N = 128; a.K = 208; a.KC = 208; a.w_rows = 128; a.b_mn = 0; a.epi = 0; a.ldo = 128; a.D = 3; a.LA = 2; break;
-        case BG_PPO_OP_LOGITS_A: a.lda = 128; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 1; a.ldo = 144; a.D = 4; a.LA = 2; break;
-        case BG_PPO_OP_LOGITS_B: a.lda = 128; a.N = 512; a.K = 128; a.KC = 128; a.w_rows = 512; a.b_mn = 0; a.epi = 1; a.ldo = 512; a.D = 2; a.LA = 1; break;
-        case BG_PPO_OP_DPRE_A:   a.lda = 144; a.N = 128; a.K = 144; a.KC = 144; a.w_rows = 144; a.b_mn = 1; a.epi = 2; a.ldo = 128; a.D = 4; a.LA = 2; break;
-        case BG_PPO_OP_DPRE_B:   a.lda = 512; a.N = 128; a.K = 512; a.KC = 128; a.w_rows = 512; a.b_mn = 1; a.epi = 2; a.ldo = 128; a.D = 2; a.LA = 1; break;
+        // A step is serial inside a CTA (issue the loads, multiply, epilogue), so the phases are overlapped ACROSS CTAs: two
+        // 256-thread CTAs per SM where the weight tile leaves room (class A), one 512-thread CTA otherwise
+        case BG_PPO_OP_HIDDEN:   a.lda = 208; a.N = 128; a.K = 208; a.KC = 208; a.w_rows = 128; a.b_mn = 0; a.epi = 0; a.ldo = 128; a.D = 3; a.LA = 2; threads = 512; per_sm = 1; break;
+        case BG_PPO_OP_LOGITS_A: a.lda = 128; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 1; a.ldo = 144; a.D = 2; a.LA = 1; threads = 256; per_sm = 2; break;
+        case BG_PPO_OP_LOGITS_B: a.lda = 128; a.N = 512; a.K = 128; a.KC = 128; a.w_rows = 512; a.b_mn = 0; a.epi = 1; a.ldo = 512; a.D = 2; a.LA = 1; threads = 512; per_sm = 1; break;
+        case BG_PPO_OP_DPRE_A:   a.lda = 144; a.N = 128; a.K = 144; a.KC = 144; a.w_rows = 144; a.b_mn = 1; a.epi = 2; a.ldo = 128; a.D = 2; a.LA = 1; threads = 256; per_sm = 2; break;
+        case BG_PPO_OP_DPRE_B:   a.lda = 512; a.N = 128; a.K = 512; a.KC = 128; a.w_rows = 512; a.b_mn = 1; a.epi = 2; a.ldo = 128; a.D = 2; a.LA = 1; threads = 512; per_sm = 1; break;
         default: return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: unknown op");
     }
     if (a.epi == 1 && !bias) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: the logits ops need the bias row");
@@ -386,9 +393,9 @@ extern "C" int bg_ppo_gemm_nt(int op, const uint16_t* A, long long row_begin, lo
     if (e != cudaSuccess) return bg_set_error(e, "bg_ppo_gemm_nt: cudaFuncSetAttribute");
     if (smem > 220 * 1024) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: stage ring does not fit shared memory");
     const long long tiles = (row_end - row_begin + kRows - 1) / kRows;
-    long long grid = (long long)bg_sm_count();
+    long long grid = (long long)bg_sm_count() * per_sm;
     if (grid > tiles) grid = tiles;
-    ppo_gemm_nt_kernel<<<(unsigned)grid, kGT, smem, (cudaStream_t)stream>>>(a);
+    ppo_gemm_nt_kernel<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(a);
     return bg_set_error(cudaGetLastError(), "bg_ppo_gemm_nt: launch");
 }
 
@@ -402,7 +409,7 @@ extern "C" int bg_ppo_gemm_tn(int op, const uint16_t* A, const uint16_t* B, long
     const long long tiles = (row_end - row_begin + kTnRows - 1) / kTnRows;
     auto launch = [&](TnArgs a) -> int {
         const size_t smem = (size_t)kTnD * ((size_t)16 + (size_t)(a.N >> 3)) * (kTnRows * 16);
-        long long grid = (long long)bg_sm_count();
+        long long grid = (long long)bg_sm_count() * 2;                 // two CTAs per SM (<= 86 KB and <= 256 TMEM columns each)
         if (grid > tiles) grid = tiles;
         ppo_gemm_tn_kernel<<<(unsigned)grid, kGT, smem, (cudaStream_t)stream>>>(a);
         return bg_set_error(cudaGetLastError(), "bg_ppo_gemm_tn: launch");
