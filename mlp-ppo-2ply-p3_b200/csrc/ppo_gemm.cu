@@ -55,20 +55,22 @@ __device__ __forceinline__ void cp_async_wait_but(int newest) {          // wait
 __device__ __forceinline__ uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u : (n <= 64 ? 64u : (n <= 128 ? 128u : (n <= 256 ? 256u : 512u))); }
 
 // rows [row0, row0 + ROWS) x columns [col0, col0 + 8 nch) of a row-major bf16 matrix -> the chunk layout at `dst` (shared address).
-// A warp moves 8 rows x 4 chunks per instruction: 64 contiguous bytes per row in global memory, 128 contiguous bytes per
-// chunk column in shared memory.  Rows >= row_end are zero-filled.
+// 16-byte accesses are coalesced per QUARTER warp (8 lanes): a quarter covers 4 rows x 2 adjacent chunks, i.e. one full
+// 32-byte sector per row in global memory (8 rows x 1 chunk fetched every sector twice: measured 2x L2 traffic) and two
+// 64-byte runs in shared memory (a 2-way bank conflict at most).  A warp moves 16 rows x 2 chunks per instruction.
+// Rows >= row_end are zero-filled.
 template <int ROWS>
 __device__ __forceinline__ void stage_tile(uint32_t dst, unsigned char* dst_generic, const uint16_t* __restrict__ src, long long ld,
                                            long long row0, long long row_end, int col0, int nch, int tid) {
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    constexpr int RB = ROWS / 8;                                       // 8-row blocks of the tile
-    const int r_in = lane & 7, c_in = lane >> 3;
+    constexpr int RB = ROWS / 16;                                      // 16-row blocks of the tile
+    const int r_in = (lane >> 3) * 4 + (lane & 3), c_in = (lane >> 2) & 1;
     const uint16_t* base = src + row0 * ld + col0;
-    // unit u = (row block rb, chunk block cb), rb fastest; a warp walks units warp, warp + nwarps, ... without divisions
+    // unit u = (row block rb, chunk pair cb), rb fastest; a warp walks units warp, warp + nwarps, ... without divisions
     int rb = warp % RB, cb = warp / RB;
     const int drb = nwarps % RB, dcb = nwarps / RB;
-    for (; 4 * cb < nch; ) {
-        const int r = 8 * rb + r_in, c8 = 4 * cb + c_in;
+    for (; 2 * cb < nch; ) {
+        const int r = 16 * rb + r_in, c8 = 2 * cb + c_in;
         if (c8 < nch) {
             const uint32_t off = (uint32_t)(c8 * (ROWS * 16) + r * 16);
             if (row0 + r < row_end) cp_async16_s(dst + off, base + (long long)r * ld + 8 * c8);
