@@ -287,11 +287,12 @@ int bg_ppo_pack_weights(const float* flat_params, uint16_t* w1p, uint16_t* wap_a
 int bg_ppo_gemm_nt(int op, const uint16_t* A, long long row_begin, long long row_end, const uint16_t* W, const float* bias,
                    const uint16_t* h_mask, uint16_t* out, void* stream);
 int bg_ppo_gemm_tn(int op, const uint16_t* A, const uint16_t* B, long long row_begin, long long row_end, float* flat_grad,
-                   void* stream);
+                   float* scratch /* GRAD_W1: [199][128] f32 (dW1p transposed; fc1.* of flat_grad are then overwritten) */, void* stream);
 int bg_ppo_loss_grad_classes(const void* logits_a, void* dlogits_a, const void* logits_b, void* dlogits_b, long long n_a, long long B,
                              const int32_t* counts, const int32_t* actions, const float* old_log_probs, const float* advantages,
                              const float* returns, float eps_clip, float value_coef, float entropy_coef, float* dbias /*[512]*/,
                              float* sums /*[3]*/, void* stream);
+int bg_ppo_gemm_debug(int flags);  /* experiment switches for scripts/exp_ppo_gemm.py (1 no MMAs, 2 no stores, 4 no loads); 0 = normal */
 int bg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                  float beta2, float eps, int step, float grad_scale, void* stream);
 

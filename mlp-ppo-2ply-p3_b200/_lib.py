@@ -64,8 +64,9 @@ SIGNATURES = {
     "bg_ppo_loss_grad": (_I, [_V, _I, _LL, _V, _V, _V, _V, _V, _V, _LL, _F, _F, _F, _V, _V, _V, _V, _V]),
     "bg_ppo_pack_weights": (_I, [_V, _V, _V, _V, _V, _V, _V]),
     "bg_ppo_gemm_nt": (_I, [_I, _V, _LL, _LL, _V, _V, _V, _V, _V]),
-    "bg_ppo_gemm_tn": (_I, [_I, _V, _V, _LL, _LL, _V, _V]),
+    "bg_ppo_gemm_tn": (_I, [_I, _V, _V, _LL, _LL, _V, _V, _V]),
     "bg_ppo_loss_grad_classes": (_I, [_V, _V, _V, _V, _LL, _LL, _V, _V, _V, _V, _V, _F, _F, _F, _V, _V, _V]),
+    "bg_ppo_gemm_debug": (_I, [_I]),
     "bg_adam_step": (_I, [_V, _V, _V, _V, _LL, _F, _F, _F, _F, _I, _F, _V]),
     "bg_pack_w1": (_I, [_V, _V, _V, _V]),
     "bg_mlp_value": (_I, [_V, _V, _I, _I, _LL, _V, _V, _V, _V, _F, _I, _V, _V]),

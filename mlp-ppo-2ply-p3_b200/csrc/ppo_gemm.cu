@@ -48,6 +48,11 @@ __device__ __forceinline__ uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn)
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
+// one full 32-byte sector per thread and instruction (STG.256, sm_100): p must be 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
+                 "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_but(int newest) {          // wait until at most `newest` (0 or 1) commit groups are pending
     if (newest >= 1) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -93,14 +98,17 @@ struct NtArgs {
     int epi;                                   // 0 relu, 1 + bias, 2 * [mask > 0]
     const float* bias; const uint16_t* mask; long long ldm;
     uint16_t* out; long long ldo;
+    int dbg;                                   // experiment switches (bg_ppo_gemm_debug): 1 no MMAs, 2 no epilogue stores, 4 no loads
 };
 
 __global__ void __launch_bounds__(512, 1) ppo_gemm_nt_kernel(const NtArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ unsigned long long bar[4];
     __shared__ uint32_t s_tmem;
+    __shared__ __align__(16) float s_bias[512];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int stage_bytes = (a.KC >> 3) * kChunk;
+    if (a.epi == 1) for (int c = tid; c < 512; c += blockDim.x) s_bias[c] = c < a.N ? a.bias[c] : 0.0f;
     unsigned char* Wg = smem;
     unsigned char* A0 = smem + ((a.w_bytes + 1023) & ~1023);
     const uint32_t Ws = smem_u32(Wg), As0 = smem_u32(A0);
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(512, 1) ppo_gemm_nt_kernel(const NtArgs a) {
     auto step_tile = [&](long long s) { return blockIdx.x + (s / n_kc) * gridDim.x; };
     // stage s (if it exists) -> buffer s % D; always one commit group per call, so that "all but the newest LA-1 groups" = stage s
     auto load = [&](long long s) {
-        if (s < n_steps) {
+        if (s < n_steps && !(a.dbg & 4)) {
             const int b = (int)(s % a.D);
             const long long row0 = a.row_begin + step_tile(s) * kRows;
             stage_tile<kRows>(As0 + (uint32_t)(b * stage_bytes), A0 + b * stage_bytes, a.A, a.lda, row0, a.row_end, (int)(s % n_kc) * a.KC, nch, tid);
@@ -136,7 +144,11 @@ __global__ void __launch_bounds__(512, 1) ppo_gemm_nt_kernel(const NtArgs a) {
     };
     uint32_t ph[4] = {0u, 0u, 0u, 0u};
     bool pending[4] = {false, false, false, false};
-    auto ensure_done = [&](int b) { if (pending[b]) { mbar_wait(&bar[b], ph[b]); ph[b] ^= 1u; pending[b] = false; } };
+    // ONE thread polls the MMA barrier, the rest wait at the CTA barrier: 512 threads spinning on an mbarrier (shared memory)
+    // starved the tensor core's operand fetches -- an SS MMA took ~400 cycles instead of ~64
+    auto ensure_done = [&](int b) {
+        if (pending[b]) { if (tid == 0) mbar_wait(&bar[b], ph[b]); __syncthreads(); ph[b] ^= 1u; pending[b] = false; }
+    };
     const int q = warp & 3, part = warp >> 2, nparts = (int)(blockDim.x >> 7);   // the warps of a TMEM lane quarter split the columns
     for (int j = 0; j < a.LA; ++j) load(j);
     for (long long s = 0; s < n_steps; ++s) {
@@ -147,7 +159,7 @@ __global__ void __launch_bounds__(512, 1) ppo_gemm_nt_kernel(const NtArgs a) {
         __syncthreads();
         ensure_done((int)((s + a.LA) % a.D));                          // the MMAs that last read the buffer stage s + LA goes into
         load(s + a.LA);
-        if (tid == 0) {
+        if (tid == 0 && !(a.dbg & 1)) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t Ab = As0 + (uint32_t)(b * stage_bytes);
             for (int ks = 0; ks < a.KC / 16; ++ks) {
@@ -168,7 +180,7 @@ __global__ void __launch_bounds__(512, 1) ppo_gemm_nt_kernel(const NtArgs a) {
             }
             umma_commit(&bar[b]);
         }
-        pending[b] = true;
+        pending[b] = !(a.dbg & 1);
         if (kc == n_kc - 1) {
             // ---- epilogue of the tile: thread = row (TMEM lane), the warps of a lane quarter split the columns
             ensure_done(b);
@@ -195,17 +207,17 @@ __global__ void __launch_bounds__(512, 1) ppo_gemm_nt_kernel(const NtArgs a) {
                     for (int j = 0; j < 16; ++j) {
                         float v0 = __uint_as_float(acc[2 * j]), v1 = __uint_as_float(acc[2 * j + 1]);
                         if (a.epi == 0) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
-                        else if (a.epi == 1) { if (2 * j < w) { v0 += __ldg(a.bias + c0 + 2 * j); v1 += __ldg(a.bias + c0 + 2 * j + 1); } }
+                        else if (a.epi == 1) { const float2 bb = *reinterpret_cast<const float2*>(&s_bias[c0 + 2 * j]); v0 += bb.x; v1 += bb.y; }
                         else {                                                       // relu'(h): h is bf16 >= 0, so "> 0" is "!= 0"
                             if ((mk[j] & 0x0000FFFFu) == 0u) v0 = 0.0f;
                             if ((mk[j] & 0xFFFF0000u) == 0u) v1 = 0.0f;
                         }
                         o[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v1)) << 16);
                     }
-                    uint4* op = reinterpret_cast<uint4*>(a.out + row * a.ldo + c0);
+                    uint16_t* op = a.out + row * a.ldo + c0;               // rows are 256 / 288 / 1024 bytes: every block is sector aligned
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (8 * j < w) op[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    for (int j = 0; j < 2; ++j)
+                        if (16 * j < w && !(a.dbg & 2)) st_global_256(op + 16 * j, o + 8 * j);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -228,6 +240,8 @@ struct TnArgs {
     int mode;                                  // 0 dWap class A (N = 144: 128 slots, value head at column 128), 1 dWap class B (slot = col_base + n), 2 dW1p (N = 208)
     int col_base;
     float* grad;                               // flat f32 gradient (kNumParams)
+    float* scratch;                            // mode 2: [199][128] f32, dW1p transposed (zeroed by the caller)
+    int dbg;
 };
 
 constexpr int kTnRows = 64;               // sample rows per stage of the TN kernel (four MMA K-steps)
@@ -256,7 +270,7 @@ __global__ void __launch_bounds__(512, 1) ppo_gemm_tn_kernel(const TnArgs a) {
     const long long n_tiles = (a.row_end - a.row_begin + kTnRows - 1) / kTnRows;
     const long long n_steps = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     auto load = [&](long long s) {
-        if (s < n_steps) {
+        if (s < n_steps && !(a.dbg & 4)) {
             const int b = (int)(s % kTnD);
             const long long row0 = a.row_begin + (blockIdx.x + s * gridDim.x) * kTnRows;
             stage_tile<kTnRows>(S0 + (uint32_t)(b * stage_bytes), smem + b * stage_bytes, a.A, a.lda, row0, a.row_end, 0, 16, tid);
@@ -266,7 +280,9 @@ __global__ void __launch_bounds__(512, 1) ppo_gemm_tn_kernel(const TnArgs a) {
     };
     uint32_t ph[kTnD] = {};
     bool pending[kTnD] = {};
-    auto ensure_done = [&](int b) { if (pending[b]) { mbar_wait(&bar[b], ph[b]); ph[b] ^= 1u; pending[b] = false; } };
+    auto ensure_done = [&](int b) {                                    // (one poller, see ppo_gemm_nt_kernel)
+        if (pending[b]) { if (tid == 0) mbar_wait(&bar[b], ph[b]); __syncthreads(); ph[b] ^= 1u; pending[b] = false; }
+    };
     for (int j = 0; j < kTnLA; ++j) load(j);
     const uint32_t idesc = idesc_bf16(128, a.N, 1, 1);
     for (long long s = 0; s < n_steps; ++s) {
@@ -276,7 +292,7 @@ __global__ void __launch_bounds__(512, 1) ppo_gemm_tn_kernel(const TnArgs a) {
         __syncthreads();
         ensure_done((int)((s + kTnLA) % kTnD));                        // the MMAs that last read that buffer
         load(s + kTnLA);
-        if (tid == 0) {
+        if (tid == 0 && !(a.dbg & 1)) {
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t Ab = S0 + (uint32_t)(b * stage_bytes), Bb = Ab + (uint32_t)a_bytes;
 #pragma unroll 1
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(512, 1) ppo_gemm_tn_kernel(const TnArgs a) {
             }
             umma_commit(&bar[b]);
         }
-        pending[b] = true;
+        pending[b] = !(a.dbg & 1);
     }
     for (int i = 0; i < kTnD; ++i) ensure_done(i);
     cp_async_wait_but(0);
@@ -309,7 +325,7 @@ __global__ void __launch_bounds__(512, 1) ppo_gemm_tn_kernel(const TnArgs a) {
                 float* dst = nullptr;
                 if (a.mode == 0) { if (n < 128) dst = a.grad + kOffWa + n * 128 + m; else if (n == 128) dst = a.grad + kOffWv + m; }
                 else if (a.mode == 1) { const int slot = a.col_base + n; if (slot < 500) dst = a.grad + kOffWa + slot * 128 + m; else if (slot == 500) dst = a.grad + kOffWv + m; }
-                else { if (n < 198) dst = a.grad + kOffW1 + m * 198 + n; else if (n == 198) dst = a.grad + kOffB1 + m; }
+                else { if (n <= 198) dst = a.scratch + n * 128 + m; }       // dW1p^T: lanes = consecutive addresses (finished by grad_w1_finish_kernel)
                 if (dst) atomicAdd(dst, v);
             }
         }
@@ -317,6 +333,16 @@ __global__ void __launch_bounds__(512, 1) ppo_gemm_tn_kernel(const TnArgs a) {
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(ncols) : "memory");
+}
+
+// dW1p^T [199][128] (scratch of GRAD_W1: with lane = hidden unit the atomics of the accumulator tile are only coalesced in this
+// orientation; fc1.weight is [hidden][feature], where they hit a different sector each: 115 us per launch) -> fc1.weight, fc1.bias
+__global__ void grad_w1_finish_kernel(const float* __restrict__ scratch, float* __restrict__ grad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;               // i = m * 199 + n
+    if (i >= 128 * 199) return;
+    const int m = i / 199, n = i - m * 199;
+    const float v = scratch[n * 128 + m];
+    if (n < 198) grad[kOffW1 + m * 198 + n] = v; else grad[kOffB1 + m] = v;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -361,6 +387,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 using namespace bg;
 
+static int g_ppo_gemm_dbg = 0;
+extern "C" int bg_ppo_gemm_debug(int flags) { g_ppo_gemm_dbg = flags; return BG_OK; }
+
 extern "C" int bg_ppo_pack_weights(const float* flat_params, uint16_t* w1p, uint16_t* wap_a, uint16_t* wap_b, float* bias_a,
                                    float* bias_b, void* stream) {
     if (!flat_params || !w1p || !wap_a || !wap_b || !bias_a || !bias_b) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_pack_weights: null pointer");
@@ -375,7 +404,7 @@ extern "C" int bg_ppo_gemm_nt(int op, const uint16_t* A, long long row_begin, lo
     if (!A || !W || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: null pointer");
     NtArgs a{};
     int threads = 256, per_sm = 1;
-    a.A = A; a.row_begin = row_begin; a.row_end = row_end; a.W = W; a.bias = bias; a.mask = h_mask; a.ldm = 128; a.out = out;
+    a.A = A; a.row_begin = row_begin; a.row_end = row_end; a.W = W; a.bias = bias; a.mask = h_mask; a.ldm = 128; a.out = out; a.dbg = g_ppo_gemm_dbg;
     switch (op) {
         // (ring D / stages in flight LA: what fits beside the weight tile in 220 KB)
         // A step is serial inside a CTA (issue the loads, multiply, epilogue), so the phases are overlapped ACROSS CTAs: two
@@ -402,10 +431,11 @@ extern "C" int bg_ppo_gemm_nt(int op, const uint16_t* A, long long row_begin, lo
 }
 
 extern "C" int bg_ppo_gemm_tn(int op, const uint16_t* A, const uint16_t* B, long long row_begin, long long row_end,
-                              float* flat_grad, void* stream) {
+                              float* flat_grad, float* scratch, void* stream) {
     if (row_begin < 0 || row_end < row_begin) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_tn: bad row range");
     if (row_end == row_begin) return BG_OK;
     if (!A || !B || !flat_grad) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_tn: null pointer");
+    if (op == BG_PPO_OP_GRAD_W1 && !scratch) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_tn: GRAD_W1 needs the scratch");
     cudaError_t e = cudaFuncSetAttribute(ppo_gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return bg_set_error(e, "bg_ppo_gemm_tn: cudaFuncSetAttribute");
     const long long tiles = (row_end - row_begin + kTnRows - 1) / kTnRows;
@@ -417,10 +447,18 @@ extern "C" int bg_ppo_gemm_tn(int op, const uint16_t* A, const uint16_t* B, long
         return bg_set_error(cudaGetLastError(), "bg_ppo_gemm_tn: launch");
     };
     TnArgs a{};
-    a.A = A; a.lda = 128; a.B = B; a.row_begin = row_begin; a.row_end = row_end; a.grad = flat_grad;
+    a.A = A; a.lda = 128; a.B = B; a.row_begin = row_begin; a.row_end = row_end; a.grad = flat_grad; a.scratch = scratch; a.dbg = g_ppo_gemm_dbg;
     switch (op) {
         case BG_PPO_OP_GRAD_WA_A: a.ldb = 144; a.N = 144; a.mode = 0; return launch(a);
-        case BG_PPO_OP_GRAD_W1:   a.ldb = 208; a.N = 208; a.mode = 2; return launch(a);
+        case BG_PPO_OP_GRAD_W1: {
+            a.ldb = 208; a.N = 208; a.mode = 2;
+            cudaError_t e2 = cudaMemsetAsync(scratch, 0, sizeof(float) * 199 * 128, (cudaStream_t)stream);
+            if (e2 != cudaSuccess) return bg_set_error(e2, "bg_ppo_gemm_tn: memset");
+            const int rc = launch(a);
+            if (rc != BG_OK) return rc;
+            grad_w1_finish_kernel<<<(128 * 199 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch, flat_grad);   // (overwrites fc1.*: nobody else adds to them)
+            return bg_set_error(cudaGetLastError(), "bg_ppo_gemm_tn: finish launch");
+        }
         case BG_PPO_OP_GRAD_WA_B:
             for (int cb = 0; cb < 4; ++cb) {                          // four blocks of 128 action slots (value head = slot 500, in the last)
                 a.ldb = 512; a.N = 128; a.mode = 1; a.col_base = 128 * cb; a.B = B + 128 * cb;

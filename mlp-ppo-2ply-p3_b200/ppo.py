@@ -247,8 +247,8 @@ class TensorCoreUpdate:
         self.bias_a, self.bias_b = z((144,), torch.float32), z((512,), torch.float32)
         self.gflat, self.pflat = z((90101,), torch.float32), z((90101,), torch.float32)
         self.dbias, self.sums = z((512,), torch.float32), z((3,), torch.float32)
+        self.w1t = z((199 * 128,), torch.float32)              # scratch of GRAD_W1 (dW1p transposed)
         self.B = -1
-        self._sorted_key = None
 
     # the class of a sample: csrc/ppo.cu loss_row_is_packed
     @staticmethod
@@ -312,9 +312,9 @@ class TensorCoreUpdate:
                                              self.dbias.data_ptr(), self.sums.data_ptr(), st), "bg_ppo_loss_grad_classes")
             check(L.bg_ppo_gemm_nt(3, self.dla.data_ptr(), 0, n_a, self.wap_a.data_ptr(), None, hp, dp, st), "ppo gemm DPRE_A")
             check(L.bg_ppo_gemm_nt(4, dlb_off, n_a, B, self.wap_b.data_ptr(), None, hp, dp, st), "ppo gemm DPRE_B")
-            check(L.bg_ppo_gemm_tn(5, hp, self.dla.data_ptr(), 0, n_a, gflat.data_ptr(), st), "ppo gemm GRAD_WA_A")
-            check(L.bg_ppo_gemm_tn(6, hp, dlb_off, n_a, B, gflat.data_ptr(), st), "ppo gemm GRAD_WA_B")
-            check(L.bg_ppo_gemm_tn(7, dp, xp, 0, B, gflat.data_ptr(), st), "ppo gemm GRAD_W1")
+            check(L.bg_ppo_gemm_tn(5, hp, self.dla.data_ptr(), 0, n_a, gflat.data_ptr(), None, st), "ppo gemm GRAD_WA_A")
+            check(L.bg_ppo_gemm_tn(6, hp, dlb_off, n_a, B, gflat.data_ptr(), None, st), "ppo gemm GRAD_WA_B")
+            check(L.bg_ppo_gemm_tn(7, dp, xp, 0, B, gflat.data_ptr(), self.w1t.data_ptr(), st), "ppo gemm GRAD_W1")
         # bias gradients = column sums of dlogits, accumulated by the loss kernels
         OFF_BA, OFF_BV = 128 * 198 + 128 + 500 * 128, 128 * 198 + 128 + 500 * 128 + 500 + 128
         gflat[OFF_BA:OFF_BA + ACTIONS].copy_(self.dbias[:ACTIONS])

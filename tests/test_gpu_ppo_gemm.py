@@ -82,9 +82,10 @@ def test_backward_gemms_match_torch(B, n_a):
     want = torch.cat([dla[:n_a].float() @ S["WapA"], dlb[:B - n_a].float() @ S["WapB"]], 0) * mask
     _close(dpre, want)
     gflat = torch.zeros(90101, device=DEV)
-    check(L.bg_ppo_gemm_tn(5, h.data_ptr(), dla.data_ptr(), 0, n_a, gflat.data_ptr(), s), "GRAD_WA_A")
-    check(L.bg_ppo_gemm_tn(6, h.data_ptr(), dlb.data_ptr() - n_a * 1024, n_a, B, gflat.data_ptr(), s), "GRAD_WA_B")
-    check(L.bg_ppo_gemm_tn(7, dpre.data_ptr(), x.data_ptr(), 0, B, gflat.data_ptr(), s), "GRAD_W1")
+    scratch = torch.empty(199 * 128, device=DEV)
+    check(L.bg_ppo_gemm_tn(5, h.data_ptr(), dla.data_ptr(), 0, n_a, gflat.data_ptr(), None, s), "GRAD_WA_A")
+    check(L.bg_ppo_gemm_tn(6, h.data_ptr(), dlb.data_ptr() - n_a * 1024, n_a, B, gflat.data_ptr(), None, s), "GRAD_WA_B")
+    check(L.bg_ppo_gemm_tn(7, dpre.data_ptr(), x.data_ptr(), 0, B, gflat.data_ptr(), scratch.data_ptr(), s), "GRAD_W1")
     torch.cuda.synchronize()
     gA = dla[:n_a].float().t() @ h[:n_a].float()                       # (144,128)
     gB = dlb[:B - n_a].float().t() @ h[n_a:].float()                   # (512,128)
