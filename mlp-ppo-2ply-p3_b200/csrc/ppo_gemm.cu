@@ -53,9 +53,15 @@ __device__ __forceinline__ void st_global_256(void* p, const uint32_t* v) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]),
                  "r"(v[6]), "r"(v[7]) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_but(int newest) {          // wait until at most `newest` (0 or 1) commit groups are pending
-    if (newest >= 1) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+__device__ __forceinline__ void cp_async_wait_but(int newest) {          // wait until at most `newest` (0, 1 or 2) commit groups are pending
+    if (newest >= 2) asm volatile("cp.async.wait_group 2;\n" ::: "memory");
+    else if (newest == 1) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     else asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+// one lane polls an mbarrier for its warp (every polling thread is shared-memory traffic the tensor core's operand fetches compete with)
+__device__ __forceinline__ void warp_wait(unsigned long long* bar, uint32_t parity, int lane) {
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
 }
 __device__ __forceinline__ uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u : (n <= 64 ? 64u : (n <= 128 ? 128u : (n <= 256 ? 256u : 512u))); }
 
@@ -66,8 +72,7 @@ __device__ __forceinline__ uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u 
 // Rows >= row_end are zero-filled.
 template <int ROWS>
 __device__ __forceinline__ void stage_tile(uint32_t dst, unsigned char* dst_generic, const uint16_t* __restrict__ src, long long ld,
-                                           long long row0, long long row_end, int col0, int nch, int tid) {
-    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+                                           long long row0, long long row_end, int col0, int nch, int warp, int nwarps, int lane) {
     constexpr int RB = ROWS / 16;                                      // 16-row blocks of the tile
     const int r_in = (lane >> 3) * 4 + (lane & 3), c_in = (lane >> 2) & 1;
     const uint16_t* base = src + row0 * ld + col0;
@@ -94,16 +99,21 @@ struct NtArgs {
     const uint16_t* W; int w_bytes; int w_rows;   // packed weight tile (chunk layout) and its number of rows
     int N, K, KC;                              // output columns (<= 512), reduction length, K per stage (K % KC == 0, KC % 16 == 0)
     int b_mn;                                  // 0: W rows = N, columns = K (K-major B);  1: W rows = K, columns = N = 128 (MN-major B)
-    int D, LA;                                 // ring of D stage buffers, LA stages loading ahead of the one being multiplied (D > LA)
+    int D, LA;                                 // ring of D stage buffers (<= 8); LA unused (the producers keep min(D-1, 3) stages in flight)
     int epi;                                   // 0 relu, 1 + bias, 2 * [mask > 0]
     const float* bias; const uint16_t* mask; long long ldm;
     uint16_t* out; long long ldo;
     int dbg;                                   // experiment switches (bg_ppo_gemm_debug): 1 no MMAs, 2 no epilogue stores, 4 no loads
 };
 
-__global__ void __launch_bounds__(512, 1) ppo_gemm_nt_kernel(const NtArgs a) {
+// Warp-specialised like K4 (mlp.cu): warps 0-7 epilogue (warp w: TMEM lane quarter w % 4, column half w / 4), warps 8-11
+// producers (cp.async of the A tiles into a ring of D stage buffers, up to three stages in flight per thread), warp 12 the
+// MMA issuer; two accumulators in TMEM (when N <= 256), so loading tile t+2, multiplying tile t+1 and writing out tile t
+// overlap.  (Before this split a step was serial inside the CTA and the kernel ran at 1.8 .. 3 TB/s.)
+constexpr int kNtEpiWarps = 8, kNtProdWarps = 4, kNtThreads = 32 * (kNtEpiWarps + kNtProdWarps + 1);
+__global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ unsigned long long bar[4];
+    __shared__ unsigned long long full[8], empty[8], acc_full[2], acc_empty[2];
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_bias[512];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -113,99 +123,115 @@ __global__ void __launch_bounds__(512, 1) ppo_gemm_nt_kernel(const NtArgs a) {
     unsigned char* A0 = smem + ((a.w_bytes + 1023) & ~1023);
     const uint32_t Ws = smem_u32(Wg), As0 = smem_u32(A0);
     for (int c = tid; c < a.w_bytes / 16; c += blockDim.x) cp_async16_s(Ws + 16u * c, reinterpret_cast<const unsigned char*>(a.W) + 16 * c);
-    // (W travels in the first stage's commit group)
+    cp_async_commit();
+    cp_async_wait_but(0);
+    const int nacc = a.N <= 256 ? 2 : 1;                               // accumulators in TMEM (columns 0.. and 256..)
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(&bar[i], 1);
+        for (int i = 0; i < 8; ++i) { mbar_init(&full[i], kNtProdWarps * 32); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kNtEpiWarps * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    const uint32_t ncols = tmem_cols_for(a.N);
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(&s_tmem)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the weight tile is visible to the tensor-core proxy
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = s_tmem;
     const long long n_tiles = (a.row_end - a.row_begin + kRows - 1) / kRows;
     const int n_kc = a.K / a.KC, nch = a.KC >> 3;
-    // steps of this CTA: (tile, K chunk), tiles blockIdx.x, + gridDim.x, ...
-    long long my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const long long n_steps = my_tiles * n_kc;
-    auto step_tile = [&](long long s) { return blockIdx.x + (s / n_kc) * gridDim.x; };
-    // stage s (if it exists) -> buffer s % D; always one commit group per call, so that "all but the newest LA-1 groups" = stage s
-    auto load = [&](long long s) {
-        if (s < n_steps && !(a.dbg & 4)) {
+    const long long my_tiles = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long n_steps = my_tiles * n_kc;                         // steps of this CTA: (tile, K chunk)
+    auto tile_of = [&](long long t) { return blockIdx.x + t * gridDim.x; };
+
+    if (warp >= kNtEpiWarps && warp < kNtEpiWarps + kNtProdWarps) {
+        // ================= producers =================
+        const int pw = warp - kNtEpiWarps;
+        const int ahead = a.D >= 4 ? 2 : (a.D == 3 ? 1 : 0);           // stages this thread keeps in flight beyond the one it completes
+        for (long long s = 0; s < n_steps; ++s) {
             const int b = (int)(s % a.D);
-            const long long row0 = a.row_begin + step_tile(s) * kRows;
-            stage_tile<kRows>(As0 + (uint32_t)(b * stage_bytes), A0 + b * stage_bytes, a.A, a.lda, row0, a.row_end, (int)(s % n_kc) * a.KC, nch, tid);
+            const uint32_t it = (uint32_t)(s / a.D);
+            warp_wait(&empty[b], (it & 1u) ^ 1u, lane);                // the MMAs that read this buffer D steps ago are done
+            if (!(a.dbg & 4))
+                stage_tile<kRows>(As0 + (uint32_t)(b * stage_bytes), A0 + b * stage_bytes, a.A, a.lda, a.row_begin + tile_of(s / n_kc) * kRows,
+                                  a.row_end, (int)(s % n_kc) * a.KC, nch, pw, kNtProdWarps, lane);
+            cp_async_commit();
+            if (s >= ahead) {                                          // stage s - ahead has landed: hand it to the MMA warp
+                cp_async_wait_but(ahead);
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                mbar_arrive(&full[(int)((s - ahead) % a.D)]);
+            }
         }
-        cp_async_commit();
-    };
-    uint32_t ph[4] = {0u, 0u, 0u, 0u};
-    bool pending[4] = {false, false, false, false};
-    // ONE thread polls the MMA barrier, the rest wait at the CTA barrier: 512 threads spinning on an mbarrier (shared memory)
-    // starved the tensor core's operand fetches -- an SS MMA took ~400 cycles instead of ~64
-    auto ensure_done = [&](int b) {
-        if (pending[b]) { if (tid == 0) mbar_wait(&bar[b], ph[b]); __syncthreads(); ph[b] ^= 1u; pending[b] = false; }
-    };
-    const int q = warp & 3, part = warp >> 2, nparts = (int)(blockDim.x >> 7);   // the warps of a TMEM lane quarter split the columns
-    for (int j = 0; j < a.LA; ++j) load(j);
-    for (long long s = 0; s < n_steps; ++s) {
-        const int b = (int)(s % a.D);
-        const int kc = (int)(s % n_kc);
-        cp_async_wait_but(a.LA - 1);                                   // this thread's share of stage s (and of W) has landed
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); // ... and is visible to the tensor-core proxy
-        __syncthreads();
-        ensure_done((int)((s + a.LA) % a.D));                          // the MMAs that last read the buffer stage s + LA goes into
-        load(s + a.LA);
-        if (tid == 0 && !(a.dbg & 1)) {
+        for (long long s = n_steps > ahead ? n_steps - ahead : 0; s < n_steps; ++s) {
+            cp_async_wait_but((int)(n_steps - 1 - s));
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            mbar_arrive(&full[(int)(s % a.D)]);
+        }
+    } else if (warp == kNtEpiWarps + kNtProdWarps) {
+        // ================= MMA issuer =================
+        for (long long s = 0; s < n_steps; ++s) {
+            const int b = (int)(s % a.D);
+            const uint32_t it = (uint32_t)(s / a.D);
+            const long long t = s / n_kc;
+            const int kc = (int)(s % n_kc), acc = (int)(t % nacc);
+            warp_wait(&full[b], it & 1u, lane);
+            if (kc == 0) warp_wait(&acc_empty[acc], ((uint32_t)(t / nacc) & 1u) ^ 1u, lane);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const uint32_t Ab = As0 + (uint32_t)(b * stage_bytes);
-            for (int ks = 0; ks < a.KC / 16; ++ks) {
-                const int kg = kc * a.KC + ks * 16;                    // first reduction index of this MMA
-                const uint64_t da = make_smem_desc_kmajor(Ab + (uint32_t)(ks * 2 * kChunk), kChunk, 128);
-                const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
-                if (a.b_mn) {
-                    // W rows = reduction index (action slots), columns = N = 128 hidden units: MN-major, K groups 128 B apart
-                    const uint64_t db = make_smem_desc_kmajor(Ws + (uint32_t)(kg * 16), 128, (uint32_t)(a.w_rows * 16));
-                    mma_bf16_ss(tmem, da, db, idesc_bf16(128, a.N, 0, 1), acc);
-                } else {
-                    for (int n0 = 0; n0 < a.N; n0 += 256) {
-                        const int nn = a.N - n0 < 256 ? a.N - n0 : 256;
-                        const uint64_t db = make_smem_desc_kmajor(Ws + (uint32_t)((kg >> 3) * a.w_rows * 16 + n0 * 16), (uint32_t)(a.w_rows * 16), 128);
-                        mma_bf16_ss(tmem + (uint32_t)n0, da, db, idesc_bf16(128, nn, 0, 0), acc);
+            if (lane == 0 && !(a.dbg & 1)) {
+                const uint32_t Ab = As0 + (uint32_t)(b * stage_bytes), D0 = tmem + (uint32_t)(acc * 256);
+                for (int ks = 0; ks < a.KC / 16; ++ks) {
+                    const int kg = kc * a.KC + ks * 16;                // first reduction index of this MMA
+                    const uint64_t da = make_smem_desc_kmajor(Ab + (uint32_t)(ks * 2 * kChunk), kChunk, 128);
+                    const uint32_t accum = (kc > 0 || ks > 0) ? 1u : 0u;
+                    if (a.b_mn) {
+                        // W rows = reduction index (action slots), columns = N = 128 hidden units: MN-major, K groups 128 B apart
+                        const uint64_t db = make_smem_desc_kmajor(Ws + (uint32_t)(kg * 16), 128, (uint32_t)(a.w_rows * 16));
+                        mma_bf16_ss(D0, da, db, idesc_bf16(128, a.N, 0, 1), accum);
+                    } else {
+                        for (int n0 = 0; n0 < a.N; n0 += 256) {
+                            const int nn = a.N - n0 < 256 ? a.N - n0 : 256;
+                            const uint64_t db = make_smem_desc_kmajor(Ws + (uint32_t)((kg >> 3) * a.w_rows * 16 + n0 * 16), (uint32_t)(a.w_rows * 16), 128);
+                            mma_bf16_ss(D0 + (uint32_t)n0, da, db, idesc_bf16(128, nn, 0, 0), accum);
+                        }
                     }
                 }
             }
-            umma_commit(&bar[b]);
+            if (lane == 0) {
+                umma_commit(&empty[b]);                                // the stage buffer may be refilled
+                if (kc == n_kc - 1) umma_commit(&acc_full[acc]);       // the tile's accumulator is complete
+            }
+            __syncwarp();
         }
-        pending[b] = !(a.dbg & 1);
-        if (kc == n_kc - 1) {
-            // ---- epilogue of the tile: thread = row (TMEM lane), the warps of a lane quarter split the columns
-            ensure_done(b);
+    } else if (warp < kNtEpiWarps) {
+        // ================= epilogue: thread = row (TMEM lane), the two warps of a lane quarter split the columns =================
+        const int q = warp & 3, part = warp >> 2;
+        for (long long t = 0; t < my_tiles; ++t) {
+            const int acc = (int)(t % nacc);
+            warp_wait(&acc_full[acc], (uint32_t)(t / nacc) & 1u, lane);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const long long row = a.row_begin + step_tile(s) * kRows + q * 32 + lane;
+            const long long row = a.row_begin + tile_of(t) * kRows + q * 32 + lane;
             const bool live = row < a.row_end;
             const int nblk = (a.N + 31) >> 5;                          // blocks of 32 columns (the last may be 16 wide: N = 144)
-            for (int blk = part; blk < nblk; blk += nparts) {
+            for (int blk = part; blk < nblk; blk += 2) {
                 const int c0 = 32 * blk, w = a.N - c0 < 32 ? a.N - c0 : 32;
-                uint32_t acc[32];
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-                if (w == 32) tmem_ld32(taddr, acc);
-                else { tmem_ld8(taddr, acc); tmem_ld8(taddr + 8, acc + 8); }       // w == 16
+                uint32_t av[32];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + c0);
+                if (w == 32) tmem_ld32(taddr, av);
+                else { tmem_ld8(taddr, av); tmem_ld8(taddr + 8, av + 8); }         // w == 16
                 tmem_ld_wait();
                 if (live) {
                     uint32_t mk[16];
                     if (a.epi == 2) {
                         const uint4* mp = reinterpret_cast<const uint4*>(a.mask + row * a.ldm + c0);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) { const uint4 v = (4 * j * 2 < w) ? __ldg(mp + j) : make_uint4(0u, 0u, 0u, 0u); mk[4 * j] = v.x; mk[4 * j + 1] = v.y; mk[4 * j + 2] = v.z; mk[4 * j + 3] = v.w; }
+                        for (int j = 0; j < 4; ++j) { const uint4 v = (8 * j < w) ? __ldg(mp + j) : make_uint4(0u, 0u, 0u, 0u); mk[4 * j] = v.x; mk[4 * j + 1] = v.y; mk[4 * j + 2] = v.z; mk[4 * j + 3] = v.w; }
                     }
                     uint32_t o[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        float v0 = __uint_as_float(acc[2 * j]), v1 = __uint_as_float(acc[2 * j + 1]);
+                        float v0 = __uint_as_float(av[2 * j]), v1 = __uint_as_float(av[2 * j + 1]);
                         if (a.epi == 0) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
                         else if (a.epi == 1) { const float2 bb = *reinterpret_cast<const float2*>(&s_bias[c0 + 2 * j]); v0 += bb.x; v1 += bb.y; }
                         else {                                                       // relu'(h): h is bf16 >= 0, so "> 0" is "!= 0"
@@ -221,14 +247,12 @@ __global__ void __launch_bounds__(512, 1) ppo_gemm_nt_kernel(const NtArgs a) {
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            __syncthreads();                                           // everybody has read the accumulators: the next tile may overwrite them
+            mbar_arrive(&acc_empty[acc]);                              // the accumulator may be overwritten
         }
     }
-    for (int i = 0; i < 4; ++i) ensure_done(i);
-    cp_async_wait_but(0);
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(ncols) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem), "r"(512u) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -241,21 +265,24 @@ struct TnArgs {
     int col_base;
     float* grad;                               // flat f32 gradient (kNumParams)
     float* scratch;                            // mode 2: [199][128] f32, dW1p transposed (zeroed by the caller)
+    int D;                                     // stage ring size
     int dbg;
 };
 
 constexpr int kTnRows = 64;               // sample rows per stage of the TN kernel (four MMA K-steps)
-constexpr int kTnD = 2, kTnLA = 1;        // double buffer per CTA; two or three CTAs per SM overlap each other's phases
-__global__ void __launch_bounds__(512, 1) ppo_gemm_tn_kernel(const TnArgs a) {
+constexpr int kTnProdWarps = 4, kTnThreads = 32 * (kTnProdWarps + 1);
+// warps 0-3: producers (cp.async ring of D stages, three in flight per thread), then the epilogue; warp 4: MMA issuer
+__global__ void __launch_bounds__(kTnThreads, 1) ppo_gemm_tn_kernel(const TnArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ unsigned long long bar[kTnD];
+    __shared__ unsigned long long full[8], empty[8], done_bar;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int CS = kTnRows * 16;                                   // chunk-column stride of a stage tile
     const int a_bytes = 16 * CS, b_bytes = (a.N >> 3) * CS, stage_bytes = a_bytes + b_bytes;
     const uint32_t S0 = smem_u32(smem);
     if (tid == 0) {
-        for (int i = 0; i < kTnD; ++i) mbar_init(&bar[i], 1);
+        for (int i = 0; i < 8; ++i) { mbar_init(&full[i], kTnProdWarps * 32); mbar_init(&empty[i], 1); }
+        mbar_init(&done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     const uint32_t ncols = tmem_cols_for(a.N);
@@ -269,55 +296,69 @@ __global__ void __launch_bounds__(512, 1) ppo_gemm_tn_kernel(const TnArgs a) {
     const uint32_t tmem = s_tmem;
     const long long n_tiles = (a.row_end - a.row_begin + kTnRows - 1) / kTnRows;
     const long long n_steps = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    auto load = [&](long long s) {
-        if (s < n_steps && !(a.dbg & 4)) {
-            const int b = (int)(s % kTnD);
-            const long long row0 = a.row_begin + (blockIdx.x + s * gridDim.x) * kTnRows;
-            stage_tile<kTnRows>(S0 + (uint32_t)(b * stage_bytes), smem + b * stage_bytes, a.A, a.lda, row0, a.row_end, 0, 16, tid);
-            stage_tile<kTnRows>(S0 + (uint32_t)(b * stage_bytes + a_bytes), smem + b * stage_bytes + a_bytes, a.B, a.ldb, row0, a.row_end, 0, a.N >> 3, tid);
-        }
-        cp_async_commit();
-    };
-    uint32_t ph[kTnD] = {};
-    bool pending[kTnD] = {};
-    auto ensure_done = [&](int b) {                                    // (one poller, see ppo_gemm_nt_kernel)
-        if (pending[b]) { if (tid == 0) mbar_wait(&bar[b], ph[b]); __syncthreads(); ph[b] ^= 1u; pending[b] = false; }
-    };
-    for (int j = 0; j < kTnLA; ++j) load(j);
-    const uint32_t idesc = idesc_bf16(128, a.N, 1, 1);
-    for (long long s = 0; s < n_steps; ++s) {
-        const int b = (int)(s % kTnD);
-        cp_async_wait_but(kTnLA - 1);
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        __syncthreads();
-        ensure_done((int)((s + kTnLA) % kTnD));                        // the MMAs that last read that buffer
-        load(s + kTnLA);
-        if (tid == 0 && !(a.dbg & 1)) {
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const uint32_t Ab = S0 + (uint32_t)(b * stage_bytes), Bb = Ab + (uint32_t)a_bytes;
-#pragma unroll 1
-            for (int ks = 0; ks < kTnRows / 16; ++ks) {
-                // both tiles are read MN-major: the reduction index is the ROW (sample); 16 rows = two 8-row groups 128 B apart
-                const uint64_t da = make_smem_desc_kmajor(Ab + (uint32_t)(ks * 256), 128, CS);
-                const uint64_t db = make_smem_desc_kmajor(Bb + (uint32_t)(ks * 256), 128, CS);
-                mma_bf16_ss(tmem, da, db, idesc, (s > 0 || ks > 0) ? 1u : 0u);
+    const int D = a.D;
+    if (warp < kTnProdWarps) {
+        // ================= producers =================
+        const int ahead = D >= 4 ? 2 : (D == 3 ? 1 : 0);
+        for (long long s = 0; s < n_steps; ++s) {
+            const int b = (int)(s % D);
+            const uint32_t it = (uint32_t)(s / D);
+            warp_wait(&empty[b], (it & 1u) ^ 1u, lane);
+            if (!(a.dbg & 4)) {
+                const long long row0 = a.row_begin + (blockIdx.x + s * gridDim.x) * kTnRows;
+                stage_tile<kTnRows>(S0 + (uint32_t)(b * stage_bytes), smem + b * stage_bytes, a.A, a.lda, row0, a.row_end, 0, 16, warp, kTnProdWarps, lane);
+                stage_tile<kTnRows>(S0 + (uint32_t)(b * stage_bytes + a_bytes), smem + b * stage_bytes + a_bytes, a.B, a.ldb, row0, a.row_end, 0, a.N >> 3,
+                                    warp, kTnProdWarps, lane);
             }
-            umma_commit(&bar[b]);
+            cp_async_commit();
+            if (s >= ahead) {
+                cp_async_wait_but(ahead);
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                mbar_arrive(&full[(int)((s - ahead) % D)]);
+            }
         }
-        pending[b] = !(a.dbg & 1);
+        for (long long s = n_steps > ahead ? n_steps - ahead : 0; s < n_steps; ++s) {
+            cp_async_wait_but((int)(n_steps - 1 - s));
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            mbar_arrive(&full[(int)(s % D)]);
+        }
+    } else {
+        // ================= MMA issuer =================
+        const uint32_t idesc = idesc_bf16(128, a.N, 1, 1);
+        for (long long s = 0; s < n_steps; ++s) {
+            const int b = (int)(s % D);
+            const uint32_t it = (uint32_t)(s / D);
+            warp_wait(&full[b], it & 1u, lane);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (lane == 0) {
+                if (!(a.dbg & 1)) {
+                    const uint32_t Ab = S0 + (uint32_t)(b * stage_bytes), Bb = Ab + (uint32_t)a_bytes;
+#pragma unroll 1
+                    for (int ks = 0; ks < kTnRows / 16; ++ks) {
+                        // both tiles are read MN-major: the reduction index is the ROW (sample); 16 rows = two 8-row groups 128 B apart
+                        const uint64_t da = make_smem_desc_kmajor(Ab + (uint32_t)(ks * 256), 128, CS);
+                        const uint64_t db = make_smem_desc_kmajor(Bb + (uint32_t)(ks * 256), 128, CS);
+                        mma_bf16_ss(tmem, da, db, idesc, (s > 0 || ks > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[b]);
+                if (s == n_steps - 1) umma_commit(&done_bar);
+            }
+            __syncwarp();
+        }
     }
-    for (int i = 0; i < kTnD; ++i) ensure_done(i);
-    cp_async_wait_but(0);
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    if (n_steps > 0) {
-        // accumulator: lane = hidden unit m, column = n.  Thread = (m, half of the columns).
-        const int q = warp & 3, part = warp >> 2, nparts = (int)(blockDim.x >> 7);
+    if (n_steps > 0 && warp < 4) {
+        // ---- epilogue: accumulator lane = hidden unit m, column = n; warp w reads the lanes of its quarter
+        warp_wait(&done_bar, 0u, lane);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const int q = warp & 3;
         const int m = q * 32 + lane;
         const int nblk = a.N >> 3;
-        for (int blk = part; blk < nblk; blk += nparts) {
+        for (int blk = 0; blk < nblk; ++blk) {
             uint32_t acc[8];
             tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(8 * blk), acc);
             tmem_ld_wait();
+            if (a.dbg & 1) continue;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int n = 8 * blk + j;
@@ -403,17 +444,15 @@ extern "C" int bg_ppo_gemm_nt(int op, const uint16_t* A, long long row_begin, lo
     if (row_end == row_begin) return BG_OK;
     if (!A || !W || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: null pointer");
     NtArgs a{};
-    int threads = 256, per_sm = 1;
     a.A = A; a.row_begin = row_begin; a.row_end = row_end; a.W = W; a.bias = bias; a.mask = h_mask; a.ldm = 128; a.out = out; a.dbg = g_ppo_gemm_dbg;
     switch (op) {
         // (ring D / stages in flight LA: what fits beside the weight tile in 220 KB)
-        // A step is serial inside a CTA (issue the loads, multiply, epilogue), so the phases are overlapped ACROSS CTAs: two
-        // 256-thread CTAs per SM where the weight tile leaves room (class A), one 512-thread CTA otherwise
-        case BG_PPO_OP_HIDDEN:   a.lda = 208; a.N = 128; a.K = 208; a.KC = 208; a.w_rows = 128; a.b_mn = 0; a.epi = 0; a.ldo = 128; a.D = 3; a.LA = 2; threads = 512; per_sm = 1; break;
-        case BG_PPO_OP_LOGITS_A: a.lda = 128; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 1; a.ldo = 144; a.D = 2; a.LA = 1; threads = 256; per_sm = 2; break;
-        case BG_PPO_OP_LOGITS_B: a.lda = 128; a.N = 512; a.K = 128; a.KC = 128; a.w_rows = 512; a.b_mn = 0; a.epi = 1; a.ldo = 512; a.D = 2; a.LA = 1; threads = 512; per_sm = 1; break;
-        case BG_PPO_OP_DPRE_A:   a.lda = 144; a.N = 128; a.K = 144; a.KC = 144; a.w_rows = 144; a.b_mn = 1; a.epi = 2; a.ldo = 128; a.D = 2; a.LA = 1; threads = 256; per_sm = 2; break;
-        case BG_PPO_OP_DPRE_B:   a.lda = 512; a.N = 128; a.K = 512; a.KC = 128; a.w_rows = 512; a.b_mn = 1; a.epi = 2; a.ldo = 128; a.D = 2; a.LA = 1; threads = 512; per_sm = 1; break;
+        // ring sizes: what fits beside the weight tile in 220 KB of shared memory
+        case BG_PPO_OP_HIDDEN:   a.lda = 208; a.N = 128; a.K = 208; a.KC = 208; a.w_rows = 128; a.b_mn = 0; a.epi = 0; a.ldo = 128; a.D = 3; break;
+        case BG_PPO_OP_LOGITS_A: a.lda = 128; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 1; a.ldo = 144; a.D = 5; break;
+        case BG_PPO_OP_LOGITS_B: a.lda = 128; a.N = 512; a.K = 128; a.KC = 128; a.w_rows = 512; a.b_mn = 0; a.epi = 1; a.ldo = 512; a.D = 2; break;
+        case BG_PPO_OP_DPRE_A:   a.lda = 144; a.N = 128; a.K = 144; a.KC = 144; a.w_rows = 144; a.b_mn = 1; a.epi = 2; a.ldo = 128; a.D = 4; break;
+        case BG_PPO_OP_DPRE_B:   a.lda = 512; a.N = 128; a.K = 512; a.KC = 128; a.w_rows = 512; a.b_mn = 1; a.epi = 2; a.ldo = 128; a.D = 2; break;
         default: return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: unknown op");
     }
     if (a.epi == 1 && !bias) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: the logits ops need the bias row");
@@ -424,9 +463,9 @@ extern "C" int bg_ppo_gemm_nt(int op, const uint16_t* A, long long row_begin, lo
     if (e != cudaSuccess) return bg_set_error(e, "bg_ppo_gemm_nt: cudaFuncSetAttribute");
     if (smem > 220 * 1024) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: stage ring does not fit shared memory");
     const long long tiles = (row_end - row_begin + kRows - 1) / kRows;
-    long long grid = (long long)bg_sm_count() * per_sm;
+    long long grid = (long long)bg_sm_count();
     if (grid > tiles) grid = tiles;
-    ppo_gemm_nt_kernel<<<(unsigned)grid, threads, smem, (cudaStream_t)stream>>>(a);
+    ppo_gemm_nt_kernel<<<(unsigned)grid, kNtThreads, smem, (cudaStream_t)stream>>>(a);
     return bg_set_error(cudaGetLastError(), "bg_ppo_gemm_nt: launch");
 }
 
@@ -440,10 +479,13 @@ extern "C" int bg_ppo_gemm_tn(int op, const uint16_t* A, const uint16_t* B, long
     if (e != cudaSuccess) return bg_set_error(e, "bg_ppo_gemm_tn: cudaFuncSetAttribute");
     const long long tiles = (row_end - row_begin + kTnRows - 1) / kTnRows;
     auto launch = [&](TnArgs a) -> int {
-        const size_t smem = (size_t)kTnD * ((size_t)16 + (size_t)(a.N >> 3)) * (kTnRows * 16);
-        long long grid = (long long)bg_sm_count() * 2;                 // two CTAs per SM (<= 86 KB and <= 256 TMEM columns each)
+        const size_t stage = ((size_t)16 + (size_t)(a.N >> 3)) * (kTnRows * 16);
+        a.D = (int)((215 * 1024) / stage);
+        if (a.D > 6) a.D = 6;
+        const size_t smem = (size_t)a.D * stage;
+        long long grid = (long long)bg_sm_count();
         if (grid > tiles) grid = tiles;
-        ppo_gemm_tn_kernel<<<(unsigned)grid, kGT, smem, (cudaStream_t)stream>>>(a);
+        ppo_gemm_tn_kernel<<<(unsigned)grid, kTnThreads, smem, (cudaStream_t)stream>>>(a);
         return bg_set_error(cudaGetLastError(), "bg_ppo_gemm_tn: launch");
     };
     TnArgs a{};
