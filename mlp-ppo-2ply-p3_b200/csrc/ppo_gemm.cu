@@ -151,9 +151,12 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
         // Each producer warp loads WHOLE stages (steps pw, pw + 4, ...) on its own: issue, wait for its own copies, proxy fence,
         // arrive.  (With every thread loading a slice of every stage, the per-stage fence.proxy.async also waited for the
         // younger stages' copies in flight: one stage at a time, 2.4 .. 2.9 TB/s.)  Up to four stages are in flight per SM.
+        // A stage BUFFER always belongs to the same warp (b % 4), so a warp's waits on empty[b] are never more than one phase
+        // behind (a parity wait two phases ahead passes immediately: measured as a launch failure at 1 M rows).
         const int pw = warp - kNtEpiWarps;
-        for (long long s = pw; s < n_steps; s += kNtProdWarps) {
+        for (long long s = 0; s < n_steps; ++s) {
             const int b = (int)(s % a.D);
+            if (b % kNtProdWarps != pw) continue;
             const uint32_t it = (uint32_t)(s / a.D);
             warp_wait(&empty[b], (it & 1u) ^ 1u, lane);                // the MMAs that read this buffer D steps ago are done
             if (!(a.dbg & 4))
@@ -294,8 +297,9 @@ __global__ void __launch_bounds__(kTnThreads, 1) ppo_gemm_tn_kernel(const TnArgs
     const int D = a.D;
     if (warp < kTnProdWarps) {
         // ================= producers: one warp per stage (see ppo_gemm_nt_kernel) =================
-        for (long long s = warp; s < n_steps; s += kTnProdWarps) {
+        for (long long s = 0; s < n_steps; ++s) {
             const int b = (int)(s % D);
+            if (b % kTnProdWarps != warp) continue;                    // a buffer always belongs to the same warp (phase safety)
             const uint32_t it = (uint32_t)(s / D);
             warp_wait(&empty[b], (it & 1u) ^ 1u, lane);
             if (!(a.dbg & 4)) {
