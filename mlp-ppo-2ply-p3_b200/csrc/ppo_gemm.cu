@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
     cp_async_wait_but(0);
     const int nacc = a.N <= 256 ? 2 : 1;                               // accumulators in TMEM (columns 0.. and 256..)
     if (tid == 0) {
-        for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 32); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 8; ++i) { mbar_init(&full[i], kNtProdWarps * 32); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kNtEpiWarps * 32); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -148,24 +148,26 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
 
     if (warp >= kNtEpiWarps && warp < kNtEpiWarps + kNtProdWarps) {
         // ================= producers =================
-        // Each producer warp loads WHOLE stages (steps pw, pw + 4, ...) on its own: issue, wait for its own copies, proxy fence,
-        // arrive.  (With every thread loading a slice of every stage, the per-stage fence.proxy.async also waited for the
-        // younger stages' copies in flight: one stage at a time, 2.4 .. 2.9 TB/s.)  Up to four stages are in flight per SM.
-        // A stage BUFFER always belongs to the same warp (b % 4), so a warp's waits on empty[b] are never more than one phase
-        // behind (a parity wait two phases ahead passes immediately: measured as a launch failure at 1 M rows).
         const int pw = warp - kNtEpiWarps;
+        const int ahead = a.D >= 4 ? 2 : (a.D == 3 ? 1 : 0);           // stages this thread keeps in flight beyond the one it completes
         for (long long s = 0; s < n_steps; ++s) {
             const int b = (int)(s % a.D);
-            if (b % kNtProdWarps != pw) continue;
             const uint32_t it = (uint32_t)(s / a.D);
             warp_wait(&empty[b], (it & 1u) ^ 1u, lane);                // the MMAs that read this buffer D steps ago are done
             if (!(a.dbg & 4))
                 stage_tile<kRows>(As0 + (uint32_t)(b * stage_bytes), A0 + b * stage_bytes, a.A, a.lda, a.row_begin + tile_of(s / n_kc) * kRows,
-                                  a.row_end, (int)(s % n_kc) * a.KC, nch, 0, 1, lane);
+                                  a.row_end, (int)(s % n_kc) * a.KC, nch, pw, kNtProdWarps, lane);
             cp_async_commit();
-            cp_async_wait_but(0);
+            if (s >= ahead) {                                          // stage s - ahead has landed: hand it to the MMA warp
+                cp_async_wait_but(ahead);
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                mbar_arrive(&full[(int)((s - ahead) % a.D)]);
+            }
+        }
+        for (long long s = n_steps > ahead ? n_steps - ahead : 0; s < n_steps; ++s) {
+            cp_async_wait_but((int)(n_steps - 1 - s));
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            mbar_arrive(&full[b]);
+            mbar_arrive(&full[(int)(s % a.D)]);
         }
     } else if (warp == kNtEpiWarps + kNtProdWarps) {
         // ================= MMA issuer =================
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(kTnThreads, 1) ppo_gemm_tn_kernel(const TnArgs
     const int a_bytes = 16 * CS, b_bytes = (a.N >> 3) * CS, stage_bytes = a_bytes + b_bytes;
     const uint32_t S0 = smem_u32(smem);
     if (tid == 0) {
-        for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 32); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 8; ++i) { mbar_init(&full[i], kTnProdWarps * 32); mbar_init(&empty[i], 1); }
         mbar_init(&done_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -296,22 +298,29 @@ __global__ void __launch_bounds__(kTnThreads, 1) ppo_gemm_tn_kernel(const TnArgs
     const long long n_steps = n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int D = a.D;
     if (warp < kTnProdWarps) {
-        // ================= producers: one warp per stage (see ppo_gemm_nt_kernel) =================
+        // ================= producers =================
+        const int ahead = D >= 4 ? 2 : (D == 3 ? 1 : 0);
         for (long long s = 0; s < n_steps; ++s) {
             const int b = (int)(s % D);
-            if (b % kTnProdWarps != warp) continue;                    // a buffer always belongs to the same warp (phase safety)
             const uint32_t it = (uint32_t)(s / D);
             warp_wait(&empty[b], (it & 1u) ^ 1u, lane);
             if (!(a.dbg & 4)) {
                 const long long row0 = a.row_begin + (blockIdx.x + s * gridDim.x) * kTnRows;
-                stage_tile<kTnRows>(S0 + (uint32_t)(b * stage_bytes), smem + b * stage_bytes, a.A, a.lda, row0, a.row_end, 0, 16, 0, 1, lane);
+                stage_tile<kTnRows>(S0 + (uint32_t)(b * stage_bytes), smem + b * stage_bytes, a.A, a.lda, row0, a.row_end, 0, 16, warp, kTnProdWarps, lane);
                 stage_tile<kTnRows>(S0 + (uint32_t)(b * stage_bytes + a_bytes), smem + b * stage_bytes + a_bytes, a.B, a.ldb, row0, a.row_end, 0, a.N >> 3,
-                                    0, 1, lane);
+                                    warp, kTnProdWarps, lane);
             }
             cp_async_commit();
-            cp_async_wait_but(0);
+            if (s >= ahead) {
+                cp_async_wait_but(ahead);
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                mbar_arrive(&full[(int)((s - ahead) % D)]);
+            }
+        }
+        for (long long s = n_steps > ahead ? n_steps - ahead : 0; s < n_steps; ++s) {
+            cp_async_wait_but((int)(n_steps - 1 - s));
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            mbar_arrive(&full[b]);
+            mbar_arrive(&full[(int)(s % D)]);
         }
     } else {
         // ================= MMA issuer =================
