@@ -254,23 +254,28 @@ int bg_ppo_loss_grad(const void* logits, int flags /* BG_LOSS_* */, long long ld
                      float* dbias /*nullable*/, float* sums, void* stream);
 
 /* N2  the linear algebra of one PPO epoch (agent/ppo_agent.py:268-305: forward of both layers, loss.backward()) as
- * hand-written tcgen05 GEMMs (csrc/ppo_gemm.cu) -- no library GEMM on the update path.  The caller keeps the batch sorted
- * by class: rows [0, n_a) = class A (1..128 legal slots, stored action among them), rows [n_a, B) = class B (passes, more
- * slots).  bf16 row-major buffers: x [B][208] (K3's rows with column 198 = 1.0: the bias), h / dpre [B][128],
- * logits / dlogits of class A [n_a][144] (slots 0..127, value head in column 128), of class B [B - n_a][512] (value head
- * in column 500).  Row ranges are absolute rows of x / h / dpre; the class buffers are indexed from their own row 0, so
- * pass them offset: e.g. LOGITS_B with A = h, out = logits_b - n_a * 512 (the kernel only touches rows in range).
+ * hand-written tcgen05 GEMMs (csrc/ppo_gemm.cu) -- no library GEMM on the update path.
+ * Layout: every activation matrix is bf16 and TILE-BLOCKED -- tiles of 128 rows, inside a tile 16-byte chunks ordered
+ * [column / 8][row][8 columns], i.e. element (r, c) of a matrix with C columns sits at 16-bit index
+ * (r / 128) * (128 C) + (c / 8) * 1024 + (r % 128) * 8 + c % 8: a tile is the tensor cores' shared-memory operand image, so
+ * a pipeline stage is one bulk copy.  The batch is sorted by class and each class padded to whole tiles with zero rows:
+ * tiles [0, TA) = class A (1..128 legal slots, stored action among them), tiles [TA, TA + TB) = class B (passes, more slots).
+ * Buffers: x [(TA+TB) tiles][208 columns] (K3's rows, column 198 = 1.0: the bias), h / dpre [..][128]; logits / dlogits of class A
+ * [TA tiles][144] (slots 0..127, value head in column 128), of class B [TB tiles][512] (value head in column 500).  Tile ranges
+ * are absolute tiles of x / h / dpre; the class B buffers are indexed from their own tile 0, so pass them offset by -TA tiles.
+ *   bg_ppo_gather_block: x_blocked row p = x_rowmajor[perm[p]] (zero row where perm[p] < 0), column set_one_col set to 1.0.
  *   bg_ppo_pack_weights: flat f32 master weights (fc1.weight, fc1.bias, action_head.weight, action_head.bias,
  *     value_head.weight, value_head.bias: 90,101 floats) -> bf16 operand tiles w1p [26][128][8], wap_a [16][144][8],
  *     wap_b [16][512][8] and the f32 bias rows bias_a [144], bias_b [512].
- *   bg_ppo_gemm_nt(op): out = epilogue(A . W^T) for rows [row_begin, row_end):
+ *   bg_ppo_gemm_nt(op): out = epilogue(A . W^T) for tiles [tile_begin, tile_end):
  *     HIDDEN   h = relu(x w1p^T);  LOGITS_A / _B  logits = h wap^T + bias;  DPRE_A / _B  dpre = (dlogits wap) * [h > 0]
  *     (W = the matching tile; bias for the LOGITS ops; h_mask = h for the DPRE ops).
- *   bg_ppo_gemm_tn(op): flat_grad += A^T . B over rows [row_begin, row_end) (f32 atomics; caller zeroes flat_grad):
+ *   bg_ppo_gemm_tn(op): flat_grad += A^T . B over tiles [tile_begin, tile_end) (f32 atomics; caller zeroes flat_grad):
  *     GRAD_WA_A  A = h, B = dlogits_a -> action_head.weight[0..127], value_head.weight;  GRAD_WA_B  A = h, B = dlogits_b
  *     -> action_head.weight, value_head.weight;  GRAD_W1  A = dpre, B = x -> fc1.weight, fc1.bias.
- *   bg_ppo_loss_grad_classes: bg_ppo_loss_grad on the two class buffers (means over B; dbias [512]: columns 0..499 =
- *     action_head.bias, 500 = value_head.bias).
+ *   bg_ppo_loss_grad_classes: bg_ppo_loss_grad on the two (tile-blocked) class buffers: n_a / n_b real rows, the per-sample
+ *     arrays hold class B at [b_offset, ..) (b_offset = 128 TA); means over n_a + n_b; dbias [512]: columns 0..499 =
+ *     action_head.bias, 500 = value_head.bias.
  *   bg_adam_step: torch.optim.Adam's update (ppo_agent.py:83) of the flat parameters, one kernel; step counts from 1;
  *     grads are multiplied by grad_scale first (1 / world size after a summing all-reduce). */
 #define BG_PPO_OP_HIDDEN 0
@@ -284,12 +289,14 @@ int bg_ppo_loss_grad(const void* logits, int flags /* BG_LOSS_* */, long long ld
 #define BG_PPO_NUM_PARAMS 90101
 int bg_ppo_pack_weights(const float* flat_params, uint16_t* w1p, uint16_t* wap_a, uint16_t* wap_b, float* bias_a, float* bias_b,
                         void* stream);
-int bg_ppo_gemm_nt(int op, const uint16_t* A, long long row_begin, long long row_end, const uint16_t* W, const float* bias,
+int bg_ppo_gather_block(const uint16_t* x_rowmajor, long long ld_src, const int32_t* perm, long long rows_pad, int ncols,
+                        int set_one_col /* -1: none */, uint16_t* x_blocked, void* stream);
+int bg_ppo_gemm_nt(int op, const uint16_t* A, long long tile_begin, long long tile_end, const uint16_t* W, const float* bias,
                    const uint16_t* h_mask, uint16_t* out, void* stream);
-int bg_ppo_gemm_tn(int op, const uint16_t* A, const uint16_t* B, long long row_begin, long long row_end, float* flat_grad,
+int bg_ppo_gemm_tn(int op, const uint16_t* A, const uint16_t* B, long long tile_begin, long long tile_end, float* flat_grad,
                    float* scratch /* GRAD_W1: [199][128] f32 (dW1p transposed; fc1.* of flat_grad are then overwritten) */, void* stream);
-int bg_ppo_loss_grad_classes(const void* logits_a, void* dlogits_a, const void* logits_b, void* dlogits_b, long long n_a, long long B,
-                             const int32_t* counts, const int32_t* actions, const float* old_log_probs, const float* advantages,
+int bg_ppo_loss_grad_classes(const void* logits_a, void* dlogits_a, const void* logits_b, void* dlogits_b, long long n_a, long long n_b,
+                             long long b_offset, const int32_t* counts, const int32_t* actions, const float* old_log_probs, const float* advantages,
                              const float* returns, float eps_clip, float value_coef, float entropy_coef, float* dbias /*[512]*/,
                              float* sums /*[3]*/, void* stream);
 int bg_ppo_gemm_debug(int flags);  /* experiment switches for scripts/exp_ppo_gemm.py (1 no MMAs, 2 no stores, 4 no loads); 0 = normal */

@@ -73,6 +73,13 @@ template <> struct Vec4<__nv_bfloat16> {
     }
 };
 
+// Element offset of (row r, column c) of a matrix with ld columns: row-major, or (blocked) the tile-blocked layout of
+// ppo_gemm.cu -- tiles of 128 rows, inside a tile 16-byte chunks [c / 8][row][8].  c is a multiple of 4 wherever a 4-vector
+// is accessed, so a vector never straddles a chunk.
+__device__ __forceinline__ long long mat_off(long long r, int c, long long ld, int blocked) {
+    return blocked ? (r >> 7) * (ld * 128) + (long long)(c >> 3) * 1024 + (r & 127) * 8 + (c & 7) : r * ld + c;
+}
+
 // A warp per sample, persistent warps striding over the rows; lane l holds slots 128 q + 4 l + e (q, e < 4), so that every
 // load / store instruction of the warp covers 256 (bf16) or 512 (f32) contiguous bytes, and the next row's logits and
 // scalars are fetched before the current row is worked on (the kernel needs ~125 registers, i.e. 16 warps per SM: one
@@ -101,14 +108,13 @@ __device__ __forceinline__ float loss_scalar(const __nv_bfloat16* p) { return __
 template <typename T>
 __device__ __forceinline__ void loss_row_load(LossRow<T>& r, long long row, int n, int a, int lane, const T* __restrict__ logits,
                                               long long ld, const float* __restrict__ values, const float* __restrict__ old_logp,
-                                              const float* __restrict__ adv, const float* __restrict__ returns) {
-    const T* src = logits + row * ld;
+                                              const float* __restrict__ adv, const float* __restrict__ returns, int blocked) {
     const int nq = loss_active_quads(n, a);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int i0 = 128 * q + 4 * lane;
         const bool need = q < nq || (q == 3 && !values && lane == 29);               // lane 29 of quad 3: column 500 = the value
-        r.x[q] = (need && i0 < ld) ? Vec4<T>::load_raw(src + i0) : Vec4<T>::zero();
+        r.x[q] = (need && i0 < ld) ? Vec4<T>::load_raw(logits + mat_off(row, i0, ld, blocked)) : Vec4<T>::zero();
     }
     r.n = n; r.a = a;
     r.adv = __ldg(adv + row); r.old_logp = __ldg(old_logp + row); r.ret = __ldg(returns + row);
@@ -128,17 +134,16 @@ template <typename T>
 __device__ __forceinline__ void loss_packed_load(LossPacked<T>& d, long long r, long long B, int sub, const T* __restrict__ logits, long long ld,
                                                  const float* __restrict__ values, const int32_t* __restrict__ counts,
                                                  const int32_t* __restrict__ actions, const float* __restrict__ old_logp,
-                                                 const float* __restrict__ adv, const float* __restrict__ returns, int value_col) {
+                                                 const float* __restrict__ adv, const float* __restrict__ returns, int value_col, int blocked) {
     d.n = 0; d.a = 0; d.adv = 0.0f; d.old_logp = 0.0f; d.ret = 0.0f; d.v = 0.0f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) d.x[k] = Vec4<T>::zero();
     if (r < B) {
-        const T* src = logits + r * ld;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) d.x[k] = Vec4<T>::load_raw(src + 16 * sub + 4 * k);     // (read whatever the row's class: no dependent load)
+        for (int k = 0; k < 4; ++k) d.x[k] = Vec4<T>::load_raw(logits + mat_off(r, 16 * sub + 4 * k, ld, blocked));     // (read whatever the row's class: no dependent load)
         d.n = __ldg(counts + r); d.a = __ldg(actions + r);
         d.adv = __ldg(adv + r); d.old_logp = __ldg(old_logp + r); d.ret = __ldg(returns + r);
-        d.v = values ? __ldg(values + r) : loss_scalar(src + value_col);
+        d.v = values ? __ldg(values + r) : loss_scalar(logits + mat_off(r, value_col, ld, blocked));
     }
 }
 
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
     const int32_t* __restrict__ actions, const float* __restrict__ old_logp, const float* __restrict__ adv,
     const float* __restrict__ returns, long long B, float eps_clip, float value_coef, float entropy_coef,
     T* __restrict__ dlogits, float* __restrict__ dvalues, float* __restrict__ dbias, float* __restrict__ sums, int prezeroed,
-    int value_col, long long B_norm) {
+    int value_col, long long B_norm, int blocked) {
     // value_col: column of the logits / dlogits row that carries the value head when values == NULL (500 in the 512-wide
     // layout, 128 in the 144-wide class A layout of ppo_gemm.cu); B_norm: the batch size the means are taken over (this call
     // may cover only a part of the batch)
@@ -164,11 +169,11 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
     const long long S = (long long)gridDim.x * kLossWarps;          // persistent warps stride over groups of 4 rows
     long long g4 = (long long)blockIdx.x * kLossWarps + warp;
     LossPacked<T> nx;
-    loss_packed_load(nx, g4 * 4 + grp, B, sub, logits, ld, values, counts, actions, old_logp, adv, returns, value_col);
+    loss_packed_load(nx, g4 * 4 + grp, B, sub, logits, ld, values, counts, actions, old_logp, adv, returns, value_col, blocked);
 #pragma unroll 1
     for (; g4 * 4 < B; g4 += S) {
         const LossPacked<T> cur = nx;
-        loss_packed_load(nx, (g4 + S) * 4 + grp, B, sub, logits, ld, values, counts, actions, old_logp, adv, returns, value_col);
+        loss_packed_load(nx, (g4 + S) * 4 + grp, B, sub, logits, ld, values, counts, actions, old_logp, adv, returns, value_col, blocked);
         const long long row = g4 * 4 + grp;
         const bool act = row < B && loss_row_is_packed(cur.n, cur.a);
         const int n = act ? cur.n : 1, a = act ? cur.a : 0;         // (idle lanes compute on a finite dummy row)
@@ -214,7 +219,6 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
         const float dv = cur.v - cur.ret;
         const float dvalue = 2.0f * value_coef * dv * invB;
         if (act) {
-            T* dst = dlogits + row * ld;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float x[4];
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
                     x[e] = d;
                     colsum[kk] += d;
                 }
-                Vec4<T>::store(dst + 16 * sub + 4 * k, x);
+                Vec4<T>::store(dlogits + mat_off(row, 16 * sub + 4 * k, ld, blocked), x);
             }
             // quads 1..3 and the padding of the GEMM's N: exact zeros; column 500 carries d loss / d value when the value rides there
             // (prezeroed: the caller guarantees zeros there already -- only the value column is written)
@@ -235,14 +239,14 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
                 for (int c = 128 + 4 * sub; c < ld; c += 32) {
                     float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                     if (!values && c == value_col) { x[0] = dvalue; vsum += dvalue; }
-                    Vec4<T>::store(dst + c, x);
+                    Vec4<T>::store(dlogits + mat_off(row, c, ld, blocked), x);
                 }
             } else if (!values && sub >= 4) {
                 // the value column's whole 32-byte sector (columns 496 .. 511: a lone 8-byte store would cost a read-modify-write)
                 const int c = BG_ACTIONS - 4 + 4 * (sub - 4);
                 float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                 if (sub == 5) { x[0] = dvalue; vsum += dvalue; }
-                if (c < ld) Vec4<T>::store(dst + c, x);
+                if (c < ld) Vec4<T>::store(dlogits + mat_off(row, c, ld, blocked), x);
             }
             if (sub == 0) {
                 if (dvalues) dvalues[row] = dvalue;
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_kernel(
     const int32_t* __restrict__ actions, const float* __restrict__ old_logp, const float* __restrict__ adv,
     const float* __restrict__ returns, long long B, float eps_clip, float value_coef, float entropy_coef,
     T* __restrict__ dlogits, float* __restrict__ dvalues, float* __restrict__ dbias, float* __restrict__ sums, int all_rows,
-    long long B_norm) {
+    long long B_norm, int blocked) {
     constexpr float kMaskLog = -103.27893f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ float s_part[kLossWarps][3];
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_kernel(
       LossRow<T> nx;
       if (todo) {
           const int j = __ffs(todo) - 1;
-          loss_row_load(nx, blk * 32 + j, __shfl_sync(kFull, nl, j), __shfl_sync(kFull, al, j), lane, logits, ld, values, old_logp, adv, returns);
+          loss_row_load(nx, blk * 32 + j, __shfl_sync(kFull, nl, j), __shfl_sync(kFull, al, j), lane, logits, ld, values, old_logp, adv, returns, blocked);
       }
 #pragma unroll 1
       while (todo) {
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_kernel(
         const LossRow<T> cur = nx;
         if (todo) {
             const int j = __ffs(todo) - 1;
-            loss_row_load(nx, blk * 32 + j, __shfl_sync(kFull, nl, j), __shfl_sync(kFull, al, j), lane, logits, ld, values, old_logp, adv, returns);
+            loss_row_load(nx, blk * 32 + j, __shfl_sync(kFull, nl, j), __shfl_sync(kFull, al, j), lane, logits, ld, values, old_logp, adv, returns, blocked);
         }
         const int n = cur.n, a = cur.a;
         const int nq = loss_active_quads(n, a);
@@ -391,7 +395,6 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_kernel(
         const float v = values ? cur.v : __shfl_sync(kFull, xv, 29);
         const float dv = v - cur.ret;
         const float dvalue = 2.0f * value_coef * dv * invB;
-        T* dst = dlogits + row * ld;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int i0 = 128 * q + 4 * lane;
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_kernel(
             if (q == 3 && !values && i0 == BG_ACTIONS) x[0] = dvalue;
 #pragma unroll
             for (int e = 0; e < 4; ++e) colsum[4 * q + e] += x[e];
-            if (i0 < ld) Vec4<T>::store(dst + i0, x);          // masked quads and slots 500 .. ld-1 (padding of the GEMM's N): exact zeros
+            if (i0 < ld) Vec4<T>::store(dlogits + mat_off(row, i0, ld, blocked), x);          // masked quads and slots 500 .. ld-1 (padding of the GEMM's N): exact zeros
         }
         if (lane == 0) {
             if (dvalues) dvalues[row] = dvalue;
@@ -463,33 +466,35 @@ extern "C" int bg_ppo_loss_grad(const void* logits, int flags, long long ld, con
         if (!general_only)
             bg::ppo_loss_grad_packed_kernel<__nv_bfloat16><<<grid_p, bg::kLossWarps * 32, 0, st>>>(
                 (const __nv_bfloat16*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
-                entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums, prezeroed, BG_ACTIONS, B);
+                entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums, prezeroed, BG_ACTIONS, B, 0);
         bg::ppo_loss_grad_kernel<__nv_bfloat16><<<grid_g, bg::kLossWarps * 32, 0, st>>>(
             (const __nv_bfloat16*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
-            entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums, general_only, B);
+            entropy_coef, (__nv_bfloat16*)dlogits, dvalues, dbias, sums, general_only, B, 0);
     } else {
         if (!general_only)
             bg::ppo_loss_grad_packed_kernel<float><<<grid_p, bg::kLossWarps * 32, 0, st>>>(
                 (const float*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
-                entropy_coef, (float*)dlogits, dvalues, dbias, sums, prezeroed, BG_ACTIONS, B);
+                entropy_coef, (float*)dlogits, dvalues, dbias, sums, prezeroed, BG_ACTIONS, B, 0);
         bg::ppo_loss_grad_kernel<float><<<grid_g, bg::kLossWarps * 32, 0, st>>>(
             (const float*)logits, ld, values, counts, actions, old_log_probs, advantages, returns, B, eps_clip, value_coef,
-            entropy_coef, (float*)dlogits, dvalues, dbias, sums, general_only, B);
+            entropy_coef, (float*)dlogits, dvalues, dbias, sums, general_only, B, 0);
     }
     return bg_set_error(cudaGetLastError(), "bg_ppo_loss_grad: launch");
 }
 
-// The loss over a batch that ppo_gemm.cu keeps sorted by class: rows [0, n_a) in the 144-column class A layout (128 slots,
-// value head in column 128) through the packed kernel, rows [n_a, B) in the 512-column layout (value head in column 500)
-// through the general kernel; every mean is taken over B.  bf16 logits / dlogits, value head inside the logits.
+// The loss over a batch that ppo_gemm.cu keeps sorted by class, on its tile-blocked buffers: n_a class A rows in the
+// 144-column layout (128 slots, value head in column 128) through the packed kernel, n_b class B rows in the 512-column layout
+// (value head in column 500) through the general kernel; the per-sample arrays hold class A at [0, n_a) and class B at
+// [b_offset, b_offset + n_b) (b_offset = n_a rounded up to a whole tile); every mean is taken over n_a + n_b.
 extern "C" int bg_ppo_loss_grad_classes(const void* logits_a, void* dlogits_a, const void* logits_b, void* dlogits_b, long long n_a,
-                                        long long B, const int32_t* counts, const int32_t* actions, const float* old_log_probs,
-                                        const float* advantages, const float* returns, float eps_clip, float value_coef,
-                                        float entropy_coef, float* dbias, float* sums, void* stream) {
-    if (B < 0 || n_a < 0 || n_a > B) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_loss_grad_classes: bad sizes");
+                                        long long n_b, long long b_offset, const int32_t* counts, const int32_t* actions,
+                                        const float* old_log_probs, const float* advantages, const float* returns, float eps_clip,
+                                        float value_coef, float entropy_coef, float* dbias, float* sums, void* stream) {
+    if (n_a < 0 || n_b < 0 || b_offset < n_a) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_loss_grad_classes: bad sizes");
+    const long long B = n_a + n_b;
     if (B == 0) return BG_OK;
     if (!counts || !actions || !old_log_probs || !advantages || !returns || !sums || (n_a > 0 && (!logits_a || !dlogits_a)) ||
-        (n_a < B && (!logits_b || !dlogits_b)))
+        (n_b > 0 && (!logits_b || !dlogits_b)))
         return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_loss_grad_classes: null pointer");
     const long long resident = (long long)bg_sm_count() * 2;
     cudaStream_t st = (cudaStream_t)stream;
@@ -497,13 +502,14 @@ extern "C" int bg_ppo_loss_grad_classes(const void* logits_a, void* dlogits_a, c
         const long long need = (n_a + 4 * bg::kLossWarps - 1) / (4 * bg::kLossWarps);
         bg::ppo_loss_grad_packed_kernel<__nv_bfloat16><<<(unsigned)(need < resident ? need : resident), bg::kLossWarps * 32, 0, st>>>(
             (const __nv_bfloat16*)logits_a, 144, nullptr, counts, actions, old_log_probs, advantages, returns, n_a, eps_clip, value_coef,
-            entropy_coef, (__nv_bfloat16*)dlogits_a, nullptr, dbias, sums, 0, 128, B);
+            entropy_coef, (__nv_bfloat16*)dlogits_a, nullptr, dbias, sums, 0, 128, B, 1);
     }
-    if (n_a < B) {
-        const long long nb = B - n_a, need = (nb + 32 * bg::kLossWarps - 1) / (32 * bg::kLossWarps);
+    if (n_b > 0) {
+        const long long need = (n_b + 32 * bg::kLossWarps - 1) / (32 * bg::kLossWarps);
         bg::ppo_loss_grad_kernel<__nv_bfloat16><<<(unsigned)(need < resident ? need : resident), bg::kLossWarps * 32, 0, st>>>(
-            (const __nv_bfloat16*)logits_b, 512, nullptr, counts + n_a, actions + n_a, old_log_probs + n_a, advantages + n_a, returns + n_a,
-            nb, eps_clip, value_coef, entropy_coef, (__nv_bfloat16*)dlogits_b, nullptr, dbias, sums, 1, B);
+            (const __nv_bfloat16*)logits_b, 512, nullptr, counts + b_offset, actions + b_offset, old_log_probs + b_offset,
+            advantages + b_offset, returns + b_offset, n_b, eps_clip, value_coef, entropy_coef, (__nv_bfloat16*)dlogits_b, nullptr, dbias,
+            sums, 1, B, 1);
     }
     return bg_set_error(cudaGetLastError(), "bg_ppo_loss_grad_classes: launch");
 }

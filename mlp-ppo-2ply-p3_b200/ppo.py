@@ -227,15 +227,18 @@ class TensorCoreUpdate:
 
     The work follows the action mask: the samples are sorted once per rollout into class A (1..128 legal slots and the
     stored action among them -- ~94 % of a self-play batch) and class B (passes, whose reference arithmetic is a softmax over
-    all 500 slots, and rows with more slots).  Class A rows only touch slots 0..127, so their logits / dlogits are 144
-    columns wide (128 slots + the value head in column 128) instead of 512: a quarter of the head's FLOPs and traffic.
+    all 500 slots, and rows with more slots), each class padded to whole 128-row tiles with zero rows.  Class A rows only
+    touch slots 0..127, so their logits / dlogits are 144 columns wide (128 slots + the value head in column 128) instead
+    of 512: a quarter of the head's FLOPs and traffic.  Every activation matrix is kept TILE-BLOCKED in HBM (the tensor
+    cores' shared-memory operand image, see csrc/ppo_gemm.cu), so the kernels stream whole tiles with bulk copies.
 
-        h       = relu(x W1p^T)                                   bg_ppo_gemm_nt HIDDEN      (fc1.bias rides in column 198 of x)
+        xb      = x[perm] blocked, bias column set              bg_ppo_gather_block        (once per rollout: prepare())
+        h       = relu(xb W1p^T)                                   bg_ppo_gemm_nt HIDDEN
         logits  = h Wap^T + b          per class                   bg_ppo_gemm_nt LOGITS_A / _B (value head = one more row of Wap)
         dlogits = d loss / d logits    per class                   bg_ppo_loss_grad_classes
         dpre    = (dlogits Wap) [h>0]  per class                   bg_ppo_gemm_nt DPRE_A / _B
         dWap   += dlogits^T h          per class                   bg_ppo_gemm_tn GRAD_WA_A / _B   -> flat f32 gradient
-        dW1p   += dpre^T x                                         bg_ppo_gemm_tn GRAD_W1
+        dW1p   += dpre^T xb                                        bg_ppo_gemm_tn GRAD_W1
     """
 
     ONE_COL = 198
@@ -248,44 +251,70 @@ class TensorCoreUpdate:
         self.gflat, self.pflat = z((90101,), torch.float32), z((90101,), torch.float32)
         self.dbias, self.sums = z((512,), torch.float32), z((3,), torch.float32)
         self.w1t = z((199 * 128,), torch.float32)              # scratch of GRAD_W1 (dW1p transposed)
-        self.B = -1
+        self._cap = (0, 0)
+        self._p = None
 
     # the class of a sample: csrc/ppo.cu loss_row_is_packed
     @staticmethod
     def class_a(counts, actions):
         return (counts >= 1) & (counts <= 128) & (actions >= 0) & (actions < counts)
 
-    def sort_by_class(self, counts, actions):
-        """-> (perm (B,) i64: class A rows first, original order inside a class; n_a).  One host read (n_a)."""
-        a = self.class_a(counts, actions)
-        perm = torch.argsort((~a).to(torch.int8), stable=True)
-        return perm, int(a.sum().item())
+    @staticmethod
+    def to_blocked(m):
+        """(R, C) row-major, R % 128 == 0, C % 8 == 0 -> the tile-blocked layout (flat); for tests and debugging"""
+        R, C = m.shape
+        return m.view(R // 128, 128, C // 8, 8).permute(0, 2, 1, 3).contiguous().view(-1)
 
-    def _buffers(self, B, n_a):
-        if B != self.B:
-            e = lambda shape: torch.empty(shape, dtype=torch.bfloat16, device=self.device)
-            self.h, self.dpre = e((B, 128)), e((B, 128))
-            self.la, self.dla = e((B, 144)), e((B, 144))              # class A logits / dlogits (rows [0, n_a))
-            self.B = B
-            self.lb = self.dlb = None
-        nb = B - n_a
-        if self.lb is None or self.lb.shape[0] < nb:
-            cap = max(nb, B // 8, 1)
-            self.lb = torch.empty((cap, 512), dtype=torch.bfloat16, device=self.device)
-            self.dlb = torch.empty((cap, 512), dtype=torch.bfloat16, device=self.device)
+    @staticmethod
+    def from_blocked(b, R, C):
+        return b.view(R // 128, C // 8, 128, 8).permute(0, 2, 1, 3).reshape(R, C)
+
+    def prepare(self, x, counts, actions, old_logp, adv, returns):
+        """Once per rollout: sort the samples by class (class A first, original order inside a class), pad each class to whole
+        tiles, gather the per-sample vectors and build the blocked x (with the bias column).  One host read (the class sizes)."""
+        B = x.shape[0]
+        dev = self.device
+        a = self.class_a(counts, actions)
+        order = torch.argsort((~a).to(torch.int8), stable=True).to(torch.int32)
+        n_a = int(a.sum().item())
+        n_b = B - n_a
+        TA, TB = -(-n_a // 128), -(-n_b // 128)
+        rows = (TA + TB) * 128
+        perm = torch.full((max(rows, 1),), -1, dtype=torch.int32, device=dev)
+        perm[:n_a] = order[:n_a]
+        perm[TA * 128:TA * 128 + n_b] = order[n_a:]
+        idx = perm.clamp(min=0).long()
+        g = lambda t, dt: t.to(dt)[idx].contiguous()
+        p = dict(B=B, n_a=n_a, n_b=n_b, TA=TA, TB=TB, rows=rows, perm=perm, counts=g(counts, torch.int32), actions=g(actions, torch.int32),
+                 old_logp=g(old_logp, torch.float32), adv=g(adv, torch.float32), returns=g(returns, torch.float32))
+        if self._cap[0] < TA + TB or self._cap[1] < TB:
+            ct, cb = max(TA + TB, self._cap[0]), max(TB, self._cap[1], (TA + TB) // 8 + 1)
+            e = lambda n: torch.zeros(n, dtype=torch.bfloat16, device=dev)
+            self.xb, self.h, self.dpre = e(ct * 128 * 208), e(ct * 128 * 128), e(ct * 128 * 128)
+            self.la, self.dla = e(ct * 128 * 144), e(ct * 128 * 144)
+            self.lb, self.dlb = e(cb * 128 * 512), e(cb * 128 * 512)
+            self._cap = (ct, cb)
+        # the padding rows of the last tile of each class must read as zeros in dlogits (the loss kernels never write them)
+        if TA:
+            self.dla[(TA - 1) * 128 * 144:TA * 128 * 144].zero_()
+        if TB:
+            self.dlb[(TB - 1) * 128 * 512:TB * 128 * 512].zero_()
+        x = x.contiguous()
+        with torch.cuda.device(dev):
+            check(lib().bg_ppo_gather_block(x.data_ptr(), x.shape[1], perm.data_ptr(), rows, 208, self.ONE_COL, self.xb.data_ptr(), _stream()),
+                  "bg_ppo_gather_block")
+        self._p = p
+        return p
 
     @torch.no_grad()
-    def epoch(self, params, grads, x, counts, actions, old_logp, adv, returns, eps_clip, value_coef, entropy_coef, n_a=None,
+    def epoch(self, params, grads, x, counts, actions, old_logp, adv, returns, eps_clip, value_coef, entropy_coef, prepared=False,
               flat_params=None, flat_grads=None):
-        """Same contract as ManualUpdate.epoch.  n_a: the rows are already sorted by class (class A = rows [0, n_a)); None =
-        sort here (a gather of every per-sample array: the learner does it once per rollout instead).  flat_params /
-        flat_grads: the learner's flat f32 buffers (KEYS order) -- read / written in place instead of through the dicts."""
-        B = x.shape[0]
-        if n_a is None:
-            perm, n_a = self.sort_by_class(counts, actions)
-            x, counts, actions = x[perm].contiguous(), counts[perm].contiguous(), actions[perm].contiguous()
-            old_logp, adv, returns = old_logp[perm].contiguous(), adv[perm].contiguous(), returns[perm].contiguous()
-        self._buffers(B, n_a)
+        """Same contract as ManualUpdate.epoch.  prepared: prepare() has been called for this rollout (the learner does it once
+        for all epochs); else it is done here.  flat_params / flat_grads: the learner's flat f32 buffers (KEYS order), read /
+        written in place instead of through the dicts."""
+        p = self._p if prepared else self.prepare(x, counts, actions, old_logp, adv, returns)
+        B, n_a, n_b, TA, TB = p["B"], p["n_a"], p["n_b"], p["TA"], p["TB"]
+        TT = TA + TB
         L = lib()
         if flat_params is None:
             o = 0
@@ -297,24 +326,24 @@ class TensorCoreUpdate:
         gflat = flat_grads if flat_grads is not None else self.gflat
         gflat.zero_(); self.dbias.zero_(); self.sums.zero_()
         st = _stream()
-        xp, hp, dp = x.data_ptr(), self.h.data_ptr(), self.dpre.data_ptr()
-        # class B buffers are indexed from their own row 0: pass them offset by -n_a rows (only rows in range are touched)
-        lb_off, dlb_off = self.lb.data_ptr() - n_a * 512 * 2, self.dlb.data_ptr() - n_a * 512 * 2
+        xp, hp, dp = self.xb.data_ptr(), self.h.data_ptr(), self.dpre.data_ptr()
+        # class B buffers are indexed from their own tile 0: pass them offset by -TA tiles (only tiles in range are touched)
+        lb_off, dlb_off = self.lb.data_ptr() - TA * 128 * 512 * 2, self.dlb.data_ptr() - TA * 128 * 512 * 2
         with torch.cuda.device(self.device):
             check(L.bg_ppo_pack_weights(flat_params.data_ptr(), self.w1p.data_ptr(), self.wap_a.data_ptr(), self.wap_b.data_ptr(),
                                         self.bias_a.data_ptr(), self.bias_b.data_ptr(), st), "bg_ppo_pack_weights")
-            check(L.bg_ppo_gemm_nt(0, xp, 0, B, self.w1p.data_ptr(), None, None, hp, st), "ppo gemm HIDDEN")
-            check(L.bg_ppo_gemm_nt(1, hp, 0, n_a, self.wap_a.data_ptr(), self.bias_a.data_ptr(), None, self.la.data_ptr(), st), "ppo gemm LOGITS_A")
-            check(L.bg_ppo_gemm_nt(2, hp, n_a, B, self.wap_b.data_ptr(), self.bias_b.data_ptr(), None, lb_off, st), "ppo gemm LOGITS_B")
-            check(L.bg_ppo_loss_grad_classes(self.la.data_ptr(), self.dla.data_ptr(), self.lb.data_ptr(), self.dlb.data_ptr(), n_a, B,
-                                             counts.data_ptr(), actions.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
-                                             returns.data_ptr(), float(eps_clip), float(value_coef), float(entropy_coef),
-                                             self.dbias.data_ptr(), self.sums.data_ptr(), st), "bg_ppo_loss_grad_classes")
-            check(L.bg_ppo_gemm_nt(3, self.dla.data_ptr(), 0, n_a, self.wap_a.data_ptr(), None, hp, dp, st), "ppo gemm DPRE_A")
-            check(L.bg_ppo_gemm_nt(4, dlb_off, n_a, B, self.wap_b.data_ptr(), None, hp, dp, st), "ppo gemm DPRE_B")
-            check(L.bg_ppo_gemm_tn(5, hp, self.dla.data_ptr(), 0, n_a, gflat.data_ptr(), None, st), "ppo gemm GRAD_WA_A")
-            check(L.bg_ppo_gemm_tn(6, hp, dlb_off, n_a, B, gflat.data_ptr(), None, st), "ppo gemm GRAD_WA_B")
-            check(L.bg_ppo_gemm_tn(7, dp, xp, 0, B, gflat.data_ptr(), self.w1t.data_ptr(), st), "ppo gemm GRAD_W1")
+            check(L.bg_ppo_gemm_nt(0, xp, 0, TT, self.w1p.data_ptr(), None, None, hp, st), "ppo gemm HIDDEN")
+            check(L.bg_ppo_gemm_nt(1, hp, 0, TA, self.wap_a.data_ptr(), self.bias_a.data_ptr(), None, self.la.data_ptr(), st), "ppo gemm LOGITS_A")
+            check(L.bg_ppo_gemm_nt(2, hp, TA, TT, self.wap_b.data_ptr(), self.bias_b.data_ptr(), None, lb_off, st), "ppo gemm LOGITS_B")
+            check(L.bg_ppo_loss_grad_classes(self.la.data_ptr(), self.dla.data_ptr(), self.lb.data_ptr(), self.dlb.data_ptr(), n_a, n_b,
+                                             TA * 128, p["counts"].data_ptr(), p["actions"].data_ptr(), p["old_logp"].data_ptr(),
+                                             p["adv"].data_ptr(), p["returns"].data_ptr(), float(eps_clip), float(value_coef),
+                                             float(entropy_coef), self.dbias.data_ptr(), self.sums.data_ptr(), st), "bg_ppo_loss_grad_classes")
+            check(L.bg_ppo_gemm_nt(3, self.dla.data_ptr(), 0, TA, self.wap_a.data_ptr(), None, hp, dp, st), "ppo gemm DPRE_A")
+            check(L.bg_ppo_gemm_nt(4, dlb_off, TA, TT, self.wap_b.data_ptr(), None, hp, dp, st), "ppo gemm DPRE_B")
+            check(L.bg_ppo_gemm_tn(5, hp, self.dla.data_ptr(), 0, TA, gflat.data_ptr(), None, st), "ppo gemm GRAD_WA_A")
+            check(L.bg_ppo_gemm_tn(6, hp, dlb_off, TA, TT, gflat.data_ptr(), None, st), "ppo gemm GRAD_WA_B")
+            check(L.bg_ppo_gemm_tn(7, dp, xp, 0, TT, gflat.data_ptr(), self.w1t.data_ptr(), st), "ppo gemm GRAD_W1")
         # bias gradients = column sums of dlogits, accumulated by the loss kernels
         OFF_BA, OFF_BV = 128 * 198 + 128 + 500 * 128, 128 * 198 + 128 + 500 * 128 + 500 + 128
         gflat[OFF_BA:OFF_BA + ACTIONS].copy_(self.dbias[:ACTIONS])
@@ -427,7 +456,6 @@ class PPOLearner:
         manual = (c.manual_backward and c.autocast and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2
                   and x.shape[1] == 208 and x.is_contiguous())
         tc = manual and c.update_impl == "tcgen05" and mb == 1
-        n_a = None
         if manual:
             if self._manual is None or isinstance(self._manual, TensorCoreUpdate) != tc:
                 self._manual = TensorCoreUpdate(self.device) if tc else ManualUpdate(self.device)
@@ -436,10 +464,7 @@ class PPOLearner:
             old_logp, returns, adv = old_logp.float().contiguous(), returns.float().contiguous(), adv.float().contiguous()
             grads = {k: p.grad for k, p in self.fp.params.items()}
             if tc:
-                # sort the rollout by class once (the epochs reuse it): class A rows first
-                perm, n_a = self._manual.sort_by_class(counts, actions)
-                x, counts, actions = x[perm].contiguous(), counts[perm].contiguous(), actions[perm].contiguous()
-                old_logp, returns, adv = old_logp[perm].contiguous(), returns[perm].contiguous(), adv[perm].contiguous()
+                self._manual.prepare(x, counts, actions, old_logp, adv, returns)   # class sort + blocked x, once for all epochs
             else:
                 self._manual.invalidate()
         for _ in range(c.num_epochs):
@@ -447,7 +472,7 @@ class PPOLearner:
                 sl = slice(k * B // mb, (k + 1) * B // mb)
                 if tc:
                     st = self._manual.epoch(self.fp.params, grads, x, counts, actions, old_logp, adv, returns, c.eps_clip,
-                                            c.value_loss_coef, self.entropy_coef, n_a=n_a, flat_params=self.fp.flat,
+                                            c.value_loss_coef, self.entropy_coef, prepared=True, flat_params=self.fp.flat,
                                             flat_grads=self.fp.flat_grad)
                 elif manual:
                     st = self._manual.epoch(self.fp.params, grads, x[sl], counts[sl], actions[sl], old_logp[sl], adv[sl], returns[sl],

@@ -14,7 +14,7 @@ OFF = dict(w1=0, b1=128 * 198, wa=128 * 198 + 128, ba=128 * 198 + 128 + 64000, w
            bv=128 * 198 + 128 + 64000 + 500 + 128)
 
 
-def _setup(B=1000, n_a=700, seed=0):
+def _setup(seed=0):
     import bg_b200
     from bg_b200._lib import lib, check
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -33,7 +33,7 @@ def _setup(B=1000, n_a=700, seed=0):
     WapB = torch.zeros(512, 128, device=DEV); WapB[:500] = Wa; WapB[500] = wv
     biasA = torch.zeros(144, device=DEV); biasA[:128] = ba[:128]; biasA[128] = bv
     biasB = torch.zeros(512, device=DEV); biasB[:500] = ba; biasB[500] = bv
-    return dict(L=L, check=check, s=s, tc=tc, flat=flat, W1p=bf(W1p), WapA=bf(WapA), WapB=bf(WapB), biasA=biasA, biasB=biasB, B=B, n_a=n_a, g=g)
+    return dict(L=L, check=check, s=s, tc=tc, flat=flat, W1p=bf(W1p), WapA=bf(WapA), WapB=bf(WapB), biasA=biasA, biasB=biasB, g=g)
 
 
 def _rand_bf16(g, shape, scale=1.0):
@@ -47,48 +47,64 @@ def _close(got, want, rel=1e-2):
     assert err <= rel * scale, (err, scale)
 
 
-@pytest.mark.parametrize("B,n_a", [(1000, 700), (128, 128), (257, 0), (5, 3)])
-def test_forward_gemms_match_torch(B, n_a):
-    S = _setup(B, n_a)
+def _blk(bg, m):
+    return bg.TensorCoreUpdate.to_blocked(m)
+
+
+def _unblk(bg, b, R, C):
+    return bg.TensorCoreUpdate.from_blocked(b, R, C)
+
+
+@pytest.mark.parametrize("TA,TB", [(6, 2), (1, 0), (0, 3), (300, 20)])
+def test_forward_gemms_match_torch(TA, TB):
+    """HIDDEN / LOGITS_A / LOGITS_B on tile-blocked operands (TA class A tiles, TB class B tiles of 128 rows)"""
+    import bg_b200 as bg
+    S = _setup()
     L, check, s, tc = S["L"], S["check"], S["s"], S["tc"]
-    x = _rand_bf16(S["g"], (B, 208)); x[:, 198] = 1.0; x[:, 199:] = 0
-    h = torch.full((B, 128), 7.0, dtype=torch.bfloat16, device=DEV)
-    check(L.bg_ppo_gemm_nt(0, x.data_ptr(), 0, B, tc.w1p.data_ptr(), None, None, h.data_ptr(), s), "HIDDEN")
-    want_h = torch.relu(x.float() @ S["W1p"].t())
-    _close(h, want_h)
-    la = torch.full((max(n_a, 1), 144), 7.0, dtype=torch.bfloat16, device=DEV)
-    lb = torch.full((max(B - n_a, 1), 512), 7.0, dtype=torch.bfloat16, device=DEV)
-    check(L.bg_ppo_gemm_nt(1, h.data_ptr(), 0, n_a, tc.wap_a.data_ptr(), tc.bias_a.data_ptr(), None, la.data_ptr(), s), "LOGITS_A")
-    check(L.bg_ppo_gemm_nt(2, h.data_ptr(), n_a, B, tc.wap_b.data_ptr(), tc.bias_b.data_ptr(), None, lb.data_ptr() - n_a * 1024, s), "LOGITS_B")
+    R, RA, RB = (TA + TB) * 128, TA * 128, TB * 128
+    x = _rand_bf16(S["g"], (R, 208)); x[:, 198] = 1.0; x[:, 199:] = 0
+    xb = _blk(bg, x)
+    hb = torch.full((R * 128,), 7.0, dtype=torch.bfloat16, device=DEV)
+    check(L.bg_ppo_gemm_nt(0, xb.data_ptr(), 0, TA + TB, tc.w1p.data_ptr(), None, None, hb.data_ptr(), s), "HIDDEN")
+    h = _unblk(bg, hb, R, 128)
+    _close(h, torch.relu(x.float() @ S["W1p"].t()))
+    la = torch.full((max(RA, 128) * 144,), 7.0, dtype=torch.bfloat16, device=DEV)
+    lb = torch.full((max(RB, 128) * 512,), 7.0, dtype=torch.bfloat16, device=DEV)
+    check(L.bg_ppo_gemm_nt(1, hb.data_ptr(), 0, TA, tc.wap_a.data_ptr(), tc.bias_a.data_ptr(), None, la.data_ptr(), s), "LOGITS_A")
+    check(L.bg_ppo_gemm_nt(2, hb.data_ptr(), TA, TA + TB, tc.wap_b.data_ptr(), tc.bias_b.data_ptr(), None, lb.data_ptr() - TA * 128 * 1024, s), "LOGITS_B")
     torch.cuda.synchronize()
-    if n_a:
-        _close(la[:n_a, :129], (h[:n_a].float() @ S["WapA"].t() + S["biasA"])[:, :129])
-    if B > n_a:
-        _close(lb[:B - n_a, :501], (h[n_a:].float() @ S["WapB"].t() + S["biasB"])[:, :501])
+    if TA:
+        _close(_unblk(bg, la[:RA * 144], RA, 144)[:, :129], (h[:RA].float() @ S["WapA"].t() + S["biasA"])[:, :129])
+    if TB:
+        _close(_unblk(bg, lb[:RB * 512], RB, 512)[:, :501], (h[RA:].float() @ S["WapB"].t() + S["biasB"])[:, :501])
 
 
-@pytest.mark.parametrize("B,n_a", [(1000, 700), (300, 300), (130, 1)])
-def test_backward_gemms_match_torch(B, n_a):
-    S = _setup(B, n_a, seed=1)
+@pytest.mark.parametrize("TA,TB", [(6, 2), (3, 0), (1, 1), (200, 12)])
+def test_backward_gemms_match_torch(TA, TB):
+    import bg_b200 as bg
+    S = _setup(seed=1)
     L, check, s, tc, g = S["L"], S["check"], S["s"], S["tc"], S["g"]
-    x = _rand_bf16(g, (B, 208)); x[:, 198] = 1.0; x[:, 199:] = 0
-    h = torch.relu(_rand_bf16(g, (B, 128)))
-    dla = _rand_bf16(g, (max(n_a, 1), 144), 0.05); dla[:, 129:] = 0
-    dlb = _rand_bf16(g, (max(B - n_a, 1), 512), 0.05); dlb[:, 501:] = 0
-    dpre = torch.full((B, 128), 7.0, dtype=torch.bfloat16, device=DEV)
-    check(L.bg_ppo_gemm_nt(3, dla.data_ptr(), 0, n_a, tc.wap_a.data_ptr(), None, h.data_ptr(), dpre.data_ptr(), s), "DPRE_A")
-    check(L.bg_ppo_gemm_nt(4, dlb.data_ptr() - n_a * 1024, n_a, B, tc.wap_b.data_ptr(), None, h.data_ptr(), dpre.data_ptr(), s), "DPRE_B")
+    R, RA, RB = (TA + TB) * 128, TA * 128, TB * 128
+    x = _rand_bf16(g, (R, 208)); x[:, 198] = 1.0; x[:, 199:] = 0
+    h = torch.relu(_rand_bf16(g, (R, 128)))
+    dla = _rand_bf16(g, (max(RA, 128), 144), 0.05); dla[:, 129:] = 0
+    dlb = _rand_bf16(g, (max(RB, 128), 512), 0.05); dlb[:, 501:] = 0
+    xb, hb, dlab, dlbb = _blk(bg, x), _blk(bg, h), _blk(bg, dla), _blk(bg, dlb)
+    dpreb = torch.full((R * 128,), 7.0, dtype=torch.bfloat16, device=DEV)
+    check(L.bg_ppo_gemm_nt(3, dlab.data_ptr(), 0, TA, tc.wap_a.data_ptr(), None, hb.data_ptr(), dpreb.data_ptr(), s), "DPRE_A")
+    check(L.bg_ppo_gemm_nt(4, dlbb.data_ptr() - TA * 128 * 1024, TA, TA + TB, tc.wap_b.data_ptr(), None, hb.data_ptr(), dpreb.data_ptr(), s), "DPRE_B")
+    dpre = _unblk(bg, dpreb, R, 128)
     mask = (h.float() > 0).float()
-    want = torch.cat([dla[:n_a].float() @ S["WapA"], dlb[:B - n_a].float() @ S["WapB"]], 0) * mask
+    want = torch.cat([dla[:RA].float() @ S["WapA"], dlb[:RB].float() @ S["WapB"]], 0) * mask
     _close(dpre, want)
     gflat = torch.zeros(90101, device=DEV)
     scratch = torch.empty(199 * 128, device=DEV)
-    check(L.bg_ppo_gemm_tn(5, h.data_ptr(), dla.data_ptr(), 0, n_a, gflat.data_ptr(), None, s), "GRAD_WA_A")
-    check(L.bg_ppo_gemm_tn(6, h.data_ptr(), dlb.data_ptr() - n_a * 1024, n_a, B, gflat.data_ptr(), None, s), "GRAD_WA_B")
-    check(L.bg_ppo_gemm_tn(7, dpre.data_ptr(), x.data_ptr(), 0, B, gflat.data_ptr(), scratch.data_ptr(), s), "GRAD_W1")
+    check(L.bg_ppo_gemm_tn(5, hb.data_ptr(), dlab.data_ptr(), 0, TA, gflat.data_ptr(), None, s), "GRAD_WA_A")
+    check(L.bg_ppo_gemm_tn(6, hb.data_ptr(), dlbb.data_ptr() - TA * 128 * 1024, TA, TA + TB, gflat.data_ptr(), None, s), "GRAD_WA_B")
+    check(L.bg_ppo_gemm_tn(7, dpreb.data_ptr(), xb.data_ptr(), 0, TA + TB, gflat.data_ptr(), scratch.data_ptr(), s), "GRAD_W1")
     torch.cuda.synchronize()
-    gA = dla[:n_a].float().t() @ h[:n_a].float()                       # (144,128)
-    gB = dlb[:B - n_a].float().t() @ h[n_a:].float()                   # (512,128)
+    gA = dla[:RA].float().t() @ h[:RA].float()                         # (144,128)
+    gB = dlb[:RB].float().t() @ h[RA:].float()                         # (512,128)
     want_wa = gB[:500].clone(); want_wa[:128] += gA[:128]
     want_wv = gB[500] + gA[128]
     gW1 = dpre.float().t() @ x.float()                                 # (128,208)
@@ -97,6 +113,26 @@ def test_backward_gemms_match_torch(B, n_a):
     _close(gflat[:OFF["b1"]].view(128, 198), gW1[:, :198], 2e-3)
     _close(gflat[OFF["b1"]:OFF["wa"]], gW1[:, 198], 2e-3)
     assert float(gflat[OFF["ba"]:OFF["wv"]].abs().sum()) == 0.0        # biases are not these kernels' business
+
+
+def test_gather_block_matches_torch():
+    import bg_b200 as bg
+    from bg_b200._lib import lib, check
+    g = torch.Generator().manual_seed(5)
+    x = _rand_bf16(g, (1000, 208))
+    perm = torch.randperm(1000, generator=g)[:700].to(torch.int32)
+    pp = torch.full((768,), -1, dtype=torch.int32)
+    pp[:300] = perm[:300]                                   # class A: 300 rows + 84 padding rows
+    pp[384:384 + 380] = perm[300:680]                       # class B: 380 rows + 4 padding rows
+    pp = pp.to(DEV)
+    out = torch.full((768 * 208,), 3.0, dtype=torch.bfloat16, device=DEV)
+    check(lib().bg_ppo_gather_block(x.data_ptr(), 208, pp.data_ptr(), 768, 208, 198, out.data_ptr(), torch.cuda.current_stream().cuda_stream), "gather")
+    got = bg.TensorCoreUpdate.from_blocked(out, 768, 208)
+    want = torch.zeros((768, 208), dtype=torch.bfloat16, device=DEV)
+    valid = pp >= 0
+    want[valid] = x[pp[valid].long()]
+    want[valid, 198] = 1.0
+    assert torch.equal(got, want)
 
 
 def test_adam_kernel_matches_torch():
