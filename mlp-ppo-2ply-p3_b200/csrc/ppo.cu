@@ -80,6 +80,13 @@ __device__ __forceinline__ long long mat_off(long long r, int c, long long ld, i
     return blocked ? (r >> 7) * (ld * 128) + (long long)(c >> 3) * 1024 + (r & 127) * 8 + (c & 7) : r * ld + c;
 }
 
+// Slot (column) kk = 0..15 of lane group `sub` in the packed kernel.  Row-major: 16 consecutive slots per lane.  Blocked: two whole
+// 16-byte chunks per lane (slots 8 sub .. 8 sub + 7 and 64 + 8 sub ..), so that a warp's accesses cover full sectors of the
+// tile-blocked layout (with 16 consecutive slots per lane every sector was fetched four times: the kernel ran 2x slower).
+__device__ __forceinline__ int pk_col(int sub, int kk, int blocked) {
+    return blocked ? ((kk >> 3) << 6) + 8 * sub + (kk & 7) : 16 * sub + kk;
+}
+
 // A warp per sample, persistent warps striding over the rows; lane l holds slots 128 q + 4 l + e (q, e < 4), so that every
 // load / store instruction of the warp covers 256 (bf16) or 512 (f32) contiguous bytes, and the next row's logits and
 // scalars are fetched before the current row is worked on (the kernel needs ~125 registers, i.e. 16 warps per SM: one
@@ -140,7 +147,7 @@ __device__ __forceinline__ void loss_packed_load(LossPacked<T>& d, long long r, 
     for (int k = 0; k < 4; ++k) d.x[k] = Vec4<T>::zero();
     if (r < B) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) d.x[k] = Vec4<T>::load_raw(logits + mat_off(r, 16 * sub + 4 * k, ld, blocked));     // (read whatever the row's class: no dependent load)
+        for (int k = 0; k < 4; ++k) d.x[k] = Vec4<T>::load_raw(logits + mat_off(r, pk_col(sub, 4 * k, blocked), ld, blocked));     // (read whatever the row's class: no dependent load)
         d.n = __ldg(counts + r); d.a = __ldg(actions + r);
         d.adv = __ldg(adv + r); d.old_logp = __ldg(old_logp + r); d.ret = __ldg(returns + r);
         d.v = values ? __ldg(values + r) : loss_scalar(logits + mat_off(r, value_col, ld, blocked));
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
             Vec4<T>::unpack(cur.x[k], x);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int i = 16 * sub + 4 * k + e;
+                const int i = pk_col(sub, 4 * k + e, blocked);
                 z[4 * k + e] = i < n ? (act ? x[e] : 0.0f) : -INFINITY;
                 m = fmaxf(m, z[4 * k + e]);
             }
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
             const float lp = z[k] - lse;
             p[k] = __expf(lp);
             if (p[k] > 0.0f) h -= p[k] * lp;
-            if (16 * sub + k == a) lpa = lp;
+            if (pk_col(sub, k, blocked) == a) lpa = lp;
             z[k] = lp;
         }
 #pragma unroll
@@ -227,11 +234,11 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
                     const int kk = 4 * k + e;
                     const float pk = p[kk];
                     float d = -g * pk + (pk > 0.0f ? ce * pk * (z[kk] + h) : 0.0f);
-                    if (16 * sub + kk == a) d += g;
+                    if (pk_col(sub, kk, blocked) == a) d += g;
                     x[e] = d;
                     colsum[kk] += d;
                 }
-                Vec4<T>::store(dlogits + mat_off(row, 16 * sub + 4 * k, ld, blocked), x);
+                Vec4<T>::store(dlogits + mat_off(row, pk_col(sub, 4 * k, blocked), ld, blocked), x);
             }
             // quads 1..3 and the padding of the GEMM's N: exact zeros; column 500 carries d loss / d value when the value rides there
             // (prezeroed: the caller guarantees zeros there already -- only the value column is written)
@@ -265,7 +272,7 @@ __global__ void __launch_bounds__(kLossWarps * 32) ppo_loss_grad_packed_kernel(
     if (lane == 0) { s_part[warp][0] = pl; s_part[warp][1] = vl; s_part[warp][2] = ent; }
     if (grp == 0) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) s_col[warp][16 * sub + k] = colsum[k];
+        for (int k = 0; k < 16; ++k) s_col[warp][pk_col(sub, k, blocked)] = colsum[k];
     }
     if (lane == ((value_col - 128) & 31) >> 2) s_col[warp][128] = vsum;   // the lane group that wrote the value column (500: group 5, 128: group 0)
     __syncthreads();

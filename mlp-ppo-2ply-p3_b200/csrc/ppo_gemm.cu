@@ -88,7 +88,8 @@ struct NtArgs {
     int dbg;                                   // experiment switches (bg_ppo_gemm_debug): 1 no MMAs, 2 no epilogue stores, 4 no loads
 };
 
-constexpr int kNtEpiWarps = 8, kNtThreads = 32 * (kNtEpiWarps + 2);      // warps 0-7 epilogue, warp 8 producer, warp 9 MMA issuer
+constexpr int kNtEpiWarps = 16, kNtParts = kNtEpiWarps / 4;               // warps 0-15 epilogue (four per TMEM lane quarter), 16 producer, 17 MMA issuer
+constexpr int kNtThreads = 32 * (kNtEpiWarps + 2);
 __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ unsigned long long full[8], empty[8], acc_full[2], acc_empty[2], w_bar;
@@ -173,18 +174,27 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
             __syncwarp();
         }
     } else if (warp < kNtEpiWarps) {
-        // ================= epilogue: thread = row (TMEM lane), the two warps of a lane quarter split the columns =================
+        // ================= epilogue: thread = row (TMEM lane), the four warps of a lane quarter split the column blocks =================
+        // (the epilogue is the busiest role: with eight warps HIDDEN and LOGITS_A were bound by it)
         const int q = warp & 3, part = warp >> 2;
         const int r = q * 32 + lane;                                   // row inside the tile
+        const int nblk = (a.N + 31) >> 5;                              // blocks of 32 columns (the last may be 16 wide: N = 144)
         for (long long t = 0; t < my_tiles; ++t) {
             const int acc = (int)(t % nacc);
-            warp_wait(&acc_full[acc], (uint32_t)(t / nacc) & 1u, lane);
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const size_t tile = (size_t)tile_of(t);
             unsigned char* otile = reinterpret_cast<unsigned char*>(a.out) + tile * a.nc_out * kChunk + r * 16;
-            const unsigned char* mtile = reinterpret_cast<const unsigned char*>(a.mask) + tile * 16 * kChunk + r * 16;
-            const int nblk = (a.N + 31) >> 5;                          // blocks of 32 columns (the last may be 16 wide: N = 144)
-            for (int blk = part; blk < nblk; blk += 2) {
+            // relu'(h) mask of this thread's blocks: fetched BEFORE waiting for the accumulator, so that the latency of the loads
+            // hides behind the MMAs (loaded after the wait, DPRE_A ran at 2.6 TB/s)
+            // (the dpre ops have N = 128: exactly one block per warp)
+            uint4 mk[4];
+            if (a.epi == 2) {
+                const unsigned char* mtile = reinterpret_cast<const unsigned char*>(a.mask) + tile * 16 * kChunk + r * 16;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mk[j] = __ldg(reinterpret_cast<const uint4*>(mtile + (size_t)(4 * part + j) * kChunk));
+            }
+            warp_wait(&acc_full[acc], (uint32_t)(t / nacc) & 1u, lane);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            for (int blk = part; blk < nblk; blk += kNtParts) {
                 const int c0 = 32 * blk, w = a.N - c0 < 32 ? a.N - c0 : 32;
                 uint32_t av[32];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + c0);
@@ -194,9 +204,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {                          // chunk column c0 / 8 + j: 8 results = 16 bytes, a warp writes 512 contiguous bytes
                     if (8 * j >= w) break;
-                    uint4 mk = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-                    if (a.epi == 2) mk = __ldg(reinterpret_cast<const uint4*>(mtile + (size_t)((c0 >> 3) + j) * kChunk));
-                    const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+                    const uint32_t mw[4] = {mk[j].x, mk[j].y, mk[j].z, mk[j].w};
                     uint32_t o[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -207,7 +215,8 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
                             if ((mw[e] & 0x0000FFFFu) == 0u) v0 = 0.0f;
                             if ((mw[e] & 0xFFFF0000u) == 0u) v1 = 0.0f;
                         }
-                        o[e] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v1)) << 16);
+                        const __nv_bfloat162 pr = __floats2bfloat162_rn(v0, v1);
+                        o[e] = *reinterpret_cast<const uint32_t*>(&pr);
                     }
                     if (!(a.dbg & 2)) *reinterpret_cast<uint4*>(otile + (size_t)((c0 >> 3) + j) * kChunk) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
