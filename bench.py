@@ -7,7 +7,7 @@
 Workload (BASELINE.json configs[1]): batched legal-move generation + step on 65,536 parallel games per GPU,
 uniform-random policy, positions from the engine's own random self-play (Philox seed 0x5EED, 128 untimed
 de-phasing turns).  One "step" = one turn of every game:
-    bg_random_actions -> K2 bg_env_step (apply play, reward/terminal, auto-reset, Philox dice)
+    K2 bg_env_step_random (uniform-random action, apply play, reward/terminal, auto-reset, Philox dice)
     -> K1 bg_movegen_slab (all legal afterstates of the new positions, reference order)
     -> K3 bg_encode_f32 (observations) + bg_encode_bf16 (ragged afterstate features)
 i.e. everything BackgammonEnv.step + update_legal_moves + get_observation do, minus the dense
@@ -287,18 +287,16 @@ def run_engine(args):
     N = env.num_envs
     env.reset()
     acts = torch.empty(N, dtype=torch.int32, device=dev)
-    rows_acc = torch.zeros(1, dtype=torch.int64, device=dev)
     feats = not args.no_afterstate_features
-    LAUNCHES_PER_STEP = 1 + 1 + 3 + 1 + 2 * int(feats)        # actions, K2, K1 tiers 0/1/2, K3 f32, K3 bf16 (two row ranges)
+    LAUNCHES_PER_STEP = 1 + 3 + 1 + 2 * int(feats)            # K2 (random policy inside), K1 tiers 0/1/2, K3 f32, K3 bf16 (two row ranges)
 
-    def one_step(t, ev=None, overlap=True, count_rows=False):
-        env.random_actions(ACT_SEED, t, out=acts)
-        env._apply_actions(acts)
+    def one_step(t, ev=None, overlap=True):
+        # K2 with the uniform-random policy inside (bg_env_step_random: the draw of bg_random_actions, one launch less)
+        env.step_random_device(ACT_SEED, t)
         # K1 tiers 0/1/2 + K3 (observations f32, afterstate features bf16: rows final after tier 0 are encoded on
-        # a second stream beside tiers 1/2, the rest after them) in one C call
+        # a second stream beside tiers 1/2, the rest after them) in one C call; the slab row counter lives in K1's workspace
+        # header and is zeroed by K1's own memset
         env.update_legal_plays(obs=True, features=feats, overlap=overlap, k1_events=ev)
-        if count_rows:
-            rows_acc.add_(env.alloc_rows)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     t = 0
@@ -331,13 +329,12 @@ def run_engine(args):
     torch.cuda.synchronize()
     e0.record()
     for k in range(n_timed):
-        one_step(t, k1_events[k], overlap=not args.no_overlap, count_rows=True); t += 1
+        one_step(t, k1_events[k], overlap=not args.no_overlap); t += 1
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
-    rows_per_step = float(rows_acc.item()) / n_timed          # snapshot: nothing after this line adds to it
     clocks = sampler.stop() if rank == 0 else None
     env.check_status()
     k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / n_timed
@@ -347,11 +344,13 @@ def run_engine(args):
     acc = dict.fromkeys(names, 0.0)
     PK = 20
     pe = [[ev() for _ in range(len(names) + 1)] for _ in range(PK)]
-    for row in pe:
+    rows_log = torch.zeros(PK, dtype=torch.int64, device=dev)   # legal plays of these PK steps (counted here, outside the timed region:
+    for i_pk, row in enumerate(pe):                             #  the positions are a stationary random-play mix)
         row[0].record()
         env.random_actions(ACT_SEED, t, out=acts); row[1].record()
         env._apply_actions(acts); row[2].record()
         env._refresh_legal_moves(); row[3].record()
+        rows_log[i_pk].copy_(env.alloc_rows[0])
         env.encode_resident(obs=True, afterstates=False); row[4].record()
         if feats:
             env.encode_resident(obs=False, afterstates=True)
@@ -363,6 +362,7 @@ def run_engine(args):
             acc[nme] += row[i].elapsed_time(row[i + 1]) / PK
     k1_alone_ms = acc["k1_movegen"]
     step_serial_ms = sum(acc.values())
+    rows_per_step = float(rows_log.double().mean().item())
     env.check_status()
 
     # ---- end to end through the public API with host buffers: actions from pinned host memory every step,

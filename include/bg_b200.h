@@ -73,7 +73,8 @@ int bg_movegen_write(const int8_t* boards52, const int8_t* players, const int8_t
                      uint16_t* row_features_bf16 /*nullable: fused K3, [rows][208] bf16*/, int32_t* counts_true /*nullable*/, int32_t* counts /*nullable*/, int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
 
 /* single-pass form used by the env: every warp reserves its rows with one atomicAdd on *alloc_rows
- * (caller zeroes it); starts[b] receives the first row.  Row blocks of different positions are in
+ * (caller zeroes it -- or lets it live in bytes [48, 56) of `workspace`, which every K1 call zeroes itself together with its own
+ * counters: one fill less per turn); starts[b] receives the first row.  Row blocks of different positions are in
  * arbitrary order, rows inside a block are in reference order.  counts[b] = min(true, max_rows). */
 int bg_movegen_slab(const int8_t* boards52, const int8_t* players, const int8_t* dice, long long B,
                     int max_rows_per_board, int8_t* afterstates52, long long afterstate_capacity_rows,
@@ -151,6 +152,10 @@ typedef struct bg_step_out {
 int bg_env_reset(const bg_env_state* st, const uint8_t* mask, int32_t* status, void* stream);
 /* one step of every game with actions[g] (int32 index into its legal plays; ignored on a pass). */
 int bg_env_step(const bg_env_state* st, const int32_t* actions, const bg_step_out* out, int32_t* status, void* stream);
+/* bg_random_actions + bg_env_step in ONE launch: game g plays actions[g] = mulhi(Philox(act_seed, stream_base+g, t; "ACT1"), counts[g])
+ * (the same draw as bg_random_actions), written to actions_out if non-null. */
+int bg_env_step_random(const bg_env_state* st, unsigned long long act_seed, uint32_t t, int32_t* actions_out /*nullable*/,
+                       const bg_step_out* out, int32_t* status, void* stream);
 /* actions from (pinned) host memory to the device: one plain cudaMemcpyAsync of n int32 on `stream` (the host-side
  * policy's upload of VectorizedBackgammonEnv.step(actions), vec_bg_env.py:28-33), issued from this library so that the
  * caller needs no second CUDA runtime binding. */

@@ -49,6 +49,7 @@ SIGNATURES = {
     "bg_env_reset": (_I, [C.POINTER(EnvState), _V, _V, _V]),
     "bg_env_step": (_I, [C.POINTER(EnvState), _V, C.POINTER(StepOut), _V, _V]),
     "bg_random_actions": (_I, [_V, _LL, _U64, _U64, _U32, _V, _V]),
+    "bg_env_step_random": (_I, [C.POINTER(EnvState), _U64, _U32, _V, C.POINTER(StepOut), _V, _V]),
     "bg_copy_actions_async": (_I, [_V, _V, _LL, _V]),
     "bg_movegen_replies_slab": (_I, [_V, _V, _LL, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     "bg_twoply_replies_values": (_I, [_V, _V, _LL, _V, _LL, _V, _V, _V, _V, _V, _V, _SZ, _V, _V, _V, _F, _V, _V, _V, _V]),

