@@ -162,7 +162,6 @@ def test_step_random_equals_random_actions_then_step():
         a.step_device(a.random_actions(5, t))
         b.step_random_device(5, t, actions_out=acts)
         b._refresh_legal_moves()
-        assert torch.equal(acts, a.random_actions(5, t).new_tensor(acts)) or True
     for name in ("boards52", "players", "dice", "scores", "draws", "legal_counts", "rewards", "dones_u8"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert int(a.alloc_rows.item()) == int(a.legal_counts.sum().item()) == int(b.alloc_rows.item())
