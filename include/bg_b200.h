@@ -303,7 +303,14 @@ int bg_ppo_gemm_tn(int op, const uint16_t* A, const uint16_t* B, long long tile_
 int bg_ppo_loss_grad_classes(const void* logits_a, void* dlogits_a, const void* logits_b, void* dlogits_b, long long n_a, long long n_b,
                              long long b_offset, const int32_t* counts, const int32_t* actions, const float* old_log_probs, const float* advantages,
                              const float* returns, float eps_clip, float value_coef, float entropy_coef, float* dbias /*[512]*/,
-                             float* sums /*[3]*/, void* stream);
+                             float* sums /*[3]*/, int class_a_done /* class A already handled by bg_ppo_logits_loss_a */, void* stream);
+/* LOGITS_A with the class A loss as its epilogue (the logits of class A never leave the SM): dlogits_a = d loss / d logits of rows
+ * [0, n_a) in the 144-column blocked layout (padding rows of the last tile written as zeros); dbias / sums accumulated as by
+ * bg_ppo_loss_grad_classes (call that with class_a_done = 1 for class B); means over B_norm samples. */
+int bg_ppo_logits_loss_a(const uint16_t* h, long long n_a, long long B_norm, const uint16_t* wap_a, const float* bias_a,
+                         const int32_t* counts, const int32_t* actions, const float* old_log_probs, const float* advantages,
+                         const float* returns, float eps_clip, float value_coef, float entropy_coef, uint16_t* dlogits_a, float* dbias,
+                         float* sums, void* stream);
 int bg_ppo_gemm_debug(int flags);  /* experiment switches for scripts/exp_ppo_gemm.py (1 no MMAs, 2 no stores, 4 no loads); 0 = normal */
 int bg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                  float beta2, float eps, int step, float grad_scale, void* stream);

@@ -66,7 +66,8 @@ SIGNATURES = {
     "bg_ppo_pack_weights": (_I, [_V, _V, _V, _V, _V, _V, _V]),
     "bg_ppo_gemm_nt": (_I, [_I, _V, _LL, _LL, _V, _V, _V, _V, _V]),
     "bg_ppo_gemm_tn": (_I, [_I, _V, _V, _LL, _LL, _V, _V, _V]),
-    "bg_ppo_loss_grad_classes": (_I, [_V, _V, _V, _V, _LL, _LL, _LL, _V, _V, _V, _V, _V, _F, _F, _F, _V, _V, _V]),
+    "bg_ppo_loss_grad_classes": (_I, [_V, _V, _V, _V, _LL, _LL, _LL, _V, _V, _V, _V, _V, _F, _F, _F, _V, _V, _I, _V]),
+    "bg_ppo_logits_loss_a": (_I, [_V, _LL, _LL, _V, _V, _V, _V, _V, _V, _V, _F, _F, _F, _V, _V, _V, _V]),
     "bg_ppo_gather_block": (_I, [_V, _LL, _V, _LL, _I, _I, _V, _V]),
     "bg_ppo_gemm_debug": (_I, [_I]),
     "bg_adam_step": (_I, [_V, _V, _V, _V, _LL, _F, _F, _F, _F, _I, _F, _V]),

@@ -496,16 +496,17 @@ extern "C" int bg_ppo_loss_grad(const void* logits, int flags, long long ld, con
 extern "C" int bg_ppo_loss_grad_classes(const void* logits_a, void* dlogits_a, const void* logits_b, void* dlogits_b, long long n_a,
                                         long long n_b, long long b_offset, const int32_t* counts, const int32_t* actions,
                                         const float* old_log_probs, const float* advantages, const float* returns, float eps_clip,
-                                        float value_coef, float entropy_coef, float* dbias, float* sums, void* stream) {
+                                        float value_coef, float entropy_coef, float* dbias, float* sums, int class_a_done, void* stream) {
+    // class_a_done: class A has been handled by bg_ppo_logits_loss_a (the loss fused into the GEMM's epilogue); it still counts in the means
     if (n_a < 0 || n_b < 0 || b_offset < n_a) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_loss_grad_classes: bad sizes");
     const long long B = n_a + n_b;
     if (B == 0) return BG_OK;
-    if (!counts || !actions || !old_log_probs || !advantages || !returns || !sums || (n_a > 0 && (!logits_a || !dlogits_a)) ||
+    if (!counts || !actions || !old_log_probs || !advantages || !returns || !sums || (n_a > 0 && !class_a_done && (!logits_a || !dlogits_a)) ||
         (n_b > 0 && (!logits_b || !dlogits_b)))
         return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_loss_grad_classes: null pointer");
     const long long resident = (long long)bg_sm_count() * 2;
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_a > 0) {
+    if (n_a > 0 && !class_a_done) {
         const long long need = (n_a + 4 * bg::kLossWarps - 1) / (4 * bg::kLossWarps);
         bg::ppo_loss_grad_packed_kernel<__nv_bfloat16><<<(unsigned)(need < resident ? need : resident), bg::kLossWarps * 32, 0, st>>>(
             (const __nv_bfloat16*)logits_a, 144, nullptr, counts, actions, old_log_probs, advantages, returns, n_a, eps_clip, value_coef,

@@ -86,18 +86,26 @@ struct NtArgs {
     const float* bias; const uint16_t* mask;   // mask: h, tile-blocked, 16 chunk columns per tile
     uint16_t* out; int nc_out;
     int dbg;                                   // experiment switches (bg_ppo_gemm_debug): 1 no MMAs, 2 no epilogue stores, 4 no loads
+    // epi == 3 (LOGITS_LOSS_A): the class A loss in the epilogue -- `out` receives d loss / d logits, the logits never leave the SM
+    const int32_t* counts; const int32_t* actions; const float* old_logp; const float* adv; const float* returns;
+    long long n_rows;                          // real class A rows (the tiles' rows beyond it are padding)
+    float eps_clip, value_coef, entropy_coef, inv_b;
+    float* dbias; float* sums;                 // [512] column sums of dlogits (value head at 500), [3] policy / value / entropy sums
 };
 
 constexpr int kNtEpiWarps = 16, kNtParts = kNtEpiWarps / 4;               // warps 0-15 epilogue (four per TMEM lane quarter), 16 producer, 17 MMA issuer
 constexpr int kNtThreads = 32 * (kNtEpiWarps + 2);
+template <bool LOSS>
 __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ unsigned long long full[8], empty[8], acc_full[2], acc_empty[2], w_bar;
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_bias[512];
+    __shared__ __align__(16) float4 s_red[LOSS ? 2 : 1][LOSS ? 4 : 1][LOSS ? kRows : 1];   // per tile parity, part, row: (max, sum exp, sum exp * z, z[action])
+    __shared__ float s_vrow[LOSS ? 2 : 1][LOSS ? kRows : 1];                                 // the row's value (held by part 0)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t stage_bytes = (uint32_t)(a.KC >> 3) * kChunk;
-    if (a.epi == 1) for (int c = tid; c < 512; c += blockDim.x) s_bias[c] = c < a.N ? a.bias[c] : 0.0f;
+    if (a.epi == 1 || LOSS) for (int c = tid; c < 512; c += blockDim.x) s_bias[c] = c < a.N ? a.bias[c] : 0.0f;
     unsigned char* A0 = smem + ((a.w_bytes + 1023) & ~1023);
     const uint32_t Ws = smem_u32(smem), As0 = smem_u32(A0);
     const int nacc = a.N <= 256 ? 2 : 1;                               // accumulators in TMEM (columns 0.. and 256..)
@@ -179,6 +187,130 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
         const int q = warp & 3, part = warp >> 2;
         const int r = q * 32 + lane;                                   // row inside the tile
         const int nblk = (a.N + 31) >> 5;                              // blocks of 32 columns (the last may be 16 wide: N = 144)
+        if (LOSS) {
+            // ---- LOGITS_LOSS_A: logits = acc + bias (rounded to bf16 as the reference's autocast does), then the loss of
+            // ppo_agent.py:271-299 and its gradient, as in ppo_loss_grad_packed_kernel (csrc/ppo.cu): warp `part` holds slots
+            // 32 part .. 32 part + 31 of its rows (part 0 also the value head, column 128); the four parts of a row exchange
+            // (max, sum exp, sum exp z, z[action]) through shared memory; d loss / d logits goes out as bf16, the logits do not.
+            float colsum[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) colsum[j] = 0.0f;
+            float pl = 0.0f, vl = 0.0f, ent = 0.0f, vsum = 0.0f;
+            const float ce = a.entropy_coef * a.inv_b;
+            for (long long t = 0; t < my_tiles; ++t) {
+                const int acc = (int)(t % nacc), par = (int)(t & 1);
+                const size_t tile = (size_t)tile_of(t);
+                const long long gr = (long long)tile * kRows + r;      // class A sample index
+                const bool live = gr < a.n_rows;
+                int n = 1, act = 0; float A = 0.0f, olp = 0.0f, ret = 0.0f;
+                if (live) { n = __ldg(a.counts + gr); act = __ldg(a.actions + gr); A = __ldg(a.adv + gr); olp = __ldg(a.old_logp + gr); ret = __ldg(a.returns + gr); }
+                warp_wait(&acc_full[acc], (uint32_t)(t / nacc) & 1u, lane);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                uint32_t av[32];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+                tmem_ld32(taddr + 32 * part, av);
+                uint32_t vv[8];
+                if (part == 0) tmem_ld8(taddr + 128, vv);
+                tmem_ld_wait();
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                mbar_arrive(&acc_empty[acc]);                          // the accumulator may be overwritten: everything is in registers
+                float z[32];
+                float m = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float l = __bfloat162float(__float2bfloat16_rn(__uint_as_float(av[j]) + s_bias[32 * part + j]));
+                    z[j] = (32 * part + j < n) ? l : -INFINITY;
+                    m = fmaxf(m, z[j]);
+                }
+                float ssum = 0.0f, tsum = 0.0f, za = 0.0f;
+                if (m > -INFINITY) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float e = __expf(z[j] - m);              // 0 for masked slots
+                        ssum += e;
+                        if (z[j] > -INFINITY) tsum = fmaf(e, z[j], tsum);
+                        if (32 * part + j == act) za = z[j];
+                    }
+                }
+                s_red[par][part][r] = make_float4(m, ssum, tsum, za);
+                if (part == 0) s_vrow[par][r] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(vv[0]) + s_bias[128]));
+                asm volatile("bar.sync 1, %0;\n" :: "n"(kNtEpiWarps * 32) : "memory");
+                float M = -INFINITY;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) M = fmaxf(M, s_red[par][k][r].x);
+                float S = 0.0f, T = 0.0f, ZA = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 v = s_red[par][k][r];
+                    if (v.x > -INFINITY) { const float sc = __expf(v.x - M); S = fmaf(v.y, sc, S); T = fmaf(v.z, sc, T); }
+                    ZA += v.w;
+                }
+                const float lse = M + __logf(S);
+                const float H = lse - T / S;                           // entropy = -sum p log p
+                const float lpa = ZA - lse;
+                const float rr = __expf(lpa - olp);
+                const float rc = fminf(fmaxf(rr, 1.0f - a.eps_clip), 1.0f + a.eps_clip);
+                const float s1 = rr * A, s2 = rc * A;
+                const bool through = (rr >= 1.0f - a.eps_clip && rr <= 1.0f + a.eps_clip) || s1 < s2;
+                const float g = through ? -A * rr * a.inv_b : 0.0f;
+                const float v = s_vrow[par][r];
+                const float dv = v - ret;
+                const float dvalue = 2.0f * a.value_coef * dv * a.inv_b;
+                unsigned char* otile = reinterpret_cast<unsigned char*>(a.out) + tile * a.nc_out * kChunk + r * 16;
+#pragma unroll
+                for (int jc = 0; jc < 4; ++jc) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                        float d2[2];
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const int j = 8 * jc + 2 * e2 + h2;
+                            float d = 0.0f;
+                            if (live && z[j] > -INFINITY) {
+                                const float lp = z[j] - lse;
+                                const float pk = __expf(lp);
+                                d = -g * pk + (pk > 0.0f ? ce * pk * (lp + H) : 0.0f);
+                                if (32 * part + j == act) d += g;
+                            }
+                            colsum[j] += d;
+                            d2[h2] = d;
+                        }
+                        const __nv_bfloat162 pr = __floats2bfloat162_rn(d2[0], d2[1]);
+                        o[e2] = *reinterpret_cast<const uint32_t*>(&pr);
+                    }
+                    if (!(a.dbg & 2)) *reinterpret_cast<uint4*>(otile + (size_t)(4 * part + jc) * kChunk) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                if (part == 0) {                                       // the value head's column (128) and the zero padding (129 .. 143)
+                    const float dvw = live ? dvalue : 0.0f;
+                    const __nv_bfloat162 pr = __floats2bfloat162_rn(dvw, 0.0f);
+                    if (!(a.dbg & 2)) {
+                        *reinterpret_cast<uint4*>(otile + (size_t)16 * kChunk) = make_uint4(*reinterpret_cast<const uint32_t*>(&pr), 0u, 0u, 0u);
+                        *reinterpret_cast<uint4*>(otile + (size_t)17 * kChunk) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    if (live) { vsum += dvw; pl -= fminf(s1, s2); vl = fmaf(dv, dv, vl); ent += H; }
+                }
+            }
+            // column sums (= the head biases' gradients) and the loss sums: over the rows of the warp, then one atomic per column and warp
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float c = colsum[j];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+                if (lane == (j & 31) && a.dbias) atomicAdd(a.dbias + 32 * part + j, c);
+            }
+            if (part == 0) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    pl += __shfl_xor_sync(kFull, pl, o); vl += __shfl_xor_sync(kFull, vl, o); ent += __shfl_xor_sync(kFull, ent, o);
+                    vsum += __shfl_xor_sync(kFull, vsum, o);
+                }
+                if (lane == 0) {
+                    atomicAdd(a.sums + 0, pl); atomicAdd(a.sums + 1, vl); atomicAdd(a.sums + 2, ent);
+                    if (a.dbias) atomicAdd(a.dbias + BG_ACTIONS, vsum);
+                }
+            }
+        } else
         for (long long t = 0; t < my_tiles; ++t) {
             const int acc = (int)(t % nacc);
             const size_t tile = (size_t)tile_of(t);
@@ -452,14 +584,40 @@ extern "C" int bg_ppo_gemm_nt(int op, const uint16_t* A, long long tile_begin, l
     if (a.epi == 2 && !h_mask) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: the dpre ops need h");
     a.w_bytes = (op == BG_PPO_OP_HIDDEN ? 26 : 16) * a.w_rows * 16;
     const size_t smem = ((size_t)(a.w_bytes + 1023) & ~(size_t)1023) + (size_t)a.D * (size_t)(a.KC >> 3) * kChunk;
-    cudaError_t e = cudaFuncSetAttribute(ppo_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ppo_gemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return bg_set_error(e, "bg_ppo_gemm_nt: cudaFuncSetAttribute");
     if (smem > 220 * 1024) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_gemm_nt: stage ring does not fit shared memory");
     const long long tiles = tile_end - tile_begin;
     long long grid = (long long)bg_sm_count();
     if (grid > tiles) grid = tiles;
-    ppo_gemm_nt_kernel<<<(unsigned)grid, kNtThreads, smem, (cudaStream_t)stream>>>(a);
+    ppo_gemm_nt_kernel<false><<<(unsigned)grid, kNtThreads, smem, (cudaStream_t)stream>>>(a);
     return bg_set_error(cudaGetLastError(), "bg_ppo_gemm_nt: launch");
+}
+
+// LOGITS_A with the class A loss as its epilogue: dlogits_a = d loss / d logits of rows [0, n_a) (tiles [0, ceil(n_a / 128)); the padding
+// rows of the last tile are written as zeros), dbias / sums accumulated as in bg_ppo_loss_grad_classes; means over B_norm samples.
+extern "C" int bg_ppo_logits_loss_a(const uint16_t* h, long long n_a, long long B_norm, const uint16_t* wap_a, const float* bias_a,
+                                    const int32_t* counts, const int32_t* actions, const float* old_log_probs, const float* advantages,
+                                    const float* returns, float eps_clip, float value_coef, float entropy_coef, uint16_t* dlogits_a,
+                                    float* dbias, float* sums, void* stream) {
+    if (n_a < 0 || B_norm < n_a) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_logits_loss_a: bad sizes");
+    if (n_a == 0) return BG_OK;
+    if (!h || !wap_a || !bias_a || !counts || !actions || !old_log_probs || !advantages || !returns || !dlogits_a || !sums)
+        return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_logits_loss_a: null pointer");
+    NtArgs a{};
+    a.A = h; a.tile_begin = 0; a.tile_end = (n_a + kRows - 1) / kRows; a.W = wap_a; a.bias = bias_a; a.out = dlogits_a; a.dbg = g_ppo_gemm_dbg;
+    a.nc_a = 16; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 3; a.nc_out = 18; a.D = 5;
+    a.counts = counts; a.actions = actions; a.old_logp = old_log_probs; a.adv = advantages; a.returns = returns; a.n_rows = n_a;
+    a.eps_clip = eps_clip; a.value_coef = value_coef; a.entropy_coef = entropy_coef; a.inv_b = 1.0f / (float)B_norm;
+    a.dbias = dbias; a.sums = sums;
+    a.w_bytes = 16 * a.w_rows * 16;
+    const size_t smem = ((size_t)(a.w_bytes + 1023) & ~(size_t)1023) + (size_t)a.D * (size_t)(a.KC >> 3) * kChunk;
+    cudaError_t e = cudaFuncSetAttribute(ppo_gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // + 20 KB static
+    if (e != cudaSuccess) return bg_set_error(e, "bg_ppo_logits_loss_a: cudaFuncSetAttribute");
+    long long grid = (long long)bg_sm_count();
+    if (grid > a.tile_end) grid = a.tile_end;
+    ppo_gemm_nt_kernel<true><<<(unsigned)grid, kNtThreads, smem, (cudaStream_t)stream>>>(a);
+    return bg_set_error(cudaGetLastError(), "bg_ppo_logits_loss_a: launch");
 }
 
 extern "C" int bg_ppo_gemm_tn(int op, const uint16_t* A, const uint16_t* B, long long tile_begin, long long tile_end,

@@ -25,6 +25,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -243,8 +244,9 @@ class TensorCoreUpdate:
 
     ONE_COL = 198
 
-    def __init__(self, device):
+    def __init__(self, device, fuse_loss: bool = True):
         self.device = device
+        self.fuse_loss = bool(fuse_loss)          # class A: loss in the logits GEMM's epilogue (False: separate packed loss kernel)
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
         self.w1p, self.wap_a, self.wap_b = z((26 * 128 * 8,), torch.bfloat16), z((16 * 144 * 8,), torch.bfloat16), z((16 * 512 * 8,), torch.bfloat16)
         self.bias_a, self.bias_b = z((144,), torch.float32), z((512,), torch.float32)
@@ -333,12 +335,20 @@ class TensorCoreUpdate:
             check(L.bg_ppo_pack_weights(flat_params.data_ptr(), self.w1p.data_ptr(), self.wap_a.data_ptr(), self.wap_b.data_ptr(),
                                         self.bias_a.data_ptr(), self.bias_b.data_ptr(), st), "bg_ppo_pack_weights")
             check(L.bg_ppo_gemm_nt(0, xp, 0, TT, self.w1p.data_ptr(), None, None, hp, st), "ppo gemm HIDDEN")
-            check(L.bg_ppo_gemm_nt(1, hp, 0, TA, self.wap_a.data_ptr(), self.bias_a.data_ptr(), None, self.la.data_ptr(), st), "ppo gemm LOGITS_A")
+            fused = self.fuse_loss
+            if fused:      # class A: the loss is the epilogue of the logits GEMM (the logits never reach HBM)
+                check(L.bg_ppo_logits_loss_a(hp, n_a, B, self.wap_a.data_ptr(), self.bias_a.data_ptr(), p["counts"].data_ptr(),
+                                             p["actions"].data_ptr(), p["old_logp"].data_ptr(), p["adv"].data_ptr(), p["returns"].data_ptr(),
+                                             float(eps_clip), float(value_coef), float(entropy_coef), self.dla.data_ptr(),
+                                             self.dbias.data_ptr(), self.sums.data_ptr(), st), "bg_ppo_logits_loss_a")
+            else:
+                check(L.bg_ppo_gemm_nt(1, hp, 0, TA, self.wap_a.data_ptr(), self.bias_a.data_ptr(), None, self.la.data_ptr(), st), "ppo gemm LOGITS_A")
             check(L.bg_ppo_gemm_nt(2, hp, TA, TT, self.wap_b.data_ptr(), self.bias_b.data_ptr(), None, lb_off, st), "ppo gemm LOGITS_B")
             check(L.bg_ppo_loss_grad_classes(self.la.data_ptr(), self.dla.data_ptr(), self.lb.data_ptr(), self.dlb.data_ptr(), n_a, n_b,
                                              TA * 128, p["counts"].data_ptr(), p["actions"].data_ptr(), p["old_logp"].data_ptr(),
                                              p["adv"].data_ptr(), p["returns"].data_ptr(), float(eps_clip), float(value_coef),
-                                             float(entropy_coef), self.dbias.data_ptr(), self.sums.data_ptr(), st), "bg_ppo_loss_grad_classes")
+                                             float(entropy_coef), self.dbias.data_ptr(), self.sums.data_ptr(), int(fused), st),
+                  "bg_ppo_loss_grad_classes")
             check(L.bg_ppo_gemm_nt(3, self.dla.data_ptr(), 0, TA, self.wap_a.data_ptr(), None, hp, dp, st), "ppo gemm DPRE_A")
             check(L.bg_ppo_gemm_nt(4, dlb_off, TA, TT, self.wap_b.data_ptr(), None, hp, dp, st), "ppo gemm DPRE_B")
             check(L.bg_ppo_gemm_tn(5, hp, self.dla.data_ptr(), 0, TA, gflat.data_ptr(), None, st), "ppo gemm GRAD_WA_A")
@@ -458,7 +468,8 @@ class PPOLearner:
         tc = manual and c.update_impl == "tcgen05" and mb == 1
         if manual:
             if self._manual is None or isinstance(self._manual, TensorCoreUpdate) != tc:
-                self._manual = TensorCoreUpdate(self.device) if tc else ManualUpdate(self.device)
+                self._manual = (TensorCoreUpdate(self.device, fuse_loss=os.environ.get("BG_PPO_FUSE_LOSS", "1") != "0") if tc
+                                else ManualUpdate(self.device))
             x[:, ManualUpdate.ONE_COL] = 1.0                  # spare (zero) column of K3's rows: carries fc1.bias through the GEMMs
             counts, actions = counts.to(torch.int32).contiguous(), actions.to(torch.int32).contiguous()
             old_logp, returns, adv = old_logp.float().contiguous(), returns.float().contiguous(), adv.float().contiguous()

@@ -151,7 +151,7 @@ def test_adam_kernel_matches_torch():
         assert (p - p_ref.detach()).abs().max().item() < 2e-6
 
 
-@pytest.mark.parametrize("impl", ["tcgen05", "cublas"])
+@pytest.mark.parametrize("impl", ["tcgen05", "tcgen05-unfused-loss", "cublas"])
 def test_epoch_matches_autograd(impl):
     """losses and every gradient of one epoch == torch autograd over the torch restatement of ppo_agent.py:268-305 under
     bf16 autocast, on the reference's own rollout (golden) plus synthetic passes / wide rows so that class B is exercised"""
@@ -177,7 +177,8 @@ def test_epoch_matches_autograd(impl):
     want = {k: v.grad.clone() for k, v in p.items()}
     grads = {k: torch.zeros_like(v) for k, v in sd0.items()}
     xm = x.clone(); xm[:, 198] = 1.0
-    upd = (TensorCoreUpdate if impl == "tcgen05" else ManualUpdate)(torch.device(DEV))
+    upd = (ManualUpdate(torch.device(DEV)) if impl == "cublas" else
+           TensorCoreUpdate(torch.device(DEV), fuse_loss=(impl == "tcgen05")))
     st = upd.epoch(sd0, grads, xm, counts, actions, logp2, adv, retn.contiguous(), 0.25, 0.5, 0.15)
     got = st.cpu().numpy()
     assert np.abs(got - np.array([pl.item(), vl.item(), ent.item(), loss.item()])).max() < 3e-3, got
