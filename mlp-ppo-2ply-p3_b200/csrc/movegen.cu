@@ -33,7 +33,7 @@ namespace bg {
 // FEATS: also write the bf16 feature row of every afterstate (optional fused K3; a separate instantiation so that
 // the common one stays inside the instruction cache)
 template <int CAP, int HS, bool FEATS>
-__global__ void __launch_bounds__(256) movegen_kernel(
+__global__ void __launch_bounds__(256, 4) movegen_kernel(
     const int8_t* __restrict__ boards, const int8_t* __restrict__ players, const int8_t* __restrict__ dice,
     long long B, const unsigned int* __restrict__ nwork_dev, const int32_t* __restrict__ worklist,
     int replicate, int flip_player, int mode, const long long* __restrict__ offsets, int max_rows,
@@ -49,18 +49,32 @@ __global__ void __launch_bounds__(256) movegen_kernel(
     if (FEATS) { load_chunk_tables(s_lut, s_desc); __syncthreads(); }
     const long long nwork = nwork_dev ? (long long)*nwork_dev : B;
 
+    // (Reading the work counter / the item's global loads one or two items AHEAD was tried and lost 15 us: with ~14 items per
+    // warp and item costs from 3 to 80 us, items parked in a busy warp's pipeline cost more at the tail than the hidden latency
+    // gains -- scripts/exp_k1_variants.py, profiles/r2_summary.md.)
+    // (Also tried, and not kept: walking the items twice, doubles -- 4 levels, up to ~80 us for a lone warp -- first and the other
+    // rolls after them.  With the games physically sorted doubles-first K1 takes 14 us less, but the in-kernel version (groups of 8
+    // dice loads, doubles skipped in the second walk) pays that back in extra fetches: 181 us against 178.)
+    struct Item { unsigned int wi; uint32_t bword; int pl, d0, d1; };
     for (;;) {
-        unsigned int wi = 0;
-        if (lane == 0) wi = atomicAdd(work_ctr, 1u);
-        wi = __shfl_sync(kFull, wi, 0);
-        if ((long long)wi >= nwork) break;
-        const long long g = worklist ? (long long)worklist[wi] : (long long)wi;
+        unsigned int wi0 = 0;
+        if (lane == 0) wi0 = atomicAdd(work_ctr, 1u);
+        wi0 = __shfl_sync(kFull, wi0, 0);
+        if ((long long)wi0 >= nwork) break;
+        Item cur; cur.wi = wi0;
+        {
+            const long long g0 = worklist ? (long long)worklist[wi0] : (long long)wi0;
+            const long long src = replicate > 1 ? g0 / replicate : g0;
+            cur.bword = load_board_word(boards, src, lane);
+            cur.pl = players[src];
+            if (replicate > 1) { const int r = (int)(g0 - src * replicate); cur.d0 = kRoll21[r][0]; cur.d1 = kRoll21[r][1]; }
+            else { cur.d0 = dice[2 * g0]; cur.d1 = dice[2 * g0 + 1]; }
+        }
+        const long long g = worklist ? (long long)worklist[cur.wi] : (long long)cur.wi;
 
         // ---- the work item, its root (13 words, coalesced) and the mover-relative view (bg_movegen_common.cuh)
-        const long long src = replicate > 1 ? g / replicate : g;
-        const uint32_t bword = load_board_word(boards, src, lane);
-        const WorkItem item = decode_work_item(g, src, replicate, flip_player, players, dice);
-        const int player = item.player, d0 = item.d0, d1 = item.d1;
+        const uint32_t bword = cur.bword;
+        const int player = (cur.pl ^ flip_player) & 1, d0 = cur.d0, d1 = cur.d1;
         Warp<CAP, HS> W(S, lane);
         Node root;
         const bool bad = !build_root(bword, player, lane, S.rootw, W.R, root) ||
@@ -93,25 +107,21 @@ __global__ void __launch_bounds__(256) movegen_kernel(
             continue;
         }
         const int nw = (max_rows > 0 && n > max_rows) ? max_rows : n;     // rows written (env truncation)
+        // slab mode: the allocation (an atomic on one address, ~1 us) is issued here and read only after the first rows have
+        // been staged
         long long start = 0;
+        unsigned long long s0 = 0;
         if (mode == 1) start = offsets[g];
-        else if (mode == 2) {
-            unsigned long long s0 = 0;
-            if (lane == 0) s0 = atomicAdd(alloc, (unsigned long long)nw);
-            start = (long long)__shfl_sync(kFull, s0, 0);
-        }
+        else if (mode == 2 && lane == 0) s0 = atomicAdd(alloc, (unsigned long long)nw);
         if (lane == 0) {
             if (counts_true) counts_true[g] = n;
             if (counts) counts[g] = nw;
-            if (mode == 2 && starts) starts[g] = start;
         }
+        if (mode == 2 && nw == 0 && lane == 0 && starts) starts[g] = (long long)s0;
         if (mode != 0 && nw > 0) {
-            if (start + nw > after_cap_rows) {
-                if (lane == 0) { atomicOr(status, BG_STATUS_OUTPUT_OVERFLOW); if (counts) counts[g] = 0; }
-            } else {
-                // stage 32 rows x 13 words in the region that does not hold the result, then copy out coalesced
+            {
                 uint32_t* stage = reinterpret_cast<uint32_t*>(&S.key[obase < CAP ? CAP : 0]);
-                uint32_t* gout = reinterpret_cast<uint32_t*>(after) + start * kBoardWords;
+                uint32_t* gout = nullptr;
                 const RowContext rc = make_row_context(player, S.rootw);
                 for (int r0 = 0; r0 < nw; r0 += 32) {
                     int r = r0 + lane;
@@ -119,8 +129,25 @@ __global__ void __launch_bounds__(256) movegen_kernel(
                         build_row(S.key[obase + r], player, rc, S.rootw, stage + lane * kBoardWords);
                     }
                     __syncwarp();
+                    if (r0 == 0) {
+                        if (mode == 2) {
+                            start = (long long)__shfl_sync(kFull, s0, 0);
+                            if (lane == 0 && starts) starts[g] = start;
+                        }
+                        if (start + nw > after_cap_rows) {
+                            if (lane == 0) { atomicOr(status, BG_STATUS_OUTPUT_OVERFLOW); if (counts) counts[g] = 0; }
+                            break;
+                        }
+                        gout = reinterpret_cast<uint32_t*>(after) + start * kBoardWords;
+                    }
                     int rows = min(32, nw - r0);
-                    for (int k2 = lane; k2 < rows * kBoardWords; k2 += 32) gout[(long long)r0 * kBoardWords + k2] = stage[k2];
+                    {   // copy out: 13 predicated word copies at immediate offsets (no per-iteration address arithmetic)
+                        const int total = rows * kBoardWords;
+                        uint32_t* gp = gout + (long long)r0 * kBoardWords + lane;
+                        const uint32_t* sp = stage + lane;
+#pragma unroll
+                        for (int i = 0; i < kBoardWords; ++i) if (lane + 32 * i < total) gp[32 * i] = sp[32 * i];
+                    }
                     if (row_players && lane < rows) row_players[start + r0 + lane] = (int8_t)player;
                     if (FEATS && row_feats) {
                         // fused K3: the 208-wide bf16 feature rows of these afterstates (mover's turn flag,
@@ -204,6 +231,9 @@ int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* d
     cudaError_t e = cudaMemsetAsync(ws, 0, BG_WS_LISTS, stream);
     if (e != cudaSuccess) return bg_set_error(e, "movegen: memset");
     // Tier 0: every position, BG_MOVEGEN_CAP_SMALL boards per level, 8 warps per CTA.
+    // (Splitting tier 0 into 2..8 launches over ranges of games, so that K3 could encode part p's rows beside part p + 1, was tried:
+    // every extra part cost ~26 us -- each launch ends with its own tail of lone warps finishing big doubles -- and the step got
+    // slower, 265 -> 298 us with two parts; scripts/exp_tier0_pipeline.py in the history, profiles/r2_summary.md.)
     int rc = launch_movegen<BG_MOVEGEN_CAP_SMALL, 2 * BG_MOVEGEN_CAP_SMALL, 8>(
         boards, players, dice, B, nullptr, nullptr, replicate, flip_player, mode, offsets, max_rows, after,
         after_cap_rows, row_players, row_feats, counts_true, counts, starts, alloc, status, ctr + 0, list_a, ctr + 1,

@@ -95,3 +95,34 @@ extern "C" int emul_legal_moves(const int8_t* b52, int player, int d0, int d1, i
     }
     return n;
 }
+
+// Level sizes of a doubles position (distinct boards per level 1..4 and candidates built per level): sizing data for the
+// kernel's per-warp scratch (scripts/level_stats.py).
+extern "C" void emul_doubles_levels(const int8_t* b52, int player, int d, int* sizes4, int* cands4) {
+    const int8_t* own = b52 + (player ? 24 : 0);
+    const int8_t* opp = b52 + (player ? 0 : 24);
+    Root R; R.player = player; R.block = 0; R.blot = 0; R.mA = 0; R.cnt2 = 0;
+    Node root; root.lo = 0; root.hi = 0; root.occ = 0; root.hit = 0; root.last = 31u;
+    int total = 0;
+    for (int p = 0; p < 24; ++p) {
+        if (own[p] >= 2) R.cnt2 |= 1u << p;
+        if (opp[p] >= 2) R.block |= 1u << p;
+        if (opp[p] == 1) R.blot |= 1u << p;
+        if (own[p] > 0) root.occ |= 1u << p;
+        if (p < 16) root.lo |= (unsigned long long)(own[p] & 15) << (4 * p);
+        else root.hi |= (unsigned long long)(own[p] & 15) << (4 * (p - 16));
+        total += own[p];
+    }
+    int ownbar = b52[48 + player], ownoff = b52[50 + player];
+    root.hi |= (unsigned long long)((ownbar & 15) | ((ownoff & 15) << 4)) << 32;
+    R.tot15 = (total + ownbar + ownoff) == 15;
+    std::vector<Node> cur{root};
+    for (int k = 0; k < 4; ++k) { sizes4[k] = 0; cands4[k] = 0; }
+    for (int depth = 0; depth < 4; ++depth) {
+        std::vector<Node> nxt;
+        int t = expand(cur, R, d, nxt, true);
+        if (t == 0) break;
+        sizes4[depth] = (int)nxt.size(); cands4[depth] = t;
+        cur = nxt;
+    }
+}
