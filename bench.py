@@ -572,8 +572,22 @@ def run_extras(bg_b200, env, torch, dev, args, dist, rank, world):
             torch.empty(N, dtype=torch.float32, device=dev))
     step_ctr = [0]
     t = timed(lambda: pnet.act(env.boards52, env.players, env.legal_counts, seed=1, step=0, out=pout), 20)
-    out["policy_sample"] = {"positions_per_s": total(N) / t, "ms": t * 1e3,
-                            "what": "fused policy/value kernel: encode + 198->128 + 128->500 on tcgen05, prefix mask, softmax, Gumbel-max sample"}
+    # the same call as a CUDA graph (memset + partition + fused kernel), replayed: the device time without the host's launch path
+    # (at 65,536 positions the Python call above is launch-bound: ~45 us of host work per call)
+    gstream = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(gstream):
+        pnet.act(env.boards52, env.players, env.legal_counts, seed=1, step=0, out=pout)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=gstream):
+            pnet.act(env.boards52, env.players, env.legal_counts, seed=1, step=0, out=pout)
+    torch.cuda.synchronize()
+    t_dev = timed(graph.replay, 50)
+    out["policy_sample"] = {"positions_per_s": total(N) / t, "ms": t * 1e3, "device_ms": t_dev * 1e3,
+                            "device_positions_per_s": total(N) / t_dev,
+                            "what": "fused policy/value kernel: encode + 198->128 + 128->500 on tcgen05, prefix mask, softmax, categorical sample; "
+                                    "ms = through PolicyValueNet.act (host launch path included), device_ms = the same call replayed as a CUDA graph"}
 
     def ppo_rollout_step():
         step_ctr[0] += 1
@@ -624,6 +638,8 @@ def run_ppo_loop(bg_b200, env, pnet, torch, dev, args, dist, world):
     return {"env_steps_per_s": world * N * T * U / ((roll_ms + upd_ms) * 1e-3), "updates": U, "horizon": T, "games_per_gpu": N,
             "samples_per_update_per_gpu": N * T, "epochs": cfg.num_epochs,
             "rollout_ms_per_update": roll_ms / U, "update_ms_per_update": upd_ms / U,
+            "update_ms_all_this_rank": [round(m[1].elapsed_time(m[2]), 3) for m in marks],
+            "reserved_gib": round(torch.cuda.memory_reserved() / 2**30, 2),
             "allreduce_ms_per_call": ar_ms, "allreduce_calls_per_update": cfg.num_epochs * cfg.num_minibatches,
             "allreduce_bytes": tr.learner.fp.numel * 4, "last_stats": {k: v for k, v in stats.items() if isinstance(v, float)},
             "what": "configs[4]: rollout + GAE + update, one 90,101-float NCCL all-reduce per optimiser step (the only collective); "

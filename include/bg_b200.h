@@ -213,7 +213,8 @@ int bg_mlp_value(const int8_t* boards52, const int8_t* flags, int flag_all, int 
  *   wa_bf16: 512 x 128 bf16 as written by bg_pack_wa (opaque: action_head.weight, rows 500..511 zero, in the tcgen05
  *   operand layout), ba: [500] f32;
  *   w1_bf16 / b1 as in bg_mlp_value (b1 == NULL: bias folded into w1_bf16).
- *   sampling: Gumbel-max with Philox4x32-10 keyed by seed, counter (stream_base + b, step, slot): reproducible
+ *   sampling: exact categorical sampling (inverse CDF inside blocks of slots, blocks merged reservoir-style) with uniforms from
+ *   Philox4x32-10 keyed by seed, counter (stream_base + b, step, block): reproducible
  *   and independent of the batch split; greedy = 1 takes argmax (lowest slot on ties) like the inference mode.
  *   outputs: actions [B] i32, log_probs [B] f32 (nullable), values [B] f32 (nullable),
  *            logits_out [B][500] f32 (nullable; unmasked logits, for parity checks).

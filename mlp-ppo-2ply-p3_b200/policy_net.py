@@ -95,7 +95,10 @@ class PolicyValueNet(ValueNet):
         actions, logp, values = out
         logits = torch.empty((B, ACTIONS), dtype=torch.float32, device=dev) if want_logits else None
         ws = getattr(self, "_ws", None)                           # row-class lists (persistent scratch)
-        need = int(lib().bg_policy_workspace_bytes(max(B, 1)))    # the C ABI's own requirement (two int32 row lists)
+        need_of = self.__dict__.setdefault("_ws_need", {})        # the C ABI's own requirement (row lists + class B partials), per batch size
+        need = need_of.get(B)
+        if need is None:
+            need = need_of[B] = int(lib().bg_policy_workspace_bytes(max(B, 1)))
         if ws is None or ws.numel() < need or ws.device != dev:
             ws = self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):

@@ -290,7 +290,9 @@ class TensorCoreUpdate:
         p = dict(B=B, n_a=n_a, n_b=n_b, TA=TA, TB=TB, rows=rows, perm=perm, counts=g(counts, torch.int32), actions=g(actions, torch.int32),
                  old_logp=g(old_logp, torch.float32), adv=g(adv, torch.float32), returns=g(returns, torch.float32))
         if self._cap[0] < TA + TB or self._cap[1] < TB:
-            ct, cb = max(TA + TB, self._cap[0]), max(TB, self._cap[1], (TA + TB) // 8 + 1)
+            # sized for ANY split of B samples into the two classes (TA + TB <= ceil(B / 128) + 1), so that the next rollout of the
+            # same size never reallocates (a reallocation of these buffers is a 20 ms hiccup at 4 M samples)
+            ct, cb = max(-(-B // 128) + 1, self._cap[0]), max(TB + TB // 4 + 1, self._cap[1], (TA + TB) // 8 + 1)
             e = lambda n: torch.zeros(n, dtype=torch.bfloat16, device=dev)
             self.xb, self.h, self.dpre = e(ct * 128 * 208), e(ct * 128 * 128), e(ct * 128 * 128)
             self.la, self.dla = e(ct * 128 * 144), e(ct * 128 * 144)
