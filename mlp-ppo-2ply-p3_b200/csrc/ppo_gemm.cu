@@ -192,9 +192,11 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
             // ppo_agent.py:271-299 and its gradient, as in ppo_loss_grad_packed_kernel (csrc/ppo.cu): warp `part` holds slots
             // 32 part .. 32 part + 31 of its rows (part 0 also the value head, column 128); the four parts of a row exchange
             // (max, sum exp, sum exp z, z[action]) through shared memory; d loss / d logits goes out as bf16, the logits do not.
-            float colsum[32];
+            // column sums of d loss / d logits (= the head biases' gradients): one private shared-memory slot per (thread, column)
+            // behind the stage ring -- 32 more live registers would spill in this epilogue
+            float* colsum = reinterpret_cast<float*>(A0 + (size_t)a.D * stage_bytes) + (tid & (kNtEpiWarps * 32 - 1));
 #pragma unroll
-            for (int j = 0; j < 32; ++j) colsum[j] = 0.0f;
+            for (int j = 0; j < 32; ++j) colsum[j * (kNtEpiWarps * 32)] = 0.0f;
             float pl = 0.0f, vl = 0.0f, ent = 0.0f, vsum = 0.0f;
             const float ce = a.entropy_coef * a.inv_b;
             for (long long t = 0; t < my_tiles; ++t) {
@@ -206,34 +208,55 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
                 if (live) { n = __ldg(a.counts + gr); act = __ldg(a.actions + gr); A = __ldg(a.adv + gr); olp = __ldg(a.old_logp + gr); ret = __ldg(a.returns + gr); }
                 warp_wait(&acc_full[acc], (uint32_t)(t / nacc) & 1u, lane);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                uint32_t av[32];
+                // the rows arrive sorted by their number of legal slots (TensorCoreUpdate.prepare), so for most groups of 32 rows the
+                // slots 32 .. 127 are illegal for every row: those warps skip their block (zeros go out as its d loss / d logits).
+                // The block is streamed from tensor memory twice, eight columns at a time (pass 1: online max / sums, pass 2: the
+                // gradient): holding its 32 logits in registers across the exchange spilled.
+                const bool blk = __any_sync(kFull, n > 32 * part);
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-                tmem_ld32(taddr + 32 * part, av);
-                uint32_t vv[8];
-                if (part == 0) tmem_ld8(taddr + 128, vv);
-                tmem_ld_wait();
-                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                mbar_arrive(&acc_empty[acc]);                          // the accumulator may be overwritten: everything is in registers
-                float z[32];
-                float m = -INFINITY;
+                auto logits8 = [&](int sb, float (&z)[8]) {            // slots 32 part + 8 sb .. + 7 of this thread's row: bf16(acc + bias), -inf if illegal
+                    uint32_t av[8];
+                    tmem_ld8(taddr + 32 * part + 8 * sb, av);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float l = __bfloat162float(__float2bfloat16_rn(__uint_as_float(av[j]) + s_bias[32 * part + j]));
-                    z[j] = (32 * part + j < n) ? l : -INFINITY;
-                    m = fmaxf(m, z[j]);
-                }
-                float ssum = 0.0f, tsum = 0.0f, za = 0.0f;
-                if (m > -INFINITY) {
+                    for (int j = 0; j < 8; ++j) {
+                        const int c = 32 * part + 8 * sb + j;
+                        const float l = __bfloat162float(__float2bfloat16_rn(__uint_as_float(av[j]) + s_bias[c]));
+                        z[j] = c < n ? l : -INFINITY;
+                    }
+                };
+                float m = -INFINITY, ssum = 0.0f, tsum = 0.0f, za = 0.0f;
+                if (blk) {
+#pragma unroll 1
+                    for (int sb = 0; sb < 4; ++sb) {
+                        if (!__any_sync(kFull, n > 32 * part + 8 * sb)) break;
+                        float z[8];
+                        logits8(sb, z);
+                        float cm = z[0];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float e = __expf(z[j] - m);              // 0 for masked slots
-                        ssum += e;
-                        if (z[j] > -INFINITY) tsum = fmaf(e, z[j], tsum);
-                        if (32 * part + j == act) za = z[j];
+                        for (int j = 1; j < 8; ++j) cm = fmaxf(cm, z[j]);
+                        if (cm > -INFINITY) {
+                            const float mn = fmaxf(m, cm);
+                            const float sc = __expf(m - mn);           // 0 on the first block (m = -inf)
+                            ssum *= sc; tsum *= sc;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float e = __expf(z[j] - mn);     // 0 for masked slots
+                                ssum += e;
+                                if (z[j] > -INFINITY) tsum = fmaf(e, z[j], tsum);
+                                if (32 * part + 8 * sb + j == act) za = z[j];
+                            }
+                            m = mn;
+                        }
                     }
                 }
                 s_red[par][part][r] = make_float4(m, ssum, tsum, za);
-                if (part == 0) s_vrow[par][r] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(vv[0]) + s_bias[128]));
+                if (part == 0) {
+                    uint32_t vv[8];
+                    tmem_ld8(taddr + 128, vv);
+                    tmem_ld_wait();
+                    s_vrow[par][r] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(vv[0]) + s_bias[128]));
+                }
                 asm volatile("bar.sync 1, %0;\n" :: "n"(kNtEpiWarps * 32) : "memory");
                 float M = -INFINITY;
 #pragma unroll
@@ -257,30 +280,36 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
                 const float dv = v - ret;
                 const float dvalue = 2.0f * a.value_coef * dv * a.inv_b;
                 unsigned char* otile = reinterpret_cast<unsigned char*>(a.out) + tile * a.nc_out * kChunk + r * 16;
+#pragma unroll 1
+                for (int sb = 0; sb < 4; ++sb) {
+                    uint32_t o[4] = {0u, 0u, 0u, 0u};
+                    if (blk && __any_sync(kFull, n > 32 * part + 8 * sb)) {
+                        float z[8];
+                        logits8(sb, z);
 #pragma unroll
-                for (int jc = 0; jc < 4; ++jc) {
-                    uint32_t o[4];
+                        for (int e2 = 0; e2 < 4; ++e2) {
+                            float d2[2];
 #pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2) {
-                        float d2[2];
-#pragma unroll
-                        for (int h2 = 0; h2 < 2; ++h2) {
-                            const int j = 8 * jc + 2 * e2 + h2;
-                            float d = 0.0f;
-                            if (live && z[j] > -INFINITY) {
-                                const float lp = z[j] - lse;
-                                const float pk = __expf(lp);
-                                d = -g * pk + (pk > 0.0f ? ce * pk * (lp + H) : 0.0f);
-                                if (32 * part + j == act) d += g;
+                            for (int h2 = 0; h2 < 2; ++h2) {
+                                const int j = 2 * e2 + h2;
+                                float d = 0.0f;
+                                if (live && z[j] > -INFINITY) {
+                                    const float lp = z[j] - lse;
+                                    const float pk = __expf(lp);
+                                    d = -g * pk + (pk > 0.0f ? ce * pk * (lp + H) : 0.0f);
+                                    if (32 * part + 8 * sb + j == act) d += g;
+                                }
+                                colsum[(8 * sb + j) * (kNtEpiWarps * 32)] += d;
+                                d2[h2] = d;
                             }
-                            colsum[j] += d;
-                            d2[h2] = d;
+                            const __nv_bfloat162 pr = __floats2bfloat162_rn(d2[0], d2[1]);
+                            o[e2] = *reinterpret_cast<const uint32_t*>(&pr);
                         }
-                        const __nv_bfloat162 pr = __floats2bfloat162_rn(d2[0], d2[1]);
-                        o[e2] = *reinterpret_cast<const uint32_t*>(&pr);
                     }
-                    if (!(a.dbg & 2)) *reinterpret_cast<uint4*>(otile + (size_t)(4 * part + jc) * kChunk) = make_uint4(o[0], o[1], o[2], o[3]);
+                    if (!(a.dbg & 2)) *reinterpret_cast<uint4*>(otile + (size_t)(4 * part + sb) * kChunk) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                mbar_arrive(&acc_empty[acc]);                          // the accumulator has been read for the last time
                 if (part == 0) {                                       // the value head's column (128) and the zero padding (129 .. 143)
                     const float dvw = live ? dvalue : 0.0f;
                     const __nv_bfloat162 pr = __floats2bfloat162_rn(dvw, 0.0f);
@@ -294,7 +323,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
             // column sums (= the head biases' gradients) and the loss sums: over the rows of the warp, then one atomic per column and warp
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                float c = colsum[j];
+                float c = colsum[j * (kNtEpiWarps * 32)];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
                 if (lane == (j & 31) && a.dbias) atomicAdd(a.dbias + 32 * part + j, c);
@@ -606,12 +635,12 @@ extern "C" int bg_ppo_logits_loss_a(const uint16_t* h, long long n_a, long long 
         return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_logits_loss_a: null pointer");
     NtArgs a{};
     a.A = h; a.tile_begin = 0; a.tile_end = (n_a + kRows - 1) / kRows; a.W = wap_a; a.bias = bias_a; a.out = dlogits_a; a.dbg = g_ppo_gemm_dbg;
-    a.nc_a = 16; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 3; a.nc_out = 18; a.D = 5;
+    a.nc_a = 16; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 3; a.nc_out = 18; a.D = 3;   // (the epilogue bounds this kernel: three stages are enough, and the column sums need the room)
     a.counts = counts; a.actions = actions; a.old_logp = old_log_probs; a.adv = advantages; a.returns = returns; a.n_rows = n_a;
     a.eps_clip = eps_clip; a.value_coef = value_coef; a.entropy_coef = entropy_coef; a.inv_b = 1.0f / (float)B_norm;
     a.dbias = dbias; a.sums = sums;
     a.w_bytes = 16 * a.w_rows * 16;
-    const size_t smem = ((size_t)(a.w_bytes + 1023) & ~(size_t)1023) + (size_t)a.D * (size_t)(a.KC >> 3) * kChunk;
+    const size_t smem = ((size_t)(a.w_bytes + 1023) & ~(size_t)1023) + (size_t)a.D * (size_t)(a.KC >> 3) * kChunk + 32 * kNtEpiWarps * 32 * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(ppo_gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // + 20 KB static
     if (e != cudaSuccess) return bg_set_error(e, "bg_ppo_logits_loss_a: cudaFuncSetAttribute");
     long long grid = (long long)bg_sm_count();

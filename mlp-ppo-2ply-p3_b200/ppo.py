@@ -272,12 +272,15 @@ class TensorCoreUpdate:
         return b.view(R // 128, C // 8, 128, 8).permute(0, 2, 1, 3).reshape(R, C)
 
     def prepare(self, x, counts, actions, old_logp, adv, returns):
-        """Once per rollout: sort the samples by class (class A first, original order inside a class), pad each class to whole
+        """Once per rollout: sort the samples by class (class A first, by legal count; original order inside class B), pad each class to whole
         tiles, gather the per-sample vectors and build the blocked x (with the bias column).  One host read (the class sizes)."""
         B = x.shape[0]
         dev = self.device
         a = self.class_a(counts, actions)
-        order = torch.argsort((~a).to(torch.int8), stable=True).to(torch.int32)
+        # class A first, and inside class A by the number of legal slots: most tiles then hold only rows with <= 32 slots, and the
+        # fused logits / loss kernel skips the blocks of slots that are illegal for all 32 rows of a warp
+        key = torch.where(a, counts.to(torch.int32), torch.full_like(counts, 1 << 20, dtype=torch.int32))
+        order = torch.argsort(key, stable=True).to(torch.int32)
         n_a = int(a.sum().item())
         n_b = B - n_a
         TA, TB = -(-n_a // 128), -(-n_b // 128)
