@@ -13,7 +13,7 @@
 #define BG_MOVEGEN_HASH_BIG 4096
 
 // K1 workspace layout (bytes; bg_movegen_workspace_bytes): [0] work_ctr0, [4] overflow_ctr A, [8] work_ctr1, [12] overflow_ctr B,
-// [16] work_ctr2, [40] rows_after_tier0 (u64 snapshot of the slab allocator for the tier-0 fork, refresh.cu), [48] u64 left to the
+// [16] work_ctr2, [24] list B's length after tier 0, [28] work counter of tier 2's second pass, [40] rows_after_tier0 (u64 snapshot of the slab allocator for the tier-0 fork, refresh.cu), [48] u64 left to the
 // caller (the env's slab row allocator: zeroed by the same memset as the counters), [64 ..] overflow
 // list A int32[B], then overflow list B int32[B]
 #define BG_WS_ROWS_AFTER_TIER0 40
@@ -55,8 +55,9 @@ int movegen_team_mid(const int8_t* boards, const int8_t* players, const int8_t* 
                      int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
                      unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr, cudaStream_t stream,
                      int team_threads_hint = 0);
+// entries [*first_dev (0 if null), *nwork_dev) of the list
 int movegen_team_big(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
-                     const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
+                     const unsigned int* first_dev, const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
                      int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, uint16_t* row_feats, int32_t* counts_true,
                      int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
                      unsigned int* work_ctr, cudaStream_t stream);

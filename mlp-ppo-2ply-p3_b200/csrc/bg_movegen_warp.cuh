@@ -30,8 +30,9 @@ struct Warp {
     Root R;
     int lane;
     bool overflow;
+    int ovf_stage;              // the stage (0-based: level stage -> stage + 1) whose children did not fit, when overflow is set
 
-    __device__ Warp(WarpScratch<CAP, HS>& s, int l) : S(s), lane(l), overflow(false) {}
+    __device__ Warp(WarpScratch<CAP, HS>& s, int l) : S(s), lane(l), overflow(false), ovf_stage(3) {}
 
     __device__ __forceinline__ Node load(int i) const {
         uint4 k = S.key[i];
@@ -225,7 +226,7 @@ struct Warp {
             }
             int nc = nc0;
             if (do_expand) nc = expand(pbase, np, split, dA, dB, cfrom, cto, cbase, nc0, true, use_hash);   // the only call site
-            if (overflow) return;
+            if (overflow) { ovf_stage = dbl ? stage : 3; return; }
             if (dbl) { pbase = cbase; np = nc; obase = cbase; n = nc; }
             else {
                 // filter_full_moves_by_max_submoves (get_all_moves.py:73-94), applied AFTER dedupe

@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(256, 4) movegen_kernel(
     int8_t* __restrict__ after, long long after_cap_rows, int8_t* __restrict__ row_players,
     uint16_t* __restrict__ row_feats, int32_t* __restrict__ counts_true, int32_t* __restrict__ counts, long long* __restrict__ starts,
     unsigned long long* __restrict__ alloc, int32_t* __restrict__ status,
-    unsigned int* __restrict__ work_ctr, int32_t* __restrict__ overflow_list, unsigned int* __restrict__ overflow_ctr) {
+    unsigned int* __restrict__ work_ctr, int32_t* __restrict__ overflow_list, unsigned int* __restrict__ overflow_ctr,
+    int32_t* __restrict__ overflow_list_big, unsigned int* __restrict__ overflow_ctr_big) {
     static_assert(CAP * 16 >= 32 * kBoardWords * 4, "a region must be able to stage 32 output rows");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,7 +97,11 @@ __global__ void __launch_bounds__(256, 4) movegen_kernel(
         if (W.overflow) {
             // too many boards for this launch's per-warp scratch: hand the position to the large-scratch pass
             if (lane == 0) {
-                if (overflow_list) { unsigned int k = atomicAdd(overflow_ctr, 1u); overflow_list[k] = (int32_t)g; }
+                // a doubles position whose THIRD level (or an earlier one) already exceeds the scratch is headed for a last level of
+                // several hundred boards: straight to the big-scratch tier, which then runs beside tier 1 instead of after it
+                // (scripts/level_stats.py: 0.06 % of the positions, and every position that overflows tier 1 is among them)
+                if (overflow_list_big && W.ovf_stage <= 2) { unsigned int k = atomicAdd(overflow_ctr_big, 1u); overflow_list_big[k] = (int32_t)g; }
+                else if (overflow_list) { unsigned int k = atomicAdd(overflow_ctr, 1u); overflow_list[k] = (int32_t)g; }
                 else {
                     atomicOr(status, BG_STATUS_SCRATCH_OVERFLOW);
                     if (counts_true) counts_true[g] = -1;
@@ -182,7 +187,7 @@ static int launch_movegen(const int8_t* boards, const int8_t* players, const int
                           const long long* offsets, int max_rows, int8_t* after, long long after_cap_rows,
                           int8_t* row_players, uint16_t* row_feats, int32_t* counts_true, int32_t* counts, long long* starts, unsigned long long* alloc,
                           int32_t* status, unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr,
-                          long long grid_hint, cudaStream_t stream) {
+                          int32_t* overflow_list_big, unsigned int* overflow_ctr_big, long long grid_hint, cudaStream_t stream) {
     size_t smem = sizeof(WarpScratch<CAP, HS>) * WARPS;
     auto kern = row_feats ? movegen_kernel<CAP, HS, true> : movegen_kernel<CAP, HS, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -195,7 +200,7 @@ static int launch_movegen(const int8_t* boards, const int8_t* players, const int
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(boards, players, dice, B, nwork_dev, worklist, replicate, flip_player, mode, offsets,
                                                        max_rows, after, after_cap_rows, row_players, row_feats,
-                                                       counts_true, counts, starts, alloc, status, work_ctr, overflow_list, overflow_ctr);
+                                                       counts_true, counts, starts, alloc, status, work_ctr, overflow_list, overflow_ctr, overflow_list_big, overflow_ctr_big);
     return bg_set_error(cudaGetLastError(), "movegen: launch");
 }
 
@@ -204,9 +209,29 @@ static int launch_movegen(const int8_t* boards, const int8_t* players, const int
 using namespace bg;
 
 // Workspace layout (bytes; constants in bg_internal.h): [0] work_ctr0, [4] overflow_ctr A, [8] work_ctr1, [12] overflow_ctr B,
-// [16] work_ctr2, [BG_WS_ROWS_AFTER_TIER0 = 40] u64 row-count snapshot after tier 0 (written by callers that fork there),
+// [16] work_ctr2, [24] list B's length after tier 0 (first entry of tier 2's second pass), [28] work counter of that pass,
+// [BG_WS_ROWS_AFTER_TIER0 = 40] u64 row-count snapshot after tier 0 (written by callers that fork there),
 // [BG_WS_LISTS = 64 ..] overflow list A int32[B], then overflow list B int32[B]
 extern "C" size_t bg_movegen_workspace_bytes(long long B) { return BG_WS_LISTS + 2 * sizeof(int32_t) * (size_t)(B > 0 ? B : 1); }
+
+namespace {
+// tier 2's own stream (forked from and joined to the caller's stream inside movegen_run), one per device and host thread
+struct TierStreams { cudaStream_t stream = nullptr; cudaEvent_t tier0 = nullptr, tier2 = nullptr; int device = -1; };
+thread_local TierStreams g_tier_streams[16];
+TierStreams* tier_streams() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    TierStreams& t = g_tier_streams[dev];
+    if (t.device != dev) {
+        if (cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&t.tier0, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&t.tier2, cudaEventDisableTiming) != cudaSuccess)
+            return nullptr;
+        t.device = dev;
+    }
+    return &t;
+}
+}  // namespace
 
 int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* dice, long long B, int replicate,
                     int flip_player, int mode,
@@ -234,28 +259,55 @@ int bg::movegen_run(const int8_t* boards, const int8_t* players, const int8_t* d
     // (Splitting tier 0 into 2..8 launches over ranges of games, so that K3 could encode part p's rows beside part p + 1, was tried:
     // every extra part cost ~26 us -- each launch ends with its own tail of lone warps finishing big doubles -- and the step got
     // slower, 265 -> 298 us with two parts; scripts/exp_tier0_pipeline.py in the history, profiles/r2_summary.md.)
+    // Large batches: tier 0 sends the positions that are certainly huge straight to tier 2's list, and tier 2 takes those on a
+    // stream of its own BESIDE tier 1 (both are latency bound: one CTA per position); a second, usually empty, tier-2 pass after
+    // tier 1 takes what tier 1 itself could not hold.
+    // Not when a consumer of the rows runs beside the tiers (the hook: K3 / K4 on the caller's side stream): that consumer is HBM
+    // bound and needs its CTAs resident; tier 2's 165 KB CTAs beside it cost the env step 5 us more than they save (265 -> 270 us),
+    // and so does the routing alone (272 us).  K1 on its own (policy rollouts, bg_movegen_*, the unfused 2-ply): 178 -> 166 us.
+    const bool hooked = hook && mode == 2;
+    TierStreams* ts = (B >= 4096 && !hooked) ? tier_streams() : nullptr;
     int rc = launch_movegen<BG_MOVEGEN_CAP_SMALL, 2 * BG_MOVEGEN_CAP_SMALL, 8>(
         boards, players, dice, B, nullptr, nullptr, replicate, flip_player, mode, offsets, max_rows, after,
         after_cap_rows, row_players, row_feats, counts_true, counts, starts, alloc, status, ctr + 0, list_a, ctr + 1,
-        (B + 7) / 8, stream);
+        ts ? list_b : nullptr, ctr + 3, (B + 7) / 8, stream);
     if (rc != BG_OK) return rc;
-    // Slab mode: rows [0, *alloc) are final once tier 0 is done (tiers 1/2 only append).  A caller that wants to
+    bool forked = false;
+    if (ts) {
+        // fork: [snapshot of list B's length] -> [tier 2 on entries [0, snapshot)] on ts->stream
+        e = cudaEventRecord(ts->tier0, stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ts->stream, ts->tier0, 0);
+        if (e != cudaSuccess) return bg_set_error(e, "movegen: fork");
+        forked = true;                                              // from here on every exit goes through the join
+        e = cudaMemcpyAsync(ctr + 6, ctr + 3, sizeof(unsigned int), cudaMemcpyDeviceToDevice, ts->stream);
+        rc = e == cudaSuccess ? BG_OK : bg_set_error(e, "movegen: snapshot");
+        if (rc == BG_OK)
+            rc = movegen_team_big(boards, players, dice, ctr + 6, nullptr, list_b, replicate, flip_player, mode, offsets, max_rows, after,
+                                  after_cap_rows, row_players, row_feats, counts_true, counts, starts, alloc, status, ctr + 4, ts->stream);
+    }
+    // Slab mode: rows [0, *alloc) are final once tier 0 is done (the other tiers only append).  A caller that wants to
     // consume them while the latency-bound overflow tiers run gets the row count snapshot and a fork point here.
-    if (hook && mode == 2) {
+    if (rc == BG_OK && hook && mode == 2) {
         e = cudaMemcpyAsync(hook->rows_after_tier0, alloc, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream);
-        if (e != cudaSuccess) return bg_set_error(e, "movegen: snapshot");
-        rc = hook->fn(hook->user);
-        if (rc != BG_OK) return rc;
+        rc = e == cudaSuccess ? hook->fn(hook->user) : bg_set_error(e, "movegen: snapshot");
     }
     // Tier 1: the (~1 %) positions whose levels did not fit: one CTA per position (movegen_team.cu),
     // BG_MOVEGEN_CAP_MID boards per level.  Work counts of tiers 1 and 2 are read from device memory, so no host
     // synchronisation is needed.
-    rc = movegen_team_mid(boards, players, dice, ctr + 1, list_a, replicate, flip_player, mode, offsets, max_rows, after,
-                          after_cap_rows, row_players, row_feats, counts_true, counts, starts, alloc, status, ctr + 2, list_b,
-                          ctr + 3, stream, ((hook && mode == 2) || B >= 262144) ? 128 : 0);   // 128 threads per position when something shares the GPU or the list is long (throughput, not latency)
+    if (rc == BG_OK)
+        rc = movegen_team_mid(boards, players, dice, ctr + 1, list_a, replicate, flip_player, mode, offsets, max_rows, after,
+                              after_cap_rows, row_players, row_feats, counts_true, counts, starts, alloc, status, ctr + 2, list_b,
+                              ctr + 3, stream, ((hook && mode == 2) || B >= 262144) ? 128 : 0);   // 128 threads per position when something shares the GPU or the list is long (throughput, not latency)
+    if (forked) {                                                   // join
+        e = cudaEventRecord(ts->tier2, ts->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, ts->tier2, 0);
+        if (e != cudaSuccess && rc == BG_OK) rc = bg_set_error(e, "movegen: join");
+    }
     if (rc != BG_OK) return rc;
     // Tier 2: the rest (> BG_MOVEGEN_CAP_MID boards in a level): one big CTA per position, BG_MOVEGEN_CAP_BIG
     // boards per level.  Positions that do not fit even this raise BG_STATUS_SCRATCH_OVERFLOW (never dropped silently).
-    return movegen_team_big(boards, players, dice, ctr + 3, list_b, replicate, flip_player, mode, offsets, max_rows, after,
-                            after_cap_rows, row_players, row_feats, counts_true, counts, starts, alloc, status, ctr + 4, stream);
+    // Forked form: entries [snapshot, end) of list B -- what tier 1 appended.
+    return movegen_team_big(boards, players, dice, ctr + 3, forked ? ctr + 6 : nullptr, list_b, replicate, flip_player, mode, offsets,
+                            max_rows, after, after_cap_rows, row_players, row_feats, counts_true, counts, starts, alloc, status,
+                            forked ? ctr + 7 : ctr + 4, stream);
 }

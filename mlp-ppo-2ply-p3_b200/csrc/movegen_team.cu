@@ -261,7 +261,7 @@ struct Team {
 template <int CAP, int HS, int T>
 __global__ void __launch_bounds__(T) movegen_team_kernel(
     const int8_t* __restrict__ boards, const int8_t* __restrict__ players, const int8_t* __restrict__ dice,
-    const unsigned int* __restrict__ nwork_dev, const int32_t* __restrict__ worklist,
+    const unsigned int* __restrict__ nwork_dev, const unsigned int* __restrict__ first_dev, const int32_t* __restrict__ worklist,
     int replicate, int flip_player, int mode, const long long* __restrict__ offsets, int max_rows,
     int8_t* __restrict__ after, long long after_cap_rows, int8_t* __restrict__ row_players,
     uint16_t* __restrict__ row_feats, int32_t* __restrict__ counts_true, int32_t* __restrict__ counts, long long* __restrict__ starts,
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(T) movegen_team_kernel(
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TeamScratch<CAP, HS, T>& S = *reinterpret_cast<TeamScratch<CAP, HS, T>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long nwork = (long long)*nwork_dev;
+    const long long nwork = (long long)*nwork_dev, first = first_dev ? (long long)*first_dev : 0;   // list entries [first, nwork)
     __shared__ uint32_t s_lut[32], s_desc[32];
     load_chunk_tables(s_lut, s_desc);
     __syncthreads();
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(T) movegen_team_kernel(
     for (;;) {
         if (tid == 0) S.bcast[1] = (int)atomicAdd(work_ctr, 1u);
         __syncthreads();
-        const long long wi = (long long)(unsigned int)S.bcast[1];
+        const long long wi = first + (long long)(unsigned int)S.bcast[1];
         if (wi >= nwork) break;
         const long long g = (long long)worklist[wi];
         const WorkItem item = decode_work_item(g, replicate > 1 ? g / replicate : g, replicate, flip_player, players, dice);
@@ -364,7 +364,7 @@ static int g_team_mid_override = 0, g_team_big_override = 0;
 
 template <int CAP, int HS, int T>
 static int launch_team(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
-                       const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
+                       const unsigned int* first_dev, const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
                        int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, uint16_t* row_feats,
                        int32_t* counts_true,
                        int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
@@ -377,7 +377,7 @@ static int launch_team(const int8_t* boards, const int8_t* players, const int8_t
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem);
     if (occ < 1) occ = 1;
     unsigned grid = (unsigned)(bg_sm_count() * occ);
-    kern<<<grid, T, smem, stream>>>(boards, players, dice, nwork_dev, worklist, replicate, flip_player, mode, offsets,
+    kern<<<grid, T, smem, stream>>>(boards, players, dice, nwork_dev, first_dev, worklist, replicate, flip_player, mode, offsets,
                                     max_rows, after, after_cap_rows, row_players, row_feats, counts_true, counts, starts,
                                     alloc, status, work_ctr, overflow_list, overflow_ctr);
     return bg_set_error(cudaGetLastError(), "movegen(team): launch");
@@ -391,7 +391,7 @@ int movegen_team_mid(const int8_t* boards, const int8_t* players, const int8_t* 
                      unsigned int* work_ctr, int32_t* overflow_list, unsigned int* overflow_ctr, cudaStream_t stream,
                      int team_threads_hint) {
 #define BG_TEAM_MID(T) launch_team<BG_MOVEGEN_CAP_MID, 2 * BG_MOVEGEN_CAP_MID, T>( \
-        boards, players, dice, nwork_dev, worklist, replicate, flip_player, mode, offsets, max_rows, after, after_cap_rows, \
+        boards, players, dice, nwork_dev, nullptr, worklist, replicate, flip_player, mode, offsets, max_rows, after, after_cap_rows, \
         row_players, row_feats, counts_true, counts, starts, alloc, status, work_ctr, overflow_list, overflow_ctr, stream)
     // 256 threads per position is the fastest alone; when an encoder runs beside the tiers (bg_update_legal_plays)
     // 128 leaves it more of the SMs' thread slots and the pair finishes sooner
@@ -403,13 +403,13 @@ int movegen_team_mid(const int8_t* boards, const int8_t* players, const int8_t* 
 #undef BG_TEAM_MID
 }
 int movegen_team_big(const int8_t* boards, const int8_t* players, const int8_t* dice, const unsigned int* nwork_dev,
-                     const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
+                     const unsigned int* first_dev, const int32_t* worklist, int replicate, int flip_player, int mode, const long long* offsets,
                      int max_rows, int8_t* after, long long after_cap_rows, int8_t* row_players, uint16_t* row_feats,
                        int32_t* counts_true,
                      int32_t* counts, long long* starts, unsigned long long* alloc, int32_t* status,
                      unsigned int* work_ctr, cudaStream_t stream) {
 #define BG_TEAM_BIG(T) launch_team<BG_MOVEGEN_CAP_BIG, BG_MOVEGEN_HASH_BIG, T>( \
-        boards, players, dice, nwork_dev, worklist, replicate, flip_player, mode, offsets, max_rows, after, after_cap_rows, \
+        boards, players, dice, nwork_dev, first_dev, worklist, replicate, flip_player, mode, offsets, max_rows, after, after_cap_rows, \
         row_players, row_feats, counts_true, counts, starts, alloc, status, work_ctr, nullptr, nullptr, stream)
     static const int t2_env = team_size_env("BG_TEAM_BIG", 512);
     const int t2 = g_team_big_override ? g_team_big_override : t2_env;

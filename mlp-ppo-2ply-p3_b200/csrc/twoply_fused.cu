@@ -576,7 +576,7 @@ extern "C" int bg_twoply(const int8_t* boards52, const int8_t* players, const in
         rc = movegen_team_mid(afterstates52, row_players, nullptr, ovf_ctr, list_a, 21, 1, 2, nullptr, 0, ovf_rows, P.ovf_cap_rows, ovf_rowp,
                               nullptr, nullptr, ovf_counts, ovf_starts, ovf_alloc, status, ctr + 0, list_b, ctr + 1, stream, 128);
         if (rc != BG_OK) return rc;
-        rc = movegen_team_big(afterstates52, row_players, nullptr, ctr + 1, list_b, 21, 1, 2, nullptr, 0, ovf_rows, P.ovf_cap_rows, ovf_rowp,
+        rc = movegen_team_big(afterstates52, row_players, nullptr, ctr + 1, nullptr, list_b, 21, 1, 2, nullptr, 0, ovf_rows, P.ovf_cap_rows, ovf_rowp,
                               nullptr, nullptr, ovf_counts, ovf_starts, ovf_alloc, status, ctr + 2, stream);
         if (rc != BG_OK) return rc;
         rc = mlp_value_launch(ovf_rows, ovf_rowp, 0, 0, P.ovf_cap_rows, nullptr, ovf_alloc, w1_bf16, nullptr, wv, bv, 1, ovf_leaf, stream);

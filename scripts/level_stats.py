@@ -37,3 +37,8 @@ for tot in (192, 256, 320, 384):
 print("  doubles: mean boards per level", sz.mean(0), "mean candidates per level", cd.mean(0))
 ov = mx > 128
 print("  overflowing (>128): mean level sizes", sz[ov].mean(0), "mean candidates", cd[ov].mean(0), " last level >512:", np.mean(mx > 512) * len(R) / positions * 100, "%")
+# routing predictor for the overflow tiers: a position whose THIRD level already exceeds 128 boards ...
+early = (sz[:, :3].max(1) > 128)
+big = mx > 512
+print(f"  level <= 3 already > 128: {early.sum() / positions * 100:.3f} % of positions; of the {big.sum()} positions with a level > 512, {int((early & big).sum())} are among them;"
+      f" of the early ones {int((early & ~big).sum())} would have fitted 512")

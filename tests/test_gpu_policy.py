@@ -127,3 +127,31 @@ def test_policy_class_paths_logp_and_values():
     picked = masked.gather(1, g.long()[:, None])[:, 0]
     assert (best - picked).abs().max().item() < 1e-2                # (ties / bf16 boundary cases: the value, not the index)
     assert (glp - ref_lsm.gather(1, g.long()[:, None])[:, 0]).abs().max().item() < 1e-2
+
+
+def test_policy_many_class_b_rows_serial_chunks():
+    """More class B tiles than the kernel deals out chunk by chunk (kMaxSplitB = 64 tiles): the CTAs then walk the four chunks of
+    such a tile one after the other.  9,000 passes (no legal slot: the reference's softmax over all 500 slots) + ordinary rows: same
+    checks as above, and the split form (few class B rows) must give the same log-prob for the same row and action."""
+    import bg_b200
+    env = _positions(3000, seed=9)
+    net = bg_b200.PolicyValueNet.random_init("cuda:0", seed=6)
+    net.params["action_head.weight"].mul_(4.0); net.sync()
+    reps = 4
+    boards = env.boards52.repeat(reps, 1).contiguous()
+    players = env.players.repeat(reps).contiguous()
+    counts = env.legal_counts.to(torch.int32).repeat(reps).contiguous()
+    counts[:9000] = 0                                              # 71 class B tiles
+    ref_logits, _, ref_v, _ = _reference(net, env, bf16_operands=True)
+    ref_logits, ref_v = ref_logits.repeat(reps, 1), ref_v.repeat(reps)
+    n = counts.long()
+    slot = torch.arange(500, device=ref_logits.device)[None, :]
+    masked = ref_logits + torch.where((slot < n[:, None]), 0.0, -103.27893)
+    ref_lsm = torch.log_softmax(masked, -1)
+    a, lp, v = net.act(boards, players, counts, seed=5, step=2)
+    al = a.long()
+    assert bool((torch.where(n > 0, al < n, al < 500) & (al >= 0)).all())
+    assert (lp - ref_lsm.gather(1, al[:, None])[:, 0]).abs().max().item() < 1e-2
+    assert (v - ref_v).abs().max().item() < 1e-3
+    # passes sample among all 500 slots: the draws must spread over the chunks
+    assert int((al[:9000] >= 128).sum()) > 4000 and int((al[:9000] >= 384).sum()) > 1000
