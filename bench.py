@@ -610,17 +610,21 @@ def run_ppo_loop(bg_b200, env, pnet, torch, dev, args, dist, world):
     cfg = PPOConfig(t_horizon=args.ppo_horizon)
     tr = PPOTrainer(env, pnet, cfg, dist, seed=0)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    ret = tr.collect(); tr.count_episodes(); tr.update(ret)             # warm-up update (allocations, cuBLAS handles)
+    for _ in range(2):                                                   # warm-up updates: the caching allocator reaches its steady state in the second
+        ret = tr.collect(); tr.count_episodes(); tr.update(ret)         # (device_allocs_per_update in the output shows cudaMalloc calls inside the timed ones)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     marks = [[ev(), ev(), ev()] for _ in range(args.ppo_updates)]
+    dev_allocs = []                                                       # cudaMalloc calls of the caching allocator during each update
     for m in marks:
         m[0].record()
         ret = tr.collect()
         m[1].record()
         tr.count_episodes()
+        n0 = torch.cuda.memory_stats().get("num_device_alloc", 0)
         stats = tr.update(ret)
+        dev_allocs.append(int(torch.cuda.memory_stats().get("num_device_alloc", 0) - n0))
         m[2].record()
     torch.cuda.synchronize()
     ar0, ar1 = ev(), ev()
@@ -639,7 +643,7 @@ def run_ppo_loop(bg_b200, env, pnet, torch, dev, args, dist, world):
             "samples_per_update_per_gpu": N * T, "epochs": cfg.num_epochs,
             "rollout_ms_per_update": roll_ms / U, "update_ms_per_update": upd_ms / U,
             "update_ms_all_this_rank": [round(m[1].elapsed_time(m[2]), 3) for m in marks],
-            "reserved_gib": round(torch.cuda.memory_reserved() / 2**30, 2),
+            "reserved_gib": round(torch.cuda.memory_reserved() / 2**30, 2), "device_allocs_per_update": dev_allocs,
             "allreduce_ms_per_call": ar_ms, "allreduce_calls_per_update": cfg.num_epochs * cfg.num_minibatches,
             "allreduce_bytes": tr.learner.fp.numel * 4, "last_stats": {k: v for k, v in stats.items() if isinstance(v, float)},
             "what": "configs[4]: rollout + GAE + update, one 90,101-float NCCL all-reduce per optimiser step (the only collective); "

@@ -276,6 +276,7 @@ class TensorCoreUpdate:
         tiles, gather the per-sample vectors and build the blocked x (with the bias column).  One host read (the class sizes)."""
         B = x.shape[0]
         dev = self.device
+        self._p = None                                   # drop the previous rollout's vectors first: the allocator reuses their blocks
         a = self.class_a(counts, actions)
         # class A first, and inside class A by the number of legal slots: most tiles then hold only rows with <= 32 slots, and the
         # fused logits / loss kernel skips the blocks of slots that are illegal for all 32 rows of a warp
