@@ -255,6 +255,7 @@ class TensorCoreUpdate:
         self.w1t = z((199 * 128,), torch.float32)              # scratch of GRAD_W1 (dW1p transposed)
         self._cap = (0, 0)
         self._p = None
+        self._scratch = {}
 
     # the class of a sample: csrc/ppo.cu loss_row_is_packed
     @staticmethod
@@ -276,23 +277,43 @@ class TensorCoreUpdate:
         tiles, gather the per-sample vectors and build the blocked x (with the bias column).  One host read (the class sizes)."""
         B = x.shape[0]
         dev = self.device
-        self._p = None                                   # drop the previous rollout's vectors first: the allocator reuses their blocks
+        self._p = None
         a = self.class_a(counts, actions)
         # class A first, and inside class A by the number of legal slots: most tiles then hold only rows with <= 32 slots, and the
         # fused logits / loss kernel skips the blocks of slots that are illegal for all 32 rows of a warp
-        key = torch.where(a, counts.to(torch.int32), torch.full_like(counts, 1 << 20, dtype=torch.int32))
-        order = torch.argsort(key, stable=True).to(torch.int32)
+        # (persistent scratch for everything that is B long: no allocation on this path after the first rollout of a size)
+        sc = self._scratch
+        if sc.get("B") != B:
+            sc.clear()
+            rows_cap = (-(-B // 128) + 1) * 128
+            sc.update(B=B, key=torch.empty(B, dtype=torch.int32, device=dev), skey=torch.empty(B, dtype=torch.int32, device=dev),
+                      order=torch.empty(B, dtype=torch.int64, device=dev), perm=torch.empty(rows_cap, dtype=torch.int32, device=dev),
+                      idx=torch.empty(rows_cap, dtype=torch.int64, device=dev),
+                      counts=torch.empty(rows_cap, dtype=torch.int32, device=dev), actions=torch.empty(rows_cap, dtype=torch.int32, device=dev),
+                      old_logp=torch.empty(rows_cap, dtype=torch.float32, device=dev), adv=torch.empty(rows_cap, dtype=torch.float32, device=dev),
+                      returns=torch.empty(rows_cap, dtype=torch.float32, device=dev))
+        key = sc["key"]
+        key.copy_(counts)
+        key.masked_fill_(~a, 1 << 20)
+        torch.sort(key, stable=True, out=(sc["skey"], sc["order"]))
+        order = sc["order"]
         n_a = int(a.sum().item())
         n_b = B - n_a
         TA, TB = -(-n_a // 128), -(-n_b // 128)
         rows = (TA + TB) * 128
-        perm = torch.full((max(rows, 1),), -1, dtype=torch.int32, device=dev)
+        perm = sc["perm"][:max(rows, 1)]
+        perm.fill_(-1)
         perm[:n_a] = order[:n_a]
         perm[TA * 128:TA * 128 + n_b] = order[n_a:]
-        idx = perm.clamp(min=0).long()
-        g = lambda t, dt: t.to(dt)[idx].contiguous()
-        p = dict(B=B, n_a=n_a, n_b=n_b, TA=TA, TB=TB, rows=rows, perm=perm, counts=g(counts, torch.int32), actions=g(actions, torch.int32),
-                 old_logp=g(old_logp, torch.float32), adv=g(adv, torch.float32), returns=g(returns, torch.float32))
+        idx = sc["idx"][:max(rows, 1)]
+        idx.copy_(perm)
+        idx.clamp_(min=0)
+        def g(t, dt, name):
+            src = t if t.dtype == dt else t.to(dt)
+            return torch.index_select(src, 0, idx, out=sc[name][:idx.shape[0]])
+        p = dict(B=B, n_a=n_a, n_b=n_b, TA=TA, TB=TB, rows=rows, perm=perm, counts=g(counts, torch.int32, "counts"),
+                 actions=g(actions, torch.int32, "actions"), old_logp=g(old_logp, torch.float32, "old_logp"),
+                 adv=g(adv, torch.float32, "adv"), returns=g(returns, torch.float32, "returns"))
         if self._cap[0] < TA + TB or self._cap[1] < TB:
             # sized for ANY split of B samples into the two classes (TA + TB <= ceil(B / 128) + 1), so that the next rollout of the
             # same size never reallocates (a reallocation of these buffers is a 20 ms hiccup at 4 M samples)
@@ -578,7 +599,12 @@ class PPOTrainer:
     def update(self, returns):
         buf = self.buf
         B = buf.T * buf.N
-        x = encode(buf.boards.view(B, 52), buf.players.view(B), dtype=torch.bfloat16 if self.cfg.autocast else torch.float32)
+        dt = torch.bfloat16 if self.cfg.autocast else torch.float32
+        xb = getattr(self, "_x", None)                    # persistent: a fresh 1.7 GB tensor per update made the caching allocator split and
+        if xb is None or xb.dtype != dt or xb.shape[0] != B:   # re-grow its largest block every few updates (20-100 ms cudaMalloc hiccups)
+            self._x = None
+            xb = self._x = torch.empty((B, 208 if self.cfg.autocast else 198), dtype=dt, device=self.device)
+        x = encode(buf.boards.view(B, 52), buf.players.view(B), dtype=dt, out=xb)
         if not self.cfg.autocast:
             x = x[:, :198]
         stats = self.learner.update(x, buf.counts.view(B), buf.actions.view(B), buf.logp.view(B), buf.values.view(B), returns.reshape(B))
