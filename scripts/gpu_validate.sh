@@ -1,5 +1,5 @@
 #!/bin/bash
-# full GPU suite + bench on HEAD
+# full GPU suite + bench on HEAD (what the driver runs at round end)
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
 timeout 900 python bench.py > gpurun_out/bench_r2ae.json 2> gpurun_out/bench_r2ae.err; tail -c 300 gpurun_out/bench_r2ae.err
 python - <<'PY'
