@@ -85,7 +85,8 @@ struct NtArgs {
     int epi;                                   // 0 relu, 1 + bias, 2 * [mask > 0]
     const float* bias; const uint16_t* mask;   // mask: h, tile-blocked, 16 chunk columns per tile
     uint16_t* out; int nc_out;
-    int dbg;                                   // experiment switches (bg_ppo_gemm_debug): 1 no MMAs, 2 no epilogue stores, 4 no loads
+    int dbg;                                   // experiment switches (bg_ppo_gemm_debug): 1 no MMAs, 2 no epilogue stores, 4 no loads, 8 A operand stays in shared memory
+    int a_tmem;                                // the A tile is copied shared -> tensor memory (tcgen05.cp) and the MMAs read it from there (N <= 128, KC == K <= 208)
     // epi == 3 (LOGITS_LOSS_A): the class A loss in the epilogue -- `out` receives d loss / d logits, the logits never leave the SM
     const int32_t* counts; const int32_t* actions; const float* old_logp; const float* adv; const float* returns;
     long long n_rows;                          // real class A rows (the tiles' rows beyond it are padding)
@@ -158,6 +159,21 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             if (lane == 0 && !(a.dbg & 1)) {
                 const uint32_t Ab = As0 + (uint32_t)b * stage_bytes, D0 = tmem + (uint32_t)(acc * 256);
+                if (a.a_tmem && !(a.dbg & 8)) {
+                    // A through tensor memory: one tcgen05.cp per 16-byte chunk column (128 rows x 128 bits -> 4 TMEM columns, the layout
+                    // K4 builds with tcgen05.st), then TS MMAs -- an SS MMA on two no-swizzle operands costs ~450 cycles per K16 step,
+                    // a TS MMA 64 (K4).  cp and mma of one thread execute in issue order: no barrier between them, and the copy of
+                    // tile t + 2 cannot overtake the MMAs of tile t that read the same columns.
+                    const uint32_t At = D0 + 128u;
+                    for (int c = 0; c < a.KC / 8; ++c) {
+                        const uint64_t sd = make_smem_desc_kmajor(Ab + (uint32_t)(c * kChunk), kChunk, 128);
+                        asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;\n" :: "r"(At + (uint32_t)(4 * c)), "l"(sd) : "memory");
+                    }
+                    for (int ks = 0; ks < a.KC / 16; ++ks) {
+                        const uint64_t db = make_smem_desc_kmajor(Ws + (uint32_t)(ks * 2 * a.w_rows * 16), (uint32_t)(a.w_rows * 16), 128);
+                        mma_bf16_ts(D0, At + (uint32_t)(ks * 8), db, idesc_bf16(128, a.N, 0, 0), ks > 0 ? 1u : 0u);
+                    }
+                } else
                 for (int ks = 0; ks < a.KC / 16; ++ks) {
                     const int kg = kc * a.KC + ks * 16;                // first reduction index of this MMA
                     const uint64_t da = make_smem_desc_kmajor(Ab + (uint32_t)(ks * 2 * kChunk), kChunk, 128);
@@ -602,7 +618,7 @@ extern "C" int bg_ppo_gemm_nt(int op, const uint16_t* A, long long tile_begin, l
     a.A = A; a.tile_begin = tile_begin; a.tile_end = tile_end; a.W = W; a.bias = bias; a.mask = h_mask; a.out = out; a.dbg = g_ppo_gemm_dbg;
     switch (op) {
         // ring sizes: what fits beside the weight tile in 220 KB of shared memory
-        case BG_PPO_OP_HIDDEN:   a.nc_a = 26; a.N = 128; a.K = 208; a.KC = 208; a.w_rows = 128; a.b_mn = 0; a.epi = 0; a.nc_out = 16; a.D = 3; break;
+        case BG_PPO_OP_HIDDEN:   a.nc_a = 26; a.N = 128; a.K = 208; a.KC = 208; a.w_rows = 128; a.b_mn = 0; a.epi = 0; a.nc_out = 16; a.D = 3; a.a_tmem = 1; break;
         case BG_PPO_OP_LOGITS_A: a.nc_a = 16; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 1; a.nc_out = 18; a.D = 5; break;
         case BG_PPO_OP_LOGITS_B: a.nc_a = 16; a.N = 512; a.K = 128; a.KC = 128; a.w_rows = 512; a.b_mn = 0; a.epi = 1; a.nc_out = 64; a.D = 2; break;
         case BG_PPO_OP_DPRE_A:   a.nc_a = 18; a.N = 128; a.K = 144; a.KC = 144; a.w_rows = 144; a.b_mn = 1; a.epi = 2; a.nc_out = 16; a.D = 4; break;

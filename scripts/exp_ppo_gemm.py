@@ -27,7 +27,7 @@ ops = {
     "GRAD_WA_A(544 B/row)": (lambda: check(L.bg_ppo_gemm_tn(5, h.data_ptr(), la.data_ptr(), 0, T, g.data_ptr(), None, st)), 544),
     "GRAD_W1  (672 B/row)": (lambda: check(L.bg_ppo_gemm_tn(7, dpre.data_ptr(), x.data_ptr(), 0, T, g.data_ptr(), scr.data_ptr(), st)), 672),
 }
-for flags, what in ((0, "normal"), (1, "no MMAs"), (2, "no stores"), (3, "no MMAs, no stores"), (4, "no loads"), (7, "nothing but the loop")):
+for flags, what in ((0, "normal"), (8, "A operand from shared memory (SS MMAs) where the default is tensor memory"), (1, "no MMAs"), (2, "no stores"), (3, "no MMAs, no stores"), (4, "no loads"), (7, "nothing but the loop")):
     L.bg_ppo_gemm_debug(flags)
     print(f"--- {what}")
     for name, (fn, bpr) in ops.items():
