@@ -584,8 +584,15 @@ def run_extras(bg_b200, env, torch, dev, args, dist, rank, world):
             pnet.act(env.boards52, env.players, env.legal_counts, seed=1, step=0, out=pout)
     torch.cuda.synchronize()
     t_dev = timed(graph.replay, 50)
+    # executed tensor-core work of the call: hidden layer 2*128*208 per position (four times for a class B row: its four chunks are
+    # four work items that each recompute it), policy GEMM one 128-slot chunk for class A rows (1..128 legal slots), four for class B
+    n_legal = env.legal_counts
+    n_cls_a = int(((n_legal >= 1) & (n_legal <= 128)).sum().item())
+    flop_exec = n_cls_a * (2 * 128 * 208 + 2 * 128 * 128) + (N - n_cls_a) * 4 * (2 * 128 * 208 + 2 * 128 * 128)
     out["policy_sample"] = {"positions_per_s": total(N) / t, "ms": t * 1e3, "device_ms": t_dev * 1e3,
                             "device_positions_per_s": total(N) / t_dev,
+                            "executed_tflops_bf16_per_gpu": flop_exec / t_dev / 1e12, "class_a_rows": n_cls_a, "rows": N,
+                            "flop_note": "executed MMAs only (chunks actually multiplied, K padded to 208), not the 500-slot head for every row",
                             "what": "fused policy/value kernel: encode + 198->128 + 128->500 on tcgen05, prefix mask, softmax, categorical sample; "
                                     "ms = through PolicyValueNet.act (host launch path included), device_ms = the same call replayed as a CUDA graph"}
 
