@@ -574,16 +574,21 @@ def run_extras(bg_b200, env, torch, dev, args, dist, rank, world):
     t = timed(lambda: pnet.act(env.boards52, env.players, env.legal_counts, seed=1, step=0, out=pout), 20)
     # the same call as a CUDA graph (memset + partition + fused kernel), replayed: the device time without the host's launch path
     # (at 65,536 positions the Python call above is launch-bound: ~45 us of host work per call)
-    gstream = torch.cuda.Stream()
-    graph = torch.cuda.CUDAGraph()
-    torch.cuda.synchronize()
-    with torch.cuda.stream(gstream):
-        pnet.act(env.boards52, env.players, env.legal_counts, seed=1, step=0, out=pout)
+    try:
+        gstream = torch.cuda.Stream()
+        graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        with torch.cuda.graph(graph, stream=gstream):
+        with torch.cuda.stream(gstream):
             pnet.act(env.boards52, env.players, env.legal_counts, seed=1, step=0, out=pout)
-    torch.cuda.synchronize()
-    t_dev = timed(graph.replay, 50)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph, stream=gstream):
+                pnet.act(env.boards52, env.players, env.legal_counts, seed=1, step=0, out=pout)
+        torch.cuda.synchronize()
+        t_dev = timed(graph.replay, 50)
+    except Exception as e:                                         # (a capture failure must not take the bench line down)
+        sys.stderr.write("policy_sample: CUDA graph capture failed (%s); device_ms = ms\n" % e)
+        torch.cuda.synchronize()
+        t_dev = t
     # executed tensor-core work of the call: hidden layer 2*128*208 per position (four times for a class B row: its four chunks are
     # four work items that each recompute it), policy GEMM one 128-slot chunk for class A rows (1..128 legal slots), four for class B
     n_legal = env.legal_counts
