@@ -155,3 +155,16 @@ def test_policy_many_class_b_rows_serial_chunks():
     assert (v - ref_v).abs().max().item() < 1e-3
     # passes sample among all 500 slots: the draws must spread over the chunks
     assert int((al[:9000] >= 128).sum()) > 4000 and int((al[:9000] >= 384).sum()) > 1000
+
+
+def test_policy_act_with_a_growing_batch():
+    """act() on 256 rows, then on 400, then on 3000 with the same net: the cached workspace must follow the C ABI's own requirement
+    (bg_policy_workspace_bytes), not a private formula."""
+    import bg_b200
+    env = _positions(3000, seed=2)
+    net = bg_b200.PolicyValueNet.random_init("cuda:0", seed=3)
+    ref = net.act(env.boards52, env.players, env.legal_counts, seed=9, step=1)
+    for B in (256, 400, 3000):
+        a, lp, v = net.act(env.boards52[:B], env.players[:B], env.legal_counts[:B], seed=9, step=1)
+        torch.cuda.synchronize()
+        assert torch.equal(a, ref[0][:B]) and torch.equal(lp, ref[1][:B]) and torch.equal(v, ref[2][:B])   # keyed by row: independent of the batch
