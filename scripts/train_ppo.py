@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--eval-every", type=int, default=5)
     ap.add_argument("--save", default="")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--update-impl", default="tcgen05", choices=["tcgen05", "cublas"], help="the update's linear algebra: hand-written kernels / library GEMMs")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -48,7 +49,8 @@ def main():
     env = make_env(bg_b200, dev, args.games, rank, world, args.seed)
     env.reset()
     net = bg_b200.PolicyValueNet.random_init(dev, seed=args.seed)          # same weights on every rank
-    cfg = PPOConfig(t_horizon=args.horizon, num_epochs=args.epochs, num_minibatches=args.minibatches, lam=args.lam, bootstrap=args.bootstrap)
+    cfg = PPOConfig(t_horizon=args.horizon, num_epochs=args.epochs, num_minibatches=args.minibatches, lam=args.lam, bootstrap=args.bootstrap,
+                    update_impl=args.update_impl)
     tr = PPOTrainer(env, net, cfg, dist if world > 1 else None, seed=args.seed)
     for u in range(args.updates):
         torch.cuda.synchronize(); t0 = time.perf_counter()
