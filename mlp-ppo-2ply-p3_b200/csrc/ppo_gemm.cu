@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_bias[512];
     __shared__ __align__(16) float4 s_red[LOSS ? 2 : 1][LOSS ? 4 : 1][LOSS ? kRows : 1];   // per tile parity, part, row: (max, sum exp, sum exp * z, z[action])
-    __shared__ float s_vrow[LOSS ? 2 : 1][LOSS ? kRows : 1];                                 // the row's value (held by part 0)
+    __shared__ float s_vrow[LOSS ? 2 : 1][LOSS ? 2 * kRows : 1];                             // the row's value, per tile parity and group
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t stage_bytes = (uint32_t)(a.KC >> 3) * kChunk;
     if (a.epi == 1 || LOSS) for (int c = tid; c < 512; c += blockDim.x) s_bias[c] = c < a.N ? a.bias[c] : 0.0f;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
     const int nacc = a.N <= 256 ? 2 : 1;                               // accumulators in TMEM (columns 0.. and 256..)
     if (tid == 0) {
         for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kNtEpiWarps * 32); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], LOSS ? kNtEpiWarps * 16 : kNtEpiWarps * 32); }   // (LOSS: one group of eight warps per accumulator)
         mbar_init(&w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -205,85 +205,80 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
         const int nblk = (a.N + 31) >> 5;                              // blocks of 32 columns (the last may be 16 wide: N = 144)
         if (LOSS) {
             // ---- LOGITS_LOSS_A: logits = acc + bias (rounded to bf16 as the reference's autocast does), then the loss of
-            // ppo_agent.py:271-299 and its gradient, as in ppo_loss_grad_packed_kernel (csrc/ppo.cu): warp `part` holds slots
-            // 32 part .. 32 part + 31 of its rows (part 0 also the value head, column 128); the four parts of a row exchange
-            // (max, sum exp, sum exp z, z[action]) through shared memory; d loss / d logits goes out as bf16, the logits do not.
-            // column sums of d loss / d logits (= the head biases' gradients): one private shared-memory slot per (thread, column)
-            // behind the stage ring -- 32 more live registers would spill in this epilogue
-            float* colsum = reinterpret_cast<float*>(A0 + (size_t)a.D * stage_bytes) + (tid & (kNtEpiWarps * 32 - 1));
-#pragma unroll
-            for (int j = 0; j < 32; ++j) colsum[j * (kNtEpiWarps * 32)] = 0.0f;
+            // ppo_agent.py:271-299 and its gradient, as in ppo_loss_grad_packed_kernel (csrc/ppo.cu); d loss / d logits goes out as bf16,
+            // the logits do not.  TWO GROUPS of eight warps, each on its own accumulator (tiles t = group, group + 2, ...): the phases of
+            // a tile (wait for the MMAs, pass 1, exchange + barrier, pass 2) are serial, and with all sixteen warps on one tile the
+            // issue slots idled at every hand-over; two tiles in different phases fill each other's gaps.  Inside a group: lane quarter
+            // q (TMEM lanes 32 q ..), column part p of two; the 128 slots of a row are 16 sub-blocks of 8 (one 16-byte chunk column of
+            // the blocked output), sub-block sb belongs to part sb & 1 -- so that rows with few legal slots load both parts alike --
+            // and is STREAMED from tensor memory twice (pass 1: online max / sums; pass 2: the gradient): holding a row's logits in
+            // registers across the exchange spilled.  The rows arrive sorted by their number of legal slots (TensorCoreUpdate.prepare),
+            // so most warps stop after the first one or two of their eight sub-blocks and write zeros for the rest.
+            const int grp = warp >> 3, lpart = (warp >> 2) & 1;
+            float cs[8];                                               // column sums of d loss / d logits (the head biases' gradients): sub-block 2 j + lpart,
+#pragma unroll                                                         // column 4 bit4 + 2 bit3 + bit2 of the lane (see the reduce-scatter below)
+            for (int j = 0; j < 8; ++j) cs[j] = 0.0f;
             float pl = 0.0f, vl = 0.0f, ent = 0.0f, vsum = 0.0f;
             const float ce = a.entropy_coef * a.inv_b;
-            for (long long t = 0; t < my_tiles; ++t) {
-                const int acc = (int)(t % nacc), par = (int)(t & 1);
+            for (long long t = grp; t < my_tiles; t += 2) {
+                const int acc = grp, par = (int)((t >> 1) & 1);
                 const size_t tile = (size_t)tile_of(t);
                 const long long gr = (long long)tile * kRows + r;      // class A sample index
                 const bool live = gr < a.n_rows;
                 int n = 1, act = 0; float A = 0.0f, olp = 0.0f, ret = 0.0f;
                 if (live) { n = __ldg(a.counts + gr); act = __ldg(a.actions + gr); A = __ldg(a.adv + gr); olp = __ldg(a.old_logp + gr); ret = __ldg(a.returns + gr); }
-                warp_wait(&acc_full[acc], (uint32_t)(t / nacc) & 1u, lane);
+                warp_wait(&acc_full[acc], (uint32_t)(t >> 1) & 1u, lane);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                // the rows arrive sorted by their number of legal slots (TensorCoreUpdate.prepare), so for most groups of 32 rows the
-                // slots 32 .. 127 are illegal for every row: those warps skip their block (zeros go out as its d loss / d logits).
-                // The block is streamed from tensor memory twice, eight columns at a time (pass 1: online max / sums, pass 2: the
-                // gradient): holding its 32 logits in registers across the exchange spilled.
-                const bool blk = __any_sync(kFull, n > 32 * part);
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-                auto logits8 = [&](int sb, float (&z)[8]) {            // slots 32 part + 8 sb .. + 7 of this thread's row: bf16(acc + bias), -inf if illegal
+                auto logits8 = [&](int sb, float (&z)[8]) {            // slots 8 sb .. 8 sb + 7 of this thread's row: bf16(acc + bias), -inf if illegal
                     uint32_t av[8];
-                    tmem_ld8(taddr + 32 * part + 8 * sb, av);
+                    tmem_ld8(taddr + 8 * sb, av);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int c = 32 * part + 8 * sb + j;
+                        const int c = 8 * sb + j;
                         const float l = __bfloat162float(__float2bfloat16_rn(__uint_as_float(av[j]) + s_bias[c]));
                         z[j] = c < n ? l : -INFINITY;
                     }
                 };
                 float m = -INFINITY, ssum = 0.0f, tsum = 0.0f, za = 0.0f;
-                if (blk) {
 #pragma unroll 1
-                    for (int sb = 0; sb < 4; ++sb) {
-                        if (!__any_sync(kFull, n > 32 * part + 8 * sb)) break;
-                        float z[8];
-                        logits8(sb, z);
-                        float cm = z[0];
+                for (int j = 0; j < 8; ++j) {
+                    const int sb = 2 * j + lpart;
+                    if (!__any_sync(kFull, n > 8 * sb)) break;
+                    float z[8];
+                    logits8(sb, z);
+                    float cm = z[0];
 #pragma unroll
-                        for (int j = 1; j < 8; ++j) cm = fmaxf(cm, z[j]);
-                        if (cm > -INFINITY) {
-                            const float mn = fmaxf(m, cm);
-                            const float sc = __expf(m - mn);           // 0 on the first block (m = -inf)
-                            ssum *= sc; tsum *= sc;
+                    for (int i = 1; i < 8; ++i) cm = fmaxf(cm, z[i]);
+                    if (cm > -INFINITY) {
+                        const float mn = fmaxf(m, cm);
+                        const float sc = __expf(m - mn);               // 0 on the first block (m = -inf)
+                        ssum *= sc; tsum *= sc;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float e = __expf(z[j] - mn);     // 0 for masked slots
-                                ssum += e;
-                                if (z[j] > -INFINITY) tsum = fmaf(e, z[j], tsum);
-                                if (32 * part + 8 * sb + j == act) za = z[j];
-                            }
-                            m = mn;
+                        for (int i = 0; i < 8; ++i) {
+                            const float e = __expf(z[i] - mn);         // 0 for masked slots
+                            ssum += e;
+                            if (z[i] > -INFINITY) tsum = fmaf(e, z[i], tsum);
+                            if (8 * sb + i == act) za = z[i];
                         }
+                        m = mn;
                     }
                 }
-                s_red[par][part][r] = make_float4(m, ssum, tsum, za);
-                if (part == 0) {
+                s_red[par][2 * grp + lpart][r] = make_float4(m, ssum, tsum, za);
+                if (lpart == 0) {
                     uint32_t vv[8];
                     tmem_ld8(taddr + 128, vv);
                     tmem_ld_wait();
-                    s_vrow[par][r] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(vv[0]) + s_bias[128]));
+                    s_vrow[par][grp * kRows + r] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(vv[0]) + s_bias[128]));
                 }
-                asm volatile("bar.sync 1, %0;\n" :: "n"(kNtEpiWarps * 32) : "memory");
-                float M = -INFINITY;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) M = fmaxf(M, s_red[par][k][r].x);
-                float S = 0.0f, T = 0.0f, ZA = 0.0f;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float4 v = s_red[par][k][r];
-                    if (v.x > -INFINITY) { const float sc = __expf(v.x - M); S = fmaf(v.y, sc, S); T = fmaf(v.z, sc, T); }
-                    ZA += v.w;
-                }
+                asm volatile("bar.sync %0, %1;\n" :: "r"(1 + grp), "n"(kNtEpiWarps * 16) : "memory");
+                const float4 r0 = s_red[par][2 * grp][r], r1 = s_red[par][2 * grp + 1][r];
+                const float M = fmaxf(r0.x, r1.x);
+                float S = 0.0f, T = 0.0f;
+                if (r0.x > -INFINITY) { const float sc = __expf(r0.x - M); S = r0.y * sc; T = r0.z * sc; }
+                if (r1.x > -INFINITY) { const float sc = __expf(r1.x - M); S = fmaf(r1.y, sc, S); T = fmaf(r1.z, sc, T); }
+                const float ZA = r0.w + r1.w;
                 const float lse = M + __logf(S);
                 const float H = lse - T / S;                           // entropy = -sum p log p
                 const float lpa = ZA - lse;
@@ -292,41 +287,51 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
                 const float s1 = rr * A, s2 = rc * A;
                 const bool through = (rr >= 1.0f - a.eps_clip && rr <= 1.0f + a.eps_clip) || s1 < s2;
                 const float g = through ? -A * rr * a.inv_b : 0.0f;
-                const float v = s_vrow[par][r];
+                const float v = s_vrow[par][grp * kRows + r];
                 const float dv = v - ret;
                 const float dvalue = 2.0f * a.value_coef * dv * a.inv_b;
                 unsigned char* otile = reinterpret_cast<unsigned char*>(a.out) + tile * a.nc_out * kChunk + r * 16;
-#pragma unroll 1
-                for (int sb = 0; sb < 4; ++sb) {
+                const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int sb = 2 * j + lpart;
                     uint32_t o[4] = {0u, 0u, 0u, 0u};
-                    if (blk && __any_sync(kFull, n > 32 * part + 8 * sb)) {
-                        float z[8];
+                    if (__any_sync(kFull, n > 8 * sb)) {
+                        float z[8], d[8];
                         logits8(sb, z);
 #pragma unroll
-                        for (int e2 = 0; e2 < 4; ++e2) {
-                            float d2[2];
-#pragma unroll
-                            for (int h2 = 0; h2 < 2; ++h2) {
-                                const int j = 2 * e2 + h2;
-                                float d = 0.0f;
-                                if (live && z[j] > -INFINITY) {
-                                    const float lp = z[j] - lse;
-                                    const float pk = __expf(lp);
-                                    d = -g * pk + (pk > 0.0f ? ce * pk * (lp + H) : 0.0f);
-                                    if (32 * part + 8 * sb + j == act) d += g;
-                                }
-                                colsum[(8 * sb + j) * (kNtEpiWarps * 32)] += d;
-                                d2[h2] = d;
+                        for (int i = 0; i < 8; ++i) {
+                            float di = 0.0f;
+                            if (live && z[i] > -INFINITY) {
+                                const float lp = z[i] - lse;
+                                const float pk = __expf(lp);
+                                di = -g * pk + (pk > 0.0f ? ce * pk * (lp + H) : 0.0f);
+                                if (8 * sb + i == act) di += g;
                             }
-                            const __nv_bfloat162 pr = __floats2bfloat162_rn(d2[0], d2[1]);
+                            d[i] = di;
+                        }
+#pragma unroll
+                        for (int e2 = 0; e2 < 4; ++e2) {
+                            const __nv_bfloat162 pr = __floats2bfloat162_rn(d[2 * e2], d[2 * e2 + 1]);
                             o[e2] = *reinterpret_cast<const uint32_t*>(&pr);
                         }
+                        // column sums over the warp's 32 rows, reduce-scatter: after three halving rounds a lane holds ONE column (4 bit4 +
+                        // 2 bit3 + bit2) summed over 8 lanes, two more rounds finish it -- 9 shuffles for 8 columns instead of 40
+                        float w4[4], w2[2];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) w4[k] = (b4 ? d[4 + k] : d[k]) + __shfl_xor_sync(kFull, b4 ? d[k] : d[4 + k], 16);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) w2[k] = (b3 ? w4[2 + k] : w4[k]) + __shfl_xor_sync(kFull, b3 ? w4[k] : w4[2 + k], 8);
+                        float w1 = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(kFull, b2 ? w2[0] : w2[1], 4);
+                        w1 += __shfl_xor_sync(kFull, w1, 2);
+                        w1 += __shfl_xor_sync(kFull, w1, 1);
+                        cs[j] += w1;
                     }
-                    if (!(a.dbg & 2)) *reinterpret_cast<uint4*>(otile + (size_t)(4 * part + sb) * kChunk) = make_uint4(o[0], o[1], o[2], o[3]);
+                    if (!(a.dbg & 2)) *reinterpret_cast<uint4*>(otile + (size_t)sb * kChunk) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
                 mbar_arrive(&acc_empty[acc]);                          // the accumulator has been read for the last time
-                if (part == 0) {                                       // the value head's column (128) and the zero padding (129 .. 143)
+                if (lpart == 0) {                                      // the value head's column (128) and the zero padding (129 .. 143)
                     const float dvw = live ? dvalue : 0.0f;
                     const __nv_bfloat162 pr = __floats2bfloat162_rn(dvw, 0.0f);
                     if (!(a.dbg & 2)) {
@@ -336,15 +341,13 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
                     if (live) { vsum += dvw; pl -= fminf(s1, s2); vl = fmaf(dv, dv, vl); ent += H; }
                 }
             }
-            // column sums (= the head biases' gradients) and the loss sums: over the rows of the warp, then one atomic per column and warp
+            // the column sums (one atomic per column and warp: the lanes with lane % 4 == 0 hold the eight columns of a sub-block) and the loss sums
+            if ((lane & 3) == 0 && a.dbias) {
+                const int ci = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float c = colsum[j * (kNtEpiWarps * 32)];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
-                if (lane == (j & 31) && a.dbias) atomicAdd(a.dbias + 32 * part + j, c);
+                for (int j = 0; j < 8; ++j) atomicAdd(a.dbias + 8 * (2 * j + lpart) + ci, cs[j]);
             }
-            if (part == 0) {
+            if (lpart == 0) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     pl += __shfl_xor_sync(kFull, pl, o); vl += __shfl_xor_sync(kFull, vl, o); ent += __shfl_xor_sync(kFull, ent, o);
@@ -651,12 +654,12 @@ extern "C" int bg_ppo_logits_loss_a(const uint16_t* h, long long n_a, long long 
         return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_logits_loss_a: null pointer");
     NtArgs a{};
     a.A = h; a.tile_begin = 0; a.tile_end = (n_a + kRows - 1) / kRows; a.W = wap_a; a.bias = bias_a; a.out = dlogits_a; a.dbg = g_ppo_gemm_dbg;
-    a.nc_a = 16; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 3; a.nc_out = 18; a.D = 3;   // (the epilogue bounds this kernel: three stages are enough, and the column sums need the room)
+    a.nc_a = 16; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 3; a.nc_out = 18; a.D = 5;
     a.counts = counts; a.actions = actions; a.old_logp = old_log_probs; a.adv = advantages; a.returns = returns; a.n_rows = n_a;
     a.eps_clip = eps_clip; a.value_coef = value_coef; a.entropy_coef = entropy_coef; a.inv_b = 1.0f / (float)B_norm;
     a.dbias = dbias; a.sums = sums;
     a.w_bytes = 16 * a.w_rows * 16;
-    const size_t smem = ((size_t)(a.w_bytes + 1023) & ~(size_t)1023) + (size_t)a.D * (size_t)(a.KC >> 3) * kChunk + 32 * kNtEpiWarps * 32 * sizeof(float);
+    const size_t smem = ((size_t)(a.w_bytes + 1023) & ~(size_t)1023) + (size_t)a.D * (size_t)(a.KC >> 3) * kChunk;
     cudaError_t e = cudaFuncSetAttribute(ppo_gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // + 20 KB static
     if (e != cudaSuccess) return bg_set_error(e, "bg_ppo_logits_loss_a: cudaFuncSetAttribute");
     long long grid = (long long)bg_sm_count();
