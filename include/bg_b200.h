@@ -160,6 +160,9 @@ int bg_env_step_random(const bg_env_state* st, unsigned long long act_seed, uint
  * policy's upload of VectorizedBackgammonEnv.step(actions), vec_bg_env.py:28-33), issued from this library so that the
  * caller needs no second CUDA runtime binding. */
 int bg_copy_actions_async(int32_t* actions_dev, const int32_t* host_actions, long long n, void* stream);
+/* A rollout's record of a step's inputs in one launch: boards52 [N][52], players [N], legal-play counts [N] of the env state copied to
+ * the caller's buffers (the slices of its [T][N] rollout buffer: what BackgammonPPOAgent.store_transition keeps, ppo_agent.py:193-204). */
+int bg_record_state(const bg_env_state* st, int8_t* boards52_out, int8_t* players_out, int32_t* counts_out, void* stream);
 /* uniform random policy: actions[g] = mulhi(Philox(seed, stream_base+g, t; "ACT1"), counts[g]) (0 if none). */
 int bg_random_actions(const int32_t* counts, long long N, unsigned long long seed, unsigned long long stream_base,
                       uint32_t t, int32_t* actions, void* stream);

@@ -198,6 +198,29 @@ extern "C" int bg_copy_actions_async(int32_t* actions_dev, const int32_t* host_a
                                         (cudaStream_t)stream), "bg_copy_actions_async");
 }
 
+// The rollout's record of a step's inputs (RolloutBuffer: boards52, mover, legal-play count of every game) in ONE launch.
+namespace bg {
+__global__ void __launch_bounds__(256) record_state_kernel(const uint32_t* __restrict__ boards, const int8_t* __restrict__ players,
+                                                           const int32_t* __restrict__ counts, long long N, uint32_t* __restrict__ boards_out,
+                                                           int8_t* __restrict__ players_out, int32_t* __restrict__ counts_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nw = N * kBoardWords;
+    if (i < nw) boards_out[i] = boards[i];
+    if (i < N) { players_out[i] = players[i]; counts_out[i] = counts[i]; }
+}
+}  // namespace bg
+extern "C" int bg_record_state(const bg_env_state* st, int8_t* boards52_out, int8_t* players_out, int32_t* counts_out, void* stream) {
+    int rc = check_state(st, "bg_record_state: bad state");
+    if (rc != BG_OK) return rc;
+    if (st->n_games == 0) return BG_OK;
+    if (!st->counts || !boards52_out || !players_out || !counts_out) return bg_set_error_msg(BG_ERR_INVALID, "bg_record_state: null pointer");
+    const long long nw = st->n_games * kBoardWords;
+    record_state_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint32_t*>(st->boards52), st->players, st->counts, st->n_games, reinterpret_cast<uint32_t*>(boards52_out),
+        players_out, counts_out);
+    return bg_set_error(cudaGetLastError(), "bg_record_state: launch");
+}
+
 extern "C" int bg_random_actions(const int32_t* counts, long long N, unsigned long long seed,
                                  unsigned long long stream_base, uint32_t t, int32_t* actions, void* stream) {
     if (N < 0 || (N > 0 && (!counts || !actions))) return bg_set_error_msg(BG_ERR_INVALID, "bg_random_actions: bad args");

@@ -576,10 +576,11 @@ class PPOTrainer:
             if self.cfg.reset_each_update:
                 env.reset()
             for t in range(buf.T):
-                buf.boards[t].copy_(env.boards52); buf.players[t].copy_(env.players); buf.counts[t].copy_(env.legal_counts)
+                st = env._state()
+                check(L.bg_record_state(C.byref(st), buf.boards[t].data_ptr(), buf.players[t].data_ptr(), buf.counts[t].data_ptr(), _stream()),
+                      "bg_record_state")                           # boards, movers, legal counts of this step in one launch
                 net.act(env.boards52, env.players, env.legal_counts, seed=self.seed, stream_base=env.stream_base,
                         step=self.global_step, out=(buf.actions[t], buf.logp[t], buf.values[t]))
-                st = env._state()
                 out = StepOut(buf.rewards[t].data_ptr(), buf.dones[t].data_ptr(), buf.info_player[t].data_ptr(),
                               buf.winner[t].data_ptr(), buf.game_score[t].data_ptr(), buf.flags[t].data_ptr())
                 check(L.bg_env_step(C.byref(st), buf.actions[t].data_ptr(), C.byref(out), env.status.data_ptr(), _stream()),

@@ -166,3 +166,21 @@ def test_step_random_equals_random_actions_then_step():
         assert torch.equal(getattr(a, name), getattr(b, name)), name
     assert int(a.alloc_rows.item()) == int(a.legal_counts.sum().item()) == int(b.alloc_rows.item())
     a.check_status(); b.check_status()
+
+
+def test_record_state_copies_boards_players_counts():
+    """bg_record_state (the rollout's one-launch record of a step's inputs) == three plain copies"""
+    import ctypes as C
+    import bg_b200
+    from bg_b200._lib import lib, check
+    env = bg_b200.B200BackgammonVecEnv(num_envs=1000, device="cuda:0", seed=5, check_every=0)
+    env.reset()
+    for t in range(9):
+        env.step_device(env.random_actions(3, t))
+    b = torch.full((1000, 52), -7, dtype=torch.int8, device="cuda:0")
+    p = torch.full((1000,), -7, dtype=torch.int8, device="cuda:0")
+    c = torch.full((1000,), -7, dtype=torch.int32, device="cuda:0")
+    st = env._state()
+    check(lib().bg_record_state(C.byref(st), b.data_ptr(), p.data_ptr(), c.data_ptr(), torch.cuda.current_stream().cuda_stream), "bg_record_state")
+    torch.cuda.synchronize()
+    assert torch.equal(b, env.boards52) and torch.equal(p, env.players) and torch.equal(c, env.legal_counts)
