@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(256) step_kernel(bg_env_state st, const int32_
     if (g >= st.n_games) return;
     const int cur = st.players[g] & 1;
     const int n = st.counts[g];
+    const long long row0 = st.starts[g];                      // (read up front: one dependent round trip less before the row loads)
     int a;
     if (actions) a = actions[g];
     else {
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(256) step_kernel(bg_env_state st, const int32_
     } else if (a < 0 || a >= n) {                             // invalid action: :143-149 (state unchanged)
         flags = 2; reward = -1.0f;
     } else {
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(st.afterstates52 + (st.starts[g] + a) * kBoardBytes);
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(st.afterstates52 + (row0 + a) * kBoardBytes);
         uint32_t w[kBoardWords];
 #pragma unroll
         for (int k = 0; k < kBoardWords; ++k) w[k] = row[k];                                              // :152-153
