@@ -60,6 +60,14 @@ __device__ __forceinline__ void warp_wait(unsigned long long* bar, uint32_t pari
     if (lane == 0) mbar_wait(bar, parity);
     __syncwarp();
 }
+// the same for the (many) epilogue warps, with a pause between tries: sixteen lanes spinning on try_wait were two thirds of HIDDEN's
+// executed instructions and shared their schedulers with the ONE thread that issues the copies and MMAs of a tile
+__device__ __forceinline__ void warp_wait_relaxed(unsigned long long* bar, uint32_t parity, int lane) {
+    if (lane == 0) {
+        while (!mbar_try_wait(bar, parity)) __nanosleep(128);
+    }
+    __syncwarp();
+}
 // `bytes` contiguous bytes global -> shared by the TMA engine; completion is counted on `bar` (armed with expect_tx)
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
                 const bool live = gr < a.n_rows;
                 int n = 1, act = 0; float A = 0.0f, olp = 0.0f, ret = 0.0f;
                 if (live) { n = __ldg(a.counts + gr); act = __ldg(a.actions + gr); A = __ldg(a.adv + gr); olp = __ldg(a.old_logp + gr); ret = __ldg(a.returns + gr); }
-                warp_wait(&acc_full[acc], (uint32_t)(t >> 1) & 1u, lane);
+                warp_wait_relaxed(&acc_full[acc], (uint32_t)(t >> 1) & 1u, lane);
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
                 auto logits8 = [&](int sb, float (&z)[8]) {            // slots 8 sb .. 8 sb + 7 of this thread's row: bf16(acc + bias), -inf if illegal
@@ -372,7 +380,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
 #pragma unroll
                 for (int j = 0; j < 4; ++j) mk[j] = __ldg(reinterpret_cast<const uint4*>(mtile + (size_t)(4 * part + j) * kChunk));
             }
-            warp_wait(&acc_full[acc], (uint32_t)(t / nacc) & 1u, lane);
+            warp_wait_relaxed(&acc_full[acc], (uint32_t)(t / nacc) & 1u, lane);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             for (int blk = part; blk < nblk; blk += kNtParts) {
                 const int c0 = 32 * blk, w = a.N - c0 < 32 ? a.N - c0 : 32;
