@@ -107,7 +107,7 @@ constexpr int kNtThreads = 32 * (kNtEpiWarps + 2);
 template <bool LOSS>
 __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ unsigned long long full[8], empty[8], acc_full[2], acc_empty[2], w_bar;
+    __shared__ unsigned long long full[8], empty[8], acc_full[2], acc_empty[2], a_ready[2], w_bar;
     __shared__ uint32_t s_tmem;
     __shared__ __align__(16) float s_bias[512];
     __shared__ __align__(16) float4 s_red[LOSS ? 2 : 1][LOSS ? 4 : 1][LOSS ? kRows : 1];   // per tile parity, part, row: (max, sum exp, sum exp * z, z[action])
@@ -118,9 +118,16 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
     unsigned char* A0 = smem + ((a.w_bytes + 1023) & ~1023);
     const uint32_t Ws = smem_u32(smem), As0 = smem_u32(A0);
     const int nacc = a.N <= 256 ? 2 : 1;                               // accumulators in TMEM (columns 0.. and 256..)
+    const bool conv = !LOSS && a.a_tmem && !(a.dbg & 8);
     if (tid == 0) {
-        for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], LOSS ? kNtEpiWarps * 16 : kNtEpiWarps * 32); }   // (LOSS: one group of eight warps per accumulator)
+        // conv (HIDDEN): warps 12-15 carry the A tile from shared to tensor memory; they release the stage (128 arrivals) and tell the MMA
+        // issuer (a_ready); the epilogue is then warps 0-11
+        for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], conv ? 128 : 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], LOSS ? kNtEpiWarps * 16 : (conv ? 12 * 32 : kNtEpiWarps * 32));   // (LOSS: one group of eight warps per accumulator)
+            mbar_init(&a_ready[i], 128);
+        }
         mbar_init(&w_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -162,21 +169,17 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
             const uint32_t it = (uint32_t)(s / a.D);
             const long long t = s / n_kc;
             const int kc = (int)(s % n_kc), acc = (int)(t % nacc);
-            warp_wait(&full[b], it & 1u, lane);
+            if (conv) warp_wait(&a_ready[acc], (uint32_t)(t / nacc) & 1u, lane);     // the A tile is in tensor memory
+            else warp_wait(&full[b], it & 1u, lane);
             if (kc == 0) warp_wait(&acc_empty[acc], ((uint32_t)(t / nacc) & 1u) ^ 1u, lane);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             if (lane == 0 && !(a.dbg & 1)) {
                 const uint32_t Ab = As0 + (uint32_t)b * stage_bytes, D0 = tmem + (uint32_t)(acc * 256);
-                if (a.a_tmem && !(a.dbg & 8)) {
-                    // A through tensor memory: one tcgen05.cp per 16-byte chunk column (128 rows x 128 bits -> 4 TMEM columns, the layout
-                    // K4 builds with tcgen05.st), then TS MMAs -- an SS MMA on two no-swizzle operands costs ~450 cycles per K16 step,
-                    // a TS MMA 64 (K4).  cp and mma of one thread execute in issue order: no barrier between them, and the copy of
-                    // tile t + 2 cannot overtake the MMAs of tile t that read the same columns.
+                if (conv) {
+                    // A from tensor memory (TS MMAs: 64 cycles per K16 step against ~415 with both operands in no-swizzle shared memory).
+                    // (tcgen05.cp.128x128b as the carrier was measured too: 26 copies of 2 KB cost ~4.5 k cycles per tile and the kernel
+                    // stayed MMA-pipe bound at 159 us whatever the loads and stores did; the converter warps below do it in ~1 k.)
                     const uint32_t At = D0 + 128u;
-                    for (int c = 0; c < a.KC / 8; ++c) {
-                        const uint64_t sd = make_smem_desc_kmajor(Ab + (uint32_t)(c * kChunk), kChunk, 128);
-                        asm volatile("tcgen05.cp.cta_group::1.128x128b [%0], %1;\n" :: "r"(At + (uint32_t)(4 * c)), "l"(sd) : "memory");
-                    }
                     for (int ks = 0; ks < a.KC / 16; ++ks) {
                         const uint64_t db = make_smem_desc_kmajor(Ws + (uint32_t)(ks * 2 * a.w_rows * 16), (uint32_t)(a.w_rows * 16), 128);
                         mma_bf16_ts(D0, At + (uint32_t)(ks * 8), db, idesc_bf16(128, a.N, 0, 0), ks > 0 ? 1u : 0u);
@@ -200,10 +203,27 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
                 }
             }
             if (lane == 0) {
-                umma_commit(&empty[b]);                                // the stage buffer may be refilled
+                if (!conv) umma_commit(&empty[b]);                     // the stage buffer may be refilled
                 if (kc == n_kc - 1) umma_commit(&acc_full[acc]);       // the tile's accumulator is complete
             }
             __syncwarp();
+        }
+    } else if (conv && warp >= 12) {
+        // ================= converters (HIDDEN): thread = row; its 26 chunks of the staged A tile -> registers -> tensor memory =================
+        const int q = warp & 3, r = q * 32 + lane;
+        for (long long t = 0; t < my_tiles; ++t) {
+            const int b = (int)(t % a.D), acc = (int)(t % nacc);
+            warp_wait(&full[b], (uint32_t)(t / a.D) & 1u, lane);
+            if (t >= nacc) warp_wait(&acc_full[acc], (uint32_t)((t - nacc) / nacc) & 1u, lane);   // the MMAs that read these TMEM columns two tiles ago are done
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint4* src = reinterpret_cast<const uint4*>(A0 + (size_t)b * stage_bytes) + r;
+            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + 128);
+#pragma unroll 2
+            for (int c = 0; c < a.KC / 8; ++c) tmem_st4(trow + (uint32_t)(4 * c), src[c * (kChunk / 16)]);
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            mbar_arrive(&empty[b]);                                    // the stage buffer may be refilled
+            mbar_arrive(&a_ready[acc]);
         }
     } else if (warp < kNtEpiWarps) {
         // ================= epilogue: thread = row (TMEM lane), the four warps of a lane quarter split the column blocks =================
@@ -382,7 +402,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
             }
             warp_wait_relaxed(&acc_full[acc], (uint32_t)(t / nacc) & 1u, lane);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            for (int blk = part; blk < nblk; blk += kNtParts) {
+            for (int blk = part; blk < nblk; blk += (conv ? 3 : kNtParts)) {
                 const int c0 = 32 * blk, w = a.N - c0 < 32 ? a.N - c0 : 32;
                 uint32_t av[32];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + c0);
