@@ -104,8 +104,9 @@ struct NtArgs {
 
 constexpr int kNtEpiWarps = 16, kNtParts = kNtEpiWarps / 4;               // warps 0-15 epilogue (four per TMEM lane quarter), 16 producer, 17 MMA issuer
 constexpr int kNtThreads = 32 * (kNtEpiWarps + 2);
+constexpr int kNtThreadsLoss = 32 * (kNtEpiWarps + 2 + 4);                  // + warps 18-21: converters (all sixteen epilogue warps are busy with the loss)
 template <bool LOSS>
-__global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs a) {
+__global__ void __launch_bounds__(LOSS ? kNtThreadsLoss : kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ unsigned long long full[8], empty[8], acc_full[2], acc_empty[2], a_ready[2], w_bar;
     __shared__ uint32_t s_tmem;
@@ -118,7 +119,9 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
     unsigned char* A0 = smem + ((a.w_bytes + 1023) & ~1023);
     const uint32_t Ws = smem_u32(smem), As0 = smem_u32(A0);
     const int nacc = a.N <= 256 ? 2 : 1;                               // accumulators in TMEM (columns 0.. and 256..)
-    const bool conv = !LOSS && a.a_tmem && !(a.dbg & 8);
+    const bool conv = a.a_tmem && !(a.dbg & 8);
+    const int conv_warp0 = LOSS ? kNtEpiWarps + 2 : 12;                // the four converter warps (one per TMEM lane quarter)
+    const uint32_t a_col = LOSS ? 160u : 128u;                         // the A image's columns inside an accumulator's half of tensor memory (N <= 144)
     if (tid == 0) {
         // conv (HIDDEN): warps 12-15 carry the A tile from shared to tensor memory; they release the stage (128 arrivals) and tell the MMA
         // issuer (a_ready); the epilogue is then warps 0-11
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
                     // A from tensor memory (TS MMAs: 64 cycles per K16 step against ~415 with both operands in no-swizzle shared memory).
                     // (tcgen05.cp.128x128b as the carrier was measured too: 26 copies of 2 KB cost ~4.5 k cycles per tile and the kernel
                     // stayed MMA-pipe bound at 159 us whatever the loads and stores did; the converter warps below do it in ~1 k.)
-                    const uint32_t At = D0 + 128u;
+                    const uint32_t At = D0 + a_col;
                     for (int ks = 0; ks < a.KC / 16; ++ks) {
                         const uint64_t db = make_smem_desc_kmajor(Ws + (uint32_t)(ks * 2 * a.w_rows * 16), (uint32_t)(a.w_rows * 16), 128);
                         mma_bf16_ts(D0, At + (uint32_t)(ks * 8), db, idesc_bf16(128, a.N, 0, 0), ks > 0 ? 1u : 0u);
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
             }
             __syncwarp();
         }
-    } else if (conv && warp >= 12) {
+    } else if (conv && warp >= conv_warp0 && warp < conv_warp0 + 4) {
         // ================= converters (HIDDEN): thread = row; its 26 chunks of the staged A tile -> registers -> tensor memory =================
         const int q = warp & 3, r = q * 32 + lane;
         for (long long t = 0; t < my_tiles; ++t) {
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(kNtThreads, 1) ppo_gemm_nt_kernel(const NtArgs
             if (t >= nacc) warp_wait(&acc_full[acc], (uint32_t)((t - nacc) / nacc) & 1u, lane);   // the MMAs that read these TMEM columns two tiles ago are done
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint4* src = reinterpret_cast<const uint4*>(A0 + (size_t)b * stage_bytes) + r;
-            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + 128);
+            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256) + a_col;
 #pragma unroll 2
             for (int c = 0; c < a.KC / 8; ++c) tmem_st4(trow + (uint32_t)(4 * c), src[c * (kChunk / 16)]);
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
@@ -682,7 +685,7 @@ extern "C" int bg_ppo_logits_loss_a(const uint16_t* h, long long n_a, long long 
         return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_logits_loss_a: null pointer");
     NtArgs a{};
     a.A = h; a.tile_begin = 0; a.tile_end = (n_a + kRows - 1) / kRows; a.W = wap_a; a.bias = bias_a; a.out = dlogits_a; a.dbg = g_ppo_gemm_dbg;
-    a.nc_a = 16; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 3; a.nc_out = 18; a.D = 5;
+    a.nc_a = 16; a.N = 144; a.K = 128; a.KC = 128; a.w_rows = 144; a.b_mn = 0; a.epi = 3; a.nc_out = 18; a.D = 5; a.a_tmem = 1;
     a.counts = counts; a.actions = actions; a.old_logp = old_log_probs; a.adv = advantages; a.returns = returns; a.n_rows = n_a;
     a.eps_clip = eps_clip; a.value_coef = value_coef; a.entropy_coef = entropy_coef; a.inv_b = 1.0f / (float)B_norm;
     a.dbias = dbias; a.sums = sums;
@@ -692,7 +695,7 @@ extern "C" int bg_ppo_logits_loss_a(const uint16_t* h, long long n_a, long long 
     if (e != cudaSuccess) return bg_set_error(e, "bg_ppo_logits_loss_a: cudaFuncSetAttribute");
     long long grid = (long long)bg_sm_count();
     if (grid > a.tile_end) grid = a.tile_end;
-    ppo_gemm_nt_kernel<true><<<(unsigned)grid, kNtThreads, smem, (cudaStream_t)stream>>>(a);
+    ppo_gemm_nt_kernel<true><<<(unsigned)grid, kNtThreadsLoss, smem, (cudaStream_t)stream>>>(a);
     return bg_set_error(cudaGetLastError(), "bg_ppo_logits_loss_a: launch");
 }
 

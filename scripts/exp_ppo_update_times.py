@@ -8,6 +8,9 @@ games = int(os.environ.get("GAMES", 65536))
 env = bg_b200.B200BackgammonVecEnv(num_envs=games, device=dev, seed=1, check_every=0); env.reset()
 net = bg_b200.PolicyValueNet.random_init(dev, seed=0)
 tr = PPOTrainer(env, net, PPOConfig(t_horizon=64), seed=0)
+if os.environ.get("BG_PPO_DBG"):                     # experiment switches of the GEMM kernels (results are garbage, timings are not)
+    from bg_b200._lib import lib
+    lib().bg_ppo_gemm_debug(int(os.environ["BG_PPO_DBG"]))
 ev = lambda: torch.cuda.Event(enable_timing=True)
 for u in range(6):
     a, b, c = ev(), ev(), ev()
