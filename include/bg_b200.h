@@ -300,6 +300,11 @@ int bg_ppo_pack_weights(const float* flat_params, uint16_t* w1p, uint16_t* wap_a
                         void* stream);
 int bg_ppo_gather_block(const uint16_t* x_rowmajor, long long ld_src, const int32_t* perm, long long rows_pad, int ncols,
                         int set_one_col /* -1: none */, uint16_t* x_blocked, void* stream);
+/* The same result without the row-major features: x_blocked = tile-blocked bf16 features (208 columns, reference feature order,
+ * zero padding, column set_one_col = 1.0 if >= 0) of boards52[perm[p]] with the turn flag of flags[perm[p]], zero rows where
+ * perm[p] < 0 -- K3 and the gather in one pass (what PPOTrainer's update uses: the rollout stores boards, not features). */
+int bg_ppo_encode_block(const int8_t* boards52, const int8_t* flags, const int32_t* perm, long long rows_pad, int set_one_col,
+                        uint16_t* x_blocked, void* stream);
 int bg_ppo_gemm_nt(int op, const uint16_t* A, long long tile_begin, long long tile_end, const uint16_t* W, const float* bias,
                    const uint16_t* h_mask, uint16_t* out, void* stream);
 int bg_ppo_gemm_tn(int op, const uint16_t* A, const uint16_t* B, long long tile_begin, long long tile_end, float* flat_grad,

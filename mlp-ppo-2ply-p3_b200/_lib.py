@@ -42,6 +42,7 @@ SIGNATURES = {
     "bg_movegen_count": (_I, [_V, _V, _V, _LL, _V, _V, _V, _SZ, _V]),
     "bg_movegen_write": (_I, [_V, _V, _V, _LL, _V, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _SZ, _V]),
     "bg_movegen_slab": (_I, [_V, _V, _V, _LL, _I, _V, _LL, _V, _V, _V, _V, _V, _V, _V, _V, _SZ, _V]),
+    "bg_ppo_encode_block": (_I, [_V, _V, _V, _LL, _I, _V, _V]),
     "bg_record_state": (_I, [_V, _V, _V, _V, _V]),
     "bg_set_team_threads": (_I, [_I, _I]),
     "bg_encode_f32": (_I, [_V, _V, _I, _LL, _V, _V, _LL, _V]),

@@ -28,6 +28,7 @@
 // issuer (both operands from shared memory, accumulators in TMEM, two of them when N <= 256), eight epilogue warps.
 #include <cuda_bf16.h>
 #include "bg_device.cuh"
+#include "bg_features.cuh"
 #include "bg_tcgen05.cuh"
 #include "bg_internal.h"
 
@@ -570,6 +571,46 @@ __global__ void __launch_bounds__(256) gather_block_kernel(const uint16_t* __res
     *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(dst) + ((size_t)(p >> 7) * nch + c8) * kChunk + (size_t)(p & 127) * 16) = v;
 }
 
+// K3 + the gather in one pass: the bf16 feature rows of boards52[perm[p]] (reference feature order, turn flag = flags[perm[p]]), written
+// straight into the tile-blocked layout with the bias column set -- no row-major feature tensor in between (it was written by K3, read
+// by the gather and never used again: 2 x 436 B per sample of traffic and 1.7 GB per 4 M samples).  One thread per row: its 26 chunks
+// go to 26 chunk columns, so a warp writes 512 contiguous bytes per chunk.
+__global__ void __launch_bounds__(128) encode_block_kernel(const int8_t* __restrict__ boards, const int8_t* __restrict__ flags,
+                                                           const int32_t* __restrict__ perm, long long rows_pad, int set_one_col,
+                                                           uint16_t* __restrict__ dst) {
+    __shared__ uint2 lut[16];
+    load_units_lut(lut);
+    __syncthreads();
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= rows_pad) return;
+    const int g = perm[p];
+    uint32_t w[kBoardWords];
+#pragma unroll
+    for (int i = 0; i < kBoardWords; ++i) w[i] = 0u;
+    int flag = 0;
+    if (g >= 0) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(boards + (long long)g * kBoardBytes);
+#pragma unroll
+        for (int i = 0; i < kBoardWords; ++i) w[i] = __ldg(src + i);
+        flag = flags[g] & 1;
+    }
+    unsigned char* out = reinterpret_cast<unsigned char*>(dst) + (size_t)(p >> 7) * 26 * kChunk + (size_t)(p & 127) * 16;
+    const int8_t* b = reinterpret_cast<const int8_t*>(w);
+#pragma unroll
+    for (int k = 0; k < 26; ++k) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (g >= 0) {
+            v = feature_chunk_lut(b, flag, k, lut);
+            if (set_one_col >= 0 && (set_one_col >> 3) == k) {             // the bias column: 1.0 in bf16
+                uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
+                const int e = set_one_col & 7;
+                vw[e >> 1] = (e & 1) ? ((vw[e >> 1] & 0x0000FFFFu) | 0x3F800000u) : ((vw[e >> 1] & 0xFFFF0000u) | 0x00003F80u);
+            }
+        }
+        *reinterpret_cast<uint4*>(out + (size_t)k * kChunk) = v;
+    }
+}
+
 // dW1p^T [199][128] (scratch of GRAD_W1: with lane = hidden unit the atomics of the accumulator tile are only coalesced in this
 // orientation; fc1.weight is [hidden][feature], where they hit a different sector each: 115 us per launch) -> fc1.weight, fc1.bias
 __global__ void grad_w1_finish_kernel(const float* __restrict__ scratch, float* __restrict__ grad) {
@@ -641,6 +682,15 @@ extern "C" int bg_ppo_gather_block(const uint16_t* x_rowmajor, long long ld_src,
     const long long n = rows_pad * (ncols >> 3);
     gather_block_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x_rowmajor, ld_src, perm, rows_pad, ncols >> 3, set_one_col, x_blocked);
     return bg_set_error(cudaGetLastError(), "bg_ppo_gather_block: launch");
+}
+
+extern "C" int bg_ppo_encode_block(const int8_t* boards52, const int8_t* flags, const int32_t* perm, long long rows_pad, int set_one_col,
+                                   uint16_t* x_blocked, void* stream) {
+    if (rows_pad < 0 || (rows_pad & 127) || set_one_col >= 208) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_encode_block: rows_pad must be a multiple of 128");
+    if (rows_pad == 0) return BG_OK;
+    if (!boards52 || !flags || !perm || !x_blocked) return bg_set_error_msg(BG_ERR_INVALID, "bg_ppo_encode_block: null pointer");
+    encode_block_kernel<<<(unsigned)((rows_pad + 127) / 128), 128, 0, (cudaStream_t)stream>>>(boards52, flags, perm, rows_pad, set_one_col, x_blocked);
+    return bg_set_error(cudaGetLastError(), "bg_ppo_encode_block: launch");
 }
 
 extern "C" int bg_ppo_gemm_nt(int op, const uint16_t* A, long long tile_begin, long long tile_end, const uint16_t* W,

@@ -272,10 +272,10 @@ class TensorCoreUpdate:
     def from_blocked(b, R, C):
         return b.view(R // 128, C // 8, 128, 8).permute(0, 2, 1, 3).reshape(R, C)
 
-    def prepare(self, x, counts, actions, old_logp, adv, returns):
+    def prepare(self, x, counts, actions, old_logp, adv, returns, boards=None):
         """Once per rollout: sort the samples by class (class A first, by legal count; original order inside class B), pad each class to whole
         tiles, gather the per-sample vectors and build the blocked x (with the bias column).  One host read (the class sizes)."""
-        B = x.shape[0]
+        B = counts.shape[0]                              # (boards = (boards52 (B,52) int8, movers (B,) int8): x may be None, see below)
         dev = self.device
         self._p = None
         a = self.class_a(counts, actions)
@@ -328,10 +328,16 @@ class TensorCoreUpdate:
             self.dla[(TA - 1) * 128 * 144:TA * 128 * 144].zero_()
         if TB:
             self.dlb[(TB - 1) * 128 * 512:TB * 128 * 512].zero_()
-        x = x.contiguous()
         with torch.cuda.device(dev):
-            check(lib().bg_ppo_gather_block(x.data_ptr(), x.shape[1], perm.data_ptr(), rows, 208, self.ONE_COL, self.xb.data_ptr(), _stream()),
-                  "bg_ppo_gather_block")
+            if boards is not None:
+                # K3 and the gather in one pass: features straight from the stored boards into the blocked layout (no row-major x)
+                b52, movers = boards
+                check(lib().bg_ppo_encode_block(b52.data_ptr(), movers.data_ptr(), perm.data_ptr(), rows, self.ONE_COL, self.xb.data_ptr(),
+                                                _stream()), "bg_ppo_encode_block")
+            else:
+                x = x.contiguous()
+                check(lib().bg_ppo_gather_block(x.data_ptr(), x.shape[1], perm.data_ptr(), rows, 208, self.ONE_COL, self.xb.data_ptr(), _stream()),
+                      "bg_ppo_gather_block")
         self._p = p
         return p
 
@@ -480,29 +486,44 @@ class PPOLearner:
         var = (s[1] - n * mean * mean) / torch.clamp(n - 1, min=1.0)
         return mean.float(), var.clamp(min=0).sqrt().float()
 
-    def update(self, x, counts, actions, old_logp, old_values, returns):
+    def tensor_core_path(self) -> bool:
+        """True if update() will run the hand-written tcgen05 update (then it can take the stored boards instead of features)"""
+        c = self.cfg
+        return bool(c.manual_backward and c.autocast and c.update_impl == "tcgen05" and max(1, int(c.num_minibatches)) == 1
+                    and torch.device(self.device).type == "cuda")
+
+    def update(self, x, counts, actions, old_logp, old_values, returns, boards=None):
         """x (B,198+) features, the rest (B,).  Normalises the returns, advantages = returns - V_old (ppo_agent.py:256-259),
-        then num_epochs passes over the batch (full batch, or num_minibatches slices)."""
+        then num_epochs passes over the batch (full batch, or num_minibatches slices).
+        boards = (boards52 (B,52) int8, movers (B,) int8) with x = None: only on the tensor-core path (tensor_core_path()), which
+        then encodes the features straight into its blocked operand layout."""
         c = self.cfg
         mean, std = self._global_mean_std(returns)
         returns = (returns - mean) / (std + 1e-5)
         adv = returns - old_values
-        B = x.shape[0]
+        B = counts.shape[0]
         mb = max(1, int(c.num_minibatches))
-        stats = torch.zeros(4, device=x.device)
-        manual = (c.manual_backward and c.autocast and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2
-                  and x.shape[1] == 208 and x.is_contiguous())
+        stats = torch.zeros(4, device=counts.device)
+        if x is None:
+            if boards is None or not self.tensor_core_path():
+                raise BgError("PPOLearner.update: x = None needs boards and the tensor-core update path")
+            manual = True
+        else:
+            boards = None
+            manual = (c.manual_backward and c.autocast and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2
+                      and x.shape[1] == 208 and x.is_contiguous())
         tc = manual and c.update_impl == "tcgen05" and mb == 1
         if manual:
             if self._manual is None or isinstance(self._manual, TensorCoreUpdate) != tc:
                 self._manual = (TensorCoreUpdate(self.device, fuse_loss=os.environ.get("BG_PPO_FUSE_LOSS", "1") != "0") if tc
                                 else ManualUpdate(self.device))
-            x[:, ManualUpdate.ONE_COL] = 1.0                  # spare (zero) column of K3's rows: carries fc1.bias through the GEMMs
+            if x is not None:
+                x[:, ManualUpdate.ONE_COL] = 1.0              # spare (zero) column of K3's rows: carries fc1.bias through the GEMMs
             counts, actions = counts.to(torch.int32).contiguous(), actions.to(torch.int32).contiguous()
             old_logp, returns, adv = old_logp.float().contiguous(), returns.float().contiguous(), adv.float().contiguous()
             grads = {k: p.grad for k, p in self.fp.params.items()}
             if tc:
-                self._manual.prepare(x, counts, actions, old_logp, adv, returns)   # class sort + blocked x, once for all epochs
+                self._manual.prepare(x, counts, actions, old_logp, adv, returns, boards=boards)   # class sort + blocked x, once for all epochs
             else:
                 self._manual.invalidate()
         for _ in range(c.num_epochs):
@@ -600,6 +621,11 @@ class PPOTrainer:
     def update(self, returns):
         buf = self.buf
         B = buf.T * buf.N
+        if self.learner.tensor_core_path():               # the update encodes the features itself, straight into its operand layout
+            stats = self.learner.update(None, buf.counts.view(B), buf.actions.view(B), buf.logp.view(B), buf.values.view(B), returns.reshape(B),
+                                        boards=(buf.boards.view(B, 52), buf.players.view(B)))
+            self.net.sync()
+            return stats
         dt = torch.bfloat16 if self.cfg.autocast else torch.float32
         xb = getattr(self, "_x", None)                    # persistent: a fresh 1.7 GB tensor per update made the caching allocator split and
         if xb is None or xb.dtype != dt or xb.shape[0] != B:   # re-grow its largest block every few updates (20-100 ms cudaMalloc hiccups)

@@ -209,3 +209,28 @@ def test_update_paths_agree():
     for key in ("policy_loss", "value_loss", "entropy", "total_loss"):
         for o in outs[1:]:
             assert abs(outs[0][1][key] - o[1][key]) < 5e-3, (key, outs[0][1], o[1])
+
+
+def test_encode_block_equals_encode_then_gather():
+    """bg_ppo_encode_block (features of boards52[perm] straight into the blocked layout) == K3's bf16 encoder followed by bg_ppo_gather_block,
+    bit for bit, padding rows and bias column included"""
+    import bg_b200
+    from bg_b200._lib import lib, check
+    from bg_b200.engine import encode
+    env = bg_b200.B200BackgammonVecEnv(num_envs=700, device=DEV, seed=11, check_every=0)
+    env.reset()
+    for t in range(40):
+        env.step_device(env.random_actions(5, t))
+    rows = 768
+    g = torch.Generator(device="cpu").manual_seed(3)
+    perm = torch.full((rows,), -1, dtype=torch.int32)
+    perm[:700] = torch.randperm(700, generator=g).to(torch.int32)
+    perm = perm.to(DEV)
+    x = encode(env.boards52, env.players, dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+    a = torch.full((rows * 208,), 7.0, dtype=torch.bfloat16, device=DEV)
+    b = torch.full((rows * 208,), 9.0, dtype=torch.bfloat16, device=DEV)
+    check(lib().bg_ppo_gather_block(x.data_ptr(), x.shape[1], perm.data_ptr(), rows, 208, 198, a.data_ptr(), st), "gather")
+    check(lib().bg_ppo_encode_block(env.boards52.data_ptr(), env.players.data_ptr(), perm.data_ptr(), rows, 198, b.data_ptr(), st), "encode_block")
+    torch.cuda.synchronize()
+    assert torch.equal(a.view(torch.int16), b.view(torch.int16))
