@@ -571,6 +571,29 @@ __global__ void __launch_bounds__(256) gather_block_kernel(const uint16_t* __res
     *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(dst) + ((size_t)(p >> 7) * nch + c8) * kChunk + (size_t)(p & 127) * 16) = v;
 }
 
+// chunk k (features 8k .. 8k+7, reference order) of the bf16 feature row of a board held as 13 words in registers: feature_chunk_lut
+// (bg_features.cuh) with the byte loads spelled as shifts of compile-time-indexed words, so that the board never goes to local memory
+__device__ __forceinline__ uint4 feature_chunk_words(const uint32_t (&w)[kBoardWords], int flag, int k, const uint2* lut) {
+    auto cnt = [&](int byte) -> uint32_t { return (w[byte >> 2] >> (8 * (byte & 3))) & 15u; };
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (k < 12) {                                    // PLAYER1 points 2k, 2k+1
+        const uint2 a = lut[cnt(2 * k)], c = lut[cnt(2 * k + 1)];
+        o = make_uint4(a.x, a.y, c.x, c.y);
+    } else if (k == 12) {                            // bar1/2, off1/15, P2 point 0, first half of P2 point 1
+        const uint2 a = lut[cnt(24)], c = lut[cnt(25)];
+        o = make_uint4(bar_off_pair_bf16((int)cnt(48), (int)cnt(50)), a.x, a.y, c.x);
+    } else if (k < 24) {                             // second half of P2 point q, P2 point q+1, first half of q+2
+        const int q = 2 * (k - 12) - 1;
+        const uint2 a = lut[cnt(24 + q)], c = lut[cnt(25 + q)], e = lut[cnt(26 + q)];
+        o = make_uint4(a.y, c.x, c.y, e.x);
+    } else if (k == 24) {                            // second half of P2 point 23, bar2/2, off2/15, flags, pad
+        o.x = lut[cnt(47)].y;
+        o.y = bar_off_pair_bf16((int)cnt(49), (int)cnt(51));
+        o.z = flag == 0 ? 0x00003F80u : 0x3F800000u;
+    }
+    return o;
+}
+
 // K3 + the gather in one pass: the bf16 feature rows of boards52[perm[p]] (reference feature order, turn flag = flags[perm[p]]), written
 // straight into the tile-blocked layout with the bias column set -- no row-major feature tensor in between (it was written by K3, read
 // by the gather and never used again: 2 x 436 B per sample of traffic and 1.7 GB per 4 M samples).  One thread per row: its 26 chunks
@@ -595,16 +618,18 @@ __global__ void __launch_bounds__(128) encode_block_kernel(const int8_t* __restr
         flag = flags[g] & 1;
     }
     unsigned char* out = reinterpret_cast<unsigned char*>(dst) + (size_t)(p >> 7) * 26 * kChunk + (size_t)(p & 127) * 16;
-    const int8_t* b = reinterpret_cast<const int8_t*>(w);
 #pragma unroll
     for (int k = 0; k < 26; ++k) {
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (g >= 0) {
-            v = feature_chunk_lut(b, flag, k, lut);
-            if (set_one_col >= 0 && (set_one_col >> 3) == k) {             // the bias column: 1.0 in bf16
-                uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
+            v = feature_chunk_words(w, flag, k, lut);
+            if (set_one_col >= 0 && (set_one_col >> 3) == k) {             // the bias column: 1.0 in bf16 (no indexing into v: it stays in registers)
                 const int e = set_one_col & 7;
-                vw[e >> 1] = (e & 1) ? ((vw[e >> 1] & 0x0000FFFFu) | 0x3F800000u) : ((vw[e >> 1] & 0xFFFF0000u) | 0x00003F80u);
+                const uint32_t keep = (e & 1) ? 0x0000FFFFu : 0xFFFF0000u, one = (e & 1) ? 0x3F800000u : 0x00003F80u;
+                if ((e >> 1) == 0) v.x = (v.x & keep) | one;
+                else if ((e >> 1) == 1) v.y = (v.y & keep) | one;
+                else if ((e >> 1) == 2) v.z = (v.z & keep) | one;
+                else v.w = (v.w & keep) | one;
             }
         }
         *reinterpret_cast<uint4*>(out + (size_t)k * kChunk) = v;
