@@ -79,4 +79,20 @@ __device__ __forceinline__ void build_row(const uint4& k, int player, const RowC
                           : (pb | (ob << 8) | (c.opp_off0 << 16) | (oo << 24));
 }
 
+// The same row written straight to global memory by its own lane (13 word stores; no staging, no dynamic register indexing)
+__device__ __forceinline__ void store_row_direct(const uint4& k, int player, const RowContext& c, const uint32_t* rootw, uint32_t* __restrict__ dst) {
+    uint32_t own[6], opp[6];
+    own[0] = spread_nibbles(k.x); own[1] = spread_nibbles(k.x >> 16);
+    own[2] = spread_nibbles(k.y); own[3] = spread_nibbles(k.y >> 16);
+    own[4] = spread_nibbles(k.z); own[5] = spread_nibbles(k.z >> 16);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) opp[q] = rootw[c.opp0 + q] - spread_bits(k.w >> (4 * q));
+    const uint32_t ob = (k.w >> 24) & 15u, oo = k.w >> 28;
+    const uint32_t pb = c.opp_bar0 + (uint32_t)__popc(k.w & 0xFFFFFFu);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { dst[q] = player ? opp[q] : own[q]; dst[6 + q] = player ? own[q] : opp[q]; }
+    dst[12] = player == 0 ? (ob | (pb << 8) | (oo << 16) | (c.opp_off0 << 24))
+                          : (pb | (ob << 8) | (c.opp_off0 << 16) | (oo << 24));
+}
+
 }  // namespace bg

@@ -128,6 +128,25 @@ __global__ void __launch_bounds__(256, 4) movegen_kernel(
                 uint32_t* stage = reinterpret_cast<uint32_t*>(&S.key[obase < CAP ? CAP : 0]);
                 uint32_t* gout = nullptr;
                 const RowContext rc = make_row_context(player, S.rootw);
+#ifndef BG_K1_STAGED_OUTPUT
+                if (!FEATS) {
+                    // every lane writes its own row straight to global memory (13 word stores at a 52-byte stride: L2 merges the sectors;
+                    // K1 is issue bound, not memory bound, and the staged copy cost more instructions than these stores cost transactions)
+                    if (mode == 2) {
+                        start = (long long)__shfl_sync(kFull, s0, 0);
+                        if (lane == 0 && starts) starts[g] = start;
+                    }
+                    if (start + nw > after_cap_rows) {
+                        if (lane == 0) { atomicOr(status, BG_STATUS_OUTPUT_OVERFLOW); if (counts) counts[g] = 0; }
+                    } else {
+                        gout = reinterpret_cast<uint32_t*>(after) + start * kBoardWords;
+                        for (int r = lane; r < nw; r += 32) {
+                            store_row_direct(S.key[obase + r], player, rc, S.rootw, gout + (long long)r * kBoardWords);
+                            if (row_players) row_players[start + r] = (int8_t)player;
+                        }
+                    }
+                } else
+#endif
                 for (int r0 = 0; r0 < nw; r0 += 32) {
                     int r = r0 + lane;
                     if (r < nw) {
