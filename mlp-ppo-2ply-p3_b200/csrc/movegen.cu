@@ -112,8 +112,8 @@ __global__ void __launch_bounds__(256, 4) movegen_kernel(
             continue;
         }
         const int nw = (max_rows > 0 && n > max_rows) ? max_rows : n;     // rows written (env truncation)
-        // slab mode: the allocation (an atomic on one address, ~1 us) is issued here and read only after the first rows have
-        // been staged
+        // slab mode: the allocation (an atomic on one address, ~1 us) is issued here, before the counts are written, and read where the
+        // rows are stored (FEATS: after the first rows have been staged)
         long long start = 0;
         unsigned long long s0 = 0;
         if (mode == 1) start = offsets[g];
